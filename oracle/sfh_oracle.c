@@ -1,0 +1,272 @@
+/*
+ * sfh_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C restatement of the fitting hot path of cgarling/StarFormationHistories.jl
+ * (v1.3.1): composite! -> loglikelihood -> grad-loglikelihood! (fused as fg!), the MZR/AMR
+ * chain rules and the per-walker MCMC model.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the product
+ * (libsfhcuda.so) never links, loads or falls back to it.
+ *
+ * PARITY PINNING.  The reference is Julia and cannot run in this image (no julia binary,
+ * no network), so there is no oracle/_ref build.  This oracle is pinned against every
+ * golden value of the reference's own tests that is reproducible without Julia's RNG
+ * streams: test/fitting/fitting_core_test.jl:14-28,37-67,77-123,132-159,168-192 and the
+ * doctests of dispersion_models.jl:63-68 and mzr.jl:245-250 (tests/test_oracle_golden.py).
+ * The StableRNG-seeded goldens of mzr_test.jl:74-76 / amr_test.jl:45-47,264-265 are NOT
+ * reproducible here; for those rows the chain rules are pinned instead by complex-step
+ * differentiation of an independent numpy forward model and by the __float128 build of
+ * this same file  ==> hierarchical-gradient golden VALUES: "parity unpinned" (properties only).
+ *
+ * Three precisions are instantiated from oracle_impl.inc:
+ *   _f32  Julia Float32 semantics (everything, accumulators included, in float)
+ *   _f64  Julia Float64 semantics
+ *   _f128 __float128 arbiter (libquadmath) against which both GPU and _f64 are judged
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <math.h>
+#include <float.h>
+#include <quadmath.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---------------- float ---------------- */
+#define REAL float
+#define FN(name) sfho_##name##_f32
+#define R_EPS FLT_EPSILON
+#define R_LOG logf
+#define R_LOG10 log10f
+#define R_EXP expf
+#define R_EXP10(x) powf(10.0f, (x))
+#define R_INF INFINITY
+#define R_NAN NAN
+#include "oracle_impl.inc"
+#undef REAL
+#undef FN
+#undef R_EPS
+#undef R_LOG
+#undef R_LOG10
+#undef R_EXP
+#undef R_EXP10
+#undef R_INF
+#undef R_NAN
+
+/* ---------------- double ---------------- */
+#define REAL double
+#define FN(name) sfho_##name##_f64
+#define R_EPS DBL_EPSILON
+#define R_LOG log
+#define R_LOG10 log10
+#define R_EXP exp
+#define R_EXP10(x) pow(10.0, (x))
+#define R_INF ((double)INFINITY)
+#define R_NAN ((double)NAN)
+#include "oracle_impl.inc"
+#undef REAL
+#undef FN
+#undef R_EPS
+#undef R_LOG
+#undef R_LOG10
+#undef R_EXP
+#undef R_EXP10
+#undef R_INF
+#undef R_NAN
+
+/* ---------------- __float128 arbiter ----------------
+ * eps stays eps(Float64): the arbiter evaluates the Float64 problem exactly, it does
+ * not change the clamp the reference applies (fitting_base.jl:90).                   */
+#define REAL __float128
+#define FN(name) sfho_##name##_f128
+#define R_EPS ((__float128)DBL_EPSILON)
+#define R_LOG logq
+#define R_LOG10 log10q
+#define R_EXP expq
+#define R_EXP10(x) powq(10.0Q, (x))
+#define R_INF ((__float128)INFINITY)
+#define R_NAN ((__float128)NAN)
+#include "oracle_impl.inc"
+#undef REAL
+#undef FN
+#undef R_EPS
+#undef R_LOG
+#undef R_LOG10
+#undef R_EXP
+#undef R_EXP10
+#undef R_INF
+#undef R_NAN
+
+/* ---- double-in / double-out front ends to the __float128 arbiter (ctypes has no f128) ---- */
+
+/* fg! in quad on double inputs; returns -logL rounded to double, G rounded to double.
+ * gscale (nt, nullable) receives sum_i |M_ij * (1 - n_i/m_i)| -- the backward-error scale
+ * against which gradient differences are judged near an optimum.  */
+double sfho_fg_quad(int want_G, double *G, double *gscale, const double *coeffs, const double *M,
+                    const double *data, double *C_out, int64_t nb, int64_t nt)
+{
+    __float128 *C = (__float128 *)malloc(sizeof(__float128) * (size_t)nb);
+    for (int64_t i = 0; i < nb; ++i) C[i] = 0;
+    for (int64_t k = 0; k < nt; ++k) {
+        const __float128 ck = coeffs[k];
+        const double *col = M + k * nb;
+        for (int64_t i = 0; i < nb; ++i) C[i] += (__float128)col[i] * ck;
+    }
+    __float128 logL = 0;
+    for (int64_t i = 0; i < nb; ++i) {
+        __float128 ci = C[i];
+        if (C_out) C_out[i] = (double)ci;
+        if (ci < (__float128)DBL_EPSILON) ci = (__float128)DBL_EPSILON;
+        const __float128 ni = data[i];
+        logL += (ni > 0) ? (ni - ci - ni * logq(ni / ci)) : -ci;
+        C[i] = 1 - ni / ci;
+    }
+    if (want_G) {
+        for (int64_t k = 0; k < nt; ++k) {
+            const double *col = M + k * nb;
+            __float128 acc = 0, sc = 0;
+            for (int64_t i = 0; i < nb; ++i) { const __float128 p = (__float128)col[i] * C[i]; acc += p; sc += fabsq(p); }
+            G[k] = (double)acc;
+            if (gscale) gscale[k] = (double)sc;
+        }
+    }
+    free(C);
+    return (logL != 0) ? (double)(-logL) : (double)INFINITY;
+}
+
+/* Same for Float32-STORED templates with exact (quad) arithmetic: what the GPU's
+ * "F32 storage, FP64 accumulate" mode is compared against at 1e-6 (BASELINE.json).   */
+double sfho_fg_quad_f32(int want_G, double *G, double *gscale, const double *coeffs, const float *M,
+                        const float *data, int64_t nb, int64_t nt)
+{
+    __float128 *C = (__float128 *)malloc(sizeof(__float128) * (size_t)nb);
+    for (int64_t i = 0; i < nb; ++i) C[i] = 0;
+    for (int64_t k = 0; k < nt; ++k) {
+        const __float128 ck = coeffs[k];
+        const float *col = M + k * nb;
+        for (int64_t i = 0; i < nb; ++i) C[i] += (__float128)col[i] * ck;
+    }
+    __float128 logL = 0;
+    for (int64_t i = 0; i < nb; ++i) {
+        __float128 ci = C[i];
+        if (ci < (__float128)DBL_EPSILON) ci = (__float128)DBL_EPSILON;
+        const __float128 ni = data[i];
+        logL += (ni > 0) ? (ni - ci - ni * logq(ni / ci)) : -ci;
+        C[i] = 1 - ni / ci;
+    }
+    if (want_G) {
+        for (int64_t k = 0; k < nt; ++k) {
+            const float *col = M + k * nb;
+            __float128 acc = 0, sc = 0;
+            for (int64_t i = 0; i < nb; ++i) { const __float128 p = (__float128)col[i] * C[i]; acc += p; sc += fabsq(p); }
+            G[k] = (double)acc;
+            if (gscale) gscale[k] = (double)sc;
+        }
+    }
+    free(C);
+    return (logL != 0) ? (double)(-logL) : (double)INFINITY;
+}
+
+/* hierarchical fg! in quad on double inputs */
+double sfho_fg_hier_quad(int want_G, double *G, int kind, const double *fixed, const int *free3,
+                         const double *variables, int64_t nj, const double *M, const double *data,
+                         int64_t nb, const double *logAge, const double *MH, int64_t nt, double *fullG_out)
+{
+    __float128 *qM = (__float128 *)malloc(sizeof(__float128) * (size_t)(nb * nt));
+    __float128 *qd = (__float128 *)malloc(sizeof(__float128) * (size_t)nb);
+    __float128 *qC = (__float128 *)malloc(sizeof(__float128) * (size_t)nb);
+    __float128 *qv = (__float128 *)malloc(sizeof(__float128) * (size_t)(nj + 3));
+    __float128 *qG = (__float128 *)malloc(sizeof(__float128) * (size_t)(nj + 3));
+    __float128 *qa = (__float128 *)malloc(sizeof(__float128) * (size_t)nt);
+    __float128 *qm = (__float128 *)malloc(sizeof(__float128) * (size_t)nt);
+    __float128 *qf = (__float128 *)malloc(sizeof(__float128) * (size_t)nt);
+    __float128 qfixed[4];
+    for (int i = 0; i < 4; ++i) qfixed[i] = fixed[i];
+    for (int64_t i = 0; i < nb * nt; ++i) qM[i] = M[i];
+    for (int64_t i = 0; i < nb; ++i) qd[i] = data[i];
+    for (int64_t i = 0; i < nj + 3; ++i) qv[i] = variables[i];
+    for (int64_t i = 0; i < nt; ++i) { qa[i] = logAge[i]; qm[i] = MH[i]; }
+    const __float128 r = sfho_fg_hier_f128(want_G, qG, kind, qfixed, free3, qv, nj, qM, qd, qC, nb, qa, qm, nt, qf);
+    if (want_G) {
+        for (int64_t i = 0; i < nj + 3; ++i) G[i] = (double)qG[i];
+        if (fullG_out) for (int64_t i = 0; i < nt; ++i) fullG_out[i] = (double)qf[i];
+    }
+    free(qM); free(qd); free(qC); free(qv); free(qG); free(qa); free(qm); free(qf);
+    return (double)r;
+}
+
+/* ---- MCMCModel callable (src/fitting/mcmc_sample.jl:12-23) over W walkers.
+ *      X is nt x W column-major.  Any negative coefficient -> typemin(T) = -Inf, tested
+ *      before any arithmetic (:15-19).                                               */
+void sfho_mcmc_logl_f64(const double *X, int64_t W, const double *M, const double *data,
+                        int64_t nb, int64_t nt, double *out)
+{
+#pragma omp parallel
+    {
+        double *C = (double *)malloc(sizeof(double) * (size_t)nb);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t w = 0; w < W; ++w) {
+            const double *x = X + w * nt;
+            int neg = 0;
+            for (int64_t k = 0; k < nt; ++k) if (x[k] < 0.0) { neg = 1; break; }
+            if (neg) { out[w] = -(double)INFINITY; continue; }
+            sfho_composite_f64(C, x, M, nb, nt);
+            out[w] = sfho_loglikelihood_f64(C, data, nb);
+        }
+        free(C);
+    }
+}
+
+/* ---- threaded two-pass fg! : the CPU BASELINE bench.py times beside the GPU.
+ *      Same algorithm and pass structure as the reference's flat path (gemv 'N',
+ *      Poisson loop, residual loop, gemv 'T'; the stack is read twice), parallelised
+ *      the way a threaded BLAS would: row blocks for 'N', column blocks for 'T'.     */
+#define DEFINE_FG_OMP(REAL, SUF, EPS, LOGF)                                                        \
+double sfho_fg_omp_##SUF(REAL *G, const REAL *coeffs, const REAL *M, const REAL *data, REAL *C,     \
+                         int64_t nb, int64_t nt)                                                   \
+{                                                                                                  \
+    const int64_t RB = 2048;                                                                       \
+    const int64_t nblk = (nb + RB - 1) / RB;                                                       \
+    double logL = 0.0;                                                                             \
+    _Pragma("omp parallel for schedule(static) reduction(+:logL)")                                 \
+    for (int64_t b = 0; b < nblk; ++b) {                                                           \
+        const int64_t i0 = b * RB, i1 = (i0 + RB < nb) ? i0 + RB : nb;                             \
+        for (int64_t i = i0; i < i1; ++i) C[i] = (REAL)0;                                          \
+        for (int64_t k = 0; k < nt; ++k) {                                                         \
+            const REAL ck = coeffs[k]; const REAL *col = M + k * nb;                               \
+            _Pragma("omp simd")                                                                    \
+            for (int64_t i = i0; i < i1; ++i) C[i] = col[i] * ck + C[i];                           \
+        }                                                                                          \
+        REAL part = (REAL)0;                                                                       \
+        for (int64_t i = i0; i < i1; ++i) {                                                        \
+            REAL ci = C[i]; if (ci < EPS) ci = EPS;                                                \
+            const REAL ni = data[i];                                                               \
+            part += (ni > (REAL)0) ? (ni - ci - ni * LOGF(ni / ci)) : -ci;                         \
+            C[i] = (REAL)1 - ni / ci;                                                              \
+        }                                                                                          \
+        logL += (double)part;                                                                      \
+    }                                                                                              \
+    _Pragma("omp parallel for schedule(static)")                                                   \
+    for (int64_t k = 0; k < nt; ++k) {                                                             \
+        const REAL *col = M + k * nb;                                                              \
+        REAL a0 = 0, a1 = 0, a2 = 0, a3 = 0;                                                       \
+        int64_t i = 0;                                                                             \
+        for (; i + 3 < nb; i += 4) {                                                               \
+            a0 += col[i] * C[i]; a1 += col[i + 1] * C[i + 1];                                      \
+            a2 += col[i + 2] * C[i + 2]; a3 += col[i + 3] * C[i + 3];                              \
+        }                                                                                          \
+        for (; i < nb; ++i) a0 += col[i] * C[i];                                                   \
+        G[k] = (a0 + a1) + (a2 + a3);                                                              \
+    }                                                                                              \
+    return (logL != 0.0) ? -logL : (double)INFINITY;                                               \
+}
+DEFINE_FG_OMP(double, f64, DBL_EPSILON, log)
+DEFINE_FG_OMP(float, f32, FLT_EPSILON, logf)
+
+int sfho_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
