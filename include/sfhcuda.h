@@ -1,0 +1,182 @@
+/*
+ * sfhcuda.h -- C-ABI of libsfhcuda.so: the B200 (sm_100a) fitting hot path of
+ * StarFormationHistories.jl (composite -> Poisson log-likelihood -> gradient, plus the MZR/AMR
+ * chain rules and the batched-walker log-likelihood).
+ *
+ * The reference (pure Julia, /root/reference) has NO FFI for this path; it is reached by multiple
+ * dispatch.  Each entry point below therefore names the Julia METHOD whose body it replaces
+ * (file:line under /root/reference/src).  INTEGRATION.md shows the `ccall` method bodies a
+ * maintainer would add, and the ctypes binding used by this repo's tests.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No C++/torch types.  Every call returns an sfh_status;
+ *     results are written only on SFH_OK; nothing throws or calls back into the host runtime.
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - scalars in/out are always double, whatever the storage dtype of the stack.
+ *   - one sfh_ctx == one concurrent caller (mirrors TaskLocalValue, fitting/hmc_sample.jl:127);
+ *     the sfh_stack is immutable after creation and may be shared by any number of contexts
+ *     on any number of host threads.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     SFH_ERR_NO_DEVICE.
+ */
+#ifndef SFHCUDA_H
+#define SFHCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFH_VERSION_MAJOR 0
+#define SFH_VERSION_MINOR 1
+
+typedef struct sfh_stack sfh_stack; /* device-resident template stack + data (one row shard) */
+typedef struct sfh_ctx sfh_ctx;     /* per-caller stream, scratch, pinned result buffers     */
+
+typedef enum sfh_status {
+    SFH_OK = 0,
+    SFH_ERR_INVALID_ARG = 1, /* NULL pointer, bad enum, bad size                                        */
+    SFH_ERR_SHAPE = 2,       /* the reference's @argcheck ArgumentError (fitting_base.jl:58-59,271-272;  */
+                             /* solvers.jl:9-12; mzr.jl:55-57)                                          */
+    SFH_ERR_NO_DEVICE = 3,   /* no usable CUDA device / driver                                          */
+    SFH_ERR_CUDA = 4,        /* a CUDA runtime/driver call failed (message in sfh_last_error)           */
+    SFH_ERR_OOM = 5,         /* device or pinned-host allocation failed                                 */
+    SFH_ERR_NCCL = 6,        /* NCCL missing or a collective failed                                     */
+    SFH_ERR_UNSUPPORTED = 7, /* valid request this build cannot serve (e.g. not sm_100)                 */
+    SFH_ERR_NOT_BOUND = 8    /* hierarchical call before sfh_hier_bind                                  */
+} sfh_status;
+
+typedef enum sfh_dtype { SFH_F32 = 0, SFH_F64 = 1, SFH_I64 = 2 } sfh_dtype;
+
+/* metallicity models with a device-side chain rule (hierarchical/mzr.jl:263-284,
+ * hierarchical/amr.jl:181-213, :250-298) and the generic escape hatch */
+typedef enum sfh_mh_kind {
+    SFH_MH_POWERLAW_MZR = 0, /* fixed = {logMstar0}                    */
+    SFH_MH_LINEAR_AMR = 1,   /* fixed = {T_max}                        */
+    SFH_MH_LOG_AMR = 2       /* fixed = {T_max, solZ, Y_p, gamma}      */
+} sfh_mh_kind;
+typedef enum sfh_disp_kind { SFH_DISP_GAUSSIAN = 0 } sfh_disp_kind; /* dispersion_models.jl:80-110 */
+
+/* Options for stack creation.  Zero-initialise, set struct_size, override what you need. */
+typedef struct sfh_opts {
+    int32_t struct_size; /* = sizeof(sfh_opts)                                                      */
+    int32_t device;      /* CUDA device ordinal (default 0)                                         */
+    int64_t row_begin;   /* bin-row shard [row_begin, row_end) of the host matrix this stack holds; */
+    int64_t row_end;     /* 0,0 = all rows.  (one process per GPU)            */
+    double clamp_eps;    /* max(m, eps) clamp; 0 = eps(storage dtype) like the reference            */
+                         /* (fitting_base.jl:90,277)                                                */
+    int32_t tile_bins;   /* 0 = auto; else bins per tile of the fused kernel (16/32/64/128)         */
+    int32_t cluster;     /* 0 = auto; else thread-block-cluster size (1,2,4,8,16)                   */
+    int32_t force_unfused; /* 1 = always use the two-pass kernels (debug / A-B measurements)        */
+    int32_t reserved;
+} sfh_opts;
+
+typedef struct sfh_info {
+    int64_t nbins_total, ntemplates, row_begin, row_end, ld; /* ld = padded leading dimension (elements) */
+    int32_t dtype, device;
+    int32_t fused;     /* 1 if the single-pass fused kernel is in use                  */
+    int32_t tile_bins, cluster, chunks_per_tile, ring_slots, n_clusters;
+    int32_t sm_count, cc_major, cc_minor;
+    int64_t stack_bytes; /* device bytes held by the stack (padded)                    */
+    double clamp_eps;
+} sfh_info;
+
+typedef struct sfh_stats {
+    int64_t evals;          /* evaluations issued through this context                               */
+    int64_t kernel_launches;/* kernels launched by this context                                      */
+    double last_device_ms;  /* device time of the last evaluation (CUDA events on the ctx stream)    */
+} sfh_stats;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int sfh_version(void);              /* major*100 + minor                                         */
+const char *sfh_last_error(void);   /* thread-local message for the last non-OK status           */
+int sfh_device_count(int *count);   /* SFH_OK with *count = 0 when there is no driver            */
+
+/* ---- stack: the device mirror of stack_models (src/fitting/utilities.jl:12-13) ------------- */
+/* models: host, column-major nbins x ntemplates, leading dimension nbins (exactly the Matrix
+ * stack_models returns).  data: host vector of nbins (F32/F64/I64: fitting_core_test.jl:38 passes
+ * Int64).  Replaces the per-call host arrays captured by every driver closure
+ * (solvers.jl:88,181-196; hmc_sample.jl:109; mcmc_sample.jl:102; generic_fitting.jl:306,317).  */
+int sfh_stack_create(sfh_stack **out, const void *models, int64_t nbins, int64_t ntemplates,
+                     int dtype, const void *data, int data_dtype, const sfh_opts *opts);
+/* Synthetic stack generated ON DEVICE: M_ij = scale*U(0,1) from
+ * Philox4x32-10 keyed by seed with counter = global linear index i + nbins*j (so any sharding sees
+ * the same matrix); data_i ~ Poisson((M x_true)_i) (x_true host, ntemplates doubles).          */
+int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_t ntemplates, int dtype,
+                               uint64_t seed, double scale, const double *x_true,
+                               const sfh_opts *opts);
+int sfh_stack_destroy(sfh_stack *s); /* idempotent on NULL; safe from a finalizer thread        */
+int sfh_stack_info(const sfh_stack *s, sfh_info *info);
+int sfh_stack_set_data(sfh_stack *s, const void *data, int data_dtype); /* MCMCModelDistance-style rebinding */
+/* copy the shard back to host (column-major rows x ntemplates, ld = rows) -- used by tests      */
+int sfh_stack_download(const sfh_stack *s, void *models_out, double *data_out);
+
+/* ---- context ----------------------------------------------------------------------------- */
+/* stream: an existing cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a
+ * private non-blocking stream.                                                                 */
+int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out);
+int sfh_ctx_destroy(sfh_ctx *c);
+int sfh_ctx_stats(const sfh_ctx *c, sfh_stats *out);
+
+/* ---- core path --------------------------------------------------------------------------- */
+/* fg!(F, G, coeffs, models, data, composite)  src/fitting/solvers.jl:20-38.
+ *   neg_logL != NULL  <=>  F !== nothing ;  G != NULL  <=>  G !== nothing.
+ *   *neg_logL = -logL (logL == 0 -> +Inf, fitting_base.jl:95);  G[j] = sum_i M_ij (1 - n_i/m_i).
+ *   composite_out (nullable, nbins doubles): what the reference leaves in `composite`:
+ *   the residual 1 - n/m when G != NULL (fitting_base.jl:219), else M*coeffs.                  */
+int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, double *G, double *composite_out);
+/* composite!(C, coeffs, models)  fitting_base.jl:55-65 */
+int sfh_composite(sfh_ctx *c, const double *coeffs, double *composite_out);
+/* loglikelihood(composite, data)  fitting_base.jl:84-96 (data = the vector bound to the stack) */
+int sfh_loglikelihood(sfh_ctx *c, const double *composite, double *logL);
+/* loglikelihood(coeffs, models, data)  fitting_base.jl:117-125 */
+int sfh_loglikelihood_coeffs(sfh_ctx *c, const double *coeffs, double *logL);
+/* grad-loglikelihood!(G, composite, models, data)  fitting_base.jl:265-285:
+ * composite (in/out, nbins) is overwritten with 1 - n/max(composite,eps); G = -M' * that.     */
+int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, double *G);
+
+/* ---- hierarchical path -------------------------------------------------------------------- */
+/* Precompute the age grouping of mzr.jl:131-140 / amr.jl:131 from value-equality of logAge
+ * entries in first-appearance order.  *n_ages_out = length(unique(logAge)).                   */
+int sfh_hier_bind(sfh_ctx *c, const double *logAge, const double *metallicities, int64_t *n_ages_out);
+/* calculate_coeffs(MHmodel, dispmodel, R, logAge, MH)  mzr.jl:50-79 / amr.jl:50-73.
+ * variables = [R_1..R_Nj, alpha, beta, sigma] in natural units.                               */
+int sfh_calculate_coeffs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind,
+                         const double *variables, double *coeffs_out);
+/* fg!(F, G, MHmodel0, dispmodel0, variables, models, data, composite, logAge, MH)
+ * mzr.jl:84-215 ("fg_mzr!") and amr.jl:78-173 ("fg_amr!").  free_mask[3] = free_params of
+ * (alpha, beta, sigma); fixed ones receive 0 (mzr.jl:175,196,201).  G has Nj+3 entries.       */
+int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind,
+                     const double *variables, const uint8_t *free_mask,
+                     double *neg_logL, double *G);
+
+/* ---- batched walkers (new; per-walker semantics of MCMCModel, fitting/mcmc_sample.jl:12-23) -- */
+/* X: ntemplates x W column-major.  logL[w] = -Inf if any X[:,w] < 0 (:15-19) else
+ * loglikelihood(M*X[:,w], data).                                                               */
+int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL);
+
+/* ---- multi-GPU: bin-row shards, one process per GPU -------------------- */
+/* 128-byte NCCL unique id (rank 0 creates, the host runtime broadcasts it).                    */
+int sfh_comm_unique_id(void *id128);
+/* After this, every evaluation all-reduces [logL, G_1..G_T] (sum, FP64) over the ranks on the
+ * context stream before results are returned, so each rank receives the full-stack answer.     */
+int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128);
+
+/* ---- device-side plumbing (no host round trip; used by bench.py and torch interop) ---------- */
+/* Enqueue one fused evaluation on the ctx stream.  d_coeffs: device, ntemplates doubles.
+ * d_out: device, 1+ntemplates doubles = [logL (raw sum, un-guarded), G...].  Asynchronous.
+ * want_G = 0 skips the gradient pass.                                                          */
+int sfh_enqueue_fg(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G);
+int sfh_enqueue_logl_batched(sfh_ctx *c, const double *d_X, int64_t W, double *d_logL);
+int sfh_ctx_synchronize(sfh_ctx *c);
+/* Time `reps` back-to-back evaluations with CUDA events on the ctx stream (inputs resident).
+ * flush_l2 != 0 writes a >L2-sized buffer between evaluations (outside the per-kernel events).
+ * ms_kernel_out (nullable): mean duration of the fused kernel alone.                           */
+int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2,
+                double *ms_per_eval_out, double *ms_kernel_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFHCUDA_H */

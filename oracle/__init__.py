@@ -87,7 +87,7 @@ def _declare(L):
     PD, PF = C.POINTER(dbl), C.POINTER(flt)
     L.sfho_fg_quad.argtypes = [C.c_int, PD, PD, PD, PD, PD, PD, i64, i64]
     L.sfho_fg_quad.restype = dbl
-    L.sfho_fg_quad_f32.argtypes = [C.c_int, PD, PD, PD, PF, PF, i64, i64]
+    L.sfho_fg_quad_f32.argtypes = [C.c_int, PD, PD, PD, PF, PF, i64, i64, dbl]
     L.sfho_fg_quad_f32.restype = dbl
     L.sfho_fg_hier_quad.argtypes = [C.c_int, PD, C.c_int, PD, pint, PD, i64, PD, PD, i64, PD, PD, i64, PD]
     L.sfho_fg_hier_quad.restype = dbl
@@ -179,14 +179,15 @@ def fg_quad(coeffs, M, data, want_G=True):
     return r, (G if want_G else None), (gs if want_G else None), Cm
 
 
-def fg_quad_f32(coeffs, M32, data32, want_G=True):
-    """__float128 arbiter on Float32-STORED templates/data (coeffs Float64)."""
+def fg_quad_f32(coeffs, M32, data32, want_G=True, eps=float(np.finfo(np.float32).eps)):
+    """__float128 arbiter on Float32-STORED templates/data (coeffs Float64); clamp eps(Float32) like a
+    Float32 fit in the reference (fitting_base.jl:86,90)."""
     M = _fcol(M32, np.float32); nb, nt = M.shape
     c = np.ascontiguousarray(coeffs, dtype=np.float64)
     d = np.ascontiguousarray(np.asarray(data32).reshape(-1, order="F"), dtype=np.float32)
     G = np.empty(nt); gs = np.empty(nt)
     D = C.c_double
-    r = lib().sfho_fg_quad_f32(int(want_G), _p(G, D), _p(gs, D), _p(c, D), _p(M, C.c_float), _p(d, C.c_float), nb, nt)
+    r = lib().sfho_fg_quad_f32(int(want_G), _p(G, D), _p(gs, D), _p(c, D), _p(M, C.c_float), _p(d, C.c_float), nb, nt, float(eps))
     return r, (G if want_G else None), (gs if want_G else None)
 
 

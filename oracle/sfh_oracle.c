@@ -134,9 +134,10 @@ double sfho_fg_quad(int want_G, double *G, double *gscale, const double *coeffs,
 }
 
 /* Same for Float32-STORED templates with exact (quad) arithmetic: what the GPU's
- * "F32 storage, FP64 accumulate" mode is compared against at 1e-6 (BASELINE.json).   */
+ * "F32 storage, FP64 accumulate" mode is compared against at 1e-6 (BASELINE.json).
+ * eps: the clamp; the reference uses eps(Float32) for a Float32 fit (fitting_base.jl:86,90). */
 double sfho_fg_quad_f32(int want_G, double *G, double *gscale, const double *coeffs, const float *M,
-                        const float *data, int64_t nb, int64_t nt)
+                        const float *data, int64_t nb, int64_t nt, double eps)
 {
     __float128 *C = (__float128 *)malloc(sizeof(__float128) * (size_t)nb);
     for (int64_t i = 0; i < nb; ++i) C[i] = 0;
@@ -148,7 +149,7 @@ double sfho_fg_quad_f32(int want_G, double *G, double *gscale, const double *coe
     __float128 logL = 0;
     for (int64_t i = 0; i < nb; ++i) {
         __float128 ci = C[i];
-        if (ci < (__float128)DBL_EPSILON) ci = (__float128)DBL_EPSILON;
+        if (ci < (__float128)eps) ci = (__float128)eps;
         const __float128 ni = data[i];
         logL += (ni > 0) ? (ni - ci - ni * logq(ni / ci)) : -ci;
         C[i] = 1 - ni / ci;

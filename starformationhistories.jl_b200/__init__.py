@@ -1,0 +1,35 @@
+"""sfh_b200 -- B200-native fitting hot path of StarFormationHistories.jl.
+
+The directory is named ``starformationhistories.jl_b200`` (not importable by name because of the dot);
+import it through the ``sfh_b200`` shim at the repository root::
+
+    import sfh_b200 as sfh
+    stack = sfh.DeviceStack(models, data)               # upload once per fit
+    nlogL = sfh.fg_(True, G, coeffs, stack, data)       # fg!  (src/fitting/solvers.jl:20-38)
+
+Importing this package loads ``libsfhcuda.so`` and fails loudly if it is missing.
+"""
+from . import _lib
+from ._lib import SFHError, device_count
+from .fitting import (DeviceStack, clear_cache, composite_, device_stack, fg_ as fg_flat_, grad_loglikelihood,
+                      grad_loglikelihood_, loglikelihood, stack_models)
+from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR, LogarithmicAMR, PowerLawMZR,
+                           calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams)
+from .sampling import HMCModel, MCMCModel
+
+
+def fg_(F, G, *args):
+    """``fg!`` with the reference's two method families (multiple dispatch on the third argument):
+
+    ``fg_(F, G, coeffs, models, data[, composite])``                                    solvers.jl:20-38
+    ``fg_(F, G, MHmodel0, dispmodel0, variables, models, data, composite, logAge, MH)``  mzr.jl:84 / amr.jl:78
+    """
+    if args and hasattr(args[0], "kind") and hasattr(args[0], "free_params"):
+        return fg_hier_(F, G, *args)
+    return fg_flat_(F, G, *args)
+
+
+__all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite_", "loglikelihood",
+           "grad_loglikelihood", "grad_loglikelihood_", "fg_", "calculate_coeffs", "PowerLawMZR", "LinearAMR",
+           "LogarithmicAMR", "GaussianDispersion", "HierarchicalOptimizer", "HMCModel", "MCMCModel", "nparams",
+           "exptransform", "logtransform", "clear_cache", "device_stack"]

@@ -1,0 +1,108 @@
+"""ctypes binding of ``libsfhcuda.so`` -- one prototype per symbol declared in ``include/sfhcuda.h``.
+
+The library is loaded at import time from THIS directory (built in-tree by ``csrc/Makefile`` /
+``__graft_entry__.build()``).  If it is missing the import fails loudly: there is no Python, numpy
+or CPU implementation of the hot path behind this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfhcuda.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+        "(or __graft_entry__.build()).  There is no CPU fallback for the fitting hot path."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+# ---- enums (include/sfhcuda.h) -------------------------------------------------------------
+SFH_OK, SFH_ERR_INVALID_ARG, SFH_ERR_SHAPE, SFH_ERR_NO_DEVICE, SFH_ERR_CUDA = 0, 1, 2, 3, 4
+SFH_ERR_OOM, SFH_ERR_NCCL, SFH_ERR_UNSUPPORTED, SFH_ERR_NOT_BOUND = 5, 6, 7, 8
+SFH_F32, SFH_F64, SFH_I64 = 0, 1, 2
+SFH_MH_POWERLAW_MZR, SFH_MH_LINEAR_AMR, SFH_MH_LOG_AMR = 0, 1, 2
+SFH_DISP_GAUSSIAN = 0
+
+
+class sfh_opts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("row_begin", C.c_int64), ("row_end", C.c_int64),
+                ("clamp_eps", C.c_double), ("tile_bins", C.c_int32), ("cluster", C.c_int32),
+                ("force_unfused", C.c_int32), ("reserved", C.c_int32)]
+
+
+class sfh_info(C.Structure):
+    _fields_ = [("nbins_total", C.c_int64), ("ntemplates", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
+                ("ld", C.c_int64), ("dtype", C.c_int32), ("device", C.c_int32), ("fused", C.c_int32),
+                ("tile_bins", C.c_int32), ("cluster", C.c_int32), ("chunks_per_tile", C.c_int32),
+                ("ring_slots", C.c_int32), ("n_clusters", C.c_int32), ("sm_count", C.c_int32), ("cc_major", C.c_int32),
+                ("cc_minor", C.c_int32), ("stack_bytes", C.c_int64), ("clamp_eps", C.c_double)]
+
+
+class sfh_stats(C.Structure):
+    _fields_ = [("evals", C.c_int64), ("kernel_launches", C.c_int64), ("last_device_ms", C.c_double)]
+
+
+_vp, _i64, _int, _dp = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+
+# every exported symbol of include/sfhcuda.h: name -> (restype, argtypes)
+PROTOTYPES = {
+    "sfh_version": (_int, []),
+    "sfh_last_error": (C.c_char_p, []),
+    "sfh_device_count": (_int, [C.POINTER(_int)]),
+    "sfh_stack_create": (_int, [C.POINTER(_vp), _vp, _i64, _i64, _int, _vp, _int, C.POINTER(sfh_opts)]),
+    "sfh_stack_create_synthetic": (_int, [C.POINTER(_vp), _i64, _i64, _int, C.c_uint64, C.c_double, _dp, C.POINTER(sfh_opts)]),
+    "sfh_stack_destroy": (_int, [_vp]),
+    "sfh_stack_info": (_int, [_vp, C.POINTER(sfh_info)]),
+    "sfh_stack_set_data": (_int, [_vp, _vp, _int]),
+    "sfh_stack_download": (_int, [_vp, _vp, _dp]),
+    "sfh_ctx_create": (_int, [_vp, _vp, C.POINTER(_vp)]),
+    "sfh_ctx_destroy": (_int, [_vp]),
+    "sfh_ctx_stats": (_int, [_vp, C.POINTER(sfh_stats)]),
+    "sfh_eval_fg": (_int, [_vp, _dp, _dp, _dp, _dp]),
+    "sfh_composite": (_int, [_vp, _dp, _dp]),
+    "sfh_loglikelihood": (_int, [_vp, _dp, _dp]),
+    "sfh_loglikelihood_coeffs": (_int, [_vp, _dp, _dp]),
+    "sfh_grad_loglikelihood": (_int, [_vp, _dp, _dp]),
+    "sfh_hier_bind": (_int, [_vp, _dp, _dp, C.POINTER(_i64)]),
+    "sfh_calculate_coeffs": (_int, [_vp, _int, _dp, _int, _dp, _dp]),
+    "sfh_eval_fg_hier": (_int, [_vp, _int, _dp, _int, _dp, _u8p, _dp, _dp]),
+    "sfh_eval_logl_batched": (_int, [_vp, _dp, _i64, _dp]),
+    "sfh_comm_unique_id": (_int, [_vp]),
+    "sfh_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "sfh_enqueue_fg": (_int, [_vp, _vp, _vp, _int]),
+    "sfh_enqueue_logl_batched": (_int, [_vp, _vp, _i64, _vp]),
+    "sfh_ctx_synchronize": (_int, [_vp]),
+    "sfh_time_fg": (_int, [_vp, _dp, _int, _int, _int, _dp, _dp]),
+}
+
+for _name, (_res, _args) in PROTOTYPES.items():
+    _f = getattr(lib, _name)  # AttributeError here == the .so does not export what the header declares
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class SFHError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libsfhcuda status {status}: {message}")
+        self.status = status
+
+
+def check(status: int) -> None:
+    """Map a non-OK status to the exception the reference would raise (ArgumentError -> ValueError)."""
+    if status == SFH_OK:
+        return
+    msg = (lib.sfh_last_error() or b"").decode("utf-8", "replace")
+    if status in (SFH_ERR_SHAPE, SFH_ERR_INVALID_ARG):
+        raise ValueError(f"libsfhcuda: {msg}")
+    raise SFHError(status, msg)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib.sfh_device_count(C.byref(n)))
+    return n.value

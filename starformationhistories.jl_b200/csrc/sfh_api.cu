@@ -1,0 +1,1011 @@
+// sfh_api.cu -- the C-ABI of libsfhcuda.so (include/sfhcuda.h): handle lifecycle, upload,
+// kernel selection/launch, result plumbing, NCCL row-shard reduction.  No CPU fallback: every
+// compute entry point fails with SFH_ERR_NO_DEVICE when there is no GPU.
+#include "../../include/sfhcuda.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sfh_batched.cuh"
+#include "sfh_fused.cuh"
+#include "sfh_small.cuh"
+
+using namespace sfh;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            const int _c = (_e == cudaErrorMemoryAllocation) ? SFH_ERR_OOM                            \
+                           : (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver)           \
+                               ? SFH_ERR_NO_DEVICE                                                    \
+                               : SFH_ERR_CUDA;                                                        \
+            return fail(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                             \
+    } while (0)
+#define SFH_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != SFH_OK) return _s;  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so the library has no link-time dependency on it
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+bool load_nccl() {
+    std::call_once(g_nccl_once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.h) break;
+        }
+        if (!g_nccl.h) return;
+        g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.h, "ncclGetUniqueId");
+        g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.h, "ncclCommInitRank");
+        g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.h, "ncclAllReduce");
+        g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.h, "ncclCommDestroy");
+        g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.h, "ncclGetErrorString");
+    });
+    return g_nccl.h && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline size_t elem_size(int dtype) { return dtype == SFH_F32 ? 4 : 8; }
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct sfh_stack {
+    int device = 0, dtype = SFH_F64;
+    int64_t nb_total = 0, nt = 0, row_begin = 0, row_end = 0, rows = 0, ld = 0;
+    void *dM = nullptr;
+    double *d_data = nullptr;
+    double eps = 0.0;
+    // kernel configuration
+    bool fused = false;
+    int bt = 0, cluster = 1, kt = 0, ring = 0, n_clusters = 0, n_tiles = 0;
+    uint32_t smem = 0;
+    bool evict_first = false;
+    CUtensorMap tmap;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t l2_bytes = 0;
+};
+
+struct sfh_ctx {
+    sfh_stack *s = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // scratch
+    double *d_coeffs = nullptr, *d_out = nullptr, *d_composite = nullptr, *d_residual = nullptr;
+    double *d_gpart = nullptr, *d_lpart = nullptr;
+    unsigned int *d_ticket = nullptr;
+    int64_t gstride = 0;
+    double *h_in = nullptr, *h_out = nullptr;  // pinned
+    size_t h_in_n = 0, h_out_n = 0;
+    // hierarchical binding
+    bool bound = false;
+    int32_t nj = 0;
+    double *d_logAge_u = nullptr, *d_MH = nullptr, *d_vars = nullptr, *d_hscratch = nullptr, *d_Ajk = nullptr,
+           *d_outh = nullptr;
+    int32_t *d_jidx = nullptr, *d_gptr = nullptr, *d_gmem = nullptr, *d_sidx = nullptr;
+    // batched walkers
+    int64_t wcap = 0, wld = 0;
+    double *d_X = nullptr, *d_Xt = nullptr, *d_part = nullptr, *d_logl = nullptr;
+    int32_t *d_neg = nullptr;
+    // multi-GPU
+    NcclComm comm = nullptr;
+    int nranks = 1, rank = 0;
+    // timing / stats
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    float4 *d_flush = nullptr;
+    int64_t flush_n4 = 0;
+    sfh_stats stats{};
+};
+
+// ---------------------------------------------------------------------------------------------
+// fused-kernel configuration and launch
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB
+
+struct TileGeom { int vec, lpr, rpw, rpc; };
+TileGeom geom(int dtype, int bt) {
+    TileGeom g;
+    g.vec = 16 / (int)elem_size(dtype);
+    g.lpr = bt / g.vec;
+    g.rpw = 32 / g.lpr;
+    g.rpc = g.rpw * kConsumerWarps;
+    return g;
+}
+
+template <typename S, int BT, bool G>
+cudaError_t set_attr(uint32_t smem, bool nonportable) {
+    auto k = sfh_fg_fused_kernel<S, BT, G>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (nonportable) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
+}
+template <typename S, int BT, bool G>
+cudaError_t max_clusters(const sfh_stack *s, int *out) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(s->cluster * 1024u);
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = s->smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s->cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(out, sfh_fg_fused_kernel<S, BT, G>, &cfg);
+}
+template <typename S, int BT, bool G>
+cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(s->n_clusters * s->cluster));
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = s->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s->cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, G>, s->tmap, p);
+}
+
+#define SFH_DISPATCH(s, want_g, CALL)                                             \
+    [&]() -> cudaError_t {                                                        \
+        if ((s)->dtype == SFH_F64) {                                              \
+            switch ((s)->bt) {                                                    \
+            case 64: return (want_g) ? CALL(double, 64, true) : CALL(double, 64, false); \
+            case 32: return (want_g) ? CALL(double, 32, true) : CALL(double, 32, false); \
+            default: return (want_g) ? CALL(double, 16, true) : CALL(double, 16, false); \
+            }                                                                     \
+        } else {                                                                  \
+            switch ((s)->bt) {                                                    \
+            case 128: return (want_g) ? CALL(float, 128, true) : CALL(float, 128, false); \
+            case 64: return (want_g) ? CALL(float, 64, true) : CALL(float, 64, false);   \
+            default: return (want_g) ? CALL(float, 32, true) : CALL(float, 32, false);   \
+            }                                                                     \
+        }                                                                         \
+    }()
+
+// choose tile / cluster / ring for this stack; returns false if the fused tiling cannot hold T
+bool choose_config(sfh_stack *s, const sfh_opts *o) {
+    const int cands64[3] = {64, 32, 16}, cands32[3] = {128, 64, 32};
+    const int *cands = (s->dtype == SFH_F64) ? cands64 : cands32;
+    int best_bt = 0, best_c = 0, best_kt = 0;
+    for (int ci = 0; ci < 3; ++ci) {
+        const int bt = cands[ci];
+        if (o && o->tile_bins && o->tile_bins != bt) continue;
+        const TileGeom g = geom(s->dtype, bt);
+        int c_found = 0, kt_found = 0;
+        const int cl_opts[5] = {1, 2, 4, 8, 16};
+        for (int c : cl_opts) {
+            if (o && o->cluster && o->cluster != c) continue;
+            const int64_t kt = (s->nt + (int64_t)c * g.rpc - 1) / ((int64_t)c * g.rpc);
+            if (kt <= kKMax) { c_found = c; kt_found = (int)std::max<int64_t>(kt, 1); break; }
+        }
+        if (!c_found) continue;
+        best_bt = bt; best_c = c_found; best_kt = kt_found;
+        // keep the largest tile that still leaves >= 2 tiles per resident cluster (load balance)
+        const int64_t n_tiles = (s->rows + bt - 1) / bt;
+        const int64_t n_cl = std::max(1, s->sm_count / c_found);
+        if (n_tiles >= 2 * n_cl || (o && o->tile_bins)) break;
+    }
+    if (!best_bt) return false;
+    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt;
+    // ring: everything shared memory allows (>= kt+1 so the producer can always run ahead)
+    const TileGeom g = geom(s->dtype, s->bt);
+    const FusedSmem fixed = FusedSmem::make(0, s->bt, s->cluster, s->kt * g.rpc);
+    int ring = (int)((kMaxDynSmem - fixed.total - 64) / (kChunkBytes + 16));
+    ring = std::min(ring, 27);
+    if (ring < s->kt + 1) return false;
+    s->ring = ring;
+    s->smem = FusedSmem::make(ring, s->bt, s->cluster, s->kt * g.rpc).total;
+    s->n_tiles = (int)((s->rows + s->bt - 1) / s->bt);
+    return true;
+}
+
+int setup_fused(sfh_stack *s, const sfh_opts *o) {
+    s->fused = false;
+    if (o && o->force_unfused) return SFH_OK;
+    if (s->cc_major != 10) return SFH_OK;  // TMA/cluster path is written for sm_100a only
+    if (s->rows <= 0 || s->nt <= 0) return SFH_OK;
+    if (!choose_config(s, o)) return SFH_OK;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    const TileGeom g = geom(s->dtype, s->bt);
+    const cuuint64_t gdim[2] = {(cuuint64_t)s->rows, (cuuint64_t)s->nt};
+    const cuuint64_t gstr[1] = {(cuuint64_t)s->ld * elem_size(s->dtype)};
+    const cuuint32_t box[2] = {(cuuint32_t)s->bt, (cuuint32_t)g.rpc};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&s->tmap, s->dtype == SFH_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     s->dM, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const bool nonport = s->cluster > 8;
+#define SET_ATTR(S, BT, G) set_attr<S, BT, G>(s->smem, nonport)
+    CU_TRY(SFH_DISPATCH(s, true, SET_ATTR));
+    CU_TRY(SFH_DISPATCH(s, false, SET_ATTR));
+#undef SET_ATTR
+    int maxcl = 0;
+#define MAX_CL(S, BT, G) max_clusters<S, BT, G>(s, &maxcl)
+    CU_TRY(SFH_DISPATCH(s, true, MAX_CL));
+#undef MAX_CL
+    if (maxcl <= 0) return SFH_OK;  // cannot co-schedule this cluster shape: stay unfused
+    s->n_clusters = std::min(maxcl, s->n_tiles);
+    // the stack is streamed exactly once per evaluation: do not let it evict the O(Nb) vectors
+    s->evict_first = (size_t)s->ld * s->nt * elem_size(s->dtype) > s->l2_bytes;
+    s->fused = true;
+    return SFH_OK;
+}
+
+int device_props(sfh_stack *s) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(SFH_ERR_NO_DEVICE, "no CUDA device (%s)", cudaGetErrorString(e));
+    if (s->device < 0 || s->device >= n) return fail(SFH_ERR_INVALID_ARG, "device %d out of range (%d)", s->device, n);
+    CU_TRY(cudaSetDevice(s->device));
+    cudaDeviceProp pr;
+    CU_TRY(cudaGetDeviceProperties(&pr, s->device));
+    s->sm_count = pr.multiProcessorCount;
+    s->cc_major = pr.major;
+    s->cc_minor = pr.minor;
+    s->l2_bytes = (size_t)pr.l2CacheSize;
+    return SFH_OK;
+}
+
+int upload_data(sfh_stack *s, const void *data, int data_dtype, int64_t row_begin) {
+    const int64_t n = s->rows;
+    if (n == 0) return SFH_OK;
+    if (data_dtype == SFH_F64) {
+        CU_TRY(cudaMemcpy(s->d_data, (const double *)data + row_begin, n * 8, cudaMemcpyHostToDevice));
+    } else {
+        const size_t es = (data_dtype == SFH_F32) ? 4 : 8;
+        void *tmp = nullptr;
+        CU_TRY(cudaMalloc(&tmp, n * es));
+        cudaError_t e = cudaMemcpy(tmp, (const char *)data + row_begin * es, n * es, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            const int th = 256;
+            const unsigned bl = (unsigned)((n + th - 1) / th);
+            if (data_dtype == SFH_F32)
+                sfh_to_double_kernel<float><<<bl, th>>>((const float *)tmp, s->d_data, n);
+            else
+                sfh_to_double_kernel<long long><<<bl, th>>>((const long long *)tmp, s->d_data, n);
+            e = cudaDeviceSynchronize();
+        }
+        cudaFree(tmp);
+        CU_TRY(e);
+    }
+    return SFH_OK;
+}
+
+int stack_common_init(sfh_stack *s, int64_t nbins, int64_t ntemplates, int dtype, const sfh_opts *opts) {
+    if (nbins < 0 || ntemplates < 0) return fail(SFH_ERR_INVALID_ARG, "negative size");
+    if (dtype != SFH_F32 && dtype != SFH_F64) return fail(SFH_ERR_INVALID_ARG, "stack dtype must be F32 or F64");
+    if (opts && opts->struct_size != (int32_t)sizeof(sfh_opts))
+        return fail(SFH_ERR_INVALID_ARG, "sfh_opts.struct_size mismatch (%d vs %zu)", opts->struct_size, sizeof(sfh_opts));
+    s->device = opts ? opts->device : 0;
+    s->dtype = dtype;
+    s->nb_total = nbins;
+    s->nt = ntemplates;
+    s->row_begin = 0;
+    s->row_end = nbins;
+    if (opts && !(opts->row_begin == 0 && opts->row_end == 0)) {
+        if (opts->row_begin < 0 || opts->row_end > nbins || opts->row_begin > opts->row_end)
+            return fail(SFH_ERR_SHAPE, "row shard [%lld,%lld) outside [0,%lld)", (long long)opts->row_begin,
+                        (long long)opts->row_end, (long long)nbins);
+        s->row_begin = opts->row_begin;
+        s->row_end = opts->row_end;
+    }
+    s->rows = s->row_end - s->row_begin;
+    s->ld = std::max<int64_t>(round_up(s->rows, 32), 32);  // 16-byte-aligned TMA stride, 128-byte rows
+    s->eps = (opts && opts->clamp_eps > 0.0) ? opts->clamp_eps
+             : (dtype == SFH_F32 ? (double)std::numeric_limits<float>::epsilon()
+                                 : std::numeric_limits<double>::epsilon());
+    SFH_TRY(device_props(s));
+    const size_t bytes = (size_t)s->ld * (size_t)std::max<int64_t>(s->nt, 1) * elem_size(dtype);
+    CU_TRY(cudaMalloc(&s->dM, bytes));
+    CU_TRY(cudaMalloc((void **)&s->d_data, (size_t)s->ld * 8));
+    CU_TRY(cudaMemset(s->d_data, 0, (size_t)s->ld * 8));
+    return SFH_OK;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_version(void) { return SFH_VERSION_MAJOR * 100 + SFH_VERSION_MINOR; }
+extern "C" const char *sfh_last_error(void) { return g_err.c_str(); }
+extern "C" int sfh_device_count(int *count) {
+    if (!count) return fail(SFH_ERR_INVALID_ARG, "count is NULL");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    *count = n;
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stack
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_stack_create(sfh_stack **out, const void *models, int64_t nbins, int64_t ntemplates, int dtype,
+                                const void *data, int data_dtype, const sfh_opts *opts) {
+    if (!out) return fail(SFH_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if ((!models && nbins * ntemplates > 0) || (!data && nbins > 0)) return fail(SFH_ERR_INVALID_ARG, "models/data is NULL");
+    if (data_dtype != SFH_F32 && data_dtype != SFH_F64 && data_dtype != SFH_I64)
+        return fail(SFH_ERR_INVALID_ARG, "bad data dtype %d", data_dtype);
+    sfh_stack *s = new (std::nothrow) sfh_stack();
+    if (!s) return fail(SFH_ERR_OOM, "host allocation failed");
+    int st = stack_common_init(s, nbins, ntemplates, dtype, opts);
+    if (st == SFH_OK && s->rows > 0 && s->nt > 0) {
+        const size_t es = elem_size(dtype);
+        // zero the padding rows, then a strided copy of the row shard of the column-major host matrix
+        cudaError_t e = cudaMemset(s->dM, 0, (size_t)s->ld * s->nt * es);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(s->dM, (size_t)s->ld * es, (const char *)models + (size_t)s->row_begin * es,
+                             (size_t)nbins * es, (size_t)s->rows * es, (size_t)s->nt, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) st = fail(SFH_ERR_CUDA, "stack upload failed: %s", cudaGetErrorString(e));
+    }
+    if (st == SFH_OK) st = upload_data(s, data, data_dtype, s->row_begin);
+    if (st == SFH_OK) st = setup_fused(s, opts);
+    if (st != SFH_OK) { sfh_stack_destroy(s); return st; }
+    *out = s;
+    return SFH_OK;
+}
+
+extern "C" int sfh_stack_set_data(sfh_stack *s, const void *data, int data_dtype) {
+    if (!s || !data) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    if (data_dtype != SFH_F32 && data_dtype != SFH_F64 && data_dtype != SFH_I64)
+        return fail(SFH_ERR_INVALID_ARG, "bad data dtype %d", data_dtype);
+    CU_TRY(cudaSetDevice(s->device));
+    return upload_data(s, data, data_dtype, s->row_begin);
+}
+
+extern "C" int sfh_stack_destroy(sfh_stack *s) {
+    if (!s) return SFH_OK;
+    if (s->dM || s->d_data) {
+        cudaSetDevice(s->device);
+        cudaFree(s->dM);
+        cudaFree(s->d_data);
+    }
+    delete s;
+    return SFH_OK;
+}
+
+extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
+    if (!s || !info) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    memset(info, 0, sizeof *info);
+    info->nbins_total = s->nb_total; info->ntemplates = s->nt; info->row_begin = s->row_begin; info->row_end = s->row_end;
+    info->ld = s->ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
+    info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
+    info->n_clusters = s->n_clusters; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
+    info->stack_bytes = (int64_t)((size_t)s->ld * s->nt * elem_size(s->dtype)); info->clamp_eps = s->eps;
+    return SFH_OK;
+}
+
+extern "C" int sfh_stack_download(const sfh_stack *s, void *models_out, double *data_out) {
+    if (!s) return fail(SFH_ERR_INVALID_ARG, "NULL stack");
+    CU_TRY(cudaSetDevice(s->device));
+    const size_t es = elem_size(s->dtype);
+    if (models_out && s->rows > 0 && s->nt > 0)
+        CU_TRY(cudaMemcpy2D(models_out, (size_t)s->rows * es, s->dM, (size_t)s->ld * es, (size_t)s->rows * es,
+                            (size_t)s->nt, cudaMemcpyDeviceToHost));
+    if (data_out && s->rows > 0) CU_TRY(cudaMemcpy(data_out, s->d_data, (size_t)s->rows * 8, cudaMemcpyDeviceToHost));
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out) {
+    if (!s || !out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(s->device));
+    sfh_ctx *c = new (std::nothrow) sfh_ctx();
+    if (!c) return fail(SFH_ERR_OOM, "host allocation failed");
+    c->s = s;
+    auto bail = [&](int st) { sfh_ctx_destroy(c); return st; };
+#define CTX_TRY(expr)                                                                               \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return bail(fail(_e == cudaErrorMemoryAllocation ? SFH_ERR_OOM : SFH_ERR_CUDA, "%s: %s", #expr, \
+                             cudaGetErrorString(_e)));                                              \
+    } while (0)
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    const int64_t nt = std::max<int64_t>(s->nt, 1), ld = s->ld;
+    c->gstride = round_up(nt, 16);
+    const int ncl = std::max(s->n_clusters, 1);
+    CTX_TRY(cudaMalloc((void **)&c->d_coeffs, nt * 8));
+    CTX_TRY(cudaMalloc((void **)&c->d_out, (1 + nt) * 8));
+    CTX_TRY(cudaMalloc((void **)&c->d_composite, ld * 8));
+    CTX_TRY(cudaMalloc((void **)&c->d_residual, ld * 8));
+    CTX_TRY(cudaMalloc((void **)&c->d_gpart, (size_t)ncl * c->gstride * 8));
+    CTX_TRY(cudaMalloc((void **)&c->d_lpart, 1024 * 8));
+    CTX_TRY(cudaMalloc((void **)&c->d_ticket, 64));
+    CTX_TRY(cudaMemset(c->d_ticket, 0, 64));
+    CTX_TRY(cudaMemset(c->d_composite, 0, ld * 8));
+    CTX_TRY(cudaMemset(c->d_out, 0, (1 + nt) * 8));
+    c->h_in_n = (size_t)std::max<int64_t>(nt, ld) + 16;
+    c->h_out_n = (size_t)std::max<int64_t>(nt + 1, ld) + 16;
+    CTX_TRY(cudaMallocHost((void **)&c->h_in, c->h_in_n * 8));
+    CTX_TRY(cudaMallocHost((void **)&c->h_out, c->h_out_n * 8));
+    CTX_TRY(cudaEventCreate(&c->ev0));
+    CTX_TRY(cudaEventCreate(&c->ev1));
+    CTX_TRY(cudaEventCreate(&c->evk0));
+    CTX_TRY(cudaEventCreate(&c->evk1));
+#undef CTX_TRY
+    *out = c;
+    return SFH_OK;
+}
+
+extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
+    if (!c) return SFH_OK;
+    if (c->s) cudaSetDevice(c->s->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_coeffs); cudaFree(c->d_out); cudaFree(c->d_composite); cudaFree(c->d_residual);
+    cudaFree(c->d_gpart); cudaFree(c->d_lpart); cudaFree(c->d_ticket);
+    cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
+    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx);
+    cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
+    cudaFree(c->d_flush);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evk0) cudaEventDestroy(c->evk0);
+    if (c->evk1) cudaEventDestroy(c->evk1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SFH_OK;
+}
+
+extern "C" int sfh_ctx_stats(const sfh_ctx *c, sfh_stats *out) {
+    if (!c || !out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *out = c->stats;
+    return SFH_OK;
+}
+extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
+    if (!c) return fail(SFH_ERR_INVALID_ARG, "NULL ctx");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluation plumbing (device side)
+// ---------------------------------------------------------------------------------------------
+namespace {
+int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce) {
+    const sfh_stack *s = c->s;
+    FinalizeParams fp{};
+    fp.nb = s->rows; fp.nt = s->nt; fp.gstride = c->gstride; fp.n_clusters = s->n_clusters; fp.want_G = want_G_reduce;
+    fp.eps = s->eps; fp.composite = composite; fp.data = s->d_data; fp.gpart = c->d_gpart; fp.out = d_out;
+    fp.lpart = c->d_lpart; fp.ticket = c->d_ticket;
+    const int64_t work = std::max<int64_t>(s->rows, want_G_reduce ? s->nt : 0);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>((work + kFinalizeThreads - 1) / kFinalizeThreads, 1),
+                                      std::min(1024, 2 * std::max(s->sm_count, 1)));
+    sfh_finalize_kernel<<<grid, kFinalizeThreads, 0, c->stream>>>(fp);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    return SFH_OK;
+}
+
+// d_out = [logL raw, G...]; leaves M*coeffs in c->d_composite and (want_G) the residual in c->d_residual
+int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G, bool time_kernel) {
+    sfh_stack *s = c->s;
+    if (s->rows == 0 || s->nt == 0) {
+        CU_TRY(cudaMemsetAsync(d_out, 0, (1 + std::max<int64_t>(s->nt, 0)) * 8, c->stream));
+        return SFH_OK;
+    }
+    if (s->fused) {
+        FusedParams p{};
+        p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ring = s->ring; p.n_tiles = s->n_tiles;
+        p.evict_first = s->evict_first ? 1 : 0; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
+        p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
+        p.gstride = c->gstride;
+        if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
+#define LAUNCH(S, BT, G) launch_fused_t<S, BT, G>(s, p, c->stream)
+        CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
+#undef LAUNCH
+        if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
+        c->stats.kernel_launches++;
+        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G));
+    } else {
+        // two-pass path: gemv 'N' -> logL -> residual -> gemv 'T'  (the reference's own pass structure)
+        const unsigned gb = (unsigned)((s->rows + 127) / 128);
+        if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
+        if (s->dtype == SFH_F64)
+            sfh_composite_kernel<double><<<gb, 512, 0, c->stream>>>((const double *)s->dM, s->ld, s->rows, s->nt, d_coeffs, c->d_composite);
+        else
+            sfh_composite_kernel<float><<<gb, 512, 0, c->stream>>>((const float *)s->dM, s->ld, s->rows, s->nt, d_coeffs, c->d_composite);
+        CU_TRY(cudaGetLastError());
+        c->stats.kernel_launches++;
+        SFH_TRY(launch_finalize(c, c->d_composite, d_out, 0));
+        if (want_G) {
+            CU_TRY(cudaMemcpyAsync(c->d_residual, c->d_composite, s->rows * 8, cudaMemcpyDeviceToDevice, c->stream));
+            sfh_residual_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, c->stream>>>(c->d_residual, s->d_data, s->rows, s->eps);
+            const unsigned gt = (unsigned)((s->nt + 7) / 8);
+            if (s->dtype == SFH_F64)
+                sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->ld, s->rows, s->nt, c->d_residual, 1.0, d_out + 1);
+            else
+                sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->ld, s->rows, s->nt, c->d_residual, 1.0, d_out + 1);
+            CU_TRY(cudaGetLastError());
+            c->stats.kernel_launches += 2;
+        }
+        if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
+    }
+    if (c->comm) {
+        const size_t cnt = want_G ? (size_t)(1 + s->nt) : 1;
+        int r = g_nccl.AllReduce(d_out, d_out, cnt, kNcclFloat64, kNcclSum, c->comm, c->stream);
+        if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    c->stats.evals++;
+    return SFH_OK;
+}
+
+inline double guard_neg_logl(double logL) {  // fitting_base.jl:95 then the sign flip of solvers.jl:31
+    return (logL != 0.0) ? -logL : std::numeric_limits<double>::infinity();
+}
+}  // namespace
+
+extern "C" int sfh_enqueue_fg(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G) {
+    if (!c || !d_coeffs || !d_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(c->s->device));
+    return enqueue_fg_impl(c, d_coeffs, d_out, want_G, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// core path, host-synchronous
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, double *G, double *composite_out) {
+    if (!c || !coeffs) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    const int want_G = G != nullptr;
+    memcpy(c->h_in, coeffs, (size_t)s->nt * 8);
+    CU_TRY(cudaMemcpyAsync(c->d_coeffs, c->h_in, (size_t)s->nt * 8, cudaMemcpyHostToDevice, c->stream));
+    SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false));
+    const size_t n_out = want_G ? (size_t)(1 + s->nt) : 1;
+    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (neg_logL) *neg_logL = guard_neg_logl(c->h_out[0]);
+    if (G) memcpy(G, c->h_out + 1, (size_t)s->nt * 8);
+    if (composite_out && s->rows > 0) {
+        // what the reference leaves in `composite`: the residual after grad-loglikelihood! (fitting_base.jl:219)
+        CU_TRY(cudaMemcpy(composite_out, want_G ? c->d_residual : c->d_composite, (size_t)s->rows * 8,
+                          cudaMemcpyDeviceToHost));
+    }
+    return SFH_OK;
+}
+
+extern "C" int sfh_composite(sfh_ctx *c, const double *coeffs, double *composite_out) {
+    if (!c || !coeffs || !composite_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    SFH_TRY(sfh_eval_fg(c, coeffs, nullptr, nullptr, composite_out));
+    return SFH_OK;
+}
+
+extern "C" int sfh_loglikelihood_coeffs(sfh_ctx *c, const double *coeffs, double *logL) {
+    if (!c || !coeffs || !logL) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    double nl = 0.0;
+    SFH_TRY(sfh_eval_fg(c, coeffs, &nl, nullptr, nullptr));
+    *logL = -nl;
+    return SFH_OK;
+}
+
+extern "C" int sfh_loglikelihood(sfh_ctx *c, const double *composite, double *logL) {
+    if (!c || !composite || !logL) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    if (s->rows > 0) {
+        memcpy(c->h_in, composite, (size_t)s->rows * 8);
+        CU_TRY(cudaMemcpyAsync(c->d_composite, c->h_in, (size_t)s->rows * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    SFH_TRY(launch_finalize(c, c->d_composite, c->d_out, 0));
+    if (c->comm) {
+        int r = g_nccl.AllReduce(c->d_out, c->d_out, 1, kNcclFloat64, kNcclSum, c->comm, c->stream);
+        if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
+    }
+    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *logL = -guard_neg_logl(c->h_out[0]);
+    return SFH_OK;
+}
+
+extern "C" int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, double *G) {
+    if (!c || !composite_inout || !G) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    if (s->rows > 0) {
+        memcpy(c->h_in, composite_inout, (size_t)s->rows * 8);
+        CU_TRY(cudaMemcpyAsync(c->d_residual, c->h_in, (size_t)s->rows * 8, cudaMemcpyHostToDevice, c->stream));
+        sfh_residual_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, c->stream>>>(c->d_residual, s->d_data, s->rows, s->eps);
+        CU_TRY(cudaGetLastError());
+    }
+    if (s->nt > 0) {
+        const unsigned gt = (unsigned)((s->nt + 7) / 8);
+        if (s->dtype == SFH_F64)
+            sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->ld, s->rows, s->nt, c->d_residual, -1.0, c->d_out + 1);
+        else
+            sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->ld, s->rows, s->nt, c->d_residual, -1.0, c->d_out + 1);
+        CU_TRY(cudaGetLastError());
+        c->stats.kernel_launches += 2;
+        if (c->comm) {
+            int r = g_nccl.AllReduce(c->d_out + 1, c->d_out + 1, (size_t)s->nt, kNcclFloat64, kNcclSum, c->comm, c->stream);
+            if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
+        }
+        CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out + 1, (size_t)s->nt * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (s->nt > 0) memcpy(G, c->h_out, (size_t)s->nt * 8);
+    if (s->rows > 0) CU_TRY(cudaMemcpy(composite_inout, c->d_residual, (size_t)s->rows * 8, cudaMemcpyDeviceToHost));
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hierarchical path
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_hier_bind(sfh_ctx *c, const double *logAge, const double *MH, int64_t *n_ages_out) {
+    if (!c || !logAge || !MH) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    const int64_t nt = s->nt;
+    // unique(logAge) in first-appearance order, jidx, jidx_inv  (mzr.jl:54,138-140)
+    std::vector<double> uniq;
+    std::vector<int32_t> jidx((size_t)nt);
+    for (int64_t t = 0; t < nt; ++t) {
+        int32_t f = -1;
+        for (size_t j = 0; j < uniq.size(); ++j)
+            if (uniq[j] == logAge[t]) { f = (int32_t)j; break; }
+        if (f < 0) { uniq.push_back(logAge[t]); f = (int32_t)uniq.size() - 1; }
+        jidx[(size_t)t] = f;
+    }
+    const int32_t nj = (int32_t)uniq.size();
+    std::vector<int32_t> gptr((size_t)nj + 1, 0), gmem((size_t)nt), sidx((size_t)nj);
+    for (int64_t t = 0; t < nt; ++t) gptr[(size_t)jidx[(size_t)t] + 1]++;
+    for (int32_t j = 0; j < nj; ++j) gptr[(size_t)j + 1] += gptr[(size_t)j];
+    {
+        std::vector<int32_t> fill(gptr.begin(), gptr.end() - 1);
+        for (int64_t t = 0; t < nt; ++t) gmem[(size_t)fill[(size_t)jidx[(size_t)t]]++] = (int32_t)t;
+    }
+    for (int32_t j = 0; j < nj; ++j) sidx[(size_t)j] = j;  // sortperm(unique_logAge; rev=true), stable (mzr.jl:61)
+    std::stable_sort(sidx.begin(), sidx.end(), [&](int32_t a, int32_t b) { return uniq[(size_t)a] > uniq[(size_t)b]; });
+
+    cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
+    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx);
+    c->d_logAge_u = c->d_MH = c->d_vars = c->d_hscratch = c->d_Ajk = c->d_outh = nullptr;
+    c->d_jidx = c->d_gptr = c->d_gmem = c->d_sidx = nullptr;
+    c->bound = false;
+    const size_t njp = (size_t)std::max(nj, 1), ntp = (size_t)std::max<int64_t>(nt, 1);
+    CU_TRY(cudaMalloc((void **)&c->d_logAge_u, njp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_MH, ntp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_vars, (njp + 3) * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_hscratch, 10 * njp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_Ajk, ntp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_outh, (njp + 4) * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_jidx, ntp * 4));
+    CU_TRY(cudaMalloc((void **)&c->d_gptr, (njp + 1) * 4));
+    CU_TRY(cudaMalloc((void **)&c->d_gmem, ntp * 4));
+    CU_TRY(cudaMalloc((void **)&c->d_sidx, njp * 4));
+    if (nt > 0) {
+        CU_TRY(cudaMemcpy(c->d_logAge_u, uniq.data(), (size_t)nj * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_MH, MH, (size_t)nt * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_jidx, jidx.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_gptr, gptr.data(), ((size_t)nj + 1) * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_gmem, gmem.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_sidx, sidx.data(), (size_t)nj * 4, cudaMemcpyHostToDevice));
+    }
+    if ((size_t)nj + 8 > c->h_in_n || (size_t)nj + 8 > c->h_out_n) return fail(SFH_ERR_SHAPE, "more ages than templates?");
+    c->nj = nj;
+    c->bound = true;
+    if (n_ages_out) *n_ages_out = nj;
+    return SFH_OK;
+}
+
+namespace {
+int fill_hier_params(sfh_ctx *c, HierParams &hp, int mh_kind, const double *mh_fixed, int disp_kind,
+                     const uint8_t *free_mask) {
+    if (!c->bound) return fail(SFH_ERR_NOT_BOUND, "call sfh_hier_bind(logAge, MH) first");
+    if (mh_kind < SFH_MH_POWERLAW_MZR || mh_kind > SFH_MH_LOG_AMR) return fail(SFH_ERR_INVALID_ARG, "bad mh_kind %d", mh_kind);
+    if (disp_kind != SFH_DISP_GAUSSIAN) return fail(SFH_ERR_INVALID_ARG, "bad disp_kind %d", disp_kind);
+    if (!mh_fixed) return fail(SFH_ERR_INVALID_ARG, "mh_fixed is NULL");
+    memset(&hp, 0, sizeof hp);
+    hp.kind = mh_kind; hp.nj = c->nj; hp.nt = c->s->nt;
+    const int nfix = (mh_kind == SFH_MH_LOG_AMR) ? 4 : 1;
+    for (int i = 0; i < nfix; ++i) hp.fixed[i] = mh_fixed[i];
+    for (int i = 0; i < 3; ++i) hp.free_mask[i] = free_mask ? free_mask[i] : 1;
+    const size_t nj = (size_t)std::max(c->nj, 1);
+    hp.variables = c->d_vars; hp.logAge_u = c->d_logAge_u; hp.MH = c->d_MH; hp.jidx = c->d_jidx; hp.gptr = c->d_gptr;
+    hp.gmem = c->d_gmem; hp.sidx = c->d_sidx;
+    hp.mu = c->d_hscratch; hp.gA = hp.mu + nj; hp.gB = hp.gA + nj; hp.gM = hp.gB + nj; hp.Asum = hp.gM + nj;
+    hp.cum = hp.Asum + nj; hp.tmpj = hp.cum + nj;
+    hp.Ajk = c->d_Ajk; hp.coeffs = c->d_coeffs; hp.fg_out = c->d_out; hp.out = c->d_outh;
+    return SFH_OK;
+}
+}  // namespace
+
+extern "C" int sfh_calculate_coeffs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind,
+                                    const double *variables, double *coeffs_out) {
+    if (!c || !variables || !coeffs_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(c->s->device));
+    HierParams hp;
+    SFH_TRY(fill_hier_params(c, hp, mh_kind, mh_fixed, disp_kind, nullptr));
+    const size_t nv = (size_t)c->nj + 3;
+    memcpy(c->h_in, variables, nv * 8);
+    CU_TRY(cudaMemcpyAsync(c->d_vars, c->h_in, nv * 8, cudaMemcpyHostToDevice, c->stream));
+    sfh_hier_prologue_kernel<<<1, kHierThreads, 0, c->stream>>>(hp);
+    CU_TRY(cudaGetLastError());
+    c->stats.kernel_launches++;
+    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_coeffs, (size_t)c->s->nt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(coeffs_out, c->h_out, (size_t)c->s->nt * 8);
+    return SFH_OK;
+}
+
+extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *variables,
+                                const uint8_t *free_mask, double *neg_logL, double *G) {
+    if (!c || !variables) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(c->s->device));
+    HierParams hp;
+    SFH_TRY(fill_hier_params(c, hp, mh_kind, mh_fixed, disp_kind, free_mask));
+    const int want_G = G != nullptr;
+    const size_t nv = (size_t)c->nj + 3;
+    memcpy(c->h_in, variables, nv * 8);
+    CU_TRY(cudaMemcpyAsync(c->d_vars, c->h_in, nv * 8, cudaMemcpyHostToDevice, c->stream));
+    sfh_hier_prologue_kernel<<<1, kHierThreads, 0, c->stream>>>(hp);
+    CU_TRY(cudaGetLastError());
+    SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false));
+    sfh_hier_epilogue_kernel<<<1, kHierThreads, 0, c->stream>>>(hp, want_G);
+    CU_TRY(cudaGetLastError());
+    c->stats.kernel_launches += 2;
+    const size_t n_out = want_G ? 1 + nv : 1;
+    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_outh, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (neg_logL) *neg_logL = c->h_out[0];
+    if (G) memcpy(G, c->h_out + 1, nv * 8);
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched walkers
+// ---------------------------------------------------------------------------------------------
+namespace {
+int ensure_walker_capacity(sfh_ctx *c, int64_t W) {
+    if (W <= c->wcap) return SFH_OK;
+    const sfh_stack *s = c->s;
+    cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
+    c->d_X = c->d_Xt = c->d_part = c->d_logl = nullptr; c->d_neg = nullptr; c->wcap = 0;
+    const int64_t wld = round_up(W, 16);
+    const int64_t nbt = std::max<int64_t>((s->rows + kBwBM - 1) / kBwBM, 1);
+    const size_t nt = (size_t)std::max<int64_t>(s->nt, 1);
+    CU_TRY(cudaMalloc((void **)&c->d_X, nt * (size_t)W * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_Xt, nt * (size_t)wld * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_part, (size_t)nbt * (size_t)wld * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_logl, (size_t)wld * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_neg, (size_t)wld * 4));
+    c->wcap = W; c->wld = wld;
+    return SFH_OK;
+}
+
+int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_logl) {
+    sfh_stack *s = c->s;
+    const int64_t wld = c->wld;
+    const unsigned gw = (unsigned)((W + 7) / 8);
+    sfh_walker_prep_kernel<<<gw, 256, 0, c->stream>>>(d_X, s->nt, W, wld, c->d_Xt, c->d_neg);
+    CU_TRY(cudaGetLastError());
+    const int64_t nbt = (s->rows + kBwBM - 1) / kBwBM, nwt = (W + kBwBN - 1) / kBwBN;
+    BatchedParams bp{};
+    bp.nb = s->rows; bp.nt = s->nt; bp.W = W; bp.ld = s->ld; bp.wld = wld; bp.eps = s->eps; bp.Xt = c->d_Xt;
+    bp.data = s->d_data; bp.part = c->d_part;
+    if (nbt > 0) {
+        if (s->dtype == SFH_F64)
+            sfh_batched_logl_kernel<double><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const double *)s->dM, bp);
+        else
+            sfh_batched_logl_kernel<float><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const float *)s->dM, bp);
+        CU_TRY(cudaGetLastError());
+    }
+    sfh_batched_reduce_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c->stream>>>(c->d_part, nbt, W, wld, d_logl);
+    CU_TRY(cudaGetLastError());
+    if (c->comm) {
+        int r = g_nccl.AllReduce(d_logl, d_logl, (size_t)W, kNcclFloat64, kNcclSum, c->comm, c->stream);
+        if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
+    }
+    sfh_batched_guard_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c->stream>>>(d_logl, c->d_neg, W);
+    CU_TRY(cudaGetLastError());
+    c->stats.kernel_launches += 4;
+    c->stats.evals += W;
+    return SFH_OK;
+}
+}  // namespace
+
+extern "C" int sfh_enqueue_logl_batched(sfh_ctx *c, const double *d_X, int64_t W, double *d_logL) {
+    if (!c || !d_X || !d_logL || W <= 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(c->s->device));
+    SFH_TRY(ensure_walker_capacity(c, W));
+    return enqueue_batched_impl(c, d_X, W, d_logL);
+}
+
+extern "C" int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL) {
+    if (!c || !X || !logL || W < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (W == 0) return SFH_OK;
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    SFH_TRY(ensure_walker_capacity(c, W));
+    CU_TRY(cudaMemcpyAsync(c->d_X, X, (size_t)s->nt * (size_t)W * 8, cudaMemcpyHostToDevice, c->stream));
+    SFH_TRY(enqueue_batched_impl(c, c->d_X, W, c->d_logl));
+    CU_TRY(cudaMemcpyAsync(logL, c->d_logl, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_comm_unique_id(void *id128) {
+    if (!id128) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    if (!load_nccl()) return fail(SFH_ERR_NCCL, "libnccl.so.2 not found");
+    NcclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(SFH_ERR_NCCL, "ncclGetUniqueId failed (%d)", r);
+    memcpy(id128, &id, 128);
+    return SFH_OK;
+}
+
+extern "C" int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (!load_nccl()) return fail(SFH_ERR_NCCL, "libnccl.so.2 not found");
+    CU_TRY(cudaSetDevice(c->s->device));
+    NcclUniqueId id;
+    memcpy(&id, id128, 128);
+    int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) {
+        c->comm = nullptr;
+        return fail(SFH_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    c->nranks = nranks;
+    c->rank = rank;
+    return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic stacks + device-timed loop (bench plumbing)
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_t ntemplates, int dtype, uint64_t seed,
+                                          double scale, const double *x_true, const sfh_opts *opts) {
+    if (!out || !x_true) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    sfh_stack *s = new (std::nothrow) sfh_stack();
+    if (!s) return fail(SFH_ERR_OOM, "host allocation failed");
+    int st = stack_common_init(s, nbins, ntemplates, dtype, opts);
+    auto done = [&](int code) { if (code != SFH_OK) sfh_stack_destroy(s); else *out = s; return code; };
+    if (st != SFH_OK) return done(st);
+    if (s->rows > 0 && s->nt > 0) {
+        cudaError_t e = cudaMemset(s->dM, 0, (size_t)s->ld * s->nt * elem_size(dtype));
+        if (e != cudaSuccess) return done(fail(SFH_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
+        const int grid = s->sm_count * 16;
+        if (dtype == SFH_F64)
+            sfh_fill_uniform_kernel<double><<<grid, 256>>>((double *)s->dM, s->ld, s->rows, s->nt, s->row_begin, nbins, seed, scale);
+        else
+            sfh_fill_uniform_kernel<float><<<grid, 256>>>((float *)s->dM, s->ld, s->rows, s->nt, s->row_begin, nbins, seed, scale);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return done(fail(SFH_ERR_CUDA, "fill: %s", cudaGetErrorString(e)));
+    }
+    st = setup_fused(s, opts);
+    if (st != SFH_OK) return done(st);
+    // data ~ Poisson(M x_true): composite through the production kernels, then sample
+    sfh_ctx *c = nullptr;
+    st = sfh_ctx_create(s, nullptr, &c);
+    if (st != SFH_OK) return done(st);
+    st = [&]() -> int {
+        if (s->rows == 0 || s->nt == 0) return SFH_OK;
+        CU_TRY(cudaMemcpy(c->d_coeffs, x_true, (size_t)s->nt * 8, cudaMemcpyHostToDevice));
+        SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, 0, false));
+        sfh_poisson_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, c->stream>>>(c->d_composite, s->d_data, s->rows,
+                                                                                     s->row_begin, seed ^ 0x9E3779B97F4A7C15ull);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (dtype == SFH_F32) {  // an F32 fit stores its data in F32 too: counts above 2^24 would round
+            // (Poisson counts are integers; they are exactly representable well beyond any realistic Hess bin)
+        }
+        return SFH_OK;
+    }();
+    sfh_ctx_destroy(c);
+    return done(st);
+}
+
+extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,
+                           double *ms_kernel_out) {
+    if (!c || !coeffs || reps < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaMemcpy(c->d_coeffs, coeffs, (size_t)s->nt * 8, cudaMemcpyHostToDevice));
+    if (flush_l2 && !c->d_flush) {
+        c->flush_n4 = (int64_t)(std::max<size_t>(s->l2_bytes, (size_t)128 << 20) * 2 / 16);
+        CU_TRY(cudaMalloc((void **)&c->d_flush, (size_t)c->flush_n4 * 16));
+    }
+    double tot = 0.0, totk = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        if (flush_l2) sfh_l2_flush_kernel<<<s->sm_count * 8, 256, 0, c->stream>>>(c->d_flush, c->flush_n4);
+        CU_TRY(cudaEventRecord(c->ev0, c->stream));
+        SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, true));
+        CU_TRY(cudaEventRecord(c->ev1, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0.f, msk = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        CU_TRY(cudaEventElapsedTime(&msk, c->evk0, c->evk1));
+        tot += ms;
+        totk += msk;
+    }
+    c->stats.last_device_ms = tot / reps;
+    if (ms_per_eval_out) *ms_per_eval_out = tot / reps;
+    if (ms_kernel_out) *ms_kernel_out = totk / reps;
+    return SFH_OK;
+}

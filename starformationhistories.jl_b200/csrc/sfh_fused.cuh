@@ -1,0 +1,292 @@
+// sfh_fused.cuh -- K4: the fused composite -> residual -> transposed-gradient kernel (sm_100a).
+//
+// Replaces, in ONE pass over the template stack, the reference's
+//     composite!            src/fitting/fitting_base.jl:55-65   (gemv 'N', reads M)
+//     grad-loglikelihood!   src/fitting/fitting_base.jl:265-285 (residual + gemv 'T', reads M again)
+// as sequenced by fg! (src/fitting/solvers.jl:20-38).  The O(Nb) Poisson term of
+// loglikelihood (fitting_base.jl:84-96) is evaluated by the finalize kernel from the composite
+// vector this kernel writes (sfh_small.cuh).
+//
+// Decomposition
+//   stack M: column-major Nb x T, leading dimension ld (stack_models layout, padded).
+//   tile      = BT consecutive bins x ALL T templates; owned by one thread-block CLUSTER.
+//   CTA q of the cluster holds templates [q*KT*RPC, (q+1)*KT*RPC) of the tile in shared memory,
+//   brought in by TMA as KT chunks (boxes of BT bins x RPC templates = 8 KB each) through an
+//   mbarrier ring of R slots that is deeper than one tile, so the next tile streams in while this
+//   one is being used.
+//   pass A   every consumer lane owns 16 B of each chunk (VEC bins of one template) and FMAs it
+//            into its composite partials;  warp shuffles + one smem stage give the CTA partial;
+//            the C CTA partials are exchanged through DSMEM with st.async (data + mbarrier
+//            complete_tx in one op) and summed in fixed rank order -> every CTA holds bit-identical m.
+//   residual r = 1 - n/max(m,eps)  (fitting_base.jl:277-279)
+//   pass B   the same lanes re-read the same 16 B from SHARED memory (not HBM, not L2) and
+//            accumulate M*r into per-lane gradient partials that live in registers across ALL tiles
+//            of the CTA; slots are released to the TMA producer as pass B walks them.
+//   end      lanes sharing a template combine by shuffle; one plain store per (cluster, template)
+//            into gpart[n_clusters][T].  No atomics anywhere => bitwise run-to-run determinism.
+#pragma once
+#include "sfh_ptx.cuh"
+
+namespace sfh {
+
+constexpr int kConsumerWarps = 16;
+constexpr int kConsumerThreads = kConsumerWarps * 32;  // 512
+constexpr int kFusedThreads = kConsumerThreads + 32;   // + 1 TMA producer warp
+constexpr int kChunkBytes = kConsumerThreads * 16;     // 8192: one 16-byte vector per consumer lane
+constexpr int kKMax = 20;                              // max chunks per CTA per tile (register arrays)
+constexpr int kMaxCluster = 16;
+
+struct FusedParams {
+    int64_t nb;          // bins in this shard
+    int64_t nt;          // templates
+    int32_t kt;          // chunks per CTA per tile (<= kKMax)
+    int32_t ring;        // ring slots (>= kt + 1)
+    int32_t n_tiles;     // ceil(nb / BT)
+    int32_t evict_first; // use an L2 evict_first policy on the stack loads
+    double eps;          // clamp (fitting_base.jl:90,277)
+    const double *coeffs;   // [nt]
+    const double *data;     // [nb] (converted to double at upload)
+    double *composite;      // [nb] out: M*coeffs (unclamped)
+    double *residual;       // [nb] out (nullable): 1 - n/max(m,eps)
+    double *gpart;          // [n_clusters][gstride] out
+    int64_t gstride;
+};
+
+template <typename S, int BT>
+struct FusedCfg {
+    static constexpr int VEC = 16 / sizeof(S);  // elements per 16-byte lane vector
+    static constexpr int LPR = BT / VEC;        // lanes per template row
+    static constexpr int RPW = 32 / LPR;        // template rows per warp per chunk
+    static constexpr int RPC = RPW * kConsumerWarps;  // template rows per chunk
+    static_assert(BT % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "bad tile");
+    static_assert(RPC * BT * sizeof(S) == kChunkBytes, "chunk must be 8 KB");
+    static_assert(RPC <= 256, "TMA box dimension limit");
+};
+
+// dynamic shared memory carve-up (bytes), shared by host and device
+struct FusedSmem {
+    uint32_t ring_off, red_off, xbuf_off, rbuf_off, cs_off, bar_off, total;
+    // cs_elems = kt * RPC: this CTA's slice of the coefficient vector (kept in smem, not registers:
+    // 17 warps put 5 warps on one SM sub-partition => 96 registers/thread, too few for c[] + gacc[])
+    __host__ __device__ static FusedSmem make(int ring, int bt, int cluster, int cs_elems) {
+        FusedSmem s;
+        s.ring_off = 0;
+        s.red_off = ring * kChunkBytes;
+        s.xbuf_off = s.red_off + kConsumerWarps * bt * 8;
+        s.rbuf_off = s.xbuf_off + 2 * cluster * bt * 8;
+        s.cs_off = s.rbuf_off + bt * 8;
+        s.bar_off = s.cs_off + cs_elems * 8;
+        s.total = s.bar_off + (2 * ring + 2) * 8;
+        return s;
+    }
+};
+
+template <typename S>
+__device__ __forceinline__ void unpack(const vec16 &v, double (&out)[16 / sizeof(S)]);
+template <>
+__device__ __forceinline__ void unpack<double>(const vec16 &v, double (&out)[2]) {
+    out[0] = __hiloint2double(v.y, v.x);
+    out[1] = __hiloint2double(v.w, v.z);
+}
+template <>
+__device__ __forceinline__ void unpack<float>(const vec16 &v, double (&out)[4]) {
+    out[0] = (double)__uint_as_float(v.x);
+    out[1] = (double)__uint_as_float(v.y);
+    out[2] = (double)__uint_as_float(v.z);
+    out[3] = (double)__uint_as_float(v.w);
+}
+
+template <typename S, int BT, bool WANT_G>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+    using Cfg = FusedCfg<S, BT>;
+    constexpr int VEC = Cfg::VEC, LPR = Cfg::LPR, RPW = Cfg::RPW, RPC = Cfg::RPC;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t q = cluster_ctarank();
+    const uint32_t C = cluster_nctarank();
+    const uint32_t cl = cluster_id_x();
+    const uint32_t ncl = cluster_nid_x();
+    const int R = p.ring, kt = p.kt;
+    const FusedSmem L = FusedSmem::make(R, BT, (int)C, kt * RPC);
+
+    double *red = reinterpret_cast<double *>(smem + L.red_off);    // [16][BT]
+    double *xbuf = reinterpret_cast<double *>(smem + L.xbuf_off);  // [2][C][BT]
+    double *rbuf = reinterpret_cast<double *>(smem + L.rbuf_off);  // [BT]
+    double *cs = reinterpret_cast<double *>(smem + L.cs_off);      // [kt*RPC]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bar_off);
+    uint64_t *empty = full + R;
+    uint64_t *xbar = empty + R;  // [2]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < R; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kConsumerWarps);
+        }
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == kConsumerWarps && lane == 0) prefetch_tensormap(&tmap);
+    for (int i = tid; i < kt * RPC; i += kFusedThreads) {
+        const int64_t j = (int64_t)q * kt * RPC + i;
+        cs[i] = (j < p.nt) ? __ldg(p.coeffs + j) : 0.0;
+    }
+    __syncthreads();
+    // every CTA's barriers must be initialised before any peer signals them
+    cluster_arrive();
+    cluster_wait();
+
+    if (warp == kConsumerWarps) {
+        // ================= TMA producer (one elected lane) =================
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            int slot = 0;
+            uint32_t round = 0;  // how many times the ring has wrapped
+            const int32_t t0 = (int32_t)(q * (uint32_t)(kt * RPC));
+            for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl) {
+                for (int k = 0; k < kt; ++k) {
+                    if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1u);
+                    mbar_arrive_expect_tx(&full[slot], kChunkBytes);
+                    void *dst = smem + L.ring_off + (uint32_t)slot * kChunkBytes;
+                    if (p.evict_first)
+                        tma_load_2d_hint(dst, &tmap, tile * BT, t0 + k * RPC, &full[slot], pol);
+                    else
+                        tma_load_2d(dst, &tmap, tile * BT, t0 + k * RPC, &full[slot]);
+                    if (++slot == R) { slot = 0; ++round; }
+                }
+            }
+        }
+    } else {
+        // ================= consumers: 16 warps, one 16-byte vector per lane per chunk =========
+        const int bl = lane % LPR;  // which VEC-bin group of the tile this lane owns
+        const int rw = lane / LPR;  // which template row of the warp's RPW rows
+        const uint32_t lane_off = (uint32_t)tid * 16u;
+        const uint32_t ring_base = smem_u32(smem + L.ring_off);
+
+        // the lane's templates: j(k) = q*kt*RPC + k*RPC + warp*RPW + rw  (fixed for the whole kernel)
+        const int64_t j0 = (int64_t)q * kt * RPC + warp * RPW + rw;
+        const double *cs_lane = cs + warp * RPW + rw;  // + k*RPC
+        double gacc[kKMax];
+#pragma unroll
+        for (int k = 0; k < kKMax; ++k) gacc[k] = 0.0;
+
+        int slot = 0;
+        uint32_t phase = 0;
+        uint32_t it = 0;
+        for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl, ++it) {
+            const uint32_t par = it & 1u;
+            const int slotA = slot;
+
+            // ---- pass A: composite partials for this lane's VEC bins over its templates ----
+            double acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
+#pragma unroll
+            for (int k = 0; k < kKMax; ++k) {
+                if (k < kt) {
+                    mbar_wait(&full[slot], phase);
+                    const vec16 v = lds128(ring_base + (uint32_t)slot * kChunkBytes + lane_off);
+                    const double ck = cs_lane[k * RPC];
+                    double m[VEC];
+                    unpack<S>(v, m);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[e] = fma(m[e], ck, acc[e]);
+                    if (!WANT_G) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[slot]);
+                    }
+                    if (++slot == R) { slot = 0; phase ^= 1u; }
+                }
+            }
+            // lanes that own the same bins (different rows) combine
+#pragma unroll
+            for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+            }
+            if (rw == 0) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) red[warp * BT + bl * VEC + e] = acc[e];
+            }
+            named_bar_sync<1, kConsumerThreads>();
+
+            // ---- exchange: CTA partial -> all CTAs of the cluster; fixed-order sum; residual ----
+            if (warp * 32 < BT) {
+                const bool active = tid < BT;
+                if (active) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kConsumerWarps; ++w) s += red[w * BT + tid];
+                    if (tid == 0) mbar_arrive_expect_tx(&xbar[par], C * BT * 8u);
+                    const uint32_t my_slot = smem_u32(&xbuf[(par * C + q) * BT + tid]);
+                    const uint32_t my_bar = smem_u32(&xbar[par]);
+                    for (uint32_t d = 0; d < C; ++d) st_async_f64(mapa(my_slot, d), s, mapa(my_bar, d));
+                }
+                mbar_wait_cluster(&xbar[par], (it >> 1) & 1u);
+                if (active) {
+                    double m = 0.0;
+                    for (uint32_t d = 0; d < C; ++d) m += xbuf[(par * C + d) * BT + tid];
+                    const int64_t bin = (int64_t)tile * BT + tid;
+                    double r = 0.0;
+                    if (bin < p.nb) {
+                        const double n = __ldg(p.data + bin);
+                        const double mc = (m < p.eps) ? p.eps : m;  // NaN-propagating max
+                        r = 1.0 - n / mc;
+                        if (q == 0) {
+                            p.composite[bin] = m;
+                            if (p.residual) p.residual[bin] = r;
+                        }
+                    }
+                    rbuf[tid] = r;
+                }
+            }
+            named_bar_sync<1, kConsumerThreads>();
+
+            // ---- pass B: gradient partials from the SAME shared-memory bytes ----
+            if (WANT_G) {
+                double r[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) r[e] = rbuf[bl * VEC + e];
+                int sb = slotA;
+#pragma unroll
+                for (int k = 0; k < kKMax; ++k) {
+                    if (k < kt) {
+                        const vec16 v = lds128(ring_base + (uint32_t)sb * kChunkBytes + lane_off);
+                        double m[VEC];
+                        unpack<S>(v, m);
+                        double g = gacc[k];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) g = fma(m[e], r[e], g);
+                        gacc[k] = g;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[sb]);
+                        if (++sb == R) sb = 0;
+                    }
+                }
+            }
+        }
+
+        // ---- end of kernel: one store per (cluster, template) ----
+        if (WANT_G) {
+#pragma unroll
+            for (int k = 0; k < kKMax; ++k) {
+                if (k < kt) {
+                    double g = gacc[k];
+#pragma unroll
+                    for (int off = 1; off < LPR; off <<= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
+                    const int64_t j = j0 + (int64_t)k * RPC;
+                    if (bl == 0 && j < p.nt) p.gpart[(int64_t)cl * p.gstride + j] = g;
+                }
+            }
+        }
+    }
+    // no CTA may exit while a peer can still address its shared memory
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+}
+
+}  // namespace sfh

@@ -1,0 +1,417 @@
+// sfh_small.cuh -- the O(Nb) / O(T) kernels around K4, the two-pass (unfused) kernels that give
+// signature-level parity for direct calls of composite! / loglikelihood / grad-loglikelihood!,
+// and the on-device synthetic generators used by the large benchmark configurations.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sfh {
+
+// ------------------------------------------------------------------------------------------
+// deterministic block reduction (fixed shuffle tree + fixed smem order)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *sh /*[NT/32]*/) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        t = (lane < NT / 32) ? sh[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;  // valid in warp 0
+}
+
+// Poisson log-likelihood-ratio term, fitting_base.jl:90-92.  `ifelse` semantics: select.
+__device__ __forceinline__ double poisson_term(double m, double n, double eps) {
+    const double mc = (m < eps) ? eps : m;  // NaN propagates like Julia's scalar max
+    return (n > 0.0) ? (n - mc - n * log(n / mc)) : -mc;
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: logL = sum_i term(m_i, n_i)   (loglikelihood, fitting_base.jl:84-96, raw sum: the
+// `== 0 -> -Inf` guard of :95 is applied by the caller AFTER any cross-GPU all-reduce)
+// and G_j = sum over clusters of gpart[cl][j].  out = [logL, G_0..G_{T-1}].
+// ------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    int64_t nb, nt, gstride;
+    int32_t n_clusters, want_G;
+    double eps;
+    const double *composite, *data, *gpart;
+    double *out;
+    double *lpart;       // [gridDim.x]
+    unsigned int *ticket;
+};
+constexpr int kFinalizeThreads = 256;
+
+__global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
+    __shared__ double sh[kFinalizeThreads / 32];
+    __shared__ bool last;
+    // fixed contiguous slice of bins per block -> deterministic partials
+    const int64_t per = (p.nb + gridDim.x - 1) / gridDim.x;
+    const int64_t b0 = (int64_t)blockIdx.x * per;
+    const int64_t b1 = (b0 + per < p.nb) ? b0 + per : p.nb;
+    double acc = 0.0;
+    for (int64_t i = b0 + threadIdx.x; i < b1; i += kFinalizeThreads)
+        acc += poisson_term(p.composite[i], p.data[i], p.eps);
+    const double tot = block_sum<kFinalizeThreads>(acc, sh);
+    if (threadIdx.x == 0) p.lpart[blockIdx.x] = tot;
+
+    if (p.want_G) {
+        for (int64_t j = (int64_t)blockIdx.x * kFinalizeThreads + threadIdx.x; j < p.nt;
+             j += (int64_t)gridDim.x * kFinalizeThreads) {
+            double g = 0.0;
+            for (int cl = 0; cl < p.n_clusters; ++cl) g += p.gpart[(int64_t)cl * p.gstride + j];
+            p.out[1 + j] = g;
+        }
+    }
+    // last block folds the per-block logL partials in fixed order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile double *)p.lpart)[b];
+            p.out[0] = s;
+            *p.ticket = 0u;  // re-arm for the next evaluation on this context
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// two-pass kernels (unfused API + fallback when the fused tiling cannot hold T)
+// ------------------------------------------------------------------------------------------
+// composite!  C = M * coeffs   (fitting_base.jl:55-65): block = 128 bins x 4 template slices
+template <typename S>
+__global__ void __launch_bounds__(512) sfh_composite_kernel(const S *__restrict__ M, int64_t ld, int64_t nb, int64_t nt,
+                                                            const double *__restrict__ coeffs,
+                                                            double *__restrict__ out) {
+    __shared__ double sh[4][128];
+    const int bx = threadIdx.x & 127, sy = threadIdx.x >> 7;
+    const int64_t i = (int64_t)blockIdx.x * 128 + bx;
+    double acc = 0.0;
+    if (i < nb) {
+        const int64_t per = (nt + 3) / 4;
+        const int64_t j0 = sy * per, j1 = (j0 + per < nt) ? j0 + per : nt;
+        const S *col = M + i + j0 * ld;
+        int64_t j = j0;
+        for (; j + 7 < j1; j += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (double)col[(int64_t)u * ld];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fma(v[u], coeffs[j + u], acc);
+            col += 8 * ld;
+        }
+        for (; j < j1; ++j, col += ld) acc = fma((double)*col, coeffs[j], acc);
+    }
+    sh[sy][bx] = acc;
+    __syncthreads();
+    if (sy == 0 && i < nb) out[i] = (sh[0][bx] + sh[1][bx]) + (sh[2][bx] + sh[3][bx]);
+}
+
+// residual in place: C <- 1 - n/max(C,eps)   (fitting_base.jl:274-280)
+__global__ void sfh_residual_kernel(double *__restrict__ C, const double *__restrict__ data, int64_t nb, double eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb) {
+        const double m = C[i];
+        const double mc = (m < eps) ? eps : m;
+        C[i] = 1.0 - data[i] / mc;
+    }
+}
+
+// G_j = sign * sum_i M_ij r_i   (gemv 'T', fitting_base.jl:283): one warp per template
+template <typename S>
+__global__ void __launch_bounds__(256) sfh_gemvt_kernel(const S *__restrict__ M, int64_t ld, int64_t nb, int64_t nt,
+                                                        const double *__restrict__ r, double sign,
+                                                        double *__restrict__ G) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= nt) return;
+    const S *col = M + j * ld;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int64_t i = lane;
+    for (; i + 96 < nb; i += 128) {
+        const double v0 = (double)col[i], v1 = (double)col[i + 32], v2 = (double)col[i + 64], v3 = (double)col[i + 96];
+        a0 = fma(v0, r[i], a0);
+        a1 = fma(v1, r[i + 32], a1);
+        a2 = fma(v2, r[i + 64], a2);
+        a3 = fma(v3, r[i + 96], a3);
+    }
+    for (; i < nb; i += 32) a0 = fma((double)col[i], r[i], a0);
+    const double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) G[j] = sign * s;
+}
+
+// ------------------------------------------------------------------------------------------
+// hierarchical prologue / epilogue (K5).  One block; one warp per age group, members visited in
+// template order => deterministic.  Formulas cite src/fitting/hierarchical/{mzr,amr,dispersion_models}.jl
+// ------------------------------------------------------------------------------------------
+enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
+
+struct HierParams {
+    int32_t kind;      // sfh_mh_kind
+    int32_t nj;        // number of unique ages
+    int64_t nt;
+    double fixed[4];   // logMstar0 | T_max | T_max, solZ, Y_p, gamma
+    uint8_t free_mask[4];
+    const double *variables;  // [nj+3] device
+    const double *logAge_u;   // [nj] unique ages, first-appearance order
+    const double *MH;         // [nt]
+    const int32_t *jidx;      // [nt] template -> age
+    const int32_t *gptr;      // [nj+1] group offsets
+    const int32_t *gmem;      // [nt] group members (template indices, ascending inside a group)
+    const int32_t *sidx;      // [nj] sortperm(unique_logAge; rev=true)   mzr.jl:61
+    // scratch (device)
+    double *mu, *gA, *gB, *gM, *Asum, *cum;  // [nj]
+    double *Ajk;                             // [nt]
+    double *tmpj;                            // [4*nj]
+    double *coeffs;                          // [nt] out of the prologue
+    const double *fg_out;                    // [1+nt]: logL raw, +M'r  (input of the epilogue)
+    double *out;                             // [1 + nj + 3]: -logL (guarded), G
+};
+
+__device__ __forceinline__ double d_X_from_Z(double Z, double Yp, double gam) { return 1.0 - ((Yp + gam * Z) + Z); }
+
+// mean metallicity + gradient: PowerLawMZR mzr.jl:275-280; LinearAMR amr.jl:206-209;
+// LogarithmicAMR amr.jl:284-295 with MH_from_Z / dMH_dZ of src/utilities.jl:138-156
+__device__ __forceinline__ void d_mh_eval(int kind, double alpha, double beta, const double *fx, double arg, double &mu,
+                                          double &dA, double &dB, double &dM) {
+    if (kind == MH_POWERLAW_MZR) {
+        const double l = log10(arg) - fx[0];
+        mu = beta + alpha * l;
+        dA = l;
+        dB = 1.0;
+        dM = alpha / arg / 2.302585092994046;  // logten
+    } else {
+        const double age = exp10(arg - 9.0);
+        const double dt = fx[0] - age;
+        if (kind == MH_LINEAR_AMR) {
+            mu = beta + alpha * dt;
+            dA = dt;
+            dB = 1.0;
+            dM = 0.0;
+        } else {
+            const double Z = beta + alpha * dt;
+            const double solZ = fx[1], Yp = fx[2], gam = fx[3];
+            const double X = d_X_from_Z(Z, Yp, gam);
+            mu = (X > 0.0) ? log10(Z / (X * solZ) * d_X_from_Z(solZ, Yp, gam)) : __longlong_as_double(0x7ff8000000000000LL);
+            const double d = (Yp - 1.0) / (2.302585092994046 * Z * (Yp + Z + gam * Z - 1.0));
+            dA = d * dt;
+            dB = d;
+            dM = 0.0;
+        }
+    }
+}
+
+constexpr int kHierThreads = 1024;
+
+// calculate_coeffs: mzr.jl:50-79 / amr.jl:50-73
+__global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const HierParams p) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierThreads / 32;
+    const int nj = p.nj;
+    const double alpha = p.variables[nj], beta = p.variables[nj + 1], sigma = p.variables[nj + 2];
+    if (p.kind == MH_POWERLAW_MZR) {
+        if (tid == 0) {  // cumsum(R[s])[invperm(s)]  mzr.jl:66 -- oldest first
+            double run = 0.0;
+            for (int i = 0; i < nj; ++i) {
+                const int j = p.sidx[i];
+                run += p.variables[j];
+                p.cum[j] = run;
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < nj; j += kHierThreads) {
+        const double arg = (p.kind == MH_POWERLAW_MZR) ? p.cum[j] : p.logAge_u[j];
+        double mu, dA, dB, dM;
+        d_mh_eval(p.kind, alpha, beta, p.fixed, arg, mu, dA, dB, dM);
+        p.mu[j] = mu; p.gA[j] = dA; p.gB[j] = dB; p.gM[j] = dM;
+    }
+    __syncthreads();
+    for (int j = warp; j < nj; j += nw) {
+        const double mu = p.mu[j];
+        const int g0 = p.gptr[j], g1 = p.gptr[j + 1];
+        double a = 0.0;
+        for (int g = g0 + lane; g < g1; g += 32) {
+            const int t = p.gmem[g];
+            const double z = (p.MH[t] - mu) / sigma;
+            const double A = exp(-(z * z) / 2.0);  // dispersion_models.jl:92
+            p.Ajk[t] = A;
+            a += A;
+        }
+        a = warp_sum(a);
+        if (lane == 0) p.Asum[j] = a;
+        __syncwarp();
+        const double Rj = p.variables[j];
+        for (int g = g0 + lane; g < g1; g += 32) {
+            const int t = p.gmem[g];
+            p.coeffs[t] = p.Ajk[t] * Rj / a;  // mzr.jl:76
+        }
+    }
+}
+
+// chain rule: mzr.jl:124-210 / amr.jl:118-169.  fullG = d logL/d r = -(fg_out[1+t]).
+__global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const HierParams p, int want_G) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierThreads / 32;
+    const int nj = p.nj;
+    if (tid == 0) {
+        const double logL = p.fg_out[0];
+        p.out[0] = (logL != 0.0) ? -logL : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95
+    }
+    if (!want_G) return;
+    const double sigma = p.variables[nj + 2];
+    const double s2 = sigma * sigma, s3 = s2 * sigma;
+    double *ksumdr = p.tmpj, *same = p.tmpj + nj, *psum = p.tmpj + 2 * nj, *ssum = p.tmpj + 3 * nj;
+    for (int j = warp; j < nj; j += nw) {
+        const double mu = p.mu[j], Aj = p.Asum[j], Rj = p.variables[j], gM = p.gM[j];
+        const int g0 = p.gptr[j], g1 = p.gptr[j + 1];
+        double kAR = 0.0, kmu = 0.0, ksg = 0.0;
+        for (int g = g0 + lane; g < g1; g += 32) {
+            const int t = p.gmem[g];
+            const double A = p.Ajk[t], d = p.MH[t] - mu;
+            const double dAmu = A * d / s2;      // dispersion_models.jl:99
+            const double dAsg = A * d * d / s3;  // dispersion_models.jl:98
+            kAR += dAmu * gM;                    // mzr.jl:162,164
+            kmu += dAmu;
+            ksg += dAsg;
+        }
+        kAR = warp_sum(kAR); kmu = warp_sum(kmu); ksg = warp_sum(ksg);
+        double a_dr = 0.0, a_same = 0.0, a_p = 0.0, a_s = 0.0;
+        for (int g = g0 + lane; g < g1; g += 32) {
+            const int t = p.gmem[g];
+            const double A = p.Ajk[t], d = p.MH[t] - mu;
+            const double dAmu = A * d / s2, dAsg = A * d * d / s3;
+            const double fullG = -p.fg_out[1 + t];
+            const double RA = Rj / Aj;
+            if (p.kind == MH_POWERLAW_MZR) {
+                const double dAR = dAmu * gM;
+                a_dr += fullG * (RA * (dAR - (A * kAR / Aj)));                           // mzr.jl:166-167
+                a_same += fullG * (p.coeffs[t] / Rj + (dAR - (kAR * A / Aj)) * Rj / Aj);  // mzr.jl:188-190
+            } else {
+                a_same += fullG * p.coeffs[t] / Rj;                                      // amr.jl:141
+            }
+            a_p += fullG * RA * (dAmu - A / Aj * kmu);                                   // mzr.jl:194-195
+            a_s += fullG * RA * (dAsg - A / Aj * ksg);                                   // mzr.jl:206-207
+        }
+        a_dr = warp_sum(a_dr); a_same = warp_sum(a_same); a_p = warp_sum(a_p); a_s = warp_sum(a_s);
+        if (lane == 0) { ksumdr[j] = a_dr; same[j] = a_same; psum[j] = -a_p; ssum[j] = a_s; }
+    }
+    __syncthreads();
+    double *G = p.out + 1;
+    for (int j = tid; j < nj; j += kHierThreads) G[j] = -same[j];
+    __syncthreads();
+    if (tid == 0) {
+        if (p.kind == MH_POWERLAW_MZR) {
+            // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181
+            double run = 0.0;
+            for (int i = nj - 1; i >= 1; --i) {
+                run += ksumdr[p.sidx[i]];
+                G[p.sidx[i - 1]] -= run;
+            }
+        }
+        double ga = 0.0, gb = 0.0, gs = 0.0;
+        for (int j = 0; j < nj; ++j) {  // mzr.jl:196-198,201-208 in the reference's age order
+            ga += psum[j] * p.gA[j];
+            gb += psum[j] * p.gB[j];
+            gs -= ssum[j];
+        }
+        G[nj] = p.free_mask[0] ? ga : 0.0;
+        G[nj + 1] = p.free_mask[1] ? gb : 0.0;
+        G[nj + 2] = p.free_mask[2] ? gs : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic data on device: Philox4x32-10, counter = global linear element index
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ double philox_u01(uint64_t idx, uint64_t seed, uint32_t stream) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), stream, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
+    return (double)bits * (1.0 / 9007199254740992.0);  // [0,1)
+}
+
+template <typename S>
+__global__ void sfh_fill_uniform_kernel(S *M, int64_t ld, int64_t rows, int64_t nt, int64_t row_begin,
+                                        int64_t nbins_total, uint64_t seed, double scale) {
+    const int64_t n = rows * nt;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % rows, j = e / rows;
+        const uint64_t gidx = (uint64_t)(row_begin + i) + (uint64_t)nbins_total * (uint64_t)j;
+        M[i + j * ld] = (S)(scale * philox_u01(gidx, seed, 0u));
+    }
+}
+
+// n_i ~ Poisson(lambda_i): inversion for small lambda, PTRS (Hoermann 1993) otherwise
+__global__ void sfh_poisson_kernel(const double *lam, double *out, int64_t rows, int64_t row_begin, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const double l = lam[i];
+    const uint64_t gi = (uint64_t)(row_begin + i);
+    uint32_t draw = 0;
+    double k;
+    if (!(l > 0.0)) {
+        k = 0.0;
+    } else if (l < 10.0) {
+        const double L = exp(-l);
+        double prod = philox_u01(gi, seed, 1u + draw++);
+        k = 0.0;
+        while (prod > L && k < 1000.0) {
+            prod *= philox_u01(gi, seed, 1u + draw++);
+            k += 1.0;
+        }
+    } else {
+        const double slam = sqrt(l), loglam = log(l);
+        const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+        const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+        k = floor(l);
+        for (int tries = 0; tries < 256; ++tries) {
+            const double U = philox_u01(gi, seed, 1u + draw++) - 0.5;
+            const double V = philox_u01(gi, seed, 1u + draw++);
+            const double us = 0.5 - fabs(U);
+            const double kk = floor((2.0 * a / us + b) * U + l + 0.43);
+            if (us >= 0.07 && V <= vr) { k = kk; break; }
+            if (kk < 0.0 || (us < 0.013 && V > us)) continue;
+            if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -l + kk * loglam - lgamma(kk + 1.0)) { k = kk; break; }
+        }
+    }
+    out[i] = k;
+}
+
+// data conversion on upload (Int64 / Float32 -> double)
+template <typename D>
+__global__ void sfh_to_double_kernel(const D *in, double *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+// writes >L2 bytes: used between timed evaluations (bench hygiene)
+__global__ void sfh_l2_flush_kernel(float4 *buf, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace sfh

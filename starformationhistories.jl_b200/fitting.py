@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's core evaluation interface (L1/L2 of SURVEY.md):
+
+    stack_models            src/fitting/utilities.jl:12-13
+    composite!              src/fitting/fitting_base.jl:20-33, 55-65      -> composite_
+    loglikelihood           src/fitting/fitting_base.jl:84-96, 107-125
+    grad-loglikelihood      src/fitting/fitting_base.jl:144-160, 171-182, 193-211  -> grad_loglikelihood
+    grad-loglikelihood!     src/fitting/fitting_base.jl:227-256, 265-285  -> grad_loglikelihood_
+    fg!                     src/fitting/solvers.jl:20-38                  -> fg_
+
+Same argument order, meaning and error behaviour (the reference's ``@argcheck`` ArgumentErrors are
+ValueErrors here); Julia's ``!`` suffix becomes a trailing underscore and ``nothing`` becomes
+``None``.  Every function is a thin call through the C-ABI of ``libsfhcuda.so``; nothing is
+computed in Python.  ``models`` is a :class:`DeviceStack` (the device-resident mirror of the
+``stack_models`` matrix, uploaded once per fit) or a plain array / list of matrices, for which a
+DeviceStack is created on first use and cached by identity (mechanism 2).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+_DT = {np.dtype(np.float32): L.SFH_F32, np.dtype(np.float64): L.SFH_F64, np.dtype(np.int64): L.SFH_I64}
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def stack_models(models):
+    """``reduce(hcat, map(vec, models))`` -- column-major ``vec`` of each matrix, one template per column."""
+    return np.asfortranarray(np.stack([np.asarray(m).reshape(-1, order="F") for m in models], axis=1))
+
+
+def _as_stack_matrix(models):
+    """Accept the flat (Nb x T) layout or the vector-of-matrices layout; return F-ordered (Nb, T)."""
+    if isinstance(models, (list, tuple)):
+        return stack_models(models)
+    M = np.asarray(models)
+    if M.ndim != 2:
+        raise ValueError("models must be an (nbins x ntemplates) matrix or a list of matrices")
+    return M
+
+
+class _Ctx:
+    """One sfh_ctx per host thread (TaskLocalValue analogue, hmc_sample.jl:127)."""
+
+    def __init__(self, stack_handle, stream=None):
+        h = C.c_void_p()
+        L.check(L.lib.sfh_ctx_create(stack_handle, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.bound_key = None
+        self.n_ages = 0
+        self._fin = weakref.finalize(self, L.lib.sfh_ctx_destroy, h)
+
+    def close(self):
+        self._fin()
+
+
+class DeviceStack:
+    """Device-resident template stack + observed Hess diagram.
+
+    Parameters
+    ----------
+    models : (Nb, T) array (column-major preferred) or list of T matrices -- what ``stack_models`` builds.
+    data   : (Nb,) vector or matrix of the same shape as each template (float32/float64/int64).
+    dtype  : storage dtype on device (default: ``models.dtype``; float32 stacks accumulate in FP64).
+    rows   : optional ``(row_begin, row_end)`` bin-row shard held by this process (multi-GPU).
+    """
+
+    def __init__(self, models, data, dtype=None, device=0, rows=None, clamp_eps=0.0, tile_bins=0, cluster=0,
+                 force_unfused=False):
+        M = _as_stack_matrix(models)
+        dt = np.dtype(dtype) if dtype is not None else M.dtype
+        if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+            dt = np.dtype(np.float64)
+        M = np.asfortranarray(M, dtype=dt)
+        d = np.asarray(data)
+        d = d.reshape(-1, order="F")
+        if d.dtype not in _DT:
+            d = d.astype(np.float64)
+        d = np.ascontiguousarray(d)
+        if d.shape[0] != M.shape[0]:
+            raise ValueError("axes(models,1) != axes(data,1)")            # solvers.jl:11
+        self.shape = M.shape
+        self.dtype = dt
+        o = L.sfh_opts()
+        o.struct_size = C.sizeof(L.sfh_opts)
+        o.device = device
+        if rows is not None:
+            o.row_begin, o.row_end = int(rows[0]), int(rows[1])
+        o.clamp_eps = clamp_eps
+        o.tile_bins, o.cluster, o.force_unfused = tile_bins, cluster, int(force_unfused)
+        h = C.c_void_p()
+        L.check(L.lib.sfh_stack_create(C.byref(h), M.ctypes.data_as(C.c_void_p), M.shape[0], M.shape[1], _DT[dt],
+                                       d.ctypes.data_as(C.c_void_p), _DT[d.dtype], C.byref(o)))
+        self._finish_init(h)
+        self._data_id = id(data)
+
+    def _finish_init(self, h):
+        self.handle = h
+        self._tls = threading.local()
+        self._ctxs = []
+        self._fin = weakref.finalize(self, DeviceStack._destroy, h, self._ctxs)
+        self.rows = self.info().row_end - self.info().row_begin
+
+    @classmethod
+    def synthetic(cls, nbins, ntemplates, dtype, seed, scale, x_true, device=0, rows=None, tile_bins=0, cluster=0,
+                  force_unfused=False):
+        """On-device Philox/Poisson stack (include/sfhcuda.h: sfh_stack_create_synthetic)."""
+        self = cls.__new__(cls)
+        dt = np.dtype(dtype)
+        self.shape = (int(nbins), int(ntemplates))
+        self.dtype = dt
+        o = L.sfh_opts()
+        o.struct_size = C.sizeof(L.sfh_opts)
+        o.device = device
+        if rows is not None:
+            o.row_begin, o.row_end = int(rows[0]), int(rows[1])
+        o.tile_bins, o.cluster, o.force_unfused = tile_bins, cluster, int(force_unfused)
+        x = np.ascontiguousarray(x_true, dtype=np.float64)
+        if x.shape[0] != ntemplates:
+            raise ValueError("len(x_true) != ntemplates")
+        h = C.c_void_p()
+        L.check(L.lib.sfh_stack_create_synthetic(C.byref(h), nbins, ntemplates, _DT[dt], C.c_uint64(seed), float(scale),
+                                                 _dp(x), C.byref(o)))
+        self._finish_init(h)
+        self._data_id = None
+        return self
+
+    @staticmethod
+    def _destroy(h, ctxs):
+        for c in ctxs:
+            c.close()
+        L.lib.sfh_stack_destroy(h)
+
+    def close(self):
+        self._fin()
+
+    # -- plumbing -------------------------------------------------------------------------
+    def ctx(self) -> _Ctx:
+        c = getattr(self._tls, "ctx", None)
+        if c is None:
+            c = _Ctx(self.handle)
+            self._tls.ctx = c
+            self._ctxs.append(c)
+        return c
+
+    def new_ctx(self, stream=None) -> _Ctx:
+        c = _Ctx(self.handle, stream)
+        self._ctxs.append(c)
+        return c
+
+    def info(self) -> L.sfh_info:
+        i = L.sfh_info()
+        L.check(L.lib.sfh_stack_info(self.handle, C.byref(i)))
+        return i
+
+    def set_data(self, data):
+        d = np.asarray(data).reshape(-1, order="F")
+        if d.dtype not in _DT:
+            d = d.astype(np.float64)
+        d = np.ascontiguousarray(d)
+        if d.shape[0] != self.shape[0]:
+            raise ValueError("axes(models,1) != axes(data,1)")
+        L.check(L.lib.sfh_stack_set_data(self.handle, d.ctypes.data_as(C.c_void_p), _DT[d.dtype]))
+        self._data_id = id(data)
+
+    def download(self):
+        i = self.info()
+        rows = i.row_end - i.row_begin
+        M = np.empty((rows, self.shape[1]), dtype=self.dtype, order="F")
+        d = np.empty(rows, dtype=np.float64)
+        L.check(L.lib.sfh_stack_download(self.handle, M.ctypes.data_as(C.c_void_p), _dp(d)))
+        return M, d
+
+    # -- raw calls (all host-synchronous) ----------------------------------------------------
+    def eval_fg(self, coeffs, want_F=True, want_G=True, want_composite=False):
+        x = np.ascontiguousarray(coeffs, dtype=np.float64)
+        if x.ndim != 1 or x.shape[0] != self.shape[1]:
+            raise ValueError("axes(coeffs,1) != axes(models,2)")           # fitting_base.jl:59 / solvers.jl:10
+        nl = C.c_double()
+        G = np.empty(self.shape[1]) if want_G else None
+        comp = np.empty(self.rows) if want_composite else None
+        L.check(L.lib.sfh_eval_fg(self.ctx().handle, _dp(x), C.byref(nl) if want_F else None,
+                                  _dp(G) if want_G else None, _dp(comp) if want_composite else None))
+        return (nl.value if want_F else None), G, comp
+
+    def eval_logl_batched(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if X.shape[0] != self.shape[1]:
+            raise ValueError("size(X,1) != size(models,2)")
+        X = np.asfortranarray(X)
+        out = np.empty(X.shape[1])
+        L.check(L.lib.sfh_eval_logl_batched(self.ctx().handle, _dp(X), X.shape[1], _dp(out)))
+        return out
+
+    def time_fg(self, coeffs, reps=10, want_G=True, flush_l2=True):
+        x = np.ascontiguousarray(coeffs, dtype=np.float64)
+        ms, msk = C.c_double(), C.c_double()
+        L.check(L.lib.sfh_time_fg(self.ctx().handle, _dp(x), reps, int(want_G), int(flush_l2), C.byref(ms), C.byref(msk)))
+        return ms.value, msk.value
+
+
+# ---------------------------------------------------------------------------------------------
+# identity-keyed cache for callers that pass bare arrays on every iteration
+# ---------------------------------------------------------------------------------------------
+_cache: dict = {}
+_cache_lock = threading.Lock()
+
+
+def device_stack(models, data) -> DeviceStack:
+    if isinstance(models, DeviceStack):
+        if data is not None and models._data_id is not None and id(data) != models._data_id:
+            models.set_data(data)
+        return models
+    key = (id(models), id(data))
+    with _cache_lock:
+        ent = _cache.get(key)
+        if ent is not None:
+            return ent
+        if len(_cache) >= 8:
+            _cache.pop(next(iter(_cache))).close()
+        ds = DeviceStack(models, data)
+        _cache[key] = ds
+        return ds
+
+
+def clear_cache():
+    with _cache_lock:
+        for ds in _cache.values():
+            ds.close()
+        _cache.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's functions
+# ---------------------------------------------------------------------------------------------
+def _flat_out(arr):
+    """View of a user-supplied output array as a flat column-major vector we can fill in place."""
+    a = np.asarray(arr)
+    return a
+
+
+def composite_(composite, coeffs, models, data=None):
+    """``composite!(composite, coeffs, models)``: composite <- sum_j coeffs[j] * models[:, j].  Returns None.
+
+    (``data`` is not part of the reference signature; it is only needed when ``models`` is a bare array
+    that has not been seen before, because a DeviceStack binds data at creation.)"""
+    if isinstance(models, DeviceStack):
+        ds = models
+    else:
+        M = _as_stack_matrix(models)
+        ds = device_stack(models, data if data is not None else np.zeros(M.shape[0]))
+    comp = np.asarray(composite)
+    if comp.size != ds.shape[0]:
+        raise ValueError("axes(composite,1) != axes(models,1)")            # fitting_base.jl:58
+    x = np.ascontiguousarray(coeffs, dtype=np.float64)
+    if x.shape[0] != ds.shape[1]:
+        raise ValueError("axes(coeffs,1) != axes(models,2)")               # fitting_base.jl:59
+    out = np.empty(ds.rows)
+    L.check(L.lib.sfh_composite(ds.ctx().handle, _dp(x), _dp(out)))
+    composite[...] = out.reshape(comp.shape, order="F").astype(comp.dtype, copy=False)
+    return None
+
+
+def loglikelihood(*args):
+    """``loglikelihood(composite, data)`` or ``loglikelihood(coeffs, models, data)``.
+
+    The two-argument form needs the device copy of ``data``: pass a DeviceStack as ``data`` or use the
+    three-argument form.  Returned scalar has the promoted element type (fitting_core_test.jl:40)."""
+    if len(args) == 2:
+        composite, data = args
+        if not isinstance(data, DeviceStack):
+            raise TypeError("loglikelihood(composite, data): `data` must be the DeviceStack holding the observed "
+                            "Hess diagram (there is no host implementation)")
+        comp = np.ascontiguousarray(np.asarray(composite).reshape(-1, order="F"), dtype=np.float64)
+        if comp.shape[0] != data.rows:
+            raise ValueError("axes(composite) != axes(data)")              # fitting_base.jl:85
+        out = C.c_double()
+        L.check(L.lib.sfh_loglikelihood(data.ctx().handle, _dp(comp), C.byref(out)))
+        T = np.promote_types(np.asarray(composite).dtype, data.dtype) if np.asarray(composite).dtype.kind == "f" else data.dtype
+        return T.type(out.value)
+    coeffs, models, data = args
+    ds = device_stack(models, data)
+    x = np.ascontiguousarray(coeffs, dtype=np.float64)
+    if x.shape[0] != ds.shape[1]:
+        raise ValueError("axes(coeffs,1) != axes(models,2)")               # fitting_base.jl:120
+    out = C.c_double()
+    L.check(L.lib.sfh_loglikelihood_coeffs(ds.ctx().handle, _dp(x), C.byref(out)))
+    return ds.dtype.type(out.value)
+
+
+def grad_loglikelihood_(G, composite, models, data=None):
+    """``grad-loglikelihood!(G, composite, models, data)``: G <- -M' (1 - n/max(composite,eps)); ``composite`` is
+    overwritten with the residual (documented side effect, fitting_base.jl:219).  Returns G."""
+    ds = device_stack(models, data)
+    comp = np.asarray(composite)
+    if comp.size != ds.rows:
+        raise ValueError("axes(models,1) != axes(composite,1)")            # fitting_base.jl:272
+    if np.asarray(G).shape[0] != ds.shape[1]:
+        raise ValueError("axes(G,1) != axes(models,2)")                    # fitting_base.jl:271
+    buf = np.ascontiguousarray(comp.reshape(-1, order="F"), dtype=np.float64).copy()
+    g = np.empty(ds.shape[1])
+    L.check(L.lib.sfh_grad_loglikelihood(ds.ctx().handle, _dp(buf), _dp(g)))
+    composite[...] = buf.reshape(comp.shape, order="F").astype(comp.dtype, copy=False)
+    G[...] = g.astype(np.asarray(G).dtype, copy=False)
+    return G
+
+
+def grad_loglikelihood(*args):
+    """``grad-loglikelihood(models, composite, data)`` / ``(coeffs, models, data)`` -> new gradient vector."""
+    a, b, data = args
+    if isinstance(b, DeviceStack) or (not isinstance(a, DeviceStack) and np.asarray(a).ndim == 1 and not isinstance(a, (list, tuple))):
+        coeffs, models = a, b                                              # (coeffs, models, data)  :193-211
+        ds = device_stack(models, data)
+        _, G, _ = ds.eval_fg(coeffs, want_F=False, want_G=True)
+        return (-G).astype(ds.dtype, copy=False)
+    models, composite = a, b                                               # (models, composite, data) :171-182
+    ds = device_stack(models, data)
+    G = np.empty(ds.shape[1], dtype=ds.dtype)
+    comp = np.array(np.asarray(composite).reshape(-1, order="F"), dtype=np.float64)
+    return grad_loglikelihood_(G, comp, ds, data)
+
+
+def fg_(F, G, coeffs, models, data, composite=None):
+    """``fg!(F, G, coeffs, models, data, composite)`` -- returns -logL when ``F is not None``; fills ``G`` with the
+    gradient of -logL when ``G is not None``; with both ``None`` only the composite is formed (solvers.jl:20-38).
+    ``composite`` (optional scratch, as in the reference) receives what the reference leaves in it."""
+    ds = device_stack(models, data)
+    want_F, want_G = F is not None, G is not None
+    if want_G and np.asarray(G).shape[0] != ds.shape[1]:
+        raise ValueError("axes(G,1) != axes(models,2)")
+    if composite is not None and np.asarray(composite).size != ds.rows:
+        raise ValueError("axes(models,1) != axes(composite,1)")            # solvers.jl:11
+    nl, g, comp = ds.eval_fg(coeffs, want_F=want_F, want_G=want_G, want_composite=composite is not None)
+    if want_G:
+        G[...] = g.astype(np.asarray(G).dtype, copy=False)
+    if composite is not None:
+        ca = np.asarray(composite)
+        composite[...] = comp.reshape(ca.shape, order="F").astype(ca.dtype, copy=False)
+    if want_F:
+        return ds.dtype.type(nl)
+    return None

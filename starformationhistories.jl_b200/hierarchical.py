@@ -1,0 +1,298 @@
+"""Host-side mirror of the reference's hierarchical (metallicity-model) interface (L3/L4 of SURVEY.md):
+
+    AbstractMZR / PowerLawMZR            src/fitting/hierarchical/mzr.jl:6-48, 263-284
+    AbstractAMR / LinearAMR / LogarithmicAMR   src/fitting/hierarchical/amr.jl:6-48, 181-213, 250-298
+    GaussianDispersion                   src/fitting/hierarchical/dispersion_models.jl:80-110
+    calculate_coeffs                     mzr.jl:50-79, amr.jl:50-73
+    fg! (hierarchical method)            mzr.jl:84-215, amr.jl:78-173           -> fg_
+    HierarchicalOptimizer + logdensity_and_gradient   generic_fitting.jl:44-58, 90-199
+
+The model classes carry the reference's small model API (callable, nparams, fittable_params, gradient,
+update_params, transforms, free_params) as plain scalar host code -- it is metadata.  The O(Nb*T)
+evaluation and the O(T) coefficient expansion / chain rule of every iteration run on the device
+through ``sfh_eval_fg_hier``; only Nj+3 numbers cross the host boundary per evaluation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from .fitting import DeviceStack, _dp, device_stack
+
+LOGTEN = math.log(10.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# dispersion model
+# ---------------------------------------------------------------------------------------------
+class GaussianDispersion:
+    kind = L.SFH_DISP_GAUSSIAN
+
+    def __init__(self, sigma, free=(True,)):
+        if sigma <= 0:
+            raise ValueError("σ must be > 0")                              # dispersion_models.jl:84
+        self.sigma = float(sigma)
+        self.free = tuple(bool(f) for f in free)
+
+    def __call__(self, x, mu):
+        return math.exp(-(((x - mu) / self.sigma) ** 2) / 2)              # :92
+
+    def gradient(self, x, mu):
+        A = self(x, mu)
+        return (A * (x - mu) ** 2 / self.sigma ** 3, A * (x - mu) / self.sigma ** 2)   # :95-100 (σ, μ)
+
+    def nparams(self): return 1
+    def fittable_params(self): return (self.sigma,)
+    def update_params(self, new): return GaussianDispersion(new[0], self.free)
+    def transforms(self): return (1,)
+    def free_params(self): return self.free
+    def __eq__(self, o): return isinstance(o, GaussianDispersion) and (self.sigma, self.free) == (o.sigma, o.free)
+
+
+# ---------------------------------------------------------------------------------------------
+# metallicity models
+# ---------------------------------------------------------------------------------------------
+class _MHModel:
+    is_mzr = False
+
+    def nparams(self): return 2
+    def fittable_params(self): return (self.alpha, self.beta)
+    def free_params(self): return self.free
+
+
+class PowerLawMZR(_MHModel):
+    """[M/H](M*) = MH0 + α (log10 M* - logMstar0)   (mzr.jl:263-284)"""
+    kind = L.SFH_MH_POWERLAW_MZR
+    is_mzr = True
+
+    def __init__(self, alpha, MH0, logMstar0=6.0, free=(True, True)):
+        if alpha < 0:
+            raise ValueError("α must be ≥ 0")                              # mzr.jl:268
+        self.alpha, self.beta, self.logMstar0 = float(alpha), float(MH0), float(logMstar0)
+        self.free = tuple(bool(f) for f in free)
+
+    MH0 = property(lambda self: self.beta)
+
+    def __call__(self, Mstar): return self.beta + self.alpha * (math.log10(Mstar) - self.logMstar0)
+
+    def gradient(self, Mstar):
+        return (math.log10(Mstar) - self.logMstar0, 1.0, self.alpha / Mstar / LOGTEN)
+
+    def update_params(self, new): return PowerLawMZR(new[0], new[1], self.logMstar0, self.free)
+    def transforms(self): return (1, 0)
+    def fixed(self): return np.array([self.logMstar0, 0, 0, 0], dtype=np.float64)
+    def __eq__(self, o):
+        return isinstance(o, PowerLawMZR) and (self.alpha, self.beta, self.logMstar0, self.free) == (o.alpha, o.beta, o.logMstar0, o.free)
+
+
+class LinearAMR(_MHModel):
+    """μ_j = β + α (T_max - t_j [Gyr])   (amr.jl:181-213)"""
+    kind = L.SFH_MH_LINEAR_AMR
+
+    def __init__(self, alpha, beta, T_max=13.7, free=(True, True)):
+        if alpha < 0:
+            raise ValueError("α must be ≥ 0")                              # amr.jl:187
+        if T_max <= 0:
+            raise ValueError("T_max must be > 0")                          # amr.jl:189
+        self.alpha, self.beta, self.T_max = float(alpha), float(beta), float(T_max)
+        self.free = tuple(bool(f) for f in free)
+
+    def __call__(self, logAge): return self.beta + self.alpha * (self.T_max - 10.0 ** (logAge - 9))
+    def gradient(self, logAge): return (self.T_max - 10.0 ** (logAge - 9), 1.0)
+    def update_params(self, new): return LinearAMR(new[0], new[1], self.T_max, self.free)
+    def transforms(self): return (1, 0)
+    def fixed(self): return np.array([self.T_max, 0, 0, 0], dtype=np.float64)
+
+
+def MH_from_Z(Z, solZ=0.01524, Y_p=0.2485, gamma=1.78):
+    """src/utilities.jl:138-146 (NaN instead of a DomainError when X <= 0)."""
+    X = 1 - ((Y_p + gamma * Z) + Z)
+    Xs = 1 - ((Y_p + gamma * solZ) + solZ)
+    return math.log10(Z / (X * solZ) * Xs) if X > 0 else float("nan")
+
+
+def dMH_dZ(Z, solZ=0.01524, Y_p=0.2485, gamma=1.78):
+    """src/utilities.jl:152-155"""
+    return (Y_p - 1) / (LOGTEN * Z * (Y_p + Z + gamma * Z - 1))
+
+
+class LogarithmicAMR(_MHModel):
+    """Z_j = β + α (T_max - t_j), μ_j = MH_from_Z(Z_j)   (amr.jl:250-298).  Only the default
+    MH_from_Z / dMH_dZ pair (PARSEC: solZ, Y_p, γ) has a device-side chain rule."""
+    kind = L.SFH_MH_LOG_AMR
+
+    def __init__(self, alpha, beta, T_max=13.7, free=(True, True), solZ=0.01524, Y_p=0.2485, gamma=1.78):
+        if alpha < 0:
+            raise ValueError("α must be ≥ 0")                              # amr.jl:262
+        if beta < 0:
+            raise ValueError("β must be ≥ 0")                              # amr.jl:264
+        if T_max <= 0:
+            raise ValueError("T_max must be > 0")                          # amr.jl:266
+        self.alpha, self.beta, self.T_max = float(alpha), float(beta), float(T_max)
+        self.solZ, self.Y_p, self.gamma = float(solZ), float(Y_p), float(gamma)
+        self.free = tuple(bool(f) for f in free)
+
+    def __call__(self, logAge):
+        return MH_from_Z(self.beta + self.alpha * (self.T_max - 10.0 ** (logAge - 9)), self.solZ, self.Y_p, self.gamma)
+
+    def gradient(self, logAge):
+        age = 10.0 ** (logAge - 9)
+        d = dMH_dZ(self.beta + self.alpha * (self.T_max - age), self.solZ, self.Y_p, self.gamma)
+        return (d * (self.T_max - age), d)
+
+    def update_params(self, new):
+        return LogarithmicAMR(new[0], new[1], self.T_max, self.free, self.solZ, self.Y_p, self.gamma)
+
+    def transforms(self): return (1, 1)
+    def fixed(self): return np.array([self.T_max, self.solZ, self.Y_p, self.gamma], dtype=np.float64)
+
+
+def nparams(*models): return sum(m.nparams() for m in models)     # hierarchical_models.jl:17
+
+
+# ---------------------------------------------------------------------------------------------
+# device calls
+# ---------------------------------------------------------------------------------------------
+def _bind(ds: DeviceStack, logAge, MH):
+    """sfh_hier_bind once per (context, logAge, MH): the grouping of mzr.jl:131-140."""
+    ctx = ds.ctx()
+    la = np.ascontiguousarray(logAge, dtype=np.float64)
+    mh = np.ascontiguousarray(MH, dtype=np.float64)
+    if la.shape != mh.shape:
+        raise ValueError("length(logAge) != length(metallicities)")        # mzr.jl:57
+    if la.shape[0] != ds.shape[1]:
+        raise ValueError("length(logAge) != number of templates")
+    key = (la.tobytes(), mh.tobytes())
+    if ctx.bound_key != key:
+        n = C.c_int64()
+        L.check(L.lib.sfh_hier_bind(ctx.handle, _dp(la), _dp(mh), C.byref(n)))
+        ctx.bound_key, ctx.n_ages = key, int(n.value)
+    return ctx
+
+
+def calculate_coeffs(MHmodel, dispmodel, mstars, logAge, metallicities, models=None):
+    """``calculate_coeffs(MHmodel, dispmodel, R, logAge, MH)`` (mzr.jl:50-79 / amr.jl:50-73).
+
+    With ``models`` (a DeviceStack) the expansion runs through the device prologue kernel that every
+    hierarchical evaluation uses.  Without it -- the reference signature has no stack argument, and this
+    form is only used for one-shot set-up such as building x0 -- the same O(T) formulae are evaluated
+    on the host in float64."""
+    la = np.asarray(logAge, dtype=np.float64)
+    mh = np.asarray(metallicities, dtype=np.float64)
+    R = np.asarray(mstars, dtype=np.float64)
+    if la.shape != mh.shape:
+        raise ValueError("length(logAge) != length(metallicities)")        # mzr.jl:57
+    _, first = np.unique(la, return_index=True)
+    uniq = la[np.sort(first)]
+    if R.shape[0] != uniq.shape[0]:
+        raise ValueError("Length of `mstars` must be the same as `unique(logAge)`.")   # mzr.jl:55-56
+    if models is not None:
+        ds = device_stack(models, None)
+        ctx = _bind(ds, la, mh)
+        v = np.concatenate([R, [MHmodel.alpha, MHmodel.beta, dispmodel.sigma]])
+        out = np.empty(ds.shape[1])
+        fx = MHmodel.fixed()
+        L.check(L.lib.sfh_calculate_coeffs(ctx.handle, MHmodel.kind, _dp(fx), dispmodel.kind, _dp(v), _dp(out)))
+        return out
+    if MHmodel.is_mzr:
+        s = np.argsort(-uniq, kind="stable")                               # sortperm(rev=true)  mzr.jl:61
+        cum = np.empty_like(R)
+        cum[s] = np.cumsum(R[s])                                           # mzr.jl:66
+        mu = np.array([MHmodel(c) for c in cum])
+    else:
+        mu = np.array([MHmodel(a) for a in uniq])
+    coeffs = np.empty(la.shape[0])
+    for j, a in enumerate(uniq):
+        idx = np.nonzero(la == a)[0]
+        A = np.exp(-(((mh[idx] - mu[j]) / dispmodel.sigma) ** 2) / 2)
+        coeffs[idx] = A * R[j] / A.sum()                                   # mzr.jl:76
+    return coeffs
+
+
+def fg_(F, G, MHmodel0, dispmodel0, variables, models, data, composite, logAge, metallicities):
+    """Hierarchical ``fg!`` (mzr.jl:84-215 / amr.jl:78-173): returns -logL if ``F is not None``; fills ``G``
+    (length Nj + nparams) with d(-logL)/d variables if ``G is not None``.  ``composite`` is accepted for
+    signature parity and ignored (scratch lives on the device)."""
+    ds = device_stack(models, data)
+    ctx = _bind(ds, logAge, metallicities)
+    v = np.ascontiguousarray(variables, dtype=np.float64)
+    if v.shape[0] != ctx.n_ages + 3:
+        raise ValueError("length(variables) != length(unique(logAge)) + nparams")      # mzr.jl:55, :126
+    if G is not None and np.asarray(G).shape[0] != v.shape[0]:
+        raise ValueError("axes(G) != axes(variables)")                     # mzr.jl:126
+    free = np.array(list(MHmodel0.free_params()) + list(dispmodel0.free_params()) + [0], dtype=np.uint8)
+    nl = C.c_double()
+    g = np.empty(v.shape[0]) if G is not None else None
+    fx = MHmodel0.fixed()
+    L.check(L.lib.sfh_eval_fg_hier(ctx.handle, MHmodel0.kind, _dp(fx), dispmodel0.kind, _dp(v),
+                                   free.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nl), _dp(g) if g is not None else None))
+    if G is not None:
+        G[...] = g
+    return nl.value if F is not None else None
+
+
+def exptransform(params, transforms):
+    """src/fitting/hierarchical/transformations.jl:44"""
+    return np.array([math.exp(p) if t == 1 else (-math.exp(p) if t == -1 else p) for p, t in zip(params, transforms)])
+
+
+def logtransform(params, transforms):
+    """src/fitting/hierarchical/transformations.jl:18"""
+    return np.array([math.log(p) if t == 1 else (math.log(-p) if t == -1 else p) for p, t in zip(params, transforms)])
+
+
+class HierarchicalOptimizer:
+    """generic_fitting.jl:44-58 -- the LogDensityProblems adapter used by fit_sfh / sample_sfh."""
+
+    def __init__(self, MH_model0, disp_model0, models, data, logAge, metallicities, F=True, G=True,
+                 jacobian_corrections=True):
+        self.MH_model0, self.disp_model0 = MH_model0, disp_model0
+        self.models = device_stack(models, data)
+        self.data, self.logAge, self.metallicities = data, np.asarray(logAge, float), np.asarray(metallicities, float)
+        self.F, self.G, self.jacobian_corrections = F, G, bool(jacobian_corrections)
+
+    def dimension(self):
+        free = list(self.MH_model0.free_params()) + list(self.disp_model0.free_params())
+        return _bind(self.models, self.logAge, self.metallicities).n_ages + sum(free)
+
+    def logdensity_and_gradient(self, xvec):
+        """generic_fitting.jl:90-199.  Returns (+logp, +grad) over the FREE transformed variables
+        (only ``logp`` / only ``grad`` when ``G`` / ``F`` is None)."""
+        xvec = np.asarray(xvec, dtype=np.float64)
+        ret_F, ret_G = self.F is not None, self.G is not None
+        tf = np.array(list(self.MH_model0.transforms()) + list(self.disp_model0.transforms()))
+        free = np.array(list(self.MH_model0.free_params()) + list(self.disp_model0.free_params()), dtype=bool)
+        npar = tf.shape[0]
+        nbins = xvec.shape[0] - npar + int((~free).sum())                  # :116-118
+        x = np.empty(nbins + npar)
+        x[:nbins] = np.exp(xvec[:nbins])                                   # :127
+        x[nbins:][free] = exptransform(xvec[nbins:], tf[free])             # :129-131
+        init = np.array(list(self.MH_model0.fittable_params()) + list(self.disp_model0.fittable_params()))
+        x[nbins:][~free] = init[~free]                                     # :134-136
+        G2 = np.empty_like(x) if ret_G else None
+        nlogL = fg_(self.F, G2, self.MH_model0, self.disp_model0, x, self.models, self.data, None,
+                    self.logAge, self.metallicities)                       # :140
+        ptf = [i for i in range(npar) if tf[i] == 1 and free[i]]           # :143-145
+        idxs = list(range(nbins)) + [nbins + i for i in ptf]
+        ntf = [nbins + i for i in range(npar) if tf[i] == -1 and free[i]]
+        if self.jacobian_corrections:                                      # :148-160
+            for i in idxs:
+                if ret_F: nlogL -= math.log(x[i])
+                if ret_G: G2[i] = G2[i] * x[i] - 1
+            for i in ntf:
+                if ret_F: nlogL += math.log(x[i])
+                if ret_G: G2[i] = -G2[i] * x[i] + 1
+        else:                                                              # :161-169 (with the +Nbins the reference forgets)
+            for i in idxs:
+                if ret_G: G2[i] = G2[i] * x[i]
+            for i in ntf:
+                if ret_G: G2[i] = -G2[i] * x[i]
+        if not ret_G:
+            return -nlogL if ret_F else None                               # :172-178
+        G = np.empty_like(xvec)
+        G[:nbins] = G2[:nbins]
+        G[nbins:] = G2[nbins:][free]                                       # :181-189
+        return (-nlogL, -G) if ret_F else -G                               # :193-197

@@ -1,0 +1,124 @@
+"""CPU-side checks of the drop-in boundary (no GPU needed):
+  * libsfhcuda.so loads and exports every symbol include/sfhcuda.h declares;
+  * the ctypes table in the host package covers exactly those symbols;
+  * without a device every compute entry point fails loudly with SFH_ERR_NO_DEVICE (no CPU fallback);
+  * the product package never imports / links / loads anything under oracle/.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "starformationhistories.jl_b200")
+HEADER = os.path.join(ROOT, "include", "sfhcuda.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfh_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import sfh_b200
+    syms = header_symbols()
+    assert len(syms) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", sfh_b200._lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (sfh_[a-z0-9_]+)", out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, f"declared in sfhcuda.h but not exported: {missing}"
+    assert set(sfh_b200._lib.PROTOTYPES) == set(syms), set(sfh_b200._lib.PROTOTYPES) ^ set(syms)
+    for s in syms:
+        getattr(sfh_b200._lib.lib, s)
+
+
+def test_struct_layouts_match_header():
+    import sfh_b200
+    L = sfh_b200._lib
+    assert C.sizeof(L.sfh_opts) == 48      # 2*i32, 2*i64, f64, 4*i32
+    assert C.sizeof(L.sfh_stats) == 24
+    assert L.lib.sfh_version() == 1
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import sfh_b200
+    assert sfh_b200.device_count() == 0
+    with pytest.raises(sfh_b200.SFHError) as ei:
+        sfh_b200.DeviceStack(np.ones((8, 3)), np.ones(8))
+    assert ei.value.status == sfh_b200._lib.SFH_ERR_NO_DEVICE
+    with pytest.raises(sfh_b200.SFHError):
+        sfh_b200.fg_(True, np.zeros(3), np.ones(3), np.ones((8, 3)), np.ones(8))
+    with pytest.raises(ValueError):       # shape errors are raised before anything else
+        sfh_b200.DeviceStack(np.ones((8, 3)), np.ones(7))
+
+
+def test_argument_validation_without_device():
+    import sfh_b200
+    L = sfh_b200._lib
+    assert L.lib.sfh_device_count(None) == L.SFH_ERR_INVALID_ARG
+    assert b"NULL" in L.lib.sfh_last_error()
+    h = C.c_void_p()
+    assert L.lib.sfh_stack_create(C.byref(h), None, 4, 2, L.SFH_F64, None, L.SFH_F64, None) == L.SFH_ERR_INVALID_ARG
+    assert L.lib.sfh_stack_destroy(None) == L.SFH_OK       # idempotent on NULL (finalizer-safe)
+    assert L.lib.sfh_ctx_destroy(None) == L.SFH_OK
+
+
+def test_product_never_touches_oracle():
+    bad = []
+    for dp, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"\boracle\b|sfho_|libsfhoracle", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, f"product sources reference the oracle: {bad}"
+    import sfh_b200
+    out = subprocess.run(["ldd", sfh_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    hdr = open(HEADER).read()
+    assert "oracle" not in hdr.lower()
+
+
+def test_host_model_api_matches_reference_doctests():
+    """mzr.jl:233-261, amr.jl:213-247, dispersion_models.jl:51-78 doctests on the host model classes."""
+    import sfh_b200 as S
+    m = S.PowerLawMZR(1.0, -1, 6)
+    assert m.nparams() == 2 and abs(m(1e7)) < 1e-15
+    g = m.gradient(1e8)
+    assert g[0] == pytest.approx(2.0) and g[1] == 1.0 and g[2] == pytest.approx(1 / 1e8 / np.log(10))
+    assert S.PowerLawMZR(1.0, -1, 7, (True, False)).update_params((2.0, -2)) == S.PowerLawMZR(2.0, -2, 7, (True, False))
+    assert m.transforms() == (1, 0) and S.PowerLawMZR(1.0, -1, 7, (True, False)).free_params() == (True, False)
+    with pytest.raises(ValueError):
+        S.PowerLawMZR(-1.0, -1)
+    d = S.GaussianDispersion(0.2)
+    assert d(1.0, 1.2) == pytest.approx(np.exp(-0.5))
+    assert d.gradient(1.0, 1.2) == (pytest.approx(3.0326532985631656), pytest.approx(-3.0326532985631656))
+    assert d.transforms() == (1,) and S.GaussianDispersion(0.2, (False,)).free_params() == (False,)
+    with pytest.raises(ValueError):
+        S.GaussianDispersion(0.0)
+    assert S.LinearAMR(0.05, -1.6, 12).transforms() == (1, 0) and S.LogarithmicAMR(1e-4, 5e-5, 12).transforms() == (1, 1)
+    assert S.nparams(m, d) == 3
+    with pytest.raises(ValueError):
+        S.LogarithmicAMR(1e-4, -1.0)
+
+
+def test_host_calculate_coeffs_matches_oracle():
+    import oracle as O
+    import sfh_b200 as S
+    from conftest import make_hier_problem
+    p = make_hier_problem(nj=21, nk=26, nb=4, shuffle=True, ragged=True)
+    for model, kind, fixed in [(S.PowerLawMZR(1.0, -2.0, 6.0), O.POWERLAW_MZR, (6.0,)),
+                               (S.LinearAMR(0.05, -1.6, 12.0), O.LINEAR_AMR, (12.0,)),
+                               (S.LogarithmicAMR(1e-4, 5e-5, 12.0), O.LOG_AMR, (12.0,))]:
+        got = S.calculate_coeffs(model, S.GaussianDispersion(0.2), p["R"], p["logAge"], p["MH"])
+        want = O.calculate_coeffs(kind, model.alpha, model.beta, fixed, 0.2, p["R"], p["logAge"], p["MH"])
+        assert np.allclose(got, want, rtol=1e-13, atol=0)
+    with pytest.raises(ValueError):
+        S.calculate_coeffs(S.PowerLawMZR(1.0, -2.0), S.GaussianDispersion(0.2), p["R"][:-1], p["logAge"], p["MH"])

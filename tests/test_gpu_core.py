@@ -1,0 +1,285 @@
+"""GPU parity tests of the core path (composite! / loglikelihood / grad-loglikelihood! / fg!) through the
+C-ABI, against (i) the reference's own known-answer tests (fitting_core_test.jl), (ii) the CPU oracle
+and its __float128 arbiter on seeded inputs, (iii) size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): Float64 stacks 1e-12 relative on logL, 1e-10 per gradient
+component -- measured against the backward-error scale sum_i |M_ij (1 - n_i/m_i)| that any reordering of
+the sum is subject to (SURVEY.md section 7 "Tolerance definition"), and as plain relative error where the
+component is not a near-total cancellation.  Float32-stored stacks with FP64 accumulation: 1e-6.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import make_flat_problem
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOGL = 1e-12
+RTOL_GRAD = 1e-10
+RTOL_F32 = 1e-6
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sfh_b200
+    assert sfh_b200.device_count() >= 1
+    return sfh_b200
+
+
+def jl(rows, dt):
+    return np.array(rows, dtype=dt)
+
+
+def assert_grad_close(G, Gq, gscale, rtol=RTOL_GRAD):
+    err = np.abs(G - Gq)
+    assert np.all(err <= rtol * gscale + 1e-300), float(np.max(err / (gscale + 1e-300)))
+    big = np.abs(Gq) > 1e-3 * gscale          # not a near-total cancellation: plain relative error
+    if big.any():
+        assert np.max(err[big] / np.abs(Gq[big])) <= rtol * 1e3
+
+
+# ------------------------------------------------------------------ reference KATs through the C-ABI
+@pytest.mark.parametrize("T,rtol", [(np.float32, 1e-3), (np.float64, 1e-7)])
+def test_reference_kats(S, T, rtol):
+    # composite!  fitting_core_test.jl:9-31
+    A = jl([[0, 0, 0], [1, 1, 1], [0, 0, 0]], T); B = jl([[0, 0, 0], [0, 0, 0], [1, 1, 1]], T)
+    coeffs = np.array([1, 2], dtype=T)
+    models2 = S.stack_models([A, B])
+    assert np.array_equal(models2[:, 0], [0, 1, 0, 0, 1, 0, 0, 1, 0]) and np.array_equal(models2[:, 1], [0, 0, 1, 0, 0, 1, 0, 0, 1])
+    Cm = np.zeros((3, 3), dtype=T)
+    assert S.composite_(Cm, coeffs, [A, B], data=np.zeros((3, 3))) is None
+    assert np.array_equal(Cm, jl([[0, 0, 0], [1, 1, 1], [2, 2, 2]], T))
+    C2 = np.zeros(9, dtype=T)
+    S.composite_(C2, coeffs, models2, data=np.zeros(9))
+    assert np.array_equal(C2, np.array([0, 1, 2, 0, 1, 2, 0, 1, 2], dtype=T))
+
+    # loglikelihood  :32-70
+    data = np.array([[1, 1, 1], [2, 2, 2], [2, 2, 2]], dtype=np.int64)
+    A = jl([[1, 1, 1], [0, 0, 0], [0, 0, 0]], T); B = jl([[0, 0, 0], [1, 1, 1], [1.5, 1.5, 1.5]], T)
+    r = S.loglikelihood(coeffs, [A, B], data)
+    assert isinstance(r, T) and r == pytest.approx(-0.5672093513510137, rel=rtol)
+    ds = S.DeviceStack([A, B], data)
+    Cmat = jl([[1, 1, 1], [2, 2, 2], [3, 3, 3]], T)
+    r2 = S.loglikelihood(Cmat, ds)
+    assert isinstance(r2, T) and r2 == pytest.approx(-0.5672093513510137, rel=rtol)
+    dz = np.array([[0, 0, 0], [2, 2, 2], [2, 2, 2]], dtype=np.int64)
+    dsz = S.DeviceStack([A, B], dz)
+    assert S.loglikelihood(jl([[1.5, 1.5, 1.5], [3, 3, 3], [3, 3, 3]], T), dsz) == pytest.approx(-5.6344187027020260, rel=rtol)
+
+    # grad-loglikelihood / grad-loglikelihood!  :71-162
+    models = [jl([[1, 1, 1], [0, 0, 0], [0, 0, 0]], T), jl([[0, 0, 0], [1, 1, 1], [0, 0, 0]], T), jl([[0, 0, 0], [0, 0, 0], [1, 1, 1]], T)]
+    c3 = np.array([1.5, 3, 3], dtype=T)
+    g = S.grad_loglikelihood(c3, S.DeviceStack(models, data), data)
+    assert g.dtype == T and g.shape == (3,) and np.allclose(g, [-1, -1, -1], rtol=rtol)
+    grad = np.empty(3, dtype=T)
+    Cc = sum(c * m for c, m in zip(c3, models)).astype(T)
+    S.grad_loglikelihood_(grad, Cc, S.DeviceStack(models, data), data)
+    assert np.allclose(grad, [-1, -1, -1], rtol=rtol)
+    # side effect: composite now holds 1 - n/m  (fitting_base.jl:219)
+    assert np.allclose(Cc, 1 - data / sum(c * m for c, m in zip(c3, models)), rtol=rtol)
+    grad3 = np.empty(3, dtype=T)
+    S.grad_loglikelihood_(grad3, sum(c * m for c, m in zip(c3, models)).astype(T), S.DeviceStack(models, dz), dz)
+    assert np.allclose(grad3, [-3, -1, -1], rtol=rtol)
+
+    # fg!  :163-195
+    G = np.empty(3, dtype=T); Cs = np.empty((3, 3), dtype=T)
+    res = S.fg_(True, G, c3, models, data, Cs)
+    assert isinstance(res, T) and -res == pytest.approx(-1.4180233783775342, rel=rtol)
+    assert np.allclose(-G, [-1, -1, -1], rtol=rtol)
+    res2 = S.fg_(True, None, c3, S.stack_models(models), data.reshape(-1, order="F"), np.empty(9, dtype=T))
+    assert -res2 == pytest.approx(-1.4180233783775342, rel=rtol)
+    G2 = np.empty(3, dtype=T)
+    assert S.fg_(None, G2, c3, models, data) is None and np.allclose(G2, G)
+
+
+def test_argchecks(S):
+    M, x, data = make_flat_problem(64, 5)
+    ds = S.DeviceStack(M, data)
+    with pytest.raises(ValueError):
+        ds.eval_fg(np.ones(4))                                  # solvers.jl:10
+    with pytest.raises(ValueError):
+        S.DeviceStack(M, data[:-1])                             # solvers.jl:11
+    with pytest.raises(ValueError):
+        S.fg_(True, np.empty(4), x, ds, data)
+    with pytest.raises(ValueError):
+        S.composite_(np.empty(63), x, ds)                       # fitting_base.jl:58
+
+
+# ------------------------------------------------------------------ seeded parity vs oracle + quad arbiter
+SHAPES = [(1, 1), (7, 3), (64, 16), (100, 100), (999, 37), (9801, 142), (4096, 600), (10000, 100), (2500, 2400)]
+
+
+@pytest.mark.parametrize("nb,nt", SHAPES)
+def test_fg_parity_f64(S, nb, nt):
+    M, x, data = make_flat_problem(nb, nt, seed=58392 + nb)
+    ds = S.DeviceStack(M, data)
+    nl, G, resid = ds.eval_fg(x * 1.3, want_composite=True)
+    nlq, Gq, gs, compq = O.fg_quad(x * 1.3, M, data)
+    nlo, Go, resid_o = O.fg(x * 1.3, M, data)
+    assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
+    assert nlo == pytest.approx(nlq, rel=RTOL_LOGL)             # the double oracle obeys the same bar
+    assert_grad_close(G, Gq, gs)
+    assert_grad_close(Go, Gq, gs)
+    assert np.allclose(resid, resid_o, rtol=1e-9, atol=1e-12)   # reference side effect on `composite`
+    # logL-only call (G === nothing) and composite!
+    nl2, G2, comp = ds.eval_fg(x * 1.3, want_G=False, want_composite=True)
+    assert G2 is None and nl2 == nl
+    assert np.allclose(comp, compq, rtol=1e-13, atol=0)
+    info = ds.info()
+    assert info.cc_major == 10 and info.fused == 1, "fused sm_100a kernel must be the path that runs"
+
+
+@pytest.mark.parametrize("tile,cluster", [(16, 1), (16, 2), (32, 2), (32, 4), (64, 4), (64, 8), (32, 8), (16, 8)])
+def test_fused_configs_agree(S, tile, cluster):
+    nb, nt = 3001, 517
+    M, x, data = make_flat_problem(nb, nt, seed=11)
+    nlq, Gq, gs, _ = O.fg_quad(x, M, data)
+    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster)
+    i = ds.info()
+    assert i.fused == 1 and i.tile_bins == tile and i.cluster == cluster
+    nl, G, _ = ds.eval_fg(x)
+    assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
+    assert_grad_close(G, Gq, gs)
+
+
+def test_unfused_two_pass_agrees(S):
+    M, x, data = make_flat_problem(5000, 301, seed=5)
+    nlq, Gq, gs, _ = O.fg_quad(x, M, data)
+    ds = S.DeviceStack(M, data, force_unfused=True)
+    assert ds.info().fused == 0
+    nl, G, _ = ds.eval_fg(x)
+    assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
+    assert_grad_close(G, Gq, gs)
+
+
+def test_bitwise_determinism(S):
+    M, x, data = make_flat_problem(20000, 500, seed=3)
+    ds = S.DeviceStack(M, data)
+    a = ds.eval_fg(x)
+    for _ in range(5):
+        b = ds.eval_fg(x)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    ds2 = S.DeviceStack(M, data)                                # a second upload, another context
+    c = ds2.eval_fg(x)
+    assert a[0] == c[0] and np.array_equal(a[1], c[1])
+
+
+@pytest.mark.parametrize("nb,nt", [(100, 100), (9801, 142), (11250, 2000), (5000, 2400)])
+def test_fg_parity_f32_storage(S, nb, nt):
+    """Float32-stored templates, FP64 accumulation, vs exact arithmetic on the same stored values (1e-6)."""
+    M, x, data = make_flat_problem(nb, nt, seed=77, dtype=np.float32)
+    eps32 = float(np.finfo(np.float32).eps)
+    ds = S.DeviceStack(M, data)
+    assert ds.info().dtype == 0 and ds.info().clamp_eps == eps32
+    nl, G, _ = ds.eval_fg(x)
+    nlq, Gq, gs = O.fg_quad_f32(x, M, data)
+    assert nl == pytest.approx(nlq, rel=RTOL_F32)
+    assert_grad_close(G, Gq, gs, rtol=RTOL_F32)
+    assert isinstance(S.fg_(True, None, x, ds, data), np.float32)   # returned scalar typed like the stack
+
+
+# ------------------------------------------------------------------ semantics the reference fixes (SURVEY 8a checklist)
+def test_edge_semantics(S):
+    eps = np.finfo(np.float64).eps
+    # zero-sum guard: m == n everywhere -> every term 0 -> logL = -Inf -> fg! returns +Inf (fitting_base.jl:95)
+    M = np.asfortranarray(np.eye(6)); data = np.ones(6)
+    ds = S.DeviceStack(M, data)
+    nl, G, _ = ds.eval_fg(np.ones(6))
+    assert nl == np.inf and np.array_equal(G, np.zeros(6))
+    # clamp: composite <= 0 -> eps (fitting_base.jl:90,277): zero and negative coefficients
+    nl, G, _ = ds.eval_fg(np.zeros(6))
+    nlo, Go, _ = O.fg(np.zeros(6), M, data)
+    assert nl == pytest.approx(nlo, rel=1e-14) and np.allclose(G, Go, rtol=1e-14)
+    assert G[0] == pytest.approx(1 - 1 / eps)
+    nl, G, _ = ds.eval_fg(-np.ones(6))
+    nlo, Go, _ = O.fg(-np.ones(6), M, data)
+    assert nl == pytest.approx(nlo, rel=1e-14) and np.allclose(G, Go, rtol=1e-14)
+    # zero-count bins contribute -m_i and -c_ij; fractional "data" is legal (mzr_test.jl:66)
+    M2, x2, _ = make_flat_problem(300, 9, seed=2)
+    d2 = M2 @ x2
+    d2[::3] = 0.0
+    ds2 = S.DeviceStack(M2, d2)
+    nl, G, _ = ds2.eval_fg(x2 * 0.9)
+    nlq, Gq, gs, _ = O.fg_quad(x2 * 0.9, M2, d2)
+    assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
+    assert_grad_close(G, Gq, gs)
+    # NaN propagates
+    xn = x2.copy(); xn[4] = np.nan
+    nl, G, _ = ds2.eval_fg(xn)
+    assert np.isnan(nl) and np.isnan(G).all()
+    # Int64 and Float32 data on a Float64 stack (fitting_core_test.jl:38)
+    di = np.arange(300, dtype=np.int64) % 7
+    a = S.DeviceStack(M2, di).eval_fg(x2); b = S.DeviceStack(M2, di.astype(np.float64)).eval_fg(x2)
+    c = S.DeviceStack(M2, di.astype(np.float32)).eval_fg(x2)
+    assert a[0] == b[0] == c[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[1], c[1])
+    # set_data rebinding (MCMCModelDistance-style callers)
+    s3 = S.DeviceStack(M2, di)
+    s3.set_data(d2)
+    assert s3.eval_fg(x2 * 0.9)[0] == pytest.approx(nlq, rel=RTOL_LOGL)
+
+
+def test_row_shards_sum_to_whole(S):
+    """Bin-row sharding: logL and G are sums over shards."""
+    M, x, data = make_flat_problem(7777, 260, seed=8)
+    whole = S.DeviceStack(M, data)
+    nl, G, _ = whole.eval_fg(x)
+    cuts = [0, 1000, 1001, 5000, 7777]
+    parts = [S.DeviceStack(M, data, rows=(a, b)).eval_fg(x) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert sum(p[0] for p in parts) == pytest.approx(nl, rel=1e-13)
+    assert np.allclose(sum(p[1] for p in parts), G, rtol=1e-11, atol=1e-9)
+    Ms, ds_ = S.DeviceStack(M, data, rows=(1000, 1001)).download()
+    assert np.array_equal(Ms, M[1000:1001]) and np.array_equal(ds_, data[1000:1001])
+
+
+def test_concurrent_callers_share_a_stack(S):
+    """Many host threads, one immutable stack, one context each (hmc_sample.jl:127,135)."""
+    import threading
+    M, x, data = make_flat_problem(6000, 200, seed=4)
+    ds = S.DeviceStack(M, data)
+    ref = [ds.eval_fg(x * (1 + 0.01 * k)) for k in range(8)]
+    out = [None] * 8
+
+    def work(k):
+        for _ in range(10):
+            out[k] = ds.eval_fg(x * (1 + 0.01 * k))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for k in range(8):
+        assert out[k][0] == ref[k][0] and np.array_equal(out[k][1], ref[k][1])
+
+
+# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+@pytest.mark.parametrize("nb,nt,dtype", [(60000, 2400, np.float64), (40000, 500, np.float64), (200000, 1000, np.float32)])
+def test_full_size_properties(S, nb, nt, dtype):
+    rng = np.random.default_rng(1)
+    x = 100 * rng.random(nt)
+    ds = S.DeviceStack.synthetic(nb, nt, dtype, seed=94823, scale=1.0, x_true=x)
+    assert ds.info().fused == 1
+    x1 = x * (1 + 0.05 * rng.standard_normal(nt))
+    nl, G, resid = ds.eval_fg(x1, want_composite=True)
+    _, _, comp = ds.eval_fg(x1, want_G=False, want_composite=True)
+    Md, data = ds.download()
+    # (1) checksum of checksums:  sum_j x_j G_j == sum_i m_i (1 - n_i/m_i) == sum_i (m_i - n_i)
+    assert np.dot(x1, G) == pytest.approx(np.sum(comp - data), rel=1e-9)
+    # (2) residual identity and logL recomputed from the returned composite in numpy float64
+    assert np.allclose(resid, 1 - data / comp, rtol=1e-12)
+    term = np.where(data > 0, data - comp - data * np.log(np.where(data > 0, data, 1) / comp), -comp)
+    assert nl == pytest.approx(-term.sum(), rel=1e-11)
+    # (3) linearity of composite!
+    _, _, comp2 = ds.eval_fg(2.5 * x1, want_G=False, want_composite=True)
+    assert np.allclose(comp2, 2.5 * comp, rtol=1e-13)
+    # (4) a spot check of a few gradient components and composite rows against the oracle on the downloaded stack
+    js = [0, 1, nt // 2, nt - 1]
+    for j in js:
+        assert G[j] == pytest.approx(float(np.dot(Md[:, j].astype(np.float64), resid)), rel=1e-9, abs=1e-6)
+    rows = [0, 1, nb // 3, nb - 1]
+    for i in rows:
+        assert comp[i] == pytest.approx(float(np.dot(Md[i, :].astype(np.float64), x1)), rel=1e-12)
+    # (5) shards of the SAME synthetic matrix reproduce the whole (counter-based generator)
+    h = nb // 2 + 7
+    a = S.DeviceStack.synthetic(nb, nt, dtype, seed=94823, scale=1.0, x_true=x, rows=(0, h)).eval_fg(x1)
+    b = S.DeviceStack.synthetic(nb, nt, dtype, seed=94823, scale=1.0, x_true=x, rows=(h, nb)).eval_fg(x1)
+    assert a[0] + b[0] == pytest.approx(nl, rel=1e-12)
+    assert np.allclose(a[1] + b[1], G, rtol=1e-9, atol=1e-6)

@@ -1,0 +1,198 @@
+"""GPU parity tests of the hierarchical path (calculate_coeffs, the MZR/AMR fg! chain rules, the
+HierarchicalOptimizer / HMCModel / MCMCModel adapters) and of the batched-walker kernel, through the
+C-ABI, against the CPU oracle (itself pinned by complex-step differentiation: test_oracle_chainrule.py).
+
+Structure follows test/fitting/mzr_test.jl and amr_test.jl: fg! value + gradient (:78-80), stacked layout
+(:82-84), age-permutation invariance (:87-112), logdensity_and_gradient with / without Jacobian and with
+sigma or MH0 fixed (:115-176).  Tolerances as in test_gpu_core.py.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import make_flat_problem, make_hier_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sfh_b200
+    assert sfh_b200.device_count() >= 1
+    return sfh_b200
+
+
+def models_for(S, kind):
+    return {O.POWERLAW_MZR: (S.PowerLawMZR(1.0, -2.0, 6.0), (6.0,)),
+            O.LINEAR_AMR: (S.LinearAMR(0.05, -1.6, 12.0), (12.0,)),
+            O.LOG_AMR: (S.LogarithmicAMR(1e-4, 5e-5, 12.0), (12.0, 0.01524, 0.2485, 1.78))}[kind]
+
+
+def build(S, kind, shuffle=False, ragged=False, nb=1500, noisy=True, nj=21, nk=26):
+    p = make_hier_problem(nj=nj, nk=nk, nb=nb, shuffle=shuffle, ragged=ragged)
+    model, fixed = models_for(S, kind)
+    x = O.calculate_coeffs(kind, model.alpha, model.beta, fixed, 0.2, p["R"], p["logAge"], p["MH"])
+    lam = p["M"] @ x
+    data = p["rng"].poisson(lam).astype(np.float64) if noisy else lam
+    v = np.concatenate([p["R"], [model.alpha, model.beta, 0.2]])
+    return p, model, fixed, v, data
+
+
+KINDS = [O.POWERLAW_MZR, O.LINEAR_AMR, O.LOG_AMR]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("shuffle,ragged", [(False, False), (True, False), (True, True)])
+def test_calculate_coeffs_device(S, kind, shuffle, ragged):      # mzr.jl:50-79 / amr.jl:50-73
+    p, model, fixed, v, data = build(S, kind, shuffle, ragged)
+    ds = S.DeviceStack(p["M"], data)
+    got = S.calculate_coeffs(model, S.GaussianDispersion(0.2), p["R"], p["logAge"], p["MH"], models=ds)
+    want = O.calculate_coeffs(kind, model.alpha, model.beta, fixed, 0.2, p["R"], p["logAge"], p["MH"])
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    uniq = p["logAge"][np.sort(np.unique(p["logAge"], return_index=True)[1])]
+    for j, a in enumerate(uniq):                                  # sum_k r_jk == R_j  (mzr_test.jl:32-34)
+        assert got[p["logAge"] == a].sum() == pytest.approx(p["R"][j], rel=1e-12)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("shuffle,ragged", [(False, False), (True, False), (True, True)])
+def test_fg_hier_parity(S, kind, shuffle, ragged):                # mzr_test.jl:78-84 / amr_test.jl:69-106
+    p, model, fixed, v, data = build(S, kind, shuffle, ragged)
+    disp = S.GaussianDispersion(0.2)
+    ds = S.DeviceStack(p["M"], data)
+    nlq, Gq, _ = O.fg_hier(kind, fixed, (1, 1, 1), v, p["M"], data, p["logAge"], p["MH"], quad=True)
+    nlo, Go, _ = O.fg_hier(kind, fixed, (1, 1, 1), v, p["M"], data, p["logAge"], p["MH"])
+    G = np.empty(v.shape[0])
+    nl = S.fg_(True, G, model, disp, v, ds, data, None, p["logAge"], p["MH"])
+    assert nl == pytest.approx(nlq, rel=1e-12)
+    # the chain rule amplifies the per-template cancellation: judge against the oracle's own distance to quad
+    scale = np.abs(Gq) + 1e-10 * np.abs(Gq).max()
+    err_gpu = np.max(np.abs(G - Gq) / scale)
+    err_cpu = np.max(np.abs(Go - Gq) / scale)
+    assert err_gpu < max(1e-10, 20 * err_cpu), (err_gpu, err_cpu)
+    # F only (G === nothing)  mzr_test.jl:78
+    assert S.fg_(True, None, model, disp, v, ds, data, None, p["logAge"], p["MH"]) == pytest.approx(nlq, rel=1e-12)
+    # perturbed start (mzr_test.jl:180-182 uses 1.5x) -- away from the optimum plain relative error holds
+    v2 = v.copy(); v2[:-3] *= 1.5; v2[-3] *= 1.2; v2[-1] *= 1.3
+    nlq2, Gq2, _ = O.fg_hier(kind, fixed, (1, 1, 1), v2, p["M"], data, p["logAge"], p["MH"], quad=True)
+    G2 = np.empty(v.shape[0])
+    assert S.fg_(True, G2, model, disp, v2, ds, data, None, p["logAge"], p["MH"]) == pytest.approx(nlq2, rel=1e-12)
+    assert np.max(np.abs(G2 - Gq2) / (np.abs(Gq2) + 1e-12 * np.abs(Gq2).max())) < 1e-9
+
+
+@pytest.mark.parametrize("kind", [O.POWERLAW_MZR, O.LINEAR_AMR])
+def test_age_permutation_invariance(S, kind):                     # mzr_test.jl:87-112
+    p, model, fixed, v, data = build(S, kind)
+    disp = S.GaussianDispersion(0.2)
+    nj, nk = 21, 26
+    G = np.empty(nj + 3)
+    nl = S.fg_(True, G, model, disp, v, S.DeviceStack(p["M"], data), data, None, p["logAge"], p["MH"])
+    perm = np.random.default_rng(3).permutation(nj)
+    cols = np.concatenate([np.arange(j * nk, (j + 1) * nk) for j in perm])
+    v2 = np.concatenate([v[:nj][perm], v[nj:]])
+    G2 = np.empty(nj + 3)
+    nl2 = S.fg_(True, G2, model, disp, v2, S.DeviceStack(p["M"][:, cols], data), data, None, p["logAge"][cols], p["MH"][cols])
+    assert nl2 == pytest.approx(nl, rel=1e-12)
+    assert np.allclose(G2, np.concatenate([G[:nj][perm], G[nj:]]), rtol=1e-8, atol=1e-12 * np.abs(G).max())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_free_masks_and_logdensity(S, kind):                      # mzr_test.jl:115-176
+    p, model0, fixed, v, data = build(S, kind)
+    nj = 21
+    ds = S.DeviceStack(p["M"], data)
+    a, b, s = model0.alpha, model0.beta, 0.2
+    tf = list(model0.transforms()) + [1]
+    for free in [(True, True, True), (True, True, False), (True, False, True), (False, True, True)]:
+        model = type(model0)(a, b, fixed[0], free[:2]) if kind != O.LOG_AMR else S.LogarithmicAMR(a, b, fixed[0], free[:2])
+        disp = S.GaussianDispersion(s, (free[2],))
+        G = np.empty(nj + 3)
+        nl = S.fg_(True, G, model, disp, v, ds, data, None, p["logAge"], p["MH"])
+        nlo, Go, _ = O.fg_hier(kind, fixed, [int(f) for f in free], v, p["M"], data, p["logAge"], p["MH"])
+        assert nl == pytest.approx(nlo, rel=1e-12)
+        for i in range(3):
+            if not free[i]:
+                assert G[nj + i] == 0.0                           # mzr.jl:175,196,201
+        assert np.allclose(G, Go, rtol=1e-7, atol=1e-9 * np.abs(Go).max())
+        pars = np.array([a, b, s]); fm = np.array(free)
+        tpar = np.array([np.log(pv) if t == 1 else pv for pv, t in zip(pars, tf)])
+        xvec = np.concatenate([np.log(p["R"]), tpar[fm]])
+        for jac in (False, True):
+            opt = S.HierarchicalOptimizer(model, disp, ds, data, p["logAge"], p["MH"], True, True, jac)
+            assert opt.dimension() == nj + fm.sum()
+            lp, gr = opt.logdensity_and_gradient(xvec)
+            lpo, gro = O.hier_logdensity_and_gradient(kind, fixed, [int(f) for f in free], (a, b, s), xvec, p["M"], data,
+                                                      p["logAge"], p["MH"], jacobian_corrections=jac)
+            assert lp == pytest.approx(lpo, rel=1e-12)
+            assert gr.shape == (nj + fm.sum(),) and np.allclose(gr, gro, rtol=1e-7, atol=1e-9 * np.abs(gro).max())
+        # F-only and G-only protocol (generic_fitting.jl:172-178,195-197)
+        assert S.HierarchicalOptimizer(model, disp, ds, data, p["logAge"], p["MH"], True, None, True).logdensity_and_gradient(xvec) == pytest.approx(lp, rel=1e-13)
+
+
+def test_hier_errors(S):
+    p, model, fixed, v, data = build(S, O.POWERLAW_MZR, nb=200)
+    ds = S.DeviceStack(p["M"], data)
+    disp = S.GaussianDispersion(0.2)
+    with pytest.raises(ValueError):                               # mzr.jl:55
+        S.fg_(True, None, model, disp, v[:-1], ds, data, None, p["logAge"], p["MH"])
+    with pytest.raises(ValueError):                               # mzr.jl:57
+        S.fg_(True, None, model, disp, v, ds, data, None, p["logAge"], p["MH"][:-1])
+    with pytest.raises(ValueError):                               # mzr.jl:126
+        S.fg_(True, np.empty(3), model, disp, v, ds, data, None, p["logAge"], p["MH"])
+
+
+def test_hier_full_config3_shape(S):
+    """BASELINE config 3: 60 ages x 40 [M/H] = 2400 templates; bins reduced so the oracle finishes in seconds."""
+    p = make_hier_problem(nj=60, nk=40, nb=3000, la_hi=10.1, la_lo=6.6)
+    model, disp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
+    x = O.calculate_coeffs(O.POWERLAW_MZR, 1.0, -2.0, (6.0,), 0.2, p["R"], p["logAge"], p["MH"])
+    data = p["rng"].poisson(p["M"] @ x).astype(np.float64)
+    v = np.concatenate([p["R"], [1.0, -2.0, 0.2]]) * 1.1
+    ds = S.DeviceStack(p["M"], data)
+    G = np.empty(63)
+    nl = S.fg_(True, G, model, disp, v, ds, data, None, p["logAge"], p["MH"])
+    nlq, Gq, _ = O.fg_hier(O.POWERLAW_MZR, (6.0,), (1, 1, 1), v, p["M"], data, p["logAge"], p["MH"], quad=True)
+    assert nl == pytest.approx(nlq, rel=1e-12)
+    assert np.max(np.abs(G - Gq) / (np.abs(Gq) + 1e-12 * np.abs(Gq).max())) < 1e-9
+
+
+# ------------------------------------------------------------------ sampler adapters
+def test_hmc_model(S):                                            # hmc_sample.jl:24-37
+    M, x, data = make_flat_problem(4000, 64, seed=21)
+    hm = S.HMCModel(M, None, data)
+    assert hm.dimension() == 64
+    logx = np.log(x) + 0.01
+    lp, g = hm.logdensity_and_gradient(logx)
+    lpo, go = O.hmc_logdensity_and_gradient(logx, M, data)
+    assert lp == pytest.approx(lpo, rel=1e-12) and np.allclose(g, go, rtol=1e-8, atol=1e-8 * np.abs(go).max())
+    assert hm.logdensity(logx) == pytest.approx(lpo, rel=1e-12)
+
+
+@pytest.mark.parametrize("nb,nt,W", [(4000, 64, 1), (5000, 100, 37), (9801, 142, 256), (40000, 500, 128)])
+def test_batched_walkers(S, nb, nt, W):                           # mcmc_sample.jl:12-23
+    M, x, data = make_flat_problem(nb, nt, seed=31)
+    rng = np.random.default_rng(5)
+    X = np.maximum(0.0, x[:, None] + rng.standard_normal((nt, W)))   # examples/fitting1.ipynb cell 143
+    if W > 2:
+        X[3, 1] = -1e-9                                           # one negative entry -> -Inf (:15-19)
+        X[:, 2] = 0.0                                             # exact zeros are legal
+    mm = S.MCMCModel(M, data)
+    got = mm.batch(X)
+    want = O.mcmc_logl(X, M, data)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.array_equal(got[~fin], want[~fin])                  # -Inf exactly
+    assert np.allclose(got[fin], want[fin], rtol=1e-12, atol=0)
+    assert mm(X[:, 0]) == pytest.approx(want[0], rel=1e-12)
+    # agrees with the fused single-vector path
+    nl, _, _ = mm.models.eval_fg(X[:, 0], want_G=False)
+    assert got[0] == pytest.approx(-nl, rel=1e-13)
+
+
+def test_batched_walkers_f32_stack(S):
+    M, x, data = make_flat_problem(6000, 120, seed=33, dtype=np.float32)
+    X = np.maximum(0.0, x[:, None] + np.random.default_rng(6).standard_normal((120, 40)))
+    got = S.MCMCModel(M, data).batch(X)
+    for w in (0, 7, 39):
+        nlq, _, _ = O.fg_quad_f32(X[:, w], M, data, want_G=False)
+        assert got[w] == pytest.approx(-nlq, rel=1e-6)
