@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract in the task statement, tier section 4).
+
+A "step" is ONE fused evaluation of fg! (composite -> Poisson logL -> gradient; src/fitting/solvers.jl:20-38)
+over the BASELINE.json headline stack: 200x300 bins x 2400 templates (60 ages x 40 [M/H]), Float64,
+Poisson-sampled synthetic Hess diagram.  Each rank holds one such stack (N>1: a bin-row shard of an N x larger
+Hess diagram, [logL, G] all-reduced with NCCL on the kernel's stream every step => weak scaling).
+
+  value       evaluations/s with everything resident in HBM, timed with CUDA events on the launching stream
+  e2e         same through the reference-facing C-ABI call sfh_eval_fg with HOST buffers (H2D coeffs, D2H [-logL, G])
+  roofline    algorithmic bytes of the fused kernel / its event-timed duration, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's threaded two-pass port of the reference algorithm on this box's host cores
+
+  --impl reference : the reference arm = that same CPU port, all host threads, on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB, NJ, NK = 200 * 300, 60, 40
+NT = NJ * NK
+SEED = 94823
+METRIC = "fused loglikelihood+gradient evaluations/sec (fg!), 200x300 bins x 2400 templates Float64"
+UNIT = "evals/s"
+WORKLOAD = "config3: fit_sfh PowerLawMZR+GaussianDispersion stack, 60000 bins x 2400 templates (60 logAge x 40 [M/H]), Float64, Poisson data"
+
+
+def truth_coeffs():
+    """r_jk of mzr_test.jl:52-63 scaled to config 3: R = 1e6 U(0,1), PowerLawMZR(1,-2,6), GaussianDispersion(0.2).
+    Host float64 formulae (one-shot set-up, not the timed path)."""
+    rng = np.random.Generator(np.random.Philox(SEED))
+    uA = np.linspace(10.1, 6.6, NJ)
+    uM = np.linspace(-2.5, 0.0, NK)
+    R = rng.random(NJ) * 1e6
+    cum = np.cumsum(R)                      # ages already sorted oldest -> youngest
+    mu = -2.0 + 1.0 * (np.log10(cum) - 6.0)
+    A = np.exp(-(((uM[None, :] - mu[:, None]) / 0.2) ** 2) / 2)
+    r = (A * R[:, None] / A.sum(axis=1, keepdims=True)).reshape(-1)
+    return r
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling guide recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        return json.load(open(p)).get("fused_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def host_stack(nb, nt, x, seed=SEED):
+    """Synthetic stack on the HOST for the CPU arms (numpy Philox): U(0,1)/1e5 templates, Poisson(M x) data."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    M = np.empty((nb, nt), dtype=np.float64, order="F")
+    for j0 in range(0, nt, 100):
+        j1 = min(nt, j0 + 100)
+        M[:, j0:j1] = rng.random((nb, j1 - j0)) / 1e5
+    data = rng.poisson(M @ x).astype(np.float64)
+    return M, data
+
+
+def time_cpu(M, data, x, budget_s=12.0, min_steps=3, max_steps=200):
+    import oracle as O
+    G = np.empty(M.shape[1]); Cm = np.empty(M.shape[0])
+    O.fg_omp(x, M, data, G=G, Cm=Cm)        # warm-up (page-in)
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while (len(ts) < min_steps or time.perf_counter() < t_end) and len(ts) < max_steps:
+        t0 = time.perf_counter()
+        O.fg_omp(x, M, data, G=G, Cm=Cm)
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), len(ts), O.num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm (two-pass gemv 'N' / Poisson / residual / gemv 'T') on the host
+    cores.  Julia cannot run in this image, so this is the oracle PORT (cpu_baseline.kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle as O
+    x = truth_coeffs() * 1.02
+    M, data = host_stack(NB, NT, x)
+    G = np.empty(NT); Cm = np.empty(NB)
+    for _ in range(max(args.warmup, 1)):
+        O.fg_omp(x, M, data, G=G, Cm=Cm)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.fg_omp(x, M, data, G=G, Cm=Cm)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    cores = O.num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm: one full-size stack on rank 0, host cores only"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full evaluations of the 60000x2400 F64 stack (OpenMP two-pass port of "
+                                       f"fitting_base.jl:55-65,84-96,265-285; julia not installed)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--nw", type=int, default=0, help="consumer warps per CTA (8 or 16; 0 = auto)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import sfh_b200 as S
+    L = S._lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- one config-3 stack per rank, generated on device (counter-based: shards of one N x larger diagram)
+    x_true = truth_coeffs()
+    nb_total = NB * world
+    ds = S.DeviceStack.synthetic(nb_total, NT, np.float64, seed=SEED, scale=1e-5, x_true=x_true, device=local,
+                                 rows=(rank * NB, (rank + 1) * NB), tile_bins=args.tile, cluster=args.cluster,
+                                 consumer_warps=args.nw)
+    info = ds.info()
+    assert info.fused == 1, "fused sm_100a kernel not selected"
+    stream = torch.cuda.Stream()          # an explicit non-default stream: the kernels AND the timing events live on it
+    torch.cuda.set_stream(stream)
+    ctx = ds.new_ctx(stream.cuda_stream)
+    if world > 1:
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            L.check(L.lib.sfh_comm_unique_id(idbuf))
+        obj = [bytes(idbuf)]
+        dist.broadcast_object_list(obj, src=0)
+        L.check(L.lib.sfh_comm_init(ctx.handle, world, rank, obj[0]))
+
+    x = x_true * 1.02
+    d_x = torch.tensor(x, dtype=torch.float64, device="cuda")
+    d_out = torch.zeros(1 + NT, dtype=torch.float64, device="cuda")
+
+    def step():
+        L.check(L.lib.sfh_enqueue_fg(ctx.handle, d_x.data_ptr(), d_out.data_ptr(), 1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st0 = L.sfh_stats()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    L.check(L.lib.sfh_ctx_stats(ctx.handle, C.byref(st0)))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    st1 = L.sfh_stats()
+    L.check(L.lib.sfh_ctx_stats(ctx.handle, C.byref(st1)))
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the reference-facing call, host buffers in/out, H2D + D2H inside the timed region
+    G = np.empty(NT)
+    nl = C.c_double()
+    xh = np.ascontiguousarray(x)
+    dp = C.POINTER(C.c_double)
+    for _ in range(args.warmup):
+        L.check(L.lib.sfh_eval_fg(ctx.handle, xh.ctypes.data_as(dp), C.byref(nl), G.ctypes.data_as(dp), None))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        L.check(L.lib.sfh_eval_fg(ctx.handle, xh.ctypes.data_as(dp), C.byref(nl), G.ctypes.data_as(dp), None))
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0      # the caller-visible time of K synchronous calls (>= the event time)
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), 1e3 * wall)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item())
+    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # sanity of what was timed: the device-resident and the host-API paths agree
+    torch.cuda.synchronize()
+    out_host = d_out.cpu().numpy()
+    assert np.isfinite(nl.value) and abs(-out_host[0] - nl.value) <= 1e-12 * abs(nl.value)
+    assert np.array_equal(out_host[1:], G)
+
+    # ---- roofline of the dominant (fused) kernel: CUDA events around that kernel only, on its launch stream
+    ms_eval, ms_kernel = C.c_double(), C.c_double()
+    L.check(L.lib.sfh_time_fg(ctx.handle, xh.ctypes.data_as(dp), min(args.steps, 50), 1, 0, C.byref(ms_eval), C.byref(ms_kernel)))
+    bytes_alg = NB * NT * 8 + NB * 8 + 2 * NT * 8 + 8
+    peak, peak_src = measured_peaks()
+    achieved = bytes_alg / (ms_kernel.value * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "kernel": "sfh_fg_fused_kernel<double,%d,%d,true>" % (info.tile_bins, info.consumer_warps),
+                "kernel_ms": ms_kernel.value, "bytes_alg_per_launch": bytes_alg, "peak_source": peak_src}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Mh, dh = ds.download()
+        t_med, n_cpu, cores = time_cpu(Mh, dh, x)
+        cpu = {"value": 1.0 / t_med, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} full evaluations of the same 60000x2400 F64 stack (downloaded from the GPU), median; "
+                         "OpenMP two-pass port of the reference's gemv'N'/Poisson/residual/gemv'T' (julia not installed)"}
+        del Mh
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_stack_bytes": int(info.stack_bytes),
+                       "l2": "inputs (1.15 GB/GPU) larger than L2 (126 MB); no flush needed",
+                       "sharding": "bin rows, one 60000-bin shard per GPU; NCCL allreduce of [logL,G] (2401 f64) per step" if world > 1 else "single GPU",
+                       "value_unit_note": "N>1: value = N shard-evaluations per all-reduced step / time (weak scaling)",
+                       "tile_bins": info.tile_bins, "cluster": info.cluster, "chunks_per_tile": info.chunks_per_tile,
+                       "ring_slots": info.ring_slots, "n_clusters": info.n_clusters, "consumer_warps": info.consumer_warps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NT * 8, "d2h_bytes_per_step": (NT + 1) * 8,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

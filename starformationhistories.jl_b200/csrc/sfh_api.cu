@@ -119,7 +119,7 @@ struct sfh_stack {
     double eps = 0.0;
     // kernel configuration
     bool fused = false;
-    int bt = 0, cluster = 1, kt = 0, ring = 0, n_clusters = 0, n_tiles = 0;
+    int bt = 0, cluster = 1, kt = 0, ring = 0, n_clusters = 0, n_tiles = 0, nw = 16;
     uint32_t smem = 0;
     bool evict_first = false;
     CUtensorMap tmap;
@@ -165,28 +165,28 @@ namespace {
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB
 
 struct TileGeom { int vec, lpr, rpw, rpc; };
-TileGeom geom(int dtype, int bt) {
+TileGeom geom(int dtype, int bt, int nw) {
     TileGeom g;
     g.vec = 16 / (int)elem_size(dtype);
     g.lpr = bt / g.vec;
     g.rpw = 32 / g.lpr;
-    g.rpc = g.rpw * kConsumerWarps;
+    g.rpc = g.rpw * nw;
     return g;
 }
 
-template <typename S, int BT, bool G>
+template <typename S, int BT, int NW, bool G>
 cudaError_t set_attr(uint32_t smem, bool nonportable) {
-    auto k = sfh_fg_fused_kernel<S, BT, G>;
+    auto k = sfh_fg_fused_kernel<S, BT, NW, G>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (nonportable) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     return e;
 }
-template <typename S, int BT, bool G>
+template <typename S, int BT, int NW, bool G>
 cudaError_t max_clusters(const sfh_stack *s, int *out) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s->cluster * 1024u);
-    cfg.blockDim = dim3(kFusedThreads);
+    cfg.blockDim = dim3((NW + 1) * 32);
     cfg.dynamicSmemBytes = s->smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -195,13 +195,13 @@ cudaError_t max_clusters(const sfh_stack *s, int *out) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(out, sfh_fg_fused_kernel<S, BT, G>, &cfg);
+    return cudaOccupancyMaxActiveClusters(out, sfh_fg_fused_kernel<S, BT, NW, G>, &cfg);
 }
-template <typename S, int BT, bool G>
+template <typename S, int BT, int NW, bool G>
 cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(s->n_clusters * s->cluster));
-    cfg.blockDim = dim3(kFusedThreads);
+    cfg.blockDim = dim3((NW + 1) * 32);
     cfg.dynamicSmemBytes = s->smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -211,59 +211,84 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, G>, s->tmap, p);
+    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G>, s->tmap, p);
 }
 
-#define SFH_DISPATCH(s, want_g, CALL)                                             \
-    [&]() -> cudaError_t {                                                        \
-        if ((s)->dtype == SFH_F64) {                                              \
-            switch ((s)->bt) {                                                    \
-            case 64: return (want_g) ? CALL(double, 64, true) : CALL(double, 64, false); \
-            case 32: return (want_g) ? CALL(double, 32, true) : CALL(double, 32, false); \
-            default: return (want_g) ? CALL(double, 16, true) : CALL(double, 16, false); \
-            }                                                                     \
-        } else {                                                                  \
-            switch ((s)->bt) {                                                    \
-            case 128: return (want_g) ? CALL(float, 128, true) : CALL(float, 128, false); \
-            case 64: return (want_g) ? CALL(float, 64, true) : CALL(float, 64, false);   \
-            default: return (want_g) ? CALL(float, 32, true) : CALL(float, 32, false);   \
-            }                                                                     \
-        }                                                                         \
+#define SFH_DISPATCH_G(S, BT, NW, want_g, CALL) ((want_g) ? CALL(S, BT, NW, true) : CALL(S, BT, NW, false))
+#define SFH_DISPATCH_NW(S, BT, s, want_g, CALL) \
+    (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, want_g, CALL) : SFH_DISPATCH_G(S, BT, 16, want_g, CALL))
+#define SFH_DISPATCH(s, want_g, CALL)                                      \
+    [&]() -> cudaError_t {                                                 \
+        if ((s)->dtype == SFH_F64) {                                       \
+            switch ((s)->bt) {                                             \
+            case 64: return SFH_DISPATCH_NW(double, 64, s, want_g, CALL);  \
+            case 32: return SFH_DISPATCH_NW(double, 32, s, want_g, CALL);  \
+            default: return SFH_DISPATCH_NW(double, 16, s, want_g, CALL);  \
+            }                                                              \
+        } else {                                                           \
+            switch ((s)->bt) {                                             \
+            case 128: return SFH_DISPATCH_NW(float, 128, s, want_g, CALL); \
+            case 64: return SFH_DISPATCH_NW(float, 64, s, want_g, CALL);   \
+            default: return SFH_DISPATCH_NW(float, 32, s, want_g, CALL);   \
+            }                                                              \
+        }                                                                  \
     }()
 
-// choose tile / cluster / ring for this stack; returns false if the fused tiling cannot hold T
+// choose consumer warps / tile / cluster / ring for this stack; false if the fused tiling cannot hold T.
+// Candidates are scored by a simple model fitted to the round-1 sweeps (profiles/round1_sweep.md):
+//   * every SM should host a CTA: clusters of 8 only pack 15 per B200 (120 SMs), 4 -> 37, 2 -> 74;
+//   * the per-tile exchange costs ~1 us, so tiles should carry >= ~8 chunks, and two co-resident CTAs
+//     (NW = 8) hide it;
+//   * prefer larger bin tiles (longer contiguous TMA rows) when the above are equal.
 bool choose_config(sfh_stack *s, const sfh_opts *o) {
     const int cands64[3] = {64, 32, 16}, cands32[3] = {128, 64, 32};
     const int *cands = (s->dtype == SFH_F64) ? cands64 : cands32;
-    int best_bt = 0, best_c = 0, best_kt = 0;
-    for (int ci = 0; ci < 3; ++ci) {
-        const int bt = cands[ci];
-        if (o && o->tile_bins && o->tile_bins != bt) continue;
-        const TileGeom g = geom(s->dtype, bt);
-        int c_found = 0, kt_found = 0;
-        const int cl_opts[5] = {1, 2, 4, 8, 16};
-        for (int c : cl_opts) {
-            if (o && o->cluster && o->cluster != c) continue;
-            const int64_t kt = (s->nt + (int64_t)c * g.rpc - 1) / ((int64_t)c * g.rpc);
-            if (kt <= kKMax) { c_found = c; kt_found = (int)std::max<int64_t>(kt, 1); break; }
+    const int nws[2] = {8, 16};
+    const int cl_opts[5] = {1, 2, 4, 8, 16};
+    double best_score = -1.0;
+    int best_bt = 0, best_c = 0, best_kt = 0, best_nw = 0, best_ring = 0;
+    for (int nw : nws) {
+        if (o && o->consumer_warps && o->consumer_warps != nw) continue;
+        for (int ci = 0; ci < 3; ++ci) {
+            const int bt = cands[ci];
+            if (o && o->tile_bins && o->tile_bins != bt) continue;
+            const TileGeom g = geom(s->dtype, bt, nw);
+            if (g.rpc > 256) continue;
+            for (int c : cl_opts) {
+                if (o && o->cluster && o->cluster != c) continue;
+                const int64_t kt64 = std::max<int64_t>((s->nt + (int64_t)c * g.rpc - 1) / ((int64_t)c * g.rpc), 1);
+                if (kt64 > kKMax) continue;
+                const int kt = (int)kt64;
+                const uint32_t budget = (nw == 8) ? (kMaxDynSmem / 2 - 1024) : kMaxDynSmem;  // 2 CTAs/SM need half each
+                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw);
+                if (fixed.total + 64 >= budget) continue;
+                int ring = (int)((budget - fixed.total - 64) / (chunk_bytes(nw) + 16));
+                ring = std::min(ring, 32);
+                if (ring < kt + 2) continue;
+                // --- score ---
+                const int ctas_per_sm = (nw == 8) ? 2 : 1;
+                const int packed = (c <= 2) ? s->sm_count : (c == 4 ? s->sm_count / 4 * 4 : (c == 8 ? 120 : 96));
+                const double sm_frac = std::min(1.0, (double)packed / std::max(s->sm_count, 1));
+                const int64_t n_tiles = (s->rows + bt - 1) / bt;
+                const int64_t n_cl = std::max<int64_t>((int64_t)packed * ctas_per_sm / c, 1);
+                const double waves = (double)n_tiles / (double)n_cl;
+                const double balance = waves >= 1.0 ? waves / std::ceil(waves) : waves;  // tail effect
+                const double tile_us = (double)kt * chunk_bytes(nw) / 40e3;              // ~40 GB/s per SM
+                const double overlap = (nw == 8) ? 0.35 : 1.0;                            // exposed part of ~1 us
+                const double eff = tile_us / (tile_us + overlap * 1.0);
+                const double rowlen = std::min(1.0, 0.85 + 0.15 * (bt * elem_size(s->dtype)) / 512.0);
+                const double score = sm_frac * balance * eff * rowlen;
+                const bool forced = o && (o->tile_bins || o->cluster || o->consumer_warps);
+                if (score > best_score || (forced && best_bt == 0)) {
+                    best_score = score; best_bt = bt; best_c = c; best_kt = kt; best_nw = nw; best_ring = ring;
+                }
+            }
         }
-        if (!c_found) continue;
-        best_bt = bt; best_c = c_found; best_kt = kt_found;
-        // keep the largest tile that still leaves >= 2 tiles per resident cluster (load balance)
-        const int64_t n_tiles = (s->rows + bt - 1) / bt;
-        const int64_t n_cl = std::max(1, s->sm_count / c_found);
-        if (n_tiles >= 2 * n_cl || (o && o->tile_bins)) break;
     }
     if (!best_bt) return false;
-    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt;
-    // ring: everything shared memory allows (>= kt+1 so the producer can always run ahead)
-    const TileGeom g = geom(s->dtype, s->bt);
-    const FusedSmem fixed = FusedSmem::make(0, s->bt, s->cluster, s->kt * g.rpc);
-    int ring = (int)((kMaxDynSmem - fixed.total - 64) / (kChunkBytes + 16));
-    ring = std::min(ring, 27);
-    if (ring < s->kt + 1) return false;
-    s->ring = ring;
-    s->smem = FusedSmem::make(ring, s->bt, s->cluster, s->kt * g.rpc).total;
+    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt; s->nw = best_nw; s->ring = best_ring;
+    const TileGeom g = geom(s->dtype, s->bt, s->nw);
+    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw).total;
     s->n_tiles = (int)((s->rows + s->bt - 1) / s->bt);
     return true;
 }
@@ -276,7 +301,7 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     if (!choose_config(s, o)) return SFH_OK;
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    const TileGeom g = geom(s->dtype, s->bt);
+    const TileGeom g = geom(s->dtype, s->bt, s->nw);
     const cuuint64_t gdim[2] = {(cuuint64_t)s->rows, (cuuint64_t)s->nt};
     const cuuint64_t gstr[1] = {(cuuint64_t)s->ld * elem_size(s->dtype)};
     const cuuint32_t box[2] = {(cuuint32_t)s->bt, (cuuint32_t)g.rpc};
@@ -286,12 +311,12 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     const bool nonport = s->cluster > 8;
-#define SET_ATTR(S, BT, G) set_attr<S, BT, G>(s->smem, nonport)
+#define SET_ATTR(S, BT, NW, G) set_attr<S, BT, NW, G>(s->smem, nonport)
     CU_TRY(SFH_DISPATCH(s, true, SET_ATTR));
     CU_TRY(SFH_DISPATCH(s, false, SET_ATTR));
 #undef SET_ATTR
     int maxcl = 0;
-#define MAX_CL(S, BT, G) max_clusters<S, BT, G>(s, &maxcl)
+#define MAX_CL(S, BT, NW, G) max_clusters<S, BT, NW, G>(s, &maxcl)
     CU_TRY(SFH_DISPATCH(s, true, MAX_CL));
 #undef MAX_CL
     if (maxcl <= 0) return SFH_OK;  // cannot co-schedule this cluster shape: stay unfused
@@ -441,7 +466,7 @@ extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
     info->nbins_total = s->nb_total; info->ntemplates = s->nt; info->row_begin = s->row_begin; info->row_end = s->row_end;
     info->ld = s->ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
     info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
-    info->n_clusters = s->n_clusters; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
+    info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
     info->stack_bytes = (int64_t)((size_t)s->ld * s->nt * elem_size(s->dtype)); info->clamp_eps = s->eps;
     return SFH_OK;
 }
@@ -573,7 +598,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
         p.gstride = c->gstride;
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
-#define LAUNCH(S, BT, G) launch_fused_t<S, BT, G>(s, p, c->stream)
+#define LAUNCH(S, BT, NW, G) launch_fused_t<S, BT, NW, G>(s, p, c->stream)
         CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
 #undef LAUNCH
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));

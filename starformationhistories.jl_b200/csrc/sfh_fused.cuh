@@ -29,12 +29,11 @@
 
 namespace sfh {
 
-constexpr int kConsumerWarps = 16;
-constexpr int kConsumerThreads = kConsumerWarps * 32;  // 512
-constexpr int kFusedThreads = kConsumerThreads + 32;   // + 1 TMA producer warp
-constexpr int kChunkBytes = kConsumerThreads * 16;     // 8192: one 16-byte vector per consumer lane
-constexpr int kKMax = 20;                              // max chunks per CTA per tile (register arrays)
+// NW consumer warps (+1 TMA producer warp) per CTA.  NW = 16: one CTA per SM; NW = 8: two CTAs per SM, so one
+// CTA's exchange/residual latency is hidden behind the other CTA's streaming passes.
+constexpr int kKMax = 20;       // max chunks per CTA per tile (per-lane register array gacc[])
 constexpr int kMaxCluster = 16;
+__host__ __device__ constexpr int chunk_bytes(int nw) { return nw * 32 * 16; }  // one 16-byte vector per consumer lane
 
 struct FusedParams {
     int64_t nb;          // bins in this shard
@@ -52,14 +51,14 @@ struct FusedParams {
     int64_t gstride;
 };
 
-template <typename S, int BT>
+template <typename S, int BT, int NW>
 struct FusedCfg {
     static constexpr int VEC = 16 / sizeof(S);  // elements per 16-byte lane vector
     static constexpr int LPR = BT / VEC;        // lanes per template row
     static constexpr int RPW = 32 / LPR;        // template rows per warp per chunk
-    static constexpr int RPC = RPW * kConsumerWarps;  // template rows per chunk
+    static constexpr int RPC = RPW * NW;        // template rows per chunk
     static_assert(BT % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "bad tile");
-    static_assert(RPC * BT * sizeof(S) == kChunkBytes, "chunk must be 8 KB");
+    static_assert(RPC * BT * sizeof(S) == chunk_bytes(NW), "chunk = one 16-byte vector per consumer lane");
     static_assert(RPC <= 256, "TMA box dimension limit");
 };
 
@@ -68,11 +67,11 @@ struct FusedSmem {
     uint32_t ring_off, red_off, xbuf_off, rbuf_off, cs_off, bar_off, total;
     // cs_elems = kt * RPC: this CTA's slice of the coefficient vector (kept in smem, not registers:
     // 17 warps put 5 warps on one SM sub-partition => 96 registers/thread, too few for c[] + gacc[])
-    __host__ __device__ static FusedSmem make(int ring, int bt, int cluster, int cs_elems) {
+    __host__ __device__ static FusedSmem make(int ring, int bt, int cluster, int cs_elems, int nw) {
         FusedSmem s;
         s.ring_off = 0;
-        s.red_off = ring * kChunkBytes;
-        s.xbuf_off = s.red_off + kConsumerWarps * bt * 8;
+        s.red_off = ring * chunk_bytes(nw);
+        s.xbuf_off = s.red_off + nw * bt * 8;
         s.rbuf_off = s.xbuf_off + 2 * cluster * bt * 8;
         s.cs_off = s.rbuf_off + bt * 8;
         s.bar_off = s.cs_off + cs_elems * 8;
@@ -96,11 +95,13 @@ __device__ __forceinline__ void unpack<float>(const vec16 &v, double (&out)[4]) 
     out[3] = (double)__uint_as_float(v.w);
 }
 
-template <typename S, int BT, bool WANT_G>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <typename S, int BT, int NW, bool WANT_G>
+__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8) ? 2 : 1)
 sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
-    using Cfg = FusedCfg<S, BT>;
+    using Cfg = FusedCfg<S, BT, NW>;
     constexpr int VEC = Cfg::VEC, LPR = Cfg::LPR, RPW = Cfg::RPW, RPC = Cfg::RPC;
+    constexpr int kConsumerWarps = NW, kConsumerThreads = NW * 32, kFusedThreads = (NW + 1) * 32;
+    constexpr uint32_t kChunkBytes = chunk_bytes(NW);
 
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t q = cluster_ctarank();
@@ -108,7 +109,7 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
     const uint32_t cl = cluster_id_x();
     const uint32_t ncl = cluster_nid_x();
     const int R = p.ring, kt = p.kt;
-    const FusedSmem L = FusedSmem::make(R, BT, (int)C, kt * RPC);
+    const FusedSmem L = FusedSmem::make(R, BT, (int)C, kt * RPC, NW);
 
     double *red = reinterpret_cast<double *>(smem + L.red_off);    // [16][BT]
     double *xbuf = reinterpret_cast<double *>(smem + L.xbuf_off);  // [2][C][BT]
@@ -180,6 +181,10 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
             const uint32_t par = it & 1u;
             const int slotA = slot;
 
+            // the tile's observed counts: issued now, consumed after the exchange (off the critical path)
+            double n_obs = 0.0;
+            if (tid < BT && (int64_t)tile * BT + tid < p.nb) n_obs = __ldg(p.data + (int64_t)tile * BT + tid);
+
             // ---- pass A: composite partials for this lane's VEC bins over its templates ----
             double acc[VEC];
 #pragma unroll
@@ -232,7 +237,7 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
                     const int64_t bin = (int64_t)tile * BT + tid;
                     double r = 0.0;
                     if (bin < p.nb) {
-                        const double n = __ldg(p.data + bin);
+                        const double n = n_obs;
                         const double mc = (m < p.eps) ? p.eps : m;  // NaN-propagating max
                         r = 1.0 - n / mc;
                         if (q == 0) {

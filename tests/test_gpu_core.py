@@ -130,14 +130,15 @@ def test_fg_parity_f64(S, nb, nt):
     assert info.cc_major == 10 and info.fused == 1, "fused sm_100a kernel must be the path that runs"
 
 
-@pytest.mark.parametrize("tile,cluster", [(16, 1), (16, 2), (32, 2), (32, 4), (64, 4), (64, 8), (32, 8), (16, 8)])
-def test_fused_configs_agree(S, tile, cluster):
+@pytest.mark.parametrize("nw", [8, 16])
+@pytest.mark.parametrize("tile,cluster", [(16, 1), (16, 2), (32, 2), (32, 4), (64, 4), (64, 8), (32, 8), (16, 8), (64, 16)])
+def test_fused_configs_agree(S, tile, cluster, nw):
     nb, nt = 3001, 517
     M, x, data = make_flat_problem(nb, nt, seed=11)
     nlq, Gq, gs, _ = O.fg_quad(x, M, data)
-    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster)
+    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw)
     i = ds.info()
-    assert i.fused == 1 and i.tile_bins == tile and i.cluster == cluster
+    assert i.fused == 1 and i.tile_bins == tile and i.cluster == cluster and i.consumer_warps == nw
     nl, G, _ = ds.eval_fg(x)
     assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
     assert_grad_close(G, Gq, gs)
