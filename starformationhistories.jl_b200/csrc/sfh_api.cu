@@ -105,6 +105,19 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains;
+// every kernel launched this way calls griddepcontrol.wait before touching the predecessor's outputs.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 inline size_t elem_size(int dtype) { return dtype == SFH_F32 ? 4 : 8; }
 }  // namespace
 
@@ -204,13 +217,15 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
     cfg.blockDim = dim3((NW + 1) * 32);
     cfg.dynamicSmemBytes = s->smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = s->cluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G>, s->tmap, p);
 }
 
@@ -578,9 +593,8 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
     const int64_t work = std::max<int64_t>(s->rows, want_G_reduce ? s->nt : 0);
     int grid = (int)std::min<int64_t>(std::max<int64_t>((work + kFinalizeThreads - 1) / kFinalizeThreads, 1),
                                       std::min(1024, 2 * std::max(s->sm_count, 1)));
-    sfh_finalize_kernel<<<grid, kFinalizeThreads, 0, c->stream>>>(fp);
+    CU_TRY(launch_pdl(sfh_finalize_kernel, dim3(grid), dim3(kFinalizeThreads), 0, c->stream, fp));
     c->stats.kernel_launches++;
-    CU_TRY(cudaGetLastError());
     return SFH_OK;
 }
 
@@ -845,11 +859,9 @@ extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed,
     const size_t nv = (size_t)c->nj + 3;
     memcpy(c->h_in, variables, nv * 8);
     CU_TRY(cudaMemcpyAsync(c->d_vars, c->h_in, nv * 8, cudaMemcpyHostToDevice, c->stream));
-    sfh_hier_prologue_kernel<<<1, kHierThreads, 0, c->stream>>>(hp);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_pdl(sfh_hier_prologue_kernel, dim3(1), dim3(kHierThreads), 0, c->stream, hp));
     SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false));
-    sfh_hier_epilogue_kernel<<<1, kHierThreads, 0, c->stream>>>(hp, want_G);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_pdl(sfh_hier_epilogue_kernel, dim3(1), dim3(kHierThreads), 0, c->stream, hp, want_G));
     c->stats.kernel_launches += 2;
     const size_t n_out = want_G ? 1 + nv : 1;
     CU_TRY(cudaMemcpyAsync(c->h_out, c->d_outh, n_out * 8, cudaMemcpyDeviceToHost, c->stream));

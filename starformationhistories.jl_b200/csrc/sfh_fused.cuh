@@ -131,6 +131,8 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
         fence_mbar_init();
     }
     if (warp == kConsumerWarps && lane == 0) prefetch_tensormap(&tmap);
+    // PDL: barrier set-up above overlaps the previous kernel; its outputs (coeffs) are read only below
+    griddep_wait();
     for (int i = tid; i < kt * RPC; i += kFusedThreads) {
         const int64_t j = (int64_t)q * kt * RPC + i;
         cs[i] = (j < p.nt) ? __ldg(p.coeffs + j) : 0.0;

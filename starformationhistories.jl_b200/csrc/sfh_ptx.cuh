@@ -122,6 +122,10 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                  : "memory");
 }
 
+// ---- programmatic dependent launch: everything above this call may overlap the previous kernel's tail --------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- misc -----------------------------------------------------------------------------------
 template <int ID, int NTHREADS>
 __device__ __forceinline__ void named_bar_sync() {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "sfh_ptx.cuh"
 
 namespace sfh {
 
@@ -55,6 +56,7 @@ constexpr int kFinalizeThreads = 256;
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
+    griddep_wait();  // PDL: launched while the fused kernel drains
     // fixed contiguous slice of bins per block -> deterministic partials
     const int64_t per = (p.nb + gridDim.x - 1) / gridDim.x;
     const int64_t b0 = (int64_t)blockIdx.x * per;
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
         for (int64_t j = (int64_t)blockIdx.x * kFinalizeThreads + threadIdx.x; j < p.nt;
              j += (int64_t)gridDim.x * kFinalizeThreads) {
             double g = 0.0;
-            for (int cl = 0; cl < p.n_clusters; ++cl) g += p.gpart[(int64_t)cl * p.gstride + j];
+#pragma unroll 8
+            for (int cl = 0; cl < p.n_clusters; ++cl) g += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
             p.out[1 + j] = g;
         }
     }
@@ -80,10 +83,12 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     __syncthreads();
     if (last) {
         __threadfence();
+        // fixed assignment (thread t owns partials t, t+256, ...) + fixed shuffle tree => deterministic
+        double s = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kFinalizeThreads) s += __ldcg(p.lpart + b);
+        const double all = block_sum<kFinalizeThreads>(s, sh);
         if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile double *)p.lpart)[b];
-            p.out[0] = s;
+            p.out[0] = all;
             *p.ticket = 0u;  // re-arm for the next evaluation on this context
         }
     }
@@ -219,6 +224,7 @@ constexpr int kHierThreads = 1024;
 
 // calculate_coeffs: mzr.jl:50-79 / amr.jl:50-73
 __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const HierParams p) {
+    griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierThreads / 32;
     const int nj = p.nj;
     const double alpha = p.variables[nj], beta = p.variables[nj + 1], sigma = p.variables[nj + 2];
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const H
 
 // chain rule: mzr.jl:124-210 / amr.jl:118-169.  fullG = d logL/d r = -(fg_out[1+t]).
 __global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const HierParams p, int want_G) {
+    griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierThreads / 32;
     const int nj = p.nj;
     if (tid == 0) {
