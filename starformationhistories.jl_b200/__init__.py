@@ -16,6 +16,7 @@ from .fitting import (DeviceStack, clear_cache, composite_, device_stack, fg_ as
 from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR, LogarithmicAMR, PowerLawMZR,
                            calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams)
 from .sampling import HMCModel, MCMCModel
+from .sharding import allreduce_fg, guard_neg_logl, init_library_comm, shard_rows
 
 
 def fg_(F, G, *args):
@@ -32,4 +33,5 @@ def fg_(F, G, *args):
 __all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite_", "loglikelihood",
            "grad_loglikelihood", "grad_loglikelihood_", "fg_", "calculate_coeffs", "PowerLawMZR", "LinearAMR",
            "LogarithmicAMR", "GaussianDispersion", "HierarchicalOptimizer", "HMCModel", "MCMCModel", "nparams",
-           "exptransform", "logtransform", "clear_cache", "device_stack"]
+           "exptransform", "logtransform", "clear_cache", "device_stack", "shard_rows", "allreduce_fg", "guard_neg_logl",
+           "init_library_comm"]

@@ -1,0 +1,68 @@
+"""Multi-GPU parity check, one process per GPU:  torchrun --nproc-per-node N tests/mgpu_check.py
+Bin-row shards + in-library NCCL all-reduce must reproduce the single-GPU whole-stack answers."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import sfh_b200 as S
+from conftest import make_flat_problem, make_hier_problem
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nb, nt = 20011, 300
+    M, x, data = make_flat_problem(nb, nt, seed=99)
+    whole = S.DeviceStack(M, data, device=local)
+    nl0, G0, _ = whole.eval_fg(x * 1.1)
+    shard = S.DeviceStack(M, data, device=local, rows=S.shard_rows(nb, world, rank))
+    S.init_library_comm(shard.ctx())
+    for _ in range(3):
+        nl, G, _ = shard.eval_fg(x * 1.1)
+        assert abs(nl - nl0) <= 1e-12 * abs(nl0), (nl, nl0)
+        assert np.allclose(G, G0, rtol=1e-10, atol=1e-10 * np.abs(G0).max())
+    nl_f, _, _ = shard.eval_fg(x * 1.1, want_G=False)
+    assert abs(nl_f - nl0) <= 1e-12 * abs(nl0)
+    # every rank must hold the SAME reduced answer bit for bit (all-reduce is rank-symmetric)
+    t = torch.tensor([nl] + list(G[:8]), dtype=torch.float64, device="cuda")
+    ref = t.clone(); dist.broadcast(ref, 0)
+    assert torch.equal(t, ref)
+    # batched walkers over shards
+    X = np.maximum(0.0, x[:, None] + np.random.default_rng(1).standard_normal((nt, 33)))
+    X[5, 2] = -1.0
+    a = whole.eval_logl_batched(X); b = shard.eval_logl_batched(X)
+    assert b[2] == -np.inf and np.allclose(np.delete(a, 2), np.delete(b, 2), rtol=1e-12)
+    # hierarchical path over shards
+    p = make_hier_problem(nj=12, nk=10, nb=5003)
+    mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
+    xt = S.calculate_coeffs(mz, dp, p["R"], p["logAge"], p["MH"])
+    d = np.random.default_rng(2).poisson(p["M"] @ xt).astype(np.float64)
+    v = np.concatenate([p["R"], [1.0, -2.0, 0.2]]) * 1.07
+    w2 = S.DeviceStack(p["M"], d, device=local)
+    s2 = S.DeviceStack(p["M"], d, device=local, rows=S.shard_rows(5003, world, rank))
+    S.init_library_comm(s2.ctx())
+    Ga, Gb = np.empty(15), np.empty(15)
+    na = S.fg_(True, Ga, mz, dp, v, w2, d, None, p["logAge"], p["MH"])
+    nb_ = S.fg_(True, Gb, mz, dp, v, s2, d, None, p["logAge"], p["MH"])
+    assert abs(na - nb_) <= 1e-12 * abs(na) and np.allclose(Ga, Gb, rtol=1e-8, atol=1e-10 * np.abs(Ga).max())
+    # the counter-based synthetic generator: shards of one big diagram == the whole
+    xs = 10 * np.random.default_rng(3).random(500)
+    ws = S.DeviceStack.synthetic(40000, 500, np.float32, 7, 1.0, xs, device=local)
+    ss = S.DeviceStack.synthetic(40000, 500, np.float32, 7, 1.0, xs, device=local, rows=S.shard_rows(40000, world, rank))
+    S.init_library_comm(ss.ctx())
+    r0, r1 = ws.eval_fg(xs * 1.01), ss.eval_fg(xs * 1.01)
+    assert abs(r0[0] - r1[0]) <= 1e-12 * abs(r0[0]) and np.allclose(r0[1], r1[1], rtol=1e-9, atol=1e-9 * np.abs(r0[1]).max())
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu_check OK on {world} GPUs")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,85 @@
+"""N>1 host logic on CPU: world_size-2 `gloo` process group.  Each rank evaluates its bin-row
+shard with the CPU ORACLE as the local evaluator (tests may use the oracle; the product's local evaluator is the
+GPU), then the product's sharding code all-reduces [logL, G] and applies the guards; the result must equal the
+whole-stack oracle.  Also covers the partition function and the unique-id broadcast plumbing."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import make_flat_problem
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, nb, nt, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle as O
+        import sfh_b200 as S
+        M, x, data = make_flat_problem(nb, nt, seed=17)
+        b, e = S.shard_rows(nb, world, rank)
+        if e > b:
+            Cm = O.composite(x, M[b:e])
+            logl = float(np.sum(np.where(data[b:e] > 0, data[b:e] - Cm - data[b:e] * np.log(np.where(data[b:e] > 0, data[b:e], 1) / Cm), -Cm)))
+            _, G, _ = O.fg(x, M[b:e], data[b:e])
+        else:
+            logl, G = 0.0, np.zeros(nt)
+        out = np.concatenate([[logl], G])
+        nl, Gall = S.allreduce_fg(out)
+        uid = S.sharding.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128, 0)
+        q.put((rank, nl, Gall, uid, (b, e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nb,nt", [(1000, 7), (37, 5)])
+def test_two_rank_gloo_sharded_fg(nb, nt):
+    import oracle as O
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nb, nt, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    M, x, data = make_flat_problem(nb, nt, seed=17)
+    nl_ref, G_ref, _ = O.fg(x, M, data)
+    spans = sorted(r[4] for r in res)
+    assert spans[0][0] == 0 and spans[-1][1] == nb and spans[0][1] == spans[1][0]
+    for rank, nl, G, uid, _ in res:
+        assert nl == pytest.approx(float(nl_ref), rel=1e-13)
+        assert np.allclose(G, G_ref, rtol=1e-11, atol=1e-9)
+        assert uid == bytes(range(128))
+
+
+def test_shard_rows_partition_properties():
+    import sfh_b200 as S
+    for nb in (0, 1, 31, 32, 33, 1000, 60000, 10**6 + 7):
+        for world in (1, 2, 3, 4, 8):
+            spans = [S.shard_rows(nb, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == nb
+            for (a, b), (c, d) in zip(spans[:-1], spans[1:]):
+                assert b == c and a <= b
+                assert b % 32 == 0 or b == nb
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(s for s in sizes if s > 0 or True) <= max(32 * world, max(sizes))
+    with pytest.raises(ValueError):
+        S.shard_rows(10, 2, 2)
+
+
+def test_guard_after_reduction():
+    import sfh_b200 as S
+    assert S.guard_neg_logl(0.0) == np.inf           # fitting_base.jl:95
+    assert S.guard_neg_logl(-3.5) == 3.5
+    # two shards whose partial sums cancel exactly must trigger the guard only AFTER the sum
+    nl, G = S.allreduce_fg(np.array([0.0, 1.0, 2.0]))
+    assert nl == np.inf and np.array_equal(G, [1.0, 2.0])
