@@ -326,7 +326,8 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     const bool nonport = s->cluster > 8;
-#define SET_ATTR(S, BT, NW, G) set_attr<S, BT, NW, G>(s->smem, nonport)
+    // the opt-in MAXIMUM (not this stack's size): the attribute is per kernel function, shared by every stack
+#define SET_ATTR(S, BT, NW, G) set_attr<S, BT, NW, G>(kMaxDynSmem, nonport)
     CU_TRY(SFH_DISPATCH(s, true, SET_ATTR));
     CU_TRY(SFH_DISPATCH(s, false, SET_ATTR));
 #undef SET_ATTR

@@ -215,6 +215,24 @@ _cache: dict = {}
 _cache_lock = threading.Lock()
 
 
+def _weak_ids(obj):
+    """Weak references that pin down the IDENTITY of `obj` (an ndarray or a list of ndarrays): id() alone can be
+    recycled by the allocator once the original array is garbage collected."""
+    items = list(obj) if isinstance(obj, (list, tuple)) else [obj]
+    refs = []
+    for it in items:
+        try:
+            refs.append(weakref.ref(it))
+        except TypeError:
+            return None  # not weak-referenceable (e.g. a nested list): never cache
+    return refs
+
+
+def _same(refs, obj):
+    items = list(obj) if isinstance(obj, (list, tuple)) else [obj]
+    return refs is not None and len(refs) == len(items) and all(r() is it for r, it in zip(refs, items))
+
+
 def device_stack(models, data) -> DeviceStack:
     if isinstance(models, DeviceStack):
         if data is not None and models._data_id is not None and id(data) != models._data_id:
@@ -224,17 +242,23 @@ def device_stack(models, data) -> DeviceStack:
     with _cache_lock:
         ent = _cache.get(key)
         if ent is not None:
-            return ent
+            ds, mrefs, drefs = ent
+            if _same(mrefs, models) and _same(drefs, data):
+                return ds
+            _cache.pop(key)
+            ds.close()
         if len(_cache) >= 8:
-            _cache.pop(next(iter(_cache))).close()
+            _cache.pop(next(iter(_cache)))[0].close()
         ds = DeviceStack(models, data)
-        _cache[key] = ds
+        mrefs, drefs = _weak_ids(models), _weak_ids(data)
+        if mrefs is not None and drefs is not None:
+            _cache[key] = (ds, mrefs, drefs)
         return ds
 
 
 def clear_cache():
     with _cache_lock:
-        for ds in _cache.values():
+        for ds, _, _ in _cache.values():
             ds.close()
         _cache.clear()
 

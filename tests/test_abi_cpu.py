@@ -122,3 +122,17 @@ def test_host_calculate_coeffs_matches_oracle():
         assert np.allclose(got, want, rtol=1e-13, atol=0)
     with pytest.raises(ValueError):
         S.calculate_coeffs(S.PowerLawMZR(1.0, -2.0), S.GaussianDispersion(0.2), p["R"][:-1], p["logAge"], p["MH"])
+
+
+def test_identity_cache_detects_recycled_ids():
+    """id() of a dead array can be reused by a new one: the stack cache must compare identities through weakrefs."""
+    from sfh_b200 import fitting as F
+    a = np.ones((4, 2)); d = np.ones(4)
+    refs = F._weak_ids(a)
+    assert F._same(refs, a) and not F._same(refs, np.ones((4, 2)))
+    lst = [np.ones((2, 2)), np.zeros((2, 2))]
+    r2 = F._weak_ids(lst)
+    assert F._same(r2, lst) and not F._same(r2, [lst[0], np.zeros((2, 2))])
+    del a
+    assert refs[0]() is None and not F._same(refs, np.ones((4, 2)))
+    assert F._weak_ids([[1, 2], [3, 4]]) is None

@@ -220,6 +220,19 @@ def test_edge_semantics(S):
     assert s3.eval_fg(x2 * 0.9)[0] == pytest.approx(nlq, rel=RTOL_LOGL)
 
 
+def test_stacks_with_different_configs_coexist(S):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel function: a later, smaller stack must not
+    shrink it under an earlier, larger one that shares the instantiation."""
+    M, x, data = make_flat_problem(5003, 120, seed=12)
+    big = S.DeviceStack(M, data)
+    a = big.eval_fg(x)
+    smalls = [S.DeviceStack(M[:n], data[:n]) for n in (2502, 700, 64)]
+    for s_ in smalls:
+        s_.eval_fg(x)
+    b = big.eval_fg(x)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
 def test_row_shards_sum_to_whole(S):
     """Bin-row sharding: logL and G are sums over shards."""
     M, x, data = make_flat_problem(7777, 260, seed=8)
