@@ -69,7 +69,9 @@ typedef struct sfh_opts {
     int32_t tile_bins;   /* 0 = auto; else bins per tile of the fused kernel (16/32/64/128)         */
     int32_t cluster;     /* 0 = auto; else thread-block-cluster size (1,2,4,8,16)                   */
     int32_t force_unfused; /* 1 = always use the two-pass kernels (debug / A-B measurements)        */
-    int32_t consumer_warps; /* 0 = auto; 16 = one CTA per SM; 8 = two co-resident CTAs per SM       */
+    int32_t consumer_warps; /* 0 = auto; 8, 12 or 16 consumer warps per CTA                          */
+    int32_t variant;     /* 0 = auto; 1 = shared-memory-resident tile; 2 = register-resident tile    */
+    int32_t reserved;
 } sfh_opts;
 
 typedef struct sfh_info {
@@ -77,7 +79,7 @@ typedef struct sfh_info {
     int32_t dtype, device;
     int32_t fused;     /* 1 if the single-pass fused kernel is in use                  */
     int32_t tile_bins, cluster, chunks_per_tile, ring_slots, n_clusters, consumer_warps;
-    int32_t sm_count, cc_major, cc_minor, reserved;
+    int32_t sm_count, cc_major, cc_minor, register_tile;
     int64_t stack_bytes; /* device bytes held by the stack (padded)                    */
     double clamp_eps;
 } sfh_info;

@@ -133,6 +133,7 @@ struct sfh_stack {
     // kernel configuration
     bool fused = false;
     int bt = 0, cluster = 1, kt = 0, ring = 0, n_clusters = 0, n_tiles = 0, nw = 16;
+    bool rt = false;  // register-resident tile variant
     uint32_t smem = 0;
     bool evict_first = false;
     CUtensorMap tmap;
@@ -187,15 +188,15 @@ TileGeom geom(int dtype, int bt, int nw) {
     return g;
 }
 
-template <typename S, int BT, int NW, bool G>
+template <typename S, int BT, int NW, bool G, bool RT>
 cudaError_t set_attr(uint32_t smem, bool nonportable) {
-    auto k = sfh_fg_fused_kernel<S, BT, NW, G>;
+    auto k = sfh_fg_fused_kernel<S, BT, NW, G, RT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (nonportable) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     return e;
 }
-template <typename S, int BT, int NW, bool G>
+template <typename S, int BT, int NW, bool G, bool RT>
 cudaError_t max_clusters(const sfh_stack *s, int *out) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s->cluster * 1024u);
@@ -208,9 +209,9 @@ cudaError_t max_clusters(const sfh_stack *s, int *out) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(out, sfh_fg_fused_kernel<S, BT, NW, G>, &cfg);
+    return cudaOccupancyMaxActiveClusters(out, sfh_fg_fused_kernel<S, BT, NW, G, RT>, &cfg);
 }
-template <typename S, int BT, int NW, bool G>
+template <typename S, int BT, int NW, bool G, bool RT>
 cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(s->n_clusters * s->cluster));
@@ -226,25 +227,31 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G>, s->tmap, p);
+    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G, RT>, s->tmap, p);
 }
 
-#define SFH_DISPATCH_G(S, BT, NW, want_g, CALL) ((want_g) ? CALL(S, BT, NW, true) : CALL(S, BT, NW, false))
-#define SFH_DISPATCH_NW(S, BT, s, want_g, CALL) \
-    (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, want_g, CALL) : SFH_DISPATCH_G(S, BT, 16, want_g, CALL))
+// kernel variants: (NW=16, smem tile) (NW=8, smem tile, 2 CTAs/SM) (NW=8, register tile) (NW=12, register tile)
+#define SFH_DISPATCH_G(S, BT, NW, RT, want_g, CALL) ((want_g) ? CALL(S, BT, NW, true, RT) : CALL(S, BT, NW, false, RT))
+#define SFH_DISPATCH_NW(S, BT, s, want_g, CALL)                                                    \
+    ((s)->rt ? (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, true, want_g, CALL)                     \
+                               : SFH_DISPATCH_G(S, BT, 12, true, want_g, CALL))                   \
+             : (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, false, want_g, CALL)                    \
+                               : SFH_DISPATCH_G(S, BT, 16, false, want_g, CALL)))
 #define SFH_DISPATCH(s, want_g, CALL)                                      \
     [&]() -> cudaError_t {                                                 \
         if ((s)->dtype == SFH_F64) {                                       \
             switch ((s)->bt) {                                             \
             case 64: return SFH_DISPATCH_NW(double, 64, s, want_g, CALL);  \
             case 32: return SFH_DISPATCH_NW(double, 32, s, want_g, CALL);  \
-            default: return SFH_DISPATCH_NW(double, 16, s, want_g, CALL);  \
+            case 16: return SFH_DISPATCH_NW(double, 16, s, want_g, CALL);  \
+            default: return SFH_DISPATCH_NW(double, 8, s, want_g, CALL);   \
             }                                                              \
         } else {                                                           \
             switch ((s)->bt) {                                             \
             case 128: return SFH_DISPATCH_NW(float, 128, s, want_g, CALL); \
             case 64: return SFH_DISPATCH_NW(float, 64, s, want_g, CALL);   \
-            default: return SFH_DISPATCH_NW(float, 32, s, want_g, CALL);   \
+            case 32: return SFH_DISPATCH_NW(float, 32, s, want_g, CALL);   \
+            default: return SFH_DISPATCH_NW(float, 16, s, want_g, CALL);   \
             }                                                              \
         }                                                                  \
     }()
@@ -256,54 +263,66 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
 //     (NW = 8) hide it;
 //   * prefer larger bin tiles (longer contiguous TMA rows) when the above are equal.
 bool choose_config(sfh_stack *s, const sfh_opts *o) {
-    const int cands64[3] = {64, 32, 16}, cands32[3] = {128, 64, 32};
+    const int cands64[4] = {64, 32, 16, 8}, cands32[4] = {128, 64, 32, 16};
     const int *cands = (s->dtype == SFH_F64) ? cands64 : cands32;
-    const int nws[2] = {8, 16};
+    struct Variant { int nw; bool rt; int ctas_per_sm; };
+    const Variant variants[4] = {{12, true, 1}, {8, true, 1}, {8, false, 2}, {16, false, 1}};
     const int cl_opts[5] = {1, 2, 4, 8, 16};
+    const bool forced = o && (o->tile_bins || o->cluster || o->consumer_warps || o->variant);
     double best_score = -1.0;
     int best_bt = 0, best_c = 0, best_kt = 0, best_nw = 0, best_ring = 0;
-    for (int nw : nws) {
+    bool best_rt = false;
+    for (const Variant &v : variants) {
+        const int nw = v.nw;
         if (o && o->consumer_warps && o->consumer_warps != nw) continue;
-        for (int ci = 0; ci < 3; ++ci) {
+        if (o && o->variant == 1 && v.rt) continue;   // 1 = shared-memory tile only
+        if (o && o->variant == 2 && !v.rt) continue;  // 2 = register tile only
+        for (int ci = 0; ci < 4; ++ci) {
             const int bt = cands[ci];
             if (o && o->tile_bins && o->tile_bins != bt) continue;
             const TileGeom g = geom(s->dtype, bt, nw);
-            if (g.rpc > 256) continue;
+            if (g.lpr < 1 || g.lpr > 32 || g.rpc > 256 || bt > nw * 32) continue;
             for (int c : cl_opts) {
                 if (o && o->cluster && o->cluster != c) continue;
                 const int64_t kt64 = std::max<int64_t>((s->nt + (int64_t)c * g.rpc - 1) / ((int64_t)c * g.rpc), 1);
-                if (kt64 > kKMax) continue;
+                if (kt64 > kmax_for(nw, v.rt)) continue;
                 const int kt = (int)kt64;
-                const uint32_t budget = (nw == 8) ? (kMaxDynSmem / 2 - 1024) : kMaxDynSmem;  // 2 CTAs/SM need half each
-                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw);
+                const uint32_t budget = (v.ctas_per_sm == 2) ? (kMaxDynSmem / 2 - 1024) : kMaxDynSmem;
+                const int G = stage_chunks_for(v.rt);
+                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw, G);
                 if (fixed.total + 64 >= budget) continue;
                 int ring = (int)((budget - fixed.total - 64) / (chunk_bytes(nw) + 16));
-                ring = std::min(ring, 32);
-                if (ring < kt + 2) continue;
-                // --- score ---
-                const int ctas_per_sm = (nw == 8) ? 2 : 1;
-                const int packed = (c <= 2) ? s->sm_count : (c == 4 ? s->sm_count / 4 * 4 : (c == 8 ? 120 : 96));
-                const double sm_frac = std::min(1.0, (double)packed / std::max(s->sm_count, 1));
+                ring = std::min(ring, 64) / G * G;   // whole pipeline stages
+                const int nst = (kt + G - 1) / G;
+                if (ring / G < (v.rt ? 2 : nst + 1)) continue;
+                // --- score (model fitted to profiles/r1_sweep_*.txt) ---
+                // co-schedulable clusters on a 148-SM B200: size 8 -> 15, size 4 -> 33 (1 CTA/SM) or 71 (2 CTAs/SM)
+                const int slots = s->sm_count * v.ctas_per_sm;
+                int n_cl_max = slots / c;
+                if (c == 4) n_cl_max = (v.ctas_per_sm == 2) ? 71 : 33;
+                if (c == 8) n_cl_max = (v.ctas_per_sm == 2) ? 33 : 15;
+                if (c == 16) n_cl_max = (v.ctas_per_sm == 2) ? 14 : 7;
+                const double sm_frac = std::min(1.0, (double)n_cl_max * c / slots);
                 const int64_t n_tiles = (s->rows + bt - 1) / bt;
-                const int64_t n_cl = std::max<int64_t>((int64_t)packed * ctas_per_sm / c, 1);
-                const double waves = (double)n_tiles / (double)n_cl;
+                const double waves = (double)n_tiles / (double)std::max(n_cl_max, 1);
                 const double balance = waves >= 1.0 ? waves / std::ceil(waves) : waves;  // tail effect
-                const double tile_us = (double)kt * chunk_bytes(nw) / 40e3;              // ~40 GB/s per SM
-                const double overlap = (nw == 8) ? 0.35 : 1.0;                            // exposed part of ~1 us
-                const double eff = tile_us / (tile_us + overlap * 1.0);
-                const double rowlen = std::min(1.0, 0.85 + 0.15 * (bt * elem_size(s->dtype)) / 512.0);
+                const double tile_us = (double)kt * chunk_bytes(nw) * v.ctas_per_sm / 44e3;  // ~44 GB/s per SM
+                // measured: the register-tile variants are consumer-latency bound (2-3 warps per scheduler), not HBM bound
+                const double exposed = v.rt ? 2.5 : (v.ctas_per_sm == 2 ? 0.35 : 1.0);       // of the ~1 us exchange
+                const double eff = tile_us / (tile_us + exposed);
+                const double rowlen = std::min(1.0, 0.94 + 0.06 * (bt * elem_size(s->dtype)) / 256.0);  // 128 B rows: -3 %
                 const double score = sm_frac * balance * eff * rowlen;
-                const bool forced = o && (o->tile_bins || o->cluster || o->consumer_warps);
                 if (score > best_score || (forced && best_bt == 0)) {
                     best_score = score; best_bt = bt; best_c = c; best_kt = kt; best_nw = nw; best_ring = ring;
+                    best_rt = v.rt;
                 }
             }
         }
     }
     if (!best_bt) return false;
-    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt; s->nw = best_nw; s->ring = best_ring;
+    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt; s->nw = best_nw; s->ring = best_ring; s->rt = best_rt;
     const TileGeom g = geom(s->dtype, s->bt, s->nw);
-    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw).total;
+    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw, stage_chunks_for(s->rt)).total;
     s->n_tiles = (int)((s->rows + s->bt - 1) / s->bt);
     return true;
 }
@@ -327,12 +346,12 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     if (r != CUDA_SUCCESS) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     const bool nonport = s->cluster > 8;
     // the opt-in MAXIMUM (not this stack's size): the attribute is per kernel function, shared by every stack
-#define SET_ATTR(S, BT, NW, G) set_attr<S, BT, NW, G>(kMaxDynSmem, nonport)
+#define SET_ATTR(S, BT, NW, G, RT) set_attr<S, BT, NW, G, RT>(kMaxDynSmem, nonport)
     CU_TRY(SFH_DISPATCH(s, true, SET_ATTR));
     CU_TRY(SFH_DISPATCH(s, false, SET_ATTR));
 #undef SET_ATTR
     int maxcl = 0;
-#define MAX_CL(S, BT, NW, G) max_clusters<S, BT, NW, G>(s, &maxcl)
+#define MAX_CL(S, BT, NW, G, RT) max_clusters<S, BT, NW, G, RT>(s, &maxcl)
     CU_TRY(SFH_DISPATCH(s, true, MAX_CL));
 #undef MAX_CL
     if (maxcl <= 0) return SFH_OK;  // cannot co-schedule this cluster shape: stay unfused
@@ -482,7 +501,7 @@ extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
     info->nbins_total = s->nb_total; info->ntemplates = s->nt; info->row_begin = s->row_begin; info->row_end = s->row_end;
     info->ld = s->ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
     info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
-    info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
+    info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->register_tile = s->rt ? 1 : 0; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
     info->stack_bytes = (int64_t)((size_t)s->ld * s->nt * elem_size(s->dtype)); info->clamp_eps = s->eps;
     return SFH_OK;
 }
@@ -613,7 +632,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
         p.gstride = c->gstride;
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
-#define LAUNCH(S, BT, NW, G) launch_fused_t<S, BT, NW, G>(s, p, c->stream)
+#define LAUNCH(S, BT, NW, G, RT) launch_fused_t<S, BT, NW, G, RT>(s, p, c->stream)
         CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
 #undef LAUNCH
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));

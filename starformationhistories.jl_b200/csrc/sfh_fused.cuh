@@ -32,6 +32,14 @@ namespace sfh {
 // NW consumer warps (+1 TMA producer warp) per CTA.  NW = 16: one CTA per SM; NW = 8: two CTAs per SM, so one
 // CTA's exchange/residual latency is hidden behind the other CTA's streaming passes.
 constexpr int kKMax = 20;       // max chunks per CTA per tile (per-lane register array gacc[])
+// per-variant limit: the 12-warp register-tile variant has 128 registers/thread => 12 chunks (4+2 regs each)
+__host__ __device__ constexpr int kmax_for(int nw, bool rt) { return (rt && nw == 12) ? 12 : kKMax; }
+// chunks per pipeline STAGE: one mbarrier wait / release per stage instead of per chunk (an already-complete
+// mbarrier.try_wait still costs ~90 cycles; with few warps per SM that latency, paid per chunk, made the
+// consumers -- not HBM -- the bottleneck).  kKMax and every kmax_for() are multiples of it.
+__host__ __device__ constexpr int stage_chunks_for(bool rt) { return rt ? 4 : 1; }
+// (measured, profiles/r1_sweep_config3_staged.txt: for the shared-memory-tile variants a coarser stage costs more in
+//  prefetch depth / late release than it saves in waits: 206 us at 1 chunk per stage vs 229 us at 2)
 constexpr int kMaxCluster = 16;
 __host__ __device__ constexpr int chunk_bytes(int nw) { return nw * 32 * 16; }  // one 16-byte vector per consumer lane
 
@@ -39,7 +47,7 @@ struct FusedParams {
     int64_t nb;          // bins in this shard
     int64_t nt;          // templates
     int32_t kt;          // chunks per CTA per tile (<= kKMax)
-    int32_t ring;        // ring slots (>= kt + 1)
+    int32_t ring;        // ring chunk-slots: a multiple of the stage size
     int32_t n_tiles;     // ceil(nb / BT)
     int32_t evict_first; // use an L2 evict_first policy on the stack loads
     double eps;          // clamp (fitting_base.jl:90,277)
@@ -67,7 +75,7 @@ struct FusedSmem {
     uint32_t ring_off, red_off, xbuf_off, rbuf_off, cs_off, bar_off, total;
     // cs_elems = kt * RPC: this CTA's slice of the coefficient vector (kept in smem, not registers:
     // 17 warps put 5 warps on one SM sub-partition => 96 registers/thread, too few for c[] + gacc[])
-    __host__ __device__ static FusedSmem make(int ring, int bt, int cluster, int cs_elems, int nw) {
+    __host__ __device__ static FusedSmem make(int ring, int bt, int cluster, int cs_elems, int nw, int g) {
         FusedSmem s;
         s.ring_off = 0;
         s.red_off = ring * chunk_bytes(nw);
@@ -75,7 +83,7 @@ struct FusedSmem {
         s.rbuf_off = s.xbuf_off + 2 * cluster * bt * 8;
         s.cs_off = s.rbuf_off + bt * 8;
         s.bar_off = s.cs_off + cs_elems * 8;
-        s.total = s.bar_off + (2 * ring + 2) * 8;
+        s.total = s.bar_off + (2 * (ring / g) + 2) * 8;
         return s;
     }
 };
@@ -95,34 +103,43 @@ __device__ __forceinline__ void unpack<float>(const vec16 &v, double (&out)[4]) 
     out[3] = (double)__uint_as_float(v.w);
 }
 
-template <typename S, int BT, int NW, bool WANT_G>
-__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8) ? 2 : 1)
+// RT ("register tile"): pass A keeps its 16-byte vectors in registers for pass B and releases the smem stage at
+// once, so shared memory is a pure streaming ring (every slot in flight) and the HBM stream is decoupled from
+// the A -> exchange -> B dependency.  Needs 4*KT more registers per lane => NW <= 12, one CTA per SM.
+template <typename S, int BT, int NW, bool WANT_G, bool RT>
+__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 && !RT) ? 2 : 1)
 sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
     using Cfg = FusedCfg<S, BT, NW>;
     constexpr int VEC = Cfg::VEC, LPR = Cfg::LPR, RPW = Cfg::RPW, RPC = Cfg::RPC;
     constexpr int kConsumerWarps = NW, kConsumerThreads = NW * 32, kFusedThreads = (NW + 1) * 32;
     constexpr uint32_t kChunkBytes = chunk_bytes(NW);
+    constexpr int KMAX = kmax_for(NW, RT);
+    constexpr int G = stage_chunks_for(RT);
+    constexpr int SMAX = KMAX / G;  // stages per tile at most
+    static_assert(KMAX % G == 0, "KMAX must be a multiple of the stage size");
 
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t q = cluster_ctarank();
     const uint32_t C = cluster_nctarank();
     const uint32_t cl = cluster_id_x();
     const uint32_t ncl = cluster_nid_x();
-    const int R = p.ring, kt = p.kt;
-    const FusedSmem L = FusedSmem::make(R, BT, (int)C, kt * RPC, NW);
+    const int kt = p.kt;
+    const int NS = p.ring / G;          // stage slots in the ring
+    const int nst = (kt + G - 1) / G;   // stages per tile
+    const FusedSmem L = FusedSmem::make(p.ring, BT, (int)C, kt * RPC, NW, G);
 
-    double *red = reinterpret_cast<double *>(smem + L.red_off);    // [16][BT]
+    double *red = reinterpret_cast<double *>(smem + L.red_off);    // [NW][BT]
     double *xbuf = reinterpret_cast<double *>(smem + L.xbuf_off);  // [2][C][BT]
     double *rbuf = reinterpret_cast<double *>(smem + L.rbuf_off);  // [BT]
     double *cs = reinterpret_cast<double *>(smem + L.cs_off);      // [kt*RPC]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bar_off);
-    uint64_t *empty = full + R;
-    uint64_t *xbar = empty + R;  // [2]
+    uint64_t *empty = full + NS;
+    uint64_t *xbar = empty + NS;  // [2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < NS; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], kConsumerWarps);
         }
@@ -146,24 +163,28 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
         // ================= TMA producer (one elected lane) =================
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
-            int slot = 0;
+            int ss = 0;
             uint32_t round = 0;  // how many times the ring has wrapped
             const int32_t t0 = (int32_t)(q * (uint32_t)(kt * RPC));
             for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl) {
-                for (int k = 0; k < kt; ++k) {
-                    if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1u);
-                    mbar_arrive_expect_tx(&full[slot], kChunkBytes);
-                    void *dst = smem + L.ring_off + (uint32_t)slot * kChunkBytes;
-                    if (p.evict_first)
-                        tma_load_2d_hint(dst, &tmap, tile * BT, t0 + k * RPC, &full[slot], pol);
-                    else
-                        tma_load_2d(dst, &tmap, tile * BT, t0 + k * RPC, &full[slot]);
-                    if (++slot == R) { slot = 0; ++round; }
+                for (int s = 0; s < nst; ++s) {
+                    if (round > 0) mbar_wait(&empty[ss], (round - 1) & 1u);
+                    const int cnt = (kt - s * G < G) ? (kt - s * G) : G;
+                    mbar_arrive_expect_tx(&full[ss], (uint32_t)cnt * kChunkBytes);
+                    for (int u = 0; u < cnt; ++u) {
+                        void *dst = smem + L.ring_off + (uint32_t)(ss * G + u) * kChunkBytes;
+                        const int32_t tc = t0 + (s * G + u) * RPC;
+                        if (p.evict_first)
+                            tma_load_2d_hint(dst, &tmap, tile * BT, tc, &full[ss], pol);
+                        else
+                            tma_load_2d(dst, &tmap, tile * BT, tc, &full[ss]);
+                    }
+                    if (++ss == NS) { ss = 0; ++round; }
                 }
             }
         }
     } else {
-        // ================= consumers: 16 warps, one 16-byte vector per lane per chunk =========
+        // ================= consumers: NW warps, one 16-byte vector per lane per chunk =========
         const int bl = lane % LPR;  // which VEC-bin group of the tile this lane owns
         const int rw = lane / LPR;  // which template row of the warp's RPW rows
         const uint32_t lane_off = (uint32_t)tid * 16u;
@@ -172,16 +193,17 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
         // the lane's templates: j(k) = q*kt*RPC + k*RPC + warp*RPW + rw  (fixed for the whole kernel)
         const int64_t j0 = (int64_t)q * kt * RPC + warp * RPW + rw;
         const double *cs_lane = cs + warp * RPW + rw;  // + k*RPC
-        double gacc[kKMax];
+        double gacc[KMAX];
 #pragma unroll
-        for (int k = 0; k < kKMax; ++k) gacc[k] = 0.0;
+        for (int k = 0; k < KMAX; ++k) gacc[k] = 0.0;
 
-        int slot = 0;
+        vec16 tile_regs[RT ? KMAX : 1];  // RT: this lane's 16 bytes of every chunk of the current tile
+        int ss = 0;
         uint32_t phase = 0;
         uint32_t it = 0;
         for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl, ++it) {
             const uint32_t par = it & 1u;
-            const int slotA = slot;
+            const int ssA = ss;
 
             // the tile's observed counts: issued now, consumed after the exchange (off the critical path)
             double n_obs = 0.0;
@@ -192,20 +214,34 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
 #pragma unroll
-            for (int k = 0; k < kKMax; ++k) {
-                if (k < kt) {
-                    mbar_wait(&full[slot], phase);
-                    const vec16 v = lds128(ring_base + (uint32_t)slot * kChunkBytes + lane_off);
-                    const double ck = cs_lane[k * RPC];
-                    double m[VEC];
-                    unpack<S>(v, m);
+            for (int s = 0; s < SMAX; ++s) {
+                if (s < nst) {
+                    mbar_wait(&full[ss], phase);
+                    vec16 v[G];
+                    double ck[G];
+                    const uint32_t sbase = ring_base + (uint32_t)(ss * G) * kChunkBytes + lane_off;
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[e] = fma(m[e], ck, acc[e]);
-                    if (!WANT_G) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[slot]);
+                    for (int u = 0; u < G; ++u) {  // G independent shared-memory loads in flight
+                        if (s * G + u < kt) {
+                            v[u] = lds128(sbase + (uint32_t)u * kChunkBytes);
+                            ck[u] = cs_lane[(s * G + u) * RPC];
+                        }
                     }
-                    if (++slot == R) { slot = 0; phase ^= 1u; }
+#pragma unroll
+                    for (int u = 0; u < G; ++u) {
+                        if (s * G + u < kt) {
+                            double m[VEC];
+                            unpack<S>(v[u], m);
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) acc[e] = fma(m[e], ck[u], acc[e]);
+                            if (RT) tile_regs[RT ? s * G + u : 0] = v[u];
+                        }
+                    }
+                    if (!WANT_G || RT) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[ss]);
+                    }
+                    if (++ss == NS) { ss = 0; phase ^= 1u; }
                 }
             }
             // lanes that own the same bins (different rows) combine
@@ -224,13 +260,13 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
             if (warp * 32 < BT) {
                 const bool active = tid < BT;
                 if (active) {
-                    double s = 0.0;
+                    double sum = 0.0;
 #pragma unroll
-                    for (int w = 0; w < kConsumerWarps; ++w) s += red[w * BT + tid];
+                    for (int w = 0; w < kConsumerWarps; ++w) sum += red[w * BT + tid];
                     if (tid == 0) mbar_arrive_expect_tx(&xbar[par], C * BT * 8u);
                     const uint32_t my_slot = smem_u32(&xbuf[(par * C + q) * BT + tid]);
                     const uint32_t my_bar = smem_u32(&xbar[par]);
-                    for (uint32_t d = 0; d < C; ++d) st_async_f64(mapa(my_slot, d), s, mapa(my_bar, d));
+                    for (uint32_t d = 0; d < C; ++d) st_async_f64(mapa(my_slot, d), sum, mapa(my_bar, d));
                 }
                 mbar_wait_cluster(&xbar[par], (it >> 1) & 1u);
                 if (active) {
@@ -252,25 +288,39 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
             }
             named_bar_sync<1, kConsumerThreads>();
 
-            // ---- pass B: gradient partials from the SAME shared-memory bytes ----
+            // ---- pass B: gradient partials from the SAME bytes (shared memory, or registers if RT) ----
             if (WANT_G) {
                 double r[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) r[e] = rbuf[bl * VEC + e];
-                int sb = slotA;
+                int sb = ssA;
 #pragma unroll
-                for (int k = 0; k < kKMax; ++k) {
-                    if (k < kt) {
-                        const vec16 v = lds128(ring_base + (uint32_t)sb * kChunkBytes + lane_off);
-                        double m[VEC];
-                        unpack<S>(v, m);
-                        double g = gacc[k];
+                for (int s = 0; s < SMAX; ++s) {
+                    if (s < nst) {
+                        vec16 v[G];
+                        if (!RT) {
+                            const uint32_t sbase = ring_base + (uint32_t)(sb * G) * kChunkBytes + lane_off;
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) g = fma(m[e], r[e], g);
-                        gacc[k] = g;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[sb]);
-                        if (++sb == R) sb = 0;
+                            for (int u = 0; u < G; ++u)
+                                if (s * G + u < kt) v[u] = lds128(sbase + (uint32_t)u * kChunkBytes);
+                        }
+#pragma unroll
+                        for (int u = 0; u < G; ++u) {
+                            if (s * G + u < kt) {
+                                const vec16 vv = RT ? tile_regs[RT ? s * G + u : 0] : v[u];
+                                double m[VEC];
+                                unpack<S>(vv, m);
+                                double g = gacc[s * G + u];
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) g = fma(m[e], r[e], g);
+                                gacc[s * G + u] = g;
+                            }
+                        }
+                        if (!RT) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty[sb]);
+                            if (++sb == NS) sb = 0;
+                        }
                     }
                 }
             }
@@ -279,7 +329,7 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
         // ---- end of kernel: one store per (cluster, template) ----
         if (WANT_G) {
 #pragma unroll
-            for (int k = 0; k < kKMax; ++k) {
+            for (int k = 0; k < KMAX; ++k) {
                 if (k < kt) {
                     double g = gacc[k];
 #pragma unroll

@@ -73,7 +73,7 @@ class DeviceStack:
     """
 
     def __init__(self, models, data, dtype=None, device=0, rows=None, clamp_eps=0.0, tile_bins=0, cluster=0,
-                 force_unfused=False, consumer_warps=0):
+                 force_unfused=False, consumer_warps=0, variant=0):
         M = _as_stack_matrix(models)
         dt = np.dtype(dtype) if dtype is not None else M.dtype
         if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
@@ -95,6 +95,7 @@ class DeviceStack:
             o.row_begin, o.row_end = int(rows[0]), int(rows[1])
         o.clamp_eps = clamp_eps
         o.tile_bins, o.cluster, o.force_unfused, o.consumer_warps = tile_bins, cluster, int(force_unfused), consumer_warps
+        o.variant = variant
         h = C.c_void_p()
         L.check(L.lib.sfh_stack_create(C.byref(h), M.ctypes.data_as(C.c_void_p), M.shape[0], M.shape[1], _DT[dt],
                                        d.ctypes.data_as(C.c_void_p), _DT[d.dtype], C.byref(o)))
@@ -110,7 +111,7 @@ class DeviceStack:
 
     @classmethod
     def synthetic(cls, nbins, ntemplates, dtype, seed, scale, x_true, device=0, rows=None, tile_bins=0, cluster=0,
-                  force_unfused=False, consumer_warps=0):
+                  force_unfused=False, consumer_warps=0, variant=0):
         """On-device Philox/Poisson stack (include/sfhcuda.h: sfh_stack_create_synthetic)."""
         self = cls.__new__(cls)
         dt = np.dtype(dtype)
@@ -122,6 +123,7 @@ class DeviceStack:
         if rows is not None:
             o.row_begin, o.row_end = int(rows[0]), int(rows[1])
         o.tile_bins, o.cluster, o.force_unfused, o.consumer_warps = tile_bins, cluster, int(force_unfused), consumer_warps
+        o.variant = variant
         x = np.ascontiguousarray(x_true, dtype=np.float64)
         if x.shape[0] != ntemplates:
             raise ValueError("len(x_true) != ntemplates")

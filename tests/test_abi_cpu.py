@@ -39,7 +39,7 @@ def test_header_symbols_exported():
 def test_struct_layouts_match_header():
     import sfh_b200
     L = sfh_b200._lib
-    assert C.sizeof(L.sfh_opts) == 48      # 2*i32, 2*i64, f64, 4*i32
+    assert C.sizeof(L.sfh_opts) == 56      # 2*i32, 2*i64, f64, 6*i32
     assert C.sizeof(L.sfh_stats) == 24
     assert L.lib.sfh_version() == 1
 

@@ -130,15 +130,18 @@ def test_fg_parity_f64(S, nb, nt):
     assert info.cc_major == 10 and info.fused == 1, "fused sm_100a kernel must be the path that runs"
 
 
-@pytest.mark.parametrize("nw", [8, 16])
-@pytest.mark.parametrize("tile,cluster", [(16, 1), (16, 2), (32, 2), (32, 4), (64, 4), (64, 8), (32, 8), (16, 8), (64, 16)])
-def test_fused_configs_agree(S, tile, cluster, nw):
+@pytest.mark.parametrize("nw,variant", [(8, 1), (16, 1), (8, 2), (12, 2)])
+@pytest.mark.parametrize("tile,cluster", [(8, 2), (16, 1), (16, 2), (32, 2), (32, 4), (64, 4), (64, 8), (32, 8), (16, 8), (64, 16)])
+def test_fused_configs_agree(S, tile, cluster, nw, variant):
+    """Every kernel variant (shared-memory tile with 8/16 consumer warps, register tile with 8/12) x tile x cluster."""
     nb, nt = 3001, 517
     M, x, data = make_flat_problem(nb, nt, seed=11)
     nlq, Gq, gs, _ = O.fg_quad(x, M, data)
-    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw)
+    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw, variant=variant)
     i = ds.info()
-    assert i.fused == 1 and i.tile_bins == tile and i.cluster == cluster and i.consumer_warps == nw
+    if not i.fused:
+        pytest.skip("this (tile, cluster, warps) combination cannot hold T in its per-lane registers")
+    assert i.tile_bins == tile and i.cluster == cluster and i.consumer_warps == nw and i.register_tile == variant - 1
     nl, G, _ = ds.eval_fg(x)
     assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
     assert_grad_close(G, Gq, gs)
