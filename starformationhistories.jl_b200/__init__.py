@@ -16,6 +16,9 @@ from .fitting import (DeviceStack, clear_cache, composite_, device_stack, fg_ as
 from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR, LogarithmicAMR, PowerLawMZR,
                            calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams)
 from .sampling import HMCModel, MCMCModel
+from . import sharding, solvers
+from .solvers import (fit_sfh, fit_templates, fit_templates_fast, fit_templates_lbfgsb, hmc_sample, mcmc_sample,
+                      renormalize_x0)
 from .sharding import allreduce_fg, guard_neg_logl, init_library_comm, shard_rows
 
 
@@ -34,4 +37,5 @@ __all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite
            "grad_loglikelihood", "grad_loglikelihood_", "fg_", "calculate_coeffs", "PowerLawMZR", "LinearAMR",
            "LogarithmicAMR", "GaussianDispersion", "HierarchicalOptimizer", "HMCModel", "MCMCModel", "nparams",
            "exptransform", "logtransform", "clear_cache", "device_stack", "shard_rows", "allreduce_fg", "guard_neg_logl",
-           "init_library_comm"]
+           "init_library_comm", "fit_templates_lbfgsb", "fit_templates", "fit_templates_fast", "fit_sfh", "mcmc_sample",
+           "hmc_sample", "renormalize_x0"]

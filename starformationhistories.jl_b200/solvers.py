@@ -1,0 +1,348 @@
+"""Host-side mirrors of the reference DRIVERS that own the iteration loop (SURVEY.md section 8f "next" rows):
+
+    renormalize_x0           src/fitting/utilities.jl:104-121
+    fit_templates_lbfgsb     src/fitting/solvers.jl:70-90     (LBFGSB.jl  -> scipy's L-BFGS-B 3.0, same Fortran lineage)
+    fit_templates            src/fitting/solvers.jl:163-221   (Optim BFGS on log-coefficients: MAP then MLE)
+    fit_templates_fast       src/fitting/solvers.jl:238-275   (Optim BFGS on sqrt-coefficients: MLE only)
+    fit_sfh                  src/fitting/hierarchical/generic_fitting.jl:242-411 (BFGS on the HierarchicalOptimizer)
+    mcmc_sample              src/fitting/mcmc_sample.jl:97-130 (KissMCMC.emcee -> affine-invariant stretch move;
+                             each half-ensemble is ONE batched device call instead of W/2 host gemv's)
+    hmc_sample               src/fitting/hmc_sample.jl:105-143 (DynamicHMC NUTS -> a compact NUTS with dual averaging)
+
+The optimisation / sampling ENGINES are third-party in the reference too (LBFGSB, Optim, DynamicHMC, KissMCMC);
+they are replaced by scipy or by short textbook implementations and are NOT part of the parity claim --
+per-iterate trajectories differ between engines, converged answers and posterior moments do not.  Every
+objective / gradient / log-likelihood evaluation goes through the device path (`fg_`, `HierarchicalOptimizer`,
+`MCMCModel.batch`, `HMCModel`); nothing here evaluates the model on the host.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy import optimize
+
+from .fitting import DeviceStack, composite_, device_stack, fg_ as _fg_flat
+from .hierarchical import HierarchicalOptimizer, calculate_coeffs, logtransform, exptransform
+from .sampling import HMCModel, MCMCModel
+
+
+# ---------------------------------------------------------------------------------------------
+def renormalize_x0(data, models, x0, full_coeffs=None):
+    """Scale x0 so that sum(composite(full_coeffs)) == sum(data)  (fitting/utilities.jl:104-115)."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    full = x0 if full_coeffs is None else np.asarray(full_coeffs, dtype=np.float64)
+    ds = device_stack(models, data)
+    comp = np.empty(ds.rows)
+    composite_(comp, full, ds)
+    csum = comp.sum()
+    if csum == 0:
+        return x0.copy()                                                   # :112
+    return x0 * (np.asarray(data, dtype=np.float64).sum() / csum)          # :113-114
+
+
+def _check_sizes(x0, ds):
+    if np.asarray(x0).shape[0] != ds.shape[1]:
+        raise ValueError("axes(coeffs,1) != axes(models,2)")               # solvers.jl:10
+
+
+# ---------------------------------------------------------------------------------------------
+def fit_templates_lbfgsb(models, data, x0=None, factr=1e-12, pgtol=1e-5, iprint=0, **kws):
+    """Returns (-logL, coeffs): box-constrained (coeffs >= 0) L-BFGS-B on fg!  (solvers.jl:82-90)."""
+    ds = device_stack(models, data)
+    x0 = np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, dtype=np.float64)
+    _check_sizes(x0, ds)
+    x0 = renormalize_x0(data, ds, x0)                                      # :86
+    G = np.empty(ds.shape[1])
+
+    def fg(x):                                                             # :88
+        return float(_fg_flat(True, G, x, ds, data)), G.copy()
+
+    kws.setdefault("m", 10)
+    kws.setdefault("maxfun", 100000)
+    kws.setdefault("maxiter", 100000)
+    # (`iprint` is accepted for signature parity; recent scipy dropped the L-BFGS-B print switch)
+    x, f, info = optimize.fmin_l_bfgs_b(fg, x0, bounds=[(0.0, None)] * ds.shape[1], factr=factr, pgtol=pgtol, **kws)
+    return f, x
+
+
+@dataclass
+class LogTransformFTResult:
+    """solvers.jl:115-129: mu (natural units), sigma = sqrt(diag(invH)) * mu, invH in log space, engine result."""
+    mu: np.ndarray
+    sigma: np.ndarray
+    invH: np.ndarray
+    result: object
+
+    def rand(self, rng, n):
+        z = rng.multivariate_normal(np.log(self.mu), (self.invH + self.invH.T) / 2, size=n)   # :127-128
+        return np.exp(z).T
+
+
+def _bfgs(fun, x0, gtol=1e-8, maxiter=5000):
+    return optimize.minimize(fun, x0, jac=True, method="BFGS", options={"gtol": gtol, "maxiter": maxiter})
+
+
+def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000):
+    """Returns {"map": LogTransformFTResult, "mle": ...}: BFGS on log-coefficients (solvers.jl:172-221)."""
+    ds = device_stack(models, data)
+    x0 = np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, dtype=np.float64)
+    _check_sizes(x0, ds)
+    x0 = np.log(renormalize_x0(data, ds, x0))                              # :175-176
+    G = np.empty(ds.shape[1])
+
+    def fg_map(logx):                                                      # :178-186
+        x = np.exp(logx)
+        f = float(_fg_flat(True, G, x, ds, data)) - logx.sum()
+        return f, G * x - 1
+
+    def fg_mle(logx):                                                      # :187-195
+        x = np.exp(logx)
+        f = float(_fg_flat(True, G, x, ds, data))
+        return f, G * x
+
+    rmap = _bfgs(fg_map, x0, g_abstol, iterations)                         # :206
+    rmle = _bfgs(fg_mle, rmap.x, g_abstol, iterations)                     # :207 (seeded from the MAP)
+    out = {}
+    for key, r in (("map", rmap), ("mle", rmle)):
+        mu = np.exp(r.x)
+        out[key] = LogTransformFTResult(mu, np.sqrt(np.abs(np.diag(r.hess_inv))) * mu, np.asarray(r.hess_inv), r)
+    return out
+
+
+def fit_templates_fast(models, data, x0=None, g_abstol=1e-8, iterations=5000):
+    """Returns (coeffs, result): BFGS on theta with coeffs = theta^2  (solvers.jl:248-275)."""
+    ds = device_stack(models, data)
+    x0 = np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, dtype=np.float64)
+    _check_sizes(x0, ds)
+    x0 = np.sqrt(renormalize_x0(data, ds, x0))                             # :251-252
+    G = np.empty(ds.shape[1])
+
+    def fg_mle(sqrtx):                                                     # :254-261
+        f = float(_fg_flat(True, G, sqrtx ** 2, ds, data))
+        return f, G * 2 * sqrtx
+
+    r = _bfgs(fg_mle, x0, g_abstol, iterations)
+    return r.x ** 2, r
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class BFGSResult:
+    """hierarchical/bfgs_result.jl:25-41: mu / sigma in natural units, invH in the transformed fitting space."""
+    mu: np.ndarray
+    sigma: np.ndarray
+    invH: np.ndarray
+    result: object
+    MH_model: object = None
+    disp_model: object = None
+
+
+def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000):
+    """BFGS on [log R_j, transformed free parameters]: MAP (Jacobian corrections on) then MLE seeded from it
+    (generic_fitting.jl:242-409).  Returns {"map": BFGSResult, "mle": BFGSResult}; mu holds
+    [R_1..R_Nj, alpha, beta, sigma] with fixed parameters at their initial values."""
+    ds = device_stack(models, data)
+    la, mh = np.asarray(logAge, float), np.asarray(metallicities, float)
+    _, first = np.unique(la, return_index=True)
+    nj = first.shape[0]
+    tf = np.array(list(MH_model0.transforms()) + list(disp_model0.transforms()))
+    free = np.array(list(MH_model0.free_params()) + list(disp_model0.free_params()), dtype=bool)
+    par0 = np.array(list(MH_model0.fittable_params()) + list(disp_model0.fittable_params()), dtype=np.float64)
+    if x0 is None:
+        x0 = np.ones(nj)
+    x0 = np.asarray(x0, dtype=np.float64)
+    if x0.shape[0] != nj:
+        raise ValueError("length(x0) != length(unique(logAge))")
+    full = calculate_coeffs(MH_model0, disp_model0, x0, la, mh)           # :260
+    if np.isnan(full).any():
+        raise ValueError("initial metallicity-model parameters give NaN coefficients (generic_fitting.jl:261-283)")
+    x0 = renormalize_x0(data, ds, x0, full)                                # :283
+    xstart = np.concatenate([np.log(x0), logtransform(par0, tf)[free]])    # :285-294
+    res = {}
+    start = xstart
+    for key, jac in (("map", True), ("mle", False)):                       # :304-327
+        opt = HierarchicalOptimizer(MH_model0, disp_model0, ds, data, la, mh, True, True, jac)
+
+        def fun(X, opt=opt):
+            lp, g = opt.logdensity_and_gradient(X)
+            return -lp, -g
+
+        r = _bfgs(fun, start, g_abstol, iterations)
+        start = r.x                                                        # MLE starts from the MAP minimiser
+        mu = np.empty(nj + tf.shape[0])
+        mu[:nj] = np.exp(r.x[:nj])
+        mu[nj:][free] = exptransform(r.x[nj:], tf[free])
+        mu[nj:][~free] = par0[~free]
+        # sigma: delta method through the log transforms (generic_fitting.jl:352-407)
+        sd = np.sqrt(np.abs(np.diag(r.hess_inv)))
+        sigma = np.zeros_like(mu)
+        sigma[:nj] = sd[:nj] * mu[:nj]
+        sfree = sd[nj:]
+        tfree = tf[free]
+        sigma[nj:][free] = np.where(tfree == 0, sfree, sfree * np.abs(mu[nj:][free]))
+        res[key] = BFGSResult(mu, sigma, np.asarray(r.hess_inv), r,
+                              MH_model0.update_params(mu[nj:nj + 2]), disp_model0.update_params(mu[nj + 2:]))
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+def stretch_move_ensemble(logp_batch, x0, nsteps, a_scale=2.0, rng=None, thin=1):
+    """Goodman & Weare affine-invariant ensemble sampler ("emcee", KissMCMC.emcee's algorithm) with the two
+    half-ensembles updated alternately, each half by ONE call of `logp_batch(X)` (X: (npar, W/2)).
+    x0: (npar, nwalkers).  Returns (chain (nsteps//thin, npar, nwalkers), logp, acceptance fraction)."""
+    rng = np.random.default_rng() if rng is None else rng
+    X = np.array(x0, dtype=np.float64, order="F")
+    npar, W = X.shape
+    if W % 2 or W < 2:
+        raise ValueError("need an even number of walkers")
+    half = W // 2
+    lp = logp_batch(X)
+    chain = np.empty((nsteps // thin, npar, W))
+    lps = np.empty((nsteps // thin, W))
+    acc = 0
+    for step in range(nsteps):
+        for h in (0, 1):
+            act = slice(0, half) if h == 0 else slice(half, W)
+            oth = slice(half, W) if h == 0 else slice(0, half)
+            z = ((a_scale - 1.0) * rng.random(half) + 1.0) ** 2 / a_scale  # g(z) ~ 1/sqrt(z) on [1/a, a]
+            partner = X[:, oth][:, rng.integers(0, half, size=half)]
+            prop = partner + z[None, :] * (X[:, act] - partner)
+            lpp = logp_batch(np.asfortranarray(prop))
+            with np.errstate(invalid="ignore"):
+                lnr = (npar - 1) * np.log(z) + lpp - lp[act]               # acceptance of the stretch move
+            ok = np.log(rng.random(half)) < lnr
+            ok &= np.isfinite(lpp)
+            Xa = X[:, act]
+            Xa[:, ok] = prop[:, ok]
+            X[:, act] = Xa
+            la = lp[act]
+            la[ok] = lpp[ok]
+            lp[act] = la
+            acc += int(ok.sum())
+        if (step + 1) % thin == 0:
+            chain[(step + 1) // thin - 1] = X
+            lps[(step + 1) // thin - 1] = lp
+    return chain, lps, acc / (nsteps * W)
+
+
+def mcmc_sample(models, data, x0, nsteps, nburnin=0, nthin=1, a_scale=2.0, rng=None):
+    """mcmc_sample(models, data, x0, nwalkers-implied, nsteps; nburnin, nthin, a_scale)  (mcmc_sample.jl:97-108).
+    x0: (npar, nwalkers) or list of walker vectors.  Returns samples with shape (nsteps, npar, nwalkers) like
+    convert_kissmcmc (:30-44), the log-likelihoods and the acceptance fraction."""
+    ds = device_stack(models, data)
+    X0 = np.asarray(x0, dtype=np.float64)
+    if X0.ndim == 2 and X0.shape[0] != ds.shape[1] and X0.shape[1] == ds.shape[1]:
+        X0 = X0.T                                                          # list of walker vectors
+    if X0.shape[0] != ds.shape[1]:
+        raise ValueError("length of each walker != number of templates")
+    model = MCMCModel(ds, data)
+    chain, lps, acc = stretch_move_ensemble(model.batch, X0, nsteps + nburnin, a_scale, rng, 1)
+    return chain[nburnin::nthin], lps[nburnin::nthin], acc
+
+
+# ---------------------------------------------------------------------------------------------
+def _leapfrog(lg, theta, r, grad, eps, inv_mass):
+    r = r + 0.5 * eps * grad
+    theta = theta + eps * inv_mass * r
+    lp, grad = lg(theta)
+    r = r + 0.5 * eps * grad
+    return theta, r, lp, grad
+
+
+def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None):
+    """No-U-Turn sampler (Hoffman & Gelman 2014, algorithm 6: slice NUTS with dual-averaging step size).
+    Stands in for DynamicHMC.mcmc_with_warmup (hmc_sample.jl:111); diagonal mass matrix fixed to `inv_mass`."""
+    rng = np.random.default_rng() if rng is None else rng
+    lg = logdensity_and_gradient
+    theta = np.asarray(theta0, dtype=np.float64).copy()
+    d = theta.shape[0]
+    inv_mass = np.ones(d) if inv_mass is None else np.asarray(inv_mass, dtype=np.float64)
+    lp, grad = lg(theta)
+
+    # heuristic initial step size
+    eps = 0.1 / math.sqrt(d)
+    r0 = rng.standard_normal(d) / np.sqrt(inv_mass)
+    _, r1, lp1, _ = _leapfrog(lg, theta, r0, grad, eps, inv_mass)
+    H0 = lp - 0.5 * np.dot(r0 * inv_mass, r0); H1 = lp1 - 0.5 * np.dot(r1 * inv_mass, r1)
+    a = 1.0 if (np.isfinite(H1) and H1 - H0 > math.log(0.5)) else -1.0
+    for _ in range(50):
+        _, r1, lp1, _ = _leapfrog(lg, theta, r0, grad, eps, inv_mass)
+        H1 = lp1 - 0.5 * np.dot(r1 * inv_mass, r1)
+        if not np.isfinite(H1):
+            H1 = -np.inf
+        if a * (H1 - H0) <= -a * math.log(2):
+            break
+        eps *= 2.0 ** a
+    mu, ebar, Hbar, gamma, t0, kappa = math.log(10 * eps), 1.0, 0.0, 0.05, 10.0, 0.75
+
+    def build(theta, r, grad, logu, v, j, eps, H0):
+        if j == 0:
+            th, rr, lpn, g = _leapfrog(lg, theta, r, grad, v * eps, inv_mass)
+            Hn = lpn - 0.5 * np.dot(rr * inv_mass, rr)
+            if not np.isfinite(Hn):
+                Hn = -np.inf
+            n = int(logu <= Hn)
+            s = int(logu < Hn + 1000.0)
+            return th, rr, g, th, rr, g, th, lpn, g, n, s, min(1.0, math.exp(min(0.0, Hn - H0))), 1
+        thm, rm, gm, thp, rp, gp, th1, lp1, g1, n1, s1, a1, na1 = build(theta, r, grad, logu, v, j - 1, eps, H0)
+        if s1:
+            if v == -1:
+                thm, rm, gm, _, _, _, th2, lp2, g2, n2, s2, a2, na2 = build(thm, rm, gm, logu, v, j - 1, eps, H0)
+            else:
+                _, _, _, thp, rp, gp, th2, lp2, g2, n2, s2, a2, na2 = build(thp, rp, gp, logu, v, j - 1, eps, H0)
+            if n1 + n2 > 0 and rng.random() < n2 / (n1 + n2):
+                th1, lp1, g1 = th2, lp2, g2
+            dth = thp - thm
+            s1 = s2 * int(np.dot(dth, rm * inv_mass) >= 0) * int(np.dot(dth, rp * inv_mass) >= 0)
+            n1 += n2; a1 += a2; na1 += na2
+        return thm, rm, gm, thp, rp, gp, th1, lp1, g1, n1, s1, a1, na1
+
+    samples = np.empty((nsteps, d))
+    lps = np.empty(nsteps)
+    for m in range(1, nwarmup + nsteps + 1):
+        r0 = rng.standard_normal(d) / np.sqrt(inv_mass)
+        H0 = lp - 0.5 * np.dot(r0 * inv_mass, r0)
+        logu = H0 + math.log(rng.random())
+        thm = thp = theta; rm = rp = r0; gm = gp = grad
+        j, n, s = 0, 1, 1
+        alpha, nalpha = 0.0, 1
+        while s and j < max_depth:
+            v = -1 if rng.random() < 0.5 else 1
+            if v == -1:
+                thm, rm, gm, _, _, _, th1, lp1, g1, n1, s1, alpha, nalpha = build(thm, rm, gm, logu, v, j, eps, H0)
+            else:
+                _, _, _, thp, rp, gp, th1, lp1, g1, n1, s1, alpha, nalpha = build(thp, rp, gp, logu, v, j, eps, H0)
+            if s1 and rng.random() < min(1.0, n1 / n):
+                theta, lp, grad = th1, lp1, g1
+            n += n1
+            dth = thp - thm
+            s = s1 * int(np.dot(dth, rm * inv_mass) >= 0) * int(np.dot(dth, rp * inv_mass) >= 0)
+            j += 1
+        if m <= nwarmup:                                                   # dual averaging
+            Hbar = (1 - 1 / (m + t0)) * Hbar + (delta - alpha / nalpha) / (m + t0)
+            leps = mu - math.sqrt(m) / gamma * Hbar
+            eta = m ** (-kappa)
+            ebar = math.exp(eta * leps + (1 - eta) * math.log(ebar))
+            eps = math.exp(leps)
+            if m == nwarmup:
+                eps = ebar
+        else:
+            samples[m - nwarmup - 1] = theta
+            lps[m - nwarmup - 1] = lp
+    return samples, lps, eps
+
+
+def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, max_depth=8):
+    """hmc_sample(models, data, nsteps[, nchains])  (hmc_sample.jl:105-143): NUTS on theta = log(coeffs) with the
+    Jacobian-corrected log-density of HMCModel.  Returns natural-unit samples of shape (nsteps, npar, nchains)."""
+    ds = device_stack(models, data)
+    model = HMCModel(ds, None, data)
+    rng = np.random.default_rng() if rng is None else rng
+    x0 = renormalize_x0(data, ds, np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, float))
+    out = np.empty((nsteps, ds.shape[1], nchains))
+    for c in range(nchains):
+        s, _, _ = nuts_sample(model.logdensity_and_gradient, np.log(x0), nsteps, nwarmup, max_depth, rng=rng)
+        out[:, :, c] = np.exp(s)                                           # back to natural units
+    return out

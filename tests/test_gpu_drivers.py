@@ -1,0 +1,134 @@
+"""End-to-end drivers on the device path, mirroring test/fitting/basic_linear_combinations.jl (:16-186) and the
+fit_sfh tests of mzr_test.jl:178-199: the solvers must recover the truth on noise-free data (rtol 1e-7, Julia's
+norm-wise isapprox), stay within 1e-2 on Poisson data and agree between layouts; the samplers must produce the
+right shapes -- and, beyond the reference's own shape-only checks, chains driven by the device log-likelihood must
+follow the chains driven by the CPU oracle (same engine, same RNG)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import make_hier_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sfh_b200
+    return sfh_b200
+
+
+@pytest.fixture(scope="module")
+def V():
+    from sfh_b200 import solvers
+    return solvers
+
+
+def isapprox(a, b, rtol):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) <= rtol * max(np.linalg.norm(a), np.linalg.norm(b))
+
+
+def test_single_template_exact(S, V):                              # basic_linear_combinations.jl:16-37
+    models = [np.array([[0, 0, 0], [0, 0, 0], [1, 1, 1]], dtype=np.float64)]
+    data = np.array([[0, 0, 0], [0, 0, 0], [3, 3, 3]], dtype=np.int64)
+    x0 = np.array([1.0])
+    assert V.fit_templates_lbfgsb(models, data, x0=x0)[1][0] == pytest.approx(3, rel=1e-7)
+    sm, sd = S.stack_models(models), data.reshape(-1, order="F")
+    assert V.fit_templates_lbfgsb(sm, sd, x0=x0)[1][0] == pytest.approx(3, rel=1e-7)
+    assert V.fit_templates(models, data, x0=x0)["mle"].mu[0] == pytest.approx(3, rel=1e-7)
+    assert V.fit_templates_fast(sm, sd, x0=x0)[0][0] == pytest.approx(3, rel=1e-7)
+
+
+def test_noise_free_recovery(S, V):                                # basic_linear_combinations.jl:39-89
+    rng = np.random.Generator(np.random.Philox(58392))
+    N = 10
+    x, x0 = rng.random(N), rng.random(N)
+    models = [rng.random((100, 100)) for _ in range(N)]
+    data = sum(c * m for c, m in zip(x, models))
+    sm, sd = S.stack_models(models), data.reshape(-1, order="F")
+    assert isapprox(V.fit_templates_lbfgsb(models, data, x0=x0)[1], x, 1e-7)
+    assert isapprox(V.fit_templates_lbfgsb(sm, sd, x0=x0)[1], x, 1e-7)
+    assert isapprox(V.fit_templates(sm, sd, x0=x0)["mle"].mu, x, 1e-7)
+    assert isapprox(V.fit_templates_fast(sm, sd, x0=x0)[0], x, 1e-7)
+    x2 = x.copy(); x2[0] = 0; x2[-1] = 0                               # :66-89 zero coefficients
+    d2 = sum(c * m for c, m in zip(x2, models)).reshape(-1, order="F")
+    assert isapprox(V.fit_templates_lbfgsb(sm, d2, x0=x0)[1], x2, 1e-7)
+    assert isapprox(V.fit_templates(sm, d2, x0=x0)["mle"].mu, x2, 1e-6)
+    assert isapprox(V.fit_templates_fast(sm, d2, x0=x0)[0], x2, 1e-7)
+
+
+def test_poisson_recovery_and_oracle_agreement(S, V):             # basic_linear_combinations.jl:92-118
+    from scipy import optimize
+    rng = np.random.Generator(np.random.Philox(58393))
+    N = 10
+    x = rng.random(N) * 100
+    models = [rng.random((100, 100)) for _ in range(N)]
+    data = rng.poisson(sum(c * m for c, m in zip(x, models))).astype(np.int64)
+    sm, sd = S.stack_models(models), data.reshape(-1, order="F")
+    f1, r1 = V.fit_templates_lbfgsb(models, data, x0=np.ones(N))
+    f2, r2 = V.fit_templates_lbfgsb(sm, sd, x0=np.ones(N))
+    assert isapprox(r1, x, 1e-2) and isapprox(r2, x, 1e-2) and isapprox(r1, r2, 1e-5)
+    ft = V.fit_templates(sm, sd, x0=np.ones(N))
+    assert isapprox(ft["mle"].mu, x, 1e-2) and isapprox(ft["map"].mu, x, 2e-2)
+    assert ft["mle"].sigma.shape == (N,) and np.all(ft["mle"].sigma > 0) and ft["mle"].invH.shape == (N, N)
+    assert ft["map"].rand(np.random.default_rng(0), 3).shape == (N, 3)   # solvers.jl:111-113
+    assert isapprox(V.fit_templates_fast(sm, sd, x0=np.ones(N))[0], x, 1e-2)
+    # the same engine driven by the CPU oracle converges to the same optimum (end-to-end parity of the objective)
+    x0r = np.ones(N) * sd.sum() / (sm @ np.ones(N)).sum()
+    xo, fo, _ = optimize.fmin_l_bfgs_b(lambda z: tuple(map(lambda t: t, (float(O.fg(z, sm, sd)[0]), O.fg(z, sm, sd)[1]))),
+                                       x0r, bounds=[(0, None)] * N, factr=1e-12, pgtol=1e-5, m=10)
+    assert isapprox(r2, xo, 1e-6) and f2 == pytest.approx(fo, rel=1e-10)
+
+
+def test_fit_sfh_recovers_truth(S, V):                             # mzr_test.jl:178-199
+    p = make_hier_problem(nj=21, nk=26, nb=10000)
+    mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
+    xt = S.calculate_coeffs(mz, dp, p["R"], p["logAge"], p["MH"])
+    truth = np.concatenate([p["R"], [1.0, -2.0, 0.2]])
+    data2 = p["M"] @ xt                                               # perfect data, no noise (:66)
+    x0 = p["R"] * 1.5                                                 # :180-182 start 1.5x off
+    start_mz, start_dp = S.PowerLawMZR(1.2, -2.2, 6.0), S.GaussianDispersion(0.25)
+    res = V.fit_sfh(start_mz, start_dp, p["M"], data2, p["logAge"], p["MH"], x0=x0)
+    assert np.allclose(res["mle"].mu, truth, rtol=1e-4), np.max(np.abs(res["mle"].mu / truth - 1))
+    # noisy data: within 3 sigma of the truth for nearly every parameter (:192-199)
+    data = p["rng"].poisson(p["M"] @ xt).astype(np.float64)
+    resn = V.fit_sfh(start_mz, start_dp, p["M"], data, p["logAge"], p["MH"], x0=x0)
+    z = np.abs(resn["map"].mu - truth) / resn["map"].sigma
+    assert np.mean(z < 3) > 0.9
+    # fixed sigma stays fixed and gets zero uncertainty (:202-216)
+    resf = V.fit_sfh(start_mz, S.GaussianDispersion(0.2, (False,)), p["M"], data, p["logAge"], p["MH"], x0=x0)
+    assert resf["mle"].mu[-1] == 0.2 and resf["mle"].sigma[-1] == 0.0 and resf["mle"].invH.shape == (23, 23)
+
+
+def test_mcmc_sample_shapes_and_oracle_chain(S, V):              # basic_linear_combinations.jl:120-154
+    rng = np.random.Generator(np.random.Philox(7))
+    N, nwalkers, nsteps = 10, 100, 20
+    x = rng.random(N) * 100
+    models = [rng.random((30, 30)) for _ in range(N)]
+    data = rng.poisson(sum(c * m for c, m in zip(x, models))).astype(np.int64)
+    sm, sd = S.stack_models(models), data.reshape(-1, order="F")
+    x0 = np.maximum(0.0, x[:, None] + rng.standard_normal((N, nwalkers)))
+    chain, lps, acc = V.mcmc_sample(sm, sd, x0, nsteps, rng=np.random.default_rng(11))
+    assert chain.shape == (nsteps, N, nwalkers) and chain.dtype == np.float64 and 0.05 < acc < 0.95
+    assert np.all(chain >= 0)                                         # negative proposals are rejected (-Inf)
+    # the same sampler driven by the oracle log-likelihood, same RNG: identical accept/reject decisions
+    ref, lps_o, acc_o = V.stretch_move_ensemble(lambda X: O.mcmc_logl(X, sm, sd), x0, nsteps, rng=np.random.default_rng(11))
+    assert acc == acc_o and np.allclose(chain, ref, rtol=1e-12, atol=0) and np.allclose(lps, lps_o, rtol=1e-11)
+    # posterior mean close to the MLE
+    burn = V.mcmc_sample(sm, sd, x0, 300, nburnin=200, rng=np.random.default_rng(12))[0]
+    mle = V.fit_templates_lbfgsb(sm, sd, x0=np.ones(N))[1]
+    assert np.allclose(burn.mean(axis=(0, 2)), mle, rtol=0.05, atol=0.5)
+
+
+def test_hmc_sample_shapes_and_moments(S, V):                    # basic_linear_combinations.jl:156-186
+    rng = np.random.Generator(np.random.Philox(9))
+    N = 6
+    x = rng.random(N) * 100 + 20
+    models = [rng.random((40, 40)) for _ in range(N)]
+    data = rng.poisson(sum(c * m for c, m in zip(x, models))).astype(np.int64)
+    out = V.hmc_sample(models, data, 150, nchains=2, nwarmup=100, rng=np.random.default_rng(3))
+    assert out.shape == (150, N, 2) and np.all(out > 0)
+    ft = V.fit_templates(models, data, x0=np.ones(N))
+    z = np.abs(out.mean(axis=(0, 2)) - ft["map"].mu) / ft["map"].sigma
+    assert np.all(z < 1.0), z                                          # posterior mean within 1 sigma of the MAP
