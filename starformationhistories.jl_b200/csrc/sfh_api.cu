@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <mutex>
 #include <new>
@@ -923,10 +924,23 @@ int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_log
     bp.nb = s->rows; bp.nt = s->nt; bp.W = W; bp.ld = s->ld; bp.wld = wld; bp.eps = s->eps; bp.Xt = c->d_Xt;
     bp.data = s->d_data; bp.part = c->d_part;
     if (nbt > 0) {
-        if (s->dtype == SFH_F64)
-            sfh_batched_logl_kernel<double><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const double *)s->dM, bp);
-        else
-            sfh_batched_logl_kernel<float><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const float *)s->dM, bp);
+        static const bool use_fma = [] { const char *e = getenv("SFH_BATCHED_IMPL"); return e && !strcmp(e, "fma"); }();
+        if (use_fma) {  // v1 (FP64 FMA pipe) kept for A/B measurements
+            if (s->dtype == SFH_F64)
+                sfh_batched_logl_kernel<double><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const double *)s->dM, bp);
+            else
+                sfh_batched_logl_kernel<float><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const float *)s->dM, bp);
+        } else if (s->dtype == SFH_F64) {
+            CU_TRY(cudaFuncSetAttribute(sfh_batched_logl_mma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)mma_smem_bytes<double>()));
+            sfh_batched_logl_mma_kernel<double><<<(unsigned)(nbt * nwt), kMmaThreads, mma_smem_bytes<double>(), c->stream>>>(
+                (const double *)s->dM, bp);
+        } else {
+            CU_TRY(cudaFuncSetAttribute(sfh_batched_logl_mma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)mma_smem_bytes<float>()));
+            sfh_batched_logl_mma_kernel<float><<<(unsigned)(nbt * nwt), kMmaThreads, mma_smem_bytes<float>(), c->stream>>>(
+                (const float *)s->dM, bp);
+        }
         CU_TRY(cudaGetLastError());
     }
     sfh_batched_reduce_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c->stream>>>(c->d_part, nbt, W, wld, d_logl);

@@ -143,6 +143,140 @@ __global__ void __launch_bounds__(kBwThreads) sfh_batched_logl_kernel(const S *_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K6 v2: the same contraction on the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA).  ncu on v1 showed the
+// kernel compute-bound (FP64 pipe 43 % busy, DRAM ~2 %) with its issue slots and shared-memory wavefronts spent
+// on operand delivery (8 LDS.128 + 64 DFMA per thread per k); one DMMA replaces 8 warp-wide DFMA and its
+// fragments need 5x fewer shared-memory wavefronts.  tcgen05 has no FP64 kind, so mma.sync is the tensor path
+// for this dtype.  CTA tile 128 bins x 128 walkers, 16 warps (4 x 4), warp tile 32 x 32 = 4 x 4 DMMA tiles,
+// BK = 16 templates per slab, 3-stage cp.async pipeline; rows padded by 4 doubles => conflict-free fragment loads.
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaBM = 128, kMmaBN = 128, kMmaBK = 16, kMmaStages = 3, kMmaThreads = 512;
+constexpr int kMmaLdA = kMmaBM + 4, kMmaLdB = kMmaBN + 4;  // doubles; stride = 4 (mod 16) => 16 distinct bank pairs
+template <typename S>
+__host__ __device__ constexpr size_t mma_smem_bytes() {
+    return (size_t)kMmaStages * kMmaBK * (kMmaLdA * sizeof(S) + kMmaLdB * sizeof(double)) + 4 * kMmaBN * sizeof(double);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <typename S>
+__global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(const S *__restrict__ M, const BatchedParams p) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    S *As = reinterpret_cast<S *>(bsm);                                                        // [stages][BK][LdA]
+    double *Bs = reinterpret_cast<double *>(bsm + (size_t)kMmaStages * kMmaBK * kMmaLdA * sizeof(S));  // [stages][BK][LdB]
+    double *colsum = Bs + (size_t)kMmaStages * kMmaBK * kMmaLdB;                               // [4][BN]
+    constexpr int EPV = 16 / sizeof(S);  // A elements per 16-byte cp.async
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp & 3, wn = warp >> 2;  // warp tile origin: bins wm*32, walkers wn*32
+    const int64_t n_wt = (p.W + kMmaBN - 1) / kMmaBN;
+    const int64_t bt = blockIdx.x / n_wt, wt = blockIdx.x % n_wt;  // walker tiles fastest: the M tile is shared via L2
+    const int64_t i0 = bt * kMmaBM, w0 = wt * kMmaBN;
+    const int64_t nslab = (p.nt + kMmaBK - 1) / kMmaBK;
+
+    auto issue_slab = [&](int64_t slab, int stage) {
+        const int64_t k0 = slab * kMmaBK;
+        // A: BK rows of BM elements, 16 bytes per cp.async
+        constexpr int A_VEC_PER_ROW = kMmaBM / EPV;
+        for (int v = tid; v < kMmaBK * A_VEC_PER_ROW; v += kMmaThreads) {
+            const int kk = v / A_VEC_PER_ROW, iv = (v % A_VEC_PER_ROW) * EPV;
+            const int64_t k = k0 + kk, i = i0 + iv;
+            const bool ok = (slab < nslab) && (k < p.nt) && (i < p.ld);   // rows in [nb, ld) are zero padding
+            cp_async16(As + ((size_t)stage * kMmaBK + kk) * kMmaLdA + iv, M + (ok ? i + k * p.ld : 0), ok);
+        }
+        constexpr int B_VEC_PER_ROW = kMmaBN / 2;
+        for (int v = tid; v < kMmaBK * B_VEC_PER_ROW; v += kMmaThreads) {
+            const int kk = v / B_VEC_PER_ROW, wv = (v % B_VEC_PER_ROW) * 2;
+            const int64_t k = k0 + kk, w = w0 + wv;
+            const bool ok = (slab < nslab) && (k < p.nt) && (w < p.wld);  // walkers in [W, wld) hold finite junk: masked later
+            cp_async16(Bs + ((size_t)stage * kMmaBK + kk) * kMmaLdB + wv, p.Xt + (ok ? k * p.wld + w : 0), ok);
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int s = 0; s < kMmaStages - 1; ++s) issue_slab(s, s);
+    const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
+    for (int64_t slab = 0; slab < nslab; ++slab) {
+        const int stage = (int)(slab % kMmaStages);
+        cp_async_wait<kMmaStages - 2>();
+        __syncthreads();  // slab `slab` has landed for everyone; the stage refilled below was consumed last iteration
+        issue_slab(slab + kMmaStages - 1, (int)((slab + kMmaStages - 1) % kMmaStages));
+        const S *Asl = As + (size_t)stage * kMmaBK * kMmaLdA;
+        const double *Bsl = Bs + (size_t)stage * kMmaBK * kMmaLdB;
+#pragma unroll
+        for (int k4 = 0; k4 < kMmaBK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) a[mb] = (double)Asl[(k4 + fk) * kMmaLdA + wm * 32 + mb * 8 + fr];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) b[nb] = Bsl[(k4 + fk) * kMmaLdB + wn * 32 + nb * 8 + fr];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // Poisson epilogue: lane holds C[row = mb*8 + lane/4][col = nb*8 + (lane%4)*2 + {0,1}] of its warp tile
+    double csum[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) csum[nb][0] = csum[nb][1] = 0.0;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        const int64_t i = i0 + wm * 32 + mb * 8 + fr;
+        if (i < p.nb) {
+            const double n = p.data[i];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                csum[nb][0] += poisson_term(acc[mb][nb][0], n, p.eps);
+                csum[nb][1] += poisson_term(acc[mb][nb][1], n, p.eps);
+            }
+        }
+    }
+    // sum over the 8 lanes that share lane%4 (the rows of the fragment): fixed xor tree
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double v = csum[nb][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            csum[nb][e] = v;
+        }
+    if (fr == 0) {
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) colsum[wm * kMmaBN + wn * 32 + nb * 8 + fk * 2 + e] = csum[nb][e];
+    }
+    __syncthreads();
+    if (tid < kMmaBN) {
+        const int64_t w = w0 + tid;
+        if (w < p.W)
+            p.part[bt * p.wld + w] = (colsum[tid] + colsum[kMmaBN + tid]) + (colsum[2 * kMmaBN + tid] + colsum[3 * kMmaBN + tid]);
+    }
+}
+
 // logL[w] = sum over bin tiles (fixed order); raw sums (guards applied after any all-reduce)
 __global__ void sfh_batched_reduce_kernel(const double *__restrict__ part, int64_t n_bt, int64_t W, int64_t wld,
                                           double *__restrict__ out) {
