@@ -171,6 +171,9 @@ struct sfh_ctx {
     float4 *d_flush = nullptr;
     int64_t flush_n4 = 0;
     sfh_stats stats{};
+    // CUDA graphs of the host-synchronous call sequences (one launch instead of 3-6 per evaluation)
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; bool failed = false; int64_t launches = 0, evals = 0; uint64_t key = 0; };
+    GraphSlot g_fg[2], g_hier;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -311,7 +314,8 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
                 // measured: the register-tile variants are consumer-latency bound (2-3 warps per scheduler), not HBM bound
                 const double exposed = v.rt ? 2.5 : (v.ctas_per_sm == 2 ? 0.35 : 1.0);       // of the ~1 us exchange
                 const double eff = tile_us / (tile_us + exposed);
-                const double rowlen = std::min(1.0, 0.94 + 0.06 * (bt * elem_size(s->dtype)) / 256.0);  // 128 B rows: -3 %
+                const size_t rowb = bt * elem_size(s->dtype);  // contiguous bytes per template row of a TMA box
+                const double rowlen = rowb >= 256 ? 1.0 : (rowb >= 128 ? 0.97 : 0.88);  // measured (r1_sweep_config3_*.txt)
                 const double score = sm_frac * balance * eff * rowlen;
                 if (score > best_score || (forced && best_bt == 0)) {
                     best_score = score; best_bt = bt; best_c = c; best_kt = kt; best_nw = nw; best_ring = ring;
@@ -573,6 +577,8 @@ extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
     if (c->s) cudaSetDevice(c->s->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto *g : {&c->g_fg[0], &c->g_fg[1], &c->g_hier})
+        if (g->exec) cudaGraphExecDestroy(g->exec);
     cudaFree(c->d_coeffs); cudaFree(c->d_out); cudaFree(c->d_composite); cudaFree(c->d_residual);
     cudaFree(c->d_gpart); cudaFree(c->d_lpart); cudaFree(c->d_ticket);
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
@@ -605,22 +611,26 @@ extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
 // evaluation plumbing (device side)
 // ---------------------------------------------------------------------------------------------
 namespace {
-int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce) {
+int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce, double *out_host = nullptr) {
     const sfh_stack *s = c->s;
     FinalizeParams fp{};
     fp.nb = s->rows; fp.nt = s->nt; fp.gstride = c->gstride; fp.n_clusters = s->n_clusters; fp.want_G = want_G_reduce;
     fp.eps = s->eps; fp.composite = composite; fp.data = s->d_data; fp.gpart = c->d_gpart; fp.out = d_out;
-    fp.lpart = c->d_lpart; fp.ticket = c->d_ticket;
-    const int64_t work = std::max<int64_t>(s->rows, want_G_reduce ? s->nt : 0);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>((work + kFinalizeThreads - 1) / kFinalizeThreads, 1),
-                                      std::min(1024, 2 * std::max(s->sm_count, 1)));
+    fp.out_host = out_host; fp.lpart = c->d_lpart; fp.ticket = c->d_ticket;
+    // enough blocks that every thread has <= 1 bin and every warp <= 1 template (latency-bound kernel)
+    const int64_t cap = 4 * std::max(s->sm_count, 1);
+    const int64_t nblk_l = std::min<int64_t>(std::max<int64_t>((s->rows + kFinalizeThreads - 1) / kFinalizeThreads, 1), cap);
+    const int64_t need = std::max<int64_t>(nblk_l, want_G_reduce ? (s->nt + 7) / 8 : 0);
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(need, 1), cap);
+    fp.nblk_logl = (int32_t)nblk_l;
     CU_TRY(launch_pdl(sfh_finalize_kernel, dim3(grid), dim3(kFinalizeThreads), 0, c->stream, fp));
     c->stats.kernel_launches++;
     return SFH_OK;
 }
 
 // d_out = [logL raw, G...]; leaves M*coeffs in c->d_composite and (want_G) the residual in c->d_residual
-int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G, bool time_kernel) {
+int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G, bool time_kernel,
+                    double *out_host = nullptr) {
     sfh_stack *s = c->s;
     if (s->rows == 0 || s->nt == 0) {
         CU_TRY(cudaMemsetAsync(d_out, 0, (1 + std::max<int64_t>(s->nt, 0)) * 8, c->stream));
@@ -638,8 +648,9 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
 #undef LAUNCH
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
         c->stats.kernel_launches++;
-        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G));
+        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, c->comm ? nullptr : out_host));
     } else {
+        out_host = nullptr;  // the two-pass path writes G with gemv 'T': results are copied back explicitly
         // two-pass path: gemv 'N' -> logL -> residual -> gemv 'T'  (the reference's own pass structure)
         const unsigned gb = (unsigned)((s->rows + 127) / 128);
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
@@ -672,6 +683,38 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
     return SFH_OK;
 }
 
+// Capture `enqueue()` (async work on c->stream) into a CUDA graph on first use, then replay it: one driver call per
+// evaluation.  Falls back to plain launches if capture is unavailable (e.g. the caller's stream is itself capturing).
+template <typename F>
+int run_graphed(sfh_ctx *c, sfh_ctx::GraphSlot &slot, uint64_t key, F &&enqueue) {
+    static const bool disabled = [] { const char *e = getenv("SFH_NO_GRAPH"); return e && e[0] == '1'; }();
+    if (disabled || c->comm) return enqueue();
+    if (slot.exec && slot.key != key) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; slot.failed = false; }
+    if (!slot.exec && !slot.failed) {
+        const sfh_stats before = c->stats;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int st = enqueue();
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (st != SFH_OK || e != cudaSuccess || cudaGraphInstantiate(&slot.exec, g, 0) != cudaSuccess) {
+                slot.exec = nullptr; slot.failed = true; (void)cudaGetLastError();
+            }
+            if (g) cudaGraphDestroy(g);
+        } else {
+            slot.failed = true; (void)cudaGetLastError();
+        }
+        slot.launches = c->stats.kernel_launches - before.kernel_launches;
+        slot.evals = c->stats.evals - before.evals;
+        slot.key = key;
+        c->stats = before;  // nothing ran during capture
+    }
+    if (!slot.exec) return enqueue();
+    CU_TRY(cudaGraphLaunch(slot.exec, c->stream));
+    c->stats.kernel_launches += slot.launches;
+    c->stats.evals += slot.evals;
+    return SFH_OK;
+}
+
 inline double guard_neg_logl(double logL) {  // fitting_base.jl:95 then the sign flip of solvers.jl:31
     return (logL != 0.0) ? -logL : std::numeric_limits<double>::infinity();
 }
@@ -692,10 +735,17 @@ extern "C" int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, d
     CU_TRY(cudaSetDevice(s->device));
     const int want_G = G != nullptr;
     memcpy(c->h_in, coeffs, (size_t)s->nt * 8);
-    CU_TRY(cudaMemcpyAsync(c->d_coeffs, c->h_in, (size_t)s->nt * 8, cudaMemcpyHostToDevice, c->stream));
-    SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false));
-    const size_t n_out = want_G ? (size_t)(1 + s->nt) : 1;
-    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+    // single-GPU fused path: the finalize kernel stores [logL, G] straight into the mapped pinned buffer
+    const bool direct = s->fused && !c->comm && s->rows > 0 && s->nt > 0;
+    SFH_TRY(run_graphed(c, c->g_fg[want_G], 1, [&]() -> int {
+        CU_TRY(cudaMemcpyAsync(c->d_coeffs, c->h_in, (size_t)s->nt * 8, cudaMemcpyHostToDevice, c->stream));
+        SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, direct ? c->h_out : nullptr));
+        if (!direct) {
+            const size_t n_out = want_G ? (size_t)(1 + s->nt) : 1;
+            CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        return SFH_OK;
+    }));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (neg_logL) *neg_logL = guard_neg_logl(c->h_out[0]);
     if (G) memcpy(G, c->h_out + 1, (size_t)s->nt * 8);
@@ -879,13 +929,24 @@ extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed,
     const int want_G = G != nullptr;
     const size_t nv = (size_t)c->nj + 3;
     memcpy(c->h_in, variables, nv * 8);
-    CU_TRY(cudaMemcpyAsync(c->d_vars, c->h_in, nv * 8, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(launch_pdl(sfh_hier_prologue_kernel, dim3(1), dim3(kHierThreads), 0, c->stream, hp));
-    SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false));
-    CU_TRY(launch_pdl(sfh_hier_epilogue_kernel, dim3(1), dim3(kHierThreads), 0, c->stream, hp, want_G));
-    c->stats.kernel_launches += 2;
-    const size_t n_out = want_G ? 1 + nv : 1;
-    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_outh, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+    hp.out_host = c->comm ? nullptr : c->h_out;  // epilogue stores [-logL, G] straight into the mapped pinned buffer
+    // graph key: everything baked into the captured kernel parameters
+    uint64_t key = 0xcbf29ce484222325ull;
+    auto mix = [&](const void *ptr, size_t n) { for (size_t i = 0; i < n; ++i) key = (key ^ ((const unsigned char *)ptr)[i]) * 0x100000001b3ull; };
+    mix(&hp.kind, sizeof hp.kind); mix(hp.fixed, sizeof hp.fixed); mix(hp.free_mask, sizeof hp.free_mask); mix(&want_G, sizeof want_G);
+    mix(&c->nj, sizeof c->nj); mix(&c->d_jidx, sizeof c->d_jidx);
+    SFH_TRY(run_graphed(c, c->g_hier, key, [&]() -> int {
+        CU_TRY(cudaMemcpyAsync(c->d_vars, c->h_in, nv * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(launch_pdl(sfh_hier_prologue_kernel, dim3(1), dim3(kHierThreads), 0, c->stream, hp));
+        SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false));
+        CU_TRY(launch_pdl(sfh_hier_epilogue_kernel, dim3(1), dim3(kHierThreads), 0, c->stream, hp, want_G));
+        c->stats.kernel_launches += 2;
+        if (!hp.out_host) {
+            const size_t n_out = want_G ? 1 + nv : 1;
+            CU_TRY(cudaMemcpyAsync(c->h_out, c->d_outh, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        return SFH_OK;
+    }));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (neg_logL) *neg_logL = c->h_out[0];
     if (G) memcpy(G, c->h_out + 1, nv * 8);

@@ -45,50 +45,61 @@ __device__ __forceinline__ double poisson_term(double m, double n, double eps) {
 struct FinalizeParams {
     int64_t nb, nt, gstride;
     int32_t n_clusters, want_G;
+    int32_t nblk_logl;  // blocks that own bins: depends on nb only, so logL is bitwise identical with and without G
     double eps;
     const double *composite, *data, *gpart;
-    double *out;
-    double *lpart;       // [gridDim.x]
+    double *out;       // device [1 + nt]
+    double *out_host;  // nullable: mapped pinned host copy of the same (saves the D2H memcpy of the sync API)
+    double *lpart;     // [gridDim.x] per-block logL partials
     unsigned int *ticket;
 };
 constexpr int kFinalizeThreads = 256;
 
+// Everything here is latency, not bandwidth (60 k logs, ~1 MB of partials): the shape is chosen so that no thread
+// ever waits on more than ~2 dependent L2 round trips.  Measured alternatives (ncu launch lists under profiles/):
+// 296 blocks with a per-thread serial loop over the cluster partials 13 us; one 8-CTA cluster with a DSMEM
+// reduction 27 us (too few threads: 15 dependent load+log chains each).
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
     griddep_wait();  // PDL: launched while the fused kernel drains
-    // fixed contiguous slice of bins per block -> deterministic partials
-    const int64_t per = (p.nb + gridDim.x - 1) / gridDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // logL: fixed contiguous slice of bins per block, fixed trees => deterministic
+    const int64_t per = (p.nb + p.nblk_logl - 1) / p.nblk_logl;
     const int64_t b0 = (int64_t)blockIdx.x * per;
-    const int64_t b1 = (b0 + per < p.nb) ? b0 + per : p.nb;
+    const int64_t b1 = ((int)blockIdx.x >= p.nblk_logl) ? b0 : ((b0 + per < p.nb) ? b0 + per : p.nb);
     double acc = 0.0;
     for (int64_t i = b0 + threadIdx.x; i < b1; i += kFinalizeThreads)
-        acc += poisson_term(p.composite[i], p.data[i], p.eps);
+        acc += poisson_term(__ldcg(p.composite + i), p.data[i], p.eps);
     const double tot = block_sum<kFinalizeThreads>(acc, sh);
     if (threadIdx.x == 0) p.lpart[blockIdx.x] = tot;
 
+    // G_j = sum over clusters: one WARP per template, lanes take clusters lane, lane+32, ... (independent loads)
     if (p.want_G) {
-        for (int64_t j = (int64_t)blockIdx.x * kFinalizeThreads + threadIdx.x; j < p.nt;
-             j += (int64_t)gridDim.x * kFinalizeThreads) {
-            double g = 0.0;
-#pragma unroll 8
-            for (int cl = 0; cl < p.n_clusters; ++cl) g += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
-            p.out[1 + j] = g;
+        const int64_t nwarps = (int64_t)gridDim.x * (kFinalizeThreads / 32);
+        for (int64_t j = (int64_t)blockIdx.x * (kFinalizeThreads / 32) + warp; j < p.nt; j += nwarps) {
+            double s = 0.0;
+            for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
+            s = warp_sum(s);
+            if (lane == 0) {
+                p.out[1 + j] = s;
+                if (p.out_host) p.out_host[1 + j] = s;
+            }
         }
     }
-    // last block folds the per-block logL partials in fixed order
+    // last block folds the per-block logL partials (parallel, fixed order)
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (last) {
         __threadfence();
-        // fixed assignment (thread t owns partials t, t+256, ...) + fixed shuffle tree => deterministic
         double s = 0.0;
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += kFinalizeThreads) s += __ldcg(p.lpart + b);
+        for (int b = threadIdx.x; b < p.nblk_logl; b += kFinalizeThreads) s += __ldcg(p.lpart + b);
         const double all = block_sum<kFinalizeThreads>(s, sh);
         if (threadIdx.x == 0) {
             p.out[0] = all;
+            if (p.out_host) p.out_host[0] = all;
             *p.ticket = 0u;  // re-arm for the next evaluation on this context
         }
     }
@@ -185,6 +196,7 @@ struct HierParams {
     double *coeffs;                          // [nt] out of the prologue
     const double *fg_out;                    // [1+nt]: logL raw, +M'r  (input of the epilogue)
     double *out;                             // [1 + nj + 3]: -logL (guarded), G
+    double *out_host;                        // nullable: mapped pinned host copy of `out`
 };
 
 __device__ __forceinline__ double d_X_from_Z(double Z, double Yp, double gam) { return 1.0 - ((Yp + gam * Z) + Z); }
@@ -275,7 +287,9 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const H
     const int nj = p.nj;
     if (tid == 0) {
         const double logL = p.fg_out[0];
-        p.out[0] = (logL != 0.0) ? -logL : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95
+        const double v = (logL != 0.0) ? -logL : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95
+        p.out[0] = v;
+        if (p.out_host) p.out_host[0] = v;
     }
     if (!want_G) return;
     const double sigma = p.variables[nj + 2];
@@ -337,6 +351,10 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const H
         G[nj] = p.free_mask[0] ? ga : 0.0;
         G[nj + 1] = p.free_mask[1] ? gb : 0.0;
         G[nj + 2] = p.free_mask[2] ? gs : 0.0;
+    }
+    if (p.out_host) {  // G is complete only after thread 0's serial tail above
+        __syncthreads();
+        for (int j = tid; j < nj + 3; j += kHierThreads) p.out_host[1 + j] = G[j];
     }
 }
 
