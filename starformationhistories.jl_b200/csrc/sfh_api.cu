@@ -137,6 +137,7 @@ struct sfh_stack {
     bool rt = false;  // register-resident tile variant
     uint32_t smem = 0;
     bool evict_first = false;
+    int l2_prefetch = 0;  // tiles of L2 look-ahead; measured SLOWER (209 -> 261 us at 1 tile), kept as an experiment knob
     CUtensorMap tmap;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t l2_bytes = 0;
@@ -363,6 +364,7 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     s->n_clusters = std::min(maxcl, s->n_tiles);
     // the stack is streamed exactly once per evaluation: do not let it evict the O(Nb) vectors
     s->evict_first = (size_t)s->ld * s->nt * elem_size(s->dtype) > s->l2_bytes;
+    if (const char *e = getenv("SFH_L2_PREFETCH")) s->l2_prefetch = atoi(e);
     s->fused = true;
     return SFH_OK;
 }
@@ -639,7 +641,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
     if (s->fused) {
         FusedParams p{};
         p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ring = s->ring; p.n_tiles = s->n_tiles;
-        p.evict_first = s->evict_first ? 1 : 0; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
+        p.evict_first = s->evict_first ? 1 : 0; p.l2_prefetch = s->l2_prefetch; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
         p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
         p.gstride = c->gstride;
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));

@@ -50,6 +50,7 @@ struct FusedParams {
     int32_t ring;        // ring chunk-slots: a multiple of the stage size
     int32_t n_tiles;     // ceil(nb / BT)
     int32_t evict_first; // use an L2 evict_first policy on the stack loads
+    int32_t l2_prefetch; // tiles of look-ahead for cp.async.bulk.prefetch.tensor (0 = off)
     double eps;          // clamp (fitting_base.jl:90,277)
     const double *coeffs;   // [nt]
     const double *data;     // [nb] (converted to double at upload)
@@ -166,10 +167,18 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
             int ss = 0;
             uint32_t round = 0;  // how many times the ring has wrapped
             const int32_t t0 = (int32_t)(q * (uint32_t)(kt * RPC));
+            const int pf = p.l2_prefetch * (int)ncl;  // look-ahead in tiles of THIS cluster's sequence
             for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl) {
                 for (int s = 0; s < nst; ++s) {
-                    if (round > 0) mbar_wait(&empty[ss], (round - 1) & 1u);
                     const int cnt = (kt - s * G < G) ? (kt - s * G) : G;
+                    // pull the same chunks of a LATER tile into L2 now: not gated by a free shared-memory slot
+                    if (pf > 0 && tile + pf < p.n_tiles) {
+                        for (int u = 0; u < cnt; ++u) {
+                            const int32_t tcp = t0 + (s * G + u) * RPC;
+                            if (tcp < (int32_t)p.nt) tma_prefetch_l2_2d(&tmap, (tile + pf) * BT, tcp);
+                        }
+                    }
+                    if (round > 0) mbar_wait(&empty[ss], (round - 1) & 1u);
                     mbar_arrive_expect_tx(&full[ss], (uint32_t)cnt * kChunkBytes);
                     for (int u = 0; u < cnt; ++u) {
                         void *dst = smem + L.ring_off + (uint32_t)(ss * G + u) * kChunkBytes;
