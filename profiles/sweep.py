@@ -34,6 +34,10 @@ if which == "c3":
     combos = [(8, 16, 4, 1), (16, 16, 2, 1), (8, 16, 4, 2), (8, 8, 2, 2), (8, 32, 8, 2), (12, 16, 4, 2), (12, 32, 8, 2), (12, 8, 2, 2),
               (12, 16, 8, 2), (8, 16, 8, 2), (12, 8, 4, 2), (0, 0, 0, 0)]
     run(60000, 2400, np.float64, combos, label="config3")
+elif which == "panel":
+    combos = [(8, 16, 4, 1), (16, 16, 2, 1), (8, 8, 2, 1), (16, 8, 1, 1), (8, 8, 4, 1), (8, 32, 8, 1), (16, 32, 4, 1), (16, 64, 8, 1), (8, 64, 16, 1),
+              (8, 8, 2, 2), (12, 8, 2, 2), (8, 16, 4, 2), (12, 16, 4, 2)]
+    run(60000, 2400, np.float64, combos, label="config3")
 elif which == "rt":
     run(60000, 2400, np.float64, [(0, 0, 0, 0)], label="config3 auto")
     run(40000, 500, np.float64, [(0, 0, 0, 0), (8, 64, 1, 2), (8, 32, 1, 2), (12, 64, 1, 2), (12, 32, 1, 2), (8, 64, 2, 2), (8, 64, 4, 1)], label="config2 stack")

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfhcuda.so")
+LIB_PATH = os.environ.get("SFH_LIB") or os.path.join(_HERE, "libsfhcuda.so")   # SFH_LIB: A/B experiment builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -137,8 +137,9 @@ struct sfh_stack {
     bool rt = false;  // register-resident tile variant
     uint32_t smem = 0;
     bool evict_first = false;
+    bool panel = false;  // EXPERIMENT (SFH_PANEL=1): interpret the buffer as bin-major panels (timing only)
     int l2_prefetch = 0;  // tiles of L2 look-ahead; measured SLOWER (209 -> 261 us at 1 tile), kept as an experiment knob
-    CUtensorMap tmap;
+    CUtensorMap tmap_full, tmap_tail;  // TMA boxes: a whole pipeline stage / the tile's last (shorter) stage
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t l2_bytes = 0;
 };
@@ -205,7 +206,7 @@ template <typename S, int BT, int NW, bool G, bool RT>
 cudaError_t max_clusters(const sfh_stack *s, int *out) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s->cluster * 1024u);
-    cfg.blockDim = dim3((NW + 1) * 32);
+    cfg.blockDim = dim3((NW + kProducerWarps) * 32);
     cfg.dynamicSmemBytes = s->smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -220,7 +221,7 @@ template <typename S, int BT, int NW, bool G, bool RT>
 cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(s->n_clusters * s->cluster));
-    cfg.blockDim = dim3((NW + 1) * 32);
+    cfg.blockDim = dim3((NW + kProducerWarps) * 32);
     cfg.dynamicSmemBytes = s->smem;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
@@ -232,7 +233,7 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G, RT>, s->tmap, p);
+    return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G, RT>, s->tmap_full, s->tmap_tail, p);
 }
 
 // kernel variants: (NW=16, smem tile) (NW=8, smem tile, 2 CTAs/SM) (NW=8, register tile) (NW=12, register tile)
@@ -342,13 +343,31 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     const TileGeom g = geom(s->dtype, s->bt, s->nw);
-    const cuuint64_t gdim[2] = {(cuuint64_t)s->rows, (cuuint64_t)s->nt};
-    const cuuint64_t gstr[1] = {(cuuint64_t)s->ld * elem_size(s->dtype)};
-    const cuuint32_t box[2] = {(cuuint32_t)s->bt, (cuuint32_t)g.rpc};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&s->tmap, s->dtype == SFH_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                     s->dM, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = CUDA_SUCCESS;
+    if (const char *e = getenv("SFH_PANEL")) s->panel = atoi(e) != 0;
+    const CUtensorMapDataType tdt = s->dtype == SFH_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const int G = stage_chunks_for(s->rt);
+    const bool one_op = g.rpc * G <= 256;              // a whole stage fits one TMA box (box dims <= 256)
+    const int tail = (s->kt % G) ? (s->kt % G) : G;     // chunks in the tile's last stage
+    for (int which = 0; which < 2 && r == CUDA_SUCCESS; ++which) {
+        CUtensorMap *dst = which ? &s->tmap_tail : &s->tmap_full;
+        const cuuint32_t rows_box = (cuuint32_t)(one_op ? g.rpc * (which ? tail : G) : g.rpc);
+        if (s->panel) {
+            const cuuint64_t gdim3[3] = {(cuuint64_t)s->bt, (cuuint64_t)s->nt, (cuuint64_t)s->n_tiles};
+            const cuuint64_t gstr3[2] = {(cuuint64_t)s->bt * elem_size(s->dtype), (cuuint64_t)s->bt * s->nt * elem_size(s->dtype)};
+            const cuuint32_t box3[3] = {(cuuint32_t)s->bt, rows_box, 1};
+            const cuuint32_t estr3[3] = {1, 1, 1};
+            r = enc(dst, tdt, 3, s->dM, gdim3, gstr3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t gdim[2] = {(cuuint64_t)s->rows, (cuuint64_t)s->nt};
+            const cuuint64_t gstr[1] = {(cuuint64_t)s->ld * elem_size(s->dtype)};
+            const cuuint32_t box[2] = {(cuuint32_t)s->bt, rows_box};
+            const cuuint32_t estr[2] = {1, 1};
+            r = enc(dst, tdt, 2, s->dM, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+    }
     if (r != CUDA_SUCCESS) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     const bool nonport = s->cluster > 8;
     // the opt-in MAXIMUM (not this stack's size): the attribute is per kernel function, shared by every stack
@@ -428,7 +447,7 @@ int stack_common_init(sfh_stack *s, int64_t nbins, int64_t ntemplates, int dtype
         s->row_end = opts->row_end;
     }
     s->rows = s->row_end - s->row_begin;
-    s->ld = std::max<int64_t>(round_up(s->rows, 32), 32);  // 16-byte-aligned TMA stride, 128-byte rows
+    s->ld = std::max<int64_t>(round_up(s->rows, 128), 128);  // 16-byte-aligned TMA stride; whole 128-bin panels
     s->eps = (opts && opts->clamp_eps > 0.0) ? opts->clamp_eps
              : (dtype == SFH_F32 ? (double)std::numeric_limits<float>::epsilon()
                                  : std::numeric_limits<double>::epsilon());
@@ -641,7 +660,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
     if (s->fused) {
         FusedParams p{};
         p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ring = s->ring; p.n_tiles = s->n_tiles;
-        p.evict_first = s->evict_first ? 1 : 0; p.l2_prefetch = s->l2_prefetch; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
+        p.evict_first = s->evict_first ? 1 : 0; p.l2_prefetch = s->l2_prefetch; p.panel = s->panel ? 1 : 0; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
         p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
         p.gstride = c->gstride;
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));

@@ -37,11 +37,24 @@ __host__ __device__ constexpr int kmax_for(int nw, bool rt) { return (rt && nw =
 // chunks per pipeline STAGE: one mbarrier wait / release per stage instead of per chunk (an already-complete
 // mbarrier.try_wait still costs ~90 cycles; with few warps per SM that latency, paid per chunk, made the
 // consumers -- not HBM -- the bottleneck).  kKMax and every kmax_for() are multiples of it.
-__host__ __device__ constexpr int stage_chunks_for(bool rt) { return rt ? 4 : 1; }
-// (measured, profiles/r1_sweep_config3_staged.txt: for the shared-memory-tile variants a coarser stage costs more in
-//  prefetch depth / late release than it saves in waits: 206 us at 1 chunk per stage vs 229 us at 2)
+#ifndef SFH_PRODUCERS
+#define SFH_PRODUCERS 2
+#endif
+#ifndef SFH_STAGE_SMEM
+#define SFH_STAGE_SMEM 2
+#endif
+__host__ __device__ constexpr int stage_chunks_for(bool rt) { return rt ? 4 : SFH_STAGE_SMEM; }
+// (one op per 2-chunk stage + 2 producers: 194 us; 1-chunk stages + 1 producer: 206 us; see r1_experiments.md)
 constexpr int kMaxCluster = 16;
 __host__ __device__ constexpr int chunk_bytes(int nw) { return nw * 32 * 16; }  // one 16-byte vector per consumer lane
+// TMA producer warps per CTA.  A single elected thread needs ~250 cycles per chunk (mbarrier try_wait on the empty
+// slot ~100, expect_tx, bulk-tensor issue): at 4 KB chunks that caps a CTA at ~31 GB/s (profiles/probes/bw_probe.cu
+// reproduces it: 4 KB x 26-slot ring, 1 producer thread, 1 CTA/SM -> 4.5 TB/s; 16 KB chunks -> 7.0 TB/s).
+// Two producers interleave the chunk sequence; 10 (or 18) warps still fit the 96-register budget of 5 warps/scheduler.
+constexpr int kProducerWarps = SFH_PRODUCERS;  // see profiles/r1_experiments.md for the producers x stage-size matrix
+
+// a pipeline stage (G chunks = G*RPC templates of the tile) is ONE bulk-tensor op
+constexpr int kMaxStage = 4;
 
 struct FusedParams {
     int64_t nb;          // bins in this shard
@@ -51,6 +64,7 @@ struct FusedParams {
     int32_t n_tiles;     // ceil(nb / BT)
     int32_t evict_first; // use an L2 evict_first policy on the stack loads
     int32_t l2_prefetch; // tiles of look-ahead for cp.async.bulk.prefetch.tensor (0 = off)
+    int32_t panel;       // 1: the stack is stored as bin-major panels [tile][T][BT] and the tensor map is 3-D
     double eps;          // clamp (fitting_base.jl:90,277)
     const double *coeffs;   // [nt]
     const double *data;     // [nb] (converted to double at upload)
@@ -108,16 +122,19 @@ __device__ __forceinline__ void unpack<float>(const vec16 &v, double (&out)[4]) 
 // once, so shared memory is a pure streaming ring (every slot in flight) and the HBM stream is decoupled from
 // the A -> exchange -> B dependency.  Needs 4*KT more registers per lane => NW <= 12, one CTA per SM.
 template <typename S, int BT, int NW, bool WANT_G, bool RT>
-__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 && !RT) ? 2 : 1)
-sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+__global__ void __launch_bounds__((NW + kProducerWarps) * 32, (NW <= 8 && !RT) ? 2 : 1)
+sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one whole stage (G chunks) */,
+                    const __grid_constant__ CUtensorMap tmap_tail /* box = the tile's last, shorter stage */,
+                    const FusedParams p) {
     using Cfg = FusedCfg<S, BT, NW>;
     constexpr int VEC = Cfg::VEC, LPR = Cfg::LPR, RPW = Cfg::RPW, RPC = Cfg::RPC;
-    constexpr int kConsumerWarps = NW, kConsumerThreads = NW * 32, kFusedThreads = (NW + 1) * 32;
+    constexpr int kConsumerWarps = NW, kConsumerThreads = NW * 32, kFusedThreads = (NW + kProducerWarps) * 32;
     constexpr uint32_t kChunkBytes = chunk_bytes(NW);
     constexpr int KMAX = kmax_for(NW, RT);
     constexpr int G = stage_chunks_for(RT);
     constexpr int SMAX = KMAX / G;  // stages per tile at most
-    static_assert(KMAX % G == 0, "KMAX must be a multiple of the stage size");
+    static_assert(KMAX % G == 0 && G <= kMaxStage, "KMAX must be a multiple of the stage size");
+    constexpr bool kOneOp = (G * RPC <= 256);  // a whole stage fits one TMA box (box dimensions are limited to 256)
 
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t q = cluster_ctarank();
@@ -148,7 +165,10 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
         mbar_init(&xbar[1], 1);
         fence_mbar_init();
     }
-    if (warp == kConsumerWarps && lane == 0) prefetch_tensormap(&tmap);
+    if (warp == kConsumerWarps && lane == 0) {
+        prefetch_tensormap(&tmap_full);
+        prefetch_tensormap(&tmap_tail);
+    }
     // PDL: barrier set-up above overlaps the previous kernel; its outputs (coeffs) are read only below
     griddep_wait();
     for (int i = tid; i < kt * RPC; i += kFusedThreads) {
@@ -160,36 +180,48 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
     cluster_arrive();
     cluster_wait();
 
-    if (warp == kConsumerWarps) {
-        // ================= TMA producer (one elected lane) =================
+    if (warp >= kConsumerWarps) {
+        // ================= TMA producers: warp pw issues the stages gs = pw, pw + NP, pw + 2 NP, ... =================
         if (lane == 0) {
+            const int pw = warp - kConsumerWarps;
             const uint64_t pol = l2_policy_evict_first();
-            int ss = 0;
-            uint32_t round = 0;  // how many times the ring has wrapped
             const int32_t t0 = (int32_t)(q * (uint32_t)(kt * RPC));
             const int pf = p.l2_prefetch * (int)ncl;  // look-ahead in tiles of THIS cluster's sequence
-            for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl) {
-                for (int s = 0; s < nst; ++s) {
-                    const int cnt = (kt - s * G < G) ? (kt - s * G) : G;
-                    // pull the same chunks of a LATER tile into L2 now: not gated by a free shared-memory slot
-                    if (pf > 0 && tile + pf < p.n_tiles) {
-                        for (int u = 0; u < cnt; ++u) {
-                            const int32_t tcp = t0 + (s * G + u) * RPC;
-                            if (tcp < (int32_t)p.nt) tma_prefetch_l2_2d(&tmap, (tile + pf) * BT, tcp);
-                        }
-                    }
-                    if (round > 0) mbar_wait(&empty[ss], (round - 1) & 1u);
-                    mbar_arrive_expect_tx(&full[ss], (uint32_t)cnt * kChunkBytes);
-                    for (int u = 0; u < cnt; ++u) {
-                        void *dst = smem + L.ring_off + (uint32_t)(ss * G + u) * kChunkBytes;
-                        const int32_t tc = t0 + (s * G + u) * RPC;
+            const int my_tiles = (p.n_tiles > (int)cl) ? (p.n_tiles - (int)cl + (int)ncl - 1) / (int)ncl : 0;
+            // stages this CTA consumes, in order: (it, s) advanced incrementally -- a 64-bit div/mod per stage here
+            // costs the single issuing thread ~250 cycles and showed up as a 1.8x slowdown of the whole kernel
+            int ss = pw % NS;
+            uint32_t round = (uint32_t)(pw / NS);
+            int it = pw / nst, s = pw % nst;
+            for (; it < my_tiles;) {
+                const int tile = (int)cl + it * (int)ncl;
+                const int cnt = (kt - s * G < G) ? (kt - s * G) : G;
+                // (experiment knob) pull the same chunks of a LATER tile into L2: not gated by a free smem slot
+                // box of cnt*RPC templates: the whole stage in ONE op when it fits a TMA box, else one op per chunk
+                const int nops = kOneOp ? 1 : cnt;
+                // (two __grid_constant__ maps selected by a ternary: indexing an array of maps dynamically would make
+                //  nvcc copy it to local memory, and maps fetched from global memory halve the issue rate)
+                const CUtensorMap *tmap = (kOneOp && cnt != G) ? &tmap_tail : &tmap_full;
+                if (round > 0) mbar_wait(&empty[ss], (round - 1) & 1u);
+                mbar_arrive_expect_tx(&full[ss], (uint32_t)cnt * kChunkBytes);
+                for (int u = 0; u < nops; ++u) {
+                    const int32_t tc = t0 + (s * G + u) * RPC;
+                    void *dst = smem + L.ring_off + (uint32_t)(ss * G + u) * kChunkBytes;
+                    if (pf > 0 && tile + pf < p.n_tiles && tc < (int32_t)p.nt) tma_prefetch_l2_2d(tmap, (tile + pf) * BT, tc);
+                    if (p.panel) {
                         if (p.evict_first)
-                            tma_load_2d_hint(dst, &tmap, tile * BT, tc, &full[ss], pol);
+                            tma_load_3d_hint(dst, tmap, 0, tc, tile, &full[ss], pol);
                         else
-                            tma_load_2d(dst, &tmap, tile * BT, tc, &full[ss]);
-                    }
-                    if (++ss == NS) { ss = 0; ++round; }
+                            tma_load_3d(dst, tmap, 0, tc, tile, &full[ss]);
+                    } else if (p.evict_first)
+                        tma_load_2d_hint(dst, tmap, tile * BT, tc, &full[ss], pol);
+                    else
+                        tma_load_2d(dst, tmap, tile * BT, tc, &full[ss]);
                 }
+                ss += kProducerWarps;
+                if (ss >= NS) { ss -= NS; ++round; }
+                s += kProducerWarps;
+                while (s >= nst) { s -= nst; ++it; }
             }
         }
     } else {

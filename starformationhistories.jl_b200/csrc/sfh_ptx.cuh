@@ -73,6 +73,22 @@ __device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int32_t c0, int32_t c1, int32_t c2,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *smem_dst, const CUtensorMap *tmap, int32_t c0, int32_t c1, int32_t c2,
+                                                 uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 // L2 prefetch of a tensor box (no shared-memory destination, no barrier): decouples the HBM stream from the number
 // of free shared-memory slots -- the later cp.async.bulk.tensor load then hits L2 (~0.3 us) instead of DRAM (~1.5 us)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *tmap, int32_t c0, int32_t c1) {
