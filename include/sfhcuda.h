@@ -80,6 +80,8 @@ typedef struct sfh_info {
     int32_t fused;     /* 1 if the single-pass fused kernel is in use                  */
     int32_t tile_bins, cluster, chunks_per_tile, ring_slots, n_clusters, consumer_warps;
     int32_t sm_count, cc_major, cc_minor, register_tile;
+    int32_t panel_layout; /* 1: device copy stored as bin-major panels of tile_bins bins (host layout unchanged) */
+    int32_t reserved;
     int64_t stack_bytes; /* device bytes held by the stack (padded)                    */
     double clamp_eps;
 } sfh_info;

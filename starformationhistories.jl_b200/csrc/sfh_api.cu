@@ -137,7 +137,9 @@ struct sfh_stack {
     bool rt = false;  // register-resident tile variant
     uint32_t smem = 0;
     bool evict_first = false;
-    bool panel = false;  // EXPERIMENT (SFH_PANEL=1): interpret the buffer as bin-major panels (timing only)
+    bool panel = false;   // device layout: bin-major panels of `bt` bins (see StackLayout); SFH_PANEL=0 forces column-major
+    bool cfg_ok = false;  // choose_config found a fused tiling
+    StackLayout lay{};
     int l2_prefetch = 0;  // tiles of L2 look-ahead; measured SLOWER (209 -> 261 us at 1 tile), kept as an experiment knob
     CUtensorMap tmap_full, tmap_tail;  // TMA boxes: a whole pipeline stage / the tile's last (shorter) stage
     int sm_count = 0, cc_major = 0, cc_minor = 0;
@@ -339,12 +341,11 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     if (o && o->force_unfused) return SFH_OK;
     if (s->cc_major != 10) return SFH_OK;  // TMA/cluster path is written for sm_100a only
     if (s->rows <= 0 || s->nt <= 0) return SFH_OK;
-    if (!choose_config(s, o)) return SFH_OK;
+    if (!s->cfg_ok) return SFH_OK;  // (tiling chosen in stack_common_init: the device layout depends on it)
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     const TileGeom g = geom(s->dtype, s->bt, s->nw);
     CUresult r = CUDA_SUCCESS;
-    if (const char *e = getenv("SFH_PANEL")) s->panel = atoi(e) != 0;
     const CUtensorMapDataType tdt = s->dtype == SFH_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const int G = stage_chunks_for(s->rt);
     const bool one_op = g.rpc * G <= 256;              // a whole stage fits one TMA box (box dims <= 256)
@@ -382,7 +383,7 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     if (maxcl <= 0) return SFH_OK;  // cannot co-schedule this cluster shape: stay unfused
     s->n_clusters = std::min(maxcl, s->n_tiles);
     // the stack is streamed exactly once per evaluation: do not let it evict the O(Nb) vectors
-    s->evict_first = (size_t)s->ld * s->nt * elem_size(s->dtype) > s->l2_bytes;
+    s->evict_first = (size_t)s->lay.alloc_elems() * elem_size(s->dtype) > s->l2_bytes;
     if (const char *e = getenv("SFH_L2_PREFETCH")) s->l2_prefetch = atoi(e);
     s->fused = true;
     return SFH_OK;
@@ -428,6 +429,42 @@ int upload_data(sfh_stack *s, const void *data, int data_dtype, int64_t row_begi
     return SFH_OK;
 }
 
+// host column-major (leading dimension host_ld rows) <-> device layout, in column blocks through a bounded staging
+// buffer, so even a 40 GB stack needs only 256 MB extra while it is re-tiled into panels
+int transfer_stack(const sfh_stack *s, void *host, int64_t host_ld, bool to_device) {
+    const size_t es = elem_size(s->dtype);
+    if (!s->panel) {
+        const cudaError_t e = to_device
+            ? cudaMemcpy2D(s->dM, (size_t)s->ld * es, (const char *)host + (size_t)s->row_begin * es, (size_t)host_ld * es,
+                           (size_t)s->rows * es, (size_t)s->nt, cudaMemcpyHostToDevice)
+            : cudaMemcpy2D(host, (size_t)host_ld * es, s->dM, (size_t)s->ld * es, (size_t)s->rows * es, (size_t)s->nt,
+                           cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return fail(SFH_ERR_CUDA, "stack transfer failed: %s", cudaGetErrorString(e));
+        return SFH_OK;
+    }
+    const int64_t jb = std::max<int64_t>(1, std::min<int64_t>(s->nt, ((int64_t)256 << 20) / std::max<int64_t>((int64_t)(s->rows * es), 1)));
+    void *blk = nullptr;
+    CU_TRY(cudaMalloc(&blk, (size_t)s->rows * jb * es));
+    cudaError_t e = cudaSuccess;
+    const int grid = std::max(s->sm_count, 1) * 8;
+    for (int64_t j0 = 0; j0 < s->nt && e == cudaSuccess; j0 += jb) {
+        const int64_t nc = std::min(jb, s->nt - j0);
+        char *hp = (char *)host + ((size_t)j0 * host_ld + (to_device ? (size_t)s->row_begin : 0)) * es;
+        if (to_device) e = cudaMemcpy2D(blk, (size_t)s->rows * es, hp, (size_t)host_ld * es, (size_t)s->rows * es, (size_t)nc, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        if (s->dtype == SFH_F64)
+            sfh_relayout_kernel<double><<<grid, 256>>>((double *)s->dM, s->lay, (double *)blk, s->rows, j0, nc, to_device ? 1 : 0);
+        else
+            sfh_relayout_kernel<float><<<grid, 256>>>((float *)s->dM, s->lay, (float *)blk, s->rows, j0, nc, to_device ? 1 : 0);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) break;
+        if (!to_device) e = cudaMemcpy2D(hp, (size_t)host_ld * es, blk, (size_t)s->rows * es, (size_t)s->rows * es, (size_t)nc, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(blk);
+    if (e != cudaSuccess) return fail(SFH_ERR_CUDA, "stack transfer failed: %s", cudaGetErrorString(e));
+    return SFH_OK;
+}
+
 int stack_common_init(sfh_stack *s, int64_t nbins, int64_t ntemplates, int dtype, const sfh_opts *opts) {
     if (nbins < 0 || ntemplates < 0) return fail(SFH_ERR_INVALID_ARG, "negative size");
     if (dtype != SFH_F32 && dtype != SFH_F64) return fail(SFH_ERR_INVALID_ARG, "stack dtype must be F32 or F64");
@@ -452,8 +489,21 @@ int stack_common_init(sfh_stack *s, int64_t nbins, int64_t ntemplates, int dtype
              : (dtype == SFH_F32 ? (double)std::numeric_limits<float>::epsilon()
                                  : std::numeric_limits<double>::epsilon());
     SFH_TRY(device_props(s));
-    const size_t bytes = (size_t)s->ld * (size_t)std::max<int64_t>(s->nt, 1) * elem_size(dtype);
+    // the fused tiling is chosen BEFORE allocation: the device layout (panel width) depends on it
+    s->cfg_ok = !(opts && opts->force_unfused) && s->cc_major == 10 && s->rows > 0 && s->nt > 0 && choose_config(s, opts);
+    s->panel = s->cfg_ok;
+    if (const char *e = getenv("SFH_PANEL")) s->panel = s->panel && atoi(e) != 0;
+    s->lay.nt = s->nt; s->lay.rows = s->rows; s->lay.panel = s->panel ? 1 : 0;
+    s->lay.bt_shift = 0;
+    if (s->panel) {
+        while ((1 << s->lay.bt_shift) < s->bt) ++s->lay.bt_shift;
+        s->lay.ld = (int64_t)s->n_tiles * s->bt;  // padded row count
+    } else {
+        s->lay.ld = s->ld;
+    }
+    const size_t bytes = (size_t)std::max<int64_t>(s->lay.alloc_elems(), 1) * elem_size(dtype);
     CU_TRY(cudaMalloc(&s->dM, bytes));
+    CU_TRY(cudaMemset(s->dM, 0, bytes));  // padding rows must read as zero
     CU_TRY(cudaMalloc((void **)&s->d_data, (size_t)s->ld * 8));
     CU_TRY(cudaMemset(s->d_data, 0, (size_t)s->ld * 8));
     return SFH_OK;
@@ -486,15 +536,7 @@ extern "C" int sfh_stack_create(sfh_stack **out, const void *models, int64_t nbi
     sfh_stack *s = new (std::nothrow) sfh_stack();
     if (!s) return fail(SFH_ERR_OOM, "host allocation failed");
     int st = stack_common_init(s, nbins, ntemplates, dtype, opts);
-    if (st == SFH_OK && s->rows > 0 && s->nt > 0) {
-        const size_t es = elem_size(dtype);
-        // zero the padding rows, then a strided copy of the row shard of the column-major host matrix
-        cudaError_t e = cudaMemset(s->dM, 0, (size_t)s->ld * s->nt * es);
-        if (e == cudaSuccess)
-            e = cudaMemcpy2D(s->dM, (size_t)s->ld * es, (const char *)models + (size_t)s->row_begin * es,
-                             (size_t)nbins * es, (size_t)s->rows * es, (size_t)s->nt, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) st = fail(SFH_ERR_CUDA, "stack upload failed: %s", cudaGetErrorString(e));
-    }
+    if (st == SFH_OK && s->rows > 0 && s->nt > 0) st = transfer_stack(s, const_cast<void *>(models), nbins, true);
     if (st == SFH_OK) st = upload_data(s, data, data_dtype, s->row_begin);
     if (st == SFH_OK) st = setup_fused(s, opts);
     if (st != SFH_OK) { sfh_stack_destroy(s); return st; }
@@ -525,10 +567,10 @@ extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
     if (!s || !info) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     memset(info, 0, sizeof *info);
     info->nbins_total = s->nb_total; info->ntemplates = s->nt; info->row_begin = s->row_begin; info->row_end = s->row_end;
-    info->ld = s->ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
+    info->ld = s->lay.ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
     info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
     info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->register_tile = s->rt ? 1 : 0; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
-    info->stack_bytes = (int64_t)((size_t)s->ld * s->nt * elem_size(s->dtype)); info->clamp_eps = s->eps;
+    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->clamp_eps = s->eps;
     return SFH_OK;
 }
 
@@ -536,9 +578,8 @@ extern "C" int sfh_stack_download(const sfh_stack *s, void *models_out, double *
     if (!s) return fail(SFH_ERR_INVALID_ARG, "NULL stack");
     CU_TRY(cudaSetDevice(s->device));
     const size_t es = elem_size(s->dtype);
-    if (models_out && s->rows > 0 && s->nt > 0)
-        CU_TRY(cudaMemcpy2D(models_out, (size_t)s->rows * es, s->dM, (size_t)s->ld * es, (size_t)s->rows * es,
-                            (size_t)s->nt, cudaMemcpyDeviceToHost));
+    (void)es;
+    if (models_out && s->rows > 0 && s->nt > 0) SFH_TRY(transfer_stack(s, models_out, s->rows, false));
     if (data_out && s->rows > 0) CU_TRY(cudaMemcpy(data_out, s->d_data, (size_t)s->rows * 8, cudaMemcpyDeviceToHost));
     return SFH_OK;
 }
@@ -676,9 +717,9 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         const unsigned gb = (unsigned)((s->rows + 127) / 128);
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
         if (s->dtype == SFH_F64)
-            sfh_composite_kernel<double><<<gb, 512, 0, c->stream>>>((const double *)s->dM, s->ld, s->rows, s->nt, d_coeffs, c->d_composite);
+            sfh_composite_kernel<double><<<gb, 512, 0, c->stream>>>((const double *)s->dM, s->lay, s->rows, s->nt, d_coeffs, c->d_composite);
         else
-            sfh_composite_kernel<float><<<gb, 512, 0, c->stream>>>((const float *)s->dM, s->ld, s->rows, s->nt, d_coeffs, c->d_composite);
+            sfh_composite_kernel<float><<<gb, 512, 0, c->stream>>>((const float *)s->dM, s->lay, s->rows, s->nt, d_coeffs, c->d_composite);
         CU_TRY(cudaGetLastError());
         c->stats.kernel_launches++;
         SFH_TRY(launch_finalize(c, c->d_composite, d_out, 0));
@@ -687,9 +728,9 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
             sfh_residual_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, c->stream>>>(c->d_residual, s->d_data, s->rows, s->eps);
             const unsigned gt = (unsigned)((s->nt + 7) / 8);
             if (s->dtype == SFH_F64)
-                sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->ld, s->rows, s->nt, c->d_residual, 1.0, d_out + 1);
+                sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->lay, s->rows, s->nt, c->d_residual, 1.0, d_out + 1);
             else
-                sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->ld, s->rows, s->nt, c->d_residual, 1.0, d_out + 1);
+                sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->lay, s->rows, s->nt, c->d_residual, 1.0, d_out + 1);
             CU_TRY(cudaGetLastError());
             c->stats.kernel_launches += 2;
         }
@@ -824,9 +865,9 @@ extern "C" int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, doubl
     if (s->nt > 0) {
         const unsigned gt = (unsigned)((s->nt + 7) / 8);
         if (s->dtype == SFH_F64)
-            sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->ld, s->rows, s->nt, c->d_residual, -1.0, c->d_out + 1);
+            sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->lay, s->rows, s->nt, c->d_residual, -1.0, c->d_out + 1);
         else
-            sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->ld, s->rows, s->nt, c->d_residual, -1.0, c->d_out + 1);
+            sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->lay, s->rows, s->nt, c->d_residual, -1.0, c->d_out + 1);
         CU_TRY(cudaGetLastError());
         c->stats.kernel_launches += 2;
         if (c->comm) {
@@ -1003,7 +1044,7 @@ int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_log
     CU_TRY(cudaGetLastError());
     const int64_t nbt = (s->rows + kBwBM - 1) / kBwBM, nwt = (W + kBwBN - 1) / kBwBN;
     BatchedParams bp{};
-    bp.nb = s->rows; bp.nt = s->nt; bp.W = W; bp.ld = s->ld; bp.wld = wld; bp.eps = s->eps; bp.Xt = c->d_Xt;
+    bp.nb = s->rows; bp.nt = s->nt; bp.W = W; bp.lay = s->lay; bp.wld = wld; bp.eps = s->eps; bp.Xt = c->d_Xt;
     bp.data = s->d_data; bp.part = c->d_part;
     if (nbt > 0) {
         static const bool use_fma = [] { const char *e = getenv("SFH_BATCHED_IMPL"); return e && !strcmp(e, "fma"); }();
@@ -1101,13 +1142,12 @@ extern "C" int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_
     auto done = [&](int code) { if (code != SFH_OK) sfh_stack_destroy(s); else *out = s; return code; };
     if (st != SFH_OK) return done(st);
     if (s->rows > 0 && s->nt > 0) {
-        cudaError_t e = cudaMemset(s->dM, 0, (size_t)s->ld * s->nt * elem_size(dtype));
-        if (e != cudaSuccess) return done(fail(SFH_ERR_CUDA, "memset: %s", cudaGetErrorString(e)));
+        cudaError_t e = cudaSuccess;
         const int grid = s->sm_count * 16;
         if (dtype == SFH_F64)
-            sfh_fill_uniform_kernel<double><<<grid, 256>>>((double *)s->dM, s->ld, s->rows, s->nt, s->row_begin, nbins, seed, scale);
+            sfh_fill_uniform_kernel<double><<<grid, 256>>>((double *)s->dM, s->lay, s->rows, s->nt, s->row_begin, nbins, seed, scale);
         else
-            sfh_fill_uniform_kernel<float><<<grid, 256>>>((float *)s->dM, s->ld, s->rows, s->nt, s->row_begin, nbins, seed, scale);
+            sfh_fill_uniform_kernel<float><<<grid, 256>>>((float *)s->dM, s->lay, s->rows, s->nt, s->row_begin, nbins, seed, scale);
         e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return done(fail(SFH_ERR_CUDA, "fill: %s", cudaGetErrorString(e)));
     }

@@ -39,7 +39,8 @@ __global__ void sfh_walker_prep_kernel(const double *__restrict__ X, int64_t nt,
 }
 
 struct BatchedParams {
-    int64_t nb, nt, W, ld, wld;
+    int64_t nb, nt, W, wld;
+    StackLayout lay;
     double eps;
     const double *Xt;    // [nt][wld]
     const double *data;  // [nb]
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kBwThreads) sfh_batched_logl_kernel(const S *_
         for (int u = 0; u < 4; ++u) {
             const int64_t k = k0 + a_k + 2 * u;
             const int64_t i = i0 + a_i;
-            ra[u] = (k < p.nt && i < p.nb) ? (double)M[i + k * p.ld] : 0.0;
+            ra[u] = (k < p.nt && i < p.nb) ? (double)M[p.lay.off(i, k)] : 0.0;
             const int64_t w = w0 + a_i;
             rb[u] = (k < p.nt && w < p.W) ? p.Xt[k * p.wld + w] : 0.0;
         }
@@ -193,8 +194,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(co
         for (int v = tid; v < kMmaBK * A_VEC_PER_ROW; v += kMmaThreads) {
             const int kk = v / A_VEC_PER_ROW, iv = (v % A_VEC_PER_ROW) * EPV;
             const int64_t k = k0 + kk, i = i0 + iv;
-            const bool ok = (slab < nslab) && (k < p.nt) && (i < p.ld);   // rows in [nb, ld) are zero padding
-            cp_async16(As + ((size_t)stage * kMmaBK + kk) * kMmaLdA + iv, M + (ok ? i + k * p.ld : 0), ok);
+            // rows in [nb, padded) are zero padding; a 16-byte piece never straddles a panel (bt*sizeof(S) >= 64)
+            const bool ok = (slab < nslab) && (k < p.nt) && (i < p.lay.ld);
+            cp_async16(As + ((size_t)stage * kMmaBK + kk) * kMmaLdA + iv, M + (ok ? p.lay.off(i, k) : 0), ok);
         }
         constexpr int B_VEC_PER_ROW = kMmaBN / 2;
         for (int v = tid; v < kMmaBK * B_VEC_PER_ROW; v += kMmaThreads) {

@@ -9,6 +9,26 @@
 namespace sfh {
 
 // ------------------------------------------------------------------------------------------
+// Device layout of the template stack.  The HOST-visible layout is always stack_models' column-major Nb x T
+// (src/fitting/utilities.jl:12-13); on the device the fused path stores it as BIN-MAJOR PANELS of `bt` bins:
+//     element (i, j)  ->  ((i / bt) * nt + j) * bt + (i % bt)
+// so that everything one cluster needs for a bin tile is ONE contiguous nt*bt block (sequential DRAM pages, one
+// TLB entry per tile instead of one per template: 2.2x on the 40 GB stack, +7 % at config 3 -- SURVEY.md section 7
+// option (c)).  panel == 0 keeps plain column-major with leading dimension ld (two-pass / non-sm_100 path).
+// ------------------------------------------------------------------------------------------
+struct StackLayout {
+    int64_t ld, nt, rows;
+    int32_t bt_shift, panel;
+    __host__ __device__ __forceinline__ int64_t off(int64_t i, int64_t j) const {
+        return panel ? ((((i >> bt_shift) * nt + j) << bt_shift) + (i & ((1 << bt_shift) - 1))) : (i + j * ld);
+    }
+    __host__ __device__ __forceinline__ int64_t alloc_elems() const {
+        const int64_t bt = (int64_t)1 << bt_shift;
+        return panel ? ((rows + bt - 1) >> bt_shift) * nt * bt : ld * nt;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // deterministic block reduction (fixed shuffle tree + fixed smem order)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -110,7 +130,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
 // ------------------------------------------------------------------------------------------
 // composite!  C = M * coeffs   (fitting_base.jl:55-65): block = 128 bins x 4 template slices
 template <typename S>
-__global__ void __launch_bounds__(512) sfh_composite_kernel(const S *__restrict__ M, int64_t ld, int64_t nb, int64_t nt,
+__global__ void __launch_bounds__(512) sfh_composite_kernel(const S *__restrict__ M, const StackLayout lay, int64_t nb, int64_t nt,
                                                             const double *__restrict__ coeffs,
                                                             double *__restrict__ out) {
     __shared__ double sh[4][128];
@@ -120,17 +140,18 @@ __global__ void __launch_bounds__(512) sfh_composite_kernel(const S *__restrict_
     if (i < nb) {
         const int64_t per = (nt + 3) / 4;
         const int64_t j0 = sy * per, j1 = (j0 + per < nt) ? j0 + per : nt;
-        const S *col = M + i + j0 * ld;
+        const int64_t cstride = lay.off(i, 1) - lay.off(i, 0);  // template-to-template stride (ld, or bt for panels)
+        const S *col = M + lay.off(i, j0);
         int64_t j = j0;
         for (; j + 7 < j1; j += 8) {
             double v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (double)col[(int64_t)u * ld];
+            for (int u = 0; u < 8; ++u) v[u] = (double)col[(int64_t)u * cstride];
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc = fma(v[u], coeffs[j + u], acc);
-            col += 8 * ld;
+            col += 8 * cstride;
         }
-        for (; j < j1; ++j, col += ld) acc = fma((double)*col, coeffs[j], acc);
+        for (; j < j1; ++j, col += cstride) acc = fma((double)*col, coeffs[j], acc);
     }
     sh[sy][bx] = acc;
     __syncthreads();
@@ -149,23 +170,23 @@ __global__ void sfh_residual_kernel(double *__restrict__ C, const double *__rest
 
 // G_j = sign * sum_i M_ij r_i   (gemv 'T', fitting_base.jl:283): one warp per template
 template <typename S>
-__global__ void __launch_bounds__(256) sfh_gemvt_kernel(const S *__restrict__ M, int64_t ld, int64_t nb, int64_t nt,
+__global__ void __launch_bounds__(256) sfh_gemvt_kernel(const S *__restrict__ M, const StackLayout lay, int64_t nb, int64_t nt,
                                                         const double *__restrict__ r, double sign,
                                                         double *__restrict__ G) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= nt) return;
-    const S *col = M + j * ld;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int64_t i = lane;
     for (; i + 96 < nb; i += 128) {
-        const double v0 = (double)col[i], v1 = (double)col[i + 32], v2 = (double)col[i + 64], v3 = (double)col[i + 96];
+        const double v0 = (double)M[lay.off(i, j)], v1 = (double)M[lay.off(i + 32, j)], v2 = (double)M[lay.off(i + 64, j)],
+                     v3 = (double)M[lay.off(i + 96, j)];
         a0 = fma(v0, r[i], a0);
         a1 = fma(v1, r[i + 32], a1);
         a2 = fma(v2, r[i + 64], a2);
         a3 = fma(v3, r[i + 96], a3);
     }
-    for (; i < nb; i += 32) a0 = fma((double)col[i], r[i], a0);
+    for (; i < nb; i += 32) a0 = fma((double)M[lay.off(i, j)], r[i], a0);
     const double s = warp_sum((a0 + a1) + (a2 + a3));
     if (lane == 0) G[j] = sign * s;
 }
@@ -380,13 +401,13 @@ __device__ __forceinline__ double philox_u01(uint64_t idx, uint64_t seed, uint32
 }
 
 template <typename S>
-__global__ void sfh_fill_uniform_kernel(S *M, int64_t ld, int64_t rows, int64_t nt, int64_t row_begin,
+__global__ void sfh_fill_uniform_kernel(S *M, const StackLayout lay, int64_t rows, int64_t nt, int64_t row_begin,
                                         int64_t nbins_total, uint64_t seed, double scale) {
     const int64_t n = rows * nt;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = e % rows, j = e / rows;
         const uint64_t gidx = (uint64_t)(row_begin + i) + (uint64_t)nbins_total * (uint64_t)j;
-        M[i + j * ld] = (S)(scale * philox_u01(gidx, seed, 0u));
+        M[lay.off(i, j)] = (S)(scale * philox_u01(gidx, seed, 0u));
     }
 }
 
@@ -424,6 +445,18 @@ __global__ void sfh_poisson_kernel(const double *lam, double *out, int64_t rows,
         }
     }
     out[i] = k;
+}
+
+// column-major block (rows x ncols, leading dimension rows, columns j0..j0+ncols) <-> the stack's device layout
+template <typename S>
+__global__ void sfh_relayout_kernel(S *stack, const StackLayout lay, S *colblk, int64_t rows, int64_t j0, int64_t ncols,
+                                    int to_stack) {
+    const int64_t n = rows * ncols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % rows, jj = e / rows;
+        if (to_stack) stack[lay.off(i, j0 + jj)] = colblk[e];
+        else colblk[e] = stack[lay.off(i, j0 + jj)];
+    }
 }
 
 // data conversion on upload (Int64 / Float32 -> double)
