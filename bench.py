@@ -129,7 +129,7 @@ def time_cpu(M, data, x, budget_s=12.0, min_steps=3, max_steps=200):
     return float(np.median(ts)), len(ts), O.num_threads()
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     """--impl reference: the reference's algorithm (two-pass gemv 'N' / Poisson / residual / gemv 'T') on the host
     cores.  Julia cannot run in this image, so this is the oracle PORT (cpu_baseline.kind = "port")."""
     rank = int(os.environ.get("RANK", "0"))
@@ -155,11 +155,21 @@ def run_reference(args):
                              "sample": f"{args.steps} full evaluations of the 60000x2400 F64 stack (OpenMP two-pass port of "
                                        f"fitting_base.jl:55-65,84-96,265-285; julia not installed)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=real_stdout, flush=True)
     return 0
 
 
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there) must not break it:
+    fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    real_stdout = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -172,7 +182,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -309,7 +319,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
