@@ -210,12 +210,8 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = ds.new_ctx(stream.cuda_stream)
     if world > 1:
-        idbuf = (C.c_char * 128)()
-        if rank == 0:
-            L.check(L.lib.sfh_comm_unique_id(idbuf))
-        obj = [bytes(idbuf)]
-        dist.broadcast_object_list(obj, src=0)
-        L.check(L.lib.sfh_comm_init(ctx.handle, world, rank, obj[0]))
+        # NCCL communicator for the library + (unless SFH_NO_P2P=1) the fused one-shot NVLink all-reduce
+        S.init_library_comm(ctx)
 
     x = x_true * 1.02
     d_x = torch.tensor(x, dtype=torch.float64, device="cuda")
@@ -310,7 +306,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_stack_bytes": int(info.stack_bytes),
                        "l2": "inputs (1.15 GB/GPU) larger than L2 (126 MB); no flush needed",
-                       "sharding": "bin rows, one 60000-bin shard per GPU; NCCL allreduce of [logL,G] (2401 f64) per step" if world > 1 else "single GPU",
+                       "sharding": ("bin rows, one 60000-bin shard per GPU; [logL,G] (2401 f64) all-reduced every step: "
+                                    + ("NCCL" if os.environ.get("SFH_NO_P2P") == "1" else "one-shot NVLink peer-memory reduce fused into the finalize kernel")) if world > 1 else "single GPU",
                        "value_unit_note": "N>1: value = N shard-evaluations per all-reduced step / time (weak scaling)",
                        "tile_bins": info.tile_bins, "cluster": info.cluster, "chunks_per_tile": info.chunks_per_tile,
                        "ring_slots": info.ring_slots, "n_clusters": info.n_clusters, "consumer_warps": info.consumer_warps},

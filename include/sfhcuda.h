@@ -166,6 +166,12 @@ int sfh_comm_unique_id(void *id128);
 /* After this, every evaluation all-reduces [logL, G_1..G_T] (sum, FP64) over the ranks on the
  * context stream before results are returned, so each rank receives the full-stack answer.     */
 int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128);
+/* Optional upgrade of the fused path's reduction to a ONE-SHOT all-reduce over NVLink peer memory, fused into the
+ * finalize kernel (no NCCL call on the critical path).  Each rank obtains the 64-byte CUDA-IPC handle of its inbox,
+ * the host runtime all-gathers them (nranks x 64 bytes, rank order), every rank calls sfh_comm_p2p_init.  Requires
+ * sfh_comm_init first (NCCL remains the fallback for the two-pass and batched-walker paths).                    */
+int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out);
+int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *handles);
 
 /* ---- device-side plumbing (no host round trip; used by bench.py and torch interop) ---------- */
 /* Enqueue one fused evaluation on the ctx stream.  d_coeffs: device, ntemplates doubles.

@@ -75,6 +75,8 @@ PROTOTYPES = {
     "sfh_eval_logl_batched": (_int, [_vp, _dp, _i64, _dp]),
     "sfh_comm_unique_id": (_int, [_vp]),
     "sfh_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "sfh_comm_p2p_handle": (_int, [_vp, _int, _vp]),
+    "sfh_comm_p2p_init": (_int, [_vp, _int, _int, _vp]),
     "sfh_enqueue_fg": (_int, [_vp, _vp, _vp, _int]),
     "sfh_enqueue_logl_batched": (_int, [_vp, _vp, _i64, _vp]),
     "sfh_ctx_synchronize": (_int, [_vp]),

@@ -170,6 +170,13 @@ struct sfh_ctx {
     // multi-GPU
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
+    // one-shot NVLink all-reduce (peer memory)
+    double *d_inbox = nullptr;           // mine: [2][nranks][vlen] doubles + [2][nranks] u64 flags
+    double **d_peers = nullptr;          // device array of nranks inbox pointers (own + IPC-opened)
+    std::vector<void *> ipc_opened;
+    int64_t p2p_vlen = 0;
+    unsigned long long p2p_epoch = 0;
+    bool p2p = false;
     // timing / stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     float4 *d_flush = nullptr;
@@ -639,6 +646,8 @@ extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
     if (c->s) cudaSetDevice(c->s->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(c->d_inbox); cudaFree(c->d_peers);
     for (auto *g : {&c->g_fg[0], &c->g_fg[1], &c->g_hier})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     cudaFree(c->d_coeffs); cudaFree(c->d_out); cudaFree(c->d_composite); cudaFree(c->d_residual);
@@ -673,12 +682,17 @@ extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
 // evaluation plumbing (device side)
 // ---------------------------------------------------------------------------------------------
 namespace {
-int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce, double *out_host = nullptr) {
+int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce, double *out_host = nullptr,
+                    bool p2p_push = false) {
     const sfh_stack *s = c->s;
     FinalizeParams fp{};
     fp.nb = s->rows; fp.nt = s->nt; fp.gstride = c->gstride; fp.n_clusters = s->n_clusters; fp.want_G = want_G_reduce;
     fp.eps = s->eps; fp.composite = composite; fp.data = s->d_data; fp.gpart = c->d_gpart; fp.out = d_out;
     fp.out_host = out_host; fp.lpart = c->d_lpart; fp.ticket = c->d_ticket;
+    if (p2p_push) {
+        fp.peers = c->d_peers; fp.nranks = c->nranks; fp.rank = c->rank; fp.vlen = c->p2p_vlen;
+        fp.npush = want_G_reduce ? 1 + s->nt : 1; fp.epoch = c->p2p_epoch;
+    }
     // enough blocks that every thread has <= 1 bin and every warp <= 1 template (latency-bound kernel)
     const int64_t cap = 4 * std::max(s->sm_count, 1);
     const int64_t nblk_l = std::min<int64_t>(std::max<int64_t>((s->rows + kFinalizeThreads - 1) / kFinalizeThreads, 1), cap);
@@ -694,6 +708,7 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
 int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G, bool time_kernel,
                     double *out_host = nullptr) {
     sfh_stack *s = c->s;
+    bool fused_p2p = false;
     if (s->rows == 0 || s->nt == 0) {
         CU_TRY(cudaMemsetAsync(d_out, 0, (1 + std::max<int64_t>(s->nt, 0)) * 8, c->stream));
         return SFH_OK;
@@ -710,7 +725,15 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
 #undef LAUNCH
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
         c->stats.kernel_launches++;
-        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, c->comm ? nullptr : out_host));
+        fused_p2p = c->p2p;
+        if (fused_p2p) ++c->p2p_epoch;
+        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, c->comm ? nullptr : out_host, fused_p2p));
+        if (fused_p2p) {
+            const int64_t n = want_G ? 1 + s->nt : 1;
+            CU_TRY(launch_pdl(sfh_p2p_combine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c->stream,
+                              (const double *)c->d_inbox, c->nranks, c->p2p_vlen, n, c->p2p_epoch, d_out));
+            c->stats.kernel_launches++;
+        }
     } else {
         out_host = nullptr;  // the two-pass path writes G with gemv 'T': results are copied back explicitly
         // two-pass path: gemv 'N' -> logL -> residual -> gemv 'T'  (the reference's own pass structure)
@@ -736,7 +759,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         }
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
     }
-    if (c->comm) {
+    if (c->comm && !fused_p2p) {
         const size_t cnt = want_G ? (size_t)(1 + s->nt) : 1;
         int r = g_nccl.AllReduce(d_out, d_out, cnt, kNcclFloat64, kNcclSum, c->comm, c->stream);
         if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -1126,6 +1149,51 @@ extern "C" int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128
     }
     c->nranks = nranks;
     c->rank = rank;
+    return SFH_OK;
+}
+
+// One-shot all-reduce over NVLink peer memory (K7 v2).  Each rank exposes an "inbox" through CUDA IPC; the finalize
+// kernel's tail stores this shard's [logL, G] into every rank's inbox and a combine kernel sums them in rank order.
+extern "C" int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out) {
+    if (!c || !handle64_out || nranks < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(c->s->device));
+    if (!c->d_inbox) {
+        c->p2p_vlen = round_up(1 + std::max<int64_t>(c->s->nt, 1), 2);
+        const size_t bytes = (size_t)2 * nranks * c->p2p_vlen * 8 + (size_t)2 * nranks * 8;
+        CU_TRY(cudaMalloc((void **)&c->d_inbox, bytes));
+        CU_TRY(cudaMemset(c->d_inbox, 0, bytes));
+        CU_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, c->d_inbox));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(handle64_out, &h, 64);
+    return SFH_OK;
+}
+
+extern "C" int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *handles) {
+    if (!c || !handles || nranks < 1 || rank < 0 || rank >= nranks) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (!c->d_inbox) return fail(SFH_ERR_INVALID_ARG, "call sfh_comm_p2p_handle first");
+    if (nranks > 32) return fail(SFH_ERR_UNSUPPORTED, "too many ranks for the one-shot reduce");
+    CU_TRY(cudaSetDevice(c->s->device));
+    std::vector<double *> peers((size_t)nranks, nullptr);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { peers[(size_t)r] = c->d_inbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * 64, 64);
+        void *q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(SFH_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        c->ipc_opened.push_back(q);
+        peers[(size_t)r] = (double *)q;
+    }
+    CU_TRY(cudaMalloc((void **)&c->d_peers, (size_t)nranks * sizeof(double *)));
+    CU_TRY(cudaMemcpy(c->d_peers, peers.data(), (size_t)nranks * sizeof(double *), cudaMemcpyHostToDevice));
+    c->nranks = nranks; c->rank = rank; c->p2p_epoch = 0;
+    c->p2p = true;
     return SFH_OK;
 }
 

@@ -72,7 +72,22 @@ struct FinalizeParams {
     double *out_host;  // nullable: mapped pinned host copy of the same (saves the D2H memcpy of the sync API)
     double *lpart;     // [gridDim.x] per-block logL partials
     unsigned int *ticket;
+    // K7 v2: one-shot all-reduce over NVLink peer memory, fused into this kernel's tail (nullptr = off).
+    // peers[r] = rank r's inbox, laid out [2 parities][nranks][vlen] doubles then [2][nranks] uint64 epoch flags.
+    double *const *peers;
+    int32_t nranks, rank;
+    int64_t vlen, npush;
+    unsigned long long epoch;
 };
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 constexpr int kFinalizeThreads = 256;
 
 // Everything here is latency, not bandwidth (60 k logs, ~1 MB of partials): the shape is chosen so that no thread
@@ -84,6 +99,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     __shared__ bool last;
     griddep_wait();  // PDL: launched while the fused kernel drains
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t par = (int64_t)(p.epoch & 1ull);
     // logL: fixed contiguous slice of bins per block, fixed trees => deterministic
     const int64_t per = (p.nb + p.nblk_logl - 1) / p.nblk_logl;
     const int64_t b0 = (int64_t)blockIdx.x * per;
@@ -105,9 +121,14 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
                 p.out[1 + j] = s;
                 if (p.out_host) p.out_host[1 + j] = s;
             }
+            // one-shot all-reduce, push half: every warp stores ITS gradient entry into slot [parity][rank] of every
+            // rank's inbox (plain NVLink stores, spread over the whole grid)
+            if (p.peers && lane < p.nranks)
+                p.peers[lane][(par * p.nranks + p.rank) * p.vlen + 1 + j] = s;
         }
     }
     // last block folds the per-block logL partials (parallel, fixed order)
+    if (p.peers) __threadfence_system();  // this block's peer stores are visible before its ticket is taken
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
@@ -122,6 +143,34 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
             if (p.out_host) p.out_host[0] = all;
             *p.ticket = 0u;  // re-arm for the next evaluation on this context
         }
+        if (p.peers && threadIdx.x < p.nranks) {
+            // every block fenced its gradient pushes before taking its ticket; this (last) block adds logL and then
+            // publishes the epoch with a system-scope release: compute and exchange are ONE kernel, no NCCL call
+            double *dst = p.peers[threadIdx.x] + (par * p.nranks + p.rank) * p.vlen;
+            dst[0] = all;  // block_sum leaves the total in every lane of warp 0 (nranks <= 32)
+            __threadfence_system();
+            unsigned long long *flags = reinterpret_cast<unsigned long long *>(p.peers[threadIdx.x] + 2 * p.nranks * p.vlen);
+            st_release_sys_u64(flags + par * p.nranks + p.rank, p.epoch);
+        }
+    }
+}
+
+// second half of the one-shot all-reduce: wait until every rank's epoch flag has arrived in MY inbox, then sum the
+// nranks vectors in rank order (identical order on every rank => bit-identical results everywhere, deterministic)
+__global__ void __launch_bounds__(256) sfh_p2p_combine_kernel(const double *inbox, int nranks, int64_t vlen, int64_t n,
+                                                              unsigned long long epoch, double *out) {
+    griddep_wait();
+    const int64_t par = (int64_t)(epoch & 1ull);
+    const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(inbox + 2 * nranks * vlen) + par * nranks;
+    if (threadIdx.x < nranks) {
+        while (ld_acquire_sys_u64(flags + threadIdx.x) != epoch) { }
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double s = 0.0;
+        for (int r = 0; r < nranks; ++r) s += __ldcg(inbox + (par * nranks + r) * vlen + i);
+        out[i] = s;
     }
 }
 

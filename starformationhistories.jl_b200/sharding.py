@@ -13,6 +13,7 @@ The second also runs on the `gloo` backend and is what the CPU tests cover (worl
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -63,7 +64,7 @@ def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0, group=None
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def init_library_comm(ctx, group=None):
+def init_library_comm(ctx, group=None, p2p=True):
     """Give `ctx` (a fitting._Ctx) an NCCL communicator spanning the torch process group, so that every
     evaluation on it returns the all-reduced full-stack answer."""
     import torch.distributed as dist
@@ -73,4 +74,27 @@ def init_library_comm(ctx, group=None):
         L.check(L.lib.sfh_comm_unique_id(idbuf))
     uid = broadcast_bytes(bytes(idbuf) if rank == 0 else None, 128, 0, group)
     L.check(L.lib.sfh_comm_init(ctx.handle, world, rank, uid))
+    if p2p and world > 1 and os.environ.get("SFH_NO_P2P") != "1":
+        try:
+            init_p2p(ctx, group)
+        except (L.SFHError, ValueError):
+            pass  # no peer access between these devices: the NCCL all-reduce stays in place
+    return ctx
+
+
+def init_p2p(ctx, group=None):
+    """Exchange the CUDA-IPC handles of the per-rank inboxes and switch the fused path to the one-shot NVLink
+    all-reduce that is fused into the finalize kernel (include/sfhcuda.h: sfh_comm_p2p_*)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    h = (C.c_char * 64)()
+    L.check(L.lib.sfh_comm_p2p_handle(ctx.handle, world, h))
+    mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        mine = mine.to(torch.device("cuda", torch.cuda.current_device()))
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+    L.check(L.lib.sfh_comm_p2p_init(ctx.handle, world, rank, blob))
     return ctx
