@@ -266,7 +266,8 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
             case 128: return SFH_DISPATCH_NW(float, 128, s, want_g, CALL); \
             case 64: return SFH_DISPATCH_NW(float, 64, s, want_g, CALL);   \
             case 32: return SFH_DISPATCH_NW(float, 32, s, want_g, CALL);   \
-            default: return SFH_DISPATCH_NW(float, 16, s, want_g, CALL);   \
+            case 16: return SFH_DISPATCH_NW(float, 16, s, want_g, CALL);   \
+            default: return SFH_DISPATCH_NW(float, 8, s, want_g, CALL);    \
             }                                                              \
         }                                                                  \
     }()
@@ -278,7 +279,7 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
 //     (NW = 8) hide it;
 //   * prefer larger bin tiles (longer contiguous TMA rows) when the above are equal.
 bool choose_config(sfh_stack *s, const sfh_opts *o) {
-    const int cands64[4] = {64, 32, 16, 8}, cands32[4] = {128, 64, 32, 16};
+    const int cands64[5] = {64, 32, 16, 8, 8}, cands32[5] = {128, 64, 32, 16, 8};
     const int *cands = (s->dtype == SFH_F64) ? cands64 : cands32;
     struct Variant { int nw; bool rt; int ctas_per_sm; };
     const Variant variants[4] = {{12, true, 1}, {8, true, 1}, {8, false, 2}, {16, false, 1}};
@@ -292,8 +293,9 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
         if (o && o->consumer_warps && o->consumer_warps != nw) continue;
         if (o && o->variant == 1 && v.rt) continue;   // 1 = shared-memory tile only
         if (o && o->variant == 2 && !v.rt) continue;  // 2 = register tile only
-        for (int ci = 0; ci < 4; ++ci) {
+        for (int ci = 0; ci < 5; ++ci) {
             const int bt = cands[ci];
+            if (ci == 4 && s->dtype == SFH_F64) continue;  // (f64 has four tile widths)
             if (o && o->tile_bins && o->tile_bins != bt) continue;
             const TileGeom g = geom(s->dtype, bt, nw);
             if (g.lpr < 1 || g.lpr > 32 || g.rpc > 256 || bt > nw * 32) continue;
@@ -326,7 +328,10 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
                 const double exposed = v.rt ? 2.5 : (v.ctas_per_sm == 2 ? 0.35 : 1.0);       // of the ~1 us exchange
                 const double eff = tile_us / (tile_us + exposed);
                 const size_t rowb = bt * elem_size(s->dtype);  // contiguous bytes per template row of a TMA box
-                const double rowlen = rowb >= 256 ? 1.0 : (rowb >= 128 ? 0.97 : 0.88);  // measured (r1_sweep_config3_*.txt)
+                // column-major rows shorter than 256 B cost DRAM efficiency (r1_sweep_config3_*.txt); the panel layout
+                // (always used by the fused path unless SFH_PANEL=0) makes every tile contiguous
+                static const bool colmajor = [] { const char *e = getenv("SFH_PANEL"); return e && atoi(e) == 0; }();
+                const double rowlen = !colmajor ? 1.0 : (rowb >= 256 ? 1.0 : (rowb >= 128 ? 0.97 : 0.88));
                 const double score = sm_frac * balance * eff * rowlen;
                 if (score > best_score || (forced && best_bt == 0)) {
                     best_score = score; best_bt = bt; best_c = c; best_kt = kt; best_nw = nw; best_ring = ring;

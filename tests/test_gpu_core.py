@@ -147,6 +147,25 @@ def test_fused_configs_agree(S, tile, cluster, nw, variant):
     assert_grad_close(G, Gq, gs)
 
 
+@pytest.mark.parametrize("nw,variant,tile,cluster", [(8, 1, 8, 2), (8, 1, 8, 4), (16, 1, 8, 1), (8, 1, 16, 4), (16, 1, 32, 2), (8, 1, 64, 8),
+                                                     (16, 1, 128, 4), (8, 2, 16, 2), (12, 2, 32, 4)])
+def test_fused_configs_f32(S, nw, variant, tile, cluster):
+    """Float32-stored stacks through every tile width (8 ... 128 bins) of the fused kernel."""
+    nb, nt = 2777, 701
+    M, x, data = make_flat_problem(nb, nt, seed=13, dtype=np.float32)
+    nlq, Gq, gs = O.fg_quad_f32(x, M, data)
+    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw, variant=variant)
+    i = ds.info()
+    if not i.fused:
+        pytest.skip("combination cannot hold T")
+    assert i.tile_bins == tile and i.cluster == cluster and i.panel_layout == 1
+    nl, G, _ = ds.eval_fg(x)
+    assert nl == pytest.approx(nlq, rel=RTOL_F32)
+    assert_grad_close(G, Gq, gs, rtol=RTOL_F32)
+    Md, dd = ds.download()                       # the panel re-tiling is invisible to the host
+    assert np.array_equal(Md, M) and np.array_equal(dd, data.astype(np.float64))
+
+
 def test_unfused_two_pass_agrees(S):
     M, x, data = make_flat_problem(5000, 301, seed=5)
     nlq, Gq, gs, _ = O.fg_quad(x, M, data)
