@@ -303,6 +303,7 @@ __device__ __forceinline__ void d_mh_eval(int kind, double alpha, double beta, c
 }
 
 constexpr int kHierThreads = 1024;
+constexpr int kHierSmemAges = 1024;  // per-age scratch staged in shared memory up to this many unique ages
 
 // calculate_coeffs: mzr.jl:50-79 / amr.jl:50-73
 __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const HierParams p) {
@@ -311,11 +312,20 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const H
     const int nj = p.nj;
     const double alpha = p.variables[nj], beta = p.variables[nj + 1], sigma = p.variables[nj + 2];
     if (p.kind == MH_POWERLAW_MZR) {
-        if (tid == 0) {  // cumsum(R[s])[invperm(s)]  mzr.jl:66 -- oldest first
+        // cumsum(R[s])[invperm(s)]  mzr.jl:66 -- oldest first.  The scan is serial; its operands are staged in shared
+        // memory first (a chain of dependent L2 round trips from one thread cost ~20 us at 60 ages)
+        __shared__ double sR[kHierSmemAges];
+        __shared__ int ssidx[kHierSmemAges];
+        const bool staged = nj <= kHierSmemAges;
+        if (staged) {
+            for (int j = tid; j < nj; j += kHierThreads) { sR[j] = p.variables[j]; ssidx[j] = p.sidx[j]; }
+            __syncthreads();
+        }
+        if (tid == 0) {
             double run = 0.0;
             for (int i = 0; i < nj; ++i) {
-                const int j = p.sidx[i];
-                run += p.variables[j];
+                const int j = staged ? ssidx[i] : p.sidx[i];
+                run += staged ? sR[j] : p.variables[j];
                 p.cum[j] = run;
             }
         }
@@ -401,26 +411,47 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const H
     }
     __syncthreads();
     double *G = p.out + 1;
-    for (int j = tid; j < nj; j += kHierThreads) G[j] = -same[j];
+    // serial tails (suffix scan over ages, parameter sums) run on shared-memory copies: see the prologue's note
+    __shared__ double s_dr[kHierSmemAges], s_G[kHierSmemAges];
+    __shared__ int s_sidx[kHierSmemAges];
+    __shared__ double s_par[3];
+    const bool staged = nj <= kHierSmemAges;
+    if (staged) {
+        for (int j = tid; j < nj; j += kHierThreads) { s_dr[j] = ksumdr[j]; s_G[j] = -same[j]; s_sidx[j] = p.sidx[j]; }
+    } else {
+        for (int j = tid; j < nj; j += kHierThreads) G[j] = -same[j];
+    }
+    // parameter gradients: fixed-order (strided + xor tree) block sums  (mzr.jl:196-198,201-208)
+    {
+        double ga = 0.0, gb = 0.0, gs = 0.0;
+        for (int j = tid; j < nj; j += kHierThreads) {
+            ga += psum[j] * p.gA[j];
+            gb += psum[j] * p.gB[j];
+            gs -= ssum[j];
+        }
+        __shared__ double shp[kHierThreads / 32];
+        const double ta = block_sum<kHierThreads>(ga, shp);
+        const double tb = block_sum<kHierThreads>(gb, shp);
+        const double ts = block_sum<kHierThreads>(gs, shp);
+        if (tid == 0) { s_par[0] = ta; s_par[1] = tb; s_par[2] = ts; }
+    }
     __syncthreads();
     if (tid == 0) {
         if (p.kind == MH_POWERLAW_MZR) {
             // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181
             double run = 0.0;
             for (int i = nj - 1; i >= 1; --i) {
-                run += ksumdr[p.sidx[i]];
-                G[p.sidx[i - 1]] -= run;
+                if (staged) { run += s_dr[s_sidx[i]]; s_G[s_sidx[i - 1]] -= run; }
+                else { run += ksumdr[p.sidx[i]]; G[p.sidx[i - 1]] -= run; }
             }
         }
-        double ga = 0.0, gb = 0.0, gs = 0.0;
-        for (int j = 0; j < nj; ++j) {  // mzr.jl:196-198,201-208 in the reference's age order
-            ga += psum[j] * p.gA[j];
-            gb += psum[j] * p.gB[j];
-            gs -= ssum[j];
-        }
-        G[nj] = p.free_mask[0] ? ga : 0.0;
-        G[nj + 1] = p.free_mask[1] ? gb : 0.0;
-        G[nj + 2] = p.free_mask[2] ? gs : 0.0;
+        G[nj] = p.free_mask[0] ? s_par[0] : 0.0;
+        G[nj + 1] = p.free_mask[1] ? s_par[1] : 0.0;
+        G[nj + 2] = p.free_mask[2] ? s_par[2] : 0.0;
+    }
+    __syncthreads();
+    if (staged) {
+        for (int j = tid; j < nj; j += kHierThreads) G[j] = s_G[j];
     }
     if (p.out_host) {  // G is complete only after thread 0's serial tail above
         __syncthreads();
