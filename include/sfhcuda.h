@@ -140,6 +140,10 @@ int sfh_loglikelihood_coeffs(sfh_ctx *c, const double *coeffs, double *logL);
  * composite (in/out, nbins) is overwritten with 1 - n/max(composite,eps); G = -M' * that.     */
 int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, double *G);
 
+/* colsum_j = sum_i M_ij (all ranks' shards when sharded).  Helper for the post-fit summaries that are composite-
+ * shaped products against the resident stack, e.g. mdf_amr(coeffs, logAge, MH, models)  src/fitting/mdf.jl:54-74. */
+int sfh_column_sums(sfh_ctx *c, double *colsums_out);
+
 /* ---- hierarchical path -------------------------------------------------------------------- */
 /* Precompute the age grouping of mzr.jl:131-140 / amr.jl:131 from value-equality of logAge
  * entries in first-appearance order.  *n_ages_out = length(unique(logAge)).                   */

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "sfh_loglikelihood": (_int, [_vp, _dp, _dp]),
     "sfh_loglikelihood_coeffs": (_int, [_vp, _dp, _dp]),
     "sfh_grad_loglikelihood": (_int, [_vp, _dp, _dp]),
+    "sfh_column_sums": (_int, [_vp, _dp]),
     "sfh_hier_bind": (_int, [_vp, _dp, _dp, C.POINTER(_i64)]),
     "sfh_calculate_coeffs": (_int, [_vp, _int, _dp, _int, _dp, _dp]),
     "sfh_eval_fg_hier": (_int, [_vp, _int, _dp, _int, _dp, _u8p, _dp, _dp]),

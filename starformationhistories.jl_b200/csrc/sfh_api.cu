@@ -910,6 +910,35 @@ extern "C" int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, doubl
     return SFH_OK;
 }
 
+// column sums of the stack: colsum_j = sum_i M_ij.  One-shot post-processing helper for the "next" rows of SURVEY.md
+// section 8f: mdf_amr(coeffs, logAge, MH, models) (src/fitting/mdf.jl:54-74) sums composite Hess diagrams per
+// metallicity, i.e. sum_j coeffs_j * colsum_j over the templates of that metallicity.
+extern "C" int sfh_column_sums(sfh_ctx *c, double *colsums_out) {
+    if (!c || !colsums_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    if (s->nt == 0) return SFH_OK;
+    if (s->rows > 0) {
+        sfh_fill_kernel<<<(unsigned)((s->rows + 255) / 256), 256, 0, c->stream>>>(c->d_residual, s->rows, 1.0);
+        CU_TRY(cudaGetLastError());
+    }
+    const unsigned gt = (unsigned)((s->nt + 7) / 8);
+    if (s->dtype == SFH_F64)
+        sfh_gemvt_kernel<double><<<gt, 256, 0, c->stream>>>((const double *)s->dM, s->lay, s->rows, s->nt, c->d_residual, 1.0, c->d_out + 1);
+    else
+        sfh_gemvt_kernel<float><<<gt, 256, 0, c->stream>>>((const float *)s->dM, s->lay, s->rows, s->nt, c->d_residual, 1.0, c->d_out + 1);
+    CU_TRY(cudaGetLastError());
+    c->stats.kernel_launches += 2;
+    if (c->comm) {
+        int r = g_nccl.AllReduce(c->d_out + 1, c->d_out + 1, (size_t)s->nt, kNcclFloat64, kNcclSum, c->comm, c->stream);
+        if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
+    }
+    CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out + 1, (size_t)s->nt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(colsums_out, c->h_out, (size_t)s->nt * 8);
+    return SFH_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // hierarchical path
 // ---------------------------------------------------------------------------------------------

@@ -207,6 +207,11 @@ __global__ void __launch_bounds__(512) sfh_composite_kernel(const S *__restrict_
     if (sy == 0 && i < nb) out[i] = (sh[0][bx] + sh[1][bx]) + (sh[2][bx] + sh[3][bx]);
 }
 
+__global__ void sfh_fill_kernel(double *x, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
 // residual in place: C <- 1 - n/max(C,eps)   (fitting_base.jl:274-280)
 __global__ void sfh_residual_kernel(double *__restrict__ C, const double *__restrict__ data, int64_t nb, double eps) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -203,6 +203,12 @@ class DeviceStack:
         L.check(L.lib.sfh_eval_logl_batched(self.ctx().handle, _dp(X), X.shape[1], _dp(out)))
         return out
 
+    def column_sums(self):
+        """colsum_j = sum_i M_ij of the resident stack (one device pass)."""
+        out = np.empty(self.shape[1])
+        L.check(L.lib.sfh_column_sums(self.ctx().handle, _dp(out)))
+        return out
+
     def time_fg(self, coeffs, reps=10, want_G=True, flush_l2=True):
         x = np.ascontiguousarray(coeffs, dtype=np.float64)
         ms, msk = C.c_double(), C.c_double()

@@ -243,6 +243,31 @@ def mcmc_sample(models, data, x0, nsteps, nburnin=0, nthin=1, a_scale=2.0, rng=N
 
 
 # ---------------------------------------------------------------------------------------------
+def mdf_amr(coeffs, logAge, metallicities, models=None):
+    """mdf_amr (src/fitting/mdf.jl:23-37 mass-weighted; :54-74 number-weighted with `models`).  Returns
+    (unique_MH sorted ascending, mdf).  With `models` (a DeviceStack) the per-metallicity composite sums
+    sum_i (M[:, idxs] * coeffs[idxs])_i are formed from the resident stack's column sums (one device pass)."""
+    coeffs = np.asarray(coeffs, dtype=np.float64)
+    mh = np.asarray(metallicities, dtype=np.float64)
+    if not (coeffs.shape[0] == np.asarray(logAge).shape[0] == mh.shape[0]):
+        raise ValueError("length(coeffs) == length(logAge) == length(metallicities) violated")     # mdf.jl:27 / :59
+    _, first = np.unique(mh, return_index=True)
+    umh = mh[np.sort(first)]                                                # unique() in first-appearance order
+    if models is None:
+        w = coeffs
+    else:
+        ds = device_stack(models, None)
+        if ds.shape[1] != coeffs.shape[0]:
+            raise ValueError("length(coeffs) != size(models, 2)")            # mdf.jl:59
+        w = coeffs * ds.column_sums()                                       # sum(mul!(composite, M[:,idxs], c[idxs]))  :68-69
+    mdf = np.array([w[mh == m].sum() for m in umh])
+    if models is None:
+        mdf = mdf / mdf.sum()                                               # :34 (only the mass-weighted form normalises)
+    p = np.argsort(umh, kind="stable")                                      # :35 / :71
+    return umh[p], mdf[p]
+
+
+# ---------------------------------------------------------------------------------------------
 def _leapfrog(lg, theta, r, grad, eps, inv_mass):
     r = r + 0.5 * eps * grad
     theta = theta + eps * inv_mass * r

@@ -319,3 +319,37 @@ def test_full_size_properties(S, nb, nt, dtype):
     b = S.DeviceStack.synthetic(nb, nt, dtype, seed=94823, scale=1.0, x_true=x, rows=(h, nb)).eval_fg(x1)
     assert a[0] + b[0] == pytest.approx(nl, rel=1e-12)
     assert np.allclose(a[1] + b[1], G, rtol=1e-9, atol=1e-6)
+
+
+def test_very_wide_stack_falls_back_to_two_pass(S):
+    """More templates than the fused tiling can hold (T > 16 CTAs x 20 chunks x 128 rows): the library must switch to
+    the two-pass kernels by itself and still match the oracle."""
+    nb, nt = 48, 50000
+    M, x, data = make_flat_problem(nb, nt, seed=21, scale=0.01)
+    ds = S.DeviceStack(M, data)
+    assert ds.info().fused == 0
+    nl, G, _ = ds.eval_fg(x)
+    nlq, Gq, gs, _ = O.fg_quad(x, M, data)
+    assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
+    assert_grad_close(G, Gq, gs)
+    # the widest stack the fused path still takes (16-CTA clusters)
+    M2, x2, d2 = make_flat_problem(40, 30000, seed=22, scale=0.01)
+    ds2 = S.DeviceStack(M2, d2)
+    assert ds2.info().fused == 1 and ds2.info().cluster == 16
+    nl2, G2, _ = ds2.eval_fg(x2)
+    nlq2, Gq2, gs2, _ = O.fg_quad(x2, M2, d2)
+    assert nl2 == pytest.approx(nlq2, rel=RTOL_LOGL)
+    assert_grad_close(G2, Gq2, gs2)
+
+
+def test_empty_stacks(S):
+    """Empty inputs: zero bins / zero templates (SURVEY section 8c edge cases).  An empty sum is exactly 0, which the
+    reference maps to -typemax (fitting_base.jl:95), i.e. fg! returns +Inf."""
+    ds = S.DeviceStack(np.zeros((0, 3)), np.zeros(0))
+    nl, G, _ = ds.eval_fg(np.ones(3))
+    assert nl == np.inf and np.array_equal(G, np.zeros(3))
+    ds = S.DeviceStack(np.zeros((5, 0)), np.arange(5.0))
+    nl, G, _ = ds.eval_fg(np.zeros(0))
+    assert G.shape == (0,)
+    assert nl == np.inf        # no templates: nothing is evaluated, the empty sum rule applies
+    assert S.MCMCModel(S.DeviceStack(np.ones((4, 2)), np.ones(4)), None).batch(np.zeros((2, 0))).shape == (0,)

@@ -132,3 +132,28 @@ def test_hmc_sample_shapes_and_moments(S, V):                    # basic_linear_
     ft = V.fit_templates(models, data, x0=np.ones(N))
     z = np.abs(out.mean(axis=(0, 2)) - ft["map"].mu) / ft["map"].sigma
     assert np.all(z < 1.0), z                                          # posterior mean within 1 sigma of the MAP
+
+
+def test_mdf_amr_and_renormalize_x0(S, V):                      # mdf.jl doctests :17-18, :49-51 ; utilities.jl:89-102
+    um, mdf = S.mdf_amr([1.0, 2.0, 1.0], [10, 10, 10], [-2, -1.5, -1])
+    assert np.array_equal(um, [-2.0, -1.5, -1.0]) and np.allclose(mdf, [0.25, 0.5, 0.25])
+    models = [np.full((100, 100), v) for v in (1.0, 2.0, 1.0)]
+    ds = S.DeviceStack(models, np.zeros((100, 100)))
+    um, mdf = S.mdf_amr([1.0, 2.0, 1.0], [10, 10, 10], [-2, -1.5, -1], ds)
+    assert np.array_equal(um, [-2.0, -1.5, -1.0]) and np.allclose(mdf, [10000.0, 40000.0, 10000.0], rtol=1e-13)
+    # unsorted, repeated metallicities on a random stack vs numpy
+    rng = np.random.default_rng(4)
+    M = np.asfortranarray(rng.random((777, 12))); c = rng.random(12); mh = np.tile([-1.0, -2.0, -0.5], 4)
+    ds2 = S.DeviceStack(M, np.zeros(777))
+    assert np.allclose(ds2.column_sums(), M.sum(axis=0), rtol=1e-13)
+    um, mdf = S.mdf_amr(c, np.repeat([9.0, 8.0, 7.0, 6.0], 3), mh, ds2)
+    assert np.array_equal(um, [-2.0, -1.0, -0.5])
+    assert np.allclose(mdf, [(M[:, mh == m] @ c[mh == m]).sum() for m in um], rtol=1e-12)
+    with pytest.raises(ValueError):
+        S.mdf_amr(c[:-1], np.zeros(12), mh, ds2)
+    # renormalize_x0 doctest (fitting/utilities.jl:89-102): total counts match after rescaling
+    models3 = [rng.random((5, 5)) for _ in range(3)]
+    true_x0 = np.array([1.0, 2.0, 3.0])
+    data = sum(x * m for x, m in zip(true_x0, models3))
+    x0r = S.renormalize_x0(data, models3, true_x0 * 0.5)
+    assert np.allclose(sum(x * m for x, m in zip(x0r, models3)).sum(), data.sum(), rtol=1e-12)
