@@ -1,0 +1,71 @@
+"""End-to-end runs of the five BASELINE.json configurations through the host drivers (sfh_b200.solvers), with the
+same driver running on the CPU oracle beside it where that finishes in bounded time.  Prints one JSON object per config."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sfh_b200 as S
+import oracle as O
+from scipy import optimize
+
+def out(**kw): print(json.dumps(kw), flush=True)
+
+# ---- config 1: fit_templates_lbfgsb, 100x100 bins, 100 random nonnegative F64 templates, Poisson data ---------------
+rng = np.random.Generator(np.random.Philox(58392))
+M = np.asfortranarray(rng.random((10000, 100))); x = 100 * rng.random(100); data = rng.poisson(M @ x).astype(np.float64)
+ds = S.DeviceStack(M, data)
+S.fit_templates_lbfgsb(ds, data, x0=np.ones(100))       # warm-up (graph capture etc.)
+t0 = time.perf_counter(); f_gpu, x_gpu = S.fit_templates_lbfgsb(ds, data, x0=np.ones(100)); t_gpu = time.perf_counter() - t0
+nfev = [0]
+def fg_cpu(z):
+    nfev[0] += 1
+    f, G, _ = O.fg(z, M, data); return float(f), G
+x0r = np.ones(100) * data.sum() / (M @ np.ones(100)).sum()
+t0 = time.perf_counter(); x_cpu, f_cpu, _ = optimize.fmin_l_bfgs_b(fg_cpu, x0r, bounds=[(0, None)] * 100, factr=1e-12, pgtol=1e-5, m=10, maxfun=100000, maxiter=100000); t_cpu = time.perf_counter() - t0
+out(config=1, what="fit_templates_lbfgsb 100x100 bins x 100 templates F64", gpu_s=t_gpu, cpu_oracle_1thread_s=t_cpu, fevals=nfev[0],
+    rel_diff_coeffs=float(np.linalg.norm(x_gpu - x_cpu) / np.linalg.norm(x_cpu)), rel_diff_nlogL=float(abs(f_gpu - f_cpu) / abs(f_cpu)),
+    rel_err_vs_truth=float(np.linalg.norm(x_gpu - x) / np.linalg.norm(x)))
+
+# ---- config 2: mcmc_sample ensemble, 1024 walkers, 200x200 bins x 500 templates F64 -----------------------------------
+rng = np.random.Generator(np.random.Philox(58393))
+x2 = 100 * rng.random(500)
+ds2 = S.DeviceStack.synthetic(40000, 500, np.float64, 58393, 1.0, x2)
+X0 = np.maximum(0.0, x2[:, None] + rng.standard_normal((500, 1024)))
+d2 = ds2.download_data()
+S.mcmc_sample(ds2, d2, X0, 2, rng=np.random.default_rng(1))
+nsteps = 20
+t0 = time.perf_counter(); chain, lps, acc = S.mcmc_sample(ds2, d2, X0, nsteps, rng=np.random.default_rng(1)); t_gpu = time.perf_counter() - t0
+M2, d2 = ds2.download()
+t0 = time.perf_counter(); O.mcmc_logl(X0[:, :64], M2, d2); t_cpu64 = time.perf_counter() - t0
+out(config=2, what="mcmc_sample 1024 walkers x %d steps, 200x200 bins x 500 templates F64" % nsteps, gpu_s=t_gpu,
+    gpu_walker_evals_per_s=1024 * nsteps / t_gpu, acceptance=acc,
+    cpu_oracle_walker_evals_per_s=64 / t_cpu64, cpu_threads=O.num_threads(), cpu_sample="64 walkers, threaded over walkers")
+del M2
+
+# ---- configs 3/4: fit_sfh PowerLawMZR + GaussianDispersion, 60 ages x 40 [M/H] = 2400 templates, 200x300 bins ------
+rng = np.random.Generator(np.random.Philox(94823))
+uA = np.linspace(10.1, 6.6, 60); uM = np.linspace(-2.5, 0.0, 40)
+la = np.repeat(uA, 40); mh = np.tile(uM, 60)
+R = rng.random(60) * 1e6
+mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
+xt = S.calculate_coeffs(mz, dp, R, la, mh)
+ds3 = S.DeviceStack.synthetic(60000, 2400, np.float64, 94823, 1e-5, xt)
+truth = np.concatenate([R, [1.0, -2.0, 0.2]])
+d3 = ds3.download_data()
+t0 = time.perf_counter()
+res = S.fit_sfh(S.PowerLawMZR(1.2, -2.2, 6.0), S.GaussianDispersion(0.25), ds3, d3, la, mh, x0=R * 1.5, g_abstol=1e-6)
+t_gpu = time.perf_counter() - t0
+z = np.abs(res["map"].mu - truth) / res["map"].sigma
+out(config=3, what="fit_sfh MZR (MAP+MLE BFGS), 200x300 bins x 2400 templates F64, Poisson data", gpu_s=t_gpu,
+    fevals_map=int(res["map"].result.nfev), fevals_mle=int(res["mle"].result.nfev),
+    frac_params_within_3sigma=float(np.mean(z < 3)), alpha_beta_sigma=[float(v) for v in res["mle"].mu[-3:]])
+# config 4: the HMC inner loop = sequential logdensity_and_gradient calls on the same stack
+opt = S.HierarchicalOptimizer(mz, dp, ds3, d3, la, mh, True, True, True)
+xv = np.concatenate([np.log(R), [0.0, -2.0, np.log(0.2)]])
+for _ in range(20): opt.logdensity_and_gradient(xv)
+t0 = time.perf_counter()
+for _ in range(500): opt.logdensity_and_gradient(xv)
+t_leap = (time.perf_counter() - t0) / 500
+Mh, dh = ds3.download()
+t0 = time.perf_counter(); O.fg_hier(O.POWERLAW_MZR, (6.0,), (1, 1, 1), truth, Mh, dh, la, mh); t_cpu = time.perf_counter() - t0
+out(config=4, what="HMC leapfrog = HierarchicalOptimizer.logdensity_and_gradient on the 2400-template MZR stack", gpu_us_per_eval=t_leap * 1e6,
+    gpu_evals_per_s=1 / t_leap, cpu_oracle_1thread_s_per_eval=t_cpu)

@@ -180,6 +180,13 @@ class DeviceStack:
         L.check(L.lib.sfh_stack_download(self.handle, M.ctypes.data_as(C.c_void_p), _dp(d)))
         return M, d
 
+    def download_data(self):
+        """The observed Hess diagram bound to this stack (float64), without copying the templates back."""
+        i = self.info()
+        d = np.empty(i.row_end - i.row_begin, dtype=np.float64)
+        L.check(L.lib.sfh_stack_download(self.handle, None, _dp(d)))
+        return d
+
     # -- raw calls (all host-synchronous) ----------------------------------------------------
     def eval_fg(self, coeffs, want_F=True, want_G=True, want_composite=False):
         x = np.ascontiguousarray(coeffs, dtype=np.float64)
