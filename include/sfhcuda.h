@@ -164,6 +164,11 @@ int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_k
  * loglikelihood(M*X[:,w], data).                                                               */
 int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL);
 
+/* fg! for C coefficient vectors at once (multi-chain HMC: hmc_sample.jl:123-141, generic_fitting.jl:617-626 run one
+ * chain per thread; here one device pass serves all chains).  X: ntemplates x C column-major; neg_logL[C];
+ * G: ntemplates x C column-major (nullable).  Per-vector semantics are exactly those of sfh_eval_fg.            */
+int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G);
+
 /* ---- multi-GPU: bin-row shards, one process per GPU -------------------- */
 /* 128-byte NCCL unique id (rank 0 creates, the host runtime broadcasts it).                    */
 int sfh_comm_unique_id(void *id128);

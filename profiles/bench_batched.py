@@ -44,3 +44,26 @@ if __name__ == "__main__":
     run(40000, 500, 512)
     run(40000, 500, 128)
     run(60000, 2400, 256)
+
+
+def run_fg_batched(nb, nt, Cs=(1, 8, 16, 32, 64), reps=5):
+    """sfh_eval_fg_batched (multi-chain fg): host-API time per call and per chain-evaluation, vs the single-vector path."""
+    rng = np.random.default_rng(3)
+    x = 100 * rng.random(nt)
+    ds = S.DeviceStack.synthetic(nb, nt, np.float64, seed=3, scale=1.0, x_true=x)
+    ds.eval_fg(x)
+    t0 = time.perf_counter()
+    for _ in range(20): ds.eval_fg(x)
+    t_single = (time.perf_counter() - t0) / 20
+    for C in Cs:
+        X = np.asfortranarray(x[:, None] * (1 + 0.05 * rng.standard_normal((nt, C))))
+        ds.eval_fg_batched(X)
+        t0 = time.perf_counter()
+        for _ in range(reps): ds.eval_fg_batched(X)
+        t = (time.perf_counter() - t0) / reps
+        print(json.dumps({"fg_batched": True, "nb": nb, "nt": nt, "C": C, "ms_per_call": t * 1e3, "us_per_chain_eval": t / C * 1e6,
+                          "single_vector_us_per_eval": t_single * 1e6, "fp64_tflops": 4.0 * nb * nt * C / t / 1e12}), flush=True)
+
+
+if __name__ == "__main__":
+    run_fg_batched(60000, 2400)

@@ -167,6 +167,10 @@ struct sfh_ctx {
     int64_t wcap = 0, wld = 0;
     double *d_X = nullptr, *d_Xt = nullptr, *d_part = nullptr, *d_logl = nullptr;
     int32_t *d_neg = nullptr;
+    // batched gradient (K6g)
+    double *d_resid = nullptr, *d_bgpart = nullptr, *d_bG = nullptr;
+    int64_t bg_cap = 0;
+    int bg_nsplit = 0;
     // multi-GPU
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
@@ -660,6 +664,7 @@ extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
     cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx);
     cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
+    cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG);
     cudaFree(c->d_flush);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -1093,7 +1098,8 @@ int ensure_walker_capacity(sfh_ctx *c, int64_t W) {
     return SFH_OK;
 }
 
-int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_logl) {
+int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_logl, double *d_resid = nullptr,
+                         bool apply_guard = true) {
     sfh_stack *s = c->s;
     const int64_t wld = c->wld;
     const unsigned gw = (unsigned)((W + 7) / 8);
@@ -1102,35 +1108,52 @@ int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_log
     const int64_t nbt = (s->rows + kBwBM - 1) / kBwBM, nwt = (W + kBwBN - 1) / kBwBN;
     BatchedParams bp{};
     bp.nb = s->rows; bp.nt = s->nt; bp.W = W; bp.lay = s->lay; bp.wld = wld; bp.eps = s->eps; bp.Xt = c->d_Xt;
-    bp.data = s->d_data; bp.part = c->d_part;
+    bp.data = s->d_data; bp.part = c->d_part; bp.resid = d_resid;
     if (nbt > 0) {
         static const bool use_fma = [] { const char *e = getenv("SFH_BATCHED_IMPL"); return e && !strcmp(e, "fma"); }();
-        if (use_fma) {  // v1 (FP64 FMA pipe) kept for A/B measurements
+        if (use_fma && !d_resid) {  // v1 (FP64 FMA pipe) kept for A/B measurements
             if (s->dtype == SFH_F64)
                 sfh_batched_logl_kernel<double><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const double *)s->dM, bp);
             else
                 sfh_batched_logl_kernel<float><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const float *)s->dM, bp);
-        } else if (s->dtype == SFH_F64) {
-            CU_TRY(cudaFuncSetAttribute(sfh_batched_logl_mma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)mma_smem_bytes<double>()));
-            sfh_batched_logl_mma_kernel<double><<<(unsigned)(nbt * nwt), kMmaThreads, mma_smem_bytes<double>(), c->stream>>>(
-                (const double *)s->dM, bp);
         } else {
-            CU_TRY(cudaFuncSetAttribute(sfh_batched_logl_mma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)mma_smem_bytes<float>()));
-            sfh_batched_logl_mma_kernel<float><<<(unsigned)(nbt * nwt), kMmaThreads, mma_smem_bytes<float>(), c->stream>>>(
-                (const float *)s->dM, bp);
+            // walker-tile width: 128 for ensembles, 8 / 16 / 32 / 64 for the few-chain batches of sfh_eval_fg_batched
+            const int bn = (W > 64) ? 128 : (W > 32 ? 64 : (W > 16 ? 32 : (W > 8 ? 16 : 8)));
+            const int64_t nwt_v = (W + bn - 1) / bn;
+            const unsigned grid = (unsigned)(nbt * nwt_v);
+#define SFH_LAUNCH_MMA(S_, WN_, NBW_)                                                                                  \
+    do {                                                                                                               \
+        CU_TRY(cudaFuncSetAttribute(sfh_batched_logl_mma_kernel<S_, WN_, NBW_>,                                        \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem_bytes<S_>(8 * NBW_ * WN_))); \
+        sfh_batched_logl_mma_kernel<S_, WN_, NBW_><<<grid, 128 * WN_, mma_smem_bytes<S_>(8 * NBW_ * WN_), c->stream>>>( \
+            (const S_ *)s->dM, bp);                                                                                    \
+    } while (0)
+#define SFH_LAUNCH_MMA_BN(S_)                                                                                          \
+    do {                                                                                                               \
+        switch (bn) {                                                                                                  \
+        case 128: SFH_LAUNCH_MMA(S_, 4, 4); break;                                                                     \
+        case 64: SFH_LAUNCH_MMA(S_, 2, 4); break;                                                                      \
+        case 32: SFH_LAUNCH_MMA(S_, 1, 4); break;                                                                      \
+        case 16: SFH_LAUNCH_MMA(S_, 1, 2); break;                                                                      \
+        default: SFH_LAUNCH_MMA(S_, 1, 1); break;                                                                      \
+        }                                                                                                              \
+    } while (0)
+            if (s->dtype == SFH_F64) SFH_LAUNCH_MMA_BN(double); else SFH_LAUNCH_MMA_BN(float);
+#undef SFH_LAUNCH_MMA_BN
+#undef SFH_LAUNCH_MMA
         }
         CU_TRY(cudaGetLastError());
     }
-    sfh_batched_reduce_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c->stream>>>(c->d_part, nbt, W, wld, d_logl);
+    sfh_batched_reduce_kernel<<<(unsigned)((W + 7) / 8), 256, 0, c->stream>>>(c->d_part, nbt, W, wld, d_logl);
     CU_TRY(cudaGetLastError());
     if (c->comm) {
         int r = g_nccl.AllReduce(d_logl, d_logl, (size_t)W, kNcclFloat64, kNcclSum, c->comm, c->stream);
         if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
     }
-    sfh_batched_guard_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c->stream>>>(d_logl, c->d_neg, W);
-    CU_TRY(cudaGetLastError());
+    if (apply_guard) {
+        sfh_batched_guard_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c->stream>>>(d_logl, c->d_neg, W);
+        CU_TRY(cudaGetLastError());
+    }
     c->stats.kernel_launches += 4;
     c->stats.evals += W;
     return SFH_OK;
@@ -1154,6 +1177,79 @@ extern "C" int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, dou
     SFH_TRY(enqueue_batched_impl(c, c->d_X, W, c->d_logl));
     CU_TRY(cudaMemcpyAsync(logL, c->d_logl, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    return SFH_OK;
+}
+
+// fg! for C coefficient vectors in one device pass (multi-chain HMC / many short chains): -logL_c and
+// G[:, c] = M'(1 - n/m_c) with exactly the per-vector semantics of sfh_eval_fg.
+namespace {
+template <int NB>
+cudaError_t launch_bgrad(const sfh_stack *s, const BGradParams &gp, dim3 grid, cudaStream_t st) {
+    if (s->dtype == SFH_F64) {
+        const size_t smem = bgrad_smem_bytes<double>(NB * 8);
+        cudaError_t e = cudaFuncSetAttribute(sfh_bgrad_mma_kernel<double, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sfh_bgrad_mma_kernel<double, NB><<<grid, kBgThreads, smem, st>>>((const double *)s->dM, gp);
+    } else {
+        const size_t smem = bgrad_smem_bytes<float>(NB * 8);
+        cudaError_t e = cudaFuncSetAttribute(sfh_bgrad_mma_kernel<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sfh_bgrad_mma_kernel<float, NB><<<grid, kBgThreads, smem, st>>>((const float *)s->dM, gp);
+    }
+    return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G) {
+    if (!c || !X || C < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (C == 0) return SFH_OK;
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    const int64_t nt = s->nt;
+    for (int64_t c0 = 0; c0 < C; c0 += kBgMaxC) {   // at most 64 vectors per pass (accumulators live in registers)
+        const int64_t Cb = std::min<int64_t>(kBgMaxC, C - c0);
+        SFH_TRY(ensure_walker_capacity(c, Cb));
+        const int64_t wld = c->wld;
+        const int64_t n_tt = std::max<int64_t>((nt + kBgBM - 1) / kBgBM, 1);
+        const int nsplit = (int)std::min<int64_t>(32, std::max<int64_t>(1, (2 * std::max(s->sm_count, 1) + n_tt - 1) / n_tt));
+        if (c->bg_cap < c->wcap || c->bg_nsplit != nsplit) {
+            cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG);
+            c->d_resid = c->d_bgpart = c->d_bG = nullptr; c->bg_cap = 0;
+            CU_TRY(cudaMalloc((void **)&c->d_resid, (size_t)s->ld * wld * 8));
+            CU_TRY(cudaMalloc((void **)&c->d_bgpart, (size_t)nsplit * std::max<int64_t>(nt, 1) * wld * 8));
+            CU_TRY(cudaMalloc((void **)&c->d_bG, (size_t)std::max<int64_t>(nt, 1) * wld * 8));
+            c->bg_cap = c->wcap; c->bg_nsplit = nsplit;
+        }
+        CU_TRY(cudaMemcpyAsync(c->d_X, X + c0 * nt, (size_t)nt * Cb * 8, cudaMemcpyHostToDevice, c->stream));
+        SFH_TRY(enqueue_batched_impl(c, c->d_X, Cb, c->d_logl, G ? c->d_resid : nullptr, false));
+        if (G && nt > 0) {
+            BGradParams gp{};
+            gp.nb = s->rows; gp.nt = nt; gp.wld = wld; gp.C = (int32_t)Cb; gp.nsplit = nsplit; gp.lay = s->lay;
+            gp.resid = c->d_resid; gp.gpart = c->d_bgpart;
+            const dim3 grid((unsigned)n_tt, (unsigned)nsplit);
+            const int NB = (int)((Cb + 7) / 8);
+            cudaError_t e;
+            switch (NB) {
+            case 1: e = launch_bgrad<1>(s, gp, grid, c->stream); break;
+            case 2: e = launch_bgrad<2>(s, gp, grid, c->stream); break;
+            case 3: case 4: e = launch_bgrad<4>(s, gp, grid, c->stream); break;
+            default: e = launch_bgrad<8>(s, gp, grid, c->stream); break;
+            }
+            CU_TRY(e);
+            sfh_bgrad_reduce_kernel<<<(unsigned)((nt * Cb + 255) / 256), 256, 0, c->stream>>>(c->d_bgpart, nsplit, nt, wld, Cb, c->d_bG);
+            CU_TRY(cudaGetLastError());
+            c->stats.kernel_launches += 2;
+            if (c->comm) {
+                int r = g_nccl.AllReduce(c->d_bG, c->d_bG, (size_t)(nt * Cb), kNcclFloat64, kNcclSum, c->comm, c->stream);
+                if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
+            }
+            CU_TRY(cudaMemcpyAsync(G + c0 * nt, c->d_bG, (size_t)nt * Cb * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (neg_logL) CU_TRY(cudaMemcpyAsync(neg_logL + c0, c->d_logl, (size_t)Cb * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (neg_logL)
+            for (int64_t k = 0; k < Cb; ++k) neg_logL[c0 + k] = guard_neg_logl(neg_logL[c0 + k]);
+    }
     return SFH_OK;
 }
 

@@ -45,6 +45,7 @@ struct BatchedParams {
     const double *Xt;    // [nt][wld]
     const double *data;  // [nb]
     double *part;        // [n_bin_tiles][wld]
+    double *resid;       // nullable: [nb_padded][wld] residual matrix 1 - n/max(m,eps) for the batched gradient (K6g)
 };
 
 template <typename S>
@@ -152,11 +153,15 @@ __global__ void __launch_bounds__(kBwThreads) sfh_batched_logl_kernel(const S *_
 // for this dtype.  CTA tile 128 bins x 128 walkers, 16 warps (4 x 4), warp tile 32 x 32 = 4 x 4 DMMA tiles,
 // BK = 16 templates per slab, 3-stage cp.async pipeline; rows padded by 4 doubles => conflict-free fragment loads.
 // ------------------------------------------------------------------------------------------
-constexpr int kMmaBM = 128, kMmaBN = 128, kMmaBK = 16, kMmaStages = 3, kMmaThreads = 512;
-constexpr int kMmaLdA = kMmaBM + 4, kMmaLdB = kMmaBN + 4;  // doubles; stride = 4 (mod 16) => 16 distinct bank pairs
+// WN = warps along the walker axis, NBW = 8-walker MMA blocks per warp: CTA tile = 128 bins x 8*NBW*WN walkers, 4*WN warps.
+// (WN, NBW) = (4, 4) for walker ensembles; (1, 1) / (1, 2) / (1, 4) / (2, 4) for the 8 / 16 / 32 / 64-chain batches of
+// sfh_eval_fg_batched (a 128-wide tile would waste up to 16x the math and make a few-chain pass compute-bound).
+constexpr int kMmaBM = 128, kMmaBK = 16, kMmaStages = 3;
+constexpr int kMmaBN = 128, kMmaThreads = 512;  // the (4, 4) shape (host-side grid arithmetic of the walker path)
+constexpr int kMmaLdA = kMmaBM + 4;  // doubles; stride = 4 (mod 16) => 16 distinct bank pairs
 template <typename S>
-__host__ __device__ constexpr size_t mma_smem_bytes() {
-    return (size_t)kMmaStages * kMmaBK * (kMmaLdA * sizeof(S) + kMmaLdB * sizeof(double)) + 4 * kMmaBN * sizeof(double);
+__host__ __device__ constexpr size_t mma_smem_bytes(int bn = 128) {
+    return (size_t)kMmaStages * kMmaBK * (kMmaLdA * sizeof(S) + (bn + 4) * sizeof(double)) + 4 * bn * sizeof(double);
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
@@ -172,8 +177,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <typename S>
-__global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(const S *__restrict__ M, const BatchedParams p) {
+template <typename S, int WN, int NBW>
+__global__ void __launch_bounds__(128 * WN, 1) sfh_batched_logl_mma_kernel(const S *__restrict__ M, const BatchedParams p) {
+    constexpr int kWarpN = 8 * NBW, kMmaBN = kWarpN * WN, kMmaThreads = 128 * WN, kMmaLdB = kMmaBN + 4;
     extern __shared__ __align__(16) unsigned char bsm[];
     S *As = reinterpret_cast<S *>(bsm);                                                        // [stages][BK][LdA]
     double *Bs = reinterpret_cast<double *>(bsm + (size_t)kMmaStages * kMmaBK * kMmaLdA * sizeof(S));  // [stages][BK][LdB]
@@ -208,11 +214,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(co
         cp_async_commit();
     };
 
-    double acc[4][4][2];
+    double acc[4][NBW][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < NBW; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     for (int s = 0; s < kMmaStages - 1; ++s) issue_slab(s, s);
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
@@ -225,38 +231,48 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(co
         const double *Bsl = Bs + (size_t)stage * kMmaBK * kMmaLdB;
 #pragma unroll
         for (int k4 = 0; k4 < kMmaBK; k4 += 4) {
-            double a[4], b[4];
+            double a[4], b[NBW];
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb) a[mb] = (double)Asl[(k4 + fk) * kMmaLdA + wm * 32 + mb * 8 + fr];
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) b[nb] = Bsl[(k4 + fk) * kMmaLdB + wn * 32 + nb * 8 + fr];
+            for (int nb = 0; nb < NBW; ++nb) b[nb] = Bsl[(k4 + fk) * kMmaLdB + wn * kWarpN + nb * 8 + fr];
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                for (int nb = 0; nb < NBW; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
         }
     }
     cp_async_wait<0>();
 
     // Poisson epilogue: lane holds C[row = mb*8 + lane/4][col = nb*8 + (lane%4)*2 + {0,1}] of its warp tile
-    double csum[4][2];
+    double csum[NBW][2];
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) csum[nb][0] = csum[nb][1] = 0.0;
+    for (int nb = 0; nb < NBW; ++nb) csum[nb][0] = csum[nb][1] = 0.0;
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) {
         const int64_t i = i0 + wm * 32 + mb * 8 + fr;
         if (i < p.nb) {
             const double n = p.data[i];
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
+            for (int nb = 0; nb < NBW; ++nb) {
                 csum[nb][0] += poisson_term(acc[mb][nb][0], n, p.eps);
                 csum[nb][1] += poisson_term(acc[mb][nb][1], n, p.eps);
+                if (p.resid) {  // residual of fitting_base.jl:277-279 for every (bin, chain): feeds the batched gradient
+                    const int64_t w = w0 + wn * kWarpN + nb * 8 + fk * 2;
+                    if (w < p.wld) {
+                        const double m0 = acc[mb][nb][0], m1 = acc[mb][nb][1];
+                        double2 r;
+                        r.x = 1.0 - n / ((m0 < p.eps) ? p.eps : m0);
+                        r.y = 1.0 - n / ((m1 < p.eps) ? p.eps : m1);
+                        *reinterpret_cast<double2 *>(p.resid + i * p.wld + w) = r;
+                    }
+                }
             }
         }
     }
     // sum over the 8 lanes that share lane%4 (the rows of the fragment): fixed xor tree
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
+    for (int nb = 0; nb < NBW; ++nb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             double v = csum[nb][e];
@@ -267,9 +283,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(co
         }
     if (fr == 0) {
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
+        for (int nb = 0; nb < NBW; ++nb)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) colsum[wm * kMmaBN + wn * 32 + nb * 8 + fk * 2 + e] = csum[nb][e];
+            for (int e = 0; e < 2; ++e) colsum[wm * kMmaBN + wn * kWarpN + nb * 8 + fk * 2 + e] = csum[nb][e];
     }
     __syncthreads();
     if (tid < kMmaBN) {
@@ -279,14 +295,139 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sfh_batched_logl_mma_kernel(co
     }
 }
 
-// logL[w] = sum over bin tiles (fixed order); raw sums (guards applied after any all-reduce)
-__global__ void sfh_batched_reduce_kernel(const double *__restrict__ part, int64_t n_bt, int64_t W, int64_t wld,
-                                          double *__restrict__ out) {
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= W) return;
+// ------------------------------------------------------------------------------------------
+// K6g: batched gradient  G[T x C] = M' (T x Nb) * R (Nb x C)  for C coefficient vectors at once (multi-chain HMC:
+// the reference runs chains on separate threads, hmc_sample.jl:123-141 / generic_fitting.jl:617-626; here one device
+// pass serves them all).  Split-K over bins: CTA (tt, sp) owns 128 templates x all C chains x a contiguous range of
+// bin slabs and writes a partial; sfh_bgrad_reduce_kernel sums the partials in fixed order.  DMMA m8n8k4, 4 warps,
+// warp tile 32 templates x C (C <= 64), slabs of 16 bins through a 3-stage cp.async pipeline.
+// ------------------------------------------------------------------------------------------
+constexpr int kBgBM = 128, kBgBK = 16, kBgStages = 3, kBgThreads = 128, kBgMaxC = 64;
+constexpr int kBgLdA = kBgBK + 4;  // doubles/floats per template row of a slab: stride = 4 (mod 16) => conflict-free
+struct BGradParams {
+    int64_t nb, nt, wld;   // wld: row length of the residual matrix (>= C, multiple of 8)
+    int32_t C, nsplit;
+    StackLayout lay;
+    const double *resid;   // [nb_padded][wld]
+    double *gpart;         // [nsplit][nt][wld]
+};
+template <typename S>
+__host__ __device__ constexpr size_t bgrad_smem_bytes(int C) {
+    return (size_t)kBgStages * (kBgBM * kBgLdA * sizeof(S) + kBgBK * (size_t)(C + 4) * sizeof(double));
+}
+
+template <typename S, int NB /* n-blocks of 8 chains */>
+__global__ void __launch_bounds__(kBgThreads) sfh_bgrad_mma_kernel(const S *__restrict__ M, const BGradParams p) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    constexpr int C = NB * 8, LdB = C + 4;
+    constexpr int EPV = 16 / sizeof(S);
+    S *As = reinterpret_cast<S *>(bsm);                                                      // [stages][BM][LdA]
+    double *Bs = reinterpret_cast<double *>(bsm + (size_t)kBgStages * kBgBM * kBgLdA * sizeof(S));  // [stages][BK][LdB]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int64_t j0 = (int64_t)blockIdx.x * kBgBM;
+    const int64_t nslab_all = (p.nb + kBgBK - 1) / kBgBK;
+    const int64_t per = (nslab_all + p.nsplit - 1) / p.nsplit;
+    const int64_t s0 = (int64_t)blockIdx.y * per, s1 = (s0 + per < nslab_all) ? s0 + per : nslab_all;
+
+    auto issue = [&](int64_t slab, int stage) {
+        const int64_t i0 = slab * kBgBK;
+        const bool live = slab < s1;
+        // A: 128 templates x 16 bins; 16-byte pieces along bins (contiguous inside a panel row)
+        constexpr int A_VEC = kBgBK / EPV;
+        for (int v = tid; v < kBgBM * A_VEC; v += kBgThreads) {
+            const int m = v / A_VEC, kv = (v % A_VEC) * EPV;
+            const int64_t j = j0 + m, i = i0 + kv;
+            const bool ok = live && j < p.nt && i < p.lay.ld;
+            cp_async16(As + ((size_t)stage * kBgBM + m) * kBgLdA + kv, M + (ok ? p.lay.off(i, j) : 0), ok);
+        }
+        // B: 16 bins x C chains of the residual matrix (rows beyond nb were never written: masked by `i < nb`)
+        constexpr int B_VEC = C / 2;
+        for (int v = tid; v < kBgBK * B_VEC; v += kBgThreads) {
+            const int k = v / B_VEC, cv = (v % B_VEC) * 2;
+            const int64_t i = i0 + k;
+            const bool ok = live && i < p.nb && cv < p.wld;  // the kernel's C (multiple of 8, <= 64) may exceed the row length
+            cp_async16(Bs + ((size_t)stage * kBgBK + k) * LdB + cv, p.resid + (ok ? i * p.wld + cv : 0), ok);
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][NB][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int s = 0; s < kBgStages - 1; ++s) issue(s0 + s, s);
+    for (int64_t slab = s0; slab < s1; ++slab) {
+        const int stage = (int)((slab - s0) % kBgStages);
+        cp_async_wait<kBgStages - 2>();
+        __syncthreads();
+        issue(slab + kBgStages - 1, (int)((slab - s0 + kBgStages - 1) % kBgStages));
+        const S *Asl = As + (size_t)stage * kBgBM * kBgLdA;
+        const double *Bsl = Bs + (size_t)stage * kBgBK * LdB;
+#pragma unroll
+        for (int k4 = 0; k4 < kBgBK; k4 += 4) {
+            double a[4], b[NB];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) a[mb] = (double)Asl[(warp * 32 + mb * 8 + fr) * kBgLdA + k4 + fk];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) b[nb] = Bsl[(k4 + fk) * LdB + nb * 8 + fr];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        }
+    }
+    cp_async_wait<0>();
+    // C fragment: row (template) = mb*8 + lane/4, cols (chains) = nb*8 + (lane%4)*2 + {0,1}
+    double *out = p.gpart + (size_t)blockIdx.y * p.nt * p.wld;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        const int64_t j = j0 + warp * 32 + mb * 8 + fr;
+        if (j < p.nt) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                if (nb * 8 + fk * 2 < p.wld) {
+                    double2 v;
+                    v.x = acc[mb][nb][0];
+                    v.y = acc[mb][nb][1];
+                    *reinterpret_cast<double2 *>(out + j * p.wld + nb * 8 + fk * 2) = v;
+                }
+            }
+        }
+    }
+}
+
+// G[j + nt*c] (column-major T x C, like the coefficient matrix) = sum over splits, fixed order
+__global__ void sfh_bgrad_reduce_kernel(const double *__restrict__ gpart, int nsplit, int64_t nt, int64_t wld, int64_t C,
+                                        double *__restrict__ G) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt * C) return;
+    const int64_t j = e % nt, c = e / nt;
     double s = 0.0;
-    for (int64_t b = 0; b < n_bt; ++b) s += part[b * wld + w];
-    out[w] = s;
+    for (int sp = 0; sp < nsplit; ++sp) s += gpart[((size_t)sp * nt + j) * wld + c];
+    G[e] = s;
+}
+
+// logL[w] = sum over bin tiles; raw sums (guards applied after any all-reduce).  256 threads = 8 walkers x 32 slices:
+// slice q adds tiles q, q+32, ... in order, then a fixed shared-memory tree joins the slices (deterministic, and not a
+// 469-long dependent chain per walker).
+__global__ void __launch_bounds__(256) sfh_batched_reduce_kernel(const double *__restrict__ part, int64_t n_bt, int64_t W, int64_t wld,
+                                                                  double *__restrict__ out) {
+    __shared__ double sh[32][8];
+    const int wl = threadIdx.x & 7, q = threadIdx.x >> 3;
+    const int64_t w = (int64_t)blockIdx.x * 8 + wl;
+    double s = 0.0;
+    if (w < W)
+        for (int64_t b = q; b < n_bt; b += 32) s += part[b * wld + w];
+    sh[q][wl] = s;
+    __syncthreads();
+    for (int h = 16; h >= 1; h >>= 1) {
+        if (q < h) sh[q][wl] += sh[q + h][wl];
+        __syncthreads();
+    }
+    if (q == 0 && w < W) out[w] = sh[0][wl];
 }
 
 // mcmc_sample.jl:15-19 (negative -> -Inf) and fitting_base.jl:95 (== 0 -> -Inf)

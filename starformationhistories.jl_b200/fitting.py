@@ -210,6 +210,19 @@ class DeviceStack:
         L.check(L.lib.sfh_eval_logl_batched(self.ctx().handle, _dp(X), X.shape[1], _dp(out)))
         return out
 
+    def eval_fg_batched(self, X, want_G=True):
+        """fg! for every column of X (T x C) in one device pass: returns (-logL[C], G[T, C] or None)."""
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if X.shape[0] != self.shape[1]:
+            raise ValueError("size(X,1) != size(models,2)")
+        X = np.asfortranarray(X)
+        nl = np.empty(X.shape[1])
+        G = np.empty(X.shape, order="F") if want_G else None
+        L.check(L.lib.sfh_eval_fg_batched(self.ctx().handle, _dp(X), X.shape[1], _dp(nl), _dp(G) if want_G else None))
+        return nl, G
+
     def column_sums(self):
         """colsum_j = sum_i M_ij of the resident stack (one device pass)."""
         out = np.empty(self.shape[1])

@@ -37,6 +37,13 @@ class HMCModel:
         nl, G, _ = self.models.eval_fg(x, want_F=True, want_G=True)
         return -nl + logx.sum(), -G * x + 1
 
+    def logdensity_and_gradient_batched(self, LOGX):
+        """The same for C chains at once: LOGX is (T, C); one device pass (sfh_eval_fg_batched) serves all chains."""
+        LOGX = np.asarray(LOGX, dtype=np.float64)
+        Xn = np.exp(LOGX)
+        nl, G = self.models.eval_fg_batched(Xn)
+        return -nl + LOGX.sum(axis=0), -G * Xn + 1
+
 
 class MCMCModel:
     """mcmc_sample.jl:1-24: log-likelihood only; negative coefficients -> -Inf."""

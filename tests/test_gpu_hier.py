@@ -196,3 +196,33 @@ def test_batched_walkers_f32_stack(S):
     for w in (0, 7, 39):
         nlq, _, _ = O.fg_quad_f32(X[:, w], M, data, want_G=False)
         assert got[w] == pytest.approx(-nlq, rel=1e-6)
+
+
+@pytest.mark.parametrize("nb,nt,C,dtype", [(4000, 64, 1, np.float64), (5003, 100, 5, np.float64), (9801, 142, 16, np.float64),
+                                           (20000, 600, 33, np.float64), (3000, 200, 70, np.float64), (6000, 120, 12, np.float32),
+                                           (7000, 90, 24, np.float64), (4100, 64, 9, np.float32), (2500, 33, 64, np.float32)])
+def test_fg_batched_matches_single_vector_path(S, nb, nt, C, dtype):
+    """sfh_eval_fg_batched: C coefficient vectors in one pass == C calls of fg! (solvers.jl:20-38), and == the quad oracle."""
+    M, x, data = make_flat_problem(nb, nt, seed=41, dtype=dtype)
+    X = np.maximum(1e-3, x[:, None] * (1 + 0.2 * np.random.default_rng(7).standard_normal((nt, C))))
+    ds = S.DeviceStack(M, data)
+    nl, G = ds.eval_fg_batched(X)
+    assert nl.shape == (C,) and G.shape == (nt, C)
+    for c in sorted(set([0, C // 2, C - 1])):
+        nl1, G1, _ = ds.eval_fg(X[:, c])
+        assert nl[c] == pytest.approx(nl1, rel=1e-12)
+        if dtype == np.float64:
+            nlq, Gq, gs, _ = O.fg_quad(X[:, c], M, data)
+            assert nl[c] == pytest.approx(nlq, rel=1e-12)
+            assert np.all(np.abs(G[:, c] - Gq) <= 1e-10 * gs)
+        else:
+            nlq, Gq, gs = O.fg_quad_f32(X[:, c], M, data)
+            assert nl[c] == pytest.approx(nlq, rel=1e-6) and np.all(np.abs(G[:, c] - Gq) <= 1e-6 * gs)
+        assert np.all(np.abs(G[:, c] - G1) <= 1e-10 * np.maximum(np.abs(G1), 1e-3 * np.abs(G1).max()))
+    nl_only, none = ds.eval_fg_batched(X, want_G=False)
+    assert none is None and np.array_equal(nl_only, nl)
+    # HMC adapter, all chains at once (hmc_sample.jl:24-37 per chain)
+    hm = S.HMCModel(ds, None, data)
+    LP, GR = hm.logdensity_and_gradient_batched(np.log(X))
+    lp0, g0 = hm.logdensity_and_gradient(np.log(X[:, 0]))
+    assert LP[0] == pytest.approx(lp0, rel=1e-12) and np.allclose(GR[:, 0], g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
