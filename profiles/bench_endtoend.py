@@ -69,3 +69,19 @@ Mh, dh = ds3.download()
 t0 = time.perf_counter(); O.fg_hier(O.POWERLAW_MZR, (6.0,), (1, 1, 1), truth, Mh, dh, la, mh); t_cpu = time.perf_counter() - t0
 out(config=4, what="HMC leapfrog = HierarchicalOptimizer.logdensity_and_gradient on the 2400-template MZR stack", gpu_us_per_eval=t_leap * 1e6,
     gpu_evals_per_s=1 / t_leap, cpu_oracle_1thread_s_per_eval=t_cpu)
+
+# ---- multi-chain hmc_sample: chains on threads sharing one sfh_eval_fg_batched pass vs chains one after another ------
+from sfh_b200 import solvers as V
+for (nbh, nth, nchs, nst, md) in ((60000, 200, (8,), 40, 5), (60000, 2400, (4, 8, 16), 12, 4)):
+    xh = 100 * np.random.default_rng(5).random(nth)
+    dsh = S.DeviceStack.synthetic(nbh, nth, np.float64, 5, 1.0, xh)
+    dh2 = dsh.download_data()
+    for nch in nchs:
+        tt = {}
+        for batched in (False, True):
+            t0 = time.perf_counter()
+            V.hmc_sample(dsh, dh2, nst, nchains=nch, nwarmup=nst, rng=np.random.default_rng(1), x0=xh, max_depth=md, batched=batched)
+            tt[batched] = time.perf_counter() - t0
+        out(what=f"hmc_sample (coroutine chains) {nbh} bins x {nth} templates F64, {nst} warm-up + {nst} draws per chain, max_depth {md}", nchains=nch,
+            sequential_s=tt[False], batched_s=tt[True], speedup=tt[False] / tt[True])
+    del dsh

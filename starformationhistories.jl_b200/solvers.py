@@ -268,32 +268,35 @@ def mdf_amr(coeffs, logAge, metallicities, models=None):
 
 
 # ---------------------------------------------------------------------------------------------
-def _leapfrog(lg, theta, r, grad, eps, inv_mass):
+def _leapfrog(theta, r, grad, eps, inv_mass):
+    """One leapfrog step as a coroutine: yields the position whose (logp, gradient) it needs."""
     r = r + 0.5 * eps * grad
     theta = theta + eps * inv_mass * r
-    lp, grad = lg(theta)
+    lp, grad = yield theta
     r = r + 0.5 * eps * grad
     return theta, r, lp, grad
 
 
-def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None):
-    """No-U-Turn sampler (Hoffman & Gelman 2014, algorithm 6: slice NUTS with dual-averaging step size).
-    Stands in for DynamicHMC.mcmc_with_warmup (hmc_sample.jl:111); diagonal mass matrix fixed to `inv_mass`."""
+def nuts_chain(theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None):
+    """No-U-Turn sampler (Hoffman & Gelman 2014, algorithm 6: slice NUTS with dual-averaging step size) written as a
+    coroutine: it *yields* every position at which it needs the log-density and gradient and is *sent* `(logp, grad)`
+    back; its return value is `(samples, logps, step_size)`.  Stands in for DynamicHMC.mcmc_with_warmup
+    (hmc_sample.jl:111); diagonal mass matrix fixed to `inv_mass`.  `nuts_sample` drives one chain; `run_chains_batched`
+    drives many, serving each round of requests with one batched device pass."""
     rng = np.random.default_rng() if rng is None else rng
-    lg = logdensity_and_gradient
     theta = np.asarray(theta0, dtype=np.float64).copy()
     d = theta.shape[0]
     inv_mass = np.ones(d) if inv_mass is None else np.asarray(inv_mass, dtype=np.float64)
-    lp, grad = lg(theta)
+    lp, grad = yield theta
 
     # heuristic initial step size
     eps = 0.1 / math.sqrt(d)
     r0 = rng.standard_normal(d) / np.sqrt(inv_mass)
-    _, r1, lp1, _ = _leapfrog(lg, theta, r0, grad, eps, inv_mass)
+    _, r1, lp1, _ = yield from _leapfrog(theta, r0, grad, eps, inv_mass)
     H0 = lp - 0.5 * np.dot(r0 * inv_mass, r0); H1 = lp1 - 0.5 * np.dot(r1 * inv_mass, r1)
     a = 1.0 if (np.isfinite(H1) and H1 - H0 > math.log(0.5)) else -1.0
     for _ in range(50):
-        _, r1, lp1, _ = _leapfrog(lg, theta, r0, grad, eps, inv_mass)
+        _, r1, lp1, _ = yield from _leapfrog(theta, r0, grad, eps, inv_mass)
         H1 = lp1 - 0.5 * np.dot(r1 * inv_mass, r1)
         if not np.isfinite(H1):
             H1 = -np.inf
@@ -304,19 +307,19 @@ def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=
 
     def build(theta, r, grad, logu, v, j, eps, H0):
         if j == 0:
-            th, rr, lpn, g = _leapfrog(lg, theta, r, grad, v * eps, inv_mass)
+            th, rr, lpn, g = yield from _leapfrog(theta, r, grad, v * eps, inv_mass)
             Hn = lpn - 0.5 * np.dot(rr * inv_mass, rr)
             if not np.isfinite(Hn):
                 Hn = -np.inf
             n = int(logu <= Hn)
             s = int(logu < Hn + 1000.0)
             return th, rr, g, th, rr, g, th, lpn, g, n, s, min(1.0, math.exp(min(0.0, Hn - H0))), 1
-        thm, rm, gm, thp, rp, gp, th1, lp1, g1, n1, s1, a1, na1 = build(theta, r, grad, logu, v, j - 1, eps, H0)
+        thm, rm, gm, thp, rp, gp, th1, lp1, g1, n1, s1, a1, na1 = yield from build(theta, r, grad, logu, v, j - 1, eps, H0)
         if s1:
             if v == -1:
-                thm, rm, gm, _, _, _, th2, lp2, g2, n2, s2, a2, na2 = build(thm, rm, gm, logu, v, j - 1, eps, H0)
+                thm, rm, gm, _, _, _, th2, lp2, g2, n2, s2, a2, na2 = yield from build(thm, rm, gm, logu, v, j - 1, eps, H0)
             else:
-                _, _, _, thp, rp, gp, th2, lp2, g2, n2, s2, a2, na2 = build(thp, rp, gp, logu, v, j - 1, eps, H0)
+                _, _, _, thp, rp, gp, th2, lp2, g2, n2, s2, a2, na2 = yield from build(thp, rp, gp, logu, v, j - 1, eps, H0)
             if n1 + n2 > 0 and rng.random() < n2 / (n1 + n2):
                 th1, lp1, g1 = th2, lp2, g2
             dth = thp - thm
@@ -336,9 +339,9 @@ def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=
         while s and j < max_depth:
             v = -1 if rng.random() < 0.5 else 1
             if v == -1:
-                thm, rm, gm, _, _, _, th1, lp1, g1, n1, s1, alpha, nalpha = build(thm, rm, gm, logu, v, j, eps, H0)
+                thm, rm, gm, _, _, _, th1, lp1, g1, n1, s1, alpha, nalpha = yield from build(thm, rm, gm, logu, v, j, eps, H0)
             else:
-                _, _, _, thp, rp, gp, th1, lp1, g1, n1, s1, alpha, nalpha = build(thp, rp, gp, logu, v, j, eps, H0)
+                _, _, _, thp, rp, gp, th1, lp1, g1, n1, s1, alpha, nalpha = yield from build(thp, rp, gp, logu, v, j, eps, H0)
             if s1 and rng.random() < min(1.0, n1 / n):
                 theta, lp, grad = th1, lp1, g1
             n += n1
@@ -359,15 +362,80 @@ def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=
     return samples, lps, eps
 
 
-def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, max_depth=8):
+def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None):
+    """One NUTS chain: every request of `nuts_chain` is answered by `logdensity_and_gradient(theta) -> (logp, grad)`."""
+    chain = nuts_chain(theta0, nsteps, nwarmup, max_depth, delta, rng, inv_mass)
+    try:
+        req = next(chain)
+        while True:
+            req = chain.send(logdensity_and_gradient(req))
+    except StopIteration as done:
+        return done.value
+
+
+class ChainStats:
+    n_batches = 0
+    n_evals = 0
+
+
+def run_chains_batched(batch_fn, theta0s, nsteps, nwarmup=200, max_depth=8, rngs=None, chain=None):
+    """Run len(theta0s) sampler coroutines side by side.  The reference runs HMC chains on separate threads, each
+    evaluating its own `fg!` (hmc_sample.jl:123-141, generic_fitting.jl:617-626); here every round collects the pending
+    request of each live chain and serves them all with ONE call of
+    `batch_fn(Theta[npar, C]) -> (logp[C], grad[npar, C])` (sfh_eval_fg_batched).  A chain's answers do not depend on how
+    requests were grouped, so it follows the trajectory it would have followed alone; chains that finish early drop out.
+    Returns ([(samples, logps, step_size) per chain], ChainStats)."""
+    nchains = len(theta0s)
+    rngs = list(np.random.default_rng().spawn(nchains)) if rngs is None else rngs
+    chain = nuts_chain if chain is None else chain
+    chains = [chain(theta0s[c], nsteps, nwarmup, max_depth, rng=rngs[c]) for c in range(nchains)]
+    out, stats = [None] * nchains, ChainStats()
+    pending = {}
+    for c, ch in enumerate(chains):
+        try:
+            pending[c] = next(ch)
+        except StopIteration as done:
+            out[c] = done.value
+    while pending:
+        ids = sorted(pending)
+        Theta = np.empty((pending[ids[0]].shape[0], len(ids)), order="F")
+        for k, c in enumerate(ids):
+            Theta[:, k] = pending[c]
+        lp, gr = batch_fn(Theta)
+        stats.n_batches += 1
+        stats.n_evals += len(ids)
+        for k, c in enumerate(ids):
+            try:
+                pending[c] = chains[c].send((float(lp[k]), np.array(gr[:, k], dtype=np.float64)))
+            except StopIteration as done:
+                out[c] = done.value
+                del pending[c]
+    return out, stats
+
+
+def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, max_depth=8, batched=None):
     """hmc_sample(models, data, nsteps[, nchains])  (hmc_sample.jl:105-143): NUTS on theta = log(coeffs) with the
-    Jacobian-corrected log-density of HMCModel.  Returns natural-unit samples of shape (nsteps, npar, nchains)."""
+    Jacobian-corrected log-density of HMCModel.  Returns natural-unit samples of shape (nsteps, npar, nchains).
+    With nchains > 1 (threads in the reference, hmc_sample.jl:123-141) the chains run as coroutines and, when `batched`,
+    share one sfh_eval_fg_batched pass per round of gradient requests; each chain draws from its own spawned RNG.
+    `batched=None` picks the batched pass when it pays: a stack of >= 64 MB (below that one fused single-vector evaluation
+    per chain is cheaper) and at least 4 chains (profiles/r1_results.md)."""
     ds = device_stack(models, data)
     model = HMCModel(ds, None, data)
     rng = np.random.default_rng() if rng is None else rng
     x0 = renormalize_x0(data, ds, np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, float))
     out = np.empty((nsteps, ds.shape[1], nchains))
-    for c in range(nchains):
+    if nchains == 1:
         s, _, _ = nuts_sample(model.logdensity_and_gradient, np.log(x0), nsteps, nwarmup, max_depth, rng=rng)
-        out[:, :, c] = np.exp(s)                                           # back to natural units
+        out[:, :, 0] = np.exp(s)                                           # back to natural units
+        return out
+    rngs = list(rng.spawn(nchains))
+    if batched is None:
+        batched = nchains >= 4 and ds.shape[0] * ds.shape[1] * np.dtype(ds.dtype).itemsize >= (64 << 20)
+    if batched:
+        res, _ = run_chains_batched(model.logdensity_and_gradient_batched, [np.log(x0)] * nchains, nsteps, nwarmup, max_depth, rngs)
+    else:
+        res = [nuts_sample(model.logdensity_and_gradient, np.log(x0), nsteps, nwarmup, max_depth, rng=rngs[c]) for c in range(nchains)]
+    for c in range(nchains):
+        out[:, :, c] = np.exp(res[c][0])
     return out

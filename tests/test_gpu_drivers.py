@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle as O
-from conftest import make_hier_problem
+from conftest import make_flat_problem, make_hier_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -132,6 +132,19 @@ def test_hmc_sample_shapes_and_moments(S, V):                    # basic_linear_
     ft = V.fit_templates(models, data, x0=np.ones(N))
     z = np.abs(out.mean(axis=(0, 2)) - ft["map"].mu) / ft["map"].sigma
     assert np.all(z < 1.0), z                                          # posterior mean within 1 sigma of the MAP
+
+
+def test_hmc_chains_batched_equals_sequential(S, V):          # hmc_sample.jl:123-141 (chains on threads)
+    """Chains sharing one sfh_eval_fg_batched pass draw from the same posterior as chains run one after another."""
+    M, x, data = make_flat_problem(3000, 8, seed=77)
+    ds = S.DeviceStack(M, data)
+    a = V.hmc_sample(ds, data, 120, nchains=4, nwarmup=80, rng=np.random.default_rng(5), x0=x, batched=True)
+    b = V.hmc_sample(ds, data, 120, nchains=4, nwarmup=80, rng=np.random.default_rng(5), x0=x, batched=False)
+    assert a.shape == b.shape == (120, 8, 4) and np.all(a > 0)
+    # (trajectories are chaotic: a 1e-13 difference between the batched and single-vector kernels grows over warm-up,
+    #  so the comparison is statistical; bit-identical grouping is covered on the CPU in test_host_chains.py)
+    sd = b.reshape(-1, 8, 4).std(axis=(0, 2))
+    assert np.all(np.abs(a.mean(axis=(0, 2)) - b.mean(axis=(0, 2))) < 0.5 * sd)
 
 
 def test_mdf_amr_and_renormalize_x0(S, V):                      # mdf.jl doctests :17-18, :49-51 ; utilities.jl:89-102

@@ -1,0 +1,52 @@
+"""Host logic of the multi-chain driver: sampler coroutines sharing one batched evaluation per round of requests
+(the reference runs chains on threads, each with its own fg!, hmc_sample.jl:123-141).  CPU only: the batch function is a closed-form Gaussian."""
+import numpy as np
+import pytest
+
+import sfh_b200 as S
+from sfh_b200 import solvers as V
+
+
+def _gauss(prec):
+    def single(th):
+        return float(-0.5 * th @ (prec * th)), -(prec * th)
+
+    def batch(TH):                       # column by column with the very same arithmetic, so trajectories match bit for bit
+        cols = [single(TH[:, c]) for c in range(TH.shape[1])]
+        return np.array([lp for lp, _ in cols]), np.stack([g for _, g in cols], axis=1)
+    return single, batch
+
+
+def test_batched_chains_follow_the_sequential_trajectories():
+    d, nchains = 5, 4
+    prec = np.array([1.0, 4.0, 0.25, 9.0, 2.0])
+    single, batch = _gauss(prec)
+    th0 = [np.full(d, 0.3 * (c + 1)) for c in range(nchains)]
+    seq = [V.nuts_sample(single, th0[c], 60, 40, 6, rng=np.random.default_rng(100 + c)) for c in range(nchains)]
+    res, b = V.run_chains_batched(batch, th0, 60, 40, 6, [np.random.default_rng(100 + c) for c in range(nchains)])
+    for c in range(nchains):
+        assert np.array_equal(res[c][0], seq[c][0])
+        assert res[c][2] == seq[c][2]
+    # the requests really were grouped: far fewer batches than evaluations
+    assert b.n_evals > 2 * b.n_batches and b.n_batches > 0
+    # sanity of the target: pooled variance ~ 1/prec
+    pooled = np.concatenate([r[0] for r in res])
+    assert np.all(np.abs(pooled.var(axis=0) * prec - 1) < 0.8)
+
+
+def test_chains_of_different_length_and_errors():
+    prec = np.ones(3)
+    single, batch = _gauss(prec)
+    # chains finish at different times (a chain that is done must not block the others)
+    lens = [5, 40, 17]
+
+    def chain(th0, nsteps, nwarmup, max_depth, rng=None):
+        return V.nuts_chain(th0 * 0 + 0.1, lens[int(th0[0])], 5, 4, rng=rng)
+    res, _ = V.run_chains_batched(batch, [np.full(3, float(c)) for c in range(3)], 0, chain=chain,
+                                  rngs=[np.random.default_rng(c) for c in range(3)])
+    assert [r[0].shape[0] for r in res] == lens
+
+    def bad(TH):
+        raise RuntimeError("device failure")
+    with pytest.raises(RuntimeError, match="device failure"):
+        V.run_chains_batched(bad, [np.zeros(3)] * 2, 5, 5, 3, [np.random.default_rng(c) for c in range(2)])
