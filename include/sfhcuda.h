@@ -169,6 +169,16 @@ int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL);
  * G: ntemplates x C column-major (nullable).  Per-vector semantics are exactly those of sfh_eval_fg.            */
 int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G);
 
+/* Device-resident affine-invariant ensemble sampler (Goodman & Weare stretch move, the algorithm of KissMCMC.emcee
+ * that mcmc_sample drives, fitting/mcmc_sample.jl:97-108): proposal, the log-likelihood of each half-ensemble
+ * (sfh_eval_logl_batched's kernel) and accept/reject all stay on the device.  X: ntemplates x W column-major, in = the
+ * starting walkers, out = the final ones; W even.  Every nthin-th step is stored: chain (nullable) is
+ * (nsteps/nthin) x [ntemplates x W], logl_chain (nullable) (nsteps/nthin) x W; logl_final[W], accept_frac nullable.
+ * Random numbers are Philox4x32-10 keyed by `seed` with counter (step, half, walker): a run is reproducible and
+ * independent of the GPU count.                                                                              */
+int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, int64_t nthin, double a_scale, uint64_t seed,
+                 double *chain, double *logl_chain, double *logl_final, double *accept_frac);
+
 /* ---- multi-GPU: bin-row shards, one process per GPU -------------------- */
 /* 128-byte NCCL unique id (rank 0 creates, the host runtime broadcasts it).                    */
 int sfh_comm_unique_id(void *id128);

@@ -35,7 +35,30 @@ def run(nb, nt, W, dtype=np.float64, reps=10):
                       "fp64_tflops": flops / ms / 1e9, "e2e_ms_per_batch": e2e, "e2e_walker_evals_per_s": W / e2e * 1e3}), flush=True)
     return ds, X, got
 
+def run_mcmc_engines(nb=40000, nt=500, W=1024, nsteps=20):
+    """mcmc_sample at BASELINE config 2: the device-resident ensemble sampler vs numpy proposals around one K6 call per half."""
+    from sfh_b200 import solvers as V
+    rng = np.random.default_rng(9)
+    x = 100 * rng.random(nt)
+    ds = S.DeviceStack.synthetic(nb, nt, np.float64, seed=9, scale=1.0, x_true=x)
+    data = ds.download_data()
+    X0 = np.maximum(0.0, x[:, None] + rng.standard_normal((nt, W)))
+    for engine in ("host", "device"):
+        V.mcmc_sample(ds, data, X0, 2, rng=np.random.default_rng(1), engine=engine)
+        t0 = time.perf_counter()
+        chain, lps, acc = V.mcmc_sample(ds, data, X0, nsteps, rng=np.random.default_rng(1), engine=engine)
+        t = time.perf_counter() - t0
+        print(json.dumps({"mcmc_sample": engine, "nb": nb, "nt": nt, "W": W, "nsteps": nsteps, "s": t, "ms_per_step": t / nsteps * 1e3,
+                          "walker_evals_per_s": W * nsteps / t, "accept": acc}), flush=True)
+    t0 = time.perf_counter()
+    ds.mcmc_run(X0, nsteps, 1, 2.0, seed=5, store=False)
+    t = time.perf_counter() - t0
+    print(json.dumps({"mcmc_run_no_store": True, "ms_per_step": t / nsteps * 1e3, "walker_evals_per_s": W * nsteps / t}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mcmc":
+        run_mcmc_engines(); sys.exit(0)
     ds, X, got = run(40000, 500, 1024)
     # spot parity of 3 walkers against the fused single-vector path
     for w in (0, 511, 1023):
@@ -65,5 +88,28 @@ def run_fg_batched(nb, nt, Cs=(1, 8, 16, 32, 64), reps=5):
                           "single_vector_us_per_eval": t_single * 1e6, "fp64_tflops": 4.0 * nb * nt * C / t / 1e12}), flush=True)
 
 
+def run_mcmc_engines(nb=40000, nt=500, W=1024, nsteps=20):
+    """mcmc_sample at BASELINE config 2: the device-resident ensemble sampler vs numpy proposals around one K6 call per half."""
+    from sfh_b200 import solvers as V
+    rng = np.random.default_rng(9)
+    x = 100 * rng.random(nt)
+    ds = S.DeviceStack.synthetic(nb, nt, np.float64, seed=9, scale=1.0, x_true=x)
+    data = ds.download_data()
+    X0 = np.maximum(0.0, x[:, None] + rng.standard_normal((nt, W)))
+    for engine in ("host", "device"):
+        V.mcmc_sample(ds, data, X0, 2, rng=np.random.default_rng(1), engine=engine)
+        t0 = time.perf_counter()
+        chain, lps, acc = V.mcmc_sample(ds, data, X0, nsteps, rng=np.random.default_rng(1), engine=engine)
+        t = time.perf_counter() - t0
+        print(json.dumps({"mcmc_sample": engine, "nb": nb, "nt": nt, "W": W, "nsteps": nsteps, "s": t, "ms_per_step": t / nsteps * 1e3,
+                          "walker_evals_per_s": W * nsteps / t, "accept": acc}), flush=True)
+    t0 = time.perf_counter()
+    ds.mcmc_run(X0, nsteps, 1, 2.0, seed=5, store=False)
+    t = time.perf_counter() - t0
+    print(json.dumps({"mcmc_run_no_store": True, "ms_per_step": t / nsteps * 1e3, "walker_evals_per_s": W * nsteps / t}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mcmc":
+        run_mcmc_engines(); sys.exit(0)
     run_fg_batched(60000, 2400)

@@ -22,6 +22,7 @@
 #include "sfh_batched.cuh"
 #include "sfh_fused.cuh"
 #include "sfh_small.cuh"
+#include "sfh_ensemble.cuh"
 
 using namespace sfh;
 
@@ -1177,6 +1178,74 @@ extern "C" int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, dou
     SFH_TRY(enqueue_batched_impl(c, c->d_X, W, c->d_logl));
     CU_TRY(cudaMemcpyAsync(logL, c->d_logl, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    return SFH_OK;
+}
+
+// Device-resident stretch-move ensemble sampler around K6 (see sfh_ensemble.cuh).
+namespace {
+struct DevBufs {  // frees whatever was allocated when the run ends or fails
+    std::vector<void *> v;
+    ~DevBufs() { for (void *q : v) cudaFree(q); }
+    template <typename T> cudaError_t alloc(T **out, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **)out, std::max<size_t>(bytes, 8));
+        if (e == cudaSuccess) v.push_back(*out);
+        return e;
+    }
+};
+}  // namespace
+
+extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, int64_t nthin, double a_scale, uint64_t seed,
+                            double *chain, double *logl_chain, double *logl_final, double *accept_frac) {
+    if (!c || !X || nsteps < 0 || nthin < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (W < 2 || (W & 1)) return fail(SFH_ERR_INVALID_ARG, "the ensemble needs an even number of walkers (got %lld)", (long long)W);
+    if (!(a_scale > 1.0)) return fail(SFH_ERR_INVALID_ARG, "a_scale must be > 1");
+    sfh_stack *s = c->s;
+    if (s->nt < 1) return fail(SFH_ERR_SHAPE, "empty stack");
+    CU_TRY(cudaSetDevice(s->device));
+    SFH_TRY(ensure_walker_capacity(c, W));   // c->d_X holds the proposals of one half-ensemble
+    const int64_t nt = s->nt, half = W / 2, nstore = nsteps / nthin;
+    const size_t xbytes = (size_t)nt * (size_t)W * 8;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(nstore, 1), (int64_t)((size_t)1 << 30) / (int64_t)xbytes));
+    DevBufs bufs;
+    double *dX = nullptr, *dlp = nullptr, *dz = nullptr, *dchain = nullptr, *dlchain = nullptr;
+    unsigned long long *dacc = nullptr;
+    CU_TRY(bufs.alloc(&dX, xbytes));
+    CU_TRY(bufs.alloc(&dlp, (size_t)W * 8));
+    CU_TRY(bufs.alloc(&dz, (size_t)half * 8));
+    CU_TRY(bufs.alloc(&dacc, 8));
+    if (chain && nstore > 0) CU_TRY(bufs.alloc(&dchain, (size_t)chunk * xbytes));
+    if (logl_chain && nstore > 0) CU_TRY(bufs.alloc(&dlchain, (size_t)chunk * (size_t)W * 8));
+    CU_TRY(cudaMemcpyAsync(dX, X, xbytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemsetAsync(dacc, 0, 8, c->stream));
+    SFH_TRY(enqueue_batched_impl(c, dX, W, dlp));
+    const unsigned gw = (unsigned)((half + 7) / 8);
+    for (int64_t step = 0; step < nsteps; ++step) {
+        for (int h = 0; h < 2; ++h) {
+            sfh_stretch_propose_kernel<<<gw, 256, 0, c->stream>>>(dX, nt, half, h, step, seed, a_scale, c->d_X, dz);
+            CU_TRY(cudaGetLastError());
+            SFH_TRY(enqueue_batched_impl(c, c->d_X, half, c->d_logl));
+            sfh_stretch_accept_kernel<<<gw, 256, 0, c->stream>>>(dX, dlp, c->d_X, c->d_logl, dz, nt, half, h, step, seed, dacc);
+            CU_TRY(cudaGetLastError());
+            c->stats.kernel_launches += 2;
+        }
+        if ((step + 1) % nthin == 0) {
+            const int64_t k = (step + 1) / nthin - 1, slot = k % chunk;
+            if (dchain) CU_TRY(cudaMemcpyAsync(dchain + (size_t)slot * nt * W, dX, xbytes, cudaMemcpyDeviceToDevice, c->stream));
+            if (dlchain) CU_TRY(cudaMemcpyAsync(dlchain + (size_t)slot * W, dlp, (size_t)W * 8, cudaMemcpyDeviceToDevice, c->stream));
+            if (slot == chunk - 1 || k == nstore - 1) {   // flush the stored steps [k - slot, k] to the host
+                const int64_t k0 = k - slot, n = slot + 1;
+                if (dchain) CU_TRY(cudaMemcpyAsync(chain + (size_t)k0 * nt * W, dchain, (size_t)n * xbytes, cudaMemcpyDeviceToHost, c->stream));
+                if (dlchain) CU_TRY(cudaMemcpyAsync(logl_chain + (size_t)k0 * W, dlchain, (size_t)n * W * 8, cudaMemcpyDeviceToHost, c->stream));
+                CU_TRY(cudaStreamSynchronize(c->stream));
+            }
+        }
+    }
+    unsigned long long acc = 0;
+    CU_TRY(cudaMemcpyAsync(X, dX, xbytes, cudaMemcpyDeviceToHost, c->stream));
+    if (logl_final) CU_TRY(cudaMemcpyAsync(logl_final, dlp, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(&acc, dacc, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (accept_frac) *accept_frac = nsteps > 0 ? (double)acc / ((double)nsteps * (double)W) : 0.0;
     return SFH_OK;
 }
 

@@ -223,6 +223,24 @@ class DeviceStack:
         L.check(L.lib.sfh_eval_fg_batched(self.ctx().handle, _dp(X), X.shape[1], _dp(nl), _dp(G) if want_G else None))
         return nl, G
 
+    def mcmc_run(self, X0, nsteps, nthin=1, a_scale=2.0, seed=0, store=True):
+        """Device-resident stretch-move ensemble sampler (sfh_mcmc_run).  X0: (T, W) starting walkers, W even.
+        Returns (chain (nsteps//nthin, T, W) or None, logl_chain (nsteps//nthin, W) or None, X_final, logl_final,
+        acceptance fraction)."""
+        X = np.array(X0, dtype=np.float64, order="F")
+        if X.ndim != 2 or X.shape[0] != self.shape[1]:
+            raise ValueError("length of each walker != number of templates")
+        T, W = X.shape
+        nstore = int(nsteps) // int(nthin)
+        chain_buf = np.empty((nstore, W, T)) if store else None    # each stored step is T x W column-major = W rows of T
+        lchain = np.empty((nstore, W)) if store else None
+        lfin = np.empty(W)
+        acc = C.c_double(0.0)
+        L.check(L.lib.sfh_mcmc_run(self.ctx().handle, _dp(X), W, int(nsteps), int(nthin), float(a_scale), int(seed) & (2**64 - 1),
+                                   _dp(chain_buf) if store else None, _dp(lchain) if store else None, _dp(lfin), C.byref(acc)))
+        chain = chain_buf.transpose(0, 2, 1) if store else None      # view: (nstore, T, W)
+        return chain, lchain, X, lfin, acc.value
+
     def column_sums(self):
         """colsum_j = sum_i M_ij of the resident stack (one device pass)."""
         out = np.empty(self.shape[1])

@@ -227,19 +227,34 @@ def stretch_move_ensemble(logp_batch, x0, nsteps, a_scale=2.0, rng=None, thin=1)
     return chain, lps, acc / (nsteps * W)
 
 
-def mcmc_sample(models, data, x0, nsteps, nburnin=0, nthin=1, a_scale=2.0, rng=None):
+def mcmc_sample(models, data, x0, nsteps, nburnin=0, nthin=1, a_scale=2.0, rng=None, engine="device"):
     """mcmc_sample(models, data, x0, nwalkers-implied, nsteps; nburnin, nthin, a_scale)  (mcmc_sample.jl:97-108).
     x0: (npar, nwalkers) or list of walker vectors.  Returns samples with shape (nsteps, npar, nwalkers) like
-    convert_kissmcmc (:30-44), the log-likelihoods and the acceptance fraction."""
+    convert_kissmcmc (:30-44), the log-likelihoods and the acceptance fraction.
+    engine="device": the whole ensemble sampler runs on the GPU (sfh_mcmc_run: proposal, K6, accept/reject; Philox
+    streams seeded from `rng`); engine="host": numpy proposals around one K6 call per half-ensemble."""
     ds = device_stack(models, data)
     X0 = np.asarray(x0, dtype=np.float64)
     if X0.ndim == 2 and X0.shape[0] != ds.shape[1] and X0.shape[1] == ds.shape[1]:
         X0 = X0.T                                                          # list of walker vectors
     if X0.shape[0] != ds.shape[1]:
         raise ValueError("length of each walker != number of templates")
-    model = MCMCModel(ds, data)
-    chain, lps, acc = stretch_move_ensemble(model.batch, X0, nsteps + nburnin, a_scale, rng, 1)
-    return chain[nburnin::nthin], lps[nburnin::nthin], acc
+    if engine == "host":
+        model = MCMCModel(ds, data)
+        chain, lps, acc = stretch_move_ensemble(model.batch, X0, nsteps + nburnin, a_scale, rng, 1)
+        return chain[nburnin::nthin], lps[nburnin::nthin], acc
+    if engine != "device":
+        raise ValueError("engine must be 'device' or 'host'")
+    if X0.shape[1] % 2 or X0.shape[1] < 2:
+        raise ValueError("need an even number of walkers")
+    rng = np.random.default_rng() if rng is None else rng
+    seeds = rng.integers(0, 2**63, size=2)
+    acc_b = 0.0
+    if nburnin > 0:                                                        # burn-in: nothing stored, nothing copied back
+        _, _, X0, _, acc_b = ds.mcmc_run(X0, nburnin, 1, a_scale, int(seeds[0]), store=False)
+    chain, lps, _, _, acc = ds.mcmc_run(X0, nsteps, nthin, a_scale, int(seeds[1]), store=True)
+    tot = nburnin + nsteps
+    return chain, lps, (acc_b * nburnin + acc * nsteps) / tot if tot else 0.0
 
 
 # ---------------------------------------------------------------------------------------------

@@ -109,16 +109,47 @@ def test_mcmc_sample_shapes_and_oracle_chain(S, V):              # basic_linear_
     data = rng.poisson(sum(c * m for c, m in zip(x, models))).astype(np.int64)
     sm, sd = S.stack_models(models), data.reshape(-1, order="F")
     x0 = np.maximum(0.0, x[:, None] + rng.standard_normal((N, nwalkers)))
-    chain, lps, acc = V.mcmc_sample(sm, sd, x0, nsteps, rng=np.random.default_rng(11))
-    assert chain.shape == (nsteps, N, nwalkers) and chain.dtype == np.float64 and 0.05 < acc < 0.95
-    assert np.all(chain >= 0)                                         # negative proposals are rejected (-Inf)
-    # the same sampler driven by the oracle log-likelihood, same RNG: identical accept/reject decisions
+    for engine in ("host", "device"):
+        chain, lps, acc = V.mcmc_sample(sm, sd, x0, nsteps, rng=np.random.default_rng(11), engine=engine)
+        assert chain.shape == (nsteps, N, nwalkers) and chain.dtype == np.float64 and 0.05 < acc < 0.95
+        assert lps.shape == (nsteps, nwalkers)
+        assert np.all(chain >= 0)                                     # negative proposals are rejected (-Inf)
+    # the host-engine sampler driven by the oracle log-likelihood, same RNG: identical accept/reject decisions
+    chain, lps, acc = V.mcmc_sample(sm, sd, x0, nsteps, rng=np.random.default_rng(11), engine="host")
     ref, lps_o, acc_o = V.stretch_move_ensemble(lambda X: O.mcmc_logl(X, sm, sd), x0, nsteps, rng=np.random.default_rng(11))
     assert acc == acc_o and np.allclose(chain, ref, rtol=1e-12, atol=0) and np.allclose(lps, lps_o, rtol=1e-11)
     # posterior mean close to the MLE
     burn = V.mcmc_sample(sm, sd, x0, 300, nburnin=200, rng=np.random.default_rng(12))[0]
     mle = V.fit_templates_lbfgsb(sm, sd, x0=np.ones(N))[1]
     assert np.allclose(burn.mean(axis=(0, 2)), mle, rtol=0.05, atol=0.5)
+
+
+@pytest.mark.parametrize("nb,nt,W,nsteps,nthin,dtype", [(900, 10, 100, 25, 1, np.float64), (2500, 37, 64, 12, 3, np.float64),
+                                                         (1600, 20, 48, 10, 2, np.float32)])
+def test_device_ensemble_sampler_matches_host_restatement(S, nb, nt, W, nsteps, nthin, dtype):
+    """sfh_mcmc_run (proposal + K6 + accept on the device) == the same algorithm on the host with the same Philox
+    streams and the CPU oracle's MCMCModel (mcmc_sample.jl:12-23): identical accept/reject decisions, same chain."""
+    from ensemble_ref import stretch_move_reference
+    M, x, data = make_flat_problem(nb, nt, seed=101, dtype=dtype)
+    rng = np.random.default_rng(4)
+    X0 = np.maximum(0.0, x[:, None] + rng.standard_normal((nt, W)))   # some walkers sit at exactly 0; proposals go negative
+    ds = S.DeviceStack(M, data)
+    chain, lps, Xf, lf, acc = ds.mcmc_run(X0, nsteps, nthin, 2.0, seed=0x1234ABCD5678)
+    Md, dd = M.astype(np.float64), data.astype(np.float64)
+    rc, rl, rX, rlp, racc = stretch_move_reference(lambda X: O.mcmc_logl(X, Md, dd), X0, nsteps, nthin, 2.0, seed=0x1234ABCD5678)
+    assert chain.shape == (nsteps // nthin, nt, W) and lps.shape == (nsteps // nthin, W)
+    tol = 1e-11 if dtype == np.float64 else 1e-6
+    if dtype == np.float64:
+        assert acc == racc and np.allclose(chain, rc, rtol=1e-12, atol=0) and np.allclose(Xf, rX, rtol=1e-12, atol=0)
+        assert np.allclose(lps, rl, rtol=tol) and np.allclose(lf, rlp, rtol=tol)
+    else:                           # F32 storage: logL agrees to 1e-6, so a rare decision may flip; compare the first steps
+        assert abs(acc - racc) < 0.05 and np.allclose(lps[0], rl[0], rtol=1e-5)
+    assert np.all(chain >= 0) and 0.02 < acc < 0.98
+    # nothing stored: same final state
+    _, _, Xf2, lf2, acc2 = ds.mcmc_run(X0, nsteps, nthin, 2.0, seed=0x1234ABCD5678, store=False)
+    assert np.array_equal(Xf2, Xf) and np.array_equal(lf2, lf) and acc2 == acc
+    with pytest.raises(ValueError):
+        ds.mcmc_run(X0[:, :5], 3)                                     # odd number of walkers
 
 
 def test_hmc_sample_shapes_and_moments(S, V):                    # basic_linear_combinations.jl:156-186

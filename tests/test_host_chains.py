@@ -50,3 +50,27 @@ def test_chains_of_different_length_and_errors():
         raise RuntimeError("device failure")
     with pytest.raises(RuntimeError, match="device failure"):
         V.run_chains_batched(bad, [np.zeros(3)] * 2, 5, 5, 3, [np.random.default_rng(c) for c in range(2)])
+
+
+def test_philox_restatement_known_answers():
+    """The host Philox4x32-10 used to restate the device sampler reproduces the Random123 known-answer vectors."""
+    from ensemble_ref import philox4x32_10, philox_u01
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = philox4x32_10(*[np.array([v]) for v in ctr], *key)
+        assert tuple(int(v[0]) for v in got) == want
+    u = philox_u01(np.arange(200000), 987654321, 16)
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
+
+
+def test_host_restatement_of_the_ensemble_sampler_samples_a_gaussian():
+    from ensemble_ref import stretch_move_reference
+    prec = np.array([1.0, 4.0, 0.25])
+    logl = lambda X: -0.5 * np.einsum("iw,i,iw->w", X, prec, X)
+    X0 = np.random.default_rng(0).standard_normal((3, 40))
+    chain, lps, Xf, lp, acc = stretch_move_reference(logl, X0, 600, 2, 2.0, seed=77)
+    assert chain.shape == (300, 3, 40) and 0.2 < acc < 0.9
+    v = chain[100:].transpose(1, 0, 2).reshape(3, -1).var(axis=1)
+    assert np.all(np.abs(v * prec - 1) < 0.35)
