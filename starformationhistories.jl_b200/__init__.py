@@ -17,8 +17,8 @@ from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR,
                            calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams)
 from .sampling import HMCModel, MCMCModel
 from . import sharding, solvers
-from .solvers import (fit_sfh, fit_templates, fit_templates_fast, fit_templates_lbfgsb, hmc_sample, mcmc_sample, mdf_amr,
-                      renormalize_x0)
+from .solvers import (calculate_cum_sfr, construct_x0, cum_sfr_quantiles, fit_sfh, fit_templates, fit_templates_fast, fit_templates_lbfgsb,
+                      hmc_sample, mcmc_sample, mdf_amr, rand_result, renormalize_x0)
 from .sharding import allreduce_fg, guard_neg_logl, init_library_comm, shard_rows
 
 
@@ -38,4 +38,4 @@ __all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite
            "LogarithmicAMR", "GaussianDispersion", "HierarchicalOptimizer", "HMCModel", "MCMCModel", "nparams",
            "exptransform", "logtransform", "clear_cache", "device_stack", "shard_rows", "allreduce_fg", "guard_neg_logl",
            "init_library_comm", "fit_templates_lbfgsb", "fit_templates", "fit_templates_fast", "fit_sfh", "mcmc_sample",
-           "hmc_sample", "renormalize_x0", "mdf_amr"]
+           "hmc_sample", "renormalize_x0", "mdf_amr", "calculate_cum_sfr", "cum_sfr_quantiles", "rand_result", "construct_x0"]

@@ -138,6 +138,103 @@ class BFGSResult:
     MH_model: object = None
     disp_model: object = None
 
+    def rand(self, rng, n, invH=None):
+        """`rand(result, N)` (bfgs_result.jl:43-75): draws from MvNormal(minimizer, invH) in the fitting space, transformed
+        back to natural units; fixed parameters are written in at their values.  Returns (length(mu), n)."""
+        npar = self.MH_model.nparams() + self.disp_model.nparams()
+        nj = self.mu.shape[0] - npar
+        tf = np.array(list(self.MH_model.transforms()) + list(self.disp_model.transforms()))
+        free = np.array(list(self.MH_model.free_params()) + list(self.disp_model.free_params()), dtype=bool)
+        cov = np.asarray(self.invH if invH is None else invH, dtype=np.float64)
+        z = rng.multivariate_normal(np.asarray(self.result.x, dtype=np.float64), (cov + cov.T) / 2, size=n).T
+        out = np.empty((self.mu.shape[0], n))
+        out[:nj] = np.exp(z[:nj])                                          # transformations.jl:70-72
+        tfree = tf[free]
+        zp = z[nj:]
+        vals = np.where(tfree[:, None] == 1, np.exp(zp), np.where(tfree[:, None] == -1, -np.exp(zp), zp))   # :73-90
+        out[nj:][free] = vals
+        par = np.array(list(self.MH_model.fittable_params()) + list(self.disp_model.fittable_params()), dtype=np.float64)
+        out[nj:][~free] = par[~free][:, None]
+        return out
+
+
+def rand_result(result, rng, n):
+    """`rand` for either a BFGSResult or the {"map", "mle"} pair fit_sfh returns (CompositeBFGSResult,
+    bfgs_result.jl:114-150: MLE best-fit values with the MAP inverse Hessian)."""
+    if isinstance(result, dict):
+        return result["mle"].rand(rng, n, invH=result["map"].invH)
+    return result.rand(rng, n)
+
+
+def construct_x0(logAge, T_max, normalize_value=1.0):
+    """construct_x0 (fitting/utilities.jl:31-47): starting coefficients of a constant star-formation rate whose total
+    is `normalize_value`, `logAge` being left bin edges and `T_max` [Gyr] the final right edge; order-independent."""
+    la = np.asarray(logAge, dtype=np.float64)
+    max_logAge = math.log10(T_max) + 9
+    if not max_logAge > la.max():
+        raise ValueError("log10(T_max) + 9 > maximum(logAge) must hold")                # :33
+    ua, inv, cnt = np.unique(la, return_inverse=True, return_counts=True)
+    edges = np.concatenate([10.0 ** ua, [10.0 ** max_logAge]])
+    sfr = normalize_value / (10.0 ** max_logAge - 10.0 ** la.min())
+    return sfr * np.diff(edges)[inv] / cnt[inv]
+
+
+def calculate_cum_sfr(coeffs, logAge, MH, T_max, normalize_value=1, sorted=False):
+    """calculate_cum_sfr (fitting/utilities.jl:153-195): (unique_logAge ascending, cumulative SFH normalised to 1 at the
+    youngest bin, SFR per bin with `logAge` as left edges and `T_max` [Gyr] the last right edge, mass-weighted <[M/H]>)."""
+    c = np.asarray(coeffs, dtype=np.float64) * normalize_value
+    la = np.asarray(logAge, dtype=np.float64)
+    mh = np.asarray(MH, dtype=np.float64)
+    if not (c.shape == la.shape == mh.shape):
+        raise ValueError("axes(coeffs) == axes(logAge) == axes(MH) must hold")          # :154
+    max_logAge = math.log10(T_max) + 9
+    if not max_logAge > la.max():
+        raise ValueError("log10(T_max) + 9 > maximum(logAge) must hold")                # :155
+    mtot = c.sum()
+    if not sorted:
+        idx = np.argsort(la, kind="stable")
+        la, c, mh = la[idx], c[idx], mh[idx]
+    ua, inv = np.unique(la, return_inverse=True)
+    dt = np.diff(np.concatenate([10.0 ** ua, [10.0 ** max_logAge]]))
+    mstar = np.bincount(inv, weights=c, minlength=ua.shape[0])
+    wsum = np.bincount(inv, weights=c * mh, minlength=ua.shape[0])
+    cnt = np.bincount(inv, minlength=ua.shape[0])
+    plain = np.bincount(inv, weights=mh, minlength=ua.shape[0]) / cnt
+    mean_mh = np.empty(ua.shape[0])
+    for i in range(ua.shape[0]):                                                      # :176-188
+        if mstar[i] == 0:
+            mean_mh[i] = plain[i] if i == 0 else mean_mh[i - 1]
+        else:
+            mean_mh[i] = wsum[i] / mstar[i]
+    cum = np.cumsum(mstar[::-1])[::-1] / mtot
+    return ua, cum, mstar / dt, mean_mh
+
+
+def cum_sfr_quantiles(result, logAge, MH, T_max, Nsamples, q, rng=None, **kws):
+    """cum_sfr_quantiles (fitting/utilities.jl:239-302): draw `Nsamples` SFHs from a fit_sfh result, expand each with
+    calculate_coeffs, and return per-age quantiles `q` of the cumulative SFH, the SFR and <[M/H]> plus the draws.
+    Samples whose coefficients are not all finite are dropped, as in the reference (:267-270)."""
+    rng = np.random.default_rng() if rng is None else rng
+    best = result["mle"] if isinstance(result, dict) else result
+    samples = rand_result(result, rng, int(Nsamples))
+    npm, npd = best.MH_model.nparams(), best.disp_model.nparams()
+    nj = samples.shape[0] - npm - npd
+    la, mh = np.asarray(logAge, dtype=np.float64), np.asarray(MH, dtype=np.float64)
+    rows = []
+    for i in range(samples.shape[1]):
+        r = samples[:, i]
+        mm = best.MH_model.update_params(r[nj:nj + npm])
+        dm = best.disp_model.update_params(r[nj + npm:])
+        with np.errstate(all="ignore"):
+            co = calculate_coeffs(mm, dm, r[:nj], la, mh)
+        if not np.all(np.isfinite(co)):
+            continue
+        rows.append(calculate_cum_sfr(co, la, mh, T_max, **kws)[1:])
+    qq = np.atleast_1d(np.asarray(q, dtype=np.float64))
+    stack = [np.array([row[k] for row in rows]) for k in range(3)]        # each (ngood, Nj)
+    cum_q, sfr_q, mh_q = (np.quantile(a, qq, axis=0).T for a in stack)
+    return {"cum_sfh": cum_q, "sfrs": sfr_q, "mean_mh": mh_q, "samples": samples, "n_good": len(rows)}
+
 
 def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000):
     """BFGS on [log R_j, transformed free parameters]: MAP (Jacobian corrections on) then MLE seeded from it

@@ -1,0 +1,71 @@
+"""Host-side helpers either side of the hot path, pinned by the reference's own golden values
+(test/fitting/fitting_core_test.jl:196-247).  No device needed."""
+import types
+
+import numpy as np
+import pytest
+
+import sfh_b200 as S
+from sfh_b200 import solvers as V
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_construct_x0_golden(T):                                   # fitting_core_test.jl:196-212
+    rtol = 1e-3 if T == np.float32 else 1e-7
+    want = np.tile([0.015015015015015015, 0.15015015015015015, 1.5015015015015016], 3)
+    la = np.tile(np.array([1, 2, 3], dtype=T), 3)
+    got = S.construct_x0(la, 1e-5, normalize_value=5)
+    assert np.allclose(got, want, rtol=rtol) and got.sum() == pytest.approx(5, rel=rtol)
+    got = S.construct_x0(la[::-1], 1e-5, normalize_value=5)       # no sorting assumed
+    assert np.allclose(got, want[::-1], rtol=rtol) and got.sum() == pytest.approx(5, rel=rtol)
+    with pytest.raises(ValueError):
+        S.construct_x0(la, 1e-9)
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_calculate_cum_sfr_golden(T):                              # fitting_core_test.jl:213-247
+    coeffs, la, mh = np.array([1, 2, 2, 4], T), np.array([1, 2, 1, 2], T), np.array([-2, -2, -1, -1], T)
+    r = S.calculate_cum_sfr(coeffs, la, mh, 1e-6, normalize_value=1, sorted=False)
+    assert np.array_equal(r[0], [1, 2]) and np.allclose(r[1], [1, 2 / 3]) and np.allclose(r[2], [1 / 30, 2 / 300])
+    assert np.allclose(r[3], [-4 / 3, -4 / 3])
+    r = S.calculate_cum_sfr(coeffs, la, mh, 1e-6, normalize_value=5)
+    assert np.allclose(r[1], [1, 2 / 3]) and np.allclose(r[2], [5 / 30, 10 / 300]) and np.allclose(r[3], [-4 / 3, -4 / 3])
+    r = S.calculate_cum_sfr(coeffs, np.array([1, 1, 2, 2], T), np.array([-2, -1, -2, -1], T), 1e-6, sorted=True)
+    assert np.array_equal(r[0], [1, 2]) and np.allclose(r[1], [1, 2 / 3]) and np.allclose(r[2], [1 / 30, 2 / 300])
+    assert np.allclose(r[3], [-4 / 3, -4 / 3])
+    # an age bin with zero mass inherits the previous bin's mean metallicity (utilities.jl:178-184)
+    r = S.calculate_cum_sfr(np.array([1.0, 3.0, 0.0, 0.0]), np.array([1.0, 1.0, 2.0, 2.0]), np.array([-2.0, -1.0, -2.0, -1.0]), 1e-6)
+    assert np.allclose(r[3], [-1.25, -1.25]) and np.allclose(r[1], [1.0, 0.0])
+
+
+def _fake_result(nj, rng, free=(True, True), dfree=(True,)):
+    mz, dp = S.PowerLawMZR(1.0, -1.5, 6.0, free), S.GaussianDispersion(0.2, dfree)
+    R = rng.random(nj) * 1e5 + 1e4
+    nfree = sum(free) + sum(dfree)
+    x = np.concatenate([np.log(R), S.logtransform(np.array([1.0, -1.5, 0.2]), np.array([1, 0, 1]))[np.array(free + dfree)]])
+    A = rng.standard_normal((nj + nfree, nj + nfree)) * 0.02
+    invH = A @ A.T + 1e-4 * np.eye(nj + nfree)
+    mu = np.concatenate([R, [1.0, -1.5, 0.2]])
+    return V.BFGSResult(mu, np.sqrt(np.diag(invH))[:nj + 3] if nfree == 3 else np.zeros(nj + 3), invH,
+                        types.SimpleNamespace(x=x), mz, dp)
+
+
+def test_rand_and_cum_sfr_quantiles_shapes():                      # utilities.jl:239-302 (doctest shapes :226-236)
+    rng = np.random.default_rng(3)
+    nj, nk = 12, 9
+    la = np.repeat(np.linspace(10.0, 8.9, nj), nk)
+    mh = np.tile(np.linspace(-2.0, 0.0, nk), nj)
+    res = _fake_result(nj, rng)
+    smp = res.rand(rng, 500)
+    assert smp.shape == (nj + 3, 500) and np.all(smp[:nj] > 0) and np.all(smp[nj] > 0) and np.all(smp[-1] > 0)
+    assert np.allclose(np.median(smp, axis=1), res.mu, rtol=0.1)
+    q = (0.16, 0.5, 0.84)
+    out = S.cum_sfr_quantiles({"map": res, "mle": res}, la, mh, 13.7, 400, q, rng=rng)
+    for k in ("cum_sfh", "sfrs", "mean_mh"):
+        assert out[k].shape == (nj, 3) and np.all(np.diff(out[k], axis=1) >= 0)
+    assert out["samples"].shape == (nj + 3, 400) and out["n_good"] == 400
+    assert np.allclose(out["cum_sfh"][0], 1.0) and np.all(np.diff(out["cum_sfh"][:, 1]) <= 1e-12)
+    # a fixed parameter is written in at its value for every draw (bfgs_result.jl:68-74)
+    resf = _fake_result(nj, rng, free=(True, False), dfree=(False,))
+    smp = resf.rand(rng, 50)
+    assert np.all(smp[nj + 1] == -1.5) and np.all(smp[nj + 2] == 0.2) and np.all(smp[nj] > 0)
