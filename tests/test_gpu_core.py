@@ -202,6 +202,44 @@ def test_fg_parity_f32_storage(S, nb, nt):
     assert isinstance(S.fg_(True, None, x, ds, data), np.float32)   # returned scalar typed like the stack
 
 
+def test_f32_special_values(S):
+    """F32 storage widens exactly: zeros, negative values, subnormals and FLT_MAX/FLT_MIN come out bit for bit, the fused
+    and two-pass paths agree, and Inf/NaN templates propagate like the reference's arithmetic."""
+    nb, nt = 3000, 300
+    M, x, data = make_flat_problem(nb, nt, seed=5, dtype=np.float32)
+    rng = np.random.default_rng(8)
+    M[rng.random(M.shape) < 0.3] = 0.0                                   # Hess templates are mostly empty
+    M[rng.random(M.shape) < 0.05] *= -1.0                                # sign bit
+    sub = rng.random(M.shape) < 0.02
+    M[sub] = (rng.integers(1, 1 << 23, size=int(sub.sum())).astype(np.uint32)).view(np.float32)   # subnormals
+    M[0, 0] = np.float32(np.finfo(np.float32).max); M[1, 1] = np.float32(np.finfo(np.float32).tiny)
+    ds = S.DeviceStack(M, data)
+    assert ds.info().fused == 1
+    x = x * 1e-3
+    x[0] = 1e-30                                                          # keeps FLT_MAX * x finite
+    nl, G, comp = ds.eval_fg(x, want_composite=True)
+    ds2 = S.DeviceStack(M, data, force_unfused=True)
+    nl2, G2, _ = ds2.eval_fg(x)
+    nlq, Gq, gs = O.fg_quad_f32(x, M, data)
+    assert nl == pytest.approx(nlq, rel=RTOL_F32) and nl == pytest.approx(nl2, rel=1e-12)
+    assert_grad_close(G, Gq, gs, rtol=RTOL_F32)
+    assert np.all(np.abs(G - G2) <= 1e-11 * np.maximum(np.abs(G2), 1e-3 * np.abs(G2).max()))
+    # exact F32 -> F64 widening: a one-hot coefficient vector returns the stored column bit for bit (composite = M[:, j] * 1)
+    for j in (0, 1, 17):
+        e = np.zeros(nt); e[j] = 1.0
+        c = np.empty(nb)
+        S.composite_(c, e, ds)
+        assert np.array_equal(c, M[:, j].astype(np.float64))
+    # Inf / NaN templates propagate exactly like the reference's arithmetic
+    for bad in (np.inf, np.nan):
+        Mb = M.copy(); Mb[7, 3] = bad
+        db = S.DeviceStack(Mb, data)
+        nlb, Gb, _ = db.eval_fg(np.abs(x) + 1.0)
+        nlo, Go, _ = O.fg(np.abs(x) + 1.0, Mb.astype(np.float64), data.astype(np.float64))
+        assert (np.isnan(nlb) and np.isnan(nlo)) or nlb == pytest.approx(nlo, rel=1e-5)
+        assert np.array_equal(np.isnan(Gb), np.isnan(Go))
+
+
 # ------------------------------------------------------------------ semantics the reference fixes (SURVEY 8a checklist)
 def test_edge_semantics(S):
     eps = np.finfo(np.float64).eps
