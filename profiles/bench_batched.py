@@ -59,6 +59,8 @@ def run_mcmc_engines(nb=40000, nt=500, W=1024, nsteps=20):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mcmc":
         run_mcmc_engines(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "k6":
+        run(40000, 500, 1024); run(40000, 500, 512); run(60000, 2400, 256); sys.exit(0)
     ds, X, got = run(40000, 500, 1024)
     # spot parity of 3 walkers against the fused single-vector path
     for w in (0, 511, 1023):

@@ -1119,7 +1119,13 @@ int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_log
                 sfh_batched_logl_kernel<float><<<(unsigned)(nbt * nwt), kBwThreads, 0, c->stream>>>((const float *)s->dM, bp);
         } else {
             // walker-tile width: 128 for ensembles, 8 / 16 / 32 / 64 for the few-chain batches of sfh_eval_fg_batched
-            const int bn = (W > 64) ? 128 : (W > 32 ? 64 : (W > 16 ? 32 : (W > 8 ? 16 : 8)));
+            // 32-wide tiles (4 warps, 3 CTAs/SM) are never slower than the 64/128-wide ones on B200 and up to 14 % faster
+            // (profiles/r1_experiments.md); the wide shapes stay reachable through SFH_BATCHED_BN.
+            int bn = (W > 16) ? 32 : (W > 8 ? 16 : 8);
+            if (const char *e = getenv("SFH_BATCHED_BN")) {   // experiment knob: force the walker-tile width
+                const int v = atoi(e);
+                if (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) bn = v;
+            }
             const int64_t nwt_v = (W + bn - 1) / bn;
             const unsigned grid = (unsigned)(nbt * nwt_v);
 #define SFH_LAUNCH_MMA(S_, WN_, NBW_)                                                                                  \

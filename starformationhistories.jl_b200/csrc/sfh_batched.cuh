@@ -156,7 +156,13 @@ __global__ void __launch_bounds__(kBwThreads) sfh_batched_logl_kernel(const S *_
 // WN = warps along the walker axis, NBW = 8-walker MMA blocks per warp: CTA tile = 128 bins x 8*NBW*WN walkers, 4*WN warps.
 // (WN, NBW) = (4, 4) for walker ensembles; (1, 1) / (1, 2) / (1, 4) / (2, 4) for the 8 / 16 / 32 / 64-chain batches of
 // sfh_eval_fg_batched (a 128-wide tile would waste up to 16x the math and make a few-chain pass compute-bound).
-constexpr int kMmaBM = 128, kMmaBK = 16, kMmaStages = 3;
+#ifndef SFH_MMA_STAGES
+#define SFH_MMA_STAGES 3
+#endif
+#ifndef SFH_MMA_BK
+#define SFH_MMA_BK 16
+#endif
+constexpr int kMmaBM = 128, kMmaBK = SFH_MMA_BK, kMmaStages = SFH_MMA_STAGES;
 constexpr int kMmaBN = 128, kMmaThreads = 512;  // the (4, 4) shape (host-side grid arithmetic of the walker path)
 constexpr int kMmaLdA = kMmaBM + 4;  // doubles; stride = 4 (mod 16) => 16 distinct bank pairs
 template <typename S>
