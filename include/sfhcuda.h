@@ -159,6 +159,20 @@ int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_k
                      const double *variables, const uint8_t *free_mask,
                      double *neg_logL, double *G);
 
+/* ---- template construction on the device --------------------------------------
+ * Builds the stack from ragged per-template point lists instead of uploading host-built Hess diagrams: template t
+ * is bin_cmd_smooth (src/StarFormationHistories.jl:574-621) of the points [offsets[t], offsets[t+1]) -- one addstar!
+ * (:348-408) per point with the GaussianPSFAsymmetric (cov_mult[t] == 0, :223-266) or GaussianPSFCovariant
+ * (cov_mult[t] == +-1, :272-338) kernel -- on a Hess diagram of nx x ny uniform bins whose first left edges are
+ * xfirst / yfirst and widths xstep / ystep (> 0).  Bin (ix, iy) is stack row ix + nx*iy (vec of the column-major
+ * weights matrix, fitting/utilities.jl:12-13).  colors/mags/color_err/mag_err/weights hold offsets[ntemplates]
+ * entries.  data (nullable: zeros) has nx*ny entries.                                                         */
+int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t ny, double xfirst, double xstep,
+                                 double yfirst, double ystep, int64_t ntemplates, const int64_t *offsets,
+                                 const double *colors, const double *mags, const double *color_err,
+                                 const double *mag_err, const double *weights, const int32_t *cov_mult,
+                                 int dtype, const void *data, int data_dtype, const sfh_opts *opts);
+
 /* ---- batched walkers (new; per-walker semantics of MCMCModel, fitting/mcmc_sample.jl:12-23) -- */
 /* X: ntemplates x W column-major.  logL[w] = -Inf if any X[:,w] < 0 (:15-19) else
  * loglikelihood(M*X[:,w], data).                                                               */

@@ -92,6 +92,12 @@ def _declare(L):
     L.sfho_fg_hier_quad.argtypes = [C.c_int, PD, C.c_int, PD, pint, PD, i64, PD, PD, i64, PD, PD, i64, PD]
     L.sfho_fg_hier_quad.restype = dbl
     L.sfho_mcmc_logl_f64.argtypes = [PD, i64, PD, PD, i64, i64, PD]
+    L.sfho_bin_cmd_smooth.argtypes = [i64, PD, PD, PD, PD, PD, C.c_int, i64, dbl, dbl, i64, dbl, dbl, PD]
+    L.sfho_bin_cmd_smooth.restype = None
+    L.sfho_gaussian_int_general.argtypes = [dbl] * 7
+    L.sfho_gaussian_int_general.restype = dbl
+    L.sfho_gaussian_psf_covariant.argtypes = [dbl] * 10
+    L.sfho_gaussian_psf_covariant.restype = dbl
     L.sfho_mcmc_logl_f64.restype = None
     L.sfho_num_threads.restype = C.c_int
 
@@ -337,3 +343,25 @@ def mcmc_logl(X, M, data):
     D = C.c_double
     lib().sfho_mcmc_logl_f64(_p(X, D), X.shape[1], _p(M, D), _p(d, D), nb, nt, _p(out, D))
     return out
+
+
+def bin_cmd_smooth(colors, mags, color_err, mag_err, cov_mult, weights, nx, xfirst, xstep, ny, yfirst, ystep, out=None):
+    """bin_cmd_smooth (src/StarFormationHistories.jl:574-621) onto nx x ny uniform bins; returns the (nx, ny) weights matrix."""
+    L = lib()
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (colors, mags, color_err, mag_err, weights)]
+    n = a[0].shape[0]
+    if any(v.shape != (n,) for v in a):
+        raise ValueError("axes(colors) == axes(mags) == axes(color_err) == axes(mag_err) == axes(weights) must hold")
+    img = np.zeros((nx, ny), order="F") if out is None else out
+    PD = C.POINTER(C.c_double)
+    L.sfho_bin_cmd_smooth(n, *[v.ctypes.data_as(PD) for v in a], int(cov_mult), nx, float(xfirst), float(xstep), ny, float(yfirst),
+                          float(ystep), img.ctypes.data_as(PD))
+    return img
+
+
+def gaussian_int_general(dx, dy, hx, hy, sx, sy, A):
+    return lib().sfho_gaussian_int_general(dx, dy, hx, hy, sx, sy, A)
+
+
+def gaussian_psf_covariant(x, y, hx, hy, x0, y0, sx, sy, cov_mult, A):
+    return lib().sfho_gaussian_psf_covariant(x, y, hx, hy, x0, y0, sx, sy, cov_mult, A)

@@ -271,3 +271,83 @@ int sfho_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Template construction: bin_cmd_smooth (src/StarFormationHistories.jl:574-621) = one addstar! per point
+ * (:348-364 pixel-space kernel, :366-408 real-space kernel) of
+ *   cov_mult == 0 : GaussianPSFAsymmetric (:223-266), exact pixel integral gaussian_int_general (:198-205)
+ *   cov_mult == +-1: GaussianPSFCovariant (:272-338), 3-point Gauss-Legendre in y x erf in x (:303-333)
+ * onto a Hess diagram with uniform bins: nx bins from xfirst with width xstep (edges[1] is a range of nx+1
+ * edges), likewise y.  out is the nx x ny column-major matrix (Histogram.weights), ACCUMULATED into, points in
+ * order -- the order of the reference's loop (:585, :611), so the per-pixel sums associate identically.
+ * Julia's round(Int, x) is round-half-even = rint() in the default rounding mode.
+ * ---------------------------------------------------------------------------------------------- */
+static inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
+static inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
+
+/* gaussian_int_general, Float64 method (:198-205), B = 0 */
+double sfho_gaussian_int_general(double dx, double dy, double hx, double hy, double sx, double sy, double A)
+{
+    const double s2 = sqrt(2.0);
+    return A / 4 * (erf((dx - hx) / (s2 * sx)) - erf((dx + hx) / (s2 * sx))) *
+                   (erf((dy - hy) / (s2 * sy)) - erf((dy + hy) / (s2 * sy)));
+}
+
+/* gaussian_psf_covariant (:315-333), B = 0 */
+double sfho_gaussian_psf_covariant(double x, double y, double hx, double hy, double x0, double y0, double sx, double sy,
+                                   double cov_mult, double A)
+{
+    static const double gx[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};   /* :303 */
+    static const double gw[3] = {0.5555555555555556, 0.8888888888888888, 0.5555555555555556};   /* :304 */
+    const double dx = x - x0;
+    const double prefac = A / 2 / sqrt(2.0 * M_PI) / sy;
+    const double s2 = sqrt(2.0);
+    double result = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        const double yv = gx[i] * hy + y, yw = gw[i] * hy;
+        const double Dy = yv - y0;
+        const double Dx = dx + Dy * cov_mult;
+        const double q = Dy / sy;
+        result += yw * exp(-(q * q) / 2) * (erf((Dx + hx) / s2 / sx) + erf((-Dx + hx) / s2 / sx));
+    }
+    return result * prefac;
+}
+
+void sfho_bin_cmd_smooth(int64_t n, const double *colors, const double *mags, const double *color_err, const double *mag_err,
+                         const double *weights, int cov_mult, int64_t nx, double xfirst, double xstep, int64_t ny,
+                         double yfirst, double ystep, double *out)
+{
+    for (int64_t p = 0; p < n; ++p) {
+        if (cov_mult == 0) {                                   /* :584-609 */
+            const double x0 = (colors[p] - xfirst) / xstep + 1;   /* histogram_pix, 1-based (:503) */
+            const double y0 = (mags[p] - yfirst) / ystep + 1;
+            const double sx = color_err[p] / xstep, sy = mag_err[p] / ystep;
+            const int64_t cx = (int64_t)ceil(sx * 10), cy = (int64_t)ceil(sy * 10);   /* size(obj) (:247) */
+            const int64_t x = (int64_t)rint(x0), y = (int64_t)rint(y0);               /* :350 */
+            const int64_t xo = i64max(1, cx / 2), yo = i64max(1, cy / 2);
+            const int64_t xa = i64max(1, x - xo), xb = i64min(nx, x + xo);
+            const int64_t ya = i64max(1, y - yo), yb = i64min(ny, y + yo);
+            if (xb - xa + 1 > 1 && yb - ya + 1 > 1)            /* :358 */
+                for (int64_t j = ya; j <= yb; ++j)
+                    for (int64_t i = xa; i <= xb; ++i)
+                        out[(i - 1) + nx * (j - 1)] +=
+                            sfho_gaussian_int_general(i + 0.5 - x0, j + 0.5 - y0, 0.5, 0.5, sx, sy, weights[p]);
+        } else {                                               /* :610-618, addstar! :366-408 */
+            const double xr = colors[p], yr = mags[p], sx = color_err[p], sy = mag_err[p];
+            const int64_t xp = (int64_t)rint((xr - xfirst) / xstep + 1), yp = (int64_t)rint((yr - yfirst) / ystep + 1);
+            const int64_t xo = i64max(1, (int64_t)rint(15 * sx / xstep / 2));   /* size(obj) = (15 sx, 10 sy) (:296) */
+            const int64_t yo = i64max(1, (int64_t)rint(10 * sy / ystep / 2));
+            const int64_t xa = i64max(1, xp - xo), xb = i64min(nx, xp + xo);
+            const int64_t ya = i64max(1, yp - yo), yb = i64min(ny, yp + yo);
+            if (xb - xa + 1 > 1 && yb - ya + 1 > 1) {          /* :399 */
+                /* pixel midpoints in data space: histogram_data(i + 1/2) = (i - 1/2) step + first (:525); the half
+                 * steps of those ranges are step/2 (:391) */
+                const double hx = xstep / 2, hy = ystep / 2;
+                for (int64_t j = ya; j <= yb; ++j)
+                    for (int64_t i = xa; i <= xb; ++i)
+                        out[(i - 1) + nx * (j - 1)] += sfho_gaussian_psf_covariant(
+                            (i - 0.5) * xstep + xfirst, (j - 0.5) * ystep + yfirst, hx, hy, xr, yr, sx, sy, (double)cov_mult, weights[p]);
+            }
+        }
+    }
+}

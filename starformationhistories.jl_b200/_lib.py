@@ -57,6 +57,8 @@ PROTOTYPES = {
     "sfh_device_count": (_int, [C.POINTER(_int)]),
     "sfh_stack_create": (_int, [C.POINTER(_vp), _vp, _i64, _i64, _int, _vp, _int, C.POINTER(sfh_opts)]),
     "sfh_stack_create_synthetic": (_int, [C.POINTER(_vp), _i64, _i64, _int, C.c_uint64, C.c_double, _dp, C.POINTER(sfh_opts)]),
+    "sfh_stack_create_from_points": (_int, [C.POINTER(_vp), _i64, _i64, C.c_double, C.c_double, C.c_double, C.c_double, _i64,
+                                           C.POINTER(_i64), _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32), _int, _vp, _int, C.POINTER(sfh_opts)]),
     "sfh_stack_destroy": (_int, [_vp]),
     "sfh_stack_info": (_int, [_vp, C.POINTER(sfh_info)]),
     "sfh_stack_set_data": (_int, [_vp, _vp, _int]),

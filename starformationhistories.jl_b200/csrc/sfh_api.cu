@@ -23,6 +23,7 @@
 #include "sfh_fused.cuh"
 #include "sfh_small.cuh"
 #include "sfh_ensemble.cuh"
+#include "sfh_templates.cuh"
 
 using namespace sfh;
 
@@ -1444,6 +1445,82 @@ extern "C" int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_
         return SFH_OK;
     }();
     sfh_ctx_destroy(c);
+    return done(st);
+}
+
+// Template stack built on the device from ragged per-template point lists (see sfh_templates.cuh).
+extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t ny, double xfirst, double xstep, double yfirst,
+                                            double ystep, int64_t ntemplates, const int64_t *offsets, const double *colors,
+                                            const double *mags, const double *color_err, const double *mag_err,
+                                            const double *weights, const int32_t *cov_mult, int dtype, const void *data,
+                                            int data_dtype, const sfh_opts *opts) {
+    if (!out || !offsets || !cov_mult) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    if (nx < 2 || ny < 2 || ntemplates < 0) return fail(SFH_ERR_SHAPE, "need at least 2 x 2 Hess bins (got %lld x %lld)", (long long)nx, (long long)ny);
+    if (!(xstep > 0.0) || !(ystep > 0.0)) return fail(SFH_ERR_INVALID_ARG, "bin widths must be positive");
+    if (data && data_dtype != SFH_F32 && data_dtype != SFH_F64 && data_dtype != SFH_I64)
+        return fail(SFH_ERR_INVALID_ARG, "bad data dtype %d", data_dtype);
+    if (offsets[0] != 0) return fail(SFH_ERR_INVALID_ARG, "offsets[0] must be 0");
+    for (int64_t t = 0; t < ntemplates; ++t) {
+        if (offsets[t + 1] < offsets[t]) return fail(SFH_ERR_INVALID_ARG, "offsets must be non-decreasing");
+        if (cov_mult[t] < -1 || cov_mult[t] > 1) return fail(SFH_ERR_INVALID_ARG, "cov_mult must be -1, 0 or 1");   // :579
+    }
+    const int64_t npts = offsets[ntemplates];
+    if (npts > 0 && (!colors || !mags || !color_err || !mag_err || !weights)) return fail(SFH_ERR_INVALID_ARG, "NULL point array");
+    sfh_stack *s = new (std::nothrow) sfh_stack();
+    if (!s) return fail(SFH_ERR_OOM, "host allocation failed");
+    const int64_t nbins = nx * ny;
+    int st = stack_common_init(s, nbins, ntemplates, dtype, opts);
+    auto done = [&](int code) { if (code != SFH_OK) sfh_stack_destroy(s); else *out = s; return code; };
+    if (st != SFH_OK) return done(st);
+    st = [&]() -> int {
+        if (s->rows == 0 || s->nt == 0) return SFH_OK;
+        DevBufs bufs;
+        int64_t *d_off = nullptr; int32_t *d_cov = nullptr; double *d_pts = nullptr, *d_scr = nullptr;
+        CU_TRY(bufs.alloc(&d_off, (size_t)(ntemplates + 1) * 8));
+        CU_TRY(bufs.alloc(&d_cov, (size_t)ntemplates * 4));
+        CU_TRY(bufs.alloc(&d_pts, (size_t)npts * 5 * 8));
+        CU_TRY(cudaMemcpy(d_off, offsets, (size_t)(ntemplates + 1) * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_cov, cov_mult, (size_t)ntemplates * 4, cudaMemcpyHostToDevice));
+        const double *src[5] = {colors, mags, color_err, mag_err, weights};
+        for (int a = 0; a < 5 && npts > 0; ++a)
+            CU_TRY(cudaMemcpy(d_pts + (size_t)a * npts, src[a], (size_t)npts * 8, cudaMemcpyHostToDevice));
+        const int64_t tc_max = std::max<int64_t>(1, std::min<int64_t>(ntemplates, ((int64_t)256 << 20) / (nbins * 8)));
+        CU_TRY(bufs.alloc(&d_scr, (size_t)tc_max * nbins * 8));
+        ScatterParams sp{};
+        sp.nx = nx; sp.ny = ny; sp.xfirst = xfirst; sp.xstep = xstep; sp.yfirst = yfirst; sp.ystep = ystep;
+        sp.offsets = d_off; sp.x = d_pts; sp.y = d_pts + npts; sp.sx = d_pts + 2 * npts; sp.sy = d_pts + 3 * npts; sp.w = d_pts + 4 * npts;
+        sp.cov = d_cov; sp.scratch = d_scr;
+        for (int64_t t0 = 0; t0 < ntemplates; t0 += tc_max) {
+            const int64_t tc = std::min(tc_max, ntemplates - t0);
+            // enough (template, band) warps to fill the machine, never more bands than rows
+            const int64_t want = (int64_t)std::max(s->sm_count, 1) * 48;
+            int64_t nbands = std::min<int64_t>(ny, std::max<int64_t>(1, (want + tc - 1) / tc));
+            const int64_t band_h = (ny + nbands - 1) / nbands;
+            nbands = (ny + band_h - 1) / band_h;
+            const size_t smem = (size_t)kScatterWarps * (size_t)(nx + band_h) * 8;
+            if (smem > (size_t)200 * 1024) return fail(SFH_ERR_SHAPE, "Hess diagram too wide for the scatter kernel (%lld x %lld)", (long long)nx, (long long)ny);
+            CU_TRY(cudaFuncSetAttribute(sfh_templates_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+            sp.t0 = t0; sp.tc = tc; sp.nbands = (int32_t)nbands; sp.band_h = (int32_t)band_h;
+            CU_TRY(cudaMemsetAsync(d_scr, 0, (size_t)tc * nbins * 8, 0));
+            const int64_t nwarps = tc * nbands;
+            sfh_templates_scatter_kernel<<<(unsigned)((nwarps + kScatterWarps - 1) / kScatterWarps), kScatterWarps * 32, smem>>>(sp);
+            CU_TRY(cudaGetLastError());
+            const int grid = std::max(s->sm_count, 1) * 8;
+            if (dtype == SFH_F64)
+                sfh_templates_store_kernel<double><<<grid, 256>>>(d_scr, (double *)s->dM, s->lay, s->rows, s->row_begin, nbins, t0, tc);
+            else
+                sfh_templates_store_kernel<float><<<grid, 256>>>(d_scr, (float *)s->dM, s->lay, s->rows, s->row_begin, nbins, t0, tc);
+            CU_TRY(cudaGetLastError());
+        }
+        CU_TRY(cudaDeviceSynchronize());
+        return SFH_OK;
+    }();
+    if (st != SFH_OK) return done(st);
+    st = setup_fused(s, opts);
+    if (st != SFH_OK) return done(st);
+    if (data) st = upload_data(s, data, data_dtype, s->row_begin);
+    else if (s->rows > 0 && cudaMemset(s->d_data, 0, (size_t)s->rows * 8) != cudaSuccess) st = fail(SFH_ERR_CUDA, "memset failed");
     return done(st);
 }
 

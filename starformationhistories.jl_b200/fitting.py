@@ -110,6 +110,66 @@ class DeviceStack:
         self.rows = self.info().row_end - self.info().row_begin
 
     @classmethod
+    def from_points(cls, edges, point_lists, data=None, dtype=np.float64, device=0, rows=None, force_unfused=False):
+        """Build the stack on the device from per-template point lists (include/sfhcuda.h: sfh_stack_create_from_points).
+
+        edges       : (xedges, yedges) uniform bin edges (what ``calculate_edges`` returns), nx+1 and ny+1 values.
+        point_lists : one ``(colors, mags, color_err, mag_err, weights, cov_mult)`` tuple per template -- the arguments
+                      ``bin_cmd_smooth`` (src/StarFormationHistories.jl:574-621) receives for that template.
+        data        : observed Hess diagram (nx, ny) or its vec; zeros if omitted."""
+        xe, ye = (np.asarray(e, dtype=np.float64) for e in edges)
+        nx, ny = xe.shape[0] - 1, ye.shape[0] - 1
+        if nx < 2 or ny < 2:
+            raise ValueError("need at least 2 x 2 Hess bins")
+        xstep, ystep = (xe[-1] - xe[0]) / nx, (ye[-1] - ye[0]) / ny
+        for e, st in ((xe, xstep), (ye, ystep)):
+            if not (st > 0 and np.allclose(np.diff(e), st, rtol=1e-9, atol=0)):
+                raise ValueError("edges must be uniform, increasing ranges")       # addstar! :372-374
+        offs = np.zeros(len(point_lists) + 1, dtype=np.int64)
+        cols = [[] for _ in range(5)]
+        cov = np.zeros(len(point_lists), dtype=np.int32)
+        for t, pl in enumerate(point_lists):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in pl[:5]]
+            if any(a.shape != arrs[0].shape for a in arrs):
+                raise ValueError("axes(colors) == axes(mags) == axes(color_err) == axes(mag_err) == axes(weights) must hold")  # :580
+            if int(pl[5]) not in (-1, 0, 1):
+                raise ValueError("cov_mult must be -1, 0 or 1")                     # :579
+            cov[t] = int(pl[5])
+            offs[t + 1] = offs[t] + arrs[0].shape[0]
+            for k in range(5):
+                cols[k].append(arrs[k])
+        flat = [np.concatenate(c) if c else np.zeros(0) for c in cols]
+        self = cls.__new__(cls)
+        dt = np.dtype(dtype)
+        self.shape = (nx * ny, len(point_lists))
+        self.dtype = dt
+        self.edges = (xe, ye)
+        o = L.sfh_opts()
+        o.struct_size = C.sizeof(L.sfh_opts)
+        o.device = device
+        if rows is not None:
+            o.row_begin, o.row_end = int(rows[0]), int(rows[1])
+        o.force_unfused = int(force_unfused)
+        d = None
+        if data is not None:
+            d = np.asarray(data).reshape(-1, order="F")
+            if d.dtype not in _DT:
+                d = d.astype(np.float64)
+            d = np.ascontiguousarray(d)
+            if d.shape[0] != nx * ny:
+                raise ValueError("axes(models,1) != axes(data,1)")
+        h = C.c_void_p()
+        i32p = C.POINTER(C.c_int32)
+        L.check(L.lib.sfh_stack_create_from_points(
+            C.byref(h), nx, ny, float(xe[0]), float(xstep), float(ye[0]), float(ystep), len(point_lists),
+            offs.ctypes.data_as(C.POINTER(C.c_int64)), *[_dp(a) for a in flat], cov.ctypes.data_as(i32p), _DT[dt],
+            d.ctypes.data_as(C.c_void_p) if d is not None else None, _DT[d.dtype] if d is not None else _DT[np.dtype(np.float64)],
+            C.byref(o)))
+        self._finish_init(h)
+        self._data_id = id(data) if data is not None else None
+        return self
+
+    @classmethod
     def synthetic(cls, nbins, ntemplates, dtype, seed, scale, x_true, device=0, rows=None, tile_bins=0, cluster=0,
                   force_unfused=False, consumer_warps=0, variant=0):
         """On-device Philox/Poisson stack (include/sfhcuda.h: sfh_stack_create_synthetic)."""
