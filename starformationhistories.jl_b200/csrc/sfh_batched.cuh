@@ -199,23 +199,45 @@ __global__ void __launch_bounds__(128 * WN, 1) sfh_batched_logl_mma_kernel(const
     const int64_t i0 = bt * kMmaBM, w0 = wt * kMmaBN;
     const int64_t nslab = (p.nt + kMmaBK - 1) / kMmaBK;
 
+    // Loader state is per-thread constant: a thread always copies the same 16-byte column piece (iv / wv) of rows
+    // kk0, kk0 + KPI, ... of every slab, and both layouts are linear in the template index (panel: off(i, k) =
+    // off(i, 0) + (k << bt_shift)), so a slab costs one multiply-add per cp.async instead of the layout arithmetic
+    // (the address chains were the top stall of the 4-warp tile: ncu "wait" 54 k samples vs 24 k math-pipe throttle).
+    constexpr int AVR = kMmaBM / EPV;                 // 16-byte pieces per A row
+    constexpr int A_KPI = kMmaThreads / AVR;          // A rows covered per pass over the threads
+    constexpr int A_NI = kMmaBK / A_KPI;
+    static_assert(kMmaThreads % AVR == 0 && kMmaBK % A_KPI == 0 && A_NI >= 1, "A loader shape");
+    constexpr int BVR = kMmaBN / 2;                   // 16-byte pieces per B row
+    constexpr int B_KPI = (kMmaThreads / BVR) < kMmaBK ? (kMmaThreads / BVR) : kMmaBK;
+    constexpr int B_NI = kMmaBK / B_KPI;
+    static_assert(kMmaThreads % BVR == 0 && kMmaBK % B_KPI == 0, "B loader shape");
+    const int a_iv = (tid % AVR) * EPV, a_kk0 = tid / AVR;
+    // rows in [nb, padded) are zero padding; a 16-byte piece never straddles a panel (bt*sizeof(S) >= 64)
+    const bool a_iok = (i0 + a_iv) < p.lay.ld;
+    const S *a_src = M + (a_iok ? p.lay.off(i0 + a_iv, 0) : 0);
+    const int64_t a_kstride = p.lay.panel ? ((int64_t)1 << p.lay.bt_shift) : p.lay.ld;
+    S *a_dst = As + (size_t)a_kk0 * kMmaLdA + a_iv;
+    const int b_wv = (tid % BVR) * 2, b_kk0 = tid / BVR;
+    const bool b_wok = (b_kk0 < kMmaBK) && (w0 + b_wv) < p.wld;   // walkers in [W, wld) hold finite junk: masked later
+    const double *b_src = p.Xt + (b_wok ? (w0 + b_wv) : 0);
+    double *b_dst = Bs + (size_t)(b_kk0 < kMmaBK ? b_kk0 : 0) * kMmaLdB + b_wv;
+
     auto issue_slab = [&](int64_t slab, int stage) {
         const int64_t k0 = slab * kMmaBK;
-        // A: BK rows of BM elements, 16 bytes per cp.async
-        constexpr int A_VEC_PER_ROW = kMmaBM / EPV;
-        for (int v = tid; v < kMmaBK * A_VEC_PER_ROW; v += kMmaThreads) {
-            const int kk = v / A_VEC_PER_ROW, iv = (v % A_VEC_PER_ROW) * EPV;
-            const int64_t k = k0 + kk, i = i0 + iv;
-            // rows in [nb, padded) are zero padding; a 16-byte piece never straddles a panel (bt*sizeof(S) >= 64)
-            const bool ok = (slab < nslab) && (k < p.nt) && (i < p.lay.ld);
-            cp_async16(As + ((size_t)stage * kMmaBK + kk) * kMmaLdA + iv, M + (ok ? p.lay.off(i, k) : 0), ok);
+        const bool live = slab < nslab;
+#pragma unroll
+        for (int n = 0; n < A_NI; ++n) {
+            const int64_t k = k0 + a_kk0 + n * A_KPI;
+            const bool ok = live && a_iok && (k < p.nt);
+            cp_async16(a_dst + ((size_t)stage * kMmaBK + n * A_KPI) * kMmaLdA, a_src + (ok ? k * a_kstride : 0), ok);
         }
-        constexpr int B_VEC_PER_ROW = kMmaBN / 2;
-        for (int v = tid; v < kMmaBK * B_VEC_PER_ROW; v += kMmaThreads) {
-            const int kk = v / B_VEC_PER_ROW, wv = (v % B_VEC_PER_ROW) * 2;
-            const int64_t k = k0 + kk, w = w0 + wv;
-            const bool ok = (slab < nslab) && (k < p.nt) && (w < p.wld);  // walkers in [W, wld) hold finite junk: masked later
-            cp_async16(Bs + ((size_t)stage * kMmaBK + kk) * kMmaLdB + wv, p.Xt + (ok ? k * p.wld + w : 0), ok);
+        if (b_kk0 < kMmaBK) {
+#pragma unroll
+            for (int n = 0; n < B_NI; ++n) {
+                const int64_t k = k0 + b_kk0 + n * B_KPI;
+                const bool ok = live && b_wok && (k < p.nt);
+                cp_async16(b_dst + ((size_t)stage * kMmaBK + n * B_KPI) * kMmaLdB, b_src + (ok ? k * p.wld : 0), ok);
+            }
         }
         cp_async_commit();
     };
@@ -228,11 +250,12 @@ __global__ void __launch_bounds__(128 * WN, 1) sfh_batched_logl_mma_kernel(const
 
     for (int s = 0; s < kMmaStages - 1; ++s) issue_slab(s, s);
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
+    int stage = 0, fill = kMmaStages - 1;   // ring positions kept as counters (no 64-bit modulo per slab)
     for (int64_t slab = 0; slab < nslab; ++slab) {
-        const int stage = (int)(slab % kMmaStages);
         cp_async_wait<kMmaStages - 2>();
         __syncthreads();  // slab `slab` has landed for everyone; the stage refilled below was consumed last iteration
-        issue_slab(slab + kMmaStages - 1, (int)((slab + kMmaStages - 1) % kMmaStages));
+        issue_slab(slab + kMmaStages - 1, fill);
+        fill = (fill + 1 == kMmaStages) ? 0 : fill + 1;
         const S *Asl = As + (size_t)stage * kMmaBK * kMmaLdA;
         const double *Bsl = Bs + (size_t)stage * kMmaBK * kMmaLdB;
 #pragma unroll
@@ -247,6 +270,7 @@ __global__ void __launch_bounds__(128 * WN, 1) sfh_batched_logl_mma_kernel(const
 #pragma unroll
                 for (int nb = 0; nb < NBW; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
         }
+        stage = (stage + 1 == kMmaStages) ? 0 : stage + 1;
     }
     cp_async_wait<0>();
 
