@@ -171,6 +171,7 @@ struct sfh_ctx {
     int32_t *d_neg = nullptr;
     // batched gradient (K6g)
     double *d_resid = nullptr, *d_bgpart = nullptr, *d_bG = nullptr;
+    LogTable *d_logtab = nullptr;   // table of the DMMA kernel's fast Poisson epilogue
     int64_t bg_cap = 0;
     int bg_nsplit = 0;
     // multi-GPU
@@ -666,7 +667,7 @@ extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
     cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx);
     cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
-    cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG);
+    cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG); cudaFree(c->d_logtab);
     cudaFree(c->d_flush);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -1083,7 +1084,30 @@ extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed,
 // batched walkers
 // ---------------------------------------------------------------------------------------------
 namespace {
+// {1/c_i, log c_i} for the 128 sub-intervals of [0.6875, 1.375) (see fast_log in sfh_batched.cuh).  log c_i is taken of
+// the ROUNDED reciprocal, so log z = log c_i + log1p(z * (1/c_i) - 1) holds for the stored pair exactly.
+const LogTable &host_log_table() {
+    static LogTable tab;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int i = 0; i < kLogTabEntries; ++i) {
+            long double c;
+            if (i < 80) c = 0.6875L + (i + 0.5L) / 256.0L;              // intervals of 2^-8 below 1
+            else if (i == 80) c = 1.0L;                                  // [1, 1 + 2^-7): r = z - 1 exactly, log c = 0
+            else c = 1.0L + (i - 80 + 0.5L) / 128.0L;                    // intervals of 2^-7 above 1
+            const double invc = (double)(1.0L / c);
+            tab.e[i].x = invc;
+            tab.e[i].y = (i == 80) ? 0.0 : (double)(-logl((long double)invc));
+        }
+    });
+    return tab;
+}
+
 int ensure_walker_capacity(sfh_ctx *c, int64_t W) {
+    if (!c->d_logtab) {
+        CU_TRY(cudaMalloc((void **)&c->d_logtab, sizeof(LogTable)));
+        CU_TRY(cudaMemcpy(c->d_logtab, &host_log_table(), sizeof(LogTable), cudaMemcpyHostToDevice));
+    }
     if (W <= c->wcap) return SFH_OK;
     const sfh_stack *s = c->s;
     cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
@@ -1110,7 +1134,7 @@ int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_log
     const int64_t nbt = (s->rows + kBwBM - 1) / kBwBM, nwt = (W + kBwBN - 1) / kBwBN;
     BatchedParams bp{};
     bp.nb = s->rows; bp.nt = s->nt; bp.W = W; bp.lay = s->lay; bp.wld = wld; bp.eps = s->eps; bp.Xt = c->d_Xt;
-    bp.data = s->d_data; bp.part = c->d_part; bp.resid = d_resid;
+    bp.data = s->d_data; bp.part = c->d_part; bp.resid = d_resid; bp.logtab = c->d_logtab;
     if (nbt > 0) {
         static const bool use_fma = [] { const char *e = getenv("SFH_BATCHED_IMPL"); return e && !strcmp(e, "fma"); }();
         if (use_fma && !d_resid) {  // v1 (FP64 FMA pipe) kept for A/B measurements

@@ -46,6 +46,7 @@ struct BatchedParams {
     const double *data;  // [nb]
     double *part;        // [n_bin_tiles][wld]
     double *resid;       // nullable: [nb_padded][wld] residual matrix 1 - n/max(m,eps) for the batched gradient (K6g)
+    const struct LogTable *logtab;   // device copy of the log table (fast Poisson epilogue of the DMMA kernel)
 };
 
 template <typename S>
@@ -163,11 +164,55 @@ __global__ void __launch_bounds__(kBwThreads) sfh_batched_logl_kernel(const S *_
 #define SFH_MMA_BK 16
 #endif
 constexpr int kMmaBM = 128, kMmaBK = SFH_MMA_BK, kMmaStages = SFH_MMA_STAGES;
+
+// ---- Poisson epilogue arithmetic -------------------------------------------------------------------------------
+// ncu (profiles/r1_experiments.md): with T = 500 the warps of the DMMA kernel spent 42 % of their stall samples in the
+// epilogue -- 46 FP64 + ~100 other instructions per (bin, walker) element for one IEEE division and one libdevice log,
+// both with slow-path branches that stop the compiler interleaving the 32 elements a thread owns.  The fast path below
+// is branch-free: reciprocal by rcp.approx + 2 Newton steps + one correction, and a table-driven log
+//     x = 2^k z,  z in [0.6875, 1.375),  c_i = centre of the i-th of 128 sub-intervals (c = 1 for the one starting at 1),
+//     log x = k ln2 + log c_i + log1p(r),  r = z / c_i - 1 (one FMA, |r| <= 2^-7), log1p by a degree-8 Taylor polynomial
+// (truncation < 2^-56 relative to r; log(1) = 0 exactly, so the `m == n everywhere -> logL = 0 -> -Inf` guard of
+// fitting_base.jl:95 is unchanged).  A thread whose inputs leave the fast path's domain (non-finite or out-of-range
+// values, negative "counts") takes the exact libdevice path for its whole tile.
+constexpr int kLogTabEntries = 128;
+struct LogTable { double2 e[kLogTabEntries]; };   // {1/c_i, log c_i}
+
+__device__ __forceinline__ double fast_recip(double m) {   // m in [eps, 1e300)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(m));
+    double e = fma(-m, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-m, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_div(double n, double m, double y /* ~1/m */) {
+    const double q = n * y;
+    return fma(fma(-q, m, n), y, q);
+}
+__device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab) {   // x normal, positive, finite
+    const long long ix = __double_as_longlong(x);
+    const long long tmp = ix - 0x3FE6000000000000LL;
+    const int i = (int)((tmp >> 45) & 127);
+    const int k = (int)(tmp >> 52);
+    const double z = __longlong_as_double(ix - (tmp & (long long)0xFFF0000000000000ULL));
+    const double2 t = tab[i];
+    const double r = fma(z, t.x, -1.0);
+    const double kd = (double)k;
+    double q = fma(r, -1.0 / 8, 1.0 / 7);
+    q = fma(r, q, -1.0 / 6);
+    q = fma(r, q, 1.0 / 5);
+    q = fma(r, q, -1.0 / 4);
+    q = fma(r, q, 1.0 / 3);
+    q = fma(r, q, -1.0 / 2);
+    const double lo = fma(r * r, q, kd * 1.9082149292705877e-10);          // ln2 = hi + lo, hi has 21 trailing zero bits
+    return fma(kd, 6.9314718036912382e-01, t.y) + (r + lo);
+}
 constexpr int kMmaBN = 128, kMmaThreads = 512;  // the (4, 4) shape (host-side grid arithmetic of the walker path)
 constexpr int kMmaLdA = kMmaBM + 4;  // doubles; stride = 4 (mod 16) => 16 distinct bank pairs
 template <typename S>
 __host__ __device__ constexpr size_t mma_smem_bytes(int bn = 128) {
-    return (size_t)kMmaStages * kMmaBK * (kMmaLdA * sizeof(S) + (bn + 4) * sizeof(double)) + 4 * bn * sizeof(double);
+    return (size_t)kMmaStages * kMmaBK * (kMmaLdA * sizeof(S) + (bn + 4) * sizeof(double)) + 4 * bn * sizeof(double) + kLogTabEntries * 16;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
@@ -184,15 +229,17 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 }
 
 template <typename S, int WN, int NBW>
-__global__ void __launch_bounds__(128 * WN, 1) sfh_batched_logl_mma_kernel(const S *__restrict__ M, const BatchedParams p) {
+__global__ void __launch_bounds__(128 * WN, WN == 1 ? 3 : 1) sfh_batched_logl_mma_kernel(const S *__restrict__ M, const BatchedParams p) {
     constexpr int kWarpN = 8 * NBW, kMmaBN = kWarpN * WN, kMmaThreads = 128 * WN, kMmaLdB = kMmaBN + 4;
     extern __shared__ __align__(16) unsigned char bsm[];
     S *As = reinterpret_cast<S *>(bsm);                                                        // [stages][BK][LdA]
     double *Bs = reinterpret_cast<double *>(bsm + (size_t)kMmaStages * kMmaBK * kMmaLdA * sizeof(S));  // [stages][BK][LdB]
     double *colsum = Bs + (size_t)kMmaStages * kMmaBK * kMmaLdB;                               // [4][BN]
+    double2 *ltab = reinterpret_cast<double2 *>(colsum + 4 * kMmaBN);                          // [128] log table
     constexpr int EPV = 16 / sizeof(S);  // A elements per 16-byte cp.async
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < kLogTabEntries; e += kMmaThreads) ltab[e] = p.logtab->e[e];
     const int wm = warp & 3, wn = warp >> 2;  // warp tile origin: bins wm*32, walkers wn*32
     const int64_t n_wt = (p.W + kMmaBN - 1) / kMmaBN;
     const int64_t bt = blockIdx.x / n_wt, wt = blockIdx.x % n_wt;  // walker tiles fastest: the M tile is shared via L2
@@ -274,27 +321,71 @@ __global__ void __launch_bounds__(128 * WN, 1) sfh_batched_logl_mma_kernel(const
     }
     cp_async_wait<0>();
 
+    __syncthreads();   // the log table is in shared memory even when there was no slab to wait for
+
     // Poisson epilogue: lane holds C[row = mb*8 + lane/4][col = nb*8 + (lane%4)*2 + {0,1}] of its warp tile
     double csum[NBW][2];
 #pragma unroll
     for (int nb = 0; nb < NBW; ++nb) csum[nb][0] = csum[nb][1] = 0.0;
+    // pass 1: does every element of this thread sit in the fast path's domain?  counts 0 or in [1e-140, 1e140] and
+    // composites below 1e140 (NaN fails the comparison) keep n/m and its reciprocal normal numbers.
+    double nrow[4];
+    bool fast = true;
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) {
         const int64_t i = i0 + wm * 32 + mb * 8 + fr;
-        if (i < p.nb) {
-            const double n = p.data[i];
+        const double n = (i < p.nb) ? p.data[i] : 0.0;
+        nrow[mb] = n;
+        fast = fast && ((n == 0.0) || (n >= 1e-140 && n <= 1e140));
 #pragma unroll
-            for (int nb = 0; nb < NBW; ++nb) {
-                csum[nb][0] += poisson_term(acc[mb][nb][0], n, p.eps);
-                csum[nb][1] += poisson_term(acc[mb][nb][1], n, p.eps);
-                if (p.resid) {  // residual of fitting_base.jl:277-279 for every (bin, chain): feeds the batched gradient
+        for (int nb = 0; nb < NBW; ++nb) fast = fast && (acc[mb][nb][0] < 1e140) && (acc[mb][nb][1] < 1e140);
+    }
+    if (fast) {
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int64_t i = i0 + wm * 32 + mb * 8 + fr;
+            const double n = nrow[mb];
+            const bool pos = n > 0.0, inb = i < p.nb;
+            double rr[NBW][2];
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double m = acc[mb][nb][e];
+                    const double mc = (m < p.eps) ? p.eps : m;
+                    const double ratio = fast_div(n, mc, fast_recip(mc));
+                    const double lq = fast_log(pos ? ratio : 1.0, ltab);
+                    const double term = pos ? (n - mc - n * lq) : -mc;  // fitting_base.jl:92
+                    csum[nb][e] += inb ? term : 0.0;                    // zero-padding rows beyond nb contribute nothing
+                    rr[nb][e] = 1.0 - ratio;                            // fitting_base.jl:279
+                }
+            if (p.resid && i < p.nb) {  // residual for every (bin, chain): feeds the batched gradient
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb) {
                     const int64_t w = w0 + wn * kWarpN + nb * 8 + fk * 2;
-                    if (w < p.wld) {
-                        const double m0 = acc[mb][nb][0], m1 = acc[mb][nb][1];
-                        double2 r;
-                        r.x = 1.0 - n / ((m0 < p.eps) ? p.eps : m0);
-                        r.y = 1.0 - n / ((m1 < p.eps) ? p.eps : m1);
-                        *reinterpret_cast<double2 *>(p.resid + i * p.wld + w) = r;
+                    if (w < p.wld) *reinterpret_cast<double2 *>(p.resid + i * p.wld + w) = make_double2(rr[nb][0], rr[nb][1]);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int64_t i = i0 + wm * 32 + mb * 8 + fr;
+            if (i < p.nb) {
+                const double n = p.data[i];
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb) {
+                    csum[nb][0] += poisson_term(acc[mb][nb][0], n, p.eps);
+                    csum[nb][1] += poisson_term(acc[mb][nb][1], n, p.eps);
+                    if (p.resid) {
+                        const int64_t w = w0 + wn * kWarpN + nb * 8 + fk * 2;
+                        if (w < p.wld) {
+                            const double m0 = acc[mb][nb][0], m1 = acc[mb][nb][1];
+                            double2 r;
+                            r.x = 1.0 - n / ((m0 < p.eps) ? p.eps : m0);
+                            r.y = 1.0 - n / ((m1 < p.eps) ? p.eps : m1);
+                            *reinterpret_cast<double2 *>(p.resid + i * p.wld + w) = r;
+                        }
                     }
                 }
             }

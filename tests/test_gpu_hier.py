@@ -198,6 +198,44 @@ def test_batched_walkers_f32_stack(S):
         assert got[w] == pytest.approx(-nlq, rel=1e-6)
 
 
+def test_batched_epilogue_fast_and_exact_paths(S):
+    """The DMMA kernel's branch-free Poisson epilogue (table log, Newton reciprocal) and the exact libdevice path it falls
+    back to outside its domain give the single-vector kernel's answer: zero counts, exact m == n (logL = 0 -> -Inf,
+    fitting_base.jl:95), tiny / huge / non-integer "counts", NaN coefficients."""
+    rng = np.random.default_rng(12)
+    nb, nt, W = 1500, 24, 40
+    M = np.asfortranarray(rng.random((nb, nt)))
+    x = 50 * rng.random(nt) + 1
+    X = np.maximum(0.0, x[:, None] * (1 + 0.3 * rng.standard_normal((nt, W))))
+    cases = {}
+    d = rng.poisson(M @ x).astype(np.float64); d[::7] = 0.0
+    cases["poisson with zero bins"] = d
+    cases["fractional, ratios from 1e-6 to 1e6"] = (M @ x) * 10.0 ** rng.uniform(-6, 6, nb)
+    d = rng.poisson(M @ x).astype(np.float64); d[5] = 1e-200; d[9] = 1e200; d[11] = 3e-310
+    cases["outside the fast domain (exact path)"] = d
+    for name, data in cases.items():
+        ds = S.DeviceStack(M, data)
+        got = ds.eval_logl_batched(X)
+        for w in (0, 17, W - 1):
+            nl, _, _ = ds.eval_fg(X[:, w], want_G=False)
+            assert got[w] == pytest.approx(-nl, rel=1e-12), name
+            nlq, _, _, _ = O.fg_quad(X[:, w], M, data, want_G=False)
+            assert got[w] == pytest.approx(-nlq, rel=1e-12), name
+        nlb, G = ds.eval_fg_batched(X[:, :9])
+        nl1, G1, _ = ds.eval_fg(X[:, 3])
+        assert nlb[3] == pytest.approx(nl1, rel=1e-12) and np.all(np.abs(G[:, 3] - G1) <= 1e-10 * np.abs(G1).max()), name
+    # m == n in every bin: each term is exactly 0, the sum is 0 and the guard turns it into -Inf
+    Mi = np.asfortranarray(np.eye(40)); di = np.arange(1.0, 41.0)
+    dsi = S.DeviceStack(Mi, di)
+    Xi = np.stack([di, di * 1.5, di], axis=1)
+    out = dsi.eval_logl_batched(Xi)
+    assert out[0] == -np.inf and out[2] == -np.inf and np.isfinite(out[1])
+    # NaN coefficient: that walker (only) is NaN
+    Xn = X[:, :6].copy(); Xn[4, 2] = np.nan
+    got = S.DeviceStack(M, cases["poisson with zero bins"]).eval_logl_batched(Xn)
+    assert np.isnan(got[2]) and np.all(np.isfinite(np.delete(got, 2)))
+
+
 @pytest.mark.parametrize("nb,nt,C,dtype", [(4000, 64, 1, np.float64), (5003, 100, 5, np.float64), (9801, 142, 16, np.float64),
                                            (20000, 600, 33, np.float64), (3000, 200, 70, np.float64), (6000, 120, 12, np.float32),
                                            (7000, 90, 24, np.float64), (4100, 64, 9, np.float32), (2500, 33, 64, np.float32)])
