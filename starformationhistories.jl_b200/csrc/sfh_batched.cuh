@@ -451,24 +451,43 @@ __global__ void __launch_bounds__(kBgThreads) sfh_bgrad_mma_kernel(const S *__re
     const int64_t per = (nslab_all + p.nsplit - 1) / p.nsplit;
     const int64_t s0 = (int64_t)blockIdx.y * per, s1 = (s0 + per < nslab_all) ? s0 + per : nslab_all;
 
+    // per-thread constant loader state (cf. the logL kernel): a thread copies the same 16-byte piece (bins kv..) of
+    // templates m0, m0 + A_MPI, ... and the same column pair of rows k0, k0 + B_KPI, ... of every slab
+    constexpr int A_VEC = kBgBK / EPV;                 // 16-byte pieces per template row of a slab
+    constexpr int A_MPI = kBgThreads / A_VEC;          // templates covered per pass over the threads
+    constexpr int A_NI = kBgBM / A_MPI;
+    static_assert(kBgThreads % A_VEC == 0 && kBgBM % A_MPI == 0, "A loader shape");
+    constexpr int B_VEC = C / 2;
+    constexpr int B_KPI = (kBgThreads / B_VEC) < kBgBK ? (kBgThreads / B_VEC) : kBgBK;
+    constexpr int B_NI = kBgBK / B_KPI;
+    static_assert(kBgThreads % B_VEC == 0 && kBgBK % B_KPI == 0, "B loader shape");
+    const int a_kv = (tid % A_VEC) * EPV, a_m0 = tid / A_VEC;
+    const int64_t a_sj = p.lay.panel ? ((int64_t)1 << p.lay.bt_shift) : p.lay.ld;   // stride between templates
+    S *a_dst = As + (size_t)a_m0 * kBgLdA + a_kv;
+    const int b_cv = (tid % B_VEC) * 2, b_k0 = tid / B_VEC;
+    const bool b_on = (b_k0 < kBgBK) && (b_cv < p.wld);   // the kernel's C (multiple of 8, <= 64) may exceed the row length
+    double *b_dst = Bs + (size_t)(b_k0 < kBgBK ? b_k0 : 0) * LdB + b_cv;
+
     auto issue = [&](int64_t slab, int stage) {
         const int64_t i0 = slab * kBgBK;
         const bool live = slab < s1;
         // A: 128 templates x 16 bins; 16-byte pieces along bins (contiguous inside a panel row)
-        constexpr int A_VEC = kBgBK / EPV;
-        for (int v = tid; v < kBgBM * A_VEC; v += kBgThreads) {
-            const int m = v / A_VEC, kv = (v % A_VEC) * EPV;
-            const int64_t j = j0 + m, i = i0 + kv;
-            const bool ok = live && j < p.nt && i < p.lay.ld;
-            cp_async16(As + ((size_t)stage * kBgBM + m) * kBgLdA + kv, M + (ok ? p.lay.off(i, j) : 0), ok);
+        const int64_t ia = i0 + a_kv;
+        const bool a_ok = live && ia < p.lay.ld;
+        const S *a_src = M + (a_ok ? p.lay.off(ia, j0 + a_m0) : 0);
+#pragma unroll
+        for (int n = 0; n < A_NI; ++n) {
+            const bool ok = a_ok && (j0 + a_m0 + n * A_MPI) < p.nt;
+            cp_async16(a_dst + ((size_t)stage * kBgBM + n * A_MPI) * kBgLdA, a_src + (ok ? (int64_t)(n * A_MPI) * a_sj : 0), ok);
         }
         // B: 16 bins x C chains of the residual matrix (rows beyond nb were never written: masked by `i < nb`)
-        constexpr int B_VEC = C / 2;
-        for (int v = tid; v < kBgBK * B_VEC; v += kBgThreads) {
-            const int k = v / B_VEC, cv = (v % B_VEC) * 2;
-            const int64_t i = i0 + k;
-            const bool ok = live && i < p.nb && cv < p.wld;  // the kernel's C (multiple of 8, <= 64) may exceed the row length
-            cp_async16(Bs + ((size_t)stage * kBgBK + k) * LdB + cv, p.resid + (ok ? i * p.wld + cv : 0), ok);
+        if (b_k0 < kBgBK) {
+#pragma unroll
+            for (int n = 0; n < B_NI; ++n) {
+                const int64_t i = i0 + b_k0 + n * B_KPI;
+                const bool ok = live && b_on && i < p.nb;
+                cp_async16(b_dst + ((size_t)stage * kBgBK + n * B_KPI) * LdB, p.resid + (ok ? i * p.wld + b_cv : 0), ok);
+            }
         }
         cp_async_commit();
     };
@@ -480,11 +499,12 @@ __global__ void __launch_bounds__(kBgThreads) sfh_bgrad_mma_kernel(const S *__re
         for (int b = 0; b < NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     for (int s = 0; s < kBgStages - 1; ++s) issue(s0 + s, s);
+    int stage = 0, fill = kBgStages - 1;
     for (int64_t slab = s0; slab < s1; ++slab) {
-        const int stage = (int)((slab - s0) % kBgStages);
         cp_async_wait<kBgStages - 2>();
         __syncthreads();
-        issue(slab + kBgStages - 1, (int)((slab - s0 + kBgStages - 1) % kBgStages));
+        issue(slab + kBgStages - 1, fill);
+        fill = (fill + 1 == kBgStages) ? 0 : fill + 1;
         const S *Asl = As + (size_t)stage * kBgBM * kBgLdA;
         const double *Bsl = Bs + (size_t)stage * kBgBK * LdB;
 #pragma unroll
@@ -499,6 +519,7 @@ __global__ void __launch_bounds__(kBgThreads) sfh_bgrad_mma_kernel(const S *__re
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
         }
+        stage = (stage + 1 == kBgStages) ? 0 : stage + 1;
     }
     cp_async_wait<0>();
     // C fragment: row (template) = mb*8 + lane/4, cols (chains) = nb*8 + (lane%4)*2 + {0,1}
