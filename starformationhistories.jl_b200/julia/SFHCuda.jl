@@ -32,28 +32,31 @@ dtype_code(::Type{Int64}) = SFH_I64
 
 # ---- the device mirror of stack_models (src/fitting/utilities.jl:12-13) -------------------------
 mutable struct DeviceStack{S} <: AbstractMatrix{S}
-    host::Matrix{S}             # kept so that size/getindex and CPU-only helpers keep working
+    host::Union{Nothing, Matrix{S}}   # kept (when the stack was uploaded) so that getindex and CPU-only helpers keep working
+    dims::Tuple{Int, Int}
     handle::Ptr{Cvoid}
     ctx::TaskLocalValue{Ptr{Cvoid}}   # one sfh_ctx per task, like HMCModel's TaskLocalValue (hmc_sample.jl:127)
-    function DeviceStack(models::Matrix{S}, data::AbstractVector{D}) where {S <: Union{Float32, Float64}, D}
-        size(models, 1) == length(data) || throw(ArgumentError("axes(models,1) != axes(data,1)"))
-        d = D <: Union{Float32, Float64, Int64} ? collect(data) : Float64.(data)
-        h = Ref{Ptr{Cvoid}}(C_NULL)
-        GC.@preserve models d check(ccall((:sfh_stack_create, libsfh), Cint,
-            (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
-            h, models, size(models, 1), size(models, 2), dtype_code(S), d, dtype_code(eltype(d)), C_NULL))
-        handle = h[]
+    function DeviceStack{S}(host, dims, handle::Ptr{Cvoid}) where S
         ctx = TaskLocalValue{Ptr{Cvoid}}() do
             c = Ref{Ptr{Cvoid}}(C_NULL)
             check(ccall((:sfh_ctx_create, libsfh), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), handle, C_NULL, c))
             c[]
         end
-        obj = new{S}(models, handle, ctx)
+        obj = new{S}(host, dims, handle, ctx)
         finalizer(o -> ccall((:sfh_stack_destroy, libsfh), Cint, (Ptr{Cvoid},), o.handle), obj)
         return obj
     end
 end
-Base.size(s::DeviceStack) = size(s.host)
+function DeviceStack(models::Matrix{S}, data::AbstractVector{D}) where {S <: Union{Float32, Float64}, D}
+    size(models, 1) == length(data) || throw(ArgumentError("axes(models,1) != axes(data,1)"))
+    d = D <: Union{Float32, Float64, Int64} ? collect(data) : Float64.(data)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve models d check(ccall((:sfh_stack_create, libsfh), Cint,
+        (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        h, models, size(models, 1), size(models, 2), dtype_code(S), d, dtype_code(eltype(d)), C_NULL))
+    return DeviceStack{S}(models, size(models), h[])
+end
+Base.size(s::DeviceStack) = s.dims
 Base.getindex(s::DeviceStack, i...) = getindex(s.host, i...)
 DeviceStack(models::AbstractVector{<:AbstractMatrix}, data::AbstractMatrix) = DeviceStack(SFH.stack_models(models), vec(data))
 
@@ -134,5 +137,47 @@ function batched_loglikelihood(models::DeviceStack, X::Matrix{Float64})
     return out
 end
 (problem::SFH.MCMCModel{<:DeviceStack})(θ) = batched_loglikelihood(problem.models, reshape(convert(Vector{Float64}, θ), :, 1))[1]
+
+# fg! for C coefficient vectors at once: what the chain threads of hmc_sample / sample_sfh evaluate one by one
+# (hmc_sample.jl:123-141, generic_fitting.jl:617-626).  X is ntemplates x C; returns (-logL[C], G[ntemplates, C]).
+function batched_fg(models::DeviceStack, X::Matrix{Float64}; want_G::Bool=true)
+    nl = Vector{Float64}(undef, size(X, 2))
+    G = want_G ? Matrix{Float64}(undef, size(X)) : nothing
+    check(ccall((:sfh_eval_fg_batched, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                models.ctx[], X, size(X, 2), nl, want_G ? G : C_NULL))
+    return nl, G
+end
+
+# The whole stretch-move ensemble sampler on the device: replaces KissMCMC.emcee(MCMCModel(...), x0; ...) inside
+# mcmc_sample (mcmc_sample.jl:104).  x0 is ntemplates x nwalkers (nwalkers even); returns samples shaped like
+# convert_kissmcmc (:30-44) -- (nsteps / nthin, ntemplates, nwalkers) -- their log-likelihoods and the acceptance fraction.
+function device_emcee(models::DeviceStack, x0::Matrix{Float64}, nsteps::Integer; nthin::Integer=1, a_scale::Real=2.0,
+                      seed::UInt64=rand(UInt64))
+    T, W = size(x0); nstore = nsteps ÷ nthin
+    X = copy(x0); chain = Array{Float64,3}(undef, T, W, nstore); lps = Matrix{Float64}(undef, W, nstore)
+    lfin = Vector{Float64}(undef, W); acc = Ref{Float64}(0.0)
+    check(ccall((:sfh_mcmc_run, libsfh), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                models.ctx[], X, W, nsteps, nthin, a_scale, seed, chain, lps, lfin, acc))
+    return permutedims(chain, (3, 1, 2)), permutedims(lps), acc[]
+end
+
+# The template stack built on the device from the per-point arguments partial_cmd_smooth hands to bin_cmd_smooth
+# (src/StarFormationHistories.jl:886-888) for every template: no host Hess diagrams, no upload.  `points[t]` is a
+# NamedTuple (colors, mags, color_err, mag_err, weights, cov_mult); edges are the ranges calculate_edges returns.
+function DeviceStack(edges::Tuple{<:AbstractRange,<:AbstractRange}, points::AbstractVector, data; S::Type=Float64)
+    nx, ny = length(edges[1]) - 1, length(edges[2]) - 1
+    offs = Int64[0; cumsum(length(p.colors) for p in points)]
+    cat(f) = convert(Vector{Float64}, reduce(vcat, (f(p) for p in points)))
+    cov = Int32[p.cov_mult for p in points]
+    d = convert(Vector{Float64}, vec(data)); h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sfh_stack_create_from_points, libsfh), Cint,
+                (Ref{Ptr{Cvoid}}, Int64, Int64, Float64, Float64, Float64, Float64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                h, nx, ny, first(edges[1]), step(edges[1]), first(edges[2]), step(edges[2]), length(points), offs,
+                cat(p -> p.colors), cat(p -> p.mags), cat(p -> p.color_err), cat(p -> p.mag_err), cat(p -> p.weights), cov,
+                dtype_code(S), d, dtype_code(Float64), C_NULL))
+    return DeviceStack{S}(nothing, (nx * ny, length(points)), h[])   # same finalizer / per-task contexts as the uploading constructor
+end
 
 end # module
