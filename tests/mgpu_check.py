@@ -38,6 +38,30 @@ def main():
     X[5, 2] = -1.0
     a = whole.eval_logl_batched(X); b = shard.eval_logl_batched(X)
     assert b[2] == -np.inf and np.allclose(np.delete(a, 2), np.delete(b, 2), rtol=1e-12)
+    # fg! for several coefficient vectors at once over shards (logL and the T x C gradient are all-reduced)
+    nla, Ga_ = whole.eval_fg_batched(X[:, 3:12]); nlb, Gb_ = shard.eval_fg_batched(X[:, 3:12])
+    assert np.allclose(nla, nlb, rtol=1e-12) and np.allclose(Ga_, Gb_, rtol=1e-9, atol=1e-10 * np.abs(Ga_).max())
+    # the device-resident ensemble sampler over shards: same Philox streams on every rank, all-reduced logL ->
+    # every rank walks the SAME chain (bit for bit), and it is the single-GPU chain
+    X0 = np.maximum(0.0, x[:, None] + np.random.default_rng(4).standard_normal((nt, 24)))
+    ca, la_, Xa, lfa, acca = whole.mcmc_run(X0, 6, 2, 2.0, seed=77)
+    cb, lb_, Xb, lfb, accb = shard.mcmc_run(X0, 6, 2, 2.0, seed=77)
+    assert acca == accb and np.allclose(ca, cb, rtol=1e-12, atol=0) and np.allclose(la_, lb_, rtol=1e-11)
+    t = torch.tensor(np.ascontiguousarray(Xb).ravel(), dtype=torch.float64, device="cuda")
+    ref = t.clone(); dist.broadcast(ref, 0)
+    assert torch.equal(t, ref)
+    # a stack built on the device from point lists, each rank building only its rows
+    rng = np.random.default_rng(6)
+    xe, ye = np.linspace(0.0, 1.0, 41), np.linspace(20.0, 25.0, 61)
+    pls = [(rng.uniform(0, 1, 80), rng.uniform(20, 25, 80), rng.uniform(0.01, 0.08, 80), rng.uniform(0.03, 0.3, 80),
+            rng.uniform(1, 5, 80), (0, 1, -1)[t % 3]) for t in range(9)]
+    dpt = rng.poisson(30.0, 40 * 60).astype(np.float64)
+    wp = S.DeviceStack.from_points((xe, ye), pls, data=dpt, device=local)
+    sp = S.DeviceStack.from_points((xe, ye), pls, data=dpt, device=local, rows=S.shard_rows(40 * 60, world, rank))
+    S.init_library_comm(sp.ctx())
+    xc = rng.uniform(0.5, 2.0, 9)
+    (fa, ga, _), (fb, gb, _) = wp.eval_fg(xc), sp.eval_fg(xc)
+    assert abs(fa - fb) <= 1e-12 * abs(fa) and np.allclose(ga, gb, rtol=1e-10, atol=1e-10 * np.abs(ga).max())
     # hierarchical path over shards
     p = make_hier_problem(nj=12, nk=10, nb=5003)
     mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
