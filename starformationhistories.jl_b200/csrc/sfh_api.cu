@@ -1235,17 +1235,42 @@ extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, in
     CU_TRY(cudaSetDevice(s->device));
     SFH_TRY(ensure_walker_capacity(c, W));   // c->d_X holds the proposals of one half-ensemble
     const int64_t nt = s->nt, half = W / 2, nstore = nsteps / nthin;
-    const size_t xbytes = (size_t)nt * (size_t)W * 8;
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(nstore, 1), (int64_t)((size_t)1 << 30) / (int64_t)xbytes));
+    const size_t xbytes = (size_t)nt * (size_t)W * 8, lbytes = (size_t)W * 8;
+    const bool store = (chain || logl_chain) && nstore > 0;
+    // stored steps leave through a small ring of device slots: the sampler's stream fills a slot (D2D), a second stream
+    // copies it to the (page-locked for the duration of the run) host arrays, so the copy-back overlaps the next steps
+    const int nslots = store ? (int)std::min<int64_t>(nstore, 8) : 0;
     DevBufs bufs;
-    double *dX = nullptr, *dlp = nullptr, *dz = nullptr, *dchain = nullptr, *dlchain = nullptr;
+    struct Ring {
+        cudaStream_t copy = nullptr;
+        std::vector<cudaEvent_t> filled, copied;
+        void *reg[2] = {nullptr, nullptr};
+        ~Ring() {
+            if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
+            for (auto e : filled) cudaEventDestroy(e);
+            for (auto e : copied) cudaEventDestroy(e);
+            for (void *r : reg) if (r) cudaHostUnregister(r);
+        }
+    } ring;   // destroyed before `bufs`: the copy stream is drained before the slots are freed
+    double *dX = nullptr, *dlp = nullptr, *dz = nullptr, *dslots = nullptr;
     unsigned long long *dacc = nullptr;
     CU_TRY(bufs.alloc(&dX, xbytes));
-    CU_TRY(bufs.alloc(&dlp, (size_t)W * 8));
+    CU_TRY(bufs.alloc(&dlp, lbytes));
     CU_TRY(bufs.alloc(&dz, (size_t)half * 8));
     CU_TRY(bufs.alloc(&dacc, 8));
-    if (chain && nstore > 0) CU_TRY(bufs.alloc(&dchain, (size_t)chunk * xbytes));
-    if (logl_chain && nstore > 0) CU_TRY(bufs.alloc(&dlchain, (size_t)chunk * (size_t)W * 8));
+    if (store) {
+        CU_TRY(bufs.alloc(&dslots, (size_t)nslots * (xbytes + lbytes)));
+        CU_TRY(cudaStreamCreateWithFlags(&ring.copy, cudaStreamNonBlocking));
+        ring.filled.resize(nslots); ring.copied.resize(nslots);
+        for (int k = 0; k < nslots; ++k) {
+            CU_TRY(cudaEventCreateWithFlags(&ring.filled[k], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ring.copied[k], cudaEventDisableTiming));
+        }
+        // pinning is an optimisation only: if it is refused the copies are staged by the driver
+        if (chain && cudaHostRegister(chain, (size_t)nstore * xbytes, cudaHostRegisterDefault) == cudaSuccess) ring.reg[0] = chain;
+        if (logl_chain && cudaHostRegister(logl_chain, (size_t)nstore * lbytes, cudaHostRegisterDefault) == cudaSuccess) ring.reg[1] = logl_chain;
+        (void)cudaGetLastError();
+    }
     CU_TRY(cudaMemcpyAsync(dX, X, xbytes, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaMemsetAsync(dacc, 0, 8, c->stream));
     SFH_TRY(enqueue_batched_impl(c, dX, W, dlp));
@@ -1259,16 +1284,18 @@ extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, in
             CU_TRY(cudaGetLastError());
             c->stats.kernel_launches += 2;
         }
-        if ((step + 1) % nthin == 0) {
-            const int64_t k = (step + 1) / nthin - 1, slot = k % chunk;
-            if (dchain) CU_TRY(cudaMemcpyAsync(dchain + (size_t)slot * nt * W, dX, xbytes, cudaMemcpyDeviceToDevice, c->stream));
-            if (dlchain) CU_TRY(cudaMemcpyAsync(dlchain + (size_t)slot * W, dlp, (size_t)W * 8, cudaMemcpyDeviceToDevice, c->stream));
-            if (slot == chunk - 1 || k == nstore - 1) {   // flush the stored steps [k - slot, k] to the host
-                const int64_t k0 = k - slot, n = slot + 1;
-                if (dchain) CU_TRY(cudaMemcpyAsync(chain + (size_t)k0 * nt * W, dchain, (size_t)n * xbytes, cudaMemcpyDeviceToHost, c->stream));
-                if (dlchain) CU_TRY(cudaMemcpyAsync(logl_chain + (size_t)k0 * W, dlchain, (size_t)n * W * 8, cudaMemcpyDeviceToHost, c->stream));
-                CU_TRY(cudaStreamSynchronize(c->stream));
-            }
+        if (store && (step + 1) % nthin == 0) {
+            const int64_t k = (step + 1) / nthin - 1;
+            const int slot = (int)(k % nslots);
+            double *sx = dslots + (size_t)slot * ((xbytes + lbytes) / 8), *sl = sx + xbytes / 8;
+            if (k >= nslots) CU_TRY(cudaStreamWaitEvent(c->stream, ring.copied[slot], 0));   // slot's previous contents are out
+            if (chain) CU_TRY(cudaMemcpyAsync(sx, dX, xbytes, cudaMemcpyDeviceToDevice, c->stream));
+            if (logl_chain) CU_TRY(cudaMemcpyAsync(sl, dlp, lbytes, cudaMemcpyDeviceToDevice, c->stream));
+            CU_TRY(cudaEventRecord(ring.filled[slot], c->stream));
+            CU_TRY(cudaStreamWaitEvent(ring.copy, ring.filled[slot], 0));
+            if (chain) CU_TRY(cudaMemcpyAsync(chain + (size_t)k * nt * W, sx, xbytes, cudaMemcpyDeviceToHost, ring.copy));
+            if (logl_chain) CU_TRY(cudaMemcpyAsync(logl_chain + (size_t)k * W, sl, lbytes, cudaMemcpyDeviceToHost, ring.copy));
+            CU_TRY(cudaEventRecord(ring.copied[slot], ring.copy));
         }
     }
     unsigned long long acc = 0;
@@ -1276,6 +1303,7 @@ extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, in
     if (logl_final) CU_TRY(cudaMemcpyAsync(logl_final, dlp, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemcpyAsync(&acc, dacc, 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    if (ring.copy) CU_TRY(cudaStreamSynchronize(ring.copy));
     if (accept_frac) *accept_frac = nsteps > 0 ? (double)acc / ((double)nsteps * (double)W) : 0.0;
     return SFH_OK;
 }
