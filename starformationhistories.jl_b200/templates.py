@@ -56,16 +56,15 @@ def mini_spacing(m_ini, colors, mags, dmag, ret_spacing=False):
     first = m[0]                                                          # :116 (before sorting, as in the reference)
     idx = np.argsort(m, kind="stable")
     m, c, y = m[idx], c[idx], y[idx]
-    out = [first]
-    for i in range(m.shape[0] - 1):
-        d = math.hypot(c[i + 1] - c[i], y[i + 1] - y[i])
-        if d > dmag:                                                       # :128-135
-            n = int(math.ceil(d / dmag))
-            step = (m[i + 1] - m[i]) / n
-            out.extend(m[i] + step * j for j in range(1, n + 1))
-        else:
-            out.append(m[i + 1])
-    new = np.array(out)
+    d = np.hypot(np.diff(c), np.diff(y))
+    interp = d > dmag                                                      # :128
+    n = np.where(interp, np.ceil(d / dmag), 1.0).astype(np.int64)          # round(Int, d / dmag, RoundUp)
+    step = np.diff(m) / n
+    seg = np.repeat(np.arange(n.shape[0]), n)                              # segment of every new point
+    j = np.arange(seg.shape[0]) - np.repeat(np.cumsum(n) - n, n) + 1       # 1..n within the segment
+    pts = m[:-1][seg] + step[seg] * j                                      # m_ini[i] + mass_step*j  (:133)
+    pts = np.where(interp[seg], pts, m[1:][seg])                           # uninterpolated segments push m_ini[i+1] itself (:136)
+    new = np.concatenate([[first], pts])
     _, keep = np.unique(new, return_index=True)                            # unique(): first occurrences, original order
     new = new[np.sort(keep)]
     return (new, np.diff(new)) if ret_spacing else new
