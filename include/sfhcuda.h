@@ -183,6 +183,12 @@ int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL);
  * G: ntemplates x C column-major (nullable).  Per-vector semantics are exactly those of sfh_eval_fg.            */
 int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G);
 
+/* Hierarchical fg! for C variable vectors at once (the chains of sample_sfh / tsample_sfh,
+ * fitting/hierarchical/generic_fitting.jl:564-665): V is (Nj+3) x C column-major in natural units, neg_logL[C],
+ * G (nullable) (Nj+3) x C.  Per-vector semantics are exactly those of sfh_eval_fg_hier.                       */
+int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *V,
+                             int64_t C, const uint8_t *free_mask, double *neg_logL, double *G);
+
 /* Device-resident affine-invariant ensemble sampler (Goodman & Weare stretch move, the algorithm of KissMCMC.emcee
  * that mcmc_sample drives, fitting/mcmc_sample.jl:97-108): proposal, the log-likelihood of each half-ensemble
  * (sfh_eval_logl_batched's kernel) and accept/reject all stay on the device.  X: ntemplates x W column-major, in = the

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "sfh_eval_fg_hier": (_int, [_vp, _int, _dp, _int, _dp, _u8p, _dp, _dp]),
     "sfh_eval_logl_batched": (_int, [_vp, _dp, _i64, _dp]),
     "sfh_eval_fg_batched": (_int, [_vp, _dp, _i64, _dp, _dp]),
+    "sfh_eval_fg_hier_batched": (_int, [_vp, _int, _dp, _int, _dp, _i64, _u8p, _dp, _dp]),
     "sfh_mcmc_run": (_int, [_vp, _dp, _i64, _i64, _i64, C.c_double, C.c_uint64, _dp, _dp, _dp, _dp]),
     "sfh_comm_unique_id": (_int, [_vp]),
     "sfh_comm_init": (_int, [_vp, _int, _int, _vp]),

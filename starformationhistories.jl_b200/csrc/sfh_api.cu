@@ -1328,6 +1328,49 @@ cudaError_t launch_bgrad(const sfh_stack *s, const BGradParams &gp, dim3 grid, c
 }
 }  // namespace
 
+namespace {
+// G[T x Cb] = M'R for the residual matrix the logL kernel just stored in c->d_resid; result at out[k*ostride + ooff + j]
+int ensure_bgrad_capacity(sfh_ctx *c, int &nsplit_out) {
+    sfh_stack *s = c->s;
+    const int64_t nt = s->nt, wld = c->wld;
+    const int64_t n_tt = std::max<int64_t>((nt + kBgBM - 1) / kBgBM, 1);
+    const int nsplit = (int)std::min<int64_t>(32, std::max<int64_t>(1, (2 * std::max(s->sm_count, 1) + n_tt - 1) / n_tt));
+    if (c->bg_cap < c->wcap || c->bg_nsplit != nsplit) {
+        cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG);
+        c->d_resid = c->d_bgpart = c->d_bG = nullptr; c->bg_cap = 0;
+        CU_TRY(cudaMalloc((void **)&c->d_resid, (size_t)s->ld * wld * 8));
+        CU_TRY(cudaMalloc((void **)&c->d_bgpart, (size_t)nsplit * std::max<int64_t>(nt, 1) * wld * 8));
+        CU_TRY(cudaMalloc((void **)&c->d_bG, (size_t)std::max<int64_t>(nt, 1) * wld * 8));
+        c->bg_cap = c->wcap; c->bg_nsplit = nsplit;
+    }
+    nsplit_out = nsplit;
+    return SFH_OK;
+}
+
+int enqueue_bgrad(sfh_ctx *c, int64_t Cb, int nsplit, double *out, int64_t ostride, int64_t ooff) {
+    sfh_stack *s = c->s;
+    const int64_t nt = s->nt, wld = c->wld;
+    const int64_t n_tt = std::max<int64_t>((nt + kBgBM - 1) / kBgBM, 1);
+    BGradParams gp{};
+    gp.nb = s->rows; gp.nt = nt; gp.wld = wld; gp.C = (int32_t)Cb; gp.nsplit = nsplit; gp.lay = s->lay;
+    gp.resid = c->d_resid; gp.gpart = c->d_bgpart;
+    const dim3 grid((unsigned)n_tt, (unsigned)nsplit);
+    const int NB = (int)((Cb + 7) / 8);
+    cudaError_t e;
+    switch (NB) {
+    case 1: e = launch_bgrad<1>(s, gp, grid, c->stream); break;
+    case 2: e = launch_bgrad<2>(s, gp, grid, c->stream); break;
+    case 3: case 4: e = launch_bgrad<4>(s, gp, grid, c->stream); break;
+    default: e = launch_bgrad<8>(s, gp, grid, c->stream); break;
+    }
+    CU_TRY(e);
+    sfh_bgrad_reduce_kernel<<<(unsigned)((nt * Cb + 255) / 256), 256, 0, c->stream>>>(c->d_bgpart, nsplit, nt, wld, Cb, out, ostride, ooff);
+    CU_TRY(cudaGetLastError());
+    c->stats.kernel_launches += 2;
+    return SFH_OK;
+}
+}  // namespace
+
 extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G) {
     if (!c || !X || C < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (C == 0) return SFH_OK;
@@ -1337,36 +1380,12 @@ extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, doubl
     for (int64_t c0 = 0; c0 < C; c0 += kBgMaxC) {   // at most 64 vectors per pass (accumulators live in registers)
         const int64_t Cb = std::min<int64_t>(kBgMaxC, C - c0);
         SFH_TRY(ensure_walker_capacity(c, Cb));
-        const int64_t wld = c->wld;
-        const int64_t n_tt = std::max<int64_t>((nt + kBgBM - 1) / kBgBM, 1);
-        const int nsplit = (int)std::min<int64_t>(32, std::max<int64_t>(1, (2 * std::max(s->sm_count, 1) + n_tt - 1) / n_tt));
-        if (c->bg_cap < c->wcap || c->bg_nsplit != nsplit) {
-            cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG);
-            c->d_resid = c->d_bgpart = c->d_bG = nullptr; c->bg_cap = 0;
-            CU_TRY(cudaMalloc((void **)&c->d_resid, (size_t)s->ld * wld * 8));
-            CU_TRY(cudaMalloc((void **)&c->d_bgpart, (size_t)nsplit * std::max<int64_t>(nt, 1) * wld * 8));
-            CU_TRY(cudaMalloc((void **)&c->d_bG, (size_t)std::max<int64_t>(nt, 1) * wld * 8));
-            c->bg_cap = c->wcap; c->bg_nsplit = nsplit;
-        }
+        int nsplit = 1;
+        SFH_TRY(ensure_bgrad_capacity(c, nsplit));
         CU_TRY(cudaMemcpyAsync(c->d_X, X + c0 * nt, (size_t)nt * Cb * 8, cudaMemcpyHostToDevice, c->stream));
         SFH_TRY(enqueue_batched_impl(c, c->d_X, Cb, c->d_logl, G ? c->d_resid : nullptr, false));
         if (G && nt > 0) {
-            BGradParams gp{};
-            gp.nb = s->rows; gp.nt = nt; gp.wld = wld; gp.C = (int32_t)Cb; gp.nsplit = nsplit; gp.lay = s->lay;
-            gp.resid = c->d_resid; gp.gpart = c->d_bgpart;
-            const dim3 grid((unsigned)n_tt, (unsigned)nsplit);
-            const int NB = (int)((Cb + 7) / 8);
-            cudaError_t e;
-            switch (NB) {
-            case 1: e = launch_bgrad<1>(s, gp, grid, c->stream); break;
-            case 2: e = launch_bgrad<2>(s, gp, grid, c->stream); break;
-            case 3: case 4: e = launch_bgrad<4>(s, gp, grid, c->stream); break;
-            default: e = launch_bgrad<8>(s, gp, grid, c->stream); break;
-            }
-            CU_TRY(e);
-            sfh_bgrad_reduce_kernel<<<(unsigned)((nt * Cb + 255) / 256), 256, 0, c->stream>>>(c->d_bgpart, nsplit, nt, wld, Cb, c->d_bG);
-            CU_TRY(cudaGetLastError());
-            c->stats.kernel_launches += 2;
+            SFH_TRY(enqueue_bgrad(c, Cb, nsplit, c->d_bG, nt, 0));
             if (c->comm) {
                 int r = g_nccl.AllReduce(c->d_bG, c->d_bG, (size_t)(nt * Cb), kNcclFloat64, kNcclSum, c->comm, c->stream);
                 if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
@@ -1377,6 +1396,73 @@ extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, doubl
         CU_TRY(cudaStreamSynchronize(c->stream));
         if (neg_logL)
             for (int64_t k = 0; k < Cb; ++k) neg_logL[c0 + k] = guard_neg_logl(neg_logL[c0 + k]);
+    }
+    return SFH_OK;
+}
+
+// Hierarchical fg! for C variable vectors in one pass (the chains of sample_sfh / tsample_sfh, generic_fitting.jl:564-665):
+// C prologues (calculate_coeffs) fill the T x C coefficient matrix on the device, the two DMMA GEMMs of
+// sfh_eval_fg_batched give logL_c and M'r_c, C epilogues apply the chain rule; only (Nj + 3) x C numbers cross PCIe.
+extern "C" int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *V, int64_t C,
+                                        const uint8_t *free_mask, double *neg_logL, double *G) {
+    if (!c || !V || C < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (C == 0) return SFH_OK;
+    sfh_stack *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    HierParams hp0;
+    SFH_TRY(fill_hier_params(c, hp0, mh_kind, mh_fixed, disp_kind, free_mask));
+    const int64_t nt = s->nt, nj = std::max(c->nj, 1), nv = (int64_t)c->nj + 3;
+    const int want_G = G != nullptr;
+    const int64_t per_scr = 10 * nj + std::max<int64_t>(nt, 1);           // HierParams scratch of one chain
+    for (int64_t c0 = 0; c0 < C; c0 += kBgMaxC) {
+        const int64_t Cb = std::min<int64_t>(kBgMaxC, C - c0);
+        SFH_TRY(ensure_walker_capacity(c, Cb));
+        int nsplit = 1;
+        SFH_TRY(ensure_bgrad_capacity(c, nsplit));
+        DevBufs bufs;
+        double *d_v = nullptr, *d_scr = nullptr, *d_fg = nullptr, *d_o = nullptr;
+        CU_TRY(bufs.alloc(&d_v, (size_t)Cb * nv * 8));
+        CU_TRY(bufs.alloc(&d_scr, (size_t)Cb * per_scr * 8));
+        CU_TRY(bufs.alloc(&d_fg, (size_t)Cb * (1 + nt) * 8));
+        CU_TRY(bufs.alloc(&d_o, (size_t)Cb * (1 + nv) * 8));
+        CU_TRY(cudaMemcpyAsync(d_v, V + c0 * nv, (size_t)Cb * nv * 8, cudaMemcpyHostToDevice, c->stream));
+        auto params_of = [&](int64_t k) {
+            HierParams hp = hp0;
+            double *q = d_scr + k * per_scr;
+            hp.variables = d_v + k * nv;
+            hp.mu = q; hp.gA = hp.mu + nj; hp.gB = hp.gA + nj; hp.gM = hp.gB + nj; hp.Asum = hp.gM + nj; hp.cum = hp.Asum + nj;
+            hp.tmpj = hp.cum + nj; hp.Ajk = q + 10 * nj;
+            hp.coeffs = c->d_X + k * nt;            // column k of the coefficient matrix the GEMMs read
+            hp.fg_out = d_fg + k * (1 + nt);
+            hp.out = d_o + k * (1 + nv);
+            hp.out_host = nullptr;
+            return hp;
+        };
+        for (int64_t k = 0; k < Cb; ++k) {
+            sfh_hier_prologue_kernel<<<1, kHierThreads, 0, c->stream>>>(params_of(k));
+            CU_TRY(cudaGetLastError());
+        }
+        SFH_TRY(enqueue_batched_impl(c, c->d_X, Cb, c->d_logl, want_G ? c->d_resid : nullptr, false));
+        if (want_G && nt > 0) {
+            SFH_TRY(enqueue_bgrad(c, Cb, nsplit, d_fg, 1 + nt, 1));
+            if (c->comm) {   // (the logL slots are overwritten below with the already-reduced values)
+                int r = g_nccl.AllReduce(d_fg, d_fg, (size_t)(Cb * (1 + nt)), kNcclFloat64, kNcclSum, c->comm, c->stream);
+                if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce failed (%d)", r);
+            }
+        }
+        CU_TRY(cudaMemcpy2DAsync(d_fg, (size_t)(1 + nt) * 8, c->d_logl, 8, 8, (size_t)Cb, cudaMemcpyDeviceToDevice, c->stream));
+        for (int64_t k = 0; k < Cb; ++k) {
+            sfh_hier_epilogue_kernel<<<1, kHierThreads, 0, c->stream>>>(params_of(k), want_G);
+            CU_TRY(cudaGetLastError());
+        }
+        c->stats.kernel_launches += 2 * Cb;
+        std::vector<double> h((size_t)Cb * (1 + nv));
+        CU_TRY(cudaMemcpyAsync(h.data(), d_o, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        for (int64_t k = 0; k < Cb; ++k) {
+            if (neg_logL) neg_logL[c0 + k] = h[k * (1 + nv)];
+            if (G) memcpy(G + (c0 + k) * nv, h.data() + k * (1 + nv) + 1, (size_t)nv * 8);
+        }
     }
     return SFH_OK;
 }

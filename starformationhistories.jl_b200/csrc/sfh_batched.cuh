@@ -543,13 +543,13 @@ __global__ void __launch_bounds__(kBgThreads) sfh_bgrad_mma_kernel(const S *__re
 
 // G[j + nt*c] (column-major T x C, like the coefficient matrix) = sum over splits, fixed order
 __global__ void sfh_bgrad_reduce_kernel(const double *__restrict__ gpart, int nsplit, int64_t nt, int64_t wld, int64_t C,
-                                        double *__restrict__ G) {
+                                        double *__restrict__ G, int64_t ostride, int64_t ooff) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nt * C) return;
     const int64_t j = e % nt, c = e / nt;
     double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) s += gpart[((size_t)sp * nt + j) * wld + c];
-    G[e] = s;
+    G[c * ostride + ooff + j] = s;   // ostride = nt, ooff = 0: compact T x C; (1 + nt, 1): the hierarchical epilogue's [logL, G] rows
 }
 
 // logL[w] = sum over bin tiles; raw sums (guards applied after any all-reduce).  256 threads = 8 walkers x 32 slices:

@@ -234,6 +234,23 @@ def fg_(F, G, MHmodel0, dispmodel0, variables, models, data, composite, logAge, 
     return nl.value if F is not None else None
 
 
+def fg_batched_(MHmodel0, dispmodel0, V, models, data, logAge, metallicities, want_G=True):
+    """Hierarchical ``fg!`` for every column of V ((Nj + nparams) x C, natural units) in one device pass
+    (sfh_eval_fg_hier_batched): returns (-logL[C], G[(Nj + nparams), C] or None)."""
+    ds = device_stack(models, data)
+    ctx = _bind(ds, logAge, metallicities)
+    V = np.asfortranarray(V, dtype=np.float64)
+    if V.ndim != 2 or V.shape[0] != ctx.n_ages + 3:
+        raise ValueError("size(V,1) != length(unique(logAge)) + nparams")
+    free = np.array(list(MHmodel0.free_params()) + list(dispmodel0.free_params()) + [0], dtype=np.uint8)
+    nl = np.empty(V.shape[1])
+    G = np.empty(V.shape, order="F") if want_G else None
+    fx = MHmodel0.fixed()
+    L.check(L.lib.sfh_eval_fg_hier_batched(ctx.handle, MHmodel0.kind, _dp(fx), dispmodel0.kind, _dp(V), V.shape[1],
+                                           free.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(nl), _dp(G) if want_G else None))
+    return nl, G
+
+
 def exptransform(params, transforms):
     """src/fitting/hierarchical/transformations.jl:44"""
     return np.array([math.exp(p) if t == 1 else (-math.exp(p) if t == -1 else p) for p, t in zip(params, transforms)])
@@ -296,3 +313,37 @@ class HierarchicalOptimizer:
         G[:nbins] = G2[:nbins]
         G[nbins:] = G2[nbins:][free]                                       # :181-189
         return (-nlogL, -G) if ret_F else -G                               # :193-197
+
+    def logdensity_and_gradient_batched(self, X):
+        """The same for C chains at once: X is (dimension, C); one device pass (sfh_eval_fg_hier_batched) serves all chains.
+        Returns (+logp[C], +grad[dimension, C])  (generic_fitting.jl:90-199 per column)."""
+        X = np.asarray(X, dtype=np.float64)
+        tf = np.array(list(self.MH_model0.transforms()) + list(self.disp_model0.transforms()))
+        free = np.array(list(self.MH_model0.free_params()) + list(self.disp_model0.free_params()), dtype=bool)
+        npar = tf.shape[0]
+        nbins = X.shape[0] - npar + int((~free).sum())
+        Cn = X.shape[1]
+        V = np.empty((nbins + npar, Cn))
+        V[:nbins] = np.exp(X[:nbins])                                      # :127
+        tfree = tf[free]
+        Xp = X[nbins:]
+        V[nbins:][free] = np.where(tfree[:, None] == 1, np.exp(Xp), np.where(tfree[:, None] == -1, -np.exp(Xp), Xp))   # :129-131
+        init = np.array(list(self.MH_model0.fittable_params()) + list(self.disp_model0.fittable_params()))
+        V[nbins:][~free] = init[~free][:, None]                            # :134-136
+        nl, G2 = fg_batched_(self.MH_model0, self.disp_model0, V, self.models, self.data, self.logAge, self.metallicities)
+        pos = np.zeros(nbins + npar, dtype=bool); pos[:nbins] = True
+        pos[nbins:] = (tf == 1) & free                                     # :143-145
+        neg = np.zeros(nbins + npar, dtype=bool); neg[nbins:] = (tf == -1) & free
+        if self.jacobian_corrections:                                      # :148-160
+            nl = nl - np.log(V[pos]).sum(axis=0)
+            if neg.any():                                                  # (no built-in model has a -1 transform)
+                nl = nl + np.log(V[neg]).sum(axis=0)
+            G2[pos] = G2[pos] * V[pos] - 1
+            G2[neg] = -G2[neg] * V[neg] + 1
+        else:                                                              # :161-169
+            G2[pos] = G2[pos] * V[pos]
+            G2[neg] = -G2[neg] * V[neg]
+        G = np.empty_like(X)
+        G[:nbins] = G2[:nbins]
+        G[nbins:] = G2[nbins:][free]                                       # :181-189
+        return -nl, -G                                                     # :193-197

@@ -380,47 +380,62 @@ def mdf_amr(coeffs, logAge, metallicities, models=None):
 
 
 # ---------------------------------------------------------------------------------------------
+def _vel(inv_mass, r):
+    """M^-1 r for a diagonal (vector) or dense (matrix) inverse mass."""
+    return inv_mass * r if inv_mass.ndim == 1 else inv_mass @ r
+
+
 def _leapfrog(theta, r, grad, eps, inv_mass):
     """One leapfrog step as a coroutine: yields the position whose (logp, gradient) it needs."""
     r = r + 0.5 * eps * grad
-    theta = theta + eps * inv_mass * r
+    theta = theta + eps * _vel(inv_mass, r)
     lp, grad = yield theta
     r = r + 0.5 * eps * grad
     return theta, r, lp, grad
 
 
-def nuts_chain(theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None):
+def nuts_chain(theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None, eps0=None):
     """No-U-Turn sampler (Hoffman & Gelman 2014, algorithm 6: slice NUTS with dual-averaging step size) written as a
     coroutine: it *yields* every position at which it needs the log-density and gradient and is *sent* `(logp, grad)`
     back; its return value is `(samples, logps, step_size)`.  Stands in for DynamicHMC.mcmc_with_warmup
-    (hmc_sample.jl:111); diagonal mass matrix fixed to `inv_mass`.  `nuts_sample` drives one chain; `run_chains_batched`
+    (hmc_sample.jl:111).  `inv_mass` is M^-1 of the Gaussian kinetic energy: a vector (diagonal) or a dense matrix, e.g. the
+    inverse Hessian of a fit (DynamicHMC.GaussianKineticEnergy(MAP.invH), generic_fitting.jl:479-482); it is not adapted.
+    `eps0` fixes the initial step size (the reference's ϵ) instead of the doubling heuristic.  `nuts_sample` drives one chain; `run_chains_batched`
     drives many, serving each round of requests with one batched device pass."""
     rng = np.random.default_rng() if rng is None else rng
     theta = np.asarray(theta0, dtype=np.float64).copy()
     d = theta.shape[0]
     inv_mass = np.ones(d) if inv_mass is None else np.asarray(inv_mass, dtype=np.float64)
+    if inv_mass.ndim == 2:                                                 # r ~ N(0, M), M = inv_mass^-1 = L^-T L^-1 with inv_mass = L L^T
+        Lc = np.linalg.cholesky((inv_mass + inv_mass.T) / 2)
+        draw = lambda: np.linalg.solve(Lc.T, rng.standard_normal(d))
+    else:
+        draw = lambda: rng.standard_normal(d) / np.sqrt(inv_mass)
+    kin = lambda r: 0.5 * np.dot(r, _vel(inv_mass, r))
     lp, grad = yield theta
 
     # heuristic initial step size
     eps = 0.1 / math.sqrt(d)
-    r0 = rng.standard_normal(d) / np.sqrt(inv_mass)
+    r0 = draw()
     _, r1, lp1, _ = yield from _leapfrog(theta, r0, grad, eps, inv_mass)
-    H0 = lp - 0.5 * np.dot(r0 * inv_mass, r0); H1 = lp1 - 0.5 * np.dot(r1 * inv_mass, r1)
+    H0 = lp - kin(r0); H1 = lp1 - kin(r1)
     a = 1.0 if (np.isfinite(H1) and H1 - H0 > math.log(0.5)) else -1.0
-    for _ in range(50):
+    for _ in range(50 if eps0 is None else 0):
         _, r1, lp1, _ = yield from _leapfrog(theta, r0, grad, eps, inv_mass)
-        H1 = lp1 - 0.5 * np.dot(r1 * inv_mass, r1)
+        H1 = lp1 - kin(r1)
         if not np.isfinite(H1):
             H1 = -np.inf
         if a * (H1 - H0) <= -a * math.log(2):
             break
         eps *= 2.0 ** a
+    if eps0 is not None:
+        eps = float(eps0)
     mu, ebar, Hbar, gamma, t0, kappa = math.log(10 * eps), 1.0, 0.0, 0.05, 10.0, 0.75
 
     def build(theta, r, grad, logu, v, j, eps, H0):
         if j == 0:
             th, rr, lpn, g = yield from _leapfrog(theta, r, grad, v * eps, inv_mass)
-            Hn = lpn - 0.5 * np.dot(rr * inv_mass, rr)
+            Hn = lpn - kin(rr)
             if not np.isfinite(Hn):
                 Hn = -np.inf
             n = int(logu <= Hn)
@@ -435,15 +450,15 @@ def nuts_chain(theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, in
             if n1 + n2 > 0 and rng.random() < n2 / (n1 + n2):
                 th1, lp1, g1 = th2, lp2, g2
             dth = thp - thm
-            s1 = s2 * int(np.dot(dth, rm * inv_mass) >= 0) * int(np.dot(dth, rp * inv_mass) >= 0)
+            s1 = s2 * int(np.dot(dth, _vel(inv_mass, rm)) >= 0) * int(np.dot(dth, _vel(inv_mass, rp)) >= 0)
             n1 += n2; a1 += a2; na1 += na2
         return thm, rm, gm, thp, rp, gp, th1, lp1, g1, n1, s1, a1, na1
 
     samples = np.empty((nsteps, d))
     lps = np.empty(nsteps)
     for m in range(1, nwarmup + nsteps + 1):
-        r0 = rng.standard_normal(d) / np.sqrt(inv_mass)
-        H0 = lp - 0.5 * np.dot(r0 * inv_mass, r0)
+        r0 = draw()
+        H0 = lp - kin(r0)
         logu = H0 + math.log(rng.random())
         thm = thp = theta; rm = rp = r0; gm = gp = grad
         j, n, s = 0, 1, 1
@@ -458,7 +473,7 @@ def nuts_chain(theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, in
                 theta, lp, grad = th1, lp1, g1
             n += n1
             dth = thp - thm
-            s = s1 * int(np.dot(dth, rm * inv_mass) >= 0) * int(np.dot(dth, rp * inv_mass) >= 0)
+            s = s1 * int(np.dot(dth, _vel(inv_mass, rm)) >= 0) * int(np.dot(dth, _vel(inv_mass, rp)) >= 0)
             j += 1
         if m <= nwarmup:                                                   # dual averaging
             Hbar = (1 - 1 / (m + t0)) * Hbar + (delta - alpha / nalpha) / (m + t0)
@@ -474,9 +489,9 @@ def nuts_chain(theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, in
     return samples, lps, eps
 
 
-def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None):
+def nuts_sample(logdensity_and_gradient, theta0, nsteps, nwarmup=200, max_depth=8, delta=0.8, rng=None, inv_mass=None, eps0=None):
     """One NUTS chain: every request of `nuts_chain` is answered by `logdensity_and_gradient(theta) -> (logp, grad)`."""
-    chain = nuts_chain(theta0, nsteps, nwarmup, max_depth, delta, rng, inv_mass)
+    chain = nuts_chain(theta0, nsteps, nwarmup, max_depth, delta, rng, inv_mass, eps0)
     try:
         req = next(chain)
         while True:
@@ -551,3 +566,61 @@ def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, 
     for c in range(nchains):
         out[:, :, c] = np.exp(res[c][0])
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+def _expand_posterior(best, Z):
+    """Transformed free-variable samples (nfree_total, N) -> natural-unit samples over ALL variables with the fixed
+    parameters written in (generic_fitting.jl:640-658, exptransform_samples! transformations.jl:57-93)."""
+    npar = best.MH_model.nparams() + best.disp_model.nparams()
+    nj = best.mu.shape[0] - npar
+    tf = np.array(list(best.MH_model.transforms()) + list(best.disp_model.transforms()))
+    free = np.array(list(best.MH_model.free_params()) + list(best.disp_model.free_params()), dtype=bool)
+    out = np.empty((best.mu.shape[0], Z.shape[1]))
+    out[:nj] = np.exp(Z[:nj])
+    tfree = tf[free]
+    Zp = Z[nj:]
+    out[nj:][free] = np.where(tfree[:, None] == 1, np.exp(Zp), np.where(tfree[:, None] == -1, -np.exp(Zp), Zp))
+    par = np.array(list(best.MH_model.fittable_params()) + list(best.disp_model.fittable_params()), dtype=np.float64)
+    out[nj:][~free] = par[~free][:, None]
+    return out
+
+
+def sample_sfh(bfgs_result, models, data, logAge, metallicities, Nsteps, eps=0.05, rng=None, nwarmup=0, max_depth=8):
+    """sample_sfh (generic_fitting.jl:456-556): one NUTS chain over the hierarchical model started at the MLE with the MAP
+    inverse Hessian as the Gaussian kinetic energy's M^-1 and initial step size `eps`.  Returns
+    {"posterior_matrix": (nvariables, Nsteps) in natural units, "logp": (Nsteps,), "step_size": float}."""
+    rng = np.random.default_rng() if rng is None else rng
+    MAP, MLE = bfgs_result["map"], bfgs_result["mle"]
+    inst = HierarchicalOptimizer(MLE.MH_model, MLE.disp_model, device_stack(models, data), data, logAge, metallicities, True, True, True)
+    s, lps, step = nuts_sample(inst.logdensity_and_gradient, np.asarray(MLE.result.x, dtype=np.float64), Nsteps, nwarmup, max_depth,
+                               rng=rng, inv_mass=np.asarray(MAP.invH, dtype=np.float64), eps0=eps)
+    return {"posterior_matrix": _expand_posterior(MLE, s.T), "logp": lps, "step_size": step}
+
+
+def tsample_sfh(bfgs_result, models, data, logAge, metallicities, Nsteps, eps=0.05, rng=None, chain_length=100, nwarmup=0,
+                max_depth=8, batched=True):
+    """tsample_sfh (generic_fitting.jl:564-665): ceil(Nsteps / chain_length) short chains, each started from a draw of
+    MvNormal(MLE minimizer, MAP.invH) (:586, :619).  The reference spawns one task per chain, every task evaluating its own
+    hierarchical `fg!`; here the chains are coroutines whose gradient requests are served `batched` -- one
+    sfh_eval_fg_hier_batched pass per round for all live chains.  Returns the same dictionary as `sample_sfh`."""
+    rng = np.random.default_rng() if rng is None else rng
+    MAP, MLE = bfgs_result["map"], bfgs_result["mle"]
+    x0 = np.asarray(MLE.result.x, dtype=np.float64)
+    cov = np.asarray(MAP.invH, dtype=np.float64)
+    cov = (cov + cov.T) / 2
+    lens = [min(chain_length, Nsteps - a) for a in range(0, Nsteps, chain_length)]   # Iterators.partition (:607)
+    starts = rng.multivariate_normal(x0, cov, size=len(lens))
+    rngs = list(rng.spawn(len(lens)))
+    inst = HierarchicalOptimizer(MLE.MH_model, MLE.disp_model, device_stack(models, data), data, logAge, metallicities, True, True, True)
+
+    def chain(th0, nsteps, nw, md, rng=None, _n=iter(lens)):
+        return nuts_chain(th0, next(_n), nw, md, rng=rng, inv_mass=cov, eps0=eps)
+    if batched and len(lens) > 1:
+        res, stats = run_chains_batched(inst.logdensity_and_gradient_batched, list(starts), 0, nwarmup, max_depth, rngs, chain=chain)
+    else:
+        res = [nuts_sample(inst.logdensity_and_gradient, starts[k], lens[k], nwarmup, max_depth, rng=rngs[k], inv_mass=cov, eps0=eps)
+               for k in range(len(lens))]
+    Z = np.concatenate([r[0] for r in res], axis=0).T                                  # reduce(hcat, ...) (:633)
+    return {"posterior_matrix": _expand_posterior(MLE, Z), "logp": np.concatenate([r[1] for r in res]),
+            "step_size": float(np.mean([r[2] for r in res]))}

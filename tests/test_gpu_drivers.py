@@ -101,6 +101,66 @@ def test_fit_sfh_recovers_truth(S, V):                             # mzr_test.jl
     assert resf["mle"].mu[-1] == 0.2 and resf["mle"].sigma[-1] == 0.0 and resf["mle"].invH.shape == (23, 23)
 
 
+@pytest.mark.parametrize("kind", ["mzr", "lin_amr", "log_amr"])
+def test_hier_fg_batched_matches_single(S, kind):
+    """sfh_eval_fg_hier_batched: C variable vectors in one pass == C calls of the hierarchical fg! (mzr.jl:84-215 / amr.jl:78-173)."""
+    p = make_hier_problem(nj=14, nk=11, nb=3000, ragged=(kind == "lin_amr"))
+    if kind == "mzr":
+        mh, pars = S.PowerLawMZR(1.0, -2.0, 6.0), [1.0, -2.0]
+    elif kind == "lin_amr":
+        mh, pars = S.LinearAMR(0.1, -2.2, 13.7), [0.1, -2.2]
+    else:
+        mh, pars = S.LogarithmicAMR(3e-4, 5e-5, 13.7, (True, False)), [3e-4, 5e-5]
+    dp = S.GaussianDispersion(0.2)
+    nj = np.unique(p["logAge"]).shape[0]
+    R = p["R"][:nj]
+    xt = S.calculate_coeffs(mh, dp, R, p["logAge"], p["MH"])
+    data = np.random.default_rng(5).poisson(p["M"] @ xt).astype(np.float64)
+    ds = S.DeviceStack(p["M"], data)
+    rng = np.random.default_rng(9)
+    for Cn in (1, 5, 9):
+        V = np.concatenate([R, pars, [0.2]])[:, None] * (1 + 0.05 * rng.standard_normal((nj + 3, Cn)))
+        nl, G = S.hierarchical.fg_batched_(mh, dp, V, ds, data, p["logAge"], p["MH"])
+        assert nl.shape == (Cn,) and G.shape == (nj + 3, Cn)
+        for c in range(Cn):
+            g1 = np.empty(nj + 3)
+            n1 = S.fg_(True, g1, mh, dp, V[:, c], ds, data, None, p["logAge"], p["MH"])
+            assert nl[c] == pytest.approx(n1, rel=1e-12)
+            assert np.allclose(G[:, c], g1, rtol=1e-8, atol=1e-9 * np.abs(g1).max())
+        nl2, none = S.hierarchical.fg_batched_(mh, dp, V, ds, data, p["logAge"], p["MH"], want_G=False)
+        assert none is None and np.allclose(nl2, nl, rtol=1e-14)
+    # the LogDensityProblems adapter, all chains at once (generic_fitting.jl:90-199 per column)
+    opt = S.HierarchicalOptimizer(mh, dp, ds, data, p["logAge"], p["MH"], True, True, True)
+    nfree = sum(mh.free_params()) + 1
+    X = np.concatenate([np.log(R), S.logtransform(np.array(pars + [0.2]), np.array(list(mh.transforms()) + [1]))[np.array(list(mh.free_params()) + [True])]])
+    X = X[:, None] + 0.02 * rng.standard_normal((nj + nfree, 6))
+    LP, GR = opt.logdensity_and_gradient_batched(X)
+    for c in (0, 3, 5):
+        lp, gr = opt.logdensity_and_gradient(X[:, c])
+        assert LP[c] == pytest.approx(lp, rel=1e-12) and np.allclose(GR[:, c], gr, rtol=1e-8, atol=1e-9 * np.abs(gr).max())
+
+
+def test_sample_sfh_and_tsample_sfh(S, V):                          # mzr_test.jl:218-251 (shapes, fixed rows)
+    p = make_hier_problem(nj=10, nk=12, nb=4000)
+    mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2, (False,))
+    xt = S.calculate_coeffs(mz, dp, p["R"], p["logAge"], p["MH"])
+    data = np.random.default_rng(3).poisson(p["M"] @ xt).astype(np.float64)
+    ds = S.DeviceStack(p["M"], data)
+    res = V.fit_sfh(S.PowerLawMZR(1.1, -2.1, 6.0), dp, ds, data, p["logAge"], p["MH"], x0=p["R"] * 1.2)
+    one = V.sample_sfh(res, ds, data, p["logAge"], p["MH"], 60, eps=0.2, rng=np.random.default_rng(1))
+    assert one["posterior_matrix"].shape == (13, 60) and np.all(one["posterior_matrix"][-1] == 0.2)   # fixed sigma row
+    many = V.tsample_sfh(res, ds, data, p["logAge"], p["MH"], 130, eps=0.2, rng=np.random.default_rng(2), chain_length=20)
+    seq = V.tsample_sfh(res, ds, data, p["logAge"], p["MH"], 130, eps=0.2, rng=np.random.default_rng(2), chain_length=20, batched=False)
+    for r in (many, seq):
+        pm = r["posterior_matrix"]
+        assert pm.shape == (13, 130) and np.all(pm[-1] == 0.2) and np.all(pm[:10] > 0) and r["logp"].shape == (130,)
+    # chains started from the fit's Gaussian stay near the MLE: means within 3 sigma of it
+    z = np.abs(many["posterior_matrix"].mean(axis=1)[:12] - res["mle"].mu[:12]) / np.maximum(res["map"].sigma[:12], 1e-12)
+    assert np.all(z < 3), z
+    # batched and sequential chains share starts and RNG streams: first draws of each chain agree closely
+    assert np.allclose(many["posterior_matrix"][:, ::20], seq["posterior_matrix"][:, ::20], rtol=1e-6)
+
+
 def test_mcmc_sample_shapes_and_oracle_chain(S, V):              # basic_linear_combinations.jl:120-154
     rng = np.random.Generator(np.random.Philox(7))
     N, nwalkers, nsteps = 10, 100, 20
