@@ -70,6 +70,22 @@ t0 = time.perf_counter(); O.fg_hier(O.POWERLAW_MZR, (6.0,), (1, 1, 1), truth, Mh
 out(config=4, what="HMC leapfrog = HierarchicalOptimizer.logdensity_and_gradient on the 2400-template MZR stack", gpu_us_per_eval=t_leap * 1e6,
     gpu_evals_per_s=1 / t_leap, cpu_oracle_1thread_s_per_eval=t_cpu)
 
+# ---- config 4: tsample_sfh on the 2400-template MZR stack: short chains served by one sfh_eval_fg_hier_batched pass per round ----
+tt = {}
+for batched in (False, True):
+    t0 = time.perf_counter()
+    r = S.tsample_sfh(res, ds3, d3, la, mh, 160, eps=0.05, rng=np.random.default_rng(4), chain_length=20, max_depth=5, batched=batched)
+    tt[batched] = time.perf_counter() - t0
+out(config=4, what="tsample_sfh: 8 chains x 20 NUTS draws (max_depth 5) on the 2400-template MZR stack, dim 63", sequential_s=tt[False],
+    batched_s=tt[True], speedup=tt[False] / tt[True], posterior_shape=list(r["posterior_matrix"].shape))
+tt = {}
+for batched in (False, True):
+    t0 = time.perf_counter()
+    r = S.tsample_sfh(res, ds3, d3, la, mh, 640, eps=0.05, rng=np.random.default_rng(4), chain_length=20, max_depth=5, batched=batched)
+    tt[batched] = time.perf_counter() - t0
+out(config=4, what="tsample_sfh: 32 chains x 20 NUTS draws (max_depth 5) on the 2400-template MZR stack, dim 63", sequential_s=tt[False],
+    batched_s=tt[True], speedup=tt[False] / tt[True])
+
 # ---- multi-chain hmc_sample: chains on threads sharing one sfh_eval_fg_batched pass vs chains one after another ------
 from sfh_b200 import solvers as V
 for (nbh, nth, nchs, nst, md) in ((60000, 200, (8,), 40, 5), (60000, 2400, (4, 8, 16), 12, 4)):

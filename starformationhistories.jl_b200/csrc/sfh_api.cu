@@ -172,6 +172,8 @@ struct sfh_ctx {
     // batched gradient (K6g)
     double *d_resid = nullptr, *d_bgpart = nullptr, *d_bG = nullptr;
     LogTable *d_logtab = nullptr;   // table of the DMMA kernel's fast Poisson epilogue
+    double *d_hb = nullptr;         // batched hierarchical evaluation: variables | scratch | [logL, G] rows | outputs (grow-only)
+    size_t hb_elems = 0;
     int64_t bg_cap = 0;
     int bg_nsplit = 0;
     // multi-GPU
@@ -667,7 +669,7 @@ extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
     cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx);
     cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
-    cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG); cudaFree(c->d_logtab);
+    cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG); cudaFree(c->d_logtab); cudaFree(c->d_hb);
     cudaFree(c->d_flush);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -1419,29 +1421,26 @@ extern "C" int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *m
         SFH_TRY(ensure_walker_capacity(c, Cb));
         int nsplit = 1;
         SFH_TRY(ensure_bgrad_capacity(c, nsplit));
-        DevBufs bufs;
-        double *d_v = nullptr, *d_scr = nullptr, *d_fg = nullptr, *d_o = nullptr;
-        CU_TRY(bufs.alloc(&d_v, (size_t)Cb * nv * 8));
-        CU_TRY(bufs.alloc(&d_scr, (size_t)Cb * per_scr * 8));
-        CU_TRY(bufs.alloc(&d_fg, (size_t)Cb * (1 + nt) * 8));
-        CU_TRY(bufs.alloc(&d_o, (size_t)Cb * (1 + nv) * 8));
-        CU_TRY(cudaMemcpyAsync(d_v, V + c0 * nv, (size_t)Cb * nv * 8, cudaMemcpyHostToDevice, c->stream));
-        auto params_of = [&](int64_t k) {
-            HierParams hp = hp0;
-            double *q = d_scr + k * per_scr;
-            hp.variables = d_v + k * nv;
-            hp.mu = q; hp.gA = hp.mu + nj; hp.gB = hp.gA + nj; hp.gM = hp.gB + nj; hp.Asum = hp.gM + nj; hp.cum = hp.Asum + nj;
-            hp.tmpj = hp.cum + nj; hp.Ajk = q + 10 * nj;
-            hp.coeffs = c->d_X + k * nt;            // column k of the coefficient matrix the GEMMs read
-            hp.fg_out = d_fg + k * (1 + nt);
-            hp.out = d_o + k * (1 + nv);
-            hp.out_host = nullptr;
-            return hp;
-        };
-        for (int64_t k = 0; k < Cb; ++k) {
-            sfh_hier_prologue_kernel<<<1, kHierThreads, 0, c->stream>>>(params_of(k));
-            CU_TRY(cudaGetLastError());
+        // per-context, grow-only (cudaMalloc / cudaFree of MB-sized blocks per call cost ~10 ms: profiles/r1_experiments.md)
+        const size_t need = (size_t)Cb * (size_t)(nv + per_scr + (1 + nt) + (1 + nv));
+        if (c->hb_elems < need) {
+            cudaFree(c->d_hb); c->d_hb = nullptr; c->hb_elems = 0;
+            const size_t cap = (size_t)kBgMaxC * (size_t)(nv + per_scr + (1 + nt) + (1 + nv));   // room for a full 64-chain pass
+            CU_TRY(cudaMalloc((void **)&c->d_hb, cap * 8));
+            c->hb_elems = cap;
         }
+        double *d_v = c->d_hb, *d_scr = d_v + (size_t)Cb * nv, *d_fg = d_scr + (size_t)Cb * per_scr, *d_o = d_fg + (size_t)Cb * (1 + nt);
+        CU_TRY(cudaMemcpyAsync(d_v, V + c0 * nv, (size_t)Cb * nv * 8, cudaMemcpyHostToDevice, c->stream));
+        // one block per chain: chain k's variables / scratch / coefficient column / [logL, G] row / output sit k strides on
+        HierParams hp = hp0;
+        hp.variables = d_v;
+        hp.mu = d_scr; hp.gA = hp.mu + nj; hp.gB = hp.gA + nj; hp.gM = hp.gB + nj; hp.Asum = hp.gM + nj; hp.cum = hp.Asum + nj;
+        hp.tmpj = hp.cum + nj; hp.Ajk = d_scr + 10 * nj;
+        hp.coeffs = c->d_X;                     // column k of the coefficient matrix the GEMMs read
+        hp.fg_out = d_fg; hp.out = d_o; hp.out_host = nullptr;
+        hp.bs_vars = nv; hp.bs_scratch = per_scr; hp.bs_coeffs = nt; hp.bs_fg = 1 + nt; hp.bs_out = 1 + nv;
+        sfh_hier_prologue_kernel<<<(unsigned)Cb, kHierThreads, 0, c->stream>>>(hp);
+        CU_TRY(cudaGetLastError());
         SFH_TRY(enqueue_batched_impl(c, c->d_X, Cb, c->d_logl, want_G ? c->d_resid : nullptr, false));
         if (want_G && nt > 0) {
             SFH_TRY(enqueue_bgrad(c, Cb, nsplit, d_fg, 1 + nt, 1));
@@ -1451,11 +1450,9 @@ extern "C" int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *m
             }
         }
         CU_TRY(cudaMemcpy2DAsync(d_fg, (size_t)(1 + nt) * 8, c->d_logl, 8, 8, (size_t)Cb, cudaMemcpyDeviceToDevice, c->stream));
-        for (int64_t k = 0; k < Cb; ++k) {
-            sfh_hier_epilogue_kernel<<<1, kHierThreads, 0, c->stream>>>(params_of(k), want_G);
-            CU_TRY(cudaGetLastError());
-        }
-        c->stats.kernel_launches += 2 * Cb;
+        sfh_hier_epilogue_kernel<<<(unsigned)Cb, kHierThreads, 0, c->stream>>>(hp, want_G);
+        CU_TRY(cudaGetLastError());
+        c->stats.kernel_launches += 2;
         std::vector<double> h((size_t)Cb * (1 + nv));
         CU_TRY(cudaMemcpyAsync(h.data(), d_o, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));

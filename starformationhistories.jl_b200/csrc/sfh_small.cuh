@@ -272,7 +272,22 @@ struct HierParams {
     const double *fg_out;                    // [1+nt]: logL raw, +M'r  (input of the epilogue)
     double *out;                             // [1 + nj + 3]: -logL (guarded), G
     double *out_host;                        // nullable: mapped pinned host copy of `out`
+    // batched launches (grid = chains): block k works on chain k, whose arrays sit k strides further on
+    int64_t bs_vars, bs_scratch, bs_coeffs, bs_fg, bs_out;   // element strides; all 0 for a single evaluation
 };
+
+// chain blockIdx.x of a batched launch (identity for the single-evaluation launches: all strides are 0)
+__device__ __forceinline__ HierParams hier_chain_params(const HierParams &p0) {
+    HierParams p = p0;
+    const int64_t k = blockIdx.x;
+    p.variables += k * p0.bs_vars;
+    p.mu += k * p0.bs_scratch; p.gA += k * p0.bs_scratch; p.gB += k * p0.bs_scratch; p.gM += k * p0.bs_scratch;
+    p.Asum += k * p0.bs_scratch; p.cum += k * p0.bs_scratch; p.tmpj += k * p0.bs_scratch; p.Ajk += k * p0.bs_scratch;
+    p.coeffs += k * p0.bs_coeffs;
+    p.fg_out += k * p0.bs_fg;
+    p.out += k * p0.bs_out;
+    return p;
+}
 
 __device__ __forceinline__ double d_X_from_Z(double Z, double Yp, double gam) { return 1.0 - ((Yp + gam * Z) + Z); }
 
@@ -311,7 +326,8 @@ constexpr int kHierThreads = 1024;
 constexpr int kHierSmemAges = 1024;  // per-age scratch staged in shared memory up to this many unique ages
 
 // calculate_coeffs: mzr.jl:50-79 / amr.jl:50-73
-__global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const HierParams p) {
+__global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const HierParams p0) {
+    const HierParams p = hier_chain_params(p0);
     griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierThreads / 32;
     const int nj = p.nj;
@@ -366,7 +382,8 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const H
 }
 
 // chain rule: mzr.jl:124-210 / amr.jl:118-169.  fullG = d logL/d r = -(fg_out[1+t]).
-__global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const HierParams p, int want_G) {
+__global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const HierParams p0, int want_G) {
+    const HierParams p = hier_chain_params(p0);
     griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierThreads / 32;
     const int nj = p.nj;
