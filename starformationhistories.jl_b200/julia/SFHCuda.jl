@@ -148,6 +148,19 @@ function batched_fg(models::DeviceStack, X::Matrix{Float64}; want_G::Bool=true)
     return nl, G
 end
 
+# Hierarchical fg! for C variable vectors at once (every chain task of tsample_sfh, generic_fitting.jl:617-626).
+# V is (Nj + nparams) x C in natural units; returns (-logL[C], G[(Nj + nparams), C]).
+function batched_fg(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion, V::Matrix{Float64},
+                    models::DeviceStack, logAge, MH)
+    c = bind!(models, logAge, MH)
+    nl = Vector{Float64}(undef, size(V, 2)); G = similar(V)
+    free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)..., false]
+    check(ccall((:sfh_eval_fg_hier_batched, libsfh), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}),
+                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), V, size(V, 2), free, nl, G))
+    return nl, G
+end
+
 # The whole stretch-move ensemble sampler on the device: replaces KissMCMC.emcee(MCMCModel(...), x0; ...) inside
 # mcmc_sample (mcmc_sample.jl:104).  x0 is ntemplates x nwalkers (nwalkers even); returns samples shaped like
 # convert_kissmcmc (:30-44) -- (nsteps / nthin, ntemplates, nwalkers) -- their log-likelihoods and the acceptance fraction.
