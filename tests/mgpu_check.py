@@ -75,6 +75,13 @@ def main():
     na = S.fg_(True, Ga, mz, dp, v, w2, d, None, p["logAge"], p["MH"])
     nb_ = S.fg_(True, Gb, mz, dp, v, s2, d, None, p["logAge"], p["MH"])
     assert abs(na - nb_) <= 1e-12 * abs(na) and np.allclose(Ga, Gb, rtol=1e-8, atol=1e-10 * np.abs(Ga).max())
+    # ... and for several variable vectors at once (sfh_eval_fg_hier_batched over shards)
+    Vb = v[:, None] * (1 + 0.03 * np.random.default_rng(8).standard_normal((15, 7)))
+    nla2, Gha = S.hierarchical.fg_batched_(mz, dp, Vb, w2, d, p["logAge"], p["MH"])
+    nlb2, Ghb = S.hierarchical.fg_batched_(mz, dp, Vb, s2, d, p["logAge"], p["MH"])
+    assert np.allclose(nla2, nlb2, rtol=1e-12) and np.allclose(Gha, Ghb, rtol=1e-8, atol=1e-10 * np.abs(Gha).max())
+    g1 = np.empty(15); n1 = S.fg_(True, g1, mz, dp, Vb[:, 4], s2, d, None, p["logAge"], p["MH"])
+    assert abs(n1 - nlb2[4]) <= 1e-12 * abs(n1) and np.allclose(g1, Ghb[:, 4], rtol=1e-8, atol=1e-10 * np.abs(g1).max())
     # the counter-based synthetic generator: shards of one big diagram == the whole
     xs = 10 * np.random.default_rng(3).random(500)
     ws = S.DeviceStack.synthetic(40000, 500, np.float32, 7, 1.0, xs, device=local)
