@@ -7,8 +7,10 @@
 // contraction whose Nb x W result is never materialised: the Poisson term is applied to the FP64
 // accumulators in registers and reduced over bins inside the kernel.
 //
-// FP64 throughout (tcgen05 has no FP64 kind; B200's FP64 tensor rate equals its FP64 FMA rate, so
-// the contraction runs on the FP64 pipe with an 8x8 register tile per thread).
+// FP64 throughout.  tcgen05 has no FP64 kind, so the tensor path for this dtype is mma.sync.m8n8k4.f64 (DMMA): the
+// shipped kernel is sfh_batched_logl_mma_kernel below; sfh_batched_logl_kernel (v1, FP64-FMA 8x8 register tiles) is kept
+// selectable (SFH_BATCHED_IMPL=fma) as the baseline the DMMA kernel was measured against.  The same file holds K6g, the
+// batched gradient GEMM G = M'R used by sfh_eval_fg_batched / sfh_eval_fg_hier_batched.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -151,12 +153,13 @@ __global__ void __launch_bounds__(kBwThreads) sfh_batched_logl_kernel(const S *_
 // kernel compute-bound (FP64 pipe 43 % busy, DRAM ~2 %) with its issue slots and shared-memory wavefronts spent
 // on operand delivery (8 LDS.128 + 64 DFMA per thread per k); one DMMA replaces 8 warp-wide DFMA and its
 // fragments need 5x fewer shared-memory wavefronts.  tcgen05 has no FP64 kind, so mma.sync is the tensor path
-// for this dtype.  CTA tile 128 bins x 128 walkers, 16 warps (4 x 4), warp tile 32 x 32 = 4 x 4 DMMA tiles,
-// BK = 16 templates per slab, 3-stage cp.async pipeline; rows padded by 4 doubles => conflict-free fragment loads.
+// for this dtype.  Warp tile 32 bins x 8*NBW walkers = 4 x NBW DMMA tiles, BK = 16 templates per slab, 3-stage cp.async
+// pipeline; rows padded by 4 doubles => conflict-free fragment loads.
 // ------------------------------------------------------------------------------------------
 // WN = warps along the walker axis, NBW = 8-walker MMA blocks per warp: CTA tile = 128 bins x 8*NBW*WN walkers, 4*WN warps.
-// (WN, NBW) = (4, 4) for walker ensembles; (1, 1) / (1, 2) / (1, 4) / (2, 4) for the 8 / 16 / 32 / 64-chain batches of
-// sfh_eval_fg_batched (a 128-wide tile would waste up to 16x the math and make a few-chain pass compute-bound).
+// Shipped shapes: (1, 4) = 32 walkers, 4 warps, 3 CTAs/SM for every W > 16 (never slower than the 64- and 128-wide
+// tiles (2, 4) / (4, 4), up to 14 % faster: profiles/r1_experiments.md), (1, 2) / (1, 1) for W <= 16 / W <= 8 -- the
+// few-chain batches of sfh_eval_fg_batched, where a wider tile would only multiply zeros.
 #ifndef SFH_MMA_STAGES
 #define SFH_MMA_STAGES 3
 #endif
