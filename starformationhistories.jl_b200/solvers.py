@@ -252,7 +252,7 @@ def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None
     x0 = np.asarray(x0, dtype=np.float64)
     if x0.shape[0] != nj:
         raise ValueError("length(x0) != length(unique(logAge))")
-    full = calculate_coeffs(MH_model0, disp_model0, x0, la, mh)           # :260
+    full = calculate_coeffs(MH_model0, disp_model0, x0, la, mh, models=ds)  # :260 (device prologue kernel)
     if np.isnan(full).any():
         raise ValueError("initial metallicity-model parameters give NaN coefficients (generic_fitting.jl:261-283)")
     x0 = renormalize_x0(data, ds, x0, full)                                # :283
