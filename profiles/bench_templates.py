@@ -25,10 +25,15 @@ def main(nx=200, ny=300, nage=60, nmh=40, cov_y=1):
     pts = [S.template_points(m, mg, err, cov_y, (0, 1), imf, comp, None, dmod, 1e7, 0.35, edges) for (m, mg) in isos]
     t_prep = time.perf_counter() - t0
     npts = sum(len(p[0]) for p in pts)
+    import gc
     S.DeviceStack.from_points(edges, pts[:8])                                   # warm-up (context, module load)
-    t0 = time.perf_counter()
-    ds = S.DeviceStack.from_points(edges, pts)
-    t_dev = time.perf_counter() - t0
+    t_dev = float("inf")
+    for _ in range(3):                                                          # best of 3; earlier stacks are freed OUTSIDE the timed region
+        ds = None
+        gc.collect()
+        t0 = time.perf_counter()
+        ds = S.DeviceStack.from_points(edges, pts)
+        t_dev = min(t_dev, time.perf_counter() - t0)
     # CPU oracle on a sample of templates, 1 thread
     sample = list(range(0, len(pts), max(1, len(pts) // 24)))[:24]
     t0 = time.perf_counter()
@@ -38,9 +43,11 @@ def main(nx=200, ny=300, nage=60, nmh=40, cov_y=1):
     M, _ = ds.download()
     err_max = max(np.abs(M[:, k] - cols[k].reshape(-1, order="F")).max() / cols[k].max() for k in sample)
     # what the upload path costs for the same stack (host-built templates -> sfh_stack_create)
+    gc.collect()
     t0 = time.perf_counter()
-    S.DeviceStack(M, np.zeros(M.shape[0]))
+    up = S.DeviceStack(M, np.zeros(M.shape[0]))
     t_up = time.perf_counter() - t0
+    del up
     print(json.dumps({"what": f"build {len(pts)} templates of {nx}x{ny} bins from {npts} isochrone points (cov_mult={pts[0][5]})",
                       "host_point_prep_s": t_prep, "device_build_s": t_dev, "templates_per_s_device": len(pts) / t_dev,
                       "cpu_oracle_ms_per_template_1thread": t_cpu * 1e3, "cpu_oracle_s_all_templates_1thread": t_cpu * len(pts),

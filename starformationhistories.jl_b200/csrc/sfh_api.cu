@@ -1631,13 +1631,13 @@ extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t
             // enough (template, band) warps to fill the machine, never more bands than rows
             const int64_t want = (int64_t)std::max(s->sm_count, 1) * 48;
             int64_t nbands = std::min<int64_t>(ny, std::max<int64_t>(1, (want + tc - 1) / tc));
-            // a warp keeps nx + band_h factors of the current point in shared memory: tall diagrams get more, shorter bands
-            const int64_t max_band_h = (int64_t)(200 * 1024) / (kScatterWarps * 8) - nx;
+            // a warp keeps nx + 6*band_h factors of the current point in shared memory: tall diagrams get more, shorter bands
+            const int64_t max_band_h = ((int64_t)(200 * 1024) / (kScatterWarps * 8) - nx) / 6;
             if (max_band_h < 1) return fail(SFH_ERR_SHAPE, "Hess diagram too wide for the scatter kernel (%lld bins along x)", (long long)nx);
             nbands = std::max(nbands, (ny + max_band_h - 1) / max_band_h);
             const int64_t band_h = (ny + nbands - 1) / nbands;
             nbands = (ny + band_h - 1) / band_h;
-            const size_t smem = (size_t)kScatterWarps * (size_t)(nx + band_h) * 8;
+            const size_t smem = (size_t)kScatterWarps * (size_t)(nx + 6 * band_h) * 8;
             CU_TRY(cudaFuncSetAttribute(sfh_templates_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
             sp.t0 = t0; sp.tc = tc; sp.nbands = (int32_t)nbands; sp.band_h = (int32_t)band_h;
             CU_TRY(cudaMemsetAsync(d_scr, 0, (size_t)tc * nbins * 8, 0));

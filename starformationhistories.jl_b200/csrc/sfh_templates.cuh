@@ -11,7 +11,8 @@
 // given order; lanes take the pixels of the cut-out that fall inside the band.  No atomics: every pixel receives its
 // contributions in point order -- the association of the reference's sequential loop (:585, :611) -- so the result
 // is deterministic and independent of the launch geometry.  The separable kernel evaluates its 2(w + h) erf
-// differences once per point into per-warp shared memory instead of 4 erf per pixel.
+// differences once per point into per-warp shared memory instead of 4 erf per pixel; the covariant kernel hoists its
+// three per-row exponentials (Gauss-Legendre nodes in y) the same way and keeps 6 erf per pixel.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -44,8 +45,8 @@ __global__ void __launch_bounds__(kScatterWarps * 32) sfh_templates_scatter_kern
     if (wid >= p.tc * p.nbands) return;
     const int64_t tl = wid / p.nbands;
     const int band = (int)(wid % p.nbands);
-    double *fx = sm_f + (size_t)wl * (size_t)(p.nx + p.band_h);   // [nx] x-factors of the current point
-    double *fy = fx + p.nx;                                        // [band_h]
+    double *fx = sm_f + (size_t)wl * (size_t)(p.nx + 6 * p.band_h);   // [nx] x-factors of the current point
+    double *fy = fx + p.nx;                                            // [band_h] (separable kernel) / [band_h][3][2] (covariant)
     const int64_t jb0 = (int64_t)band * p.band_h + 1;              // 1-based rows of this band
     const int64_t jb1 = min(p.ny, (int64_t)(band + 1) * p.band_h);
     double *img = p.scratch + (size_t)tl * (size_t)(p.nx * p.ny);
@@ -76,8 +77,9 @@ __global__ void __launch_bounds__(kScatterWarps * 32) sfh_templates_scatter_kern
             }
             __syncwarp();
             const double a4 = A / 4;
-            for (int64_t e = lane; e < w * h; e += 32) {
-                const int64_t k = e % w, m = e / w;
+            const uint32_t wu = (uint32_t)w, npx = (uint32_t)(w * h);   // 32-bit pixel arithmetic: a cut-out never exceeds nx * band_h
+            for (uint32_t e = lane; e < npx; e += 32) {
+                const uint32_t m = e / wu, k = e - m * wu;
                 img[(xa + k - 1) + p.nx * (ja + m - 1)] += a4 * fx[k] * fy[m];
             }
             __syncwarp();
@@ -94,20 +96,30 @@ __global__ void __launch_bounds__(kScatterWarps * 32) sfh_templates_scatter_kern
             const double hx = p.xstep / 2, hy = p.ystep / 2;
             const double prefac = A / 2 / sqrt(2.0 * 3.14159265358979323846) / ey;
             const double cm = (double)cov;
-            for (int64_t e = lane; e < w * h; e += 32) {
-                const int64_t k = e % w, m = e / w;
-                const double xv = ((double)(xa + k) - 0.5) * p.xstep + p.xfirst;                  // histogram_data(i + 1/2) (:525)
-                const double yv = ((double)(ja + m) - 0.5) * p.ystep + p.yfirst;
+            // per (row, Gauss-Legendre node): weight * exp(-(Dy/sy)^2 / 2) and the x shift Dy * cov_mult -- they do not
+            // depend on the column, so they are evaluated once per row instead of once per pixel (:321-329)
+            for (uint32_t k = lane; k < 3u * (uint32_t)h; k += 32) {
+                const uint32_t m = k / 3u;
+                const int g = (int)(k - 3u * m);
+                const double gx = (g == 0) ? -0.7745966692414834 : (g == 1 ? 0.0 : 0.7745966692414834);
+                const double gw = (g == 1) ? 0.8888888888888888 : 0.5555555555555556;
+                const double yv = ((double)(ja + m) - 0.5) * p.ystep + p.yfirst;                  // histogram_data(j + 1/2) (:525)
+                const double Dy = (gx * hy + yv) - yr;
+                const double t = Dy / ey;
+                fy[2 * k] = (gw * hy) * exp(-(t * t) / 2);
+                fy[2 * k + 1] = Dy * cm;
+            }
+            __syncwarp();
+            const uint32_t wu = (uint32_t)w, npx = (uint32_t)(w * h);
+            for (uint32_t e = lane; e < npx; e += 32) {
+                const uint32_t m = e / wu, k = e - m * wu;
+                const double xv = ((double)(xa + k) - 0.5) * p.xstep + p.xfirst;
                 const double dx = xv - xr;
                 double r = 0.0;
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {                                                      // :321-331
-                    const double gx = (g == 0) ? -0.7745966692414834 : (g == 1 ? 0.0 : 0.7745966692414834);
-                    const double gw = (g == 1) ? 0.8888888888888888 : 0.5555555555555556;
-                    const double Dy = (gx * hy + yv) - yr;
-                    const double Dx = dx + Dy * cm;
-                    const double t = Dy / ey;
-                    r += (gw * hy) * exp(-(t * t) / 2) * (erf((Dx + hx) / s2 / ex) + erf((-Dx + hx) / s2 / ex));
+                for (int g = 0; g < 3; ++g) {
+                    const double Dx = dx + fy[2 * (3 * m + g) + 1];
+                    r += fy[2 * (3 * m + g)] * (erf((Dx + hx) / s2 / ex) + erf((-Dx + hx) / s2 / ex));
                 }
                 img[(xa + k - 1) + p.nx * (ja + m - 1)] += r * prefac;
             }
