@@ -74,3 +74,33 @@ def test_host_restatement_of_the_ensemble_sampler_samples_a_gaussian():
     assert chain.shape == (300, 3, 40) and 0.2 < acc < 0.9
     v = chain[100:].transpose(1, 0, 2).reshape(3, -1).var(axis=1)
     assert np.all(np.abs(v * prec - 1) < 0.35)
+
+
+def test_dense_mass_nuts_samples_a_correlated_gaussian():
+    """nuts_chain with a dense M^-1 (what sample_sfh passes: MAP.invH, generic_fitting.jl:479-482) and a fixed step size."""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((4, 4))
+    cov = A @ A.T + 0.5 * np.eye(4)
+    prec = np.linalg.inv(cov)
+    lg = lambda th: (float(-0.5 * th @ prec @ th), -(prec @ th))
+    s, lps, eps = V.nuts_sample(lg, np.zeros(4), 1500, 0, 6, rng=np.random.default_rng(6), inv_mass=cov, eps0=0.6)
+    assert eps == 0.6 and s.shape == (1500, 4)                     # no warm-up: the step size stays the one given
+    emp = np.cov(s[200:].T)
+    assert np.all(np.abs(emp - cov) < 0.35 * np.sqrt(np.outer(np.diag(cov), np.diag(cov))))
+    # a diagonal inverse mass given as a vector or as a diagonal matrix walks the same trajectory
+    d = np.array([1.0, 4.0, 0.25, 2.0])
+    a = V.nuts_sample(lg, np.zeros(4), 40, 10, 5, rng=np.random.default_rng(7), inv_mass=d)
+    b = V.nuts_sample(lg, np.zeros(4), 40, 10, 5, rng=np.random.default_rng(7), inv_mass=np.diag(d))
+    assert np.allclose(a[0], b[0], rtol=1e-9, atol=1e-12)
+
+
+def test_expand_posterior_transforms_and_fixed_rows():
+    """Transformed samples -> natural units over all variables with fixed parameters written in (generic_fitting.jl:640-658)."""
+    import types
+    mz, dp = S.PowerLawMZR(1.0, -1.5, 6.0, (True, False)), S.GaussianDispersion(0.2, (True,))
+    best = V.BFGSResult(np.array([10.0, 20.0, 1.0, -1.5, 0.2]), np.zeros(5), np.eye(4), types.SimpleNamespace(x=np.zeros(4)), mz, dp)
+    Z = np.array([[0.0, 1.0], [np.log(3.0), 0.0], [np.log(2.0), np.log(0.5)], [np.log(0.3), np.log(0.1)]])   # R1, R2, alpha, sigma
+    out = V._expand_posterior(best, Z)
+    assert out.shape == (5, 2)
+    assert np.allclose(out[0], [1.0, np.e]) and np.allclose(out[1], [3.0, 1.0]) and np.allclose(out[2], [2.0, 0.5])
+    assert np.all(out[3] == -1.5) and np.allclose(out[4], [0.3, 0.1])
