@@ -12,7 +12,8 @@
 // contributions in point order -- the association of the reference's sequential loop (:585, :611) -- so the result
 // is deterministic and independent of the launch geometry.  The separable kernel evaluates its 2(w + h) erf
 // differences once per point into per-warp shared memory instead of 4 erf per pixel; the covariant kernel hoists its
-// three per-row exponentials (Gauss-Legendre nodes in y) the same way and keeps 6 erf per pixel.
+// three per-row exponentials (Gauss-Legendre nodes in y) the same way and evaluates erf at pixel EDGES, shared between
+// neighbouring pixels by shuffle (3 (w+1)/w instead of 6 per pixel).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -110,18 +111,25 @@ __global__ void __launch_bounds__(kScatterWarps * 32) sfh_templates_scatter_kern
                 fy[2 * k + 1] = Dy * cm;
             }
             __syncwarp();
-            const uint32_t wu = (uint32_t)w, npx = (uint32_t)(w * h);
-            for (uint32_t e = lane; e < npx; e += 32) {
-                const uint32_t m = e / wu, k = e - m * wu;
-                const double xv = ((double)(xa + k) - 0.5) * p.xstep + p.xfirst;
-                const double dx = xv - xr;
+            // erf(+(Dx + hx)/a) + erf((-Dx + hx)/a) of :326-327 is erf(right edge) - erf(left edge) of the pixel, and the right
+            // edge of pixel k is the left edge of pixel k + 1: lanes evaluate EDGES (3 erf each, one per Gauss-Legendre node)
+            // and take the neighbour's by shuffle -- 3 (w + 1) / w erf per pixel instead of 6.  Edges are flattened over the
+            // rows of the cut-out; an iteration advances by 31 so that lane 31's edge is lane 0's of the next one.
+            const uint32_t wu = (uint32_t)w, we = wu + 1, nedge = we * (uint32_t)h;
+            const double inv_a = 1.0 / (s2 * ex);
+            for (uint32_t base = 0; base < nedge; base += 31) {
+                const uint32_t e = base + lane;
+                const bool valid = e < nedge;
+                const uint32_t m = valid ? e / we : 0u, j = valid ? e - m * we : 0u;
+                const double xe = (((double)(xa + j) - 1.0) * p.xstep + p.xfirst) - xr;             // left edge of pixel xa + j
                 double r = 0.0;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    const double Dx = dx + fy[2 * (3 * m + g) + 1];
-                    r += fy[2 * (3 * m + g)] * (erf((Dx + hx) / s2 / ex) + erf((-Dx + hx) / s2 / ex));
+                    const double E = erf((xe + fy[2 * (3 * m + g) + 1]) * inv_a);
+                    const double En = __shfl_down_sync(0xffffffffu, E, 1);
+                    r += fy[2 * (3 * m + g)] * (En - E);
                 }
-                img[(xa + k - 1) + p.nx * (ja + m - 1)] += r * prefac;
+                if (valid && lane < 31 && j < wu) img[(xa + j - 1) + p.nx * (ja + m - 1)] += r * prefac;
             }
             __syncwarp();
         }
