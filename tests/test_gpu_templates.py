@@ -44,7 +44,9 @@ def test_device_scatter_matches_oracle(S, nx, ny, T, npts):
     M, _ = ds.download()
     ref = _oracle_stack(pls, xe, ye)
     scale = np.abs(ref).max(axis=0, keepdims=True) + 1e-300
-    assert np.all(np.abs(M - ref) <= 1e-12 * scale), np.max(np.abs(M - ref) / scale)
+    # 3e-12 of each template's peak: both sides round pixel-edge coordinates (values ~1, widths ~1e-2) at 1e-16 and a pixel
+    # sums hundreds of points; measured 1e-13 .. 1.6e-12 (profiles/r1_templates.txt)
+    assert np.all(np.abs(M - ref) <= 3e-12 * scale), np.max(np.abs(M - ref) / scale)
     assert not M[:, 1].any()
     # deterministic: a second build is bit-identical
     M2, _ = S.DeviceStack.from_points((xe, ye), pls).download()
@@ -92,7 +94,7 @@ def test_bin_cmd_smooth_and_partial_cmd_smooth(S):
         pts = S.template_points(m_ini, [F1, F2, F3], err, y_index, ci, imf, comp, None, dmod, 1e7, 0.35, edges)
         assert pts[5] == (1 if y_index == 1 else (-1 if y_index == 0 else 0))
         ref = O.bin_cmd_smooth(*pts[:4], pts[5], pts[4], 74, edges[0][0], edges[0][1] - edges[0][0], 99, edges[1][0], edges[1][1] - edges[1][0])
-        assert np.all(np.abs(W - ref) <= 1e-12 * ref.max())
+        assert np.all(np.abs(W - ref) <= 3e-12 * ref.max())
     with pytest.raises(NotImplementedError):
         S.partial_cmd_smooth(m_ini, [F1, F2], err[:2], 1, (0, 1), imf, comp[:2], binary_model=object(), mean_mass=0.35, edges=edges)
     with pytest.raises(ValueError):
