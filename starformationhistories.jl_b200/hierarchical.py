@@ -159,6 +159,13 @@ def nparams(*models): return sum(m.nparams() for m in models)     # hierarchical
 def _bind(ds: DeviceStack, logAge, MH):
     """sfh_hier_bind once per (context, logAge, MH): the grouping of mzr.jl:131-140."""
     ctx = ds.ctx()
+    # fast path: the same array OBJECTS as last time (every driver passes the arrays it captured once, cf. SURVEY 8b) with
+    # unchanged end points -- skips hashing 2 x T doubles on every evaluation
+    last = getattr(ctx, "bound_objs", None)
+    if (last is not None and last[0] is logAge and last[1] is MH and isinstance(logAge, np.ndarray) and isinstance(MH, np.ndarray)
+            and logAge.shape == last[2] and (logAge[0], logAge[-1], MH[0], MH[-1]) == last[3]):
+        return ctx
+    ctx.bound_objs = None
     la = np.ascontiguousarray(logAge, dtype=np.float64)
     mh = np.ascontiguousarray(MH, dtype=np.float64)
     if la.shape != mh.shape:
@@ -170,6 +177,8 @@ def _bind(ds: DeviceStack, logAge, MH):
         n = C.c_int64()
         L.check(L.lib.sfh_hier_bind(ctx.handle, _dp(la), _dp(mh), C.byref(n)))
         ctx.bound_key, ctx.n_ages = key, int(n.value)
+    if isinstance(logAge, np.ndarray) and isinstance(MH, np.ndarray) and la.shape[0] > 0:
+        ctx.bound_objs = (logAge, MH, logAge.shape, (logAge[0], logAge[-1], MH[0], MH[-1]))
     return ctx
 
 
@@ -275,38 +284,50 @@ class HierarchicalOptimizer:
         free = list(self.MH_model0.free_params()) + list(self.disp_model0.free_params())
         return _bind(self.models, self.logAge, self.metallicities).n_ages + sum(free)
 
+    def _layout(self, nx):
+        """Index sets of generic_fitting.jl:107-145 for an input of length nx (cached: they only depend on the models)."""
+        lay = getattr(self, "_lay", None)
+        if lay is None or lay[0] != nx:
+            tf = np.array(list(self.MH_model0.transforms()) + list(self.disp_model0.transforms()))
+            free = np.array(list(self.MH_model0.free_params()) + list(self.disp_model0.free_params()), dtype=bool)
+            npar = tf.shape[0]
+            nbins = nx - npar + int((~free).sum())                         # :116-118
+            init = np.array(list(self.MH_model0.fittable_params()) + list(self.disp_model0.fittable_params()), dtype=np.float64)
+            pos = np.zeros(nbins + npar, dtype=bool); pos[:nbins] = True
+            pos[nbins:] = (tf == 1) & free                                 # :143-145
+            neg = np.zeros(nbins + npar, dtype=bool); neg[nbins:] = (tf == -1) & free
+            lay = (nx, tf, free, npar, nbins, init, pos, neg, tf[free])
+            self._lay = lay
+        return lay
+
     def logdensity_and_gradient(self, xvec):
         """generic_fitting.jl:90-199.  Returns (+logp, +grad) over the FREE transformed variables
         (only ``logp`` / only ``grad`` when ``G`` / ``F`` is None)."""
         xvec = np.asarray(xvec, dtype=np.float64)
         ret_F, ret_G = self.F is not None, self.G is not None
-        tf = np.array(list(self.MH_model0.transforms()) + list(self.disp_model0.transforms()))
-        free = np.array(list(self.MH_model0.free_params()) + list(self.disp_model0.free_params()), dtype=bool)
-        npar = tf.shape[0]
-        nbins = xvec.shape[0] - npar + int((~free).sum())                  # :116-118
+        _, tf, free, npar, nbins, init, pos, neg, tfree = self._layout(xvec.shape[0])
         x = np.empty(nbins + npar)
         x[:nbins] = np.exp(xvec[:nbins])                                   # :127
-        x[nbins:][free] = exptransform(xvec[nbins:], tf[free])             # :129-131
-        init = np.array(list(self.MH_model0.fittable_params()) + list(self.disp_model0.fittable_params()))
+        xp = xvec[nbins:]
+        x[nbins:][free] = np.where(tfree == 1, np.exp(xp), np.where(tfree == -1, -np.exp(xp), xp))   # :129-131
         x[nbins:][~free] = init[~free]                                     # :134-136
         G2 = np.empty_like(x) if ret_G else None
         nlogL = fg_(self.F, G2, self.MH_model0, self.disp_model0, x, self.models, self.data, None,
                     self.logAge, self.metallicities)                       # :140
-        ptf = [i for i in range(npar) if tf[i] == 1 and free[i]]           # :143-145
-        idxs = list(range(nbins)) + [nbins + i for i in ptf]
-        ntf = [nbins + i for i in range(npar) if tf[i] == -1 and free[i]]
+        has_neg = bool(neg.any())
         if self.jacobian_corrections:                                      # :148-160
-            for i in idxs:
-                if ret_F: nlogL -= math.log(x[i])
-                if ret_G: G2[i] = G2[i] * x[i] - 1
-            for i in ntf:
-                if ret_F: nlogL += math.log(x[i])
-                if ret_G: G2[i] = -G2[i] * x[i] + 1
-        else:                                                              # :161-169 (with the +Nbins the reference forgets)
-            for i in idxs:
-                if ret_G: G2[i] = G2[i] * x[i]
-            for i in ntf:
-                if ret_G: G2[i] = -G2[i] * x[i]
+            if ret_F:
+                nlogL -= float(np.log(x[pos]).sum())
+                if has_neg:
+                    nlogL += float(np.log(x[neg]).sum())
+            if ret_G:
+                G2[pos] = G2[pos] * x[pos] - 1
+                if has_neg:
+                    G2[neg] = -G2[neg] * x[neg] + 1
+        elif ret_G:                                                        # :161-169 (with the +Nbins the reference forgets)
+            G2[pos] = G2[pos] * x[pos]
+            if has_neg:
+                G2[neg] = -G2[neg] * x[neg]
         if not ret_G:
             return -nlogL if ret_F else None                               # :172-178
         G = np.empty_like(xvec)
