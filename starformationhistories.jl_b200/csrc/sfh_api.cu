@@ -1629,7 +1629,8 @@ extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t
         for (int64_t t0 = 0; t0 < ntemplates; t0 += tc_max) {
             const int64_t tc = std::min(tc_max, ntemplates - t0);
             // enough (template, band) warps to fill the machine, never more bands than rows
-            const int64_t want = (int64_t)std::max(s->sm_count, 1) * 48;
+            static const int want_mult = [] { const char *e = getenv("SFH_SCATTER_WARPS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 48; }();
+            const int64_t want = (int64_t)std::max(s->sm_count, 1) * want_mult;
             int64_t nbands = std::min<int64_t>(ny, std::max<int64_t>(1, (want + tc - 1) / tc));
             // a warp keeps nx + 6*band_h factors of the current point in shared memory: tall diagrams get more, shorter bands
             const int64_t max_band_h = ((int64_t)(200 * 1024) / (kScatterWarps * 8) - nx) / 6;

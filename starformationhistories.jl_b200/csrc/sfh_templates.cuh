@@ -34,12 +34,15 @@ struct ScatterParams {
 };
 
 constexpr int kScatterWarps = 4;
+#ifndef SFH_SCATTER_MINB
+#define SFH_SCATTER_MINB 1
+#endif
 
 __device__ __forceinline__ int64_t clamp_to_i64(double v) {   // ceil/rint results of absurd widths stay defined
     return (v < 4.0e9) ? ((v > -4.0e9) ? (int64_t)v : (int64_t)-4000000000LL) : (int64_t)4000000000LL;
 }
 
-__global__ void __launch_bounds__(kScatterWarps * 32) sfh_templates_scatter_kernel(const ScatterParams p) {
+__global__ void __launch_bounds__(kScatterWarps * 32, SFH_SCATTER_MINB) sfh_templates_scatter_kernel(const ScatterParams p) {
     extern __shared__ double sm_f[];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int64_t wid = (int64_t)blockIdx.x * kScatterWarps + wl;
