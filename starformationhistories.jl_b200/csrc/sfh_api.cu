@@ -1336,7 +1336,18 @@ int ensure_bgrad_capacity(sfh_ctx *c, int &nsplit_out) {
     sfh_stack *s = c->s;
     const int64_t nt = s->nt, wld = c->wld;
     const int64_t n_tt = std::max<int64_t>((nt + kBgBM - 1) / kBgBM, 1);
-    const int nsplit = (int)std::min<int64_t>(32, std::max<int64_t>(1, (2 * std::max(s->sm_count, 1) + n_tt - 1) / n_tt));
+    // split-K over bins: pick the split whose CTAs (all co-resident, <= 4 per SM) load the busiest SM least --
+    // ceil(CTAs / SMs) / nsplit -- with a small charge per split for the partial sums (ncu: 304 CTAs on 148 SMs left
+    // 8 SMs with 3 CTAs and the other 140 idle for a third of the kernel; 285 CTAs are 2 per SM at most)
+    const int sms = std::max(s->sm_count, 1);
+    int nsplit = 1;
+    double best = 1e300;
+    for (int k = 1; k <= 32; ++k) {
+        const int64_t per_sm = (n_tt * k + sms - 1) / sms;
+        if (per_sm > 4) break;
+        const double cost = (double)per_sm / k + 5e-4 * k;
+        if (cost < best) { best = cost; nsplit = k; }
+    }
     if (c->bg_cap < c->wcap || c->bg_nsplit != nsplit) {
         cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG);
         c->d_resid = c->d_bgpart = c->d_bG = nullptr; c->bg_cap = 0;
