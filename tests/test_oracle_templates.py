@@ -96,3 +96,38 @@ def test_host_helpers_doctests():
     # calculate_weights: trapezoid of the IMF pdf over each mass segment (:765-776)
     w = T.calculate_weights([1.0, 2.0, 4.0], [0.5, 1.0, 1.0], lambda mm: np.asarray(mm) ** -2.0, 10.0, 2.0)
     assert np.allclose(w, [1.0 * (1 + 0.25) / 2 * 0.5 * 5, 2.0 * (0.25 + 0.0625) / 2 * 1.0 * 5])
+
+
+def test_template_points_follow_partial_cmd_smooth():
+    """The per-point arguments handed to bin_cmd_smooth (src/StarFormationHistories.jl:829-888): kernel choice, colour error,
+    completeness product, IMF weights, bias, midpoints -- host numpy, no device."""
+    m = np.linspace(0.2, 1.2, 60)
+    B, Vm, R = 6.0 - 7.0 * np.log10(m), 5.5 - 6.5 * np.log10(m), 5.0 - 6.0 * np.log10(m)
+    edges = (np.linspace(-0.5, 1.5, 41), np.linspace(20.0, 32.0, 61))
+    err = [lambda x: 0.01 + 0.0 * x, lambda x: 0.02 + 0.0 * x, lambda x: 0.03 + 0.0 * x]
+    comp = [lambda x: 0.9 + 0.0 * x, lambda x: 0.8 + 0.0 * x, lambda x: 0.5 + 0.0 * x]
+    bias = [lambda x: 0.1 + 0.0 * x, lambda x: 0.0 * x, lambda x: -0.2 + 0.0 * x]
+    imf = lambda mm: np.asarray(mm) ** -2.35
+    kw = dict(dmod=24.0, normalize_value=1e4, mean_mass=0.5, edges=edges)
+    # y = V, x = B - V: covariant kernel, cov_mult = +1, colour error = sigma_B alone, completeness = product of B and V (:857-869)
+    c, y, ce, ye, w, cov = S.template_points(m, [B, Vm, R], err, 1, (0, 1), imf, comp, bias, **kw)
+    n = c.shape[0]
+    assert cov == 1 and y.shape == ce.shape == ye.shape == w.shape == (n,)
+    assert np.allclose(ce, 0.01) and np.allclose(ye, 0.02)
+    new_m, sp = T.mini_spacing(m, B - Vm, Vm, min(0.05, 0.2), True)
+    assert n == new_m.shape[0] - 1
+    pdf = imf(new_m)
+    assert np.allclose(w, sp * (pdf[:-1] + pdf[1:]) / 2 * (0.9 * 0.8) * 1e4 / 0.5)                     # :765-776
+    Bi, Vi = T.interpolate_mini(m, B, new_m) + 24.0, T.interpolate_mini(m, Vm, new_m) + 24.0
+    assert np.allclose(c, T.midpoints((Bi + 0.1) - Vi)) and np.allclose(y, T.midpoints(Vi))           # bias: measured = intrinsic + bias
+    # y = B: cov_mult = -1 and the colour error is sigma_V
+    _, _, ce, ye, _, cov = S.template_points(m, [B, Vm, R], err, 0, (0, 1), imf, comp, bias, **kw)
+    assert cov == -1 and np.allclose(ce, 0.02) and np.allclose(ye, 0.01)
+    # y = R (not in the colour): separable kernel, colour error in quadrature, completeness of all three filters (:870-881)
+    _, y, ce, ye, w3, cov = S.template_points(m, [B, Vm, R], err, 2, (0, 1), imf, comp, bias, **kw)
+    assert cov == 0 and np.allclose(ce, np.hypot(0.01, 0.02)) and np.allclose(ye, 0.03)
+    assert w3.sum() == pytest.approx(w.sum() * 0.5, rel=0.05)                                          # extra completeness factor 0.5
+    with pytest.raises(ValueError):
+        S.template_points(m, [B, Vm], err, 1, (0, 1), imf, comp, bias, **kw)                          # length(mags) mismatch (:841)
+    with pytest.raises(ValueError):
+        S.template_points(m, [B, Vm, R], err, 1, (0, 1, 2), imf, comp, bias, **kw)                    # length(color_indices) == 2 (:840)
