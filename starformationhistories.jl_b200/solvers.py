@@ -179,6 +179,132 @@ def construct_x0(logAge, T_max, normalize_value=1.0):
     return sfr * np.diff(edges)[inv] / cnt[inv]
 
 
+def _unique_first(a):
+    """unique(a) in first-appearance order (Julia's `unique`)."""
+    a = np.asarray(a, dtype=np.float64)
+    _, first = np.unique(a, return_index=True)
+    return a[np.sort(first)]
+
+
+def construct_x0_mdf(logAge, *args, normalize_value=1.0):
+    """construct_x0_mdf (hierarchical/construct_x0_mdf.jl:58-117): one starting stellar mass per unique(logAge), in that order.
+    `construct_x0_mdf(logAge, T_max)`: constant star-formation rate; `construct_x0_mdf(logAge, cum_sfh, T_max)`: from a
+    cumulative SFH given on unique(logAge), or as a pair (logAge grid, cumulative SFH) that is interpolated onto it.
+    (The reference's index arithmetic -- the position in unique(logAge) of the i-th SORTED age indexes the SORTED widths,
+    :67-70 -- is restated as written: it is the intended pairing for ascending or descending ages.)"""
+    la = np.asarray(logAge, dtype=np.float64)
+    if len(args) == 1:
+        cum, T_max = None, args[0]
+    elif len(args) == 2:
+        cum, T_max = args
+    else:
+        raise TypeError("construct_x0_mdf(logAge, [cum_sfh,] T_max)")
+    max_logAge = math.log10(T_max) + 9
+    if not max_logAge > la.max():
+        raise ValueError("log10(T_max) + 9 > maximum(logAge) must hold")                # :59, :79
+    ua = _unique_first(la)
+    order = np.argsort(ua, kind="stable")
+    sorted_ul = np.concatenate([ua[order], [max_logAge]])
+    pos = {float(v): k for k, v in enumerate(ua)}
+    idx = np.array([pos[float(sorted_ul[i])] for i in range(ua.shape[0])])
+    if cum is None:
+        sfr = normalize_value / (10.0 ** max_logAge - 10.0 ** la.min())
+        return sfr * np.diff(10.0 ** sorted_ul)[idx]
+    if len(cum) == 2 and np.ndim(cum[0]) == 1 and np.ndim(cum[1]) == 1 and len(cum[0]) == len(cum[1]) and len(cum[0]) != 1 \
+            and not np.isscalar(cum[0]):
+        gla, gcs = np.asarray(cum[0], dtype=np.float64), np.asarray(cum[1], dtype=np.float64)
+        if gcs.max() > 1:
+            raise ValueError("Maximum of cumulative SFH must be less than or equal to one")   # :106
+        o = np.argsort(gla, kind="stable")
+        cum = np.interp(ua, np.concatenate([gla[o], [max_logAge]]), np.concatenate([gcs[o], [0.0]]))   # Flat() extrapolation
+    cum = np.asarray(cum, dtype=np.float64)
+    if cum.min() < 0:
+        raise ValueError("minimum(cum_sfh) >= 0 must hold")                              # :75
+    if cum.shape[0] != ua.shape[0]:
+        raise ValueError("`length(unique(logAge))` not equal to `length(cum_sfh)`.")     # :82
+    sc = np.concatenate([cum[order], [0.0]])
+    if np.any(np.diff(sc) > 0):
+        raise ValueError("Provided `cum_sfh` must be monotonically increasing as `logAge` decreases.")   # :87
+    return normalize_value * (sc[idx] - sc[idx + 1])
+
+
+def truncate_relweights(relweightsmin, relweights, logAge):
+    """truncate_relweights (hierarchical/fixed_amr.jl:229-243): indices (0-based) of the templates whose relative weight is
+    at least `relweightsmin` times the largest one of their age, grouped by unique(logAge) in first-appearance order."""
+    rw, la = np.asarray(relweights, dtype=np.float64), np.asarray(logAge, dtype=np.float64)
+    if rw.shape != la.shape:
+        raise ValueError("length(relweights) == length(logAge) must hold")
+    if relweightsmin == 0:
+        return np.arange(rw.shape[0])
+    keep = []
+    for a in _unique_first(la):
+        good = np.nonzero(la == a)[0]
+        keep.append(good[rw[good] >= relweightsmin * rw[good].max()])
+    return np.concatenate(keep)
+
+
+def fixed_amr(models, data, logAge, metallicities, relweights, relweightsmin=0, x0=None, g_abstol=1e-8, iterations=5000):
+    """fixed_amr (hierarchical/fixed_amr.jl:41-180): one stellar-mass coefficient per unique(logAge) under externally imposed
+    relative weights; BFGS on log-coefficients, MAP (Jacobian term) then MLE seeded from it.  Every objective evaluation is
+    one fused `fg!` on the device; the per-age contraction of the gradient (:119-121, :147-151) is O(T) on the host.
+    Returns {"map": ..., "mle": ...} with mu, sigma (sqrt of diag(invH), log space, :173-174), invH, result."""
+    la = np.asarray(logAge, dtype=np.float64)
+    mh = np.asarray(metallicities, dtype=np.float64)
+    rw = np.array(relweights, dtype=np.float64)
+    ua = _unique_first(la)
+    if x0 is None:
+        x0 = construct_x0_mdf(la, 13.7)
+    x0 = np.asarray(x0, dtype=np.float64)
+    if x0.shape[0] != ua.shape[0]:
+        raise ValueError("length(x0) == length(unique(logAge)) must hold")               # :50
+    if not (la.shape == mh.shape == rw.shape):
+        raise ValueError("size(models,2) == length(logAge) == length(metallicities) == length(relweights) must hold")
+    if np.any(rw < 0):
+        raise ValueError("all relative weights must be >= 0")                            # :53
+    if relweightsmin < 0:
+        raise ValueError("relweightsmin >= 0 must hold")                                 # :54
+    if relweightsmin != 0:                                                              # :58-64: a narrower stack
+        keep = truncate_relweights(relweightsmin, rw, la)
+        if isinstance(models, DeviceStack):
+            Mh, _ = models.download()
+            data = models.download_data() if data is None else data
+        else:
+            Mh = np.asarray(models) if not isinstance(models, (list, tuple)) else np.stack([np.asarray(m).reshape(-1, order="F") for m in models], axis=1)
+        models = np.asfortranarray(Mh[:, keep])
+        data = np.asarray(data).reshape(-1, order="F")
+        la, mh, rw = la[keep], mh[keep], rw[keep]
+    ds = device_stack(models, data)
+    if ds.shape[1] != la.shape[0]:
+        raise ValueError("size(models,2) == length(logAge) must hold")                   # :52
+    inv = np.array([int(np.nonzero(ua == a)[0][0]) for a in la])                        # template -> age (idxlogAge, :80)
+    sums = np.bincount(inv, weights=rw, minlength=ua.shape[0])
+    if not np.allclose(sums, 1.0):                                                      # :66-77
+        if relweightsmin == 0:
+            import warnings
+            warnings.warn("The relative weights provided to `fixed_amr` do not sum to 1 for every logAge and will be renormalized.")
+        rw = rw / sums[inv]
+    x0 = renormalize_x0(data, ds, x0, rw * x0[inv])                                      # :83-88
+
+    def make(jac):
+        def fun(xvec):
+            x = np.exp(xvec)
+            coeffs = rw * x[inv]                                                         # :106-108
+            nl, G, _ = ds.eval_fg(coeffs)                                                # -logL and +M'r = -fullG
+            g = np.bincount(inv, weights=G * coeffs, minlength=ua.shape[0])              # -sum(fullG[j] coeffs[j])  (:120, :150)
+            if jac:
+                return nl - xvec.sum(), g - 1                                            # :112, :120
+            return nl, g
+        return fun
+    res = {}
+    start = np.log(x0)
+    for key, jac in (("map", True), ("mle", False)):                                     # :166-167
+        r = _bfgs(make(jac), start, g_abstol, iterations)
+        start = r.x
+        invH = np.asarray(r.hess_inv)
+        res[key] = {"mu": np.exp(r.x), "sigma": np.sqrt(np.abs(np.diag(invH))), "invH": invH, "result": r}
+    return res
+
+
 def calculate_cum_sfr(coeffs, logAge, MH, T_max, normalize_value=1, sorted=False):
     """calculate_cum_sfr (fitting/utilities.jl:153-195): (unique_logAge ascending, cumulative SFH normalised to 1 at the
     youngest bin, SFR per bin with `logAge` as left edges and `T_max` [Gyr] the last right edge, mass-weighted <[M/H]>)."""

@@ -161,6 +161,33 @@ def test_sample_sfh_and_tsample_sfh(S, V):                          # mzr_test.j
     assert np.allclose(many["posterior_matrix"][:, ::20], seq["posterior_matrix"][:, ::20], rtol=1e-6)
 
 
+def test_fixed_amr_recovers_sfrs(S, V):                            # fixed_amr_test.jl:56-110
+    rng = np.random.Generator(np.random.Philox(58392))
+    uA, uM = np.linspace(10.0, 8.0, 12), np.linspace(-2.5, 0.0, 15)
+    la, mh = np.repeat(uA, 15), np.tile(uM, 12)
+    mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
+    SFRs = rng.random(12)
+    x = S.calculate_coeffs(mz, dp, SFRs, la, mh)
+    models = [rng.random((30, 25)) * 100 for _ in range(la.shape[0])]
+    data = sum(c * m for c, m in zip(x, models))
+    x0 = S.construct_x0_mdf(la, 13.7, normalize_value=1)
+    relw = S.calculate_coeffs(mz, dp, np.ones(12), la, mh)
+    res = S.fixed_amr(models, data, la, mh, relw, x0=x0)
+    assert np.allclose(res["mle"]["mu"], SFRs, rtol=1e-5) and res["mle"]["invH"].shape == (12, 12)   # :67
+    with pytest.warns(UserWarning):                                  # :72-74 badly normalised weights are renormalised
+        r2 = S.fixed_amr(models, data, la, mh, 2 * relw, x0=x0)
+    assert np.allclose(r2["mle"]["mu"], SFRs, rtol=1e-5)
+    # truncated template list: less accurate, still close (:76-108)
+    keep = S.truncate_relweights(0.05, relw, la)
+    sm = S.stack_models(models)
+    r3 = S.fixed_amr(sm[:, keep], data.reshape(-1, order="F"), la[keep], mh[keep], relw[keep], x0=x0, relweightsmin=0.0)
+    r4 = S.fixed_amr(models, data, la, mh, relw, relweightsmin=0.05, x0=x0)
+    assert not np.allclose(r3["mle"]["mu"], SFRs, rtol=1e-5) and np.allclose(r3["mle"]["mu"], SFRs, rtol=1e-2)
+    assert np.allclose(r3["mle"]["mu"], r4["mle"]["mu"], rtol=1e-6)
+    with pytest.raises(ValueError):
+        S.fixed_amr(models, data, la, mh, -relw, x0=x0)
+
+
 def test_mcmc_sample_shapes_and_oracle_chain(S, V):              # basic_linear_combinations.jl:120-154
     rng = np.random.Generator(np.random.Philox(7))
     N, nwalkers, nsteps = 10, 100, 20

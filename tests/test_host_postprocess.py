@@ -69,3 +69,36 @@ def test_rand_and_cum_sfr_quantiles_shapes():                      # utilities.j
     resf = _fake_result(nj, rng, free=(True, False), dfree=(False,))
     smp = resf.rand(rng, 50)
     assert np.all(smp[nj + 1] == -1.5) and np.all(smp[nj + 2] == 0.2) and np.all(smp[nj] > 0)
+
+
+def test_construct_x0_mdf_doctests():                             # hierarchical/construct_x0_mdf.jl:19-55
+    want = [4.504504504504504, 0.4504504504504504, 0.04504504504504504]
+    assert np.allclose(S.construct_x0_mdf([9.0, 8.0, 7.0], 10.0, normalize_value=5.0), want)
+    assert np.allclose(S.construct_x0_mdf(np.repeat([9.0, 8.0, 7.0, 8.0], 3), 10.0, normalize_value=5.0), want)
+    assert np.allclose(S.construct_x0_mdf(np.tile([9.0, 8.0, 7.0, 8.0], 3), 10.0, normalize_value=5.0),
+                       S.construct_x0([9.0, 8.0, 7.0], 10.0, normalize_value=5.0))
+    assert np.allclose(S.construct_x0_mdf([9.0, 8.0, 7.0], [0.9009, 0.99099, 1.0], 10.0, normalize_value=5.0), [4.5045, 0.4504, 0.0450], atol=1e-3)
+    assert np.allclose(S.construct_x0_mdf([9.0, 8.0, 7.0], [0.1, 0.5, 1.0], 10.0, normalize_value=5.0), [0.5, 2.0, 2.5])
+    assert np.allclose(S.construct_x0_mdf([7.0, 8.0, 9.0], [1.0, 0.5, 0.1], 10.0, normalize_value=5.0), [2.5, 2.0, 0.5])
+    a = S.construct_x0_mdf([9.0, 8.0, 7.0], [0.9009, 0.99099, 1.0], 10.0, normalize_value=5.0)
+    assert np.allclose(S.construct_x0_mdf([9.0, 8.0, 7.0], [[9.0, 8.0, 7.0], [0.9009, 0.99099, 1.0]], 10.0, normalize_value=5.0), a)
+    assert np.allclose(S.construct_x0_mdf([9.0, 8.0, 7.0], [[9.0, 8.5, 8.25, 7.0], [0.9009, 0.945945, 0.9887375, 1.0]], 10.0, normalize_value=5.0), a)
+    la = np.repeat(np.linspace(6.6, 10.1, 36), 5)                  # fixed_amr_test.jl:35-53
+    assert S.construct_x0_mdf(la, 13.7).sum() == pytest.approx(1) and S.construct_x0_mdf(la, 13.7, normalize_value=1e5).sum() == pytest.approx(1e5)
+    with pytest.raises(ValueError):
+        S.construct_x0_mdf([9.0, 8.0, 7.0], [0.5, 0.1, 1.0], 10.0)                                  # not monotonic
+    with pytest.raises(ValueError):
+        S.construct_x0_mdf([9.0, 10.2], 10.0)
+
+
+def test_truncate_relweights():                                   # fixed_amr.jl:229-243, fixed_amr_test.jl:76-104
+    la = np.array([10.0, 10.0, 10.0, 9.0, 9.0, 9.0, 9.0])
+    rw = np.array([0.02, 0.5, 0.48, 0.7, 0.2, 0.05, 0.05])
+    assert np.array_equal(S.truncate_relweights(0, rw, la), np.arange(7))
+    assert np.array_equal(S.truncate_relweights(0.1, rw, la), [1, 2, 3, 4])
+    assert np.array_equal(S.truncate_relweights(0.05, rw, la), [1, 2, 3, 4, 5, 6])
+    # the doc example (:199-224): 11 metallicities around a Gaussian MDF keep 3 templates at relweightsmin = 0.1
+    mhs = np.arange(-2.5, 0.01, 0.25)
+    w = np.exp(-0.5 * ((mhs + 2.0) / 0.2) ** 2); w /= w.sum()
+    assert np.allclose(w[:5], [0.021919934465195145, 0.2284109622221623, 0.4988954088848224, 0.2284109622221623, 0.021919934465195145])
+    assert np.array_equal(S.truncate_relweights(0.1, w, np.full(11, 10.0)), [1, 2, 3])
