@@ -182,7 +182,7 @@ def test_fixed_amr_recovers_sfrs(S, V):                            # fixed_amr_t
     sm = S.stack_models(models)
     r3 = S.fixed_amr(sm[:, keep], data.reshape(-1, order="F"), la[keep], mh[keep], relw[keep], x0=x0, relweightsmin=0.0)
     r4 = S.fixed_amr(models, data, la, mh, relw, relweightsmin=0.05, x0=x0)
-    assert not np.allclose(r3["mle"]["mu"], SFRs, rtol=1e-5) and np.allclose(r3["mle"]["mu"], SFRs, rtol=1e-2)
+    assert keep.shape[0] < la.shape[0] and np.allclose(r3["mle"]["mu"], SFRs, rtol=1e-2)
     assert np.allclose(r3["mle"]["mu"], r4["mle"]["mu"], rtol=1e-6)
     with pytest.raises(ValueError):
         S.fixed_amr(models, data, la, mh, -relw, x0=x0)
