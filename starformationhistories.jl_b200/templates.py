@@ -92,6 +92,42 @@ def exp_photerr(m, a, b, c, d):
 
 
 # ------------------------------------------------------------------------------------------------
+def bin_cmd(colors, mags, weights=None, edges=None, xlim=None, ylim=None, nbins=None, xwidth=None, ywidth=None):
+    """bin_cmd (:544-553): the weighted 2-D histogram of (colour, magnitude) points with left-closed bins [a, b)
+    (StatsBase `closed=:left`: a point on the last right edge is NOT counted).  This is how the observed Hess diagram
+    `data` of a fit is made.  Returns (weights matrix (nx, ny), (xedges, yedges))."""
+    colors = np.asarray(colors, dtype=np.float64)
+    mags = np.asarray(mags, dtype=np.float64)
+    w = np.ones(colors.shape) if weights is None else np.asarray(weights, dtype=np.float64)
+    if not (colors.shape == mags.shape == w.shape):
+        raise ValueError("length(colors) == length(mags) == length(weights) must hold")          # :550
+    xe, ye = calculate_edges(edges, xlim if xlim is not None else (colors.min(), colors.max()),
+                             ylim if ylim is not None else (mags.min(), mags.max()), nbins, xwidth, ywidth)
+    ix = np.searchsorted(xe, colors, side="right") - 1
+    iy = np.searchsorted(ye, mags, side="right") - 1
+    nx, ny = xe.shape[0] - 1, ye.shape[0] - 1
+    ok = (ix >= 0) & (ix < nx) & (iy >= 0) & (iy < ny)
+    out = np.zeros((nx, ny))
+    np.add.at(out, (ix[ok], iy[ok]), w[ok])
+    return out, (xe, ye)
+
+
+def partial_cmd(m_ini, colors, mags, imf, dmod=0.0, normalize_value=1.0, mean_mass=None, edges=None, xlim=None, ylim=None,
+                nbins=None, xwidth=None, ywidth=None):
+    """partial_cmd (:733-757): the unsmoothed template -- isochrone resampled to 0.01 mag spacing, IMF-weighted, binned."""
+    if mean_mass is None:
+        raise ValueError("mean_mass (the mean initial mass of the IMF) is required")
+    colors = np.asarray(colors, dtype=np.float64)
+    mags = np.asarray(mags, dtype=np.float64)
+    new_mini, spacing = mini_spacing(m_ini, colors, mags, 0.01, True)                          # :739
+    c = interpolate_mini(m_ini, colors, new_mini)
+    y = interpolate_mini(m_ini, mags, new_mini) + dmod
+    pdf = np.asarray(imf(new_mini), dtype=np.float64)
+    w = spacing * (pdf[:-1] + pdf[1:]) / 2 * normalize_value / mean_mass                        # :748-753
+    return bin_cmd(c[:-1], y[:-1], weights=w, edges=edges, xlim=xlim if xlim is not None else (colors.min(), colors.max()),
+                   ylim=ylim if ylim is not None else (mags.min(), mags.max()), nbins=nbins, xwidth=xwidth, ywidth=ywidth)
+
+
 def bin_cmd_smooth(colors, mags, color_err, mag_err, cov_mult=0, weights=None, edges=None, xlim=None, ylim=None,
                    nbins=None, xwidth=None, ywidth=None):
     """bin_cmd_smooth (:574-621) on the device: returns (weights matrix (nx, ny), (xedges, yedges))."""

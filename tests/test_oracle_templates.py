@@ -131,3 +131,23 @@ def test_template_points_follow_partial_cmd_smooth():
         S.template_points(m, [B, Vm], err, 1, (0, 1), imf, comp, bias, **kw)                          # length(mags) mismatch (:841)
     with pytest.raises(ValueError):
         S.template_points(m, [B, Vm, R], err, 1, (0, 1, 2), imf, comp, bias, **kw)                    # length(color_indices) == 2 (:840)
+
+
+def test_bin_cmd_and_partial_cmd():
+    """bin_cmd (:544-553): left-closed bins, weights; partial_cmd (:733-757): total weight = IMF mass of the isochrone span."""
+    xe, ye = np.linspace(0.0, 1.0, 5), np.linspace(10.0, 12.0, 3)          # 4 x 2 bins
+    c = np.array([0.0, 0.24, 0.25, 0.99, 1.0, -0.1, 0.5])
+    y = np.array([10.0, 10.99, 11.0, 11.99, 11.5, 10.5, 12.0])
+    H, ed = S.bin_cmd(c, y, edges=(xe, ye))
+    want = np.zeros((4, 2)); want[0, 0] = 2; want[1, 1] = 1; want[3, 1] = 1      # (1.0, .) and (., 12.0) sit on the excluded right edges
+    assert np.array_equal(H, want) and ed[0] is not None
+    H2, _ = S.bin_cmd(c, y, weights=np.arange(7.0), edges=(xe, ye))
+    assert H2[0, 0] == 0 + 1 and H2[1, 1] == 2 and H2[3, 1] == 3 and H2.sum() == 6
+    with pytest.raises(ValueError):
+        S.bin_cmd(c, y[:-1], edges=(xe, ye))
+    m = np.linspace(0.2, 1.2, 50)
+    col, mag = 1.0 - 0.5 * np.log10(m), 6.0 - 7.0 * np.log10(m)
+    imf = lambda mm: np.asarray(mm) ** -2.35
+    H3, _ = S.partial_cmd(m, col, mag, imf, dmod=20.0, normalize_value=100.0, mean_mass=0.5, edges=(np.linspace(0.5, 1.6, 23), np.linspace(24.0, 32.0, 81)))
+    mass = (1.2 ** -1.35 - 0.2 ** -1.35) / -1.35                         # integral of the pdf over the isochrone's mass range
+    assert H3.sum() == pytest.approx(mass * 100.0 / 0.5, rel=2e-3) and np.count_nonzero(H3) > 40
