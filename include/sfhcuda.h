@@ -44,10 +44,12 @@ typedef enum sfh_status {
     SFH_ERR_OOM = 5,         /* device or pinned-host allocation failed                                 */
     SFH_ERR_NCCL = 6,        /* NCCL missing or a collective failed                                     */
     SFH_ERR_UNSUPPORTED = 7, /* valid request this build cannot serve (e.g. not sm_100)                 */
-    SFH_ERR_NOT_BOUND = 8    /* hierarchical call before sfh_hier_bind                                  */
+    SFH_ERR_NOT_BOUND = 8,   /* hierarchical call before sfh_hier_bind                                  */
+    SFH_ERR_IO = 9           /* file missing, unreadable, truncated or failing its checksums            */
 } sfh_status;
 
-typedef enum sfh_dtype { SFH_F32 = 0, SFH_F64 = 1, SFH_I64 = 2 } sfh_dtype;
+/* SFH_U8 is valid for file arrays only (free-form metadata), never for a stack or its data */
+typedef enum sfh_dtype { SFH_F32 = 0, SFH_F64 = 1, SFH_I64 = 2, SFH_U8 = 3 } sfh_dtype;
 
 /* metallicity models with a device-side chain rule (hierarchical/mzr.jl:263-284,
  * hierarchical/amr.jl:181-213, :250-298) and the generic escape hatch */
@@ -172,6 +174,44 @@ int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t ny, double
                                  const double *colors, const double *mags, const double *color_err,
                                  const double *mag_err, const double *weights, const int32_t *cov_mult,
                                  int dtype, const void *data, int data_dtype, const sfh_opts *opts);
+
+/* ---- on-disk container for stacks and results ------------------------------------
+ * The reference defines no file format (users Serialization.serialize their templates by hand, examples/fitting1.ipynb
+ * cell 96).  This one is a little-endian, memory-mappable table of named arrays: a 128-byte header, one 128-byte entry
+ * per array, then the arrays, each on a 4096-byte boundary and stored as they sit in host memory (column-major), each
+ * with an order-independent 64-bit checksum (csrc/sfh_file.h documents the bytes; tests/file_ref.py restates them in
+ * numpy).  Files are written to a temporary name and renamed, so a reader never sees a partial file.              */
+typedef struct sfh_file sfh_file; /* a read-only mapping of one container file */
+typedef enum sfh_file_kind { SFH_FILE_GENERIC = 0, SFH_FILE_STACK = 1, SFH_FILE_RESULT = 2 } sfh_file_kind;
+typedef struct sfh_array_desc {
+    char name[48];      /* NUL-terminated, unique within the file                        */
+    int32_t dtype;      /* sfh_dtype                                                     */
+    int32_t ndim;       /* 1..4; dims[ndim..3] are 1                                     */
+    int64_t dims[4];    /* column-major: dims[0] varies fastest                          */
+    int64_t nbytes;     /* filled in by the library                                      */
+    uint64_t checksum;  /* filled in by the library                                      */
+} sfh_array_desc;
+/* sum over the 64-bit little-endian words w_i (tail zero-padded) of mix64(w_i xor (i+1)*0x9E3779B97F4A7C15), mod 2^64 */
+int sfh_checksum64(const void *data, int64_t nbytes, uint64_t *out);
+/* attrs8 (nullable): 8 free int64 attributes stored in the header.  ptrs[i] holds descs[i]'s dims in column-major order. */
+int sfh_file_write(const char *path, int kind, const int64_t *attrs8, int narrays, const sfh_array_desc *descs,
+                   const void *const *ptrs);
+int sfh_file_open(const char *path, sfh_file **out); /* validates header and array table, not the payloads */
+int sfh_file_close(sfh_file *f);                     /* idempotent on NULL; invalidates pointers from sfh_file_array */
+int sfh_file_info(const sfh_file *f, int *kind, int *narrays, int64_t *attrs8); /* each output nullable */
+int sfh_file_find(const sfh_file *f, const char *name, int *index);             /* *index = -1 when absent (still SFH_OK) */
+int sfh_file_array(const sfh_file *f, int index, sfh_array_desc *desc, const void **data); /* data points into the mapping */
+int sfh_file_verify(const sfh_file *f, int index);   /* recompute the checksum of one array (index < 0: all); SFH_ERR_IO on mismatch */
+
+/* A stack file (kind SFH_FILE_STACK) holds "models" (rows x ntemplates, F32/F64: the stack_models matrix of the rows it
+ * covers), "data" (rows, F64) and optionally "logAge" / "MH" (ntemplates, F64); attrs = {nbins_total, row_begin, row_end,
+ * nx, ny, stack dtype, 0, 0}.  sfh_stack_save copies the device stack (one bin-row shard, if sharded) straight into the
+ * mapped file in column blocks -- no host copy of the stack is made.  nx, ny (0 = unknown) record the Hess-diagram shape. */
+int sfh_stack_save(const sfh_stack *s, const char *path, int64_t nx, int64_t ny, const double *logAge, const double *MH);
+/* Upload a stack from a file.  opts->row_begin/row_end select the bin-row shard this process holds (it must lie inside
+ * the rows the file covers; 0,0 = all rows of the file): only those rows of the mapping are touched, so 8 ranks loading
+ * one 40 GB file each read an eighth of it.  verify != 0 checks the payload checksums first (reads the whole file).   */
+int sfh_stack_create_from_file(sfh_stack **out, const char *path, int verify, const sfh_opts *opts);
 
 /* ---- batched walkers (new; per-walker semantics of MCMCModel, fitting/mcmc_sample.jl:12-23) -- */
 /* X: ntemplates x W column-major.  logL[w] = -Inf if any X[:,w] < 0 (:15-19) else

@@ -16,7 +16,8 @@ from .fitting import (DeviceStack, clear_cache, composite_, device_stack, fg_ as
 from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR, LogarithmicAMR, PowerLawMZR,
                            calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams)
 from .sampling import HMCModel, MCMCModel
-from . import sharding, solvers
+from . import io, sharding, solvers
+from .io import SFHFile, load_result, read_arrays, save_result, write_arrays
 from .solvers import (calculate_cum_sfr, construct_x0, construct_x0_mdf, cum_sfr_quantiles, fixed_amr, truncate_relweights, fit_sfh, fit_templates, fit_templates_fast, fit_templates_lbfgsb,
                       hmc_sample, mcmc_sample, mdf_amr, rand_result, renormalize_x0, sample_sfh, tsample_sfh)
 from . import templates
@@ -41,4 +42,5 @@ __all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite
            "exptransform", "logtransform", "clear_cache", "device_stack", "shard_rows", "allreduce_fg", "guard_neg_logl",
            "init_library_comm", "fit_templates_lbfgsb", "fit_templates", "fit_templates_fast", "fit_sfh", "mcmc_sample",
            "hmc_sample", "renormalize_x0", "mdf_amr", "calculate_cum_sfr", "cum_sfr_quantiles", "rand_result", "construct_x0", "bin_cmd_smooth", "partial_cmd_smooth", "build_template_stack",
-           "template_points", "templates", "sample_sfh", "tsample_sfh", "fixed_amr", "truncate_relweights", "construct_x0_mdf", "bin_cmd", "partial_cmd"]
+           "template_points", "templates", "sample_sfh", "tsample_sfh", "fixed_amr", "truncate_relweights", "construct_x0_mdf", "bin_cmd", "partial_cmd",
+           "io", "SFHFile", "write_arrays", "read_arrays", "save_result", "load_result"]

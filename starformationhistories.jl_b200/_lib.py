@@ -22,8 +22,8 @@ lib = C.CDLL(LIB_PATH)
 
 # ---- enums (include/sfhcuda.h) -------------------------------------------------------------
 SFH_OK, SFH_ERR_INVALID_ARG, SFH_ERR_SHAPE, SFH_ERR_NO_DEVICE, SFH_ERR_CUDA = 0, 1, 2, 3, 4
-SFH_ERR_OOM, SFH_ERR_NCCL, SFH_ERR_UNSUPPORTED, SFH_ERR_NOT_BOUND = 5, 6, 7, 8
-SFH_F32, SFH_F64, SFH_I64 = 0, 1, 2
+SFH_ERR_OOM, SFH_ERR_NCCL, SFH_ERR_UNSUPPORTED, SFH_ERR_NOT_BOUND, SFH_ERR_IO = 5, 6, 7, 8, 9
+SFH_F32, SFH_F64, SFH_I64, SFH_U8 = 0, 1, 2, 3
 SFH_MH_POWERLAW_MZR, SFH_MH_LINEAR_AMR, SFH_MH_LOG_AMR = 0, 1, 2
 SFH_DISP_GAUSSIAN = 0
 
@@ -45,6 +45,11 @@ class sfh_info(C.Structure):
 
 class sfh_stats(C.Structure):
     _fields_ = [("evals", C.c_int64), ("kernel_launches", C.c_int64), ("last_device_ms", C.c_double)]
+
+
+class sfh_array_desc(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("dtype", C.c_int32), ("ndim", C.c_int32), ("dims", C.c_int64 * 4),
+                ("nbytes", C.c_int64), ("checksum", C.c_uint64)]
 
 
 _vp, _i64, _int, _dp = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)
@@ -87,6 +92,16 @@ PROTOTYPES = {
     "sfh_enqueue_logl_batched": (_int, [_vp, _vp, _i64, _vp]),
     "sfh_ctx_synchronize": (_int, [_vp]),
     "sfh_time_fg": (_int, [_vp, _dp, _int, _int, _int, _dp, _dp]),
+    "sfh_checksum64": (_int, [_vp, _i64, C.POINTER(C.c_uint64)]),
+    "sfh_file_write": (_int, [C.c_char_p, _int, C.POINTER(_i64), _int, C.POINTER(sfh_array_desc), C.POINTER(_vp)]),
+    "sfh_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
+    "sfh_file_close": (_int, [_vp]),
+    "sfh_file_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_i64)]),
+    "sfh_file_find": (_int, [_vp, C.c_char_p, C.POINTER(_int)]),
+    "sfh_file_array": (_int, [_vp, _int, C.POINTER(sfh_array_desc), C.POINTER(_vp)]),
+    "sfh_file_verify": (_int, [_vp, _int]),
+    "sfh_stack_save": (_int, [_vp, C.c_char_p, _i64, _i64, _dp, _dp]),
+    "sfh_stack_create_from_file": (_int, [C.POINTER(_vp), C.c_char_p, _int, C.POINTER(sfh_opts)]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

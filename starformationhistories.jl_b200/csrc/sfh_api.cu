@@ -24,6 +24,7 @@
 #include "sfh_small.cuh"
 #include "sfh_ensemble.cuh"
 #include "sfh_templates.cuh"
+#include "sfh_file.h"
 
 using namespace sfh;
 
@@ -452,11 +453,13 @@ int upload_data(sfh_stack *s, const void *data, int data_dtype, int64_t row_begi
 
 // host column-major (leading dimension host_ld rows) <-> device layout, in column blocks through a bounded staging
 // buffer, so even a 40 GB stack needs only 256 MB extra while it is re-tiled into panels
-int transfer_stack(const sfh_stack *s, void *host, int64_t host_ld, bool to_device) {
+// (host_row0 = the global bin row held in the host matrix's first row: non-zero when uploading from a shard file)
+int transfer_stack(const sfh_stack *s, void *host, int64_t host_ld, bool to_device, int64_t host_row0 = 0) {
     const size_t es = elem_size(s->dtype);
+    const size_t row_off = to_device ? (size_t)(s->row_begin - host_row0) : 0;
     if (!s->panel) {
         const cudaError_t e = to_device
-            ? cudaMemcpy2D(s->dM, (size_t)s->ld * es, (const char *)host + (size_t)s->row_begin * es, (size_t)host_ld * es,
+            ? cudaMemcpy2D(s->dM, (size_t)s->ld * es, (const char *)host + row_off * es, (size_t)host_ld * es,
                            (size_t)s->rows * es, (size_t)s->nt, cudaMemcpyHostToDevice)
             : cudaMemcpy2D(host, (size_t)host_ld * es, s->dM, (size_t)s->ld * es, (size_t)s->rows * es, (size_t)s->nt,
                            cudaMemcpyDeviceToHost);
@@ -470,7 +473,7 @@ int transfer_stack(const sfh_stack *s, void *host, int64_t host_ld, bool to_devi
     const int grid = std::max(s->sm_count, 1) * 8;
     for (int64_t j0 = 0; j0 < s->nt && e == cudaSuccess; j0 += jb) {
         const int64_t nc = std::min(jb, s->nt - j0);
-        char *hp = (char *)host + ((size_t)j0 * host_ld + (to_device ? (size_t)s->row_begin : 0)) * es;
+        char *hp = (char *)host + ((size_t)j0 * host_ld + row_off) * es;
         if (to_device) e = cudaMemcpy2D(blk, (size_t)s->rows * es, hp, (size_t)host_ld * es, (size_t)s->rows * es, (size_t)nc, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) break;
         if (s->dtype == SFH_F64)
@@ -1672,6 +1675,159 @@ extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t
     if (data) st = upload_data(s, data, data_dtype, s->row_begin);
     else if (s->rows > 0 && cudaMemset(s->d_data, 0, (size_t)s->rows * 8) != cudaSuccess) st = fail(SFH_ERR_CUDA, "memset failed");
     return done(st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// on-disk container (csrc/sfh_file.h): generic array files, stack save / load
+// ---------------------------------------------------------------------------------------------
+struct sfh_file { sfh::file::Reader r; };
+
+namespace {
+void fill_desc(const sfh::file::ArrayEntry &e, sfh_array_desc *d) {
+    memset(d, 0, sizeof *d);
+    memcpy(d->name, e.name, sizeof d->name);
+    d->dtype = e.dtype; d->ndim = e.ndim;
+    for (int k = 0; k < 4; ++k) d->dims[k] = e.dims[k];
+    d->nbytes = (int64_t)e.nbytes; d->checksum = e.checksum;
+}
+}  // namespace
+
+extern "C" int sfh_checksum64(const void *data, int64_t nbytes, uint64_t *out) {
+    if (!out || nbytes < 0 || (!data && nbytes > 0)) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    *out = sfh::file::checksum(data, (uint64_t)nbytes);
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_write(const char *path, int kind, const int64_t *attrs8, int narrays, const sfh_array_desc *descs,
+                              const void *const *ptrs) {
+    if (!path || narrays < 0 || (narrays > 0 && (!descs || !ptrs))) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    std::vector<sfh::file::ArraySpec> specs((size_t)narrays);
+    for (int i = 0; i < narrays; ++i) {
+        const sfh_array_desc &d = descs[i];
+        if (memchr(d.name, 0, sizeof d.name) == nullptr) return fail(SFH_ERR_INVALID_ARG, "array name %d is not NUL-terminated", i);
+        if (d.ndim < 1 || d.ndim > 4) return fail(SFH_ERR_INVALID_ARG, "array '%s': ndim must be 1..4", d.name);
+        specs[(size_t)i].name = d.name;
+        specs[(size_t)i].dtype = d.dtype; specs[(size_t)i].ndim = d.ndim;
+        int64_t n = 1;
+        for (int k = 0; k < 4; ++k) { specs[(size_t)i].dims[k] = k < d.ndim ? d.dims[k] : 1; if (k < d.ndim) n *= d.dims[k]; }
+        specs[(size_t)i].ptr = ptrs[i];
+        if (!ptrs[i] && n > 0) return fail(SFH_ERR_INVALID_ARG, "array '%s': NULL data", d.name);
+    }
+    sfh::file::Writer w;
+    std::string err;
+    if (!w.begin(path, kind, attrs8, specs, &err)) {
+        const bool arg = err.find("array") != std::string::npos;   // a bad spec, as opposed to a failing system call
+        return fail(arg ? SFH_ERR_INVALID_ARG : SFH_ERR_IO, "%s", err.c_str());
+    }
+    if (!w.commit(&err)) return fail(SFH_ERR_IO, "%s", err.c_str());
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_open(const char *path, sfh_file **out) {
+    if (!path || !out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    sfh_file *f = new (std::nothrow) sfh_file();
+    if (!f) return fail(SFH_ERR_OOM, "host allocation failed");
+    std::string err;
+    if (!f->r.open(path, &err)) { delete f; return fail(SFH_ERR_IO, "%s: %s", path, err.c_str()); }
+    *out = f;
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_close(sfh_file *f) {
+    delete f;
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_info(const sfh_file *f, int *kind, int *narrays, int64_t *attrs8) {
+    if (!f) return fail(SFH_ERR_INVALID_ARG, "NULL file");
+    if (kind) *kind = f->r.header().kind;
+    if (narrays) *narrays = f->r.count();
+    if (attrs8) memcpy(attrs8, f->r.header().attrs, 8 * sizeof(int64_t));
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_find(const sfh_file *f, const char *name, int *index) {
+    if (!f || !name || !index) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *index = f->r.find(name);
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_array(const sfh_file *f, int index, sfh_array_desc *desc, const void **data) {
+    if (!f) return fail(SFH_ERR_INVALID_ARG, "NULL file");
+    if (index < 0 || index >= f->r.count()) return fail(SFH_ERR_INVALID_ARG, "array index %d outside [0,%d)", index, f->r.count());
+    if (desc) fill_desc(f->r.entry(index), desc);
+    if (data) *data = f->r.data(index);
+    return SFH_OK;
+}
+
+extern "C" int sfh_file_verify(const sfh_file *f, int index) {
+    if (!f) return fail(SFH_ERR_INVALID_ARG, "NULL file");
+    if (index >= f->r.count()) return fail(SFH_ERR_INVALID_ARG, "array index %d outside [0,%d)", index, f->r.count());
+    for (int i = (index < 0 ? 0 : index); i < (index < 0 ? f->r.count() : index + 1); ++i)
+        if (!f->r.verify(i)) return fail(SFH_ERR_IO, "array '%s' fails its checksum", f->r.entry(i).name);
+    return SFH_OK;
+}
+
+extern "C" int sfh_stack_save(const sfh_stack *s, const char *path, int64_t nx, int64_t ny, const double *logAge, const double *MH) {
+    if (!s || !path) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    if ((logAge == nullptr) != (MH == nullptr)) return fail(SFH_ERR_INVALID_ARG, "logAge and MH go together");
+    if (nx < 0 || ny < 0 || (nx * ny != 0 && nx * ny != s->nb_total))
+        return fail(SFH_ERR_SHAPE, "nx*ny = %lld is not the number of bins %lld", (long long)(nx * ny), (long long)s->nb_total);
+    CU_TRY(cudaSetDevice(s->device));
+    std::vector<sfh::file::ArraySpec> specs(2);
+    specs[0].name = "models"; specs[0].dtype = s->dtype; specs[0].ndim = 2; specs[0].dims[0] = s->rows; specs[0].dims[1] = s->nt;
+    specs[1].name = "data"; specs[1].dtype = SFH_F64; specs[1].ndim = 1; specs[1].dims[0] = s->rows;
+    if (logAge) {
+        specs.resize(4);
+        specs[2].name = "logAge"; specs[2].dims[0] = s->nt; specs[2].ptr = logAge;
+        specs[3].name = "MH"; specs[3].dims[0] = s->nt; specs[3].ptr = MH;
+    }
+    const int64_t attrs[8] = {s->nb_total, s->row_begin, s->row_end, nx, ny, s->dtype, 0, 0};
+    sfh::file::Writer w;
+    std::string err;
+    if (!w.begin(path, SFH_FILE_STACK, attrs, specs, &err)) return fail(SFH_ERR_IO, "%s", err.c_str());
+    if (s->rows > 0 && s->nt > 0) SFH_TRY(transfer_stack(s, w.section(0), s->rows, false));
+    if (s->rows > 0) CU_TRY(cudaMemcpy(w.section(1), s->d_data, (size_t)s->rows * 8, cudaMemcpyDeviceToHost));
+    if (!w.commit(&err)) return fail(SFH_ERR_IO, "%s", err.c_str());
+    return SFH_OK;
+}
+
+extern "C" int sfh_stack_create_from_file(sfh_stack **out, const char *path, int verify, const sfh_opts *opts) {
+    if (!out || !path) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    if (opts && opts->struct_size != (int32_t)sizeof(sfh_opts))
+        return fail(SFH_ERR_INVALID_ARG, "sfh_opts.struct_size mismatch (%d vs %zu)", opts->struct_size, sizeof(sfh_opts));
+    sfh::file::Reader r;
+    std::string err;
+    if (!r.open(path, &err)) return fail(SFH_ERR_IO, "%s: %s", path, err.c_str());
+    const int im = r.find("models"), id = r.find("data");
+    if (r.header().kind != SFH_FILE_STACK || im < 0 || id < 0) return fail(SFH_ERR_IO, "%s is not a stack file", path);
+    const sfh::file::ArrayEntry &em = r.entry(im), &ed = r.entry(id);
+    const int64_t nb_total = r.header().attrs[0], fb = r.header().attrs[1], fe = r.header().attrs[2];
+    if ((em.dtype != SFH_F32 && em.dtype != SFH_F64) || em.ndim != 2 || ed.dtype != SFH_F64 || ed.ndim != 1 || fb < 0 || fe < fb ||
+        fe > nb_total || em.dims[0] != fe - fb || ed.dims[0] != fe - fb)
+        return fail(SFH_ERR_IO, "%s: stack arrays inconsistent with the header attributes", path);
+    if (verify && (!r.verify(im) || !r.verify(id))) return fail(SFH_ERR_IO, "%s: payload fails its checksum", path);
+    sfh_opts o;
+    memset(&o, 0, sizeof o);
+    if (opts) o = *opts;
+    o.struct_size = (int32_t)sizeof(sfh_opts);
+    if (o.row_begin == 0 && o.row_end == 0) { o.row_begin = fb; o.row_end = fe; }
+    if (o.row_begin < fb || o.row_end > fe || o.row_begin > o.row_end)
+        return fail(SFH_ERR_SHAPE, "row shard [%lld,%lld) outside the rows [%lld,%lld) the file holds", (long long)o.row_begin,
+                    (long long)o.row_end, (long long)fb, (long long)fe);
+    if (o.row_begin == 0 && o.row_end == 0 && nb_total > 0)   // (0,0 would read as "all rows" below)
+        return fail(SFH_ERR_SHAPE, "%s holds / was asked for an empty row shard", path);
+    sfh_stack *s = new (std::nothrow) sfh_stack();
+    if (!s) return fail(SFH_ERR_OOM, "host allocation failed");
+    int st = stack_common_init(s, nb_total, em.dims[1], em.dtype, &o);
+    if (st == SFH_OK && s->rows > 0 && s->nt > 0) st = transfer_stack(s, const_cast<void *>(r.data(im)), fe - fb, true, fb);
+    if (st == SFH_OK) st = upload_data(s, r.data(id), SFH_F64, s->row_begin - fb);
+    if (st == SFH_OK) st = setup_fused(s, &o);
+    if (st != SFH_OK) { sfh_stack_destroy(s); return st; }
+    *out = s;
+    return SFH_OK;
 }
 
 extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,

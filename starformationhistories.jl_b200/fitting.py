@@ -194,6 +194,51 @@ class DeviceStack:
         self._data_id = None
         return self
 
+    @classmethod
+    def from_file(cls, path, device=0, rows=None, verify=False, tile_bins=0, cluster=0, force_unfused=False, consumer_warps=0,
+                  variant=0):
+        """Upload a stack written by :meth:`save` (include/sfhcuda.h: sfh_stack_create_from_file).  ``rows`` selects the
+        bin-row shard of this process; only those rows of the memory-mapped file are read.  ``verify`` recomputes the
+        payload checksums first (reads the whole file).  ``logAge`` / ``MH`` / ``hess_shape`` are restored when stored."""
+        from .io import KIND_STACK, SFHFile
+        with SFHFile(path) as f:
+            if f.kind != KIND_STACK or "models" not in f:
+                raise ValueError(f"{path} is not a stack file")
+            nb_total, fb, fe, nx, ny = f.attrs[:5]
+            dm = f.describe("models")
+            logAge = f.read("logAge") if "logAge" in f else None
+            MH = f.read("MH") if "MH" in f else None
+        self = cls.__new__(cls)
+        self.shape = (int(nb_total), int(dm["shape"][1]))
+        self.dtype = np.dtype(dm["dtype"])
+        self.logAge, self.MH = logAge, MH
+        self.hess_shape = (int(nx), int(ny)) if nx * ny else None
+        o = L.sfh_opts()
+        o.struct_size = C.sizeof(L.sfh_opts)
+        o.device = device
+        if rows is not None:
+            o.row_begin, o.row_end = int(rows[0]), int(rows[1])
+        o.tile_bins, o.cluster, o.force_unfused, o.consumer_warps = tile_bins, cluster, int(force_unfused), consumer_warps
+        o.variant = variant
+        h = C.c_void_p()
+        L.check(L.lib.sfh_stack_create_from_file(C.byref(h), str(path).encode(), int(bool(verify)), C.byref(o)))
+        self._finish_init(h)
+        self._data_id = None
+        return self
+
+    def save(self, path, logAge=None, MH=None, hess_shape=None):
+        """Write this stack (the bin-row shard it holds) and its data to ``path`` (sfh_stack_save): the device copy goes
+        straight into the memory-mapped file in column blocks, no host copy of the stack is made."""
+        if (logAge is None) != (MH is None):
+            raise ValueError("logAge and MH go together")
+        la = np.ascontiguousarray(logAge, dtype=np.float64) if logAge is not None else None
+        mh = np.ascontiguousarray(MH, dtype=np.float64) if MH is not None else None
+        if la is not None and not (la.shape == mh.shape == (self.shape[1],)):
+            raise ValueError("size(models,2) == length(logAge) == length(metallicities) must hold")
+        nx, ny = (int(hess_shape[0]), int(hess_shape[1])) if hess_shape is not None else (0, 0)
+        L.check(L.lib.sfh_stack_save(self.handle, str(path).encode(), nx, ny, _dp(la) if la is not None else None,
+                                     _dp(mh) if mh is not None else None))
+
     @staticmethod
     def _destroy(h, ctxs):
         for c in ctxs:
