@@ -239,6 +239,58 @@ int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *mh_fixed, in
 int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, int64_t nthin, double a_scale, uint64_t seed,
                  double *chain, double *logl_chain, double *logl_final, double *accept_frac);
 
+/* ---- native driver loops (csrc/sfh_drivers.h) ---------------------------------------
+ * The reference's fit_templates (src/fitting/solvers.jl:163-221), fit_templates_fast (:238-275), fixed_amr
+ * (fitting/hierarchical/fixed_amr.jl:41-180) and fit_sfh (fitting/hierarchical/generic_fitting.jl:242-411) all run
+ * Optim.optimize(only_fg!(...), x0, BFGS(alphaguess = InitialStatic(1.0, true), linesearch = HagerZhang())) and read the
+ * final inverse Hessian off the trace.  These entry points run that loop (dense BFGS, strong-Wolfe line search) natively
+ * around the device evaluations, so one call = one whole optimisation and only the answer crosses the boundary.  The
+ * engine is third-party in the reference: iterates differ, converged answers and the role of invH do not.        */
+typedef int (*sfh_objective_fn)(void *user, const double *x, int64_t n, double *f, double *g); /* 0 = OK, else aborts */
+typedef struct sfh_bfgs_opts {
+    int32_t struct_size;   /* = sizeof(sfh_bfgs_opts)                                                            */
+    int32_t alphaguess;    /* 0 = default (1); 1: InitialStatic(1.0, scaled = true) like the reference; 2: from the */
+                           /* previous decrease (Nocedal & Wright p. 59)                                         */
+    double g_abstol;       /* stop when max|g_i| <= g_abstol; 0 = 1e-8 (solvers.jl:206)                          */
+    int64_t maxiter;       /* 0 = 5000 (solvers.jl:203)                                                          */
+} sfh_bfgs_opts;
+typedef struct sfh_bfgs_report {
+    double f, g_norm;             /* objective and max|g_i| at the returned point                               */
+    int64_t iterations, f_calls;
+    int32_t converged;            /* 1: g_norm <= g_abstol                                                      */
+    int32_t status;               /* 0 converged; 1 iteration limit; 2 line search failed; 3 start not finite   */
+} sfh_bfgs_report;
+/* x: n doubles, in = start, out = minimiser.  invH (nullable): n x n column-major final inverse-Hessian estimate.   */
+int sfh_minimize_bfgs(sfh_objective_fn fn, void *user, int64_t n, double *x, const sfh_bfgs_opts *opts,
+                      sfh_bfgs_report *report, double *invH);
+/* fit_templates / fit_templates_fast on the resident stack.  theta (ntemplates, in/out) lives in the fitting space:
+ *   SFH_FIT_LOG_MAP   theta = log coeffs, objective -logL - sum(theta), gradient G*x - 1      (solvers.jl:178-186)
+ *   SFH_FIT_LOG_MLE   theta = log coeffs, objective -logL,              gradient G*x          (solvers.jl:187-195)
+ *   SFH_FIT_SQRT_MLE  theta = sqrt coeffs, objective -logL,             gradient 2 G theta    (solvers.jl:254-261)  */
+typedef enum sfh_fit_transform { SFH_FIT_LOG_MAP = 0, SFH_FIT_LOG_MLE = 1, SFH_FIT_SQRT_MLE = 2 } sfh_fit_transform;
+int sfh_fit_templates_bfgs(sfh_ctx *c, int transform, double *theta, const sfh_bfgs_opts *opts,
+                           sfh_bfgs_report *report, double *invH);
+/* fixed_amr (fixed_amr.jl:96-167): coeffs_k = relweights_k * exp(theta[age_index_k]), one theta per unique logAge
+ * (age_index: 0-based position of template k's age in unique(logAge), n_ages of them); gradient contracted per age
+ * (:119-121, :147-151); jacobian != 0 adds the -sum(theta) / -1 terms of the MAP objective (:112, :120).           */
+int sfh_fit_fixed_amr_bfgs(sfh_ctx *c, const double *relweights, const int32_t *age_index, int64_t n_ages, int jacobian,
+                           double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH);
+/* fit_sfh: BFGS over xvec = [log R_1..R_Nj, transformed FREE parameters] on the objective of
+ * LogDensityProblems.logdensity_and_gradient(::HierarchicalOptimizer, xvec) (generic_fitting.jl:90-199), negated as
+ * fg_map! / fg_mle! do (:306-325).  params0[3] = (alpha, beta, sigma) in natural units (fixed ones are used as they
+ * are, :134-136); transforms[3] in {1, 0} for free parameters (transformations.jl:18,44; the reference's -1 branch is
+ * unvalidated, :155-159, and is refused); free_mask[3]; jacobian_corrections: 1 = MAP,
+ * 0 = MLE.  xvec holds Nj + (number of free parameters) doubles.  Requires sfh_hier_bind.                          */
+int sfh_fit_sfh_bfgs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+                     const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
+                     const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH);
+/* The same loop and the same transformed objective around a CALLER-SUPPLIED hierarchical fg! over the natural variables
+ * [R_1..R_n_ages, n_params model parameters] -> (-logL, gradient): the path for user-defined AbstractMetallicityModel /
+ * AbstractDispersionModel subtypes (SURVEY.md section 8b "GENERIC"), whose chain rule lives on the host.              */
+int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+                             const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
+                             const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH);
+
 /* ---- multi-GPU: bin-row shards, one process per GPU -------------------- */
 /* 128-byte NCCL unique id (rank 0 creates, the host runtime broadcasts it).                    */
 int sfh_comm_unique_id(void *id128);

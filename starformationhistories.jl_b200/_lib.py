@@ -52,6 +52,18 @@ class sfh_array_desc(C.Structure):
                 ("nbytes", C.c_int64), ("checksum", C.c_uint64)]
 
 
+class sfh_bfgs_opts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("alphaguess", C.c_int32), ("g_abstol", C.c_double), ("maxiter", C.c_int64)]
+
+
+class sfh_bfgs_report(C.Structure):
+    _fields_ = [("f", C.c_double), ("g_norm", C.c_double), ("iterations", C.c_int64), ("f_calls", C.c_int64),
+                ("converged", C.c_int32), ("status", C.c_int32)]
+
+
+sfh_objective_fn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double))
+SFH_FIT_LOG_MAP, SFH_FIT_LOG_MLE, SFH_FIT_SQRT_MLE = 0, 1, 2
+
 _vp, _i64, _int, _dp = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 
@@ -92,6 +104,14 @@ PROTOTYPES = {
     "sfh_enqueue_logl_batched": (_int, [_vp, _vp, _i64, _vp]),
     "sfh_ctx_synchronize": (_int, [_vp]),
     "sfh_time_fg": (_int, [_vp, _dp, _int, _int, _int, _dp, _dp]),
+    "sfh_minimize_bfgs": (_int, [sfh_objective_fn, _vp, _i64, _dp, C.POINTER(sfh_bfgs_opts), C.POINTER(sfh_bfgs_report), _dp]),
+    "sfh_fit_templates_bfgs": (_int, [_vp, _int, _dp, C.POINTER(sfh_bfgs_opts), C.POINTER(sfh_bfgs_report), _dp]),
+    "sfh_fit_fixed_amr_bfgs": (_int, [_vp, _dp, C.POINTER(C.c_int32), _i64, _int, _dp, C.POINTER(sfh_bfgs_opts),
+                                      C.POINTER(sfh_bfgs_report), _dp]),
+    "sfh_fit_sfh_bfgs": (_int, [_vp, _int, _dp, _int, _dp, C.POINTER(C.c_int32), _u8p, _int, _dp, C.POINTER(sfh_bfgs_opts),
+                                C.POINTER(sfh_bfgs_report), _dp]),
+    "sfh_fit_sfh_bfgs_generic": (_int, [sfh_objective_fn, _vp, _i64, C.c_int32, _dp, C.POINTER(C.c_int32), _u8p, _int, _dp,
+                                        C.POINTER(sfh_bfgs_opts), C.POINTER(sfh_bfgs_report), _dp]),
     "sfh_checksum64": (_int, [_vp, _i64, C.POINTER(C.c_uint64)]),
     "sfh_file_write": (_int, [C.c_char_p, _int, C.POINTER(_i64), _int, C.POINTER(sfh_array_desc), C.POINTER(_vp)]),
     "sfh_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),

@@ -25,6 +25,7 @@
 #include "sfh_ensemble.cuh"
 #include "sfh_templates.cuh"
 #include "sfh_file.h"
+#include "sfh_drivers.h"
 
 using namespace sfh;
 
@@ -1828,6 +1829,124 @@ extern "C" int sfh_stack_create_from_file(sfh_stack **out, const char *path, int
     if (st != SFH_OK) { sfh_stack_destroy(s); return st; }
     *out = s;
     return SFH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// native driver loops (csrc/sfh_drivers.h): one call = one whole BFGS optimisation around the device evaluations
+// ---------------------------------------------------------------------------------------------
+namespace {
+int run_bfgs(const sfh::drivers::Objective &obj, int64_t n, double *x, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    if (n < 1 || !x) return fail(SFH_ERR_INVALID_ARG, "need a start vector of at least one variable");
+    if (opts && opts->struct_size != (int32_t)sizeof(sfh_bfgs_opts))
+        return fail(SFH_ERR_INVALID_ARG, "sfh_bfgs_opts.struct_size mismatch (%d vs %zu)", opts->struct_size, sizeof(sfh_bfgs_opts));
+    sfh::drivers::BfgsOptions o;
+    if (opts) {
+        if (opts->g_abstol < 0 || opts->maxiter < 0 || opts->alphaguess < 0 || opts->alphaguess > 2) return fail(SFH_ERR_INVALID_ARG, "bad sfh_bfgs_opts");
+        if (opts->g_abstol > 0) o.g_abstol = opts->g_abstol;
+        if (opts->maxiter > 0) o.maxiter = opts->maxiter;
+        if (opts->alphaguess == 2) o.alphaguess = 0;
+    }
+    std::vector<double> own;
+    if (!invH) {
+        if (n > 46340) return fail(SFH_ERR_OOM, "inverse Hessian of %lld variables does not fit", (long long)n);
+        try { own.resize((size_t)n * (size_t)n); } catch (const std::bad_alloc &) { return fail(SFH_ERR_OOM, "host allocation failed"); }
+        invH = own.data();
+    }
+    sfh::drivers::BfgsReport r;
+    int st = SFH_OK;
+    try { st = sfh::drivers::bfgs_minimize(obj, n, x, o, &r, invH); } catch (const std::bad_alloc &) { return fail(SFH_ERR_OOM, "host allocation failed"); }
+    if (st != SFH_OK) return st;   // the objective's own status; its message is already in sfh_last_error
+    if (report) {
+        report->f = r.f; report->g_norm = r.g_norm; report->iterations = r.iterations; report->f_calls = r.f_calls;
+        report->converged = r.converged; report->status = r.status;
+    }
+    return SFH_OK;
+}
+}  // namespace
+
+extern "C" int sfh_minimize_bfgs(sfh_objective_fn fn, void *user, int64_t n, double *x, const sfh_bfgs_opts *opts,
+                                 sfh_bfgs_report *report, double *invH) {
+    if (!fn) return fail(SFH_ERR_INVALID_ARG, "objective is NULL");
+    return run_bfgs([&](const double *xx, double *f, double *g) { return fn(user, xx, n, f, g); }, n, x, opts, report, invH);
+}
+
+extern "C" int sfh_fit_templates_bfgs(sfh_ctx *c, int transform, double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report,
+                                      double *invH) {
+    if (!c || !theta) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    if (transform < SFH_FIT_LOG_MAP || transform > SFH_FIT_SQRT_MLE) return fail(SFH_ERR_INVALID_ARG, "bad transform %d", transform);
+    const int64_t n = c->s->nt;
+    std::vector<double> xnat((size_t)std::max<int64_t>(n, 1));
+    auto obj = [&](const double *th, double *f, double *g) -> int {
+        double sum = 0;
+        if (transform == SFH_FIT_SQRT_MLE) for (int64_t i = 0; i < n; ++i) xnat[(size_t)i] = th[i] * th[i];                    // solvers.jl:256
+        else for (int64_t i = 0; i < n; ++i) { xnat[(size_t)i] = std::exp(th[i]); sum += th[i]; }                              // :180, :189
+        SFH_TRY(sfh_eval_fg(c, xnat.data(), f, g, nullptr));
+        if (transform == SFH_FIT_LOG_MAP) { *f -= sum; for (int64_t i = 0; i < n; ++i) g[i] = g[i] * xnat[(size_t)i] - 1.0; }  // :181-184
+        else if (transform == SFH_FIT_LOG_MLE) for (int64_t i = 0; i < n; ++i) g[i] *= xnat[(size_t)i];                        // :190-193
+        else for (int64_t i = 0; i < n; ++i) g[i] *= 2.0 * th[i];                                                             // :257-259
+        return SFH_OK;
+    };
+    return run_bfgs(obj, n, theta, opts, report, invH);
+}
+
+extern "C" int sfh_fit_fixed_amr_bfgs(sfh_ctx *c, const double *relweights, const int32_t *age_index, int64_t n_ages, int jacobian,
+                                      double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    if (!c || !relweights || !age_index || !theta) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    const int64_t nt = c->s->nt;
+    if (n_ages < 1) return fail(SFH_ERR_INVALID_ARG, "n_ages must be positive");
+    for (int64_t k = 0; k < nt; ++k)
+        if (age_index[k] < 0 || age_index[k] >= n_ages) return fail(SFH_ERR_INVALID_ARG, "age_index[%lld] outside [0,%lld)", (long long)k, (long long)n_ages);
+    std::vector<double> coeffs((size_t)std::max<int64_t>(nt, 1)), G((size_t)std::max<int64_t>(nt, 1)), ex((size_t)n_ages);
+    auto obj = [&](const double *th, double *f, double *g) -> int {
+        double sum = 0;
+        for (int64_t j = 0; j < n_ages; ++j) { ex[(size_t)j] = std::exp(th[j]); sum += th[j]; g[j] = 0.0; }
+        for (int64_t k = 0; k < nt; ++k) coeffs[(size_t)k] = relweights[k] * ex[(size_t)age_index[k]];       // fixed_amr.jl:106-108
+        SFH_TRY(sfh_eval_fg(c, coeffs.data(), f, G.data(), nullptr));
+        for (int64_t k = 0; k < nt; ++k) g[age_index[k]] += G[(size_t)k] * coeffs[(size_t)k];               // :119-121, :147-151
+        if (jacobian) { *f -= sum; for (int64_t j = 0; j < n_ages; ++j) g[j] -= 1.0; }                       // :112, :120
+        return SFH_OK;
+    };
+    return run_bfgs(obj, n_ages, theta, opts, report, invH);
+}
+
+namespace {
+int check_hier_fit_args(int npar, const int32_t *transforms, const uint8_t *free_mask, int *nfree) {
+    *nfree = 0;
+    for (int k = 0; k < npar; ++k) {
+        if (transforms[k] < -1 || transforms[k] > 1) return fail(SFH_ERR_INVALID_ARG, "transforms must be -1, 0 or 1");
+        // the reference itself warns that its -1 branch is unvalidated (generic_fitting.jl:155-159: log of a negative number)
+        if (transforms[k] == -1 && free_mask[k]) return fail(SFH_ERR_UNSUPPORTED, "free parameters with a negative-log transform are not supported");
+        *nfree += free_mask[k] ? 1 : 0;
+    }
+    return SFH_OK;
+}
+}  // namespace
+
+extern "C" int sfh_fit_sfh_bfgs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+                                const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
+                                const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    if (!c || !params0 || !transforms || !free_mask || !xvec) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    if (!c->bound) return fail(SFH_ERR_NOT_BOUND, "sfh_hier_bind has not been called on this context");
+    int nfree = 0;
+    SFH_TRY(check_hier_fit_args(3, transforms, free_mask, &nfree));
+    auto inner = [=](const double *x, double *f, double *g) -> int {
+        return sfh_eval_fg_hier(c, mh_kind, mh_fixed, disp_kind, x, free_mask, f, g);
+    };
+    return run_bfgs(sfh::drivers::hier_objective(inner, c->nj, 3, params0, transforms, free_mask, jacobian_corrections != 0),
+                    (int64_t)c->nj + nfree, xvec, opts, report, invH);
+}
+
+extern "C" int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+                                        const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
+                                        const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    if (!inner_fg || !xvec || n_ages < 1 || n_params < 0 || (n_params > 0 && (!params0 || !transforms || !free_mask)))
+        return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    int nfree = 0;
+    SFH_TRY(check_hier_fit_args(n_params, transforms, free_mask, &nfree));
+    const int64_t nv = n_ages + n_params;
+    auto inner = [=](const double *x, double *f, double *g) -> int { return inner_fg(user, x, nv, f, g); };
+    return run_bfgs(sfh::drivers::hier_objective(inner, n_ages, n_params, params0, transforms, free_mask, jacobian_corrections != 0),
+                    n_ages + nfree, xvec, opts, report, invH);
 }
 
 extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,

@@ -335,6 +335,25 @@ class HierarchicalOptimizer:
         G[nbins:] = G2[nbins:][free]                                       # :181-189
         return (-nlogL, -G) if ret_F else -G                               # :193-197
 
+    def native_bfgs(self, xstart, g_abstol=1e-8, iterations=5000):
+        """Minimise -logdensity over the free transformed variables with the library's BFGS loop (sfh_fit_sfh_bfgs): the
+        objective of fg_map! / fg_mle! (generic_fitting.jl:306-325) evaluated, transformed and iterated natively -- one C
+        call per optimisation.  Returns an object with scipy's field names (x, hess_inv, fun, nit, nfev, success)."""
+        from .solvers import _bfgs_opts, _native_result
+        x = np.array(xstart, dtype=np.float64)
+        _, tf, free, npar, nbins, init, pos, neg, tfree = self._layout(x.shape[0])
+        ctx = _bind(self.models, self.logAge, self.metallicities)
+        if nbins != ctx.n_ages:
+            raise ValueError("length(x0) != length(unique(logAge)) + number of free parameters")
+        invH = np.empty((x.shape[0],) * 2, order="F")
+        rep, o, dp = L.sfh_bfgs_report(), _bfgs_opts(g_abstol, iterations), C.POINTER(C.c_double)
+        fx = self.MH_model0.fixed()
+        tf32, free8 = np.ascontiguousarray(tf, dtype=np.int32), np.ascontiguousarray(free, dtype=np.uint8)
+        L.check(L.lib.sfh_fit_sfh_bfgs(ctx.handle, self.MH_model0.kind, _dp(fx), self.disp_model0.kind, _dp(np.ascontiguousarray(init)),
+                                       tf32.ctypes.data_as(C.POINTER(C.c_int32)), free8.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       int(self.jacobian_corrections), x.ctypes.data_as(dp), C.byref(o), C.byref(rep), invH.ctypes.data_as(dp)))
+        return _native_result(x, invH, rep)
+
     def logdensity_and_gradient_batched(self, X):
         """The same for C chains at once: X is (dimension, C); one device pass (sfh_eval_fg_hier_batched) serves all chains.
         Returns (+logp[C], +grad[dimension, C])  (generic_fitting.jl:90-199 per column)."""

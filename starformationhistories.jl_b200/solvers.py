@@ -20,9 +20,12 @@ from __future__ import annotations
 import math
 from dataclasses import dataclass, field
 
+import ctypes as C
+
 import numpy as np
 from scipy import optimize
 
+from . import _lib as L
 from .fitting import DeviceStack, composite_, device_stack, fg_ as _fg_flat
 from .hierarchical import HierarchicalOptimizer, calculate_coeffs, logtransform, exptransform
 from .sampling import HMCModel, MCMCModel
@@ -84,8 +87,110 @@ def _bfgs(fun, x0, gtol=1e-8, maxiter=5000):
     return optimize.minimize(fun, x0, jac=True, method="BFGS", options={"gtol": gtol, "maxiter": maxiter})
 
 
-def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000):
-    """Returns {"map": LogTransformFTResult, "mle": ...}: BFGS on log-coefficients (solvers.jl:172-221)."""
+@dataclass
+class NativeBFGSResult:
+    """What the library's BFGS loop (include/sfhcuda.h: sfh_minimize_bfgs / sfh_fit_*_bfgs) returns, with scipy's field names."""
+    x: np.ndarray
+    hess_inv: np.ndarray
+    fun: float
+    g_norm: float
+    nit: int
+    nfev: int
+    success: bool
+    status: int          # 0 converged; 1 iteration limit; 2 line search failed; 3 start not finite
+
+
+def _bfgs_opts(gtol, maxiter, alphaguess=0):
+    o = L.sfh_bfgs_opts()
+    o.struct_size = C.sizeof(L.sfh_bfgs_opts)
+    o.g_abstol, o.maxiter, o.alphaguess = float(gtol), int(maxiter), int(alphaguess)
+    return o
+
+
+def _native_result(x, invH, rep):
+    return NativeBFGSResult(x, invH, rep.f, rep.g_norm, int(rep.iterations), int(rep.f_calls), bool(rep.converged), int(rep.status))
+
+
+def native_bfgs(fun, x0, gtol=1e-8, maxiter=5000, alphaguess=0):
+    """The library's BFGS loop on an arbitrary Python objective ``fun(x) -> (f, grad)`` (sfh_minimize_bfgs through a ctypes
+    callback).  The drivers below bind it to the device objectives natively (no callback, one C call per optimisation);
+    this generic form exists for user-defined objectives and for testing the engine itself."""
+    x = np.array(x0, dtype=np.float64)
+    n = x.shape[0]
+    err = []
+
+    def cb(_user, xp, nn, fp, gp):
+        try:
+            f, g = fun(np.ctypeslib.as_array(xp, shape=(nn,)).copy())
+            fp[0] = float(f)
+            np.ctypeslib.as_array(gp, shape=(nn,))[:] = g
+            return 0
+        except Exception as e:          # an exception must not unwind through the C frames
+            err.append(e)
+            return L.SFH_ERR_INVALID_ARG
+    invH = np.empty((n, n), order="F")
+    rep = L.sfh_bfgs_report()
+    o = _bfgs_opts(gtol, maxiter, alphaguess)
+    st = L.lib.sfh_minimize_bfgs(L.sfh_objective_fn(cb), None, n, x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(o), C.byref(rep),
+                                 invH.ctypes.data_as(C.POINTER(C.c_double)))
+    if err:
+        raise err[0]
+    L.check(st)
+    return _native_result(x, invH, rep)
+
+
+def native_fit_sfh_generic(inner_fg, n_ages, params0, transforms, free, xstart, jacobian_corrections=True, gtol=1e-8, maxiter=5000):
+    """fit_sfh's transformed objective and BFGS loop (sfh_fit_sfh_bfgs_generic) around a caller-supplied hierarchical
+    ``inner_fg(variables) -> (-logL, gradient)`` over the natural variables [R_1..R_n_ages, model parameters] -- the route for
+    user-defined metallicity / dispersion models, whose chain rule is host code (SURVEY.md section 8b "GENERIC")."""
+    x = np.array(xstart, dtype=np.float64)
+    p0 = np.ascontiguousarray(params0, dtype=np.float64)
+    tf = np.ascontiguousarray(transforms, dtype=np.int32)
+    fr = np.ascontiguousarray(free, dtype=np.uint8)
+    if not (p0.shape == tf.shape == fr.shape) or x.shape[0] != n_ages + int(fr.sum()):
+        raise ValueError("length(x0) != n_ages + number of free parameters")
+    err = []
+
+    def cb(_user, xp, nn, fp, gp):
+        try:
+            f, g = inner_fg(np.ctypeslib.as_array(xp, shape=(nn,)).copy())
+            fp[0] = float(f)
+            np.ctypeslib.as_array(gp, shape=(nn,))[:] = g
+            return 0
+        except Exception as e:
+            err.append(e)
+            return L.SFH_ERR_INVALID_ARG
+    invH = np.empty((x.shape[0],) * 2, order="F")
+    rep, o, dp = L.sfh_bfgs_report(), _bfgs_opts(gtol, maxiter), C.POINTER(C.c_double)
+    st = L.lib.sfh_fit_sfh_bfgs_generic(L.sfh_objective_fn(cb), None, int(n_ages), p0.shape[0], p0.ctypes.data_as(dp),
+                                        tf.ctypes.data_as(C.POINTER(C.c_int32)), fr.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                        int(bool(jacobian_corrections)), x.ctypes.data_as(dp), C.byref(o), C.byref(rep), invH.ctypes.data_as(dp))
+    if err:
+        raise err[0]
+    L.check(st)
+    return _native_result(x, invH, rep)
+
+
+def _native_fit_templates(ds, transform, theta0, gtol, maxiter):
+    theta = np.array(theta0, dtype=np.float64)
+    n = theta.shape[0]
+    invH = np.empty((n, n), order="F")
+    rep = L.sfh_bfgs_report()
+    o = _bfgs_opts(gtol, maxiter)
+    dp = C.POINTER(C.c_double)
+    L.check(L.lib.sfh_fit_templates_bfgs(ds.ctx().handle, transform, theta.ctypes.data_as(dp), C.byref(o), C.byref(rep), invH.ctypes.data_as(dp)))
+    return _native_result(theta, invH, rep)
+
+
+def _check_engine(engine):
+    if engine not in ("scipy", "native"):
+        raise ValueError("engine must be 'scipy' or 'native'")
+
+
+def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy"):
+    """Returns {"map": LogTransformFTResult, "mle": ...}: BFGS on log-coefficients (solvers.jl:172-221).
+    engine="native": the whole optimisation is one call into the library (sfh_fit_templates_bfgs)."""
+    _check_engine(engine)
     ds = device_stack(models, data)
     x0 = np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, dtype=np.float64)
     _check_sizes(x0, ds)
@@ -102,8 +207,12 @@ def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000):
         f = float(_fg_flat(True, G, x, ds, data))
         return f, G * x
 
-    rmap = _bfgs(fg_map, x0, g_abstol, iterations)                         # :206
-    rmle = _bfgs(fg_mle, rmap.x, g_abstol, iterations)                     # :207 (seeded from the MAP)
+    if engine == "native":
+        rmap = _native_fit_templates(ds, L.SFH_FIT_LOG_MAP, x0, g_abstol, iterations)
+        rmle = _native_fit_templates(ds, L.SFH_FIT_LOG_MLE, rmap.x, g_abstol, iterations)
+    else:
+        rmap = _bfgs(fg_map, x0, g_abstol, iterations)                     # :206
+        rmle = _bfgs(fg_mle, rmap.x, g_abstol, iterations)                 # :207 (seeded from the MAP)
     out = {}
     for key, r in (("map", rmap), ("mle", rmle)):
         mu = np.exp(r.x)
@@ -111,8 +220,10 @@ def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000):
     return out
 
 
-def fit_templates_fast(models, data, x0=None, g_abstol=1e-8, iterations=5000):
-    """Returns (coeffs, result): BFGS on theta with coeffs = theta^2  (solvers.jl:248-275)."""
+def fit_templates_fast(models, data, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy"):
+    """Returns (coeffs, result): BFGS on theta with coeffs = theta^2  (solvers.jl:248-275).
+    engine="native": one call into the library (sfh_fit_templates_bfgs, SFH_FIT_SQRT_MLE)."""
+    _check_engine(engine)
     ds = device_stack(models, data)
     x0 = np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, dtype=np.float64)
     _check_sizes(x0, ds)
@@ -123,7 +234,7 @@ def fit_templates_fast(models, data, x0=None, g_abstol=1e-8, iterations=5000):
         f = float(_fg_flat(True, G, sqrtx ** 2, ds, data))
         return f, G * 2 * sqrtx
 
-    r = _bfgs(fg_mle, x0, g_abstol, iterations)
+    r = _native_fit_templates(ds, L.SFH_FIT_SQRT_MLE, x0, g_abstol, iterations) if engine == "native" else _bfgs(fg_mle, x0, g_abstol, iterations)
     return r.x ** 2, r
 
 
@@ -243,7 +354,8 @@ def truncate_relweights(relweightsmin, relweights, logAge):
     return np.concatenate(keep)
 
 
-def fixed_amr(models, data, logAge, metallicities, relweights, relweightsmin=0, x0=None, g_abstol=1e-8, iterations=5000):
+def fixed_amr(models, data, logAge, metallicities, relweights, relweightsmin=0, x0=None, g_abstol=1e-8, iterations=5000,
+              engine="scipy"):
     """fixed_amr (hierarchical/fixed_amr.jl:41-180): one stellar-mass coefficient per unique(logAge) under externally imposed
     relative weights; BFGS on log-coefficients, MAP (Jacobian term) then MLE seeded from it.  Every objective evaluation is
     one fused `fg!` on the device; the per-age contraction of the gradient (:119-121, :147-151) is O(T) on the host.
@@ -295,10 +407,21 @@ def fixed_amr(models, data, logAge, metallicities, relweights, relweightsmin=0, 
                 return nl - xvec.sum(), g - 1                                            # :112, :120
             return nl, g
         return fun
+    _check_engine(engine)
     res = {}
     start = np.log(x0)
     for key, jac in (("map", True), ("mle", False)):                                     # :166-167
-        r = _bfgs(make(jac), start, g_abstol, iterations)
+        if engine == "native":                                                          # one library call per optimisation
+            theta = np.array(start, dtype=np.float64)
+            invH = np.empty((theta.shape[0],) * 2, order="F")
+            rep, o, dp = L.sfh_bfgs_report(), _bfgs_opts(g_abstol, iterations), C.POINTER(C.c_double)
+            rwc, inv32 = np.ascontiguousarray(rw, dtype=np.float64), np.ascontiguousarray(inv, dtype=np.int32)
+            L.check(L.lib.sfh_fit_fixed_amr_bfgs(ds.ctx().handle, rwc.ctypes.data_as(dp), inv32.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 ua.shape[0], int(jac), theta.ctypes.data_as(dp), C.byref(o), C.byref(rep),
+                                                 invH.ctypes.data_as(dp)))
+            r = _native_result(theta, invH, rep)
+        else:
+            r = _bfgs(make(jac), start, g_abstol, iterations)
         start = r.x
         invH = np.asarray(r.hess_inv)
         res[key] = {"mu": np.exp(r.x), "sigma": np.sqrt(np.abs(np.diag(invH))), "invH": invH, "result": r}
@@ -362,10 +485,11 @@ def cum_sfr_quantiles(result, logAge, MH, T_max, Nsamples, q, rng=None, **kws):
     return {"cum_sfh": cum_q, "sfrs": sfr_q, "mean_mh": mh_q, "samples": samples, "n_good": len(rows)}
 
 
-def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000):
+def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy"):
     """BFGS on [log R_j, transformed free parameters]: MAP (Jacobian corrections on) then MLE seeded from it
     (generic_fitting.jl:242-409).  Returns {"map": BFGSResult, "mle": BFGSResult}; mu holds
     [R_1..R_Nj, alpha, beta, sigma] with fixed parameters at their initial values."""
+    _check_engine(engine)
     ds = device_stack(models, data)
     la, mh = np.asarray(logAge, float), np.asarray(metallicities, float)
     _, first = np.unique(la, return_index=True)
@@ -392,7 +516,10 @@ def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None
             lp, g = opt.logdensity_and_gradient(X)
             return -lp, -g
 
-        r = _bfgs(fun, start, g_abstol, iterations)
+        if engine == "native":                                             # the loop runs inside the library (sfh_fit_sfh_bfgs)
+            r = opt.native_bfgs(start, g_abstol, iterations)
+        else:
+            r = _bfgs(fun, start, g_abstol, iterations)
         start = r.x                                                        # MLE starts from the MAP minimiser
         mu = np.empty(nj + tf.shape[0])
         mu[:nj] = np.exp(r.x[:nj])
