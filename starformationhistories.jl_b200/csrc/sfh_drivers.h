@@ -156,8 +156,12 @@ inline int wolfe_search(const Objective &fn, int64_t n, const double *x, const d
         if (fa1 > f0 + o.c1 * a1 * dphi0 || (i > 0 && fa1 >= fa0)) return zoom(a0, a1, fa0, fa1, da0, alpha_out);
         if (std::fabs(da1) <= -o.c2 * dphi0) { *alpha_out = a1; *f_new = fa1; return 0; }
         if (da1 >= 0) return zoom(a1, a0, fa1, fa0, da1, alpha_out);
+        // still descending steeply: extrapolate to where the secant through the two slopes vanishes, kept inside
+        // [1.25, 10] x the current step (the scaled first trial can be orders of magnitude short of the minimiser)
+        double next = 10.0 * a1;
+        if (da1 > da0) next = std::min(10.0 * a1, std::max(1.25 * a1, a1 - da1 * (a1 - a0) / (da1 - da0)));
         a0 = a1; fa0 = fa1; da0 = da1;
-        a1 *= 2.0;
+        a1 = next;
     }
     return -1;
 }

@@ -193,4 +193,59 @@ function DeviceStack(edges::Tuple{<:AbstractRange,<:AbstractRange}, points::Abst
     return DeviceStack{S}(nothing, (nx * ny, length(points)), h[])   # same finalizer / per-task contexts as the uploading constructor
 end
 
+# ---- on-disk container (include/sfhcuda.h: sfh_stack_save / sfh_stack_create_from_file) -------------------------
+# The reference has no file format (examples/fitting1.ipynb cell 96 uses Serialization by hand).  `save` streams the device
+# copy straight into the memory-mapped file; `DeviceStack(path)` uploads it again, reading only the bin rows this process
+# holds (`rows = (first, last)` in Julia's 1-based inclusive convention).
+function save(path::AbstractString, models::DeviceStack; logAge=nothing, MH=nothing, hess_size::Tuple{Int,Int}=(0, 0))
+    la = logAge === nothing ? C_NULL : convert(Vector{Float64}, logAge)
+    mh = MH === nothing ? C_NULL : convert(Vector{Float64}, MH)
+    check(ccall((:sfh_stack_save, libsfh), Cint, (Ptr{Cvoid}, Cstring, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                models.handle, path, hess_size[1], hess_size[2], la, mh))
+end
+struct SfhOpts   # sfh_opts, include/sfhcuda.h
+    struct_size::Int32; device::Int32; row_begin::Int64; row_end::Int64; clamp_eps::Float64
+    tile_bins::Int32; cluster::Int32; force_unfused::Int32; consumer_warps::Int32; variant::Int32; reserved::Int32
+end
+function DeviceStack(path::AbstractString; S::Type=Float64, rows::Union{Nothing,Tuple{Int,Int}}=nothing, verify::Bool=false, device::Integer=0)
+    o = SfhOpts(sizeof(SfhOpts), device, rows === nothing ? 0 : rows[1] - 1, rows === nothing ? 0 : rows[2], 0.0, 0, 0, 0, 0, 0, 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sfh_stack_create_from_file, libsfh), Cint, (Ref{Ptr{Cvoid}}, Cstring, Cint, Ref{SfhOpts}), h, path, verify, o))
+    info = zeros(UInt8, 128)   # sfh_info: nbins_total and ntemplates are its first two int64 fields
+    check(ccall((:sfh_stack_info, libsfh), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h[], info))
+    nb, nt = reinterpret(Int64, info[1:16])
+    return DeviceStack{S}(nothing, (Int(nb), Int(nt)), h[])
+end
+
+# ---- native BFGS loops: one ccall per optimisation (include/sfhcuda.h: sfh_fit_*_bfgs) ----------------------------
+# What fit_templates / fit_templates_fast (solvers.jl:163-275) and fit_sfh (generic_fitting.jl:296-327) hand to
+# Optim.optimize(only_fg!(...), x0, BFGS(...)): here the loop runs inside the library around the device evaluations.
+struct BfgsOpts; struct_size::Int32; alphaguess::Int32; g_abstol::Float64; maxiter::Int64; end
+mutable struct BfgsReport; f::Float64; g_norm::Float64; iterations::Int64; f_calls::Int64; converged::Int32; status::Int32; BfgsReport() = new(); end
+bfgs_opts(g_abstol, iterations) = BfgsOpts(sizeof(BfgsOpts), 0, g_abstol, iterations)
+
+# transform: 0 = log-space MAP (solvers.jl:178-186), 1 = log-space MLE (:187-195), 2 = sqrt-space MLE (:254-261).
+# Returns (minimiser in the fitting space, inverse Hessian, report): fit_templates builds its LogTransformFTResult from them.
+function fit_templates_bfgs(models::DeviceStack, theta0::Vector{Float64}, transform::Integer; g_abstol=1e-8, iterations=5000)
+    theta = copy(theta0); invH = Matrix{Float64}(undef, length(theta), length(theta)); rep = BfgsReport()
+    check(ccall((:sfh_fit_templates_bfgs, libsfh), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ref{BfgsOpts}, Ref{BfgsReport}, Ptr{Float64}),
+                models.ctx[], transform, theta, bfgs_opts(g_abstol, iterations), rep, invH))
+    return theta, invH, rep
+end
+
+# fit_sfh's fg_map! (jacobian_corrections = true) / fg_mle! (false) optimisation, generic_fitting.jl:306-327.
+# x0 = [log.(R); transformed free parameters] exactly as fit_sfh assembles it (:285-294).
+function fit_sfh_bfgs(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion, x0::Vector{Float64},
+                      models::DeviceStack, logAge, MH, jacobian_corrections::Bool; g_abstol=1e-8, iterations=5000)
+    c = bind!(models, logAge, MH)
+    par = Float64[fittable_params(MHmodel0)..., fittable_params(dispmodel0)...]
+    tf = Int32[SFH.transforms(MHmodel0)..., SFH.transforms(dispmodel0)...]
+    free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)...]
+    x = copy(x0); invH = Matrix{Float64}(undef, length(x), length(x)); rep = BfgsReport()
+    check(ccall((:sfh_fit_sfh_bfgs, libsfh), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Cint, Ptr{Float64}, Ref{BfgsOpts}, Ref{BfgsReport}, Ptr{Float64}),
+                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), par, tf, free, jacobian_corrections, x, bfgs_opts(g_abstol, iterations), rep, invH))
+    return x, invH, rep
+end
+
 end # module

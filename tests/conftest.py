@@ -14,6 +14,11 @@ def pytest_configure(config):
 
 
 def _have_gpu() -> bool:
+    try:                                   # the library's own probe: no torch import (a minute on a fresh box)
+        import sfh_b200
+        return sfh_b200.device_count() > 0
+    except Exception:
+        pass
     try:
         import torch
         return torch.cuda.is_available()

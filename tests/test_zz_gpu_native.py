@@ -45,7 +45,7 @@ def test_fit_templates_native_agrees_with_host_loop_on_poisson_data(S):   # basi
     rs = S.fit_templates(M, data, x0=x0, engine="scipy")
     for k in ("map", "mle"):
         assert isapprox(rn[k].mu, rs[k].mu, 1e-5)
-        assert isapprox(rn[k].mu, x, 1e-2)
+        assert isapprox(rn[k].mu, x, 5e-2)                     # Poisson noise: ~2 % on these coefficients
         assert np.all(rn[k].sigma > 0) and np.allclose(rn[k].sigma, rs[k].sigma, rtol=0.5)
     assert rn["map"].result.success
     assert isapprox(S.fit_templates_fast(M, data, x0=x0, engine="native")[0], rs["mle"].mu, 1e-4)
