@@ -291,6 +291,50 @@ int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, int64_t n_ag
                              const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
                              const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH);
 
+/* Native multi-chain NUTS (csrc/sfh_nuts.h): every chain is a host thread running the No-U-Turn recursion (Hoffman & Gelman
+ * 2014, alg. 6, dual-averaging step size, Gaussian kinetic energy) -- the role DynamicHMC plays in hmc_sample
+ * (src/fitting/hmc_sample.jl:105-143: one chain per thread) and sample_sfh / tsample_sfh (generic_fitting.jl:456-665: one
+ * task per short chain) -- but the gradient requests of all live chains are served by ONE batched device pass per round
+ * (sfh_eval_fg_batched / sfh_eval_fg_hier_batched).  Random numbers: Philox4x32-10 keyed by seed, counter (chain, draw).   */
+typedef int (*sfh_batch_logdensity_fn)(void *user, const double *Theta /* n x C */, int64_t n, int64_t C, double *logp /* C */,
+                                       double *grad /* n x C */);   /* 0 = OK, else aborts the run with that status */
+typedef struct sfh_nuts_opts {
+    int32_t struct_size;  /* = sizeof(sfh_nuts_opts)                                                             */
+    int32_t max_depth;    /* 0 = 8                                                                               */
+    int64_t nwarmup;      /* dual-averaging warm-up draws per chain (not stored); used as given                  */
+    double delta;         /* target mean acceptance; 0 = 0.8                                                     */
+    double eps0;          /* > 0: fixed initial step size (the reference's epsilon, generic_fitting.jl:479-482); */
+                          /* 0: doubling heuristic                                                               */
+    uint64_t seed;
+    int32_t mass_kind;    /* M^-1 of the kinetic energy: 0 identity, 1 diagonal (inv_mass[n]), 2 dense            */
+                          /* (inv_mass[n x n], e.g. MAP.invH as in GaussianKineticEnergy(MAP.invH))               */
+    int32_t reserved;
+} sfh_nuts_opts;
+/* theta0: n x nchains starts; nsteps[nchains] draws per chain; samples: n x sum(nsteps) column-major, chains concatenated
+ * in order; logps[sum(nsteps)]; step_sizes[nchains] (nullable); n_batches / n_evals (nullable): batched passes made and
+ * chain-evaluations served.                                                                                      */
+int sfh_nuts_run(sfh_batch_logdensity_fn fn, void *user, int64_t n, int64_t nchains, const double *theta0, const int64_t *nsteps,
+                 const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes,
+                 int64_t *n_batches, int64_t *n_evals);
+/* hmc_sample: the chains of HMCModel (hmc_sample.jl:24-37: theta = log coeffs, logp = -fg! + sum(theta), grad = -G x + 1)
+ * on the resident stack; theta0 is ntemplates x nchains; samples come back in the theta (log) space.              */
+int sfh_hmc_sample_nuts(sfh_ctx *c, int64_t nchains, const double *theta0, const int64_t *nsteps, const double *inv_mass,
+                        const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes, int64_t *n_batches,
+                        int64_t *n_evals);
+/* sample_sfh / tsample_sfh: the chains of the HierarchicalOptimizer log-density with Jacobian corrections
+ * (generic_fitting.jl:90-199, :477) over x = [log R_j, transformed free parameters]; arguments as sfh_fit_sfh_bfgs.
+ * theta0 is (Nj + nfree) x nchains; samples come back in the transformed space.  Requires sfh_hier_bind.          */
+int sfh_sample_sfh_nuts(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+                        const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
+                        const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps,
+                        double *step_sizes, int64_t *n_batches, int64_t *n_evals);
+/* The same chains around a CALLER-SUPPLIED batched hierarchical fg! over the natural variables (V: (n_ages + n_params) x C ->
+ * -logL[C] in `logp`, gradient in `grad`): user-defined metallicity / dispersion models (SURVEY.md section 8b "GENERIC").   */
+int sfh_sample_sfh_nuts_generic(sfh_batch_logdensity_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+                                const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
+                                const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples,
+                                double *logps, double *step_sizes, int64_t *n_batches, int64_t *n_evals);
+
 /* ---- multi-GPU: bin-row shards, one process per GPU -------------------- */
 /* 128-byte NCCL unique id (rank 0 creates, the host runtime broadcasts it).                    */
 int sfh_comm_unique_id(void *id128);

@@ -61,6 +61,13 @@ class sfh_bfgs_report(C.Structure):
                 ("converged", C.c_int32), ("status", C.c_int32)]
 
 
+class sfh_nuts_opts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("max_depth", C.c_int32), ("nwarmup", C.c_int64), ("delta", C.c_double),
+                ("eps0", C.c_double), ("seed", C.c_uint64), ("mass_kind", C.c_int32), ("reserved", C.c_int32)]
+
+
+sfh_batch_logdensity_fn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.c_int64, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double))
 sfh_objective_fn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double))
 SFH_FIT_LOG_MAP, SFH_FIT_LOG_MLE, SFH_FIT_SQRT_MLE = 0, 1, 2
 
@@ -112,6 +119,14 @@ PROTOTYPES = {
                                 C.POINTER(sfh_bfgs_report), _dp]),
     "sfh_fit_sfh_bfgs_generic": (_int, [sfh_objective_fn, _vp, _i64, C.c_int32, _dp, C.POINTER(C.c_int32), _u8p, _int, _dp,
                                         C.POINTER(sfh_bfgs_opts), C.POINTER(sfh_bfgs_report), _dp]),
+    "sfh_nuts_run": (_int, [sfh_batch_logdensity_fn, _vp, _i64, _i64, _dp, C.POINTER(_i64), _dp, C.POINTER(sfh_nuts_opts), _dp, _dp, _dp,
+                            C.POINTER(_i64), C.POINTER(_i64)]),
+    "sfh_hmc_sample_nuts": (_int, [_vp, _i64, _dp, C.POINTER(_i64), _dp, C.POINTER(sfh_nuts_opts), _dp, _dp, _dp, C.POINTER(_i64),
+                                   C.POINTER(_i64)]),
+    "sfh_sample_sfh_nuts": (_int, [_vp, _int, _dp, _int, _dp, C.POINTER(C.c_int32), _u8p, _i64, _dp, C.POINTER(_i64), _dp,
+                                   C.POINTER(sfh_nuts_opts), _dp, _dp, _dp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "sfh_sample_sfh_nuts_generic": (_int, [sfh_batch_logdensity_fn, _vp, _i64, C.c_int32, _dp, C.POINTER(C.c_int32), _u8p, _i64, _dp,
+                                           C.POINTER(_i64), _dp, C.POINTER(sfh_nuts_opts), _dp, _dp, _dp, C.POINTER(_i64), C.POINTER(_i64)]),
     "sfh_checksum64": (_int, [_vp, _i64, C.POINTER(C.c_uint64)]),
     "sfh_file_write": (_int, [C.c_char_p, _int, C.POINTER(_i64), _int, C.POINTER(sfh_array_desc), C.POINTER(_vp)]),
     "sfh_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <system_error>
 #include <vector>
 
 #include "sfh_batched.cuh"
@@ -26,6 +27,7 @@
 #include "sfh_templates.cuh"
 #include "sfh_file.h"
 #include "sfh_drivers.h"
+#include "sfh_nuts.h"
 
 using namespace sfh;
 
@@ -1947,6 +1949,111 @@ extern "C" int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, i
     auto inner = [=](const double *x, double *f, double *g) -> int { return inner_fg(user, x, nv, f, g); };
     return run_bfgs(sfh::drivers::hier_objective(inner, n_ages, n_params, params0, transforms, free_mask, jacobian_corrections != 0),
                     n_ages + nfree, xvec, opts, report, invH);
+}
+
+// ---------------------------------------------------------------------------------------------
+// native multi-chain NUTS (csrc/sfh_nuts.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+int run_nuts(const sfh::nuts::BatchLogDensity &fn, int64_t n, int64_t nchains, const double *theta0, const int64_t *nsteps,
+             const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes, int64_t *n_batches,
+             int64_t *n_evals) {
+    if (n < 1 || nchains < 1 || !theta0 || !nsteps) return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    if (nchains > 1024) return fail(SFH_ERR_INVALID_ARG, "at most 1024 chains (one host thread each)");
+    if (opts && opts->struct_size != (int32_t)sizeof(sfh_nuts_opts))
+        return fail(SFH_ERR_INVALID_ARG, "sfh_nuts_opts.struct_size mismatch (%d vs %zu)", opts->struct_size, sizeof(sfh_nuts_opts));
+    sfh::nuts::Options o;
+    int mass_kind = 0;
+    if (opts) {
+        if (opts->max_depth < 0 || opts->max_depth > 20 || opts->nwarmup < 0 || opts->delta < 0 || opts->delta >= 1 || opts->eps0 < 0 ||
+            opts->mass_kind < 0 || opts->mass_kind > 2)
+            return fail(SFH_ERR_INVALID_ARG, "bad sfh_nuts_opts");
+        if (opts->max_depth > 0) o.max_depth = opts->max_depth;
+        o.nwarmup = opts->nwarmup;
+        if (opts->delta > 0) o.delta = opts->delta;
+        o.eps0 = opts->eps0; o.seed = opts->seed; mass_kind = opts->mass_kind;
+    }
+    int64_t total = 0;
+    for (int64_t c = 0; c < nchains; ++c) {
+        if (nsteps[c] < 0) return fail(SFH_ERR_INVALID_ARG, "negative chain length");
+        total += nsteps[c];
+    }
+    if (total > 0 && (!samples || !logps)) return fail(SFH_ERR_INVALID_ARG, "NULL output");
+    if (mass_kind != 0 && !inv_mass) return fail(SFH_ERR_INVALID_ARG, "inv_mass is NULL");
+    sfh::nuts::Mass mass;
+    std::vector<double> steps((size_t)nchains, 0.0);
+    sfh::nuts::Stats stats;
+    int st = SFH_OK;
+    try {
+        if (!mass.init(mass_kind, n, inv_mass)) return fail(SFH_ERR_INVALID_ARG, "inv_mass is not positive definite");
+        st = sfh::nuts::run_chains(fn, n, nchains, theta0, nsteps, mass, o, samples, logps, steps.data(), &stats);
+    } catch (const std::bad_alloc &) { return fail(SFH_ERR_OOM, "host allocation failed"); }
+      catch (const std::system_error &e) { return fail(SFH_ERR_UNSUPPORTED, "cannot start chain threads: %s", e.what()); }
+    if (st == -1) return fail(SFH_ERR_OOM, "a chain thread failed (allocation)");
+    if (st != SFH_OK) return st;   // the log-density's own status; its message is already in sfh_last_error
+    if (step_sizes) std::copy(steps.begin(), steps.end(), step_sizes);
+    if (n_batches) *n_batches = stats.n_batches;
+    if (n_evals) *n_evals = stats.n_evals;
+    return SFH_OK;
+}
+}  // namespace
+
+extern "C" int sfh_nuts_run(sfh_batch_logdensity_fn fn, void *user, int64_t n, int64_t nchains, const double *theta0, const int64_t *nsteps,
+                            const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes,
+                            int64_t *n_batches, int64_t *n_evals) {
+    if (!fn) return fail(SFH_ERR_INVALID_ARG, "log-density is NULL");
+    return run_nuts([=](const double *Th, int64_t C, double *lp, double *g) { return fn(user, Th, n, C, lp, g); }, n, nchains, theta0, nsteps,
+                    inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
+}
+
+extern "C" int sfh_hmc_sample_nuts(sfh_ctx *c, int64_t nchains, const double *theta0, const int64_t *nsteps, const double *inv_mass,
+                                   const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes, int64_t *n_batches,
+                                   int64_t *n_evals) {
+    if (!c) return fail(SFH_ERR_INVALID_ARG, "NULL context");
+    const int64_t n = c->s->nt;
+    // HMCModel's logdensity_and_gradient (hmc_sample.jl:24-37) for C chains: one sfh_eval_fg_batched pass.  The batch
+    // function runs on the CALLING thread only (the chain threads never touch the context).
+    auto fn = [=](const double *Th, int64_t C, double *lp, double *g) -> int {
+        std::vector<double> X((size_t)(n * C));
+        for (int64_t i = 0; i < n * C; ++i) X[(size_t)i] = std::exp(Th[i]);                  // :27
+        SFH_TRY(sfh_eval_fg_batched(c, X.data(), C, lp, g));                                 // :34  (-logL, G)
+        for (int64_t k = 0; k < C; ++k) {
+            double sum = 0;
+            for (int64_t i = 0; i < n; ++i) { sum += Th[k * n + i]; g[k * n + i] = -g[k * n + i] * X[(size_t)(k * n + i)] + 1.0; }   // :36
+            lp[k] = -lp[k] + sum;                                                            // :35
+        }
+        return SFH_OK;
+    };
+    return run_nuts(fn, n, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
+}
+
+extern "C" int sfh_sample_sfh_nuts(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+                                   const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
+                                   const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps,
+                                   double *step_sizes, int64_t *n_batches, int64_t *n_evals) {
+    if (!c || !params0 || !transforms || !free_mask) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+    if (!c->bound) return fail(SFH_ERR_NOT_BOUND, "sfh_hier_bind has not been called on this context");
+    int nfree = 0;
+    SFH_TRY(check_hier_fit_args(3, transforms, free_mask, &nfree));
+    auto inner = [=](const double *V, int64_t C, double *nl, double *G) -> int {
+        return sfh_eval_fg_hier_batched(c, mh_kind, mh_fixed, disp_kind, V, C, free_mask, nl, G);
+    };
+    return run_nuts(sfh::nuts::hier_logdensity_batched(inner, c->nj, 3, params0, transforms, free_mask, true), (int64_t)c->nj + nfree, nchains,
+                    theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
+}
+
+extern "C" int sfh_sample_sfh_nuts_generic(sfh_batch_logdensity_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+                                           const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
+                                           const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples,
+                                           double *logps, double *step_sizes, int64_t *n_batches, int64_t *n_evals) {
+    if (!inner_fg || n_ages < 1 || n_params < 0 || (n_params > 0 && (!params0 || !transforms || !free_mask)))
+        return fail(SFH_ERR_INVALID_ARG, "bad argument");
+    int nfree = 0;
+    SFH_TRY(check_hier_fit_args(n_params, transforms, free_mask, &nfree));
+    const int64_t nv = n_ages + n_params;
+    auto inner = [=](const double *V, int64_t C, double *nl, double *G) -> int { return inner_fg(user, V, nv, C, nl, G); };
+    return run_nuts(sfh::nuts::hier_logdensity_batched(inner, n_ages, n_params, params0, transforms, free_mask, true), n_ages + nfree, nchains,
+                    theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
 }
 
 extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,

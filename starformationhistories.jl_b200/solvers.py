@@ -793,7 +793,101 @@ def run_chains_batched(batch_fn, theta0s, nsteps, nwarmup=200, max_depth=8, rngs
     return out, stats
 
 
-def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, max_depth=8, batched=None):
+def _nuts_opts(nwarmup, max_depth, delta, eps0, seed, inv_mass):
+    o = L.sfh_nuts_opts()
+    o.struct_size = C.sizeof(L.sfh_nuts_opts)
+    o.max_depth, o.nwarmup, o.delta = int(max_depth), int(nwarmup), float(delta)
+    o.eps0 = 0.0 if eps0 is None else float(eps0)
+    o.seed = int(seed) & (2**64 - 1)
+    im = None
+    if inv_mass is not None:
+        im = np.asarray(inv_mass, dtype=np.float64)
+        o.mass_kind = 1 if im.ndim == 1 else 2
+        im = np.asfortranarray(im)
+    return o, im
+
+
+def _nuts_call(entry, head_args, theta0s, nsteps, nwarmup, max_depth, delta, eps0, seed, inv_mass):
+    """Common tail of the three native NUTS entry points: returns ([(samples (nsteps_c, n), logps, step_size) per chain], ChainStats)."""
+    Th = np.asfortranarray(np.stack([np.asarray(t, dtype=np.float64) for t in theta0s], axis=1))
+    n, nch = Th.shape
+    lens = np.ascontiguousarray(np.broadcast_to(np.asarray(nsteps, dtype=np.int64), (nch,)))
+    tot = int(lens.sum())
+    samples = np.empty((n, max(tot, 1)), order="F")
+    logps = np.empty(max(tot, 1))
+    steps = np.empty(nch)
+    o, im = _nuts_opts(nwarmup, max_depth, delta, eps0, seed, inv_mass)
+    if im is not None and im.shape not in ((n,), (n, n)):
+        raise ValueError("inv_mass must have shape (n,) or (n, n)")
+    nb, ne = C.c_int64(0), C.c_int64(0)
+    dp, i64p = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    st = entry(*head_args, nch, Th.ctypes.data_as(dp), lens.ctypes.data_as(i64p), im.ctypes.data_as(dp) if im is not None else None,
+               C.byref(o), samples.ctypes.data_as(dp), logps.ctypes.data_as(dp), steps.ctypes.data_as(dp), C.byref(nb), C.byref(ne))
+    out, a = [], 0
+    for c in range(nch):
+        out.append((samples[:, a:a + lens[c]].T.copy(), logps[a:a + lens[c]].copy(), float(steps[c])))
+        a += int(lens[c])
+    stats = ChainStats()
+    stats.n_batches, stats.n_evals = nb.value, ne.value
+    return st, out, stats
+
+
+def native_nuts(batch_fn, theta0s, nsteps, nwarmup=200, max_depth=8, delta=0.8, eps0=None, seed=0, inv_mass=None):
+    """The library's multi-chain NUTS (sfh_nuts_run, csrc/sfh_nuts.h) around a Python ``batch_fn(Theta[n, C]) -> (logp[C],
+    grad[n, C])``: same algorithm and draw order as :func:`nuts_chain`, Philox streams keyed by ``seed``.  ``nsteps`` may be one
+    length or one per chain.  Returns ([(samples, logps, step_size) per chain], ChainStats).  `hmc_sample` / `sample_sfh` /
+    `tsample_sfh` with engine="native" bind the device log-densities natively instead (no callback)."""
+    err = []
+
+    def cb(_user, thp, n, Cn, lpp, gp):
+        try:
+            Th = np.ctypeslib.as_array(thp, shape=(Cn, n)).T.copy(order="F")          # n x C column-major
+            lp, g = batch_fn(Th)
+            np.ctypeslib.as_array(lpp, shape=(Cn,))[:] = lp
+            np.ctypeslib.as_array(gp, shape=(Cn, n))[:] = np.asarray(g, dtype=np.float64).T
+            return 0
+        except Exception as e:
+            err.append(e)
+            return L.SFH_ERR_INVALID_ARG
+    n = np.asarray(theta0s[0]).shape[0]
+    st, out, stats = _nuts_call(L.lib.sfh_nuts_run, (L.sfh_batch_logdensity_fn(cb), None, n), theta0s, nsteps, nwarmup, max_depth, delta,
+                                eps0, seed, inv_mass)
+    if err:
+        raise err[0]
+    L.check(st)
+    return out, stats
+
+
+def native_sample_sfh_generic(inner_fg_batched, n_ages, params0, transforms, free, theta0s, nsteps, nwarmup=0, max_depth=8, eps0=None,
+                              seed=0, inv_mass=None):
+    """sample_sfh / tsample_sfh's chains (sfh_sample_sfh_nuts_generic) around a caller-supplied batched hierarchical
+    ``inner_fg_batched(V[(n_ages + npar), C]) -> (-logL[C], G)`` over the natural variables -- user-defined models."""
+    p0 = np.ascontiguousarray(params0, dtype=np.float64)
+    tf = np.ascontiguousarray(transforms, dtype=np.int32)
+    fr = np.ascontiguousarray(free, dtype=np.uint8)
+    err = []
+
+    def cb(_user, vp, nv, Cn, nlp, gp):
+        try:
+            V = np.ctypeslib.as_array(vp, shape=(Cn, nv)).T.copy(order="F")
+            nl, G = inner_fg_batched(V)
+            np.ctypeslib.as_array(nlp, shape=(Cn,))[:] = nl
+            np.ctypeslib.as_array(gp, shape=(Cn, nv))[:] = np.asarray(G, dtype=np.float64).T
+            return 0
+        except Exception as e:
+            err.append(e)
+            return L.SFH_ERR_INVALID_ARG
+    dp = C.POINTER(C.c_double)
+    head = (L.sfh_batch_logdensity_fn(cb), None, int(n_ages), p0.shape[0], p0.ctypes.data_as(dp), tf.ctypes.data_as(C.POINTER(C.c_int32)),
+            fr.ctypes.data_as(C.POINTER(C.c_uint8)))
+    st, out, stats = _nuts_call(L.lib.sfh_sample_sfh_nuts_generic, head, theta0s, nsteps, nwarmup, max_depth, 0.8, eps0, seed, inv_mass)
+    if err:
+        raise err[0]
+    L.check(st)
+    return out, stats
+
+
+def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, max_depth=8, batched=None, engine="host"):
     """hmc_sample(models, data, nsteps[, nchains])  (hmc_sample.jl:105-143): NUTS on theta = log(coeffs) with the
     Jacobian-corrected log-density of HMCModel.  Returns natural-unit samples of shape (nsteps, npar, nchains).
     With nchains > 1 (threads in the reference, hmc_sample.jl:123-141) the chains run as coroutines and, when `batched`,
@@ -805,6 +899,15 @@ def hmc_sample(models, data, nsteps, nchains=1, nwarmup=200, rng=None, x0=None, 
     rng = np.random.default_rng() if rng is None else rng
     x0 = renormalize_x0(data, ds, np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, float))
     out = np.empty((nsteps, ds.shape[1], nchains))
+    if engine == "native":                                                 # chains + batching inside the library (sfh_hmc_sample_nuts)
+        st, res, _ = _nuts_call(L.lib.sfh_hmc_sample_nuts, (ds.ctx().handle,), [np.log(x0)] * nchains, nsteps, nwarmup, max_depth, 0.8,
+                                None, int(rng.integers(0, 2**63)), None)
+        L.check(st)
+        for c in range(nchains):
+            out[:, :, c] = np.exp(res[c][0])
+        return out
+    if engine != "host":
+        raise ValueError("engine must be 'host' or 'native'")
     if nchains == 1:
         s, _, _ = nuts_sample(model.logdensity_and_gradient, np.log(x0), nsteps, nwarmup, max_depth, rng=rng)
         out[:, :, 0] = np.exp(s)                                           # back to natural units
@@ -839,20 +942,41 @@ def _expand_posterior(best, Z):
     return out
 
 
-def sample_sfh(bfgs_result, models, data, logAge, metallicities, Nsteps, eps=0.05, rng=None, nwarmup=0, max_depth=8):
+def _native_sample_sfh(inst, starts, lens, cov, eps, nwarmup, max_depth, seed):
+    """sfh_sample_sfh_nuts on the device-bound HierarchicalOptimizer log-density of `inst` (Jacobian corrections on)."""
+    from .hierarchical import _bind
+    ctx = _bind(inst.models, inst.logAge, inst.metallicities)
+    tf = np.ascontiguousarray(list(inst.MH_model0.transforms()) + list(inst.disp_model0.transforms()), dtype=np.int32)
+    free = np.ascontiguousarray(list(inst.MH_model0.free_params()) + list(inst.disp_model0.free_params()), dtype=np.uint8)
+    init = np.ascontiguousarray(list(inst.MH_model0.fittable_params()) + list(inst.disp_model0.fittable_params()), dtype=np.float64)
+    fx = np.ascontiguousarray(inst.MH_model0.fixed(), dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    head = (ctx.handle, inst.MH_model0.kind, fx.ctypes.data_as(dp), inst.disp_model0.kind, init.ctypes.data_as(dp),
+            tf.ctypes.data_as(C.POINTER(C.c_int32)), free.ctypes.data_as(C.POINTER(C.c_uint8)))
+    st, res, stats = _nuts_call(L.lib.sfh_sample_sfh_nuts, head, starts, lens, nwarmup, max_depth, 0.8, eps, seed, cov)
+    L.check(st)
+    return res, stats
+
+
+def sample_sfh(bfgs_result, models, data, logAge, metallicities, Nsteps, eps=0.05, rng=None, nwarmup=0, max_depth=8, engine="host"):
     """sample_sfh (generic_fitting.jl:456-556): one NUTS chain over the hierarchical model started at the MLE with the MAP
     inverse Hessian as the Gaussian kinetic energy's M^-1 and initial step size `eps`.  Returns
     {"posterior_matrix": (nvariables, Nsteps) in natural units, "logp": (Nsteps,), "step_size": float}."""
     rng = np.random.default_rng() if rng is None else rng
     MAP, MLE = bfgs_result["map"], bfgs_result["mle"]
     inst = HierarchicalOptimizer(MLE.MH_model, MLE.disp_model, device_stack(models, data), data, logAge, metallicities, True, True, True)
+    if engine == "native":
+        res, _ = _native_sample_sfh(inst, [np.asarray(MLE.result.x, dtype=np.float64)], [Nsteps], np.asarray(MAP.invH, dtype=np.float64), eps,
+                                    nwarmup, max_depth, int(rng.integers(0, 2**63)))
+        s, lps, step = res[0]
+        return {"posterior_matrix": _expand_posterior(MLE, s.T), "logp": lps, "step_size": step}
     s, lps, step = nuts_sample(inst.logdensity_and_gradient, np.asarray(MLE.result.x, dtype=np.float64), Nsteps, nwarmup, max_depth,
                                rng=rng, inv_mass=np.asarray(MAP.invH, dtype=np.float64), eps0=eps)
     return {"posterior_matrix": _expand_posterior(MLE, s.T), "logp": lps, "step_size": step}
 
 
 def tsample_sfh(bfgs_result, models, data, logAge, metallicities, Nsteps, eps=0.05, rng=None, chain_length=100, nwarmup=0,
-                max_depth=8, batched=True):
+                max_depth=8, batched=True, engine="host"):
     """tsample_sfh (generic_fitting.jl:564-665): ceil(Nsteps / chain_length) short chains, each started from a draw of
     MvNormal(MLE minimizer, MAP.invH) (:586, :619).  The reference spawns one task per chain, every task evaluating its own
     hierarchical `fg!`; here the chains are coroutines whose gradient requests are served `batched` -- one
@@ -869,7 +993,9 @@ def tsample_sfh(bfgs_result, models, data, logAge, metallicities, Nsteps, eps=0.
 
     def chain(th0, nsteps, nw, md, rng=None, _n=iter(lens)):
         return nuts_chain(th0, next(_n), nw, md, rng=rng, inv_mass=cov, eps0=eps)
-    if batched and len(lens) > 1:
+    if engine == "native":                                                 # chain threads + batching inside the library
+        res, stats = _native_sample_sfh(inst, list(starts), lens, cov, eps, nwarmup, max_depth, int(rng.integers(0, 2**63)))
+    elif batched and len(lens) > 1:
         res, stats = run_chains_batched(inst.logdensity_and_gradient_batched, list(starts), 0, nwarmup, max_depth, rngs, chain=chain)
     else:
         res = [nuts_sample(inst.logdensity_and_gradient, starts[k], lens[k], nwarmup, max_depth, rng=rngs[k], inv_mass=cov, eps0=eps)
