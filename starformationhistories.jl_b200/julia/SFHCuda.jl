@@ -248,4 +248,41 @@ function fit_sfh_bfgs(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, d
     return x, invH, rep
 end
 
+# ---- native multi-chain NUTS: one ccall per sampling run (include/sfhcuda.h: sfh_hmc_sample_nuts / sfh_sample_sfh_nuts) -----------
+# Replaces the Threads.@threads loop of DynamicHMC chains in hmc_sample (hmc_sample.jl:123-141) and the task-per-chain loop of
+# tsample_sfh (generic_fitting.jl:617-626): the chains run as threads inside the library and share one batched device pass per round.
+struct NutsOpts; struct_size::Int32; max_depth::Int32; nwarmup::Int64; delta::Float64; eps0::Float64; seed::UInt64; mass_kind::Int32; reserved::Int32; end
+
+# theta0: ntemplates x nchains (log coefficients).  Returns samples in natural units shaped (nsteps, ntemplates, nchains) like hmc_sample.
+function hmc_sample_nuts(models::DeviceStack, theta0::Matrix{Float64}, nsteps::Integer; nwarmup::Integer=200, max_depth::Integer=8,
+                         seed::UInt64=rand(UInt64))
+    T, nch = size(theta0); lens = fill(Int64(nsteps), nch)
+    samples = Matrix{Float64}(undef, T, nsteps * nch); lps = Vector{Float64}(undef, nsteps * nch); steps = Vector{Float64}(undef, nch)
+    o = NutsOpts(sizeof(NutsOpts), max_depth, nwarmup, 0.8, 0.0, seed, 0, 0)
+    check(ccall((:sfh_hmc_sample_nuts, libsfh), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{NutsOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+                models.ctx[], nch, theta0, lens, C_NULL, o, samples, lps, steps, C_NULL, C_NULL))
+    return permutedims(reshape(exp.(samples), T, nsteps, nch), (2, 1, 3))
+end
+
+# x0s: (Nj + nfree) x nchains starting points in the transformed space (tsample_sfh draws them from MvNormal(MLE, MAP.invH), :586);
+# invH = MAP.invH is the dense M^-1 of the kinetic energy (:479-482), ϵ the initial step size.  Returns the transformed-space
+# samples (columns, chains concatenated) for exptransform_samples! (:640-658).
+function sample_sfh_nuts(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion, x0s::Matrix{Float64},
+                         lens::Vector{Int64}, invH::Matrix{Float64}, models::DeviceStack, logAge, MH; ϵ::Real=0.05, max_depth::Integer=8,
+                         seed::UInt64=rand(UInt64))
+    c = bind!(models, logAge, MH)
+    par = Float64[fittable_params(MHmodel0)..., fittable_params(dispmodel0)...]
+    tf = Int32[SFH.transforms(MHmodel0)..., SFH.transforms(dispmodel0)...]
+    free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)...]
+    n, nch = size(x0s); tot = sum(lens)
+    samples = Matrix{Float64}(undef, n, tot); lps = Vector{Float64}(undef, tot); steps = Vector{Float64}(undef, nch)
+    o = NutsOpts(sizeof(NutsOpts), max_depth, 0, 0.8, ϵ, seed, 2, 0)
+    check(ccall((:sfh_sample_sfh_nuts, libsfh), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64},
+                 Ref{NutsOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), par, tf, free, nch, x0s, lens, invH, o, samples, lps, steps, C_NULL, C_NULL))
+    return samples, lps, steps
+end
+
 end # module

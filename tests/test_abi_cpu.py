@@ -136,3 +136,16 @@ def test_identity_cache_detects_recycled_ids():
     del a
     assert refs[0]() is None and not F._same(refs, np.ones((4, 2)))
     assert F._weak_ids([[1, 2], [3, 4]]) is None
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/sfhcuda.h is valid C99 and a plain C program links and runs against libsfhcuda.so (tests/abi_c_smoke.c)."""
+    import sfh_b200
+    exe = tmp_path / "abi_c_smoke"
+    libdir = os.path.dirname(sfh_b200._lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c_smoke.c"), "-o", str(exe), "-L", libdir, "-l:libsfhcuda.so", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(tmp_path / "smoke.sfh")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "abi_c_smoke: ok" in r.stdout
