@@ -44,6 +44,19 @@ static int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+// No exception may cross the C boundary (include/sfhcuda.h: "nothing throws"): every entry point runs inside this guard.
+template <typename F>
+static int guarded(F &&body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return fail(SFH_ERR_OOM, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(SFH_ERR_INVALID_ARG, "unexpected exception: %s", e.what());
+    } catch (...) {
+        return fail(SFH_ERR_INVALID_ARG, "unexpected exception");
+    }
+}
 #define CU_TRY(expr)                                                                                  \
     do {                                                                                              \
         cudaError_t _e = (expr);                                                                      \
@@ -542,18 +555,21 @@ int stack_common_init(sfh_stack *s, int64_t nbins, int64_t ntemplates, int dtype
 // ---------------------------------------------------------------------------------------------
 extern "C" int sfh_version(void) { return SFH_VERSION_MAJOR * 100 + SFH_VERSION_MINOR; }
 extern "C" const char *sfh_last_error(void) { return g_err.c_str(); }
-extern "C" int sfh_device_count(int *count) {
+static int sfh_device_count_impl(int *count) {
     if (!count) return fail(SFH_ERR_INVALID_ARG, "count is NULL");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
     *count = n;
     return SFH_OK;
 }
+extern "C" int sfh_device_count(int *count) {
+    return guarded([&]() -> int { return sfh_device_count_impl(count); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // stack
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfh_stack_create(sfh_stack **out, const void *models, int64_t nbins, int64_t ntemplates, int dtype,
+static int sfh_stack_create_impl(sfh_stack **out, const void *models, int64_t nbins, int64_t ntemplates, int dtype,
                                 const void *data, int data_dtype, const sfh_opts *opts) {
     if (!out) return fail(SFH_ERR_INVALID_ARG, "out is NULL");
     *out = nullptr;
@@ -570,16 +586,23 @@ extern "C" int sfh_stack_create(sfh_stack **out, const void *models, int64_t nbi
     *out = s;
     return SFH_OK;
 }
+extern "C" int sfh_stack_create(sfh_stack **out, const void *models, int64_t nbins, int64_t ntemplates, int dtype,
+                                const void *data, int data_dtype, const sfh_opts *opts) {
+    return guarded([&]() -> int { return sfh_stack_create_impl(out, models, nbins, ntemplates, dtype, data, data_dtype, opts); });
+}
 
-extern "C" int sfh_stack_set_data(sfh_stack *s, const void *data, int data_dtype) {
+static int sfh_stack_set_data_impl(sfh_stack *s, const void *data, int data_dtype) {
     if (!s || !data) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     if (data_dtype != SFH_F32 && data_dtype != SFH_F64 && data_dtype != SFH_I64)
         return fail(SFH_ERR_INVALID_ARG, "bad data dtype %d", data_dtype);
     CU_TRY(cudaSetDevice(s->device));
     return upload_data(s, data, data_dtype, s->row_begin);
 }
+extern "C" int sfh_stack_set_data(sfh_stack *s, const void *data, int data_dtype) {
+    return guarded([&]() -> int { return sfh_stack_set_data_impl(s, data, data_dtype); });
+}
 
-extern "C" int sfh_stack_destroy(sfh_stack *s) {
+static int sfh_stack_destroy_impl(sfh_stack *s) {
     if (!s) return SFH_OK;
     if (s->dM || s->d_data) {
         cudaSetDevice(s->device);
@@ -589,8 +612,11 @@ extern "C" int sfh_stack_destroy(sfh_stack *s) {
     delete s;
     return SFH_OK;
 }
+extern "C" int sfh_stack_destroy(sfh_stack *s) {
+    return guarded([&]() -> int { return sfh_stack_destroy_impl(s); });
+}
 
-extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
+static int sfh_stack_info_impl(const sfh_stack *s, sfh_info *info) {
     if (!s || !info) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     memset(info, 0, sizeof *info);
     info->nbins_total = s->nb_total; info->ntemplates = s->nt; info->row_begin = s->row_begin; info->row_end = s->row_end;
@@ -600,8 +626,11 @@ extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
     info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->clamp_eps = s->eps;
     return SFH_OK;
 }
+extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
+    return guarded([&]() -> int { return sfh_stack_info_impl(s, info); });
+}
 
-extern "C" int sfh_stack_download(const sfh_stack *s, void *models_out, double *data_out) {
+static int sfh_stack_download_impl(const sfh_stack *s, void *models_out, double *data_out) {
     if (!s) return fail(SFH_ERR_INVALID_ARG, "NULL stack");
     CU_TRY(cudaSetDevice(s->device));
     const size_t es = elem_size(s->dtype);
@@ -610,11 +639,14 @@ extern "C" int sfh_stack_download(const sfh_stack *s, void *models_out, double *
     if (data_out && s->rows > 0) CU_TRY(cudaMemcpy(data_out, s->d_data, (size_t)s->rows * 8, cudaMemcpyDeviceToHost));
     return SFH_OK;
 }
+extern "C" int sfh_stack_download(const sfh_stack *s, void *models_out, double *data_out) {
+    return guarded([&]() -> int { return sfh_stack_download_impl(s, models_out, data_out); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out) {
+static int sfh_ctx_create_impl(sfh_stack *s, void *stream, sfh_ctx **out) {
     if (!s || !out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     *out = nullptr;
     CU_TRY(cudaSetDevice(s->device));
@@ -660,8 +692,11 @@ extern "C" int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out) {
     *out = c;
     return SFH_OK;
 }
+extern "C" int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out) {
+    return guarded([&]() -> int { return sfh_ctx_create_impl(s, stream, out); });
+}
 
-extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
+static int sfh_ctx_destroy_impl(sfh_ctx *c) {
     if (!c) return SFH_OK;
     if (c->s) cudaSetDevice(c->s->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
@@ -687,16 +722,25 @@ extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
     delete c;
     return SFH_OK;
 }
+extern "C" int sfh_ctx_destroy(sfh_ctx *c) {
+    return guarded([&]() -> int { return sfh_ctx_destroy_impl(c); });
+}
 
-extern "C" int sfh_ctx_stats(const sfh_ctx *c, sfh_stats *out) {
+static int sfh_ctx_stats_impl(const sfh_ctx *c, sfh_stats *out) {
     if (!c || !out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     *out = c->stats;
     return SFH_OK;
 }
-extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
+extern "C" int sfh_ctx_stats(const sfh_ctx *c, sfh_stats *out) {
+    return guarded([&]() -> int { return sfh_ctx_stats_impl(c, out); });
+}
+static int sfh_ctx_synchronize_impl(sfh_ctx *c) {
     if (!c) return fail(SFH_ERR_INVALID_ARG, "NULL ctx");
     CU_TRY(cudaStreamSynchronize(c->stream));
     return SFH_OK;
+}
+extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
+    return guarded([&]() -> int { return sfh_ctx_synchronize_impl(c); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -826,16 +870,19 @@ inline double guard_neg_logl(double logL) {  // fitting_base.jl:95 then the sign
 }
 }  // namespace
 
-extern "C" int sfh_enqueue_fg(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G) {
+static int sfh_enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G) {
     if (!c || !d_coeffs || !d_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     CU_TRY(cudaSetDevice(c->s->device));
     return enqueue_fg_impl(c, d_coeffs, d_out, want_G, false);
+}
+extern "C" int sfh_enqueue_fg(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G) {
+    return guarded([&]() -> int { return sfh_enqueue_fg_impl(c, d_coeffs, d_out, want_G); });
 }
 
 // ---------------------------------------------------------------------------------------------
 // core path, host-synchronous
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, double *G, double *composite_out) {
+static int sfh_eval_fg_impl(sfh_ctx *c, const double *coeffs, double *neg_logL, double *G, double *composite_out) {
     if (!c || !coeffs) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     sfh_stack *s = c->s;
     CU_TRY(cudaSetDevice(s->device));
@@ -862,22 +909,31 @@ extern "C" int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, d
     }
     return SFH_OK;
 }
+extern "C" int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, double *G, double *composite_out) {
+    return guarded([&]() -> int { return sfh_eval_fg_impl(c, coeffs, neg_logL, G, composite_out); });
+}
 
-extern "C" int sfh_composite(sfh_ctx *c, const double *coeffs, double *composite_out) {
+static int sfh_composite_impl(sfh_ctx *c, const double *coeffs, double *composite_out) {
     if (!c || !coeffs || !composite_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     SFH_TRY(sfh_eval_fg(c, coeffs, nullptr, nullptr, composite_out));
     return SFH_OK;
 }
+extern "C" int sfh_composite(sfh_ctx *c, const double *coeffs, double *composite_out) {
+    return guarded([&]() -> int { return sfh_composite_impl(c, coeffs, composite_out); });
+}
 
-extern "C" int sfh_loglikelihood_coeffs(sfh_ctx *c, const double *coeffs, double *logL) {
+static int sfh_loglikelihood_coeffs_impl(sfh_ctx *c, const double *coeffs, double *logL) {
     if (!c || !coeffs || !logL) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     double nl = 0.0;
     SFH_TRY(sfh_eval_fg(c, coeffs, &nl, nullptr, nullptr));
     *logL = -nl;
     return SFH_OK;
 }
+extern "C" int sfh_loglikelihood_coeffs(sfh_ctx *c, const double *coeffs, double *logL) {
+    return guarded([&]() -> int { return sfh_loglikelihood_coeffs_impl(c, coeffs, logL); });
+}
 
-extern "C" int sfh_loglikelihood(sfh_ctx *c, const double *composite, double *logL) {
+static int sfh_loglikelihood_impl(sfh_ctx *c, const double *composite, double *logL) {
     if (!c || !composite || !logL) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     sfh_stack *s = c->s;
     CU_TRY(cudaSetDevice(s->device));
@@ -895,8 +951,11 @@ extern "C" int sfh_loglikelihood(sfh_ctx *c, const double *composite, double *lo
     *logL = -guard_neg_logl(c->h_out[0]);
     return SFH_OK;
 }
+extern "C" int sfh_loglikelihood(sfh_ctx *c, const double *composite, double *logL) {
+    return guarded([&]() -> int { return sfh_loglikelihood_impl(c, composite, logL); });
+}
 
-extern "C" int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, double *G) {
+static int sfh_grad_loglikelihood_impl(sfh_ctx *c, double *composite_inout, double *G) {
     if (!c || !composite_inout || !G) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     sfh_stack *s = c->s;
     CU_TRY(cudaSetDevice(s->device));
@@ -925,11 +984,14 @@ extern "C" int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, doubl
     if (s->rows > 0) CU_TRY(cudaMemcpy(composite_inout, c->d_residual, (size_t)s->rows * 8, cudaMemcpyDeviceToHost));
     return SFH_OK;
 }
+extern "C" int sfh_grad_loglikelihood(sfh_ctx *c, double *composite_inout, double *G) {
+    return guarded([&]() -> int { return sfh_grad_loglikelihood_impl(c, composite_inout, G); });
+}
 
 // column sums of the stack: colsum_j = sum_i M_ij.  One-shot post-processing helper for the "next" rows of SURVEY.md
 // section 8f: mdf_amr(coeffs, logAge, MH, models) (src/fitting/mdf.jl:54-74) sums composite Hess diagrams per
 // metallicity, i.e. sum_j coeffs_j * colsum_j over the templates of that metallicity.
-extern "C" int sfh_column_sums(sfh_ctx *c, double *colsums_out) {
+static int sfh_column_sums_impl(sfh_ctx *c, double *colsums_out) {
     if (!c || !colsums_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     sfh_stack *s = c->s;
     CU_TRY(cudaSetDevice(s->device));
@@ -954,11 +1016,14 @@ extern "C" int sfh_column_sums(sfh_ctx *c, double *colsums_out) {
     memcpy(colsums_out, c->h_out, (size_t)s->nt * 8);
     return SFH_OK;
 }
+extern "C" int sfh_column_sums(sfh_ctx *c, double *colsums_out) {
+    return guarded([&]() -> int { return sfh_column_sums_impl(c, colsums_out); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // hierarchical path
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfh_hier_bind(sfh_ctx *c, const double *logAge, const double *MH, int64_t *n_ages_out) {
+static int sfh_hier_bind_impl(sfh_ctx *c, const double *logAge, const double *MH, int64_t *n_ages_out) {
     if (!c || !logAge || !MH) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     sfh_stack *s = c->s;
     CU_TRY(cudaSetDevice(s->device));
@@ -1014,6 +1079,9 @@ extern "C" int sfh_hier_bind(sfh_ctx *c, const double *logAge, const double *MH,
     if (n_ages_out) *n_ages_out = nj;
     return SFH_OK;
 }
+extern "C" int sfh_hier_bind(sfh_ctx *c, const double *logAge, const double *MH, int64_t *n_ages_out) {
+    return guarded([&]() -> int { return sfh_hier_bind_impl(c, logAge, MH, n_ages_out); });
+}
 
 namespace {
 int fill_hier_params(sfh_ctx *c, HierParams &hp, int mh_kind, const double *mh_fixed, int disp_kind,
@@ -1037,7 +1105,7 @@ int fill_hier_params(sfh_ctx *c, HierParams &hp, int mh_kind, const double *mh_f
 }
 }  // namespace
 
-extern "C" int sfh_calculate_coeffs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind,
+static int sfh_calculate_coeffs_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind,
                                     const double *variables, double *coeffs_out) {
     if (!c || !variables || !coeffs_out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     CU_TRY(cudaSetDevice(c->s->device));
@@ -1054,8 +1122,12 @@ extern "C" int sfh_calculate_coeffs(sfh_ctx *c, int mh_kind, const double *mh_fi
     memcpy(coeffs_out, c->h_out, (size_t)c->s->nt * 8);
     return SFH_OK;
 }
+extern "C" int sfh_calculate_coeffs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind,
+                                    const double *variables, double *coeffs_out) {
+    return guarded([&]() -> int { return sfh_calculate_coeffs_impl(c, mh_kind, mh_fixed, disp_kind, variables, coeffs_out); });
+}
 
-extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *variables,
+static int sfh_eval_fg_hier_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *variables,
                                 const uint8_t *free_mask, double *neg_logL, double *G) {
     if (!c || !variables) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     CU_TRY(cudaSetDevice(c->s->device));
@@ -1086,6 +1158,10 @@ extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed,
     if (neg_logL) *neg_logL = c->h_out[0];
     if (G) memcpy(G, c->h_out + 1, nv * 8);
     return SFH_OK;
+}
+extern "C" int sfh_eval_fg_hier(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *variables,
+                                const uint8_t *free_mask, double *neg_logL, double *G) {
+    return guarded([&]() -> int { return sfh_eval_fg_hier_impl(c, mh_kind, mh_fixed, disp_kind, variables, free_mask, neg_logL, G); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1200,14 +1276,17 @@ int enqueue_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_log
 }
 }  // namespace
 
-extern "C" int sfh_enqueue_logl_batched(sfh_ctx *c, const double *d_X, int64_t W, double *d_logL) {
+static int sfh_enqueue_logl_batched_impl(sfh_ctx *c, const double *d_X, int64_t W, double *d_logL) {
     if (!c || !d_X || !d_logL || W <= 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     CU_TRY(cudaSetDevice(c->s->device));
     SFH_TRY(ensure_walker_capacity(c, W));
     return enqueue_batched_impl(c, d_X, W, d_logL);
 }
+extern "C" int sfh_enqueue_logl_batched(sfh_ctx *c, const double *d_X, int64_t W, double *d_logL) {
+    return guarded([&]() -> int { return sfh_enqueue_logl_batched_impl(c, d_X, W, d_logL); });
+}
 
-extern "C" int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL) {
+static int sfh_eval_logl_batched_impl(sfh_ctx *c, const double *X, int64_t W, double *logL) {
     if (!c || !X || !logL || W < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (W == 0) return SFH_OK;
     sfh_stack *s = c->s;
@@ -1218,6 +1297,9 @@ extern "C" int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, dou
     CU_TRY(cudaMemcpyAsync(logL, c->d_logl, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return SFH_OK;
+}
+extern "C" int sfh_eval_logl_batched(sfh_ctx *c, const double *X, int64_t W, double *logL) {
+    return guarded([&]() -> int { return sfh_eval_logl_batched_impl(c, X, W, logL); });
 }
 
 // Device-resident stretch-move ensemble sampler around K6 (see sfh_ensemble.cuh).
@@ -1233,7 +1315,7 @@ struct DevBufs {  // frees whatever was allocated when the run ends or fails
 };
 }  // namespace
 
-extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, int64_t nthin, double a_scale, uint64_t seed,
+static int sfh_mcmc_run_impl(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, int64_t nthin, double a_scale, uint64_t seed,
                             double *chain, double *logl_chain, double *logl_final, double *accept_frac) {
     if (!c || !X || nsteps < 0 || nthin < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (W < 2 || (W & 1)) return fail(SFH_ERR_INVALID_ARG, "the ensemble needs an even number of walkers (got %lld)", (long long)W);
@@ -1315,6 +1397,10 @@ extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, in
     if (accept_frac) *accept_frac = nsteps > 0 ? (double)acc / ((double)nsteps * (double)W) : 0.0;
     return SFH_OK;
 }
+extern "C" int sfh_mcmc_run(sfh_ctx *c, double *X, int64_t W, int64_t nsteps, int64_t nthin, double a_scale, uint64_t seed,
+                            double *chain, double *logl_chain, double *logl_final, double *accept_frac) {
+    return guarded([&]() -> int { return sfh_mcmc_run_impl(c, X, W, nsteps, nthin, a_scale, seed, chain, logl_chain, logl_final, accept_frac); });
+}
 
 // fg! for C coefficient vectors in one device pass (multi-chain HMC / many short chains): -logL_c and
 // G[:, c] = M'(1 - n/m_c) with exactly the per-vector semantics of sfh_eval_fg.
@@ -1390,7 +1476,7 @@ int enqueue_bgrad(sfh_ctx *c, int64_t Cb, int nsplit, double *out, int64_t ostri
 }
 }  // namespace
 
-extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G) {
+static int sfh_eval_fg_batched_impl(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G) {
     if (!c || !X || C < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (C == 0) return SFH_OK;
     sfh_stack *s = c->s;
@@ -1418,11 +1504,14 @@ extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, doubl
     }
     return SFH_OK;
 }
+extern "C" int sfh_eval_fg_batched(sfh_ctx *c, const double *X, int64_t C, double *neg_logL, double *G) {
+    return guarded([&]() -> int { return sfh_eval_fg_batched_impl(c, X, C, neg_logL, G); });
+}
 
 // Hierarchical fg! for C variable vectors in one pass (the chains of sample_sfh / tsample_sfh, generic_fitting.jl:564-665):
 // C prologues (calculate_coeffs) fill the T x C coefficient matrix on the device, the two DMMA GEMMs of
 // sfh_eval_fg_batched give logL_c and M'r_c, C epilogues apply the chain rule; only (Nj + 3) x C numbers cross PCIe.
-extern "C" int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *V, int64_t C,
+static int sfh_eval_fg_hier_batched_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *V, int64_t C,
                                         const uint8_t *free_mask, double *neg_logL, double *G) {
     if (!c || !V || C < 0) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (C == 0) return SFH_OK;
@@ -1480,11 +1569,15 @@ extern "C" int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *m
     }
     return SFH_OK;
 }
+extern "C" int sfh_eval_fg_hier_batched(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *V, int64_t C,
+                                        const uint8_t *free_mask, double *neg_logL, double *G) {
+    return guarded([&]() -> int { return sfh_eval_fg_hier_batched_impl(c, mh_kind, mh_fixed, disp_kind, V, C, free_mask, neg_logL, G); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // multi-GPU
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfh_comm_unique_id(void *id128) {
+static int sfh_comm_unique_id_impl(void *id128) {
     if (!id128) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     if (!load_nccl()) return fail(SFH_ERR_NCCL, "libnccl.so.2 not found");
     NcclUniqueId id;
@@ -1493,8 +1586,11 @@ extern "C" int sfh_comm_unique_id(void *id128) {
     memcpy(id128, &id, 128);
     return SFH_OK;
 }
+extern "C" int sfh_comm_unique_id(void *id128) {
+    return guarded([&]() -> int { return sfh_comm_unique_id_impl(id128); });
+}
 
-extern "C" int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128) {
+static int sfh_comm_init_impl(sfh_ctx *c, int nranks, int rank, const void *id128) {
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (!load_nccl()) return fail(SFH_ERR_NCCL, "libnccl.so.2 not found");
     CU_TRY(cudaSetDevice(c->s->device));
@@ -1509,10 +1605,13 @@ extern "C" int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128
     c->rank = rank;
     return SFH_OK;
 }
+extern "C" int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128) {
+    return guarded([&]() -> int { return sfh_comm_init_impl(c, nranks, rank, id128); });
+}
 
 // One-shot all-reduce over NVLink peer memory (K7 v2).  Each rank exposes an "inbox" through CUDA IPC; the finalize
 // kernel's tail stores this shard's [logL, G] into every rank's inbox and a combine kernel sums them in rank order.
-extern "C" int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out) {
+static int sfh_comm_p2p_handle_impl(sfh_ctx *c, int nranks, void *handle64_out) {
     if (!c || !handle64_out || nranks < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     CU_TRY(cudaSetDevice(c->s->device));
     if (!c->d_inbox) {
@@ -1528,8 +1627,11 @@ extern "C" int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out) {
     memcpy(handle64_out, &h, 64);
     return SFH_OK;
 }
+extern "C" int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out) {
+    return guarded([&]() -> int { return sfh_comm_p2p_handle_impl(c, nranks, handle64_out); });
+}
 
-extern "C" int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *handles) {
+static int sfh_comm_p2p_init_impl(sfh_ctx *c, int nranks, int rank, const void *handles) {
     if (!c || !handles || nranks < 1 || rank < 0 || rank >= nranks) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (!c->d_inbox) return fail(SFH_ERR_INVALID_ARG, "call sfh_comm_p2p_handle first");
     if (nranks > 32) return fail(SFH_ERR_UNSUPPORTED, "too many ranks for the one-shot reduce");
@@ -1554,11 +1656,14 @@ extern "C" int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *h
     c->p2p = true;
     return SFH_OK;
 }
+extern "C" int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *handles) {
+    return guarded([&]() -> int { return sfh_comm_p2p_init_impl(c, nranks, rank, handles); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // synthetic stacks + device-timed loop (bench plumbing)
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_t ntemplates, int dtype, uint64_t seed,
+static int sfh_stack_create_synthetic_impl(sfh_stack **out, int64_t nbins, int64_t ntemplates, int dtype, uint64_t seed,
                                           double scale, const double *x_true, const sfh_opts *opts) {
     if (!out || !x_true) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     *out = nullptr;
@@ -1599,9 +1704,13 @@ extern "C" int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_
     sfh_ctx_destroy(c);
     return done(st);
 }
+extern "C" int sfh_stack_create_synthetic(sfh_stack **out, int64_t nbins, int64_t ntemplates, int dtype, uint64_t seed,
+                                          double scale, const double *x_true, const sfh_opts *opts) {
+    return guarded([&]() -> int { return sfh_stack_create_synthetic_impl(out, nbins, ntemplates, dtype, seed, scale, x_true, opts); });
+}
 
 // Template stack built on the device from ragged per-template point lists (see sfh_templates.cuh).
-extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t ny, double xfirst, double xstep, double yfirst,
+static int sfh_stack_create_from_points_impl(sfh_stack **out, int64_t nx, int64_t ny, double xfirst, double xstep, double yfirst,
                                             double ystep, int64_t ntemplates, const int64_t *offsets, const double *colors,
                                             const double *mags, const double *color_err, const double *mag_err,
                                             const double *weights, const int32_t *cov_mult, int dtype, const void *data,
@@ -1679,6 +1788,13 @@ extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t
     else if (s->rows > 0 && cudaMemset(s->d_data, 0, (size_t)s->rows * 8) != cudaSuccess) st = fail(SFH_ERR_CUDA, "memset failed");
     return done(st);
 }
+extern "C" int sfh_stack_create_from_points(sfh_stack **out, int64_t nx, int64_t ny, double xfirst, double xstep, double yfirst,
+                                            double ystep, int64_t ntemplates, const int64_t *offsets, const double *colors,
+                                            const double *mags, const double *color_err, const double *mag_err,
+                                            const double *weights, const int32_t *cov_mult, int dtype, const void *data,
+                                            int data_dtype, const sfh_opts *opts) {
+    return guarded([&]() -> int { return sfh_stack_create_from_points_impl(out, nx, ny, xfirst, xstep, yfirst, ystep, ntemplates, offsets, colors, mags, color_err, mag_err, weights, cov_mult, dtype, data, data_dtype, opts); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // on-disk container (csrc/sfh_file.h): generic array files, stack save / load
@@ -1695,13 +1811,16 @@ void fill_desc(const sfh::file::ArrayEntry &e, sfh_array_desc *d) {
 }
 }  // namespace
 
-extern "C" int sfh_checksum64(const void *data, int64_t nbytes, uint64_t *out) {
+static int sfh_checksum64_impl(const void *data, int64_t nbytes, uint64_t *out) {
     if (!out || nbytes < 0 || (!data && nbytes > 0)) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     *out = sfh::file::checksum(data, (uint64_t)nbytes);
     return SFH_OK;
 }
+extern "C" int sfh_checksum64(const void *data, int64_t nbytes, uint64_t *out) {
+    return guarded([&]() -> int { return sfh_checksum64_impl(data, nbytes, out); });
+}
 
-extern "C" int sfh_file_write(const char *path, int kind, const int64_t *attrs8, int narrays, const sfh_array_desc *descs,
+static int sfh_file_write_impl(const char *path, int kind, const int64_t *attrs8, int narrays, const sfh_array_desc *descs,
                               const void *const *ptrs) {
     if (!path || narrays < 0 || (narrays > 0 && (!descs || !ptrs))) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     std::vector<sfh::file::ArraySpec> specs((size_t)narrays);
@@ -1725,8 +1844,12 @@ extern "C" int sfh_file_write(const char *path, int kind, const int64_t *attrs8,
     if (!w.commit(&err)) return fail(SFH_ERR_IO, "%s", err.c_str());
     return SFH_OK;
 }
+extern "C" int sfh_file_write(const char *path, int kind, const int64_t *attrs8, int narrays, const sfh_array_desc *descs,
+                              const void *const *ptrs) {
+    return guarded([&]() -> int { return sfh_file_write_impl(path, kind, attrs8, narrays, descs, ptrs); });
+}
 
-extern "C" int sfh_file_open(const char *path, sfh_file **out) {
+static int sfh_file_open_impl(const char *path, sfh_file **out) {
     if (!path || !out) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     *out = nullptr;
     sfh_file *f = new (std::nothrow) sfh_file();
@@ -1736,43 +1859,61 @@ extern "C" int sfh_file_open(const char *path, sfh_file **out) {
     *out = f;
     return SFH_OK;
 }
+extern "C" int sfh_file_open(const char *path, sfh_file **out) {
+    return guarded([&]() -> int { return sfh_file_open_impl(path, out); });
+}
 
-extern "C" int sfh_file_close(sfh_file *f) {
+static int sfh_file_close_impl(sfh_file *f) {
     delete f;
     return SFH_OK;
 }
+extern "C" int sfh_file_close(sfh_file *f) {
+    return guarded([&]() -> int { return sfh_file_close_impl(f); });
+}
 
-extern "C" int sfh_file_info(const sfh_file *f, int *kind, int *narrays, int64_t *attrs8) {
+static int sfh_file_info_impl(const sfh_file *f, int *kind, int *narrays, int64_t *attrs8) {
     if (!f) return fail(SFH_ERR_INVALID_ARG, "NULL file");
     if (kind) *kind = f->r.header().kind;
     if (narrays) *narrays = f->r.count();
     if (attrs8) memcpy(attrs8, f->r.header().attrs, 8 * sizeof(int64_t));
     return SFH_OK;
 }
+extern "C" int sfh_file_info(const sfh_file *f, int *kind, int *narrays, int64_t *attrs8) {
+    return guarded([&]() -> int { return sfh_file_info_impl(f, kind, narrays, attrs8); });
+}
 
-extern "C" int sfh_file_find(const sfh_file *f, const char *name, int *index) {
+static int sfh_file_find_impl(const sfh_file *f, const char *name, int *index) {
     if (!f || !name || !index) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     *index = f->r.find(name);
     return SFH_OK;
 }
+extern "C" int sfh_file_find(const sfh_file *f, const char *name, int *index) {
+    return guarded([&]() -> int { return sfh_file_find_impl(f, name, index); });
+}
 
-extern "C" int sfh_file_array(const sfh_file *f, int index, sfh_array_desc *desc, const void **data) {
+static int sfh_file_array_impl(const sfh_file *f, int index, sfh_array_desc *desc, const void **data) {
     if (!f) return fail(SFH_ERR_INVALID_ARG, "NULL file");
     if (index < 0 || index >= f->r.count()) return fail(SFH_ERR_INVALID_ARG, "array index %d outside [0,%d)", index, f->r.count());
     if (desc) fill_desc(f->r.entry(index), desc);
     if (data) *data = f->r.data(index);
     return SFH_OK;
 }
+extern "C" int sfh_file_array(const sfh_file *f, int index, sfh_array_desc *desc, const void **data) {
+    return guarded([&]() -> int { return sfh_file_array_impl(f, index, desc, data); });
+}
 
-extern "C" int sfh_file_verify(const sfh_file *f, int index) {
+static int sfh_file_verify_impl(const sfh_file *f, int index) {
     if (!f) return fail(SFH_ERR_INVALID_ARG, "NULL file");
     if (index >= f->r.count()) return fail(SFH_ERR_INVALID_ARG, "array index %d outside [0,%d)", index, f->r.count());
     for (int i = (index < 0 ? 0 : index); i < (index < 0 ? f->r.count() : index + 1); ++i)
         if (!f->r.verify(i)) return fail(SFH_ERR_IO, "array '%s' fails its checksum", f->r.entry(i).name);
     return SFH_OK;
 }
+extern "C" int sfh_file_verify(const sfh_file *f, int index) {
+    return guarded([&]() -> int { return sfh_file_verify_impl(f, index); });
+}
 
-extern "C" int sfh_stack_save(const sfh_stack *s, const char *path, int64_t nx, int64_t ny, const double *logAge, const double *MH) {
+static int sfh_stack_save_impl(const sfh_stack *s, const char *path, int64_t nx, int64_t ny, const double *logAge, const double *MH) {
     if (!s || !path) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     if ((logAge == nullptr) != (MH == nullptr)) return fail(SFH_ERR_INVALID_ARG, "logAge and MH go together");
     if (nx < 0 || ny < 0 || (nx * ny != 0 && nx * ny != s->nb_total))
@@ -1795,8 +1936,11 @@ extern "C" int sfh_stack_save(const sfh_stack *s, const char *path, int64_t nx, 
     if (!w.commit(&err)) return fail(SFH_ERR_IO, "%s", err.c_str());
     return SFH_OK;
 }
+extern "C" int sfh_stack_save(const sfh_stack *s, const char *path, int64_t nx, int64_t ny, const double *logAge, const double *MH) {
+    return guarded([&]() -> int { return sfh_stack_save_impl(s, path, nx, ny, logAge, MH); });
+}
 
-extern "C" int sfh_stack_create_from_file(sfh_stack **out, const char *path, int verify, const sfh_opts *opts) {
+static int sfh_stack_create_from_file_impl(sfh_stack **out, const char *path, int verify, const sfh_opts *opts) {
     if (!out || !path) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     *out = nullptr;
     if (opts && opts->struct_size != (int32_t)sizeof(sfh_opts))
@@ -1832,6 +1976,9 @@ extern "C" int sfh_stack_create_from_file(sfh_stack **out, const char *path, int
     *out = s;
     return SFH_OK;
 }
+extern "C" int sfh_stack_create_from_file(sfh_stack **out, const char *path, int verify, const sfh_opts *opts) {
+    return guarded([&]() -> int { return sfh_stack_create_from_file_impl(out, path, verify, opts); });
+}
 
 // ---------------------------------------------------------------------------------------------
 // native driver loops (csrc/sfh_drivers.h): one call = one whole BFGS optimisation around the device evaluations
@@ -1866,13 +2013,17 @@ int run_bfgs(const sfh::drivers::Objective &obj, int64_t n, double *x, const sfh
 }
 }  // namespace
 
-extern "C" int sfh_minimize_bfgs(sfh_objective_fn fn, void *user, int64_t n, double *x, const sfh_bfgs_opts *opts,
+static int sfh_minimize_bfgs_impl(sfh_objective_fn fn, void *user, int64_t n, double *x, const sfh_bfgs_opts *opts,
                                  sfh_bfgs_report *report, double *invH) {
     if (!fn) return fail(SFH_ERR_INVALID_ARG, "objective is NULL");
     return run_bfgs([&](const double *xx, double *f, double *g) { return fn(user, xx, n, f, g); }, n, x, opts, report, invH);
 }
+extern "C" int sfh_minimize_bfgs(sfh_objective_fn fn, void *user, int64_t n, double *x, const sfh_bfgs_opts *opts,
+                                 sfh_bfgs_report *report, double *invH) {
+    return guarded([&]() -> int { return sfh_minimize_bfgs_impl(fn, user, n, x, opts, report, invH); });
+}
 
-extern "C" int sfh_fit_templates_bfgs(sfh_ctx *c, int transform, double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report,
+static int sfh_fit_templates_bfgs_impl(sfh_ctx *c, int transform, double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report,
                                       double *invH) {
     if (!c || !theta) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     if (transform < SFH_FIT_LOG_MAP || transform > SFH_FIT_SQRT_MLE) return fail(SFH_ERR_INVALID_ARG, "bad transform %d", transform);
@@ -1890,8 +2041,12 @@ extern "C" int sfh_fit_templates_bfgs(sfh_ctx *c, int transform, double *theta, 
     };
     return run_bfgs(obj, n, theta, opts, report, invH);
 }
+extern "C" int sfh_fit_templates_bfgs(sfh_ctx *c, int transform, double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report,
+                                      double *invH) {
+    return guarded([&]() -> int { return sfh_fit_templates_bfgs_impl(c, transform, theta, opts, report, invH); });
+}
 
-extern "C" int sfh_fit_fixed_amr_bfgs(sfh_ctx *c, const double *relweights, const int32_t *age_index, int64_t n_ages, int jacobian,
+static int sfh_fit_fixed_amr_bfgs_impl(sfh_ctx *c, const double *relweights, const int32_t *age_index, int64_t n_ages, int jacobian,
                                       double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
     if (!c || !relweights || !age_index || !theta) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     const int64_t nt = c->s->nt;
@@ -1910,6 +2065,10 @@ extern "C" int sfh_fit_fixed_amr_bfgs(sfh_ctx *c, const double *relweights, cons
     };
     return run_bfgs(obj, n_ages, theta, opts, report, invH);
 }
+extern "C" int sfh_fit_fixed_amr_bfgs(sfh_ctx *c, const double *relweights, const int32_t *age_index, int64_t n_ages, int jacobian,
+                                      double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    return guarded([&]() -> int { return sfh_fit_fixed_amr_bfgs_impl(c, relweights, age_index, n_ages, jacobian, theta, opts, report, invH); });
+}
 
 namespace {
 int check_hier_fit_args(int npar, const int32_t *transforms, const uint8_t *free_mask, int *nfree) {
@@ -1924,7 +2083,7 @@ int check_hier_fit_args(int npar, const int32_t *transforms, const uint8_t *free
 }
 }  // namespace
 
-extern "C" int sfh_fit_sfh_bfgs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+static int sfh_fit_sfh_bfgs_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
                                 const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
                                 const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
     if (!c || !params0 || !transforms || !free_mask || !xvec) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
@@ -1937,8 +2096,13 @@ extern "C" int sfh_fit_sfh_bfgs(sfh_ctx *c, int mh_kind, const double *mh_fixed,
     return run_bfgs(sfh::drivers::hier_objective(inner, c->nj, 3, params0, transforms, free_mask, jacobian_corrections != 0),
                     (int64_t)c->nj + nfree, xvec, opts, report, invH);
 }
+extern "C" int sfh_fit_sfh_bfgs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+                                const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
+                                const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    return guarded([&]() -> int { return sfh_fit_sfh_bfgs_impl(c, mh_kind, mh_fixed, disp_kind, params0, transforms, free_mask, jacobian_corrections, xvec, opts, report, invH); });
+}
 
-extern "C" int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+static int sfh_fit_sfh_bfgs_generic_impl(sfh_objective_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
                                         const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
                                         const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
     if (!inner_fg || !xvec || n_ages < 1 || n_params < 0 || (n_params > 0 && (!params0 || !transforms || !free_mask)))
@@ -1949,6 +2113,11 @@ extern "C" int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, i
     auto inner = [=](const double *x, double *f, double *g) -> int { return inner_fg(user, x, nv, f, g); };
     return run_bfgs(sfh::drivers::hier_objective(inner, n_ages, n_params, params0, transforms, free_mask, jacobian_corrections != 0),
                     n_ages + nfree, xvec, opts, report, invH);
+}
+extern "C" int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+                                        const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
+                                        const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+    return guarded([&]() -> int { return sfh_fit_sfh_bfgs_generic_impl(inner_fg, user, n_ages, n_params, params0, transforms, free_mask, jacobian_corrections, xvec, opts, report, invH); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1998,15 +2167,20 @@ int run_nuts(const sfh::nuts::BatchLogDensity &fn, int64_t n, int64_t nchains, c
 }
 }  // namespace
 
-extern "C" int sfh_nuts_run(sfh_batch_logdensity_fn fn, void *user, int64_t n, int64_t nchains, const double *theta0, const int64_t *nsteps,
+static int sfh_nuts_run_impl(sfh_batch_logdensity_fn fn, void *user, int64_t n, int64_t nchains, const double *theta0, const int64_t *nsteps,
                             const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes,
                             int64_t *n_batches, int64_t *n_evals) {
     if (!fn) return fail(SFH_ERR_INVALID_ARG, "log-density is NULL");
     return run_nuts([=](const double *Th, int64_t C, double *lp, double *g) { return fn(user, Th, n, C, lp, g); }, n, nchains, theta0, nsteps,
                     inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
 }
+extern "C" int sfh_nuts_run(sfh_batch_logdensity_fn fn, void *user, int64_t n, int64_t nchains, const double *theta0, const int64_t *nsteps,
+                            const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes,
+                            int64_t *n_batches, int64_t *n_evals) {
+    return guarded([&]() -> int { return sfh_nuts_run_impl(fn, user, n, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals); });
+}
 
-extern "C" int sfh_hmc_sample_nuts(sfh_ctx *c, int64_t nchains, const double *theta0, const int64_t *nsteps, const double *inv_mass,
+static int sfh_hmc_sample_nuts_impl(sfh_ctx *c, int64_t nchains, const double *theta0, const int64_t *nsteps, const double *inv_mass,
                                    const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes, int64_t *n_batches,
                                    int64_t *n_evals) {
     if (!c) return fail(SFH_ERR_INVALID_ARG, "NULL context");
@@ -2026,8 +2200,13 @@ extern "C" int sfh_hmc_sample_nuts(sfh_ctx *c, int64_t nchains, const double *th
     };
     return run_nuts(fn, n, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
 }
+extern "C" int sfh_hmc_sample_nuts(sfh_ctx *c, int64_t nchains, const double *theta0, const int64_t *nsteps, const double *inv_mass,
+                                   const sfh_nuts_opts *opts, double *samples, double *logps, double *step_sizes, int64_t *n_batches,
+                                   int64_t *n_evals) {
+    return guarded([&]() -> int { return sfh_hmc_sample_nuts_impl(c, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals); });
+}
 
-extern "C" int sfh_sample_sfh_nuts(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+static int sfh_sample_sfh_nuts_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
                                    const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
                                    const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps,
                                    double *step_sizes, int64_t *n_batches, int64_t *n_evals) {
@@ -2041,8 +2220,14 @@ extern "C" int sfh_sample_sfh_nuts(sfh_ctx *c, int mh_kind, const double *mh_fix
     return run_nuts(sfh::nuts::hier_logdensity_batched(inner, c->nj, 3, params0, transforms, free_mask, true), (int64_t)c->nj + nfree, nchains,
                     theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
 }
+extern "C" int sfh_sample_sfh_nuts(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
+                                   const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
+                                   const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples, double *logps,
+                                   double *step_sizes, int64_t *n_batches, int64_t *n_evals) {
+    return guarded([&]() -> int { return sfh_sample_sfh_nuts_impl(c, mh_kind, mh_fixed, disp_kind, params0, transforms, free_mask, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals); });
+}
 
-extern "C" int sfh_sample_sfh_nuts_generic(sfh_batch_logdensity_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+static int sfh_sample_sfh_nuts_generic_impl(sfh_batch_logdensity_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
                                            const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
                                            const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples,
                                            double *logps, double *step_sizes, int64_t *n_batches, int64_t *n_evals) {
@@ -2055,8 +2240,14 @@ extern "C" int sfh_sample_sfh_nuts_generic(sfh_batch_logdensity_fn inner_fg, voi
     return run_nuts(sfh::nuts::hier_logdensity_batched(inner, n_ages, n_params, params0, transforms, free_mask, true), n_ages + nfree, nchains,
                     theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals);
 }
+extern "C" int sfh_sample_sfh_nuts_generic(sfh_batch_logdensity_fn inner_fg, void *user, int64_t n_ages, int32_t n_params, const double *params0,
+                                           const int32_t *transforms, const uint8_t *free_mask, int64_t nchains, const double *theta0,
+                                           const int64_t *nsteps, const double *inv_mass, const sfh_nuts_opts *opts, double *samples,
+                                           double *logps, double *step_sizes, int64_t *n_batches, int64_t *n_evals) {
+    return guarded([&]() -> int { return sfh_sample_sfh_nuts_generic_impl(inner_fg, user, n_ages, n_params, params0, transforms, free_mask, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals); });
+}
 
-extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,
+static int sfh_time_fg_impl(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,
                            double *ms_kernel_out) {
     if (!c || !coeffs || reps < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     sfh_stack *s = c->s;
@@ -2083,4 +2274,8 @@ extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_
     if (ms_per_eval_out) *ms_per_eval_out = tot / reps;
     if (ms_kernel_out) *ms_kernel_out = totk / reps;
     return SFH_OK;
+}
+extern "C" int sfh_time_fg(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,
+                           double *ms_kernel_out) {
+    return guarded([&]() -> int { return sfh_time_fg_impl(c, coeffs, reps, want_G, flush_l2, ms_per_eval_out, ms_kernel_out); });
 }
