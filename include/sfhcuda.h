@@ -291,6 +291,32 @@ int sfh_fit_sfh_bfgs_generic(sfh_objective_fn inner_fg, void *user, int64_t n_ag
                              const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,
                              const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH);
 
+/* fit_templates_lbfgsb (src/fitting/solvers.jl:70-90) hands fg! to LBFGSB.jl with lb = 0, ub = Inf, m = 10, factr = 1e-12,
+ * pgtol = 1e-5.  The same box-constrained limited-memory method (Byrd, Lu, Nocedal & Zhu 1995: generalized Cauchy point,
+ * subspace minimisation, projected-gradient stopping rule) runs natively here (csrc/sfh_drivers.h).                  */
+typedef struct sfh_lbfgsb_opts {
+    int32_t struct_size;   /* = sizeof(sfh_lbfgsb_opts)                                                          */
+    int32_t m;             /* stored correction pairs; 0 = 10                                                    */
+    double factr;          /* relative-reduction tolerance in units of machine epsilon, as in the Fortran code;  */
+                           /* 0 = 1e-12 (solvers.jl:82)                                                          */
+    double pgtol;          /* projected-gradient tolerance; 0 = 1e-5                                             */
+    int64_t maxiter;       /* 0 = 100000                                                                         */
+    int64_t maxfun;        /* 0 = 100000                                                                         */
+} sfh_lbfgsb_opts;
+typedef struct sfh_lbfgsb_report {
+    double f, pg_norm;     /* objective and infinity norm of the projected gradient at the returned point        */
+    int64_t iterations, f_calls;
+    int32_t status;        /* 0: pg_norm <= pgtol; 1: relative reduction <= factr*eps; 2: iteration / evaluation  */
+                           /* limit; 3: line search failed (abnormal termination); 4: start not finite           */
+    int32_t reserved;
+} sfh_lbfgsb_report;
+/* lb / ub: n entries each or NULL for unbounded below / above (use +-HUGE_VAL entries for partially bounded problems). */
+int sfh_minimize_lbfgsb(sfh_objective_fn fn, void *user, int64_t n, double *x, const double *lb, const double *ub,
+                        const sfh_lbfgsb_opts *opts, sfh_lbfgsb_report *report);
+/* fit_templates_lbfgsb on the resident stack: coeffs (ntemplates, in = x0 after renormalize_x0, out = best fit), bounds
+ * 0 <= coeffs (solvers.jl:82-90); report->f = -logL at the solution.                                                 */
+int sfh_fit_templates_lbfgsb(sfh_ctx *c, double *coeffs, const sfh_lbfgsb_opts *opts, sfh_lbfgsb_report *report);
+
 /* Native multi-chain NUTS (csrc/sfh_nuts.h): every chain is a host thread running the No-U-Turn recursion (Hoffman & Gelman
  * 2014, alg. 6, dual-averaging step size, Gaussian kinetic energy) -- the role DynamicHMC plays in hmc_sample
  * (src/fitting/hmc_sample.jl:105-143: one chain per thread) and sample_sfh / tsample_sfh (generic_fitting.jl:456-665: one

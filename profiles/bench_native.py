@@ -39,6 +39,21 @@ out(what="fit_sfh native vs scipy", max_rel_diff_map_mu=float(np.max(np.abs(a["m
     max_rel_diff_mle_mu=float(np.max(np.abs(a["mle"].mu / b["mle"].mu - 1))),
     median_sigma_ratio_map=float(np.median(b["map"].sigma[:60] / a["map"].sigma[:60])))
 
+# ---- BASELINE config 1: fit_templates_lbfgsb, 100x100 bins x 100 templates -------------------------------------------------
+g = np.random.Generator(np.random.Philox(58392))
+x1 = 100 * g.random(100)
+ds1 = S.DeviceStack.synthetic(10000, 100, np.float64, 58392, 1.0, x1)
+d1 = ds1.download_data()
+tt = {}
+for engine in ("scipy", "native", "scipy", "native"):
+    t0 = time.perf_counter()
+    f, xf = S.fit_templates_lbfgsb(ds1, d1, x0=np.ones(100), engine=engine)
+    tt[engine] = (time.perf_counter() - t0, f, xf)
+out(what="fit_templates_lbfgsb config 1 (10000 bins x 100 templates)", scipy_s=tt["scipy"][0], native_s=tt["native"][0],
+    speedup=tt["scipy"][0] / tt["native"][0], rel_diff_coeffs=float(np.linalg.norm(tt["native"][2] - tt["scipy"][2]) / np.linalg.norm(tt["scipy"][2])),
+    rel_diff_nlogL=float(abs(tt["native"][1] - tt["scipy"][1]) / abs(tt["scipy"][1])))
+ds1.close()
+
 for nb, nt in ((10000, 100), (40000, 500)):
     g = np.random.Generator(np.random.Philox(58392))
     x = 100 * g.random(nt)

@@ -61,6 +61,16 @@ class sfh_bfgs_report(C.Structure):
                 ("converged", C.c_int32), ("status", C.c_int32)]
 
 
+class sfh_lbfgsb_opts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("m", C.c_int32), ("factr", C.c_double), ("pgtol", C.c_double), ("maxiter", C.c_int64),
+                ("maxfun", C.c_int64)]
+
+
+class sfh_lbfgsb_report(C.Structure):
+    _fields_ = [("f", C.c_double), ("pg_norm", C.c_double), ("iterations", C.c_int64), ("f_calls", C.c_int64), ("status", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class sfh_nuts_opts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("max_depth", C.c_int32), ("nwarmup", C.c_int64), ("delta", C.c_double),
                 ("eps0", C.c_double), ("seed", C.c_uint64), ("mass_kind", C.c_int32), ("reserved", C.c_int32)]
@@ -127,6 +137,8 @@ PROTOTYPES = {
                                    C.POINTER(sfh_nuts_opts), _dp, _dp, _dp, C.POINTER(_i64), C.POINTER(_i64)]),
     "sfh_sample_sfh_nuts_generic": (_int, [sfh_batch_logdensity_fn, _vp, _i64, C.c_int32, _dp, C.POINTER(C.c_int32), _u8p, _i64, _dp,
                                            C.POINTER(_i64), _dp, C.POINTER(sfh_nuts_opts), _dp, _dp, _dp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "sfh_minimize_lbfgsb": (_int, [sfh_objective_fn, _vp, _i64, _dp, _dp, _dp, C.POINTER(sfh_lbfgsb_opts), C.POINTER(sfh_lbfgsb_report)]),
+    "sfh_fit_templates_lbfgsb": (_int, [_vp, _dp, C.POINTER(sfh_lbfgsb_opts), C.POINTER(sfh_lbfgsb_report)]),
     "sfh_checksum64": (_int, [_vp, _i64, C.POINTER(C.c_uint64)]),
     "sfh_file_write": (_int, [C.c_char_p, _int, C.POINTER(_i64), _int, C.POINTER(sfh_array_desc), C.POINTER(_vp)]),
     "sfh_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),

@@ -2247,6 +2247,56 @@ extern "C" int sfh_sample_sfh_nuts_generic(sfh_batch_logdensity_fn inner_fg, voi
     return guarded([&]() -> int { return sfh_sample_sfh_nuts_generic_impl(inner_fg, user, n_ages, n_params, params0, transforms, free_mask, nchains, theta0, nsteps, inv_mass, opts, samples, logps, step_sizes, n_batches, n_evals); });
 }
 
+namespace {
+int run_lbfgsb(const sfh::drivers::Objective &obj, int64_t n, double *x, const double *lb, const double *ub, const sfh_lbfgsb_opts *opts,
+               sfh_lbfgsb_report *report) {
+    if (n < 1 || !x) return fail(SFH_ERR_INVALID_ARG, "need a start vector of at least one variable");
+    if (opts && opts->struct_size != (int32_t)sizeof(sfh_lbfgsb_opts))
+        return fail(SFH_ERR_INVALID_ARG, "sfh_lbfgsb_opts.struct_size mismatch (%d vs %zu)", opts->struct_size, sizeof(sfh_lbfgsb_opts));
+    sfh::drivers::LbfgsbOptions o;
+    if (opts) {
+        if (opts->m < 0 || opts->m > 1000 || opts->factr < 0 || opts->pgtol < 0 || opts->maxiter < 0 || opts->maxfun < 0) return fail(SFH_ERR_INVALID_ARG, "bad sfh_lbfgsb_opts");
+        if (opts->m > 0) o.m = opts->m;
+        if (opts->factr > 0) o.factr = opts->factr;
+        if (opts->pgtol > 0) o.pgtol = opts->pgtol;
+        if (opts->maxiter > 0) o.maxiter = opts->maxiter;
+        if (opts->maxfun > 0) o.maxfun = opts->maxfun;
+    }
+    const double inf = std::numeric_limits<double>::infinity();
+    std::vector<double> lo((size_t)n, -inf), hi((size_t)n, inf);
+    if (lb) std::copy(lb, lb + n, lo.begin());
+    if (ub) std::copy(ub, ub + n, hi.begin());
+    for (int64_t i = 0; i < n; ++i)
+        if (!(lo[(size_t)i] <= hi[(size_t)i])) return fail(SFH_ERR_INVALID_ARG, "lb[%lld] > ub[%lld] (or NaN)", (long long)i, (long long)i);
+    sfh::drivers::LbfgsbReport r;
+    const int st = sfh::drivers::lbfgsb_minimize(obj, n, x, lo.data(), hi.data(), o, &r);
+    if (st != SFH_OK) return st;
+    if (report) {
+        report->f = r.f; report->pg_norm = r.pg_norm; report->iterations = r.iterations; report->f_calls = r.f_calls;
+        report->status = r.status; report->reserved = 0;
+    }
+    return SFH_OK;
+}
+}  // namespace
+
+extern "C" int sfh_minimize_lbfgsb(sfh_objective_fn fn, void *user, int64_t n, double *x, const double *lb, const double *ub,
+                                   const sfh_lbfgsb_opts *opts, sfh_lbfgsb_report *report) {
+    return guarded([&]() -> int {
+        if (!fn) return fail(SFH_ERR_INVALID_ARG, "objective is NULL");
+        return run_lbfgsb([&](const double *xx, double *f, double *g) { return fn(user, xx, n, f, g); }, n, x, lb, ub, opts, report);
+    });
+}
+
+extern "C" int sfh_fit_templates_lbfgsb(sfh_ctx *c, double *coeffs, const sfh_lbfgsb_opts *opts, sfh_lbfgsb_report *report) {
+    return guarded([&]() -> int {
+        if (!c || !coeffs) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
+        const int64_t n = c->s->nt;
+        std::vector<double> zero((size_t)std::max<int64_t>(n, 1), 0.0);
+        auto obj = [&](const double *x, double *f, double *g) -> int { return sfh_eval_fg(c, x, f, g, nullptr); };   // solvers.jl:88
+        return run_lbfgsb(obj, n, coeffs, zero.data(), nullptr, opts, report);                                        // lb = 0, ub = Inf (:82)
+    });
+}
+
 static int sfh_time_fg_impl(sfh_ctx *c, const double *coeffs, int reps, int want_G, int flush_l2, double *ms_per_eval_out,
                            double *ms_kernel_out) {
     if (!c || !coeffs || reps < 1) return fail(SFH_ERR_INVALID_ARG, "bad argument");

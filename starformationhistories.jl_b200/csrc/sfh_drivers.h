@@ -100,9 +100,11 @@ inline double quadmin(double a, double fa, double fpa, double b, double fb) {
 // Strong-Wolfe line search along p from x (Nocedal & Wright algorithms 3.5 and 3.6).  On success x_new / g_new / *f_new hold
 // the accepted point.  Returns 0 on success, -1 if no acceptable step was found, or the objective's own (positive) status.
 inline int wolfe_search(const Objective &fn, int64_t n, const double *x, const double *p, double f0, double dphi0, double alpha1,
-                        const BfgsOptions &o, double *x_new, double *g_new, double *f_new, double *alpha_out, int64_t *f_calls) {
+                        const BfgsOptions &o, double *x_new, double *g_new, double *f_new, double *alpha_out, int64_t *f_calls,
+                        double amax = std::numeric_limits<double>::infinity()) {
     using namespace detail;
     int evals = 0;
+    alpha1 = std::min(alpha1, amax);
     int status = 0;
     auto phi = [&](double a, double *dphi) -> double {
         for (int64_t i = 0; i < n; ++i) x_new[i] = x[i] + a * p[i];
@@ -156,12 +158,13 @@ inline int wolfe_search(const Objective &fn, int64_t n, const double *x, const d
         if (fa1 > f0 + o.c1 * a1 * dphi0 || (i > 0 && fa1 >= fa0)) return zoom(a0, a1, fa0, fa1, da0, alpha_out);
         if (std::fabs(da1) <= -o.c2 * dphi0) { *alpha_out = a1; *f_new = fa1; return 0; }
         if (da1 >= 0) return zoom(a1, a0, fa1, fa0, da1, alpha_out);
+        if (a1 >= amax) { *alpha_out = a1; *f_new = fa1; return 0; }   // still descending at the largest step the bounds allow: take it
         // still descending steeply: extrapolate to where the secant through the two slopes vanishes, kept inside
         // [1.25, 10] x the current step (the scaled first trial can be orders of magnitude short of the minimiser)
         double next = 10.0 * a1;
         if (da1 > da0) next = std::min(10.0 * a1, std::max(1.25 * a1, a1 - da1 * (a1 - a0) / (da1 - da0)));
         a0 = a1; fa0 = fa1; da0 = da1;
-        a1 = next;
+        a1 = std::min(next, amax);
     }
     return -1;
 }
@@ -232,6 +235,299 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
                 for (int64_t i = 0; i < n; ++i) col[i] += a * s[(size_t)i] + b * Hy[(size_t)i];
             }
         });
+    }
+    *rep = r;
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// L-BFGS-B: fit_templates_lbfgsb (src/fitting/solvers.jl:70-90) hands fg! to LBFGSB.jl (the Fortran code of Zhu, Byrd, Lu &
+// Nocedal) with lb = 0, ub = Inf, m = 10, factr = 1e-12, pgtol = 1e-5.  Restated from the published algorithm (Byrd, Lu,
+// Nocedal & Zhu, SIAM J. Sci. Comput. 16 (1995): compact representation B = theta I - W M W', generalized Cauchy point
+// (algorithm CP), direct primal subspace minimisation (section 5.1) with the projection refinement of Morales & Nocedal
+// (ACM TOMS 38 (2011)), line search limited to the feasible segment, curvature-checked updates, projected-gradient and
+// relative-reduction stopping rules).  Third-party engine in the reference: converged answers are pinned, iterates are not.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LbfgsbOptions {
+    int m = 10;               // stored correction pairs (solvers.jl:82)
+    double factr = 1e-12;     // stop when (f_k - f_{k+1}) / max(|f_k|, |f_{k+1}|, 1) <= factr * eps(Float64): in units of machine epsilon
+                              // like the Fortran code, so the reference's 1e-12 (solvers.jl:82) leaves only "no change at all"
+    double pgtol = 1e-5;      // stop when the infinity norm of the projected gradient <= pgtol
+    int64_t maxiter = 100000, maxfun = 100000;
+};
+struct LbfgsbReport {
+    double f = 0, pg_norm = 0;
+    int64_t iterations = 0, f_calls = 0;
+    int status = 0;           // 0: projected gradient <= pgtol; 1: relative reduction <= factr; 2: iteration / evaluation limit;
+                              // 3: line search failed twice (abnormal termination); 4: start not finite
+};
+
+namespace detail {
+// solve A X = B in place for small dense systems (column-major A: k x k, B: k x nrhs), partial pivoting; false if singular
+inline bool solve_small(std::vector<double> A, int k, std::vector<double> &B, int nrhs) {
+    for (int c = 0; c < k; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < k; ++r) if (std::fabs(A[(size_t)(r + c * k)]) > std::fabs(A[(size_t)(piv + c * k)])) piv = r;
+        if (A[(size_t)(piv + c * k)] == 0.0) return false;
+        if (piv != c) {
+            for (int j = 0; j < k; ++j) std::swap(A[(size_t)(c + j * k)], A[(size_t)(piv + j * k)]);
+            for (int j = 0; j < nrhs; ++j) std::swap(B[(size_t)(c + j * k)], B[(size_t)(piv + j * k)]);
+        }
+        const double d = 1.0 / A[(size_t)(c + c * k)];
+        for (int r = c + 1; r < k; ++r) {
+            const double f = A[(size_t)(r + c * k)] * d;
+            if (f == 0.0) continue;
+            for (int j = c; j < k; ++j) A[(size_t)(r + j * k)] -= f * A[(size_t)(c + j * k)];
+            for (int j = 0; j < nrhs; ++j) B[(size_t)(r + j * k)] -= f * B[(size_t)(c + j * k)];
+        }
+    }
+    for (int j = 0; j < nrhs; ++j)
+        for (int r = k - 1; r >= 0; --r) {
+            double v = B[(size_t)(r + j * k)];
+            for (int c = r + 1; c < k; ++c) v -= A[(size_t)(r + c * k)] * B[(size_t)(c + j * k)];
+            B[(size_t)(r + j * k)] = v / A[(size_t)(r + r * k)];
+        }
+    return true;
+}
+}  // namespace detail
+
+// lb / ub: n entries each (+-infinity for "no bound").  x: in = start (projected onto the box), out = solution.
+inline int lbfgsb_minimize(const Objective &fn, int64_t n, double *x, const double *lb, const double *ub, const LbfgsbOptions &o,
+                           LbfgsbReport *rep) {
+    using namespace detail;
+    const double inf = std::numeric_limits<double>::infinity();
+    const int mmax = std::max(1, o.m);
+    std::vector<std::vector<double>> S, Y;                 // correction pairs, oldest first
+    std::vector<double> g((size_t)n), gn((size_t)n), xn((size_t)n), xcp((size_t)n), d((size_t)n), t((size_t)n), xbar((size_t)n);
+    std::vector<double> M;                                  // (2 col) x (2 col), column-major: inverse of [[-D, L'], [L, theta S'S]]
+    double theta = 1.0;
+    int col = 0;
+    LbfgsbReport r;
+    for (int64_t i = 0; i < n; ++i) x[i] = std::min(std::max(x[i], lb[i]), ub[i]);
+    double f = 0;
+    int st = fn(x, &f, g.data());
+    r.f_calls = 1;
+    if (st) return st;
+    auto proj_grad_norm = [&](const double *xx, const double *gg) {
+        double m = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            double gi = gg[i];
+            if (gi < 0) gi = std::max(xx[i] - ub[i], gi); else gi = std::min(xx[i] - lb[i], gi);
+            const double a = std::fabs(gi);
+            if (!(a <= m)) m = a;
+        }
+        return m;
+    };
+    r.f = f; r.pg_norm = proj_grad_norm(x, g.data());
+    if (!std::isfinite(f) || !std::isfinite(r.pg_norm)) { r.status = 4; *rep = r; return 0; }
+    auto wrow = [&](int64_t b, double *w) {                 // row b of W = [Y, theta S]
+        for (int j = 0; j < col; ++j) { w[j] = Y[(size_t)j][(size_t)b]; w[col + j] = theta * S[(size_t)j][(size_t)b]; }
+    };
+    auto Wt_times = [&](const double *v, const std::vector<int64_t> *subset, double *out) {   // out = W' v (over a subset of rows)
+        for (int j = 0; j < 2 * col; ++j) out[j] = 0.0;
+        auto acc = [&](int64_t i) {
+            const double vi = v[i];
+            if (vi == 0.0) return;
+            for (int j = 0; j < col; ++j) { out[j] += Y[(size_t)j][(size_t)i] * vi; out[col + j] += theta * S[(size_t)j][(size_t)i] * vi; }
+        };
+        if (subset) for (int64_t i : *subset) acc(i); else for (int64_t i = 0; i < n; ++i) acc(i);
+    };
+    auto Mv = [&](const double *v, double *out) {
+        const int k = 2 * col;
+        for (int i = 0; i < k; ++i) { double s = 0; for (int j = 0; j < k; ++j) s += M[(size_t)(i + j * k)] * v[j]; out[i] = s; }
+    };
+    auto rebuild_M = [&]() -> bool {
+        const int k = 2 * col;
+        std::vector<double> K((size_t)k * k, 0.0);
+        for (int i = 0; i < col; ++i)
+            for (int j = 0; j < col; ++j) {
+                const double sy = dot(S[(size_t)i].data(), Y[(size_t)j].data(), n);
+                if (i == j) K[(size_t)(i + j * k)] = -sy;                                         // -D
+                if (i > j) { K[(size_t)((col + i) + j * k)] = sy; K[(size_t)(j + (col + i) * k)] = sy; }   // L and L'
+                K[(size_t)((col + i) + (col + j) * k)] = theta * dot(S[(size_t)i].data(), S[(size_t)j].data(), n);
+            }
+        M.assign((size_t)k * k, 0.0);
+        for (int i = 0; i < k; ++i) M[(size_t)(i + i * k)] = 1.0;
+        return solve_small(K, k, M, k);
+    };
+    BfgsOptions ls;
+    ls.c1 = 1e-3; ls.c2 = 0.9; ls.max_linesearch = 20;       // ftol, gtol and the 20-evaluation cap of lnsrlb
+    std::vector<double> p, c, w, tmp, tmp2, v;
+    std::vector<int64_t> order, freeset;
+    bool restarted = false;
+    while (true) {
+        if (r.pg_norm <= o.pgtol) { r.status = 0; break; }
+        if (r.iterations >= o.maxiter || r.f_calls >= o.maxfun) { r.status = 2; break; }
+        const int k = 2 * col;
+        p.assign((size_t)k, 0.0); c.assign((size_t)k, 0.0); w.assign((size_t)k, 0.0); tmp.assign((size_t)k, 0.0); tmp2.assign((size_t)k, 0.0);
+        // ---- generalized Cauchy point (algorithm CP) ----
+        order.clear();
+        for (int64_t i = 0; i < n; ++i) {
+            const double gi = g[(size_t)i];
+            double ti = inf;
+            if (gi < 0 && ub[i] < inf) ti = (x[i] - ub[i]) / gi;
+            else if (gi > 0 && lb[i] > -inf) ti = (x[i] - lb[i]) / gi;
+            t[(size_t)i] = ti;
+            d[(size_t)i] = ti == 0.0 ? 0.0 : -gi;
+            xcp[(size_t)i] = x[i];
+            if (ti > 0 && ti < inf) order.push_back(i);
+        }
+        std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return t[(size_t)a] < t[(size_t)b] || (t[(size_t)a] == t[(size_t)b] && a < b); });
+        if (col > 0) Wt_times(d.data(), nullptr, p.data());
+        double fp = -dot(d.data(), d.data(), n);
+        double fpp = -theta * fp;
+        if (col > 0) { Mv(p.data(), tmp.data()); double s = 0; for (int j = 0; j < k; ++j) s += p[(size_t)j] * tmp[(size_t)j]; fpp -= s; }
+        double dtmin = fpp > 0 ? -fp / fpp : inf, told = 0.0;
+        size_t nb = 0;
+        bool hit_all = false;
+        if (fp == 0.0) dtmin = 0.0;                          // projected gradient direction is zero
+        while (nb < order.size()) {
+            const int64_t b = order[nb];
+            const double tb = t[(size_t)b], dt = tb - told;
+            if (dtmin < dt) break;
+            const double gb = g[(size_t)b];
+            xcp[(size_t)b] = d[(size_t)b] > 0 ? ub[b] : lb[b];
+            const double zb = xcp[(size_t)b] - x[b];
+            fp += dt * fpp + gb * gb + theta * gb * zb;
+            fpp -= theta * gb * gb;
+            if (col > 0) {
+                for (int j = 0; j < k; ++j) c[(size_t)j] += dt * p[(size_t)j];
+                wrow(b, w.data());
+                Mv(c.data(), tmp.data());
+                double wMc = 0, wMp = 0, wMw = 0;
+                for (int j = 0; j < k; ++j) wMc += w[(size_t)j] * tmp[(size_t)j];
+                Mv(p.data(), tmp.data());
+                for (int j = 0; j < k; ++j) wMp += w[(size_t)j] * tmp[(size_t)j];
+                Mv(w.data(), tmp.data());
+                for (int j = 0; j < k; ++j) wMw += w[(size_t)j] * tmp[(size_t)j];
+                fp -= gb * wMc;
+                fpp -= 2.0 * gb * wMp + gb * gb * wMw;
+                for (int j = 0; j < k; ++j) p[(size_t)j] += gb * w[(size_t)j];
+            }
+            fpp = std::max(fpp, std::numeric_limits<double>::epsilon() * std::fabs(fpp) + 1e-300);
+            d[(size_t)b] = 0.0;
+            dtmin = -fp / fpp;
+            told = tb;
+            ++nb;
+            if (nb == order.size() && !(std::any_of(d.begin(), d.end(), [](double q) { return q != 0.0; }))) hit_all = true;
+        }
+        if (!hit_all) {
+            dtmin = std::max(dtmin, 0.0);
+            if (!(dtmin < inf)) dtmin = 0.0;
+            told += dtmin;
+            for (int64_t i = 0; i < n; ++i) if (d[(size_t)i] != 0.0) xcp[(size_t)i] = x[i] + told * d[(size_t)i];
+            for (int j = 0; j < k; ++j) c[(size_t)j] += dtmin * p[(size_t)j];
+        }
+        // ---- subspace minimisation over the variables free at the Cauchy point (direct primal method) ----
+        xbar = xcp;
+        freeset.clear();
+        for (int64_t i = 0; i < n; ++i) if (xcp[(size_t)i] > lb[i] && xcp[(size_t)i] < ub[i]) freeset.push_back(i);
+        if (col > 0 && !freeset.empty()) {
+            // reduced gradient of the quadratic model at xcp: r = g + theta (xcp - x) - W M c   (free components)
+            Mv(c.data(), tmp.data());
+            std::vector<double> rc(freeset.size());
+            for (size_t q = 0; q < freeset.size(); ++q) {
+                const int64_t i = freeset[q];
+                wrow(i, w.data());
+                double wm = 0;
+                for (int j = 0; j < k; ++j) wm += w[(size_t)j] * tmp[(size_t)j];
+                rc[q] = g[(size_t)i] + theta * (xcp[(size_t)i] - x[i]) - wm;
+            }
+            // v = M W_F' r ;  N = I - M (W_F' W_F) / theta ;  v = N^-1 v ;  du = -r/theta - W_F v / theta^2
+            v.assign((size_t)k, 0.0);
+            std::vector<double> WtW((size_t)k * k, 0.0);
+            for (size_t q = 0; q < freeset.size(); ++q) {
+                wrow(freeset[q], w.data());
+                for (int a = 0; a < k; ++a) {
+                    v[(size_t)a] += w[(size_t)a] * rc[q];
+                    for (int b2 = 0; b2 < k; ++b2) WtW[(size_t)(a + b2 * k)] += w[(size_t)a] * w[(size_t)b2];
+                }
+            }
+            Mv(v.data(), tmp.data());
+            std::vector<double> N((size_t)k * k, 0.0), rhs(tmp.begin(), tmp.begin() + k);
+            for (int a = 0; a < k; ++a)
+                for (int b2 = 0; b2 < k; ++b2) {
+                    double sacc = 0;
+                    for (int e = 0; e < k; ++e) sacc += M[(size_t)(a + e * k)] * WtW[(size_t)(e + b2 * k)];
+                    N[(size_t)(a + b2 * k)] = (a == b2 ? 1.0 : 0.0) - sacc / theta;
+                }
+            if (solve_small(N, k, rhs, 1)) {
+                std::vector<double> du(freeset.size());
+                for (size_t q = 0; q < freeset.size(); ++q) {
+                    wrow(freeset[q], w.data());
+                    double wv = 0;
+                    for (int j = 0; j < k; ++j) wv += w[(size_t)j] * rhs[(size_t)j];
+                    du[q] = -rc[q] / theta - wv / (theta * theta);
+                }
+                // Morales & Nocedal: project xcp + du onto the box; keep it if the step from x is a descent direction,
+                // otherwise fall back to the largest feasible fraction of du
+                double dd = 0;
+                for (size_t q = 0; q < freeset.size(); ++q) {
+                    const int64_t i = freeset[q];
+                    xbar[(size_t)i] = std::min(std::max(xcp[(size_t)i] + du[q], lb[i]), ub[i]);
+                }
+                for (int64_t i = 0; i < n; ++i) dd += (xbar[(size_t)i] - x[i]) * g[(size_t)i];
+                if (!(dd < 0)) {
+                    double alpha = 1.0;
+                    for (size_t q = 0; q < freeset.size(); ++q) {
+                        const int64_t i = freeset[q];
+                        if (du[q] > 0 && ub[i] < inf) alpha = std::min(alpha, (ub[i] - xcp[(size_t)i]) / du[q]);
+                        if (du[q] < 0 && lb[i] > -inf) alpha = std::min(alpha, (lb[i] - xcp[(size_t)i]) / du[q]);
+                    }
+                    for (size_t q = 0; q < freeset.size(); ++q) xbar[(size_t)freeset[q]] = xcp[(size_t)freeset[q]] + alpha * du[q];
+                }
+            }
+        }
+        // ---- line search along d = xbar - x, limited to the feasible segment ----
+        for (int64_t i = 0; i < n; ++i) d[(size_t)i] = xbar[(size_t)i] - x[i];
+        const double dphi0 = dot(g.data(), d.data(), n), dnorm = std::sqrt(dot(d.data(), d.data(), n));
+        bool ls_failed = !(dphi0 < 0) || dnorm == 0.0;
+        double fnew = f, alpha = 0;
+        if (!ls_failed) {
+            double stpmx = 1e10;
+            bool constrained = false;
+            for (int64_t i = 0; i < n; ++i) {
+                if (lb[i] > -inf || ub[i] < inf) constrained = true;
+                const double di = d[(size_t)i];
+                if (di > 0 && ub[i] < inf) stpmx = std::min(stpmx, (ub[i] - x[i]) / di);
+                if (di < 0 && lb[i] > -inf) stpmx = std::min(stpmx, (lb[i] - x[i]) / di);
+            }
+            if (r.iterations == 0 && !constrained) stpmx = 1e10;
+            if (constrained && r.iterations > 0) stpmx = std::max(stpmx, 1.0);   // xbar is feasible, so the unit step always is
+            const double stp0 = (r.iterations == 0 && col == 0) ? std::min(1.0 / dnorm, stpmx) : 1.0;
+            st = wolfe_search(fn, n, x, d.data(), f, dphi0, stp0, ls, xn.data(), gn.data(), &fnew, &alpha, &r.f_calls, stpmx);
+            if (st > 0) return st;
+            ls_failed = st == -1;
+        }
+        if (ls_failed) {
+            if (col == 0 || restarted) {                      // steepest descent from a clean memory failed too: give up
+                if (col == 0) { r.status = 3; break; }
+            }
+            S.clear(); Y.clear(); col = 0; theta = 1.0; restarted = true;   // refresh the memory and restart (as lnsrlb's info != 0 path)
+            continue;
+        }
+        restarted = false;
+        // ---- accept, update the correction pairs ----
+        std::vector<double> s_((size_t)n), y_((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const double xi = std::min(std::max(xn[(size_t)i], lb[i]), ub[i]);   // guard against rounding outside the box
+            s_[(size_t)i] = xi - x[i]; y_[(size_t)i] = gn[(size_t)i] - g[(size_t)i]; x[i] = xi;
+        }
+        g.swap(gn);
+        const double fold = f;
+        f = fnew;
+        ++r.iterations;
+        r.f = f; r.pg_norm = proj_grad_norm(x, g.data());
+        if (r.pg_norm <= o.pgtol) { r.status = 0; break; }
+        if ((fold - f) <= o.factr * std::numeric_limits<double>::epsilon() * std::max(std::max(std::fabs(fold), std::fabs(f)), 1.0)) { r.status = 1; break; }
+        const double sy = dot(s_.data(), y_.data(), n), yy = dot(y_.data(), y_.data(), n);
+        if (sy > std::numeric_limits<double>::epsilon() * (-dphi0 * alpha) && yy > 0) {
+            if (col == mmax) { S.erase(S.begin()); Y.erase(Y.begin()); --col; }
+            S.push_back(std::move(s_)); Y.push_back(std::move(y_)); ++col;
+            theta = yy / sy;
+            if (!rebuild_M()) { S.clear(); Y.clear(); col = 0; theta = 1.0; }   // singular middle matrix: refresh the memory
+        }
     }
     *rep = r;
     return 0;

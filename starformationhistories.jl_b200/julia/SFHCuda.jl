@@ -285,4 +285,14 @@ function sample_sfh_nuts(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}
     return samples, lps, steps
 end
 
+# fit_templates_lbfgsb's LBFGSB.lbfgsb call (solvers.jl:82-90) as one ccall: x0 is the renormalised start (:86); returns (-logL, coeffs).
+struct LbfgsbOpts; struct_size::Int32; m::Int32; factr::Float64; pgtol::Float64; maxiter::Int64; maxfun::Int64; end
+mutable struct LbfgsbReport; f::Float64; pg_norm::Float64; iterations::Int64; f_calls::Int64; status::Int32; reserved::Int32; LbfgsbReport() = new(); end
+function fit_templates_lbfgsb_native(models::DeviceStack, x0::Vector{Float64}; m::Integer=10, factr::Real=1e-12, pgtol::Real=1e-5)
+    x = copy(x0); rep = LbfgsbReport()
+    check(ccall((:sfh_fit_templates_lbfgsb, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{LbfgsbOpts}, Ref{LbfgsbReport}),
+                models.ctx[], x, LbfgsbOpts(sizeof(LbfgsbOpts), m, factr, pgtol, 0, 0), rep))
+    return rep.f, x
+end
+
 end # module

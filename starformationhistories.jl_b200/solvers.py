@@ -51,12 +51,55 @@ def _check_sizes(x0, ds):
 
 
 # ---------------------------------------------------------------------------------------------
-def fit_templates_lbfgsb(models, data, x0=None, factr=1e-12, pgtol=1e-5, iprint=0, **kws):
-    """Returns (-logL, coeffs): box-constrained (coeffs >= 0) L-BFGS-B on fg!  (solvers.jl:82-90)."""
+def _lbfgsb_opts(m, factr, pgtol, maxiter, maxfun):
+    o = L.sfh_lbfgsb_opts()
+    o.struct_size = C.sizeof(L.sfh_lbfgsb_opts)
+    o.m, o.factr, o.pgtol, o.maxiter, o.maxfun = int(m), float(factr), float(pgtol), int(maxiter), int(maxfun)
+    return o
+
+
+def native_lbfgsb(fun, x0, lb=None, ub=None, m=10, factr=1e-12, pgtol=1e-5, maxiter=100000, maxfun=100000):
+    """The library's L-BFGS-B loop (sfh_minimize_lbfgsb) on a Python objective ``fun(x) -> (f, grad)``; `factr` is in units of
+    machine epsilon like LBFGSB.jl's.  Returns (x, f, info) with info = {"nit", "funcalls", "pg_norm", "status"}."""
+    x = np.array(x0, dtype=np.float64)
+    n = x.shape[0]
+    err = []
+
+    def cb(_user, xp, nn, fp, gp):
+        try:
+            f, g = fun(np.ctypeslib.as_array(xp, shape=(nn,)).copy())
+            fp[0] = float(f)
+            np.ctypeslib.as_array(gp, shape=(nn,))[:] = g
+            return 0
+        except Exception as e:
+            err.append(e)
+            return L.SFH_ERR_INVALID_ARG
+    dp = C.POINTER(C.c_double)
+    lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lb, dtype=np.float64), (n,))) if lb is not None else None
+    hi = np.ascontiguousarray(np.broadcast_to(np.asarray(ub, dtype=np.float64), (n,))) if ub is not None else None
+    rep, o = L.sfh_lbfgsb_report(), _lbfgsb_opts(m, factr, pgtol, maxiter, maxfun)
+    st = L.lib.sfh_minimize_lbfgsb(L.sfh_objective_fn(cb), None, n, x.ctypes.data_as(dp), lo.ctypes.data_as(dp) if lo is not None else None,
+                                   hi.ctypes.data_as(dp) if hi is not None else None, C.byref(o), C.byref(rep))
+    if err:
+        raise err[0]
+    L.check(st)
+    return x, rep.f, {"nit": int(rep.iterations), "funcalls": int(rep.f_calls), "pg_norm": rep.pg_norm, "status": int(rep.status)}
+
+
+def fit_templates_lbfgsb(models, data, x0=None, factr=1e-12, pgtol=1e-5, iprint=0, engine="scipy", **kws):
+    """Returns (-logL, coeffs): box-constrained (coeffs >= 0) L-BFGS-B on fg!  (solvers.jl:82-90).
+    engine="native": the whole optimisation is one call into the library (sfh_fit_templates_lbfgsb)."""
+    _check_engine(engine)
     ds = device_stack(models, data)
     x0 = np.ones(ds.shape[1]) if x0 is None else np.asarray(x0, dtype=np.float64)
     _check_sizes(x0, ds)
     x0 = renormalize_x0(data, ds, x0)                                      # :86
+    if engine == "native":
+        x = np.array(x0, dtype=np.float64)
+        rep = L.sfh_lbfgsb_report()
+        o = _lbfgsb_opts(kws.get("m", 10), factr, pgtol, kws.get("maxiter", 100000), kws.get("maxfun", 100000))
+        L.check(L.lib.sfh_fit_templates_lbfgsb(ds.ctx().handle, x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(o), C.byref(rep)))
+        return rep.f, x
     G = np.empty(ds.shape[1])
 
     def fg(x):                                                             # :88

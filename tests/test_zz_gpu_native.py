@@ -51,6 +51,27 @@ def test_fit_templates_native_agrees_with_host_loop_on_poisson_data(S):   # basi
     assert isapprox(S.fit_templates_fast(M, data, x0=x0, engine="native")[0], rs["mle"].mu, 1e-4)
 
 
+def test_fit_templates_lbfgsb_native(S):                          # basic_linear_combinations.jl:16-118
+    models = [np.array([[0, 0, 0], [0, 0, 0], [1, 1, 1]], dtype=np.float64)]
+    data = np.array([[0, 0, 0], [0, 0, 0], [3, 3, 3]], dtype=np.int64)
+    assert S.fit_templates_lbfgsb(models, data, x0=np.array([1.0]), engine="native")[1][0] == pytest.approx(3, rel=1e-7)
+    rng = np.random.Generator(np.random.Philox(58392))
+    N = 10
+    x, x0 = rng.random(N), rng.random(N)
+    models = [rng.random((100, 100)) for _ in range(N)]
+    sm = S.stack_models(models)
+    sd = sum(c * m for c, m in zip(x, models)).reshape(-1, order="F")
+    assert isapprox(S.fit_templates_lbfgsb(sm, sd, x0=x0, engine="native")[1], x, 1e-7)
+    x2 = x.copy(); x2[0] = 0; x2[-1] = 0                               # :66-89 coefficients on the bound
+    d2 = sum(c * m for c, m in zip(x2, models)).reshape(-1, order="F")
+    f2, r2 = S.fit_templates_lbfgsb(sm, d2, x0=x0, engine="native")
+    assert isapprox(r2, x2, 1e-7) and np.all(r2 >= 0)
+    M, xt, data = make_flat_problem(10000, 100)                        # BASELINE config 1
+    fn, xn = S.fit_templates_lbfgsb(M, data, x0=np.ones(100), engine="native")
+    fs, xs = S.fit_templates_lbfgsb(M, data, x0=np.ones(100), engine="scipy")
+    assert isapprox(xn, xs, 1e-5) and abs(fn - fs) <= 1e-10 * abs(fs) and isapprox(xn, xt, 5e-2)
+
+
 def test_fit_sfh_native(S):                                         # mzr_test.jl:178-216
     p = make_hier_problem(nj=21, nk=26, nb=10000)
     mz, dp = S.PowerLawMZR(1.0, -2.0, 6.0), S.GaussianDispersion(0.2)
