@@ -77,6 +77,22 @@ def test_posterior_moments():
     assert stats.n_evals / stats.n_batches > 6                    # 8 chains share nearly every batched pass
 
 
+def test_many_ragged_chains_do_not_deadlock():
+    """64 chain threads with lengths 0..7 (some finish after their first evaluations, all at different times): every round still
+    serves exactly the chains that are alive, and the run terminates."""
+    prec, mean, cov = make_target(n=3, seed=8)
+    _, batch = gaussian(prec, mean)
+    sizes = []
+
+    def counting(Th):
+        sizes.append(Th.shape[1])
+        return batch(Th)
+    lens = [k % 8 for k in range(64)]
+    res, stats = native_nuts(counting, [mean + 0.01 * k for k in range(64)], lens, nwarmup=3, max_depth=4, seed=11)
+    assert [r[0].shape[0] for r in res] == lens and stats.n_batches == len(sizes) and stats.n_evals == sum(sizes)
+    assert sizes[0] == 64 and sizes[-1] < 64 and all(np.all(np.isfinite(r[0])) for r in res)
+
+
 def test_failure_modes():
     prec, mean, cov = make_target()
     _, batch = gaussian(prec, mean)

@@ -83,3 +83,48 @@ def test_guard_after_reduction():
     # two shards whose partial sums cancel exactly must trigger the guard only AFTER the sum
     nl, G = S.allreduce_fg(np.array([0.0, 1.0, 2.0]))
     assert nl == np.inf and np.array_equal(G, [1.0, 2.0])
+
+
+def _file_worker(rank, world, port, path, q):
+    """Each rank maps the ONE stack file and evaluates only the bin rows shard_rows assigns to it (the host side of
+    sfh_stack_create_from_file's per-shard loading; the oracle stands in for the device as the local evaluator)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle as O
+        import sfh_b200 as S
+        with S.SFHFile(path) as f:
+            nb = f.attrs[0]
+            b, e = S.shard_rows(nb, world, rank)
+            M = np.array(f["models"][b:e])                       # touches only these rows of the mapping
+            data = np.array(f["data"][b:e])
+            x = f.read("x_eval")
+            csum = S.io.checksum64(np.asfortranarray(M))
+        Cm = O.composite(x, M)
+        logl = float(np.sum(np.where(data > 0, data - Cm - data * np.log(np.where(data > 0, data, 1) / Cm), -Cm)))
+        _, G, _ = O.fg(x, M, data)
+        nl, Gall = S.allreduce_fg(np.concatenate([[logl], G]))
+        q.put((rank, nl, Gall, (b, e), csum))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_load_their_shards_from_one_file(tmp_path):
+    import oracle as O
+    import sfh_b200 as S
+    nb, nt = 1500, 9
+    M, x, data = make_flat_problem(nb, nt, seed=23)
+    path = str(tmp_path / "stack.sfh")
+    S.write_arrays(path, {"models": M, "data": data.astype(np.float64), "x_eval": x}, kind=S.io.KIND_STACK, attrs=[nb, 0, nb, 0, 0, 1])
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_file_worker, args=(r, world, port, path, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    nl_ref, G_ref, _ = O.fg(x, M, data)
+    for rank, nl, G, (b, e), csum in res:
+        assert nl == pytest.approx(float(nl_ref), rel=1e-13) and np.allclose(G, G_ref, rtol=1e-11, atol=1e-9)
+        assert csum == S.io.checksum64(np.asfortranarray(M[b:e]))   # the shard each rank read is the shard of the original
