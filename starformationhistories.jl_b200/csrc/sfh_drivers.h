@@ -187,13 +187,14 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
     r.f = f; r.g_norm = infnorm(g.data(), n);
     if (!std::isfinite(f) || !std::isfinite(r.g_norm)) { r.status = 3; *rep = r; return 0; }
     double f_prev = f + std::sqrt(dot(g.data(), g.data(), n)) / 2.0;
+    // Two passes over the n x n matrix per iteration instead of three: q = H g_new (one read) gives both H y = q + p_old
+    // (p_old = -H g_old) and, after the rank-two update (one read + write), the next direction algebraically:
+    //   -p_new = H_new g_new = q - rho (s (Hy.g) + Hy (s.g)) + (rho^2 y'Hy + rho) s (s.g)
+    for (int64_t j = 0; j < n; ++j) p[(size_t)j] = -g[(size_t)j];   // H = I
+    std::vector<double> &q = Hy;                                    // q is overwritten by Hy in place
     while (true) {
         if (r.g_norm <= o.g_abstol) { r.converged = 1; r.status = 0; break; }
         if (r.iterations >= o.maxiter) { r.status = 1; break; }
-        // p = -H g
-        for_columns(n, [&](int64_t j0, int64_t j1) {
-            for (int64_t j = j0; j < j1; ++j) p[(size_t)j] = -dot(invH + j * n, g.data(), n);   // H symmetric: column j = row j
-        });
         double dphi0 = dot(g.data(), p.data(), n);
         if (!(dphi0 < 0)) {   // not a descent direction (H lost positive definiteness to rounding): restart from the identity
             for (int64_t j = 0; j < n; ++j) { double *col = invH + j * n; std::fill(col, col + n, 0.0); col[j] = 1.0; p[(size_t)j] = -g[(size_t)j]; }
@@ -220,14 +221,19 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
         if (r.g_norm <= o.g_abstol) { r.converged = 1; r.status = 0; break; }
         if (!std::isfinite(f)) { r.status = 2; break; }
         // H <- (I - rho s y') H (I - rho y s') + rho s s'  =  H - rho (s Hy' + Hy s') + (rho^2 y'Hy + rho) s s'
-        const double ys = dot(y.data(), s.data(), n);
-        const double rho = ys != 0.0 ? 1.0 / ys : 1000.0;
-        if (!(ys > 0)) continue;   // curvature condition violated (cannot happen with a Wolfe step up to rounding): skip the update
         for_columns(n, [&](int64_t j0, int64_t j1) {
-            for (int64_t j = j0; j < j1; ++j) Hy[(size_t)j] = dot(invH + j * n, y.data(), n);
+            for (int64_t j = j0; j < j1; ++j) q[(size_t)j] = dot(invH + j * n, g.data(), n);   // H symmetric: column j = row j
         });
+        const double ys = dot(y.data(), s.data(), n);
+        if (!(ys > 0)) {      // curvature condition violated (cannot happen with a Wolfe step up to rounding): skip the update
+            for (int64_t j = 0; j < n; ++j) p[(size_t)j] = -q[(size_t)j];
+            continue;
+        }
+        const double rho = 1.0 / ys;
+        for (int64_t j = 0; j < n; ++j) { const double qj = q[(size_t)j]; Hy[(size_t)j] = qj + p[(size_t)j]; p[(size_t)j] = -qj; }   // p holds -q for now
         const double yHy = dot(y.data(), Hy.data(), n);
         const double cs = rho * rho * yHy + rho;
+        const double Hyg = dot(Hy.data(), g.data(), n), sg = dot(s.data(), g.data(), n);
         for_columns(n, [&](int64_t j0, int64_t j1) {
             for (int64_t j = j0; j < j1; ++j) {
                 double *col = invH + j * n;
@@ -235,6 +241,7 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
                 for (int64_t i = 0; i < n; ++i) col[i] += a * s[(size_t)i] + b * Hy[(size_t)i];
             }
         });
+        for (int64_t j = 0; j < n; ++j) p[(size_t)j] += rho * (s[(size_t)j] * Hyg + Hy[(size_t)j] * sg) - cs * s[(size_t)j] * sg;
     }
     *rep = r;
     return 0;
