@@ -34,6 +34,14 @@ for engine, (t, r) in res.items():
     out(what="fit_sfh MZR (MAP+MLE BFGS), config 3, g_abstol 1e-6", engine=engine, wall_s=t, fevals=nf, us_per_eval_end_to_end=1e6 * t / nf,
         iterations=[int(r["map"].result.nit), int(r["mle"].result.nit)], converged=[bool(r["map"].result.success), bool(r["mle"].result.success)],
         frac_params_within_3sigma=float(np.mean(z < 3)), alpha_beta_sigma=[float(v) for v in r["mle"].mu[-3:]])
+for ag in (2, 2):                                              # first-trial step from the previous decrease instead of InitialStatic
+    t0 = time.perf_counter()
+    r = S.fit_sfh(*start, ds3, d3, la, mh, x0=R * 1.5, g_abstol=1e-6, engine="native", alphaguess=ag)
+    t = time.perf_counter() - t0
+nf = int(r["map"].result.nfev) + int(r["mle"].result.nfev)
+out(what="fit_sfh MZR config 3, native loop with alphaguess = 2 (previous-decrease first step)", wall_s=t, fevals=nf, us_per_eval_end_to_end=1e6 * t / nf,
+    iterations=[int(r["map"].result.nit), int(r["mle"].result.nit)], converged=[bool(r["map"].result.success), bool(r["mle"].result.success)],
+    max_rel_diff_mle_mu_vs_default=float(np.max(np.abs(r["mle"].mu / res["native"][1]["mle"].mu - 1))))
 a, b = res["scipy"][1], res["native"][1]
 out(what="fit_sfh native vs scipy", max_rel_diff_map_mu=float(np.max(np.abs(a["map"].mu / b["map"].mu - 1))),
     max_rel_diff_mle_mu=float(np.max(np.abs(a["mle"].mu / b["mle"].mu - 1))),

@@ -335,7 +335,7 @@ class HierarchicalOptimizer:
         G[nbins:] = G2[nbins:][free]                                       # :181-189
         return (-nlogL, -G) if ret_F else -G                               # :193-197
 
-    def native_bfgs(self, xstart, g_abstol=1e-8, iterations=5000):
+    def native_bfgs(self, xstart, g_abstol=1e-8, iterations=5000, alphaguess=0):
         """Minimise -logdensity over the free transformed variables with the library's BFGS loop (sfh_fit_sfh_bfgs): the
         objective of fg_map! / fg_mle! (generic_fitting.jl:306-325) evaluated, transformed and iterated natively -- one C
         call per optimisation.  Returns an object with scipy's field names (x, hess_inv, fun, nit, nfev, success)."""
@@ -346,7 +346,7 @@ class HierarchicalOptimizer:
         if nbins != ctx.n_ages:
             raise ValueError("length(x0) != length(unique(logAge)) + number of free parameters")
         invH = np.empty((x.shape[0],) * 2, order="F")
-        rep, o, dp = L.sfh_bfgs_report(), _bfgs_opts(g_abstol, iterations), C.POINTER(C.c_double)
+        rep, o, dp = L.sfh_bfgs_report(), _bfgs_opts(g_abstol, iterations, alphaguess), C.POINTER(C.c_double)
         fx = self.MH_model0.fixed()
         tf32, free8 = np.ascontiguousarray(tf, dtype=np.int32), np.ascontiguousarray(free, dtype=np.uint8)
         L.check(L.lib.sfh_fit_sfh_bfgs(ctx.handle, self.MH_model0.kind, _dp(fx), self.disp_model0.kind, _dp(np.ascontiguousarray(init)),

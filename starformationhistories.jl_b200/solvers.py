@@ -528,7 +528,8 @@ def cum_sfr_quantiles(result, logAge, MH, T_max, Nsamples, q, rng=None, **kws):
     return {"cum_sfh": cum_q, "sfrs": sfr_q, "mean_mh": mh_q, "samples": samples, "n_good": len(rows)}
 
 
-def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy"):
+def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy",
+            alphaguess=0):
     """BFGS on [log R_j, transformed free parameters]: MAP (Jacobian corrections on) then MLE seeded from it
     (generic_fitting.jl:242-409).  Returns {"map": BFGSResult, "mle": BFGSResult}; mu holds
     [R_1..R_Nj, alpha, beta, sigma] with fixed parameters at their initial values."""
@@ -560,7 +561,7 @@ def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None
             return -lp, -g
 
         if engine == "native":                                             # the loop runs inside the library (sfh_fit_sfh_bfgs)
-            r = opt.native_bfgs(start, g_abstol, iterations)
+            r = opt.native_bfgs(start, g_abstol, iterations, alphaguess)   # alphaguess: sfh_bfgs_opts (0/1 = the reference's InitialStatic)
         else:
             r = _bfgs(fun, start, g_abstol, iterations)
         start = r.x                                                        # MLE starts from the MAP minimiser
