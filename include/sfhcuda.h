@@ -72,7 +72,8 @@ typedef struct sfh_opts {
     int32_t cluster;     /* 0 = auto; else thread-block-cluster size (1,2,4,8,16)                   */
     int32_t force_unfused; /* 1 = always use the two-pass kernels (debug / A-B measurements)        */
     int32_t consumer_warps; /* 0 = auto; 8, 12 or 16 consumer warps per CTA                          */
-    int32_t variant;     /* 0 = auto; 1 = shared-memory-resident tile; 2 = register-resident tile    */
+    int32_t variant;     /* 0 = auto; 1 = shared-memory-resident tile; 2 = register-resident tile;   */
+                         /* 3 = shared-memory tile with two tiles in flight (experimental, opt-in)   */
     int32_t reserved;
 } sfh_opts;
 
@@ -83,7 +84,7 @@ typedef struct sfh_info {
     int32_t tile_bins, cluster, chunks_per_tile, ring_slots, n_clusters, consumer_warps;
     int32_t sm_count, cc_major, cc_minor, register_tile;
     int32_t panel_layout; /* 1: device copy stored as bin-major panels of tile_bins bins (host layout unchanged) */
-    int32_t reserved;
+    int32_t pipelined;    /* 1: gradient evaluations use the two-tiles-in-flight kernel (variant 3)               */
     int64_t stack_bytes; /* device bytes held by the stack (padded)                    */
     double clamp_eps;
 } sfh_info;

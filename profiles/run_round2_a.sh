@@ -6,3 +6,11 @@ python -m pytest tests/test_zz_gpu_nuts.py tests/test_zz_gpu_native.py tests/tes
 timeout 200 python profiles/bench_nuts.py 2>&1 | tee gpurun_out/r2a_nuts.txt
 timeout 100 python profiles/bench_native.py 2>&1 | tee gpurun_out/r2a_native.txt
 python bench.py --steps 2000 --warmup 10 2> gpurun_out/r2a_bench.err | tee gpurun_out/r2a_bench.json
+# the two-tiles-in-flight fused kernel (variant 3): parity first, then timing against the default on config 3 and on a config-5 shard
+python -m pytest tests/experimental_gpu_pipe.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r2a_pipe_tests.log
+for cfg in "0 0 0 0" "0 0 0 3" "8 8 4 3" "8 16 4 3" "8 16 8 3" "16 8 4 3" "16 16 8 3"; do
+  python profiles/one_config.py $cfg 20 2>&1 | tail -1
+done | tee gpurun_out/r2a_pipe_config3.txt
+for cfg in "0 0 0 0" "0 0 0 3" "8 8 8 3" "8 16 8 3" "16 8 8 3" "16 16 8 3" "16 16 16 3"; do
+  python profiles/one_config.py $cfg 10 125000 10000 float32 2>&1 | tail -1
+done | tee gpurun_out/r2a_pipe_config5_shard.txt

@@ -22,6 +22,7 @@
 
 #include "sfh_batched.cuh"
 #include "sfh_fused.cuh"
+#include "sfh_fused_pipe.cuh"
 #include "sfh_small.cuh"
 #include "sfh_ensemble.cuh"
 #include "sfh_templates.cuh"
@@ -154,6 +155,7 @@ struct sfh_stack {
     bool fused = false;
     int bt = 0, cluster = 1, kt = 0, ring = 0, n_clusters = 0, n_tiles = 0, nw = 16;
     bool rt = false;  // register-resident tile variant
+    bool pipe = false;  // two tiles in flight (sfh_fused_pipe.cuh; opt-in, sfh_opts.variant = 3)
     uint32_t smem = 0;
     bool evict_first = false;
     bool panel = false;   // device layout: bin-major panels of `bt` bins (see StackLayout); SFH_PANEL=0 forces column-major
@@ -271,6 +273,50 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
     return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G, RT>, s->tmap_full, s->tmap_tail, p);
 }
 
+// ---- the pipelined variant (sfh_fused_pipe.cuh): gradient evaluations only, shared-memory tile, NW = 8 or 16 ----
+template <typename S, int BT, int NW>
+cudaError_t pipe_op(const sfh_stack *s, int op, const FusedParams *p, cudaStream_t st, int *maxcl) {
+    auto k = sfh_fg_fused_pipe_kernel<S, BT, NW>;
+    if (op == 0) {   // attributes
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+        if (e == cudaSuccess && s->cluster > 8) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        return e;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(op == 1 ? s->cluster * 1024u : (unsigned)(s->n_clusters * s->cluster));
+    cfg.blockDim = dim3((NW + kProducerWarps) * 32);
+    cfg.dynamicSmemBytes = s->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    if (op == 1) { cfg.numAttrs = 1; return cudaOccupancyMaxActiveClusters(maxcl, k, &cfg); }   // occupancy
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, k, s->tmap_full, s->tmap_tail, *p);                        // launch
+}
+cudaError_t pipe_dispatch(const sfh_stack *s, int op, const FusedParams *p, cudaStream_t st, int *maxcl) {
+#define SFH_PIPE_NW(S, BT) (s->nw == 8 ? pipe_op<S, BT, 8>(s, op, p, st, maxcl) : pipe_op<S, BT, 16>(s, op, p, st, maxcl))
+    if (s->dtype == SFH_F64) {
+        switch (s->bt) {
+        case 64: return SFH_PIPE_NW(double, 64);
+        case 32: return SFH_PIPE_NW(double, 32);
+        case 16: return SFH_PIPE_NW(double, 16);
+        default: return SFH_PIPE_NW(double, 8);
+        }
+    }
+    switch (s->bt) {
+    case 128: return SFH_PIPE_NW(float, 128);
+    case 64: return SFH_PIPE_NW(float, 64);
+    case 32: return SFH_PIPE_NW(float, 32);
+    case 16: return SFH_PIPE_NW(float, 16);
+    default: return SFH_PIPE_NW(float, 8);
+    }
+#undef SFH_PIPE_NW
+}
+
 // kernel variants: (NW=16, smem tile) (NW=8, smem tile, 2 CTAs/SM) (NW=8, register tile) (NW=12, register tile)
 #define SFH_DISPATCH_G(S, BT, NW, RT, want_g, CALL) ((want_g) ? CALL(S, BT, NW, true, RT) : CALL(S, BT, NW, false, RT))
 #define SFH_DISPATCH_NW(S, BT, s, want_g, CALL)                                                    \
@@ -311,6 +357,7 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
     const Variant variants[4] = {{12, true, 1}, {8, true, 1}, {8, false, 2}, {16, false, 1}};
     const int cl_opts[5] = {1, 2, 4, 8, 16};
     const bool forced = o && (o->tile_bins || o->cluster || o->consumer_warps || o->variant);
+    const int pipe = (o && o->variant == 3) ? 1 : 0;
     double best_score = -1.0;
     int best_bt = 0, best_c = 0, best_kt = 0, best_nw = 0, best_ring = 0;
     bool best_rt = false;
@@ -319,6 +366,7 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
         if (o && o->consumer_warps && o->consumer_warps != nw) continue;
         if (o && o->variant == 1 && v.rt) continue;   // 1 = shared-memory tile only
         if (o && o->variant == 2 && !v.rt) continue;  // 2 = register tile only
+        if (o && o->variant == 3 && v.rt) continue;   // 3 = shared-memory tile, two tiles in flight (sfh_fused_pipe.cuh)
         for (int ci = 0; ci < 5; ++ci) {
             const int bt = cands[ci];
             if (ci == 4 && s->dtype == SFH_F64) continue;  // (f64 has four tile widths)
@@ -332,12 +380,12 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
                 const int kt = (int)kt64;
                 const uint32_t budget = (v.ctas_per_sm == 2) ? (kMaxDynSmem / 2 - 1024) : kMaxDynSmem;
                 const int G = stage_chunks_for(v.rt);
-                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw, G);
+                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw, G, pipe);
                 if (fixed.total + 64 >= budget) continue;
                 int ring = (int)((budget - fixed.total - 64) / (chunk_bytes(nw) + 16));
                 ring = std::min(ring, 64) / G * G;   // whole pipeline stages
                 const int nst = (kt + G - 1) / G;
-                if (ring / G < (v.rt ? 2 : nst + 1)) continue;
+                if (ring / G < (v.rt ? 2 : (pipe ? 2 * nst + 1 : nst + 1))) continue;   // pipe: the previous tile stays resident
                 // --- score (model fitted to profiles/r1_sweep_*.txt) ---
                 // co-schedulable clusters on a 148-SM B200: size 8 -> 15, size 4 -> 33 (1 CTA/SM) or 71 (2 CTAs/SM)
                 const int slots = s->sm_count * v.ctas_per_sm;
@@ -351,7 +399,7 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
                 const double balance = waves >= 1.0 ? waves / std::ceil(waves) : waves;  // tail effect
                 const double tile_us = (double)kt * chunk_bytes(nw) * v.ctas_per_sm / 44e3;  // ~44 GB/s per SM
                 // measured: the register-tile variants are consumer-latency bound (2-3 warps per scheduler), not HBM bound
-                const double exposed = v.rt ? 2.5 : (v.ctas_per_sm == 2 ? 0.35 : 1.0);       // of the ~1 us exchange
+                const double exposed = pipe ? 0.15 : (v.rt ? 2.5 : (v.ctas_per_sm == 2 ? 0.35 : 1.0));   // of the ~1 us exchange
                 const double eff = tile_us / (tile_us + exposed);
                 const size_t rowb = bt * elem_size(s->dtype);  // contiguous bytes per template row of a TMA box
                 // column-major rows shorter than 256 B cost DRAM efficiency (r1_sweep_config3_*.txt); the panel layout
@@ -368,8 +416,9 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
     }
     if (!best_bt) return false;
     s->bt = best_bt; s->cluster = best_c; s->kt = best_kt; s->nw = best_nw; s->ring = best_ring; s->rt = best_rt;
+    s->pipe = pipe != 0;
     const TileGeom g = geom(s->dtype, s->bt, s->nw);
-    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw, stage_chunks_for(s->rt)).total;
+    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw, stage_chunks_for(s->rt), pipe).total;
     s->n_tiles = (int)((s->rows + s->bt - 1) / s->bt);
     return true;
 }
@@ -418,6 +467,12 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
 #define MAX_CL(S, BT, NW, G, RT) max_clusters<S, BT, NW, G, RT>(s, &maxcl)
     CU_TRY(SFH_DISPATCH(s, true, MAX_CL));
 #undef MAX_CL
+    if (s->pipe) {   // the gradient evaluations use the pipelined kernel: same block and smem, possibly other registers
+        int maxcl_p = 0;
+        CU_TRY(pipe_dispatch(s, 0, nullptr, nullptr, nullptr));
+        CU_TRY(pipe_dispatch(s, 1, nullptr, nullptr, &maxcl_p));
+        maxcl = std::min(maxcl, maxcl_p);
+    }
     if (maxcl <= 0) return SFH_OK;  // cannot co-schedule this cluster shape: stay unfused
     s->n_clusters = std::min(maxcl, s->n_tiles);
     // the stack is streamed exactly once per evaluation: do not let it evict the O(Nb) vectors
@@ -623,7 +678,7 @@ static int sfh_stack_info_impl(const sfh_stack *s, sfh_info *info) {
     info->ld = s->lay.ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
     info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
     info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->register_tile = s->rt ? 1 : 0; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
-    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->clamp_eps = s->eps;
+    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->pipelined = s->pipe ? 1 : 0; info->clamp_eps = s->eps;
     return SFH_OK;
 }
 extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
@@ -786,7 +841,8 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         p.gstride = c->gstride;
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
 #define LAUNCH(S, BT, NW, G, RT) launch_fused_t<S, BT, NW, G, RT>(s, p, c->stream)
-        CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
+        if (s->pipe && want_G) CU_TRY(pipe_dispatch(s, 2, &p, c->stream, nullptr));
+        else CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
 #undef LAUNCH
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
         c->stats.kernel_launches++;

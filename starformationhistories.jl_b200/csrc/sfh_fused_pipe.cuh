@@ -1,132 +1,25 @@
-// sfh_fused.cuh -- K4: the fused composite -> residual -> transposed-gradient kernel (sm_100a).
+// sfh_fused_pipe.cuh -- K4 with TWO tiles in flight (opt-in: sfh_opts.variant = 3; built in round 1 after the GPU budget was
+// spent, so it is NOT the default and has not been measured yet).
 //
-// Replaces, in ONE pass over the template stack, the reference's
-//     composite!            src/fitting/fitting_base.jl:55-65   (gemv 'N', reads M)
-//     grad-loglikelihood!   src/fitting/fitting_base.jl:265-285 (residual + gemv 'T', reads M again)
-// as sequenced by fg! (src/fitting/solvers.jl:20-38).  The O(Nb) Poisson term of
-// loglikelihood (fitting_base.jl:84-96) is evaluated by the finalize kernel from the composite
-// vector this kernel writes (sfh_small.cuh).
-//
-// Decomposition
-//   stack M: column-major Nb x T, leading dimension ld (stack_models layout, padded).
-//   tile      = BT consecutive bins x ALL T templates; owned by one thread-block CLUSTER.
-//   CTA q of the cluster holds templates [q*KT*RPC, (q+1)*KT*RPC) of the tile in shared memory,
-//   brought in by TMA as KT chunks (boxes of BT bins x RPC templates = 8 KB each) through an
-//   mbarrier ring of R slots that is deeper than one tile, so the next tile streams in while this
-//   one is being used.
-//   pass A   every consumer lane owns 16 B of each chunk (VEC bins of one template) and FMAs it
-//            into its composite partials;  warp shuffles + one smem stage give the CTA partial;
-//            the C CTA partials are exchanged through DSMEM with st.async (data + mbarrier
-//            complete_tx in one op) and summed in fixed rank order -> every CTA holds bit-identical m.
-//   residual r = 1 - n/max(m,eps)  (fitting_base.jl:277-279)
-//   pass B   the same lanes re-read the same 16 B from SHARED memory (not HBM, not L2) and
-//            accumulate M*r into per-lane gradient partials that live in registers across ALL tiles
-//            of the CTA; slots are released to the TMA producer as pass B walks them.
-//   end      lanes sharing a template combine by shuffle; one plain store per (cluster, template)
-//            into gpart[n_clusters][T].  No atomics anywhere => bitwise run-to-run determinism.
+// sfh_fused.cuh runs pass A -> exchange -> pass B per tile; the cluster exchange costs ~0.8-1.1 us of a ~4.4 us tile during
+// which the consumer warps idle (profiles/r1_experiments.md; DESIGN.md section 7 item 1: wide-T F32 stacks sit at ~80 % of
+// the HBM roofline because of it).  Here the tile's partial composite is POSTED (st.async to every CTA of the cluster), then
+// pass B of the PREVIOUS tile runs from the ring while those partials are in flight, and only then the exchange is waited
+// for.  The previous tile's stages therefore stay resident one tile longer: the ring must hold two tiles (ring / G >=
+// 2 nst + 1, enforced by choose_config) and the residual buffer is double-buffered by tile parity.  Everything else --
+// producers, TMA boxes, fixed-order sums, one store per (cluster, template), bitwise determinism -- is sfh_fused.cuh's;
+// the two files are to be merged into one template once this variant has been measured.
 #pragma once
-#include "sfh_ptx.cuh"
+#include "sfh_fused.cuh"
 
 namespace sfh {
 
-// NW consumer warps (+1 TMA producer warp) per CTA.  NW = 16: one CTA per SM; NW = 8: two CTAs per SM, so one
-// CTA's exchange/residual latency is hidden behind the other CTA's streaming passes.
-constexpr int kKMax = 20;       // max chunks per CTA per tile (per-lane register array gacc[])
-// per-variant limit: the 12-warp register-tile variant has 128 registers/thread => 12 chunks (4+2 regs each)
-__host__ __device__ constexpr int kmax_for(int nw, bool rt) { return (rt && nw == 12) ? 12 : kKMax; }
-// chunks per pipeline STAGE: one mbarrier wait / release per stage instead of per chunk (an already-complete
-// mbarrier.try_wait still costs ~90 cycles; with few warps per SM that latency, paid per chunk, made the
-// consumers -- not HBM -- the bottleneck).  kKMax and every kmax_for() are multiples of it.
-#ifndef SFH_PRODUCERS
-#define SFH_PRODUCERS 2
-#endif
-#ifndef SFH_STAGE_SMEM
-#define SFH_STAGE_SMEM 2
-#endif
-__host__ __device__ constexpr int stage_chunks_for(bool rt) { return rt ? 4 : SFH_STAGE_SMEM; }
-// (one op per 2-chunk stage + 2 producers: 194 us; 1-chunk stages + 1 producer: 206 us; see r1_experiments.md)
-constexpr int kMaxCluster = 16;
-__host__ __device__ constexpr int chunk_bytes(int nw) { return nw * 32 * 16; }  // one 16-byte vector per consumer lane
-// TMA producer warps per CTA.  A single elected thread needs ~250 cycles per chunk (mbarrier try_wait on the empty
-// slot ~100, expect_tx, bulk-tensor issue): at 4 KB chunks that caps a CTA at ~31 GB/s (profiles/probes/bw_probe.cu
-// reproduces it: 4 KB x 26-slot ring, 1 producer thread, 1 CTA/SM -> 4.5 TB/s; 16 KB chunks -> 7.0 TB/s).
-// Two producers interleave the chunk sequence; 10 (or 18) warps still fit the 96-register budget of 5 warps/scheduler.
-constexpr int kProducerWarps = SFH_PRODUCERS;  // see profiles/r1_experiments.md for the producers x stage-size matrix
-
-// a pipeline stage (G chunks = G*RPC templates of the tile) is ONE bulk-tensor op
-constexpr int kMaxStage = 4;
-
-struct FusedParams {
-    int64_t nb;          // bins in this shard
-    int64_t nt;          // templates
-    int32_t kt;          // chunks per CTA per tile (<= kKMax)
-    int32_t ring;        // ring chunk-slots: a multiple of the stage size
-    int32_t n_tiles;     // ceil(nb / BT)
-    int32_t evict_first; // use an L2 evict_first policy on the stack loads
-    int32_t l2_prefetch; // tiles of look-ahead for cp.async.bulk.prefetch.tensor (0 = off)
-    int32_t panel;       // 1: the stack is stored as bin-major panels [tile][T][BT] and the tensor map is 3-D
-    double eps;          // clamp (fitting_base.jl:90,277)
-    const double *coeffs;   // [nt]
-    const double *data;     // [nb] (converted to double at upload)
-    double *composite;      // [nb] out: M*coeffs (unclamped)
-    double *residual;       // [nb] out (nullable): 1 - n/max(m,eps)
-    double *gpart;          // [n_clusters][gstride] out
-    int64_t gstride;
-};
-
 template <typename S, int BT, int NW>
-struct FusedCfg {
-    static constexpr int VEC = 16 / sizeof(S);  // elements per 16-byte lane vector
-    static constexpr int LPR = BT / VEC;        // lanes per template row
-    static constexpr int RPW = 32 / LPR;        // template rows per warp per chunk
-    static constexpr int RPC = RPW * NW;        // template rows per chunk
-    static_assert(BT % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "bad tile");
-    static_assert(RPC * BT * sizeof(S) == chunk_bytes(NW), "chunk = one 16-byte vector per consumer lane");
-    static_assert(RPC <= 256, "TMA box dimension limit");
-};
-
-// dynamic shared memory carve-up (bytes), shared by host and device
-struct FusedSmem {
-    uint32_t ring_off, red_off, xbuf_off, rbuf_off, cs_off, bar_off, total;
-    // cs_elems = kt * RPC: this CTA's slice of the coefficient vector (kept in smem, not registers:
-    // 17 warps put 5 warps on one SM sub-partition => 96 registers/thread, too few for c[] + gacc[])
-    // pipe = 1: the residual buffer is double-buffered (sfh_fused_pipe.cuh keeps two tiles in flight)
-    __host__ __device__ static FusedSmem make(int ring, int bt, int cluster, int cs_elems, int nw, int g, int pipe = 0) {
-        FusedSmem s;
-        s.ring_off = 0;
-        s.red_off = ring * chunk_bytes(nw);
-        s.xbuf_off = s.red_off + nw * bt * 8;
-        s.rbuf_off = s.xbuf_off + 2 * cluster * bt * 8;
-        s.cs_off = s.rbuf_off + (1 + pipe) * bt * 8;
-        s.bar_off = s.cs_off + cs_elems * 8;
-        s.total = s.bar_off + (2 * (ring / g) + 2) * 8;
-        return s;
-    }
-};
-
-template <typename S>
-__device__ __forceinline__ void unpack(const vec16 &v, double (&out)[16 / sizeof(S)]);
-template <>
-__device__ __forceinline__ void unpack<double>(const vec16 &v, double (&out)[2]) {
-    out[0] = __hiloint2double(v.y, v.x);
-    out[1] = __hiloint2double(v.w, v.z);
-}
-template <>
-__device__ __forceinline__ void unpack<float>(const vec16 &v, double (&out)[4]) {
-    out[0] = (double)__uint_as_float(v.x);
-    out[1] = (double)__uint_as_float(v.y);
-    out[2] = (double)__uint_as_float(v.z);
-    out[3] = (double)__uint_as_float(v.w);
-}
-
-// RT ("register tile"): pass A keeps its 16-byte vectors in registers for pass B and releases the smem stage at
-// once, so shared memory is a pure streaming ring (every slot in flight) and the HBM stream is decoupled from
-// the A -> exchange -> B dependency.  Needs 4*KT more registers per lane => NW <= 12, one CTA per SM.
-template <typename S, int BT, int NW, bool WANT_G, bool RT>
-__global__ void __launch_bounds__((NW + kProducerWarps) * 32, (NW <= 8 && !RT) ? 2 : 1)
-sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one whole stage (G chunks) */,
+__global__ void __launch_bounds__((NW + kProducerWarps) * 32, (NW <= 8) ? 2 : 1)
+sfh_fg_fused_pipe_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one whole stage (G chunks) */,
                     const __grid_constant__ CUtensorMap tmap_tail /* box = the tile's last, shorter stage */,
                     const FusedParams p) {
+    constexpr bool WANT_G = true, RT = false;
     using Cfg = FusedCfg<S, BT, NW>;
     constexpr int VEC = Cfg::VEC, LPR = Cfg::LPR, RPW = Cfg::RPW, RPC = Cfg::RPC;
     constexpr int kConsumerWarps = NW, kConsumerThreads = NW * 32, kFusedThreads = (NW + kProducerWarps) * 32;
@@ -145,11 +38,11 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one w
     const int kt = p.kt;
     const int NS = p.ring / G;          // stage slots in the ring
     const int nst = (kt + G - 1) / G;   // stages per tile
-    const FusedSmem L = FusedSmem::make(p.ring, BT, (int)C, kt * RPC, NW, G);
+    const FusedSmem L = FusedSmem::make(p.ring, BT, (int)C, kt * RPC, NW, G, 1);
 
     double *red = reinterpret_cast<double *>(smem + L.red_off);    // [NW][BT]
     double *xbuf = reinterpret_cast<double *>(smem + L.xbuf_off);  // [2][C][BT]
-    double *rbuf = reinterpret_cast<double *>(smem + L.rbuf_off);  // [BT]
+    double *rbuf = reinterpret_cast<double *>(smem + L.rbuf_off);  // [2][BT], by tile parity
     double *cs = reinterpret_cast<double *>(smem + L.cs_off);      // [kt*RPC]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bar_off);
     uint64_t *empty = full + NS;
@@ -243,6 +136,38 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one w
         int ss = 0;
         uint32_t phase = 0;
         uint32_t it = 0;
+        int ss_prev = 0;          // first ring stage of the previous tile (still resident: its pass B has not run yet)
+        bool have_prev = false;
+        // pass B of one tile: gradient partials from the bytes still sitting in the ring; releases the stages as it goes
+        auto pass_b = [&](int sb, const double *rb) {
+            double r[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) r[e] = rb[bl * VEC + e];
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) {
+                if (s < nst) {
+                    vec16 v[G];
+                    const uint32_t sbase = ring_base + (uint32_t)(sb * G) * kChunkBytes + lane_off;
+#pragma unroll
+                    for (int u = 0; u < G; ++u)
+                        if (s * G + u < kt) v[u] = lds128(sbase + (uint32_t)u * kChunkBytes);
+#pragma unroll
+                    for (int u = 0; u < G; ++u) {
+                        if (s * G + u < kt) {
+                            double m[VEC];
+                            unpack<S>(v[u], m);
+                            double g = gacc[s * G + u];
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) g = fma(m[e], r[e], g);
+                            gacc[s * G + u] = g;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[sb]);
+                    if (++sb == NS) sb = 0;
+                }
+            }
+        };
         for (int tile = (int)cl; tile < p.n_tiles; tile += (int)ncl, ++it) {
             const uint32_t par = it & 1u;
             const int ssA = ss;
@@ -298,18 +223,21 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one w
             }
             named_bar_sync<1, kConsumerThreads>();
 
-            // ---- exchange: CTA partial -> all CTAs of the cluster; fixed-order sum; residual ----
-            if (warp * 32 < BT) {
-                const bool active = tid < BT;
-                if (active) {
-                    double sum = 0.0;
+            // ---- exchange, part 1: post this CTA's partial to every CTA of the cluster (no wait yet) ----
+            const bool xwarp = warp * 32 < BT, active = tid < BT;
+            if (active) {
+                double sum = 0.0;
 #pragma unroll
-                    for (int w = 0; w < kConsumerWarps; ++w) sum += red[w * BT + tid];
-                    if (tid == 0) mbar_arrive_expect_tx(&xbar[par], C * BT * 8u);
-                    const uint32_t my_slot = smem_u32(&xbuf[(par * C + q) * BT + tid]);
-                    const uint32_t my_bar = smem_u32(&xbar[par]);
-                    for (uint32_t d = 0; d < C; ++d) st_async_f64(mapa(my_slot, d), sum, mapa(my_bar, d));
-                }
+                for (int w = 0; w < kConsumerWarps; ++w) sum += red[w * BT + tid];
+                if (tid == 0) mbar_arrive_expect_tx(&xbar[par], C * BT * 8u);
+                const uint32_t my_slot = smem_u32(&xbuf[(par * C + q) * BT + tid]);
+                const uint32_t my_bar = smem_u32(&xbar[par]);
+                for (uint32_t d = 0; d < C; ++d) st_async_f64(mapa(my_slot, d), sum, mapa(my_bar, d));
+            }
+            // ---- pass B of the PREVIOUS tile runs while the partials are in flight (the ~1 us exchange bubble) ----
+            if (have_prev) pass_b(ss_prev, rbuf + (par ^ 1u) * BT);
+            // ---- exchange, part 2: fixed-order sum; residual of THIS tile into rbuf[par] ----
+            if (xwarp) {
                 mbar_wait_cluster(&xbar[par], (it >> 1) & 1u);
                 if (active) {
                     double m = 0.0;
@@ -325,48 +253,15 @@ sfh_fg_fused_kernel(const __grid_constant__ CUtensorMap tmap_full /* box = one w
                             if (p.residual) p.residual[bin] = r;
                         }
                     }
-                    rbuf[tid] = r;
+                    rbuf[par * BT + tid] = r;
                 }
             }
+            // rbuf[par] complete, red[] free for the next tile's pass A
             named_bar_sync<1, kConsumerThreads>();
-
-            // ---- pass B: gradient partials from the SAME bytes (shared memory, or registers if RT) ----
-            if (WANT_G) {
-                double r[VEC];
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) r[e] = rbuf[bl * VEC + e];
-                int sb = ssA;
-#pragma unroll
-                for (int s = 0; s < SMAX; ++s) {
-                    if (s < nst) {
-                        vec16 v[G];
-                        if (!RT) {
-                            const uint32_t sbase = ring_base + (uint32_t)(sb * G) * kChunkBytes + lane_off;
-#pragma unroll
-                            for (int u = 0; u < G; ++u)
-                                if (s * G + u < kt) v[u] = lds128(sbase + (uint32_t)u * kChunkBytes);
-                        }
-#pragma unroll
-                        for (int u = 0; u < G; ++u) {
-                            if (s * G + u < kt) {
-                                const vec16 vv = RT ? tile_regs[RT ? s * G + u : 0] : v[u];
-                                double m[VEC];
-                                unpack<S>(vv, m);
-                                double g = gacc[s * G + u];
-#pragma unroll
-                                for (int e = 0; e < VEC; ++e) g = fma(m[e], r[e], g);
-                                gacc[s * G + u] = g;
-                            }
-                        }
-                        if (!RT) {
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty[sb]);
-                            if (++sb == NS) sb = 0;
-                        }
-                    }
-                }
-            }
+            ss_prev = ssA;
+            have_prev = true;
         }
+        if (have_prev) pass_b(ss_prev, rbuf + ((it - 1u) & 1u) * BT);   // the last tile
 
         // ---- end of kernel: one store per (cluster, template) ----
         if (WANT_G) {
