@@ -254,6 +254,10 @@ typedef struct sfh_bfgs_opts {
                            /* previous decrease (Nocedal & Wright p. 59)                                         */
     double g_abstol;       /* stop when max|g_i| <= g_abstol; 0 = 1e-8 (solvers.jl:206)                          */
     int64_t maxiter;       /* 0 = 5000 (solvers.jl:203)                                                          */
+    int32_t device_hessian;/* 1: keep the n x n inverse Hessian in device memory (matrix-vector product and       */
+                           /* rank-two update as kernels; pays off from ~500 variables).  Only for the entry       */
+                           /* points that take an sfh_ctx.  Experimental, opt-in.                                  */
+    int32_t reserved;
 } sfh_bfgs_opts;
 typedef struct sfh_bfgs_report {
     double f, g_norm;             /* objective and max|g_i| at the returned point                               */

@@ -62,23 +62,35 @@ out(what="fit_templates_lbfgsb config 1 (10000 bins x 100 templates)", scipy_s=t
     rel_diff_nlogL=float(abs(tt["native"][1] - tt["scipy"][1]) / abs(tt["scipy"][1])))
 ds1.close()
 
-for nb, nt in ((10000, 100), (40000, 500)):
+for nb, nt in ((10000, 100), (40000, 500)) + (((60000, 2400),) if os.environ.get("SFH_BENCH_DEVICE_HESSIAN") else ()):
     g = np.random.Generator(np.random.Philox(58392))
     x = 100 * g.random(nt)
     ds = S.DeviceStack.synthetic(nb, nt, np.float64, 58392, 1.0, x)
     d = ds.download_data()
     tt = {}
-    for engine in ("scipy", "native", "scipy", "native"):
+    # (scipy's dense BFGS update costs ~0.4 s per iteration at 2400 variables: not run there; iterations capped for the big case)
+    engines = ("scipy", "native", "scipy", "native") if nt < 1000 else ("native",)
+    kw = {} if nt < 1000 else {"iterations": 60}
+    for engine in engines:
         t0 = time.perf_counter()
-        r = S.fit_templates(ds, d, x0=np.ones(nt), engine=engine)
+        r = S.fit_templates(ds, d, x0=np.ones(nt), engine=engine, **kw)
         tt[engine] = (time.perf_counter() - t0, r)
     for engine, (t, r) in tt.items():
         nf = int(r["map"].result.nfev) + int(r["mle"].result.nfev)
         out(what=f"fit_templates (MAP+MLE BFGS) {nb} bins x {nt} templates", engine=engine, wall_s=t, fevals=nf, us_per_eval_end_to_end=1e6 * t / nf,
             converged=[bool(r["map"].result.success), bool(r["mle"].result.success)],
             rel_err_vs_truth=float(np.linalg.norm(r["mle"].mu - x) / np.linalg.norm(x)))
-    out(what=f"fit_templates native vs scipy, {nt} templates",
-        rel_diff_mle=float(np.linalg.norm(tt["native"][1]["mle"].mu - tt["scipy"][1]["mle"].mu) / np.linalg.norm(x)))
+    if os.environ.get("SFH_BENCH_DEVICE_HESSIAN"):               # experimental: the inverse Hessian kept in HBM
+        for _ in range(2 if nt < 1000 else 1):
+            t0 = time.perf_counter()
+            r = S.fit_templates(ds, d, x0=np.ones(nt), engine="native", device_hessian=True, **kw)
+            t = time.perf_counter() - t0
+        nf = int(r["map"].result.nfev) + int(r["mle"].result.nfev)
+        out(what=f"fit_templates (MAP+MLE BFGS) {nb} bins x {nt} templates", engine="native + device-resident inverse Hessian", wall_s=t, fevals=nf,
+            us_per_eval_end_to_end=1e6 * t / nf, rel_diff_mle_vs_host_hessian=float(np.linalg.norm(r["mle"].mu - tt["native"][1]["mle"].mu) / np.linalg.norm(x)))
+    if "scipy" in tt:
+        out(what=f"fit_templates native vs scipy, {nt} templates",
+                rel_diff_mle=float(np.linalg.norm(tt["native"][1]["mle"].mu - tt["scipy"][1]["mle"].mu) / np.linalg.norm(x)))
     ds.close()
 
 # ---- container: the 1.15 GB config-3 stack to a file and back ---------------------------------------------------------

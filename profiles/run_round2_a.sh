@@ -14,3 +14,5 @@ done | tee gpurun_out/r2a_pipe_config3.txt
 for cfg in "0 0 0 0" "0 0 0 3" "8 8 8 3" "8 16 8 3" "16 8 8 3" "16 16 8 3" "16 16 16 3"; do
   python profiles/one_config.py $cfg 10 125000 10000 float32 2>&1 | tail -1
 done | tee gpurun_out/r2a_pipe_config5_shard.txt
+# fit_templates at 2400 templates: host-resident vs device-resident inverse Hessian (the host BFGS update is ~17 ms per iteration there)
+SFH_BENCH_DEVICE_HESSIAN=1 timeout 900 python profiles/bench_native.py 2>&1 | tee gpurun_out/r2a_native_device_hessian.txt

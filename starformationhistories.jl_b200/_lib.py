@@ -53,7 +53,8 @@ class sfh_array_desc(C.Structure):
 
 
 class sfh_bfgs_opts(C.Structure):
-    _fields_ = [("struct_size", C.c_int32), ("alphaguess", C.c_int32), ("g_abstol", C.c_double), ("maxiter", C.c_int64)]
+    _fields_ = [("struct_size", C.c_int32), ("alphaguess", C.c_int32), ("g_abstol", C.c_double), ("maxiter", C.c_int64),
+                ("device_hessian", C.c_int32), ("reserved", C.c_int32)]
 
 
 class sfh_bfgs_report(C.Structure):

@@ -2040,7 +2040,58 @@ extern "C" int sfh_stack_create_from_file(sfh_stack **out, const char *path, int
 // native driver loops (csrc/sfh_drivers.h): one call = one whole BFGS optimisation around the device evaluations
 // ---------------------------------------------------------------------------------------------
 namespace {
-int run_bfgs(const sfh::drivers::Objective &obj, int64_t n, double *x, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
+// The inverse Hessian of the native BFGS loop kept in HBM (sfh_bfgs_opts.device_hessian): three small kernels on the context's
+// stream; only n-vectors cross PCIe per iteration.
+class DeviceHessian : public sfh::drivers::HessianBackend {
+public:
+    DeviceHessian(sfh_ctx *c, int64_t n) : c_(c), n_(n) {}
+    ~DeviceHessian() override { cudaFree(dH_); cudaFree(dv_); }
+    int init() {
+        CU_TRY(cudaSetDevice(c_->s->device));
+        CU_TRY(cudaMalloc((void **)&dH_, (size_t)n_ * n_ * 8));
+        CU_TRY(cudaMalloc((void **)&dv_, (size_t)n_ * 3 * 8));   // [g | q] or [s | Hy]
+        return SFH_OK;
+    }
+    int reset_identity() override {
+        sfh_bfgs_identity_kernel<<<std::max(c_->s->sm_count, 1) * 8, 256, 0, c_->stream>>>(dH_, n_);
+        CU_TRY(cudaGetLastError());
+        c_->stats.kernel_launches++;
+        return SFH_OK;
+    }
+    int matvec(const double *g, double *q) override {
+        CU_TRY(cudaMemcpyAsync(dv_, g, (size_t)n_ * 8, cudaMemcpyHostToDevice, c_->stream));
+        const unsigned blocks = (unsigned)std::min<int64_t>((n_ + 7) / 8, (int64_t)std::max(c_->s->sm_count, 1) * 16);
+        sfh_bfgs_symv_kernel<<<blocks, 256, 0, c_->stream>>>(dH_, dv_, dv_ + n_, n_);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(q, dv_ + n_, (size_t)n_ * 8, cudaMemcpyDeviceToHost, c_->stream));
+        CU_TRY(cudaStreamSynchronize(c_->stream));
+        c_->stats.kernel_launches++;
+        return SFH_OK;
+    }
+    int rank2(const double *s, const double *Hy, double rho, double cs) override {
+        CU_TRY(cudaMemcpyAsync(dv_, s, (size_t)n_ * 8, cudaMemcpyHostToDevice, c_->stream));
+        CU_TRY(cudaMemcpyAsync(dv_ + n_, Hy, (size_t)n_ * 8, cudaMemcpyHostToDevice, c_->stream));
+        const dim3 grid((unsigned)std::min<int64_t>((n_ + 255) / 256, 64), (unsigned)std::min<int64_t>(n_, 4096));
+        sfh_bfgs_rank2_kernel<<<grid, 256, 0, c_->stream>>>(dH_, dv_, dv_ + n_, rho, cs, n_);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(c_->stream));   // s / Hy are the caller's (pageable) buffers: do not return while they are being read
+        c_->stats.kernel_launches++;
+        return SFH_OK;
+    }
+    int download(double *invH) override {
+        CU_TRY(cudaMemcpyAsync(invH, dH_, (size_t)n_ * n_ * 8, cudaMemcpyDeviceToHost, c_->stream));
+        CU_TRY(cudaStreamSynchronize(c_->stream));
+        return SFH_OK;
+    }
+
+private:
+    sfh_ctx *c_;
+    int64_t n_;
+    double *dH_ = nullptr, *dv_ = nullptr;
+};
+
+int run_bfgs(const sfh::drivers::Objective &obj, int64_t n, double *x, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH,
+             sfh_ctx *ctx = nullptr) {
     if (n < 1 || !x) return fail(SFH_ERR_INVALID_ARG, "need a start vector of at least one variable");
     if (opts && opts->struct_size != (int32_t)sizeof(sfh_bfgs_opts))
         return fail(SFH_ERR_INVALID_ARG, "sfh_bfgs_opts.struct_size mismatch (%d vs %zu)", opts->struct_size, sizeof(sfh_bfgs_opts));
@@ -2050,6 +2101,19 @@ int run_bfgs(const sfh::drivers::Objective &obj, int64_t n, double *x, const sfh
         if (opts->g_abstol > 0) o.g_abstol = opts->g_abstol;
         if (opts->maxiter > 0) o.maxiter = opts->maxiter;
         if (opts->alphaguess == 2) o.alphaguess = 0;
+    }
+    if (opts && opts->device_hessian) {
+        if (!ctx) return fail(SFH_ERR_UNSUPPORTED, "device_hessian needs an entry point with an sfh_ctx");
+        DeviceHessian dh(ctx, n);
+        SFH_TRY(dh.init());
+        sfh::drivers::BfgsReport r;
+        const int st = sfh::drivers::bfgs_minimize(obj, n, x, o, &r, invH, &dh);
+        if (st != SFH_OK) return st;
+        if (report) {
+            report->f = r.f; report->g_norm = r.g_norm; report->iterations = r.iterations; report->f_calls = r.f_calls;
+            report->converged = r.converged; report->status = r.status;
+        }
+        return SFH_OK;
     }
     std::vector<double> own;
     if (!invH) {
@@ -2095,7 +2159,7 @@ static int sfh_fit_templates_bfgs_impl(sfh_ctx *c, int transform, double *theta,
         else for (int64_t i = 0; i < n; ++i) g[i] *= 2.0 * th[i];                                                             // :257-259
         return SFH_OK;
     };
-    return run_bfgs(obj, n, theta, opts, report, invH);
+    return run_bfgs(obj, n, theta, opts, report, invH, c);
 }
 extern "C" int sfh_fit_templates_bfgs(sfh_ctx *c, int transform, double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report,
                                       double *invH) {
@@ -2119,7 +2183,7 @@ static int sfh_fit_fixed_amr_bfgs_impl(sfh_ctx *c, const double *relweights, con
         if (jacobian) { *f -= sum; for (int64_t j = 0; j < n_ages; ++j) g[j] -= 1.0; }                       // :112, :120
         return SFH_OK;
     };
-    return run_bfgs(obj, n_ages, theta, opts, report, invH);
+    return run_bfgs(obj, n_ages, theta, opts, report, invH, c);
 }
 extern "C" int sfh_fit_fixed_amr_bfgs(sfh_ctx *c, const double *relweights, const int32_t *age_index, int64_t n_ages, int jacobian,
                                       double *theta, const sfh_bfgs_opts *opts, sfh_bfgs_report *report, double *invH) {
@@ -2150,7 +2214,7 @@ static int sfh_fit_sfh_bfgs_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed
         return sfh_eval_fg_hier(c, mh_kind, mh_fixed, disp_kind, x, free_mask, f, g);
     };
     return run_bfgs(sfh::drivers::hier_objective(inner, c->nj, 3, params0, transforms, free_mask, jacobian_corrections != 0),
-                    (int64_t)c->nj + nfree, xvec, opts, report, invH);
+                    (int64_t)c->nj + nfree, xvec, opts, report, invH, c);
 }
 extern "C" int sfh_fit_sfh_bfgs(sfh_ctx *c, int mh_kind, const double *mh_fixed, int disp_kind, const double *params0,
                                 const int32_t *transforms, const uint8_t *free_mask, int jacobian_corrections, double *xvec,

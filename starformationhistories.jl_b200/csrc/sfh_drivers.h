@@ -169,23 +169,45 @@ inline int wolfe_search(const Objective &fn, int64_t n, const double *x, const d
     return -1;
 }
 
+// Where the n x n inverse Hessian lives when it is not the host array: the three operations the loop needs from it.  The
+// device implementation (sfh_api.cu: DeviceHessian) keeps a 2400-template inverse Hessian (46 MB) in HBM, where the matrix-
+// vector product and the rank-two update cost ~10 us each instead of ~8 ms on the host cores.  Non-zero returns abort the run.
+struct HessianBackend {
+    virtual int reset_identity() = 0;
+    virtual int matvec(const double *g, double *q) = 0;                                  // q = H g
+    virtual int rank2(const double *s, const double *Hy, double rho, double cs) = 0;     // H += (cs s - rho Hy) s' - rho s Hy'
+    virtual int download(double *invH) = 0;                                              // column-major n x n
+    virtual ~HessianBackend() {}
+};
+
 // Dense BFGS on the inverse Hessian (column-major n x n in invH, which must hold n*n doubles; it is initialised to the
-// identity here, as Optim does).  x: in = start, out = minimiser.
-inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOptions &o, BfgsReport *rep, double *invH) {
+// identity here, as Optim does).  x: in = start, out = minimiser.  With a backend the matrix lives there during the run and
+// invH (nullable then) receives its final value.
+inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOptions &o, BfgsReport *rep, double *invH,
+                         HessianBackend *hb = nullptr) {
     using namespace detail;
     std::vector<double> g((size_t)n), gn((size_t)n), xn((size_t)n), p((size_t)n), s((size_t)n), y((size_t)n), Hy((size_t)n);
-    for (int64_t j = 0; j < n; ++j) {
-        double *col = invH + j * n;
-        std::fill(col, col + n, 0.0);
-        col[j] = 1.0;
-    }
+    auto identity = [&]() -> int {
+        if (hb) return hb->reset_identity();
+        for (int64_t j = 0; j < n; ++j) {
+            double *col = invH + j * n;
+            std::fill(col, col + n, 0.0);
+            col[j] = 1.0;
+        }
+        return 0;
+    };
+    auto finish = [&](const BfgsReport &rr) -> int {
+        *rep = rr;
+        return (hb && invH) ? hb->download(invH) : 0;
+    };
+    if (int e = identity()) return e;
     BfgsReport r;
     double f = 0;
     int st = fn(x, &f, g.data());
     r.f_calls = 1;
     if (st) return st;
     r.f = f; r.g_norm = infnorm(g.data(), n);
-    if (!std::isfinite(f) || !std::isfinite(r.g_norm)) { r.status = 3; *rep = r; return 0; }
+    if (!std::isfinite(f) || !std::isfinite(r.g_norm)) { r.status = 3; return finish(r); }
     double f_prev = f + std::sqrt(dot(g.data(), g.data(), n)) / 2.0;
     // Two passes over the n x n matrix per iteration instead of three: q = H g_new (one read) gives both H y = q + p_old
     // (p_old = -H g_old) and, after the rank-two update (one read + write), the next direction algebraically:
@@ -197,7 +219,8 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
         if (r.iterations >= o.maxiter) { r.status = 1; break; }
         double dphi0 = dot(g.data(), p.data(), n);
         if (!(dphi0 < 0)) {   // not a descent direction (H lost positive definiteness to rounding): restart from the identity
-            for (int64_t j = 0; j < n; ++j) { double *col = invH + j * n; std::fill(col, col + n, 0.0); col[j] = 1.0; p[(size_t)j] = -g[(size_t)j]; }
+            if (int e = identity()) return e;
+            for (int64_t j = 0; j < n; ++j) p[(size_t)j] = -g[(size_t)j];
             dphi0 = -dot(g.data(), g.data(), n);
             if (!(dphi0 < 0)) { r.status = 2; break; }
         }
@@ -221,9 +244,13 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
         if (r.g_norm <= o.g_abstol) { r.converged = 1; r.status = 0; break; }
         if (!std::isfinite(f)) { r.status = 2; break; }
         // H <- (I - rho s y') H (I - rho y s') + rho s s'  =  H - rho (s Hy' + Hy s') + (rho^2 y'Hy + rho) s s'
-        for_columns(n, [&](int64_t j0, int64_t j1) {
-            for (int64_t j = j0; j < j1; ++j) q[(size_t)j] = dot(invH + j * n, g.data(), n);   // H symmetric: column j = row j
-        });
+        if (hb) {
+            if (int e = hb->matvec(g.data(), q.data())) return e;
+        } else {
+            for_columns(n, [&](int64_t j0, int64_t j1) {
+                for (int64_t j = j0; j < j1; ++j) q[(size_t)j] = dot(invH + j * n, g.data(), n);   // H symmetric: column j = row j
+            });
+        }
         const double ys = dot(y.data(), s.data(), n);
         if (!(ys > 0)) {      // curvature condition violated (cannot happen with a Wolfe step up to rounding): skip the update
             for (int64_t j = 0; j < n; ++j) p[(size_t)j] = -q[(size_t)j];
@@ -234,17 +261,20 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
         const double yHy = dot(y.data(), Hy.data(), n);
         const double cs = rho * rho * yHy + rho;
         const double Hyg = dot(Hy.data(), g.data(), n), sg = dot(s.data(), g.data(), n);
-        for_columns(n, [&](int64_t j0, int64_t j1) {
-            for (int64_t j = j0; j < j1; ++j) {
-                double *col = invH + j * n;
-                const double a = cs * s[(size_t)j] - rho * Hy[(size_t)j], b = -rho * s[(size_t)j];
-                for (int64_t i = 0; i < n; ++i) col[i] += a * s[(size_t)i] + b * Hy[(size_t)i];
-            }
-        });
+        if (hb) {
+            if (int e = hb->rank2(s.data(), Hy.data(), rho, cs)) return e;
+        } else {
+            for_columns(n, [&](int64_t j0, int64_t j1) {
+                for (int64_t j = j0; j < j1; ++j) {
+                    double *col = invH + j * n;
+                    const double a = cs * s[(size_t)j] - rho * Hy[(size_t)j], b = -rho * s[(size_t)j];
+                    for (int64_t i = 0; i < n; ++i) col[i] += a * s[(size_t)i] + b * Hy[(size_t)i];
+                }
+            });
+        }
         for (int64_t j = 0; j < n; ++j) p[(size_t)j] += rho * (s[(size_t)j] * Hyg + Hy[(size_t)j] * sg) - cs * s[(size_t)j] * sg;
     }
-    *rep = r;
-    return 0;
+    return finish(r);
 }
 
 

@@ -482,6 +482,40 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_epilogue_kernel(const H
 }
 
 // ------------------------------------------------------------------------------------------
+// dense BFGS inverse Hessian resident on the device (sfh_api.cu: DeviceHessian; opt-in, sfh_bfgs_opts.device_hessian):
+// at 2400 templates the matrix is 46 MB -- one read for q = H g, one read + write for the rank-two update.
+// ------------------------------------------------------------------------------------------
+__global__ void sfh_bfgs_identity_kernel(double *H, int64_t n) {
+    const int64_t tot = n * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x)
+        H[e] = (e / n == e % n) ? 1.0 : 0.0;
+}
+// q_j = sum_i H[i + j n] g_i: one warp per column (H is symmetric, so column j is row j), lanes stride the column (coalesced),
+// fixed-order shuffle tree => deterministic
+__global__ void sfh_bfgs_symv_kernel(const double *__restrict__ H, const double *__restrict__ g, double *__restrict__ q, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+        const double *col = H + j * n;
+        double acc = 0.0;
+        for (int64_t i = lane; i < n; i += 32) acc = fma(col[i], g[i], acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) q[j] = acc;
+    }
+}
+// H[i + j n] += (cs s_j - rho Hy_j) s_i - rho s_j Hy_i   (the BFGS update written as in csrc/sfh_drivers.h)
+__global__ void sfh_bfgs_rank2_kernel(double *__restrict__ H, const double *__restrict__ s, const double *__restrict__ Hy, double rho,
+                                      double cs, int64_t n) {
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+        const double a = cs * s[j] - rho * Hy[j], b = -rho * s[j];
+        double *col = H + j * n;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+            col[i] += a * s[i] + b * Hy[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // synthetic data on device: Philox4x32-10, counter = global linear element index
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {

@@ -220,9 +220,9 @@ end
 # ---- native BFGS loops: one ccall per optimisation (include/sfhcuda.h: sfh_fit_*_bfgs) ----------------------------
 # What fit_templates / fit_templates_fast (solvers.jl:163-275) and fit_sfh (generic_fitting.jl:296-327) hand to
 # Optim.optimize(only_fg!(...), x0, BFGS(...)): here the loop runs inside the library around the device evaluations.
-struct BfgsOpts; struct_size::Int32; alphaguess::Int32; g_abstol::Float64; maxiter::Int64; end
+struct BfgsOpts; struct_size::Int32; alphaguess::Int32; g_abstol::Float64; maxiter::Int64; device_hessian::Int32; reserved::Int32; end
 mutable struct BfgsReport; f::Float64; g_norm::Float64; iterations::Int64; f_calls::Int64; converged::Int32; status::Int32; BfgsReport() = new(); end
-bfgs_opts(g_abstol, iterations) = BfgsOpts(sizeof(BfgsOpts), 0, g_abstol, iterations)
+bfgs_opts(g_abstol, iterations; device_hessian=false) = BfgsOpts(sizeof(BfgsOpts), 0, g_abstol, iterations, device_hessian, 0)
 
 # transform: 0 = log-space MAP (solvers.jl:178-186), 1 = log-space MLE (:187-195), 2 = sqrt-space MLE (:254-261).
 # Returns (minimiser in the fitting space, inverse Hessian, report): fit_templates builds its LogTransformFTResult from them.

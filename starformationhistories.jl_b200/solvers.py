@@ -143,10 +143,10 @@ class NativeBFGSResult:
     status: int          # 0 converged; 1 iteration limit; 2 line search failed; 3 start not finite
 
 
-def _bfgs_opts(gtol, maxiter, alphaguess=0):
+def _bfgs_opts(gtol, maxiter, alphaguess=0, device_hessian=False):
     o = L.sfh_bfgs_opts()
     o.struct_size = C.sizeof(L.sfh_bfgs_opts)
-    o.g_abstol, o.maxiter, o.alphaguess = float(gtol), int(maxiter), int(alphaguess)
+    o.g_abstol, o.maxiter, o.alphaguess, o.device_hessian = float(gtol), int(maxiter), int(alphaguess), int(bool(device_hessian))
     return o
 
 
@@ -214,12 +214,12 @@ def native_fit_sfh_generic(inner_fg, n_ages, params0, transforms, free, xstart, 
     return _native_result(x, invH, rep)
 
 
-def _native_fit_templates(ds, transform, theta0, gtol, maxiter):
+def _native_fit_templates(ds, transform, theta0, gtol, maxiter, device_hessian=False):
     theta = np.array(theta0, dtype=np.float64)
     n = theta.shape[0]
     invH = np.empty((n, n), order="F")
     rep = L.sfh_bfgs_report()
-    o = _bfgs_opts(gtol, maxiter)
+    o = _bfgs_opts(gtol, maxiter, 0, device_hessian)
     dp = C.POINTER(C.c_double)
     L.check(L.lib.sfh_fit_templates_bfgs(ds.ctx().handle, transform, theta.ctypes.data_as(dp), C.byref(o), C.byref(rep), invH.ctypes.data_as(dp)))
     return _native_result(theta, invH, rep)
@@ -230,7 +230,7 @@ def _check_engine(engine):
         raise ValueError("engine must be 'scipy' or 'native'")
 
 
-def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy"):
+def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy", device_hessian=False):
     """Returns {"map": LogTransformFTResult, "mle": ...}: BFGS on log-coefficients (solvers.jl:172-221).
     engine="native": the whole optimisation is one call into the library (sfh_fit_templates_bfgs)."""
     _check_engine(engine)
@@ -251,8 +251,9 @@ def fit_templates(models, data, x0=None, g_abstol=1e-8, iterations=5000, engine=
         return f, G * x
 
     if engine == "native":
-        rmap = _native_fit_templates(ds, L.SFH_FIT_LOG_MAP, x0, g_abstol, iterations)
-        rmle = _native_fit_templates(ds, L.SFH_FIT_LOG_MLE, rmap.x, g_abstol, iterations)
+        # device_hessian (experimental): the T x T inverse Hessian lives in HBM, its update and products run as kernels
+        rmap = _native_fit_templates(ds, L.SFH_FIT_LOG_MAP, x0, g_abstol, iterations, device_hessian)
+        rmle = _native_fit_templates(ds, L.SFH_FIT_LOG_MLE, rmap.x, g_abstol, iterations, device_hessian)
     else:
         rmap = _bfgs(fg_map, x0, g_abstol, iterations)                     # :206
         rmle = _bfgs(fg_mle, rmap.x, g_abstol, iterations)                 # :207 (seeded from the MAP)

@@ -76,3 +76,17 @@ def test_pipe_f32_storage_and_many_tiles_per_cluster(S):
     # hierarchical path on top of it
     f2, G2, _ = ds.eval_fg(x * 1.01)
     assert np.isfinite(f2) and np.all(np.isfinite(G2)) and f2 != f
+
+
+# ---- the BFGS inverse Hessian resident on the device (sfh_bfgs_opts.device_hessian; also written after the GPU budget was spent) ----
+@pytest.mark.parametrize("nb,nt", [(10000, 20), (20000, 600)])
+def test_device_hessian_bfgs_matches_host_hessian(S, nb, nt):
+    M, x, data = make_flat_problem(nb, nt)
+    a = S.fit_templates(M, data, x0=np.ones(nt), engine="native")
+    b = S.fit_templates(M, data, x0=np.ones(nt), engine="native", device_hessian=True)
+    for k in ("map", "mle"):
+        assert b[k].result.success == a[k].result.success
+        assert np.linalg.norm(a[k].mu - b[k].mu) <= 1e-6 * np.linalg.norm(a[k].mu)
+        H = b[k].invH
+        assert np.allclose(H, H.T, atol=1e-10 * np.abs(H).max()) and np.all(np.diag(H) > 0)
+        assert np.allclose(np.sqrt(np.diag(H)), np.sqrt(np.diag(a[k].invH)), rtol=0.3)

@@ -185,7 +185,9 @@ def test_raw_abi_argument_checks():
     o = L.sfh_bfgs_opts(); o.struct_size = 3
     assert L.lib.sfh_minimize_bfgs(cb, None, 2, x.ctypes.data_as(dp), C.byref(o), C.byref(rep), None) == L.SFH_ERR_INVALID_ARG
     assert b"struct_size" in L.lib.sfh_last_error()
-    assert C.sizeof(L.sfh_bfgs_opts) == 24 and C.sizeof(L.sfh_bfgs_report) == 40
+    assert C.sizeof(L.sfh_bfgs_opts) == 32 and C.sizeof(L.sfh_bfgs_report) == 40
+    o = L.sfh_bfgs_opts(); o.struct_size = C.sizeof(L.sfh_bfgs_opts); o.device_hessian = 1      # needs an entry point with a context
+    assert L.lib.sfh_minimize_bfgs(cb, None, 2, x.ctypes.data_as(dp), C.byref(o), C.byref(rep), None) == L.SFH_ERR_UNSUPPORTED
     # device-bound variants validate their arguments before touching a device
     assert L.lib.sfh_fit_templates_bfgs(None, 0, x.ctypes.data_as(dp), None, None, None) == L.SFH_ERR_INVALID_ARG
     assert L.lib.sfh_fit_sfh_bfgs(None, 0, None, 0, None, None, None, 1, None, None, None, None) == L.SFH_ERR_INVALID_ARG
