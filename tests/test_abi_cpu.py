@@ -149,3 +149,20 @@ def test_plain_c_consumer(tmp_path):
     r = subprocess.run([str(exe), str(tmp_path / "smoke.sfh")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "abi_c_smoke: ok" in r.stdout
+
+
+def test_native_cpp_example_builds_and_runs(tmp_path):
+    """examples/fit_sfh_native.cpp -- fit_sfh + tsample_sfh + persistence through nothing but the C-ABI -- compiles warning-free
+    and, on a box without a GPU, says so and exits 0 (on a GPU box it runs a small problem end to end)."""
+    import sfh_b200
+    exe = tmp_path / "fit_sfh_native"
+    libdir = os.path.dirname(sfh_b200._lib.LIB_PATH)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "fit_sfh_native.cpp"), "-o", str(exe), "-L", libdir, "-l:libsfhcuda.so",
+                    f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe), "40", "50", "8", "6", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    if sfh_b200.device_count() == 0:
+        assert "no CUDA device" in r.stdout
+    else:
+        assert "wrote" in r.stdout and os.path.exists(tmp_path / "fit.sfh")
