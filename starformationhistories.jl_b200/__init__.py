@@ -14,7 +14,8 @@ from ._lib import SFHError, device_count
 from .fitting import (DeviceStack, clear_cache, composite_, device_stack, fg_ as fg_flat_, grad_loglikelihood,
                       grad_loglikelihood_, loglikelihood, stack_models)
 from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR, LogarithmicAMR, PowerLawMZR,
-                           calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams)
+                           calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams, MH_from_Z, dMH_dZ, Z_from_MH, dZ_dMH,
+                           X_from_Z, Y_from_Z)
 from .sampling import HMCModel, MCMCModel
 from . import io, sharding, solvers
 from .io import SFHFile, load_result, read_arrays, save_result, write_arrays
@@ -43,4 +44,4 @@ __all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite
            "init_library_comm", "fit_templates_lbfgsb", "fit_templates", "fit_templates_fast", "fit_sfh", "mcmc_sample",
            "hmc_sample", "renormalize_x0", "mdf_amr", "calculate_cum_sfr", "cum_sfr_quantiles", "rand_result", "construct_x0", "bin_cmd_smooth", "partial_cmd_smooth", "build_template_stack",
            "template_points", "templates", "sample_sfh", "tsample_sfh", "fixed_amr", "truncate_relweights", "construct_x0_mdf", "bin_cmd", "partial_cmd",
-           "io", "SFHFile", "write_arrays", "read_arrays", "save_result", "load_result"]
+           "MH_from_Z", "dMH_dZ", "Z_from_MH", "dZ_dMH", "X_from_Z", "Y_from_Z", "io", "SFHFile", "write_arrays", "read_arrays", "save_result", "load_result"]

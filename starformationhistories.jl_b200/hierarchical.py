@@ -100,11 +100,50 @@ class LinearAMR(_MHModel):
         self.alpha, self.beta, self.T_max = float(alpha), float(beta), float(T_max)
         self.free = tuple(bool(f) for f in free)
 
+    @classmethod
+    def from_constraints(cls, constraint1, constraint2, T_max=13.7, free=(True, True)):
+        """LinearAMR(constraint1, constraint2, T_max) (amr.jl:229-245): the line through two ([M/H], lookback time [Gyr]) points."""
+        if len(constraint1) != 2 or len(constraint2) != 2:
+            raise ValueError("length(constraint1) == length(constraint2) == 2 must hold")
+        times, mhs = (constraint1[1], constraint2[1]), (constraint1[0], constraint2[0])
+        dt, dmh = times[1] - times[0], mhs[1] - mhs[0]
+        if dt == 0:
+            raise ValueError("Constraints are given at identical times.")
+        if not (np.sign(dt) != np.sign(dmh)):
+            raise ValueError("The constraints indicate metallicity is decreasing towards present-day; not allowed under LinearAMR.")
+        alpha = dmh / -dt
+        return cls(alpha, min(mhs) - alpha * (T_max - max(times)), T_max, free)
+
     def __call__(self, logAge): return self.beta + self.alpha * (self.T_max - 10.0 ** (logAge - 9))
     def gradient(self, logAge): return (self.T_max - 10.0 ** (logAge - 9), 1.0)
     def update_params(self, new): return LinearAMR(new[0], new[1], self.T_max, self.free)
+    def __eq__(self, o):
+        return isinstance(o, LinearAMR) and (self.alpha, self.beta, self.T_max, self.free) == (o.alpha, o.beta, o.T_max, o.free)
     def transforms(self): return (1, 0)
     def fixed(self): return np.array([self.T_max, 0, 0, 0], dtype=np.float64)
+
+
+def Y_from_Z(Z, Y_p=0.2485, gamma=1.78):
+    """src/utilities.jl:118"""
+    return Y_p + gamma * Z
+
+
+def X_from_Z(Z, Y_p=0.2485, gamma=1.78):
+    """src/utilities.jl:123-125"""
+    return 1 - (Y_from_Z(Z, Y_p, gamma) + Z)
+
+
+def Z_from_MH(MH, solZ=0.01524, Y_p=0.2485, gamma=1.78):
+    """src/utilities.jl:160-176: inverse of MH_from_Z under Y = Y_p + gamma Z."""
+    zoverx = 10.0 ** (MH + math.log10(solZ / X_from_Z(solZ, Y_p, gamma)))
+    return (1 - Y_p) * zoverx / (1 + (1 + gamma) * zoverx)
+
+
+def dZ_dMH(MH, solZ=0.01524, Y_p=0.2485, gamma=1.78):
+    """src/utilities.jl:182-187"""
+    prefac = 10.0 ** MH * solZ
+    X = X_from_Z(solZ, Y_p, gamma)
+    return -prefac * X * (Y_p - 1) * LOGTEN / (X + prefac * (1 + gamma)) ** 2
 
 
 def MH_from_Z(Z, solZ=0.01524, Y_p=0.2485, gamma=1.78):
@@ -134,6 +173,29 @@ class LogarithmicAMR(_MHModel):
         self.alpha, self.beta, self.T_max = float(alpha), float(beta), float(T_max)
         self.solZ, self.Y_p, self.gamma = float(solZ), float(Y_p), float(gamma)
         self.free = tuple(bool(f) for f in free)
+
+    @classmethod
+    def from_constraints(cls, constraint1, constraint2, T_max=13.7, free=(True, True), solZ=0.01524, Y_p=0.2485, gamma=1.78):
+        """LogarithmicAMR(constraint1, constraint2, T_max) (amr.jl:317-338): Z linear in lookback time through two
+        ([M/H], lookback time [Gyr]) points, with the default Z_from_MH conversion."""
+        if len(constraint1) != 2 or len(constraint2) != 2:
+            raise ValueError("length(constraint1) == length(constraint2) == 2 must hold")
+        times = (constraint1[1], constraint2[1])
+        zs = (Z_from_MH(constraint1[0], solZ, Y_p, gamma), Z_from_MH(constraint2[0], solZ, Y_p, gamma))
+        dt, dz = times[1] - times[0], zs[1] - zs[0]
+        if dt == 0:
+            raise ValueError("Constraints are given at identical times.")
+        if not (np.sign(dt) != np.sign(dz)):
+            raise ValueError("The constraints indicate metallicity is decreasing towards present-day; not allowed under LogarithmicAMR.")
+        alpha = dz / -dt
+        beta = min(zs) - alpha * (T_max - max(times))
+        if beta < 0:
+            raise ValueError("Given constraints result in a metal mass fraction Z < 0 at T_max. Please revise arguments.")
+        return cls(alpha, beta, T_max, free, solZ, Y_p, gamma)
+
+    def __eq__(self, o):
+        return isinstance(o, LogarithmicAMR) and (self.alpha, self.beta, self.T_max, self.free, self.solZ, self.Y_p, self.gamma) == \
+            (o.alpha, o.beta, o.T_max, o.free, o.solZ, o.Y_p, o.gamma)
 
     def __call__(self, logAge):
         return MH_from_Z(self.beta + self.alpha * (self.T_max - 10.0 ** (logAge - 9)), self.solZ, self.Y_p, self.gamma)

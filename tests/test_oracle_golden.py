@@ -163,3 +163,48 @@ def test_calculate_coeffs_properties(T):                # mzr_test.jl:9-47
     assert np.allclose(x, y[order], rtol=rt * 10)                         # :44
     with pytest.raises(ValueError):                                       # mzr.jl:55 argcheck
         O.calculate_coeffs(O.POWERLAW_MZR, 1.0, -1.0, (6.0,), 0.2, R[:-1], p["logAge"], p["MH"], dtype=T)
+
+
+# ---- metallicity conversions on the LogarithmicAMR path: the reference's own known answers (test/utilities/utilities_test.jl:32-43) ----
+def test_metallicity_conversion_kats_pin_oracle_and_host_mirror():
+    import sfh_b200 as S
+    # The reference asserts these at rtol 1e-7 for Float64; its literals were evidently generated from the Float32 value of 1e-3
+    # (0.0010000000474974513): with that input every digit is reproduced, with the Float64 1e-3 they hold at the reference's 1e-7.
+    z32 = float(np.float32(1e-3))
+    assert S.Y_from_Z(z32, 0.2485) == pytest.approx(0.2502800000845455, rel=1e-15)          # :32
+    assert S.X_from_Z(z32) == pytest.approx(0.748719999867957, rel=1e-15)                   # :33
+    assert S.X_from_Z(1e-3, 0.25) == pytest.approx(0.74722, rel=1e-7)                       # :34
+    assert S.MH_from_Z(z32, 0.01524) == pytest.approx(-1.206576807011171, rel=1e-15)        # :36
+    assert S.MH_from_Z(1e-3, 0.01524) == pytest.approx(-1.206576807011171, rel=1e-7)
+    assert S.Z_from_MH(-2.0, 0.01524, Y_p=0.2485) == pytest.approx(0.00016140871730361718, rel=1e-12)   # :37
+    assert S.MH_from_Z(S.Z_from_MH(-2.0, 0.01524), 0.01524) == pytest.approx(-2.0, rel=1e-12)           # :39 inverses
+    assert S.MH_from_Z(S.Z_from_MH(1.0, 0.01524), 0.01524) == pytest.approx(1.0, rel=1e-12)             # :41 (positive [M/H])
+    assert S.dMH_dZ(1e-3, 0.01524, Y_p=0.2485, gamma=1.78) == pytest.approx(435.9070188458886, rel=1e-12)   # :43
+    # dZ_dMH is the derivative of Z_from_MH (central difference) and the reciprocal of dMH_dZ at the same point
+    h = 1e-6
+    assert S.dZ_dMH(-1.0) == pytest.approx((S.Z_from_MH(-1.0 + h) - S.Z_from_MH(-1.0 - h)) / (2 * h), rel=1e-8)
+    assert S.dZ_dMH(-1.0) * S.dMH_dZ(S.Z_from_MH(-1.0)) == pytest.approx(1.0, rel=1e-12)
+    # the ORACLE's LogarithmicAMR (amr.jl:284-297) at alpha = 0, beta = Z: mean = MH_from_Z(Z), d mean / d beta = dMH_dZ(Z)
+    fixed = (13.7, 0.01524, 0.2485, 1.78)
+    assert O.mh_mean(O.LOG_AMR, 0.0, z32, fixed, 9.5) == pytest.approx(-1.206576807011171, rel=1e-14)
+    gA, gB, _ = O.mh_grad(O.LOG_AMR, 0.0, 1e-3, fixed, 9.5)
+    assert gB == pytest.approx(435.9070188458886, rel=1e-12)
+    assert gA == pytest.approx(435.9070188458886 * (13.7 - 10.0 ** (9.5 - 9)), rel=1e-12)   # amr.jl:290-291
+    assert np.isnan(O.mh_mean(O.LOG_AMR, 0.0, 0.5, fixed, 9.5))                             # X <= 0 -> NaN (utilities.jl:145)
+
+
+def test_amr_constraint_constructors_doctests():
+    import sfh_b200 as S
+    a = S.LinearAMR.from_constraints((-2.5, 13.7), (-1.0, 0.0), 13.7)                       # amr.jl:221-227
+    b = S.LinearAMR.from_constraints((-1.0, 0.0), (-2.5, 13.7), 13.7)
+    assert a == b and a.alpha == pytest.approx(1.5 / 13.7) and a.beta == pytest.approx(-2.5)
+    assert a(9 + np.log10(13.7)) == pytest.approx(-2.5) and a(-np.inf) == pytest.approx(-1.0)   # passes through both constraints
+    c = S.LogarithmicAMR.from_constraints((-2.5, 13.7), (-1.0, 0.0), 13.7)                  # amr.jl:308-315
+    d = S.LogarithmicAMR.from_constraints((-1.0, 0.0), (-2.5, 13.7), 13.7)
+    assert c == d and c(9 + np.log10(13.7)) == pytest.approx(-2.5, rel=1e-10) and c(-np.inf) == pytest.approx(-1.0, rel=1e-10)
+    with pytest.raises(ValueError):
+        S.LinearAMR.from_constraints((-2.5, 5.0), (-1.0, 5.0))                              # identical times
+    with pytest.raises(ValueError):
+        S.LinearAMR.from_constraints((-1.0, 13.7), (-2.5, 0.0))                             # metallicity decreasing towards the present
+    with pytest.raises(ValueError):
+        S.LogarithmicAMR.from_constraints((-2.5, 1.0), (-1.0, 0.0), 13.7)                   # Z < 0 at T_max

@@ -89,6 +89,9 @@ def test_host_helpers_doctests():
     assert T.histogram_pix(0.55, np.arange(0, 1.01, 0.1)) == pytest.approx(6.5)
     assert T.Martin2016_complete(28.5, 1.0, 28.5, 0.7) == pytest.approx(0.5)
     assert T.exp_photerr(36.0, 1.03, 15.0, 36.0, 0.02) == pytest.approx(1.02)
+    # the reference's own known answers (test/utilities/utilities_test.jl:44-47, BigFloat literals)
+    assert T.Martin2016_complete(20.0, 1.0, 25.0, 1.0) == pytest.approx(0.9933071490757151444406380196186748, rel=1e-15)
+    assert T.exp_photerr(20.0, 1.05, 10.0, 32.0, 0.01) == pytest.approx(0.01286605230281143891186877135084309, rel=1e-13)
     xe, ye = T.calculate_edges(None, (1.5, -1.0), (22.0, 27.2), (26, 53))
     assert xe.shape == (26,) and ye.shape == (53,) and xe[0] == -1.0 and ye[-1] == 27.2
     with pytest.raises(ValueError):
