@@ -43,6 +43,13 @@ KATS = {
                                          "value_is_exp_minus_half": True, "grad": [3.0326532985631656, -3.0326532985631656]},
                  "powerlaw_mzr": {"_cite": "mzr.jl:245-250", "alpha": 1.0, "MH0": -1, "logMstar0": 6, "at_1e7": 0.0,
                                   "grad_at_1e8": [2.0, 1.0, "1/1e8/ln(10)"]}},
+    "metallicity_utilities": {"_cite": "test/utilities/utilities_test.jl:32-47 (rtol 1e-3 Float32 / 1e-7 Float64; the literals were generated "
+                                       "from the Float32 value of 1e-3 and are reproduced to every digit with that input)",
+                              "Z": 1e-3, "Z_float32_literal": 0.0010000000474974513, "solZ": 0.01524, "Y_p": 0.2485, "gamma": 1.78,
+                              "Y_from_Z": 0.2502800000845455, "X_from_Z": 0.748719999867957, "X_from_Z_Yp_0.25": 0.74722,
+                              "MH_from_Z": -1.206576807011171, "Z_from_MH_at_-2": 0.00016140871730361718, "dMH_dZ": 435.9070188458886,
+                              "Martin2016_complete(20,1,25,1)": 0.9933071490757151444406380196186748,
+                              "exp_photerr(20,1.05,10,32,0.01)": 0.01286605230281143891186877135084309},
     "unreproducible_here": {"_why": "inputs come from StableRNG + Distributions.Poisson streams (Julia only)",
                             "mzr_test.jl:74-76": {"nlogL": 4917.491550052553}, "amr_test.jl:45-47": {"nlogL": 4903.0966770848445},
                             "amr_test.jl:264-265": {"nlogL": 5006.412301383171}},
