@@ -44,6 +44,40 @@ def test_struct_layouts_match_header():
     assert L.lib.sfh_version() == 1
 
 
+def test_every_struct_field_offset_matches_header(tmp_path):
+    """Every ctypes mirror in _lib.py has the size and the field offsets gcc computes from include/sfhcuda.h itself
+    (a field added to the header and not to the mirror -- or the other way round -- fails here, on the CPU)."""
+    import sfh_b200
+    L = sfh_b200._lib
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    names = re.findall(r"typedef\s+struct\s+(sfh_\w+)\s*\{", src)
+    assert len(names) >= 9
+    mirrors = {n: getattr(L, n) for n in names}      # AttributeError = a struct of the header without a mirror
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sfhcuda.h"', 'int main(void) {']
+    for n, cls in mirrors.items():
+        lines.append(f'  printf("{n} . %zu\\n", sizeof({n}));')
+        for f in cls._fields_:
+            lines.append(f'  printf("{n} {f[0]} %zu\\n", offsetof({n}, {f[0]}));')
+    lines += ['  return 0;', '}']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.dirname(HEADER), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        n, f, v = line.split()
+        want = C.sizeof(mirrors[n]) if f == "." else getattr(mirrors[n], f).offset
+        assert int(v) == want, f"{n}.{f}: header {v}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
+    # and the header holds no field the mirror lacks: count the declarators of each struct body
+    for n, cls in mirrors.items():
+        body = re.search(r"typedef\s+struct\s+" + n + r"\s*\{(.*?)\}\s*" + n + r"\s*;", src, flags=re.S).group(1)
+        decls = sum(len(stmt.split(",")) for stmt in body.split(";") if stmt.strip())
+        assert decls == len(cls._fields_), f"{n}: header declares {decls} fields, ctypes mirrors {len(cls._fields_)}"
+
+
 def test_no_device_fails_loudly():
     import torch
     if torch.cuda.is_available():
@@ -166,3 +200,19 @@ def test_native_cpp_example_builds_and_runs(tmp_path):
         assert "no CUDA device" in r.stdout
     else:
         assert "wrote" in r.stdout and os.path.exists(tmp_path / "fit.sfh")
+
+
+def test_julia_struct_mirrors_match_header():
+    """julia/SFHCuda.jl cannot be executed here (no julia binary): its isbits mirrors of the option / report structs are compared
+    statically, field by field (name, width, order), with the ctypes mirrors the test above checks against gcc."""
+    import sfh_b200
+    L = sfh_b200._lib
+    jl = open(os.path.join(PKG, "julia", "SFHCuda.jl")).read()
+    pairs = {"SfhOpts": L.sfh_opts, "BfgsOpts": L.sfh_bfgs_opts, "BfgsReport": L.sfh_bfgs_report, "NutsOpts": L.sfh_nuts_opts,
+             "LbfgsbOpts": L.sfh_lbfgsb_opts, "LbfgsbReport": L.sfh_lbfgsb_report}
+    jl_types = {"Int32": C.c_int32, "Int64": C.c_int64, "UInt64": C.c_uint64, "Float64": C.c_double}
+    for jname, cls in pairs.items():
+        m = re.search(r"^(?:mutable\s+)?struct\s+" + jname + r"\b(.*?)\bend\s*$", jl, flags=re.S | re.M)
+        assert m, f"{jname} not found in SFHCuda.jl"
+        fields = re.findall(r"(\w+)::(\w+)", m.group(1))
+        assert [(n, jl_types[t]) for n, t in fields] == [(f[0], f[1]) for f in cls._fields_], jname
