@@ -529,6 +529,71 @@ def cum_sfr_quantiles(result, logAge, MH, T_max, Nsamples, q, rng=None, **kws):
     return {"cum_sfh": cum_q, "sfrs": sfr_q, "mean_mh": mh_q, "samples": samples, "n_good": len(rows)}
 
 
+def tau_interp(unique_logAge, max_logAge, cum_sfh):
+    """tau_interp (fitting/utilities.jl:311-336): piecewise-linear map from the fraction of the total stellar mass formed to the
+    lookback time [Gyr].  Knots: the cumulative SFH normalised to its maximum, with (0, max_logAge) prepended -- the moment the
+    galaxy had no mass; either ordering of the inputs is accepted; equal knots are separated by one ulp each
+    (`deduplicate_knots!(...; move_knots=true)`).  Like the reference's gridded interpolant the callable refuses fractions
+    outside [0, 1] (ValueError for Julia's BoundsError) instead of clamping."""
+    la, cum = np.asarray(unique_logAge, dtype=np.float64), np.asarray(cum_sfh, dtype=np.float64)
+    if la.ndim != 1 or la.shape != cum.shape:
+        raise ValueError("length(unique_logAge) != length(cum_sfh)")                                       # :312
+    if not la.max() < max_logAge:
+        raise ValueError("`max_logAge` must be greater than the maximum of `unique_logAge`.")              # :313
+    ascending = lambda a: bool(np.all(a[1:] >= a[:-1]))
+    if not ascending(cum):                                                                                 # :314-317
+        cum, la = cum[::-1], la[::-1]
+    if not ascending(cum):
+        raise ValueError("`cum_sfh` must be sorted in ascending or descending order.")                     # :319
+    if not ascending(-la):
+        raise ValueError("`unique_logAge` must be sorted in the same order as `cum_sfh`.")                 # :320
+    if cum[0] != 0:
+        cum = np.concatenate([[0.0], cum])                                                                 # :322-324
+    if la[0] != max_logAge:
+        la = np.concatenate([[max_logAge], la])                                                            # :326-328
+    if cum.shape != la.shape:
+        raise ValueError("knots and lookback times differ in length (a cum_sfh that starts at 0 must come with max_logAge)")
+    knots = cum / cum.max()                                                                                # :330
+    for i in range(1, knots.shape[0]):                                                                     # :332
+        if knots[i] <= knots[i - 1]:
+            knots[i] = np.nextafter(knots[i - 1], np.inf)
+    t = 10.0 ** la / 1e9                                                                                   # :333
+
+    def itp(frac):
+        f = np.asarray(frac, dtype=np.float64)
+        if np.any(f < knots[0]) or np.any(f > knots[-1]) or np.any(np.isnan(f)):
+            raise ValueError(f"tau = {frac} outside the interpolation range [{knots[0]}, {knots[-1]}]")
+        out = np.interp(f, knots, t)
+        return float(out) if out.ndim == 0 else out
+
+    itp.knots, itp.values = knots, t
+    return itp
+
+
+def tau(*args, Nsamples=10_000, q=(0.16, 0.5, 0.84), rng=None, **kws):
+    """tau (fitting/utilities.jl:416-468), the reference's three methods:
+
+    ``tau(τ, unique_logAge, max_logAge, cum_sfh)``                 lookback time [Gyr] at which the fraction τ of the mass had formed
+    ``tau(τ, unique_logAge, max_logAge, cum_sfh, lower, upper)``   (length(τ), 3): columns lower / best / upper                   :420-430
+    ``tau(result, τ, logAge, MH, max_logAge; Nsamples, q, kws...)`` the same from `cum_sfr_quantiles` of a fit_sfh result          :456-468
+    """
+    if len(args) == 4:
+        frac, ula, max_logAge, cum = args
+        return tau_interp(ula, max_logAge, cum)(frac)
+    if len(args) == 6:
+        frac, ula, max_logAge, cum, lower, upper = args
+        cols = [np.atleast_1d(tau_interp(ula, max_logAge, c)(frac)) for c in (lower, cum, upper)]
+        return np.stack(cols, axis=1)
+    if len(args) == 5:
+        result, frac, logAge, MH, max_logAge = args
+        if len(q) != 3:
+            raise ValueError("q must be a tuple of three quantiles (e.g., (0.16, 0.5, 0.84))")            # :457
+        out = cum_sfr_quantiles(result, logAge, MH, 10.0 ** max_logAge / 1e9, Nsamples, q, rng=rng, **kws)
+        cm = out["cum_sfh"]
+        return tau(frac, np.unique(np.asarray(logAge, dtype=np.float64)), max_logAge, cm[:, 1], cm[:, 0], cm[:, 2])
+    raise TypeError("tau takes (τ, unique_logAge, max_logAge, cum_sfh[, lower, upper]) or (result, τ, logAge, MH, max_logAge)")
+
+
 def fit_sfh(MH_model0, disp_model0, models, data, logAge, metallicities, x0=None, g_abstol=1e-8, iterations=5000, engine="scipy",
             alphaguess=0):
     """BFGS on [log R_j, transformed free parameters]: MAP (Jacobian corrections on) then MLE seeded from it

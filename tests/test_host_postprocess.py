@@ -102,3 +102,57 @@ def test_truncate_relweights():                                   # fixed_amr.jl
     w = np.exp(-0.5 * ((mhs + 2.0) / 0.2) ** 2); w /= w.sum()
     assert np.allclose(w[:5], [0.021919934465195145, 0.2284109622221623, 0.4988954088848224, 0.2284109622221623, 0.021919934465195145])
     assert np.array_equal(S.truncate_relweights(0.1, w, np.full(11, 10.0)), [1, 2, 3])
+
+
+def test_tau_doctests():                                          # fitting/utilities.jl:358-411 (the `tau` doctest block)
+    ula, max_la = [8.0, 8.5, 9.0, 9.5, 10.0], 10.13
+    assert S.tau(0.5, ula, max_la, [1.0, 0.8, 0.5, 0.2, 0.1]) == 1.0                       # :365-366 exact knot
+    cum = [1.0, 0.8, 0.4, 0.2, 0.1]
+    assert S.tau(0.5, ula, max_la, cum) == pytest.approx(0.8290569415042095, rel=1e-14)    # :374
+    assert np.allclose(S.tau([0.5, 0.75], ula, max_la, cum), [0.8290569415042095, 0.40169929526473325], rtol=1e-14)   # :381
+    assert S.tau(0.5, ula[::-1], max_la, cum[::-1]) == pytest.approx(0.8290569415042095, rel=1e-14)                    # :388
+    upper, lower = [1.0, 0.85, 0.6, 0.3, 0.15], [1.0, 0.75, 0.3, 0.1, 0.05]
+    got = S.tau(0.5, ula, max_la, cum, lower, upper)                                                                   # :400
+    assert got.shape == (1, 3) and np.allclose(got, [[0.6961012293408169, 0.8290569415042095, 1.7207592200561264]], rtol=1e-14)
+    got = S.tau([0.5, 0.75], ula, max_la, cum, lower, upper)                                                           # :407
+    assert np.allclose(got, [[0.6961012293408169, 0.8290569415042095, 1.7207592200561264],
+                             [0.31622776601683794, 0.40169929526473325, 0.5897366596101027]], rtol=1e-14)
+
+
+def test_tau_interp_edges():                                      # fitting/utilities.jl:311-336
+    ula, max_la = np.array([8.0, 8.5, 9.0, 9.5, 10.0]), 10.13
+    itp = S.tau_interp(ula, max_la, [1.0, 0.8, 0.4, 0.2, 0.1])
+    assert itp(0.0) == pytest.approx(10 ** 10.13 / 1e9) and itp(1.0) == pytest.approx(0.1)    # no mass at max_logAge; all of it at the youngest bin
+    assert np.all(np.diff(itp.knots) > 0) and itp.knots[-1] == 1.0                            # :330 normalised to its maximum
+    assert np.allclose(S.tau_interp(ula, max_la, 7.0 * np.array([1.0, 0.8, 0.4, 0.2, 0.1]))([0.3, 0.9]), itp([0.3, 0.9]), rtol=1e-14)
+    for bad in (-0.1, 1.0001, np.nan):                                                        # Gridded(Linear()) throws outside its knots
+        with pytest.raises(ValueError):
+            itp(bad)
+    # equal cumulative values (bins that formed no mass) are separated by one ulp each (:332), so the interpolant stays defined
+    flat = S.tau_interp(ula, max_la, [1.0, 0.5, 0.5, 0.5, 0.1])
+    assert np.all(np.diff(flat.knots) > 0) and flat.knots[3] == np.nextafter(0.5, 1) and flat.knots[4] == np.nextafter(np.nextafter(0.5, 1), 1)
+    assert flat(0.3) == pytest.approx(np.interp(0.3, [0.1, 0.5], [10.0, 10 ** 0.5]))
+    with pytest.raises(ValueError):                                                           # :312
+        S.tau_interp(ula, max_la, [1.0, 0.5])
+    with pytest.raises(ValueError):                                                           # :313
+        S.tau_interp(ula, 10.0, [1.0, 0.8, 0.4, 0.2, 0.1])
+    with pytest.raises(ValueError):                                                           # :319
+        S.tau_interp(ula, max_la, [1.0, 0.3, 0.4, 0.2, 0.1])
+    with pytest.raises(ValueError):                                                           # :320 ages not in the order of cum_sfh
+        S.tau_interp(ula[::-1], max_la, [1.0, 0.8, 0.4, 0.2, 0.1])
+
+
+def test_tau_from_result():                                       # fitting/utilities.jl:456-468
+    rng = np.random.default_rng(5)
+    nj, nk = 12, 9
+    la = np.repeat(np.linspace(10.0, 8.9, nj), nk)
+    mh = np.tile(np.linspace(-2.0, 0.0, nk), nj)
+    res = _fake_result(nj, rng)
+    t = S.tau({"map": res, "mle": res}, [0.5, 0.9], la, mh, 10.13, Nsamples=300, rng=rng)
+    assert t.shape == (2, 3)
+    # a LOWER cumulative-mass quantile reaches the fraction later (smaller lookback time): columns are ordered old <- young
+    # exactly as the reference's (lower, best, upper) = (q16, q50, q84) of the cumulative SFH
+    assert np.all(t[:, 0] <= t[:, 1]) and np.all(t[:, 1] <= t[:, 2])
+    assert np.all(t[0] >= t[1]) and np.all(t > 10 ** 8.9 / 1e9 - 1e-12) and np.all(t < 10 ** 10.13 / 1e9)
+    with pytest.raises(ValueError):
+        S.tau({"map": res, "mle": res}, 0.5, la, mh, 10.13, Nsamples=10, q=(0.5,), rng=rng)
