@@ -20,7 +20,7 @@ from .sampling import HMCModel, MCMCModel
 from . import io, sharding, solvers
 from .io import SFHFile, load_result, read_arrays, save_result, write_arrays
 from .solvers import (calculate_cum_sfr, construct_x0, construct_x0_mdf, cum_sfr_quantiles, fixed_amr, truncate_relweights, fit_sfh, fit_templates, fit_templates_fast, fit_templates_lbfgsb,
-                      hmc_sample, mcmc_sample, mdf_amr, rand_result, renormalize_x0, sample_sfh, tau, tau_interp, tsample_sfh)
+                      hmc_sample, mcmc_sample, mdf_amr, rand_result, renormalize_x0, result_median, result_mode, result_std, sample_sfh, tau, tau_interp, tsample_sfh)
 from . import templates
 from .templates import bin_cmd, bin_cmd_smooth, build_template_stack, partial_cmd, partial_cmd_smooth, template_points
 from .sharding import allreduce_fg, guard_neg_logl, init_library_comm, shard_rows
@@ -42,6 +42,6 @@ __all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite
            "LogarithmicAMR", "GaussianDispersion", "HierarchicalOptimizer", "HMCModel", "MCMCModel", "nparams",
            "exptransform", "logtransform", "clear_cache", "device_stack", "shard_rows", "allreduce_fg", "guard_neg_logl",
            "init_library_comm", "fit_templates_lbfgsb", "fit_templates", "fit_templates_fast", "fit_sfh", "mcmc_sample",
-           "hmc_sample", "renormalize_x0", "mdf_amr", "calculate_cum_sfr", "cum_sfr_quantiles", "tau", "tau_interp", "rand_result", "construct_x0", "bin_cmd_smooth", "partial_cmd_smooth", "build_template_stack",
+           "hmc_sample", "renormalize_x0", "mdf_amr", "calculate_cum_sfr", "cum_sfr_quantiles", "tau", "tau_interp", "rand_result", "result_mode", "result_median", "result_std", "construct_x0", "bin_cmd_smooth", "partial_cmd_smooth", "build_template_stack",
            "template_points", "templates", "sample_sfh", "tsample_sfh", "fixed_amr", "truncate_relweights", "construct_x0_mdf", "bin_cmd", "partial_cmd",
            "MH_from_Z", "dMH_dZ", "Z_from_MH", "dZ_dMH", "X_from_Z", "Y_from_Z", "io", "SFHFile", "write_arrays", "read_arrays", "save_result", "load_result"]

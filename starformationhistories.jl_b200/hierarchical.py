@@ -244,13 +244,20 @@ def _bind(ds: DeviceStack, logAge, MH):
     return ctx
 
 
-def calculate_coeffs(MHmodel, dispmodel, mstars, logAge, metallicities, models=None):
-    """``calculate_coeffs(MHmodel, dispmodel, R, logAge, MH)`` (mzr.jl:50-79 / amr.jl:50-73).
+def calculate_coeffs(MHmodel, dispmodel, mstars, logAge=None, metallicities=None, models=None):
+    """``calculate_coeffs(MHmodel, dispmodel, R, logAge, MH)`` (mzr.jl:50-79 / amr.jl:50-73), and the three-argument method
+    ``calculate_coeffs(result, logAge, MH)`` for a fit_sfh result (bfgs_result.jl:81-90).
 
     With ``models`` (a DeviceStack) the expansion runs through the device prologue kernel that every
     hierarchical evaluation uses.  Without it -- the reference signature has no stack argument, and this
     form is only used for one-shot set-up such as building x0 -- the same O(T) formulae are evaluated
     on the host in float64."""
+    if logAge is None and metallicities is None:
+        # calculate_coeffs(result, logAge, MH) (bfgs_result.jl:81-90, 151-154): best-fit models and stellar masses of a
+        # fit_sfh result; the MLE of a {"map", "mle"} pair (CompositeBFGSResult)
+        res = MHmodel["mle"] if isinstance(MHmodel, dict) else MHmodel
+        nj = res.mu.shape[0] - res.MH_model.nparams() - res.disp_model.nparams()
+        return calculate_coeffs(res.MH_model, res.disp_model, res.mu[:nj], dispmodel, mstars, models=models)
     la = np.asarray(logAge, dtype=np.float64)
     mh = np.asarray(metallicities, dtype=np.float64)
     R = np.asarray(mstars, dtype=np.float64)

@@ -293,6 +293,18 @@ class BFGSResult:
     MH_model: object = None
     disp_model: object = None
 
+    def __len__(self):          # bfgs_result.jl:38
+        return self.mu.shape[0]
+
+    def mode(self):             # :39
+        return self.mu
+
+    def median(self):           # :40
+        return self.mu
+
+    def std(self):              # :41
+        return self.sigma
+
     def rand(self, rng, n, invH=None):
         """`rand(result, N)` (bfgs_result.jl:43-75): draws from MvNormal(minimizer, invH) in the fitting space, transformed
         back to natural units; fixed parameters are written in at their values.  Returns (length(mu), n)."""
@@ -319,6 +331,20 @@ def rand_result(result, rng, n):
     if isinstance(result, dict):
         return result["mle"].rand(rng, n, invH=result["map"].invH)
     return result.rand(rng, n)
+
+
+def result_mode(result):
+    """`mode` / `median` of a BFGSResult or of the {"map", "mle"} pair (CompositeBFGSResult: the MLE, bfgs_result.jl:39-40,109-110)."""
+    return (result["mle"] if isinstance(result, dict) else result).mu
+
+
+result_median = result_mode
+
+
+def result_std(result):
+    """`std` (bfgs_result.jl:41,111): the standard errors -- of the MAP for the {"map", "mle"} pair, whose inverse Hessian is the
+    better conditioned one."""
+    return (result["map"] if isinstance(result, dict) else result).sigma
 
 
 def construct_x0(logAge, T_max, normalize_value=1.0):

@@ -156,3 +156,20 @@ def test_tau_from_result():                                       # fitting/util
     assert np.all(t[0] >= t[1]) and np.all(t > 10 ** 8.9 / 1e9 - 1e-12) and np.all(t < 10 ** 10.13 / 1e9)
     with pytest.raises(ValueError):
         S.tau({"map": res, "mle": res}, 0.5, la, mh, 10.13, Nsamples=10, q=(0.5,), rng=rng)
+
+
+def test_result_accessors_and_calculate_coeffs_from_result():     # bfgs_result.jl:38-41, 81-90, 108-111, 151-154
+    rng = np.random.default_rng(11)
+    nj, nk = 7, 5
+    la = np.repeat(np.linspace(10.0, 8.8, nj), nk)
+    mh = np.tile(np.linspace(-2.0, 0.0, nk), nj)
+    mle, mp = _fake_result(nj, rng), _fake_result(nj, rng)
+    assert len(mle) == nj + 3 and mle.mode() is mle.mu and mle.median() is mle.mu and mle.std() is mle.sigma
+    pair = {"map": mp, "mle": mle}
+    assert S.result_mode(pair) is mle.mu and S.result_median(pair) is mle.mu and S.result_std(pair) is mp.sigma
+    assert S.result_mode(mle) is mle.mu and S.result_std(mle) is mle.sigma
+    want = S.calculate_coeffs(mle.MH_model, mle.disp_model, mle.mu[:nj], la, mh)
+    assert np.array_equal(S.calculate_coeffs(mle, la, mh), want)
+    assert np.array_equal(S.calculate_coeffs(pair, la, mh), want)          # the MLE of a CompositeBFGSResult
+    got = S.calculate_coeffs(mle, la, mh).reshape(nj, nk).sum(axis=1)      # mzr_test.jl:32-34: the masses are conserved per age
+    assert np.allclose(got, mle.mu[:nj], rtol=1e-13)
