@@ -187,7 +187,21 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
                          HessianBackend *hb = nullptr) {
     using namespace detail;
     std::vector<double> g((size_t)n), gn((size_t)n), xn((size_t)n), p((size_t)n), s((size_t)n), y((size_t)n), Hy((size_t)n);
+    // Host matrix: the rank-two update of one iteration is DEFERRED and applied column by column inside the next iteration's
+    // q = H g pass (the column is updated, then dotted while it is still in cache): one read + write of the n x n matrix per
+    // iteration instead of a read (product) plus a read + write (update).  Same expressions per column, same dot: identical bits.
+    bool pending = false;
+    double p_rho = 0, p_cs = 0;
+    std::vector<double> ps, pHy;
+    auto apply_pending = [&](int64_t j0, int64_t j1) {
+        for (int64_t j = j0; j < j1; ++j) {
+            double *col = invH + j * n;
+            const double a = p_cs * ps[(size_t)j] - p_rho * pHy[(size_t)j], b = -p_rho * ps[(size_t)j];
+            for (int64_t i = 0; i < n; ++i) col[i] += a * ps[(size_t)i] + b * pHy[(size_t)i];
+        }
+    };
     auto identity = [&]() -> int {
+        pending = false;   // the matrix is being replaced: whatever was still to be added to it is void
         if (hb) return hb->reset_identity();
         for (int64_t j = 0; j < n; ++j) {
             double *col = invH + j * n;
@@ -198,6 +212,7 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
     };
     auto finish = [&](const BfgsReport &rr) -> int {
         *rep = rr;
+        if (pending) { for_columns(n, apply_pending); pending = false; }
         return (hb && invH) ? hb->download(invH) : 0;
     };
     if (int e = identity()) return e;
@@ -209,7 +224,7 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
     r.f = f; r.g_norm = infnorm(g.data(), n);
     if (!std::isfinite(f) || !std::isfinite(r.g_norm)) { r.status = 3; return finish(r); }
     double f_prev = f + std::sqrt(dot(g.data(), g.data(), n)) / 2.0;
-    // Two passes over the n x n matrix per iteration instead of three: q = H g_new (one read) gives both H y = q + p_old
+    // One product with the n x n matrix per iteration instead of two: q = H g_new (one read) gives both H y = q + p_old
     // (p_old = -H g_old) and, after the rank-two update (one read + write), the next direction algebraically:
     //   -p_new = H_new g_new = q - rho (s (Hy.g) + Hy (s.g)) + (rho^2 y'Hy + rho) s (s.g)
     for (int64_t j = 0; j < n; ++j) p[(size_t)j] = -g[(size_t)j];   // H = I
@@ -248,8 +263,12 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
             if (int e = hb->matvec(g.data(), q.data())) return e;
         } else {
             for_columns(n, [&](int64_t j0, int64_t j1) {
-                for (int64_t j = j0; j < j1; ++j) q[(size_t)j] = dot(invH + j * n, g.data(), n);   // H symmetric: column j = row j
+                for (int64_t j = j0; j < j1; ++j) {
+                    if (pending) apply_pending(j, j + 1);
+                    q[(size_t)j] = dot(invH + j * n, g.data(), n);   // H symmetric: column j = row j
+                }
             });
+            pending = false;
         }
         const double ys = dot(y.data(), s.data(), n);
         if (!(ys > 0)) {      // curvature condition violated (cannot happen with a Wolfe step up to rounding): skip the update
@@ -264,13 +283,8 @@ inline int bfgs_minimize(const Objective &fn, int64_t n, double *x, const BfgsOp
         if (hb) {
             if (int e = hb->rank2(s.data(), Hy.data(), rho, cs)) return e;
         } else {
-            for_columns(n, [&](int64_t j0, int64_t j1) {
-                for (int64_t j = j0; j < j1; ++j) {
-                    double *col = invH + j * n;
-                    const double a = cs * s[(size_t)j] - rho * Hy[(size_t)j], b = -rho * s[(size_t)j];
-                    for (int64_t i = 0; i < n; ++i) col[i] += a * s[(size_t)i] + b * Hy[(size_t)i];
-                }
-            });
+            ps = s; pHy = Hy; p_rho = rho; p_cs = cs;   // applied by the next q = H g pass, or by finish()
+            pending = true;
         }
         for (int64_t j = 0; j < n; ++j) p[(size_t)j] += rho * (s[(size_t)j] * Hyg + Hy[(size_t)j] * sg) - cs * s[(size_t)j] * sg;
     }
