@@ -263,8 +263,9 @@ def calculate_coeffs(MHmodel, dispmodel, mstars, logAge=None, metallicities=None
     R = np.asarray(mstars, dtype=np.float64)
     if la.shape != mh.shape:
         raise ValueError("length(logAge) != length(metallicities)")        # mzr.jl:57
-    _, first = np.unique(la, return_index=True)
-    uniq = la[np.sort(first)]
+    _, first, inv = np.unique(la, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")                               # unique(logAge): first-appearance order (mzr.jl:54)
+    uniq = la[first[order]]
     if R.shape[0] != uniq.shape[0]:
         raise ValueError("Length of `mstars` must be the same as `unique(logAge)`.")   # mzr.jl:55-56
     if models is not None:
@@ -282,12 +283,12 @@ def calculate_coeffs(MHmodel, dispmodel, mstars, logAge=None, metallicities=None
         mu = np.array([MHmodel(c) for c in cum])
     else:
         mu = np.array([MHmodel(a) for a in uniq])
-    coeffs = np.empty(la.shape[0])
-    for j, a in enumerate(uniq):
-        idx = np.nonzero(la == a)[0]
-        A = np.exp(-(((mh[idx] - mu[j]) / dispmodel.sigma) ** 2) / 2)
-        coeffs[idx] = A * R[j] / A.sum()                                   # mzr.jl:76
-    return coeffs
+    rank = np.empty(order.shape[0], dtype=np.int64)
+    rank[order] = np.arange(order.shape[0])
+    jidx = rank[inv.reshape(-1)]                                           # template -> its age's position in unique(logAge)  (:71)
+    A = np.exp(-(((mh - mu[jidx]) / dispmodel.sigma) ** 2) / 2)            # :73
+    Asum = np.bincount(jidx, weights=A, minlength=uniq.shape[0])
+    return A * R[jidx] / Asum[jidx]                                        # :74-76
 
 
 def fg_(F, G, MHmodel0, dispmodel0, variables, models, data, composite, logAge, metallicities):
