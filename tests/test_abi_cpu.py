@@ -216,3 +216,71 @@ def test_julia_struct_mirrors_match_header():
         assert m, f"{jname} not found in SFHCuda.jl"
         fields = re.findall(r"(\w+)::(\w+)", m.group(1))
         assert [(n, jl_types[t]) for n, t in fields] == [(f[0], f[1]) for f in cls._fields_], jname
+
+
+def _strip_julia(s):
+    """Julia source without comments and string contents (enough for structural checks)."""
+    out, i, n = [], 0, len(s)
+    while i < n:
+        if s.startswith("#=", i):
+            i = s.index("=#", i) + 2
+        elif s[i] == "#":
+            j = s.find("\n", i)
+            i = n if j < 0 else j
+        elif s.startswith('"""', i):
+            i = s.index('"""', i + 3) + 3
+            out.append('""')
+        elif s[i] == '"':
+            j = i + 1
+            while s[j] != '"':
+                j += 2 if s[j] == "\\" else 1
+            i = j + 1
+            out.append('""')
+        else:
+            out.append(s[i])
+            i += 1
+    return "".join(out)
+
+
+def _split_top(s):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        depth += ch in "({["
+        depth -= ch in ")}]"
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur)
+    return parts
+
+
+def test_julia_binding_structure_and_ccalls_match_header():
+    """julia/SFHCuda.jl is the drop-in binding itself and cannot run here: every `ccall` must name a symbol the header declares,
+    with as many argument types as the C prototype has parameters; brackets and `function/struct/module/do ... end` blocks balance."""
+    code = _strip_julia(open(os.path.join(PKG, "julia", "SFHCuda.jl")).read())
+    for o, c in ("()", "[]", "{}"):
+        assert code.count(o) == code.count(c), (o, code.count(o), code.count(c))
+    openers = re.findall(r"(?<![\w.:@])(function|struct|if|while|let|do|begin|module|try|quote|macro)(?![\w!])", code)
+    block_for = re.findall(r"^\s*for\b", code, flags=re.M)          # a `for` that starts a line is a loop; the others are generators
+    ends = re.findall(r"(?<![\w.:@\[])end(?![\w!])", code)
+    assert len(openers) + len(block_for) == len(ends), (len(openers), len(block_for), len(ends))
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    nparams = {}
+    for m in re.finditer(r"\b(sfh_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        nparams[m.group(1)] = 0 if args in ("void", "") else len(_split_top(args))
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(\w+),\s*libsfh\),\s*[\w{}]+,\s*\(", code):
+        name, i, depth = m.group(1), m.end(), 1
+        j = i
+        while depth:
+            depth += code[j] == "("
+            depth -= code[j] == ")"
+            j += 1
+        assert name in nparams, f"ccall of {name}: not declared in sfhcuda.h"
+        assert len(_split_top(code[i:j - 1])) == nparams[name], f"ccall of {name}: {len(_split_top(code[i:j - 1]))} argument types, C prototype has {nparams[name]}"
+        seen += 1
+    assert seen >= 20 and seen == len(re.findall(r"ccall\(", code))
