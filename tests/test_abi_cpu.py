@@ -268,10 +268,28 @@ def test_julia_binding_structure_and_ccalls_match_header():
     ends = re.findall(r"(?<![\w.:@\[])end(?![\w!])", code)
     assert len(openers) + len(block_for) == len(ends), (len(openers), len(block_for), len(ends))
     hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
-    nparams = {}
+
+    def c_class(param):            # pointer / 32-bit / 64-bit / double: what the calling convention distinguishes
+        param = param.strip()
+        if "*" in param or "(" in param:
+            return "ptr"
+        t = re.sub(r"\b\w+$", "", param).replace("const", "").strip() if re.search(r"\s", param) else param
+        return {"int": "i32", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "size_t": "u64",
+                "double": "f64"}.get(t, "i32" if t.startswith("sfh_") else "?" + t)      # sfh_* by value: enums
+
+    def j_class(t):
+        t = t.strip()
+        if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+            return "ptr"
+        return {"Cint": "i32", "Int32": "i32", "UInt32": "u32", "Int64": "i64", "UInt64": "u64", "Csize_t": "u64",
+                "Float64": "f64", "Cdouble": "f64"}.get(t, "?" + t)
+
+    nparams, classes = {}, {}
     for m in re.finditer(r"\b(sfh_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
         args = m.group(2).strip()
-        nparams[m.group(1)] = 0 if args in ("void", "") else len(_split_top(args))
+        plist = [] if args in ("void", "") else _split_top(args)
+        nparams[m.group(1)] = len(plist)
+        classes[m.group(1)] = [c_class(a) for a in plist]
     seen = 0
     for m in re.finditer(r"ccall\(\(:(\w+),\s*libsfh\),\s*[\w{}]+,\s*\(", code):
         name, i, depth = m.group(1), m.end(), 1
@@ -282,5 +300,7 @@ def test_julia_binding_structure_and_ccalls_match_header():
             j += 1
         assert name in nparams, f"ccall of {name}: not declared in sfhcuda.h"
         assert len(_split_top(code[i:j - 1])) == nparams[name], f"ccall of {name}: {len(_split_top(code[i:j - 1]))} argument types, C prototype has {nparams[name]}"
+        jt = [j_class(t) for t in _split_top(code[i:j - 1])]
+        assert jt == classes[name], f"ccall of {name}: argument classes {jt}, C prototype {classes[name]}"
         seen += 1
     assert seen >= 20 and seen == len(re.findall(r"ccall\(", code))
