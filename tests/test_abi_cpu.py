@@ -275,7 +275,7 @@ def test_julia_binding_structure_and_ccalls_match_header():
             return "ptr"
         t = re.sub(r"\b\w+$", "", param).replace("const", "").strip() if re.search(r"\s", param) else param
         return {"int": "i32", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "size_t": "u64",
-                "double": "f64"}.get(t, "i32" if t.startswith("sfh_") else "?" + t)      # sfh_* by value: enums
+                "double": "f64"}.get(t, "ptr" if t.endswith("_fn") else ("i32" if t.startswith("sfh_") else "?" + t))      # sfh_* by value: enums
 
     def j_class(t):
         t = t.strip()
@@ -304,3 +304,39 @@ def test_julia_binding_structure_and_ccalls_match_header():
         assert jt == classes[name], f"ccall of {name}: argument classes {jt}, C prototype {classes[name]}"
         seen += 1
     assert seen >= 20 and seen == len(re.findall(r"ccall\(", code))
+
+
+def test_ctypes_prototypes_match_header_parameter_classes():
+    """Every ctypes prototype in _lib.py has as many parameters as the C declaration and the same class per parameter
+    (pointer / 32-bit / 64-bit integer / double) -- a c_int where the header says int64_t would truncate silently."""
+    import sfh_b200
+    L = sfh_b200._lib
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+
+    def c_class(param):
+        param = param.strip()
+        if "*" in param or "(" in param:
+            return "ptr"
+        t = re.sub(r"\b\w+$", "", param).replace("const", "").strip() if re.search(r"\s", param) else param
+        return {"int": "i32", "int32_t": "i32", "uint32_t": "i32", "int64_t": "i64", "uint64_t": "i64", "size_t": "i64",
+                "double": "f64"}.get(t, "ptr" if t.endswith("_fn") else ("i32" if t.startswith("sfh_") else "?" + t))
+
+    def py_class(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or hasattr(t, "_flags_") and issubclass(t, C._CFuncPtr):
+            return "ptr"
+        if issubclass(t, C._Pointer):
+            return "ptr"
+        return {C.c_int: "i32", C.c_int32: "i32", C.c_uint32: "i32", C.c_int64: "i64", C.c_uint64: "i64", C.c_size_t: "i64",
+                C.c_double: "f64"}.get(t, "?" + getattr(t, "__name__", str(t)))
+
+    checked = 0
+    for m in re.finditer(r"\b([\w\s\*]+?)\b(sfh_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, args = m.group(2), m.group(3).strip()
+        want = [] if args in ("void", "") else [c_class(a) for a in _split_top(args)]
+        res, argtypes = L.PROTOTYPES[name]
+        got = [py_class(t) for t in argtypes]
+        assert got == want, f"{name}: ctypes {got}, header {want}"
+        ret = m.group(1).strip()
+        assert (res is C.c_char_p) == ("char" in ret) and (res is L._int or "char" in ret or res is C.c_int), (name, ret, res)
+        checked += 1
+    assert checked == len(L.PROTOTYPES)
