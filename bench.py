@@ -9,7 +9,8 @@ Hess diagram, [logL, G] all-reduced with NCCL on the kernel's stream every step 
   value       evaluations/s with everything resident in HBM, timed with CUDA events on the launching stream
   e2e         same through the reference-facing C-ABI call sfh_eval_fg with HOST buffers (H2D coeffs, D2H [-logL, G])
   roofline    algorithmic bytes of the fused kernel / its event-timed duration, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the oracle's threaded two-pass port of the reference algorithm on this box's host cores
+  cpu_baseline  the faster of the oracle's two threaded two-pass ports of the reference algorithm (BLAS gemv route / OpenMP nest)
+                on this box's host cores
 
   --impl reference : the reference arm = that same CPU port, all host threads, on the same config.
 """
@@ -116,44 +117,70 @@ def host_stack(nb, nt, x, seed=SEED):
     return M, data
 
 
-def time_cpu(M, data, x, budget_s=12.0, min_steps=3, max_steps=200):
+def cpu_routes(M, data, x):
+    """The two CPU restatements of the reference's flat fg!, both on all host threads:
+    'blas'   -- the route Julia takes: gemv 'N' / Poisson + residual loops / gemv 'T' through OpenBLAS (oracle.fg_blas);
+    'openmp' -- the oracle's own two-pass loop nest, no BLAS (oracle.fg_omp).  The FASTER one is the reported baseline."""
     import oracle as O
     G = np.empty(M.shape[1]); Cm = np.empty(M.shape[0])
-    O.fg_omp(x, M, data, G=G, Cm=Cm)        # warm-up (page-in)
-    ts = []
-    t_end = time.perf_counter() + budget_s
-    while (len(ts) < min_steps or time.perf_counter() < t_end) and len(ts) < max_steps:
-        t0 = time.perf_counter()
-        O.fg_omp(x, M, data, G=G, Cm=Cm)
-        ts.append(time.perf_counter() - t0)
-    return float(np.median(ts)), len(ts), O.num_threads()
+    return {"blas": (lambda: O.fg_blas(x, M, data), O.blas_threads()),
+            "openmp": (lambda: O.fg_omp(x, M, data, G=G, Cm=Cm), O.num_threads())}
+
+
+def time_cpu(M, data, x, budget_s=12.0, min_steps=3, max_steps=200):
+    """cpu_baseline leg: median evaluation time of each route inside half the budget; returns the faster one."""
+    out = {}
+    for name, (fn, threads) in cpu_routes(M, data, x).items():
+        fn()                                    # warm-up (page-in)
+        ts = []
+        t_end = time.perf_counter() + budget_s / 2
+        while (len(ts) < min_steps or time.perf_counter() < t_end) and len(ts) < max_steps:
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        out[name] = (float(np.median(ts)), len(ts), threads)
+    best = min(out, key=lambda k: out[k][0])
+    return best, out
+
+
+CPU_ROUTE_TEXT = {"blas": "gemv 'N' / Poisson + residual loops / gemv 'T' through numpy's OpenBLAS, the route Julia's mul! takes",
+                  "openmp": "the oracle's OpenMP two-pass loop nest, no BLAS"}
 
 
 def run_reference(args, real_stdout):
     """--impl reference: the reference's algorithm (two-pass gemv 'N' / Poisson / residual / gemv 'T') on the host
-    cores.  Julia cannot run in this image, so this is the oracle PORT (cpu_baseline.kind = "port")."""
+    cores.  Julia cannot run in this image, so this is the oracle PORT (cpu_baseline.kind = "port"): both restatements are
+    warmed up and given a short trial; the faster one runs the timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle as O
     x = truth_coeffs() * 1.02
     M, data = host_stack(NB, NT, x)
-    G = np.empty(NT); Cm = np.empty(NB)
-    for _ in range(max(args.warmup, 1)):
-        O.fg_omp(x, M, data, G=G, Cm=Cm)
+    routes = cpu_routes(M, data, x)
+    trial = {}
+    for name, (fn, _) in routes.items():
+        for _ in range(max(args.warmup, 1)):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        trial[name] = (time.perf_counter() - t0) / 3
+    best = min(trial, key=trial.get)
+    fn, cores = routes[best]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.fg_omp(x, M, data, G=G, Cm=Cm)
+        fn()
     dt = time.perf_counter() - t0
     v = args.steps / dt
-    cores = O.num_threads()
+    other = [k for k in routes if k != best][0]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: one full-size stack on rank 0, host cores only"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} full evaluations of the 60000x2400 F64 stack (OpenMP two-pass port of "
-                                       f"fitting_base.jl:55-65,84-96,265-285; julia not installed)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "route": best,
+                             "sample": f"{args.steps} full evaluations of the 60000x2400 F64 stack; port of fitting_base.jl:55-65,84-96,"
+                                       f"265-285 (julia not installed): {CPU_ROUTE_TEXT[best]}; the slower restatement "
+                                       f"({other}: {CPU_ROUTE_TEXT[other]}) ran at {1.0 / trial[other]:.1f} evals/s in a 3-step trial"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=real_stdout, flush=True)
     return 0
@@ -295,10 +322,14 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Mh, dh = ds.download()
-        t_med, n_cpu, cores = time_cpu(Mh, dh, x)
-        cpu = {"value": 1.0 / t_med, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} full evaluations of the same 60000x2400 F64 stack (downloaded from the GPU), median; "
-                         "OpenMP two-pass port of the reference's gemv'N'/Poisson/residual/gemv'T' (julia not installed)"}
+        Mh = np.asfortranarray(Mh)
+        best, routes = time_cpu(Mh, dh, x)
+        t_med, n_cpu, cores = routes[best]
+        other = [k for k in routes if k != best][0]
+        cpu = {"value": 1.0 / t_med, "unit": UNIT, "cores": cores, "kind": "port", "route": best,
+               "sample": f"{n_cpu} full evaluations of the same 60000x2400 F64 stack (downloaded from the GPU), median; port of the "
+                         f"reference's two-pass fg! (julia not installed): {CPU_ROUTE_TEXT[best]}; the slower restatement ({other}: "
+                         f"{CPU_ROUTE_TEXT[other]}) reached {1.0 / routes[other][0]:.1f} evals/s"}
         del Mh
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -210,6 +210,35 @@ def fg_omp(coeffs, M, data, dtype=np.float64, G=None, Cm=None):
     return r, G
 
 
+def fg_blas(coeffs, M, data, dtype=np.float64):
+    """The reference's flat fg! by the route Julia itself takes: `mul!(C, M, coeffs)` and `mul!(G, M', C, -1, false)`
+    (fitting_base.jl:60, :283) are BLAS gemv 'N' / 'T' calls into OpenBLAS -- here the OpenBLAS bundled with numpy, all its
+    threads -- with the Poisson term (:84-96) and the residual (:274-280) as vectorised loops in between; fg! flips the sign
+    (solvers.jl:28-31).  The second CPU baseline bench.py times ("B1"); M must be Fortran-ordered in
+    `dtype`.  Returns (-logL, G)."""
+    dt = np.dtype(dtype).type
+    assert M.flags.f_contiguous and M.dtype == dt
+    eps = dt(np.finfo(dt).eps)
+    c = np.ascontiguousarray(coeffs, dtype=dt)
+    d = np.ascontiguousarray(data, dtype=dt)
+    m = M @ c                                                              # gemv 'N'
+    np.maximum(m, eps, out=m)                                              # :90 / :277
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = d / m
+        logl = np.where(d > 0, d - m - d * np.log(q), -m).sum(dtype=dt)    # :92 (accumulates in T like the reference, :87)
+    r = dt(1) - q                                                          # :279
+    G = r @ M                                                              # gemv 'T' (columns of M are contiguous)
+    return (float(-logl) if logl != 0 else float("inf")), G
+
+
+def blas_threads() -> int:
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(i["num_threads"]) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def num_threads() -> int:
     return int(lib().sfho_num_threads())
 

@@ -93,6 +93,9 @@ def test_oracle_identities(p):
     # the all-host-threads variant (the bench's cpu_baseline) agrees with the scalar one
     fo, Go = O.fg_omp(x, M, data)[:2]
     assert abs(fo - f) <= tol and np.all(np.abs(Go - G) <= 1e-12 * scale)
+    # ... and so does the BLAS route (gemv 'N' / loops / gemv 'T' through OpenBLAS: what Julia's mul! calls), the other baseline
+    fb, Gb = O.fg_blas(x, M, data)
+    assert (abs(fb - f) <= tol or fb == f) and np.all(np.abs(Gb - G) <= 1e-12 * scale)
 
 
 def test_mcmc_mask_and_hmc_adapter_properties():                  # mcmc_sample.jl:12-23 ; hmc_sample.jl:24-37
