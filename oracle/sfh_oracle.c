@@ -232,7 +232,15 @@ double sfho_fg_omp_##SUF(REAL *G, const REAL *coeffs, const REAL *M, const REAL 
     for (int64_t b = 0; b < nblk; ++b) {                                                           \
         const int64_t i0 = b * RB, i1 = (i0 + RB < nb) ? i0 + RB : nb;                             \
         for (int64_t i = i0; i < i1; ++i) C[i] = (REAL)0;                                          \
-        for (int64_t k = 0; k < nt; ++k) {                                                         \
+        int64_t k = 0;                                                                             \
+        for (; k + 3 < nt; k += 4) {   /* four columns per sweep of the row block (as a BLAS gemv 'N' kernel does) */ \
+            const REAL c0 = coeffs[k], c1 = coeffs[k + 1], c2 = coeffs[k + 2], c3 = coeffs[k + 3];   \
+            const REAL *m0 = M + k * nb, *m1 = m0 + nb, *m2 = m1 + nb, *m3 = m2 + nb;              \
+            _Pragma("omp simd")                                                                    \
+            for (int64_t i = i0; i < i1; ++i)                                                      \
+                C[i] = ((C[i] + m0[i] * c0) + m1[i] * c1) + (m2[i] * c2 + m3[i] * c3);             \
+        }                                                                                          \
+        for (; k < nt; ++k) {                                                                      \
             const REAL ck = coeffs[k]; const REAL *col = M + k * nb;                               \
             _Pragma("omp simd")                                                                    \
             for (int64_t i = i0; i < i1; ++i) C[i] = col[i] * ck + C[i];                           \
