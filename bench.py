@@ -143,6 +143,24 @@ def time_cpu(M, data, x, budget_s=12.0, min_steps=3, max_steps=200):
     return best, out
 
 
+def time_cpu_one_thread(M, data, x, reps=3):
+    """The BLAS route with OpenBLAS held to ONE thread: the setting of the reference's own benchmark suite
+    (benchmark/benchmarks.jl:5, BLAS.set_num_threads(1)) and of tsample_sfh (generic_fitting.jl:593).  evals/s, or None."""
+    try:
+        from threadpoolctl import threadpool_limits
+        import oracle as O
+        with threadpool_limits(limits=1, user_api="blas"):
+            O.fg_blas(x, M, data)
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                O.fg_blas(x, M, data)
+                ts.append(time.perf_counter() - t0)
+        return 1.0 / float(np.median(ts))
+    except Exception:
+        return None
+
+
 CPU_ROUTE_TEXT = {"blas": "gemv 'N' / Poisson + residual loops / gemv 'T' through numpy's OpenBLAS, the route Julia's mul! takes",
                   "openmp": "the oracle's OpenMP two-pass loop nest, no BLAS"}
 
@@ -178,6 +196,7 @@ def run_reference(args, real_stdout):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: one full-size stack on rank 0, host cores only"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "route": best,
+                             "blas_one_thread": time_cpu_one_thread(M, data, x),
                              "sample": f"{args.steps} full evaluations of the 60000x2400 F64 stack; port of fitting_base.jl:55-65,84-96,"
                                        f"265-285 (julia not installed): {CPU_ROUTE_TEXT[best]}; the slower restatement "
                                        f"({other}: {CPU_ROUTE_TEXT[other]}) ran at {1.0 / trial[other]:.1f} evals/s in a 3-step trial"},
@@ -327,6 +346,7 @@ def main():
         t_med, n_cpu, cores = routes[best]
         other = [k for k in routes if k != best][0]
         cpu = {"value": 1.0 / t_med, "unit": UNIT, "cores": cores, "kind": "port", "route": best,
+               "blas_one_thread": time_cpu_one_thread(Mh, dh, x),
                "sample": f"{n_cpu} full evaluations of the same 60000x2400 F64 stack (downloaded from the GPU), median; port of the "
                          f"reference's two-pass fg! (julia not installed): {CPU_ROUTE_TEXT[best]}; the slower restatement ({other}: "
                          f"{CPU_ROUTE_TEXT[other]}) reached {1.0 / routes[other][0]:.1f} evals/s"}

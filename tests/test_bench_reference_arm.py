@@ -32,6 +32,8 @@ def test_reference_arm_json_line():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["route"] in ("blas", "openmp") and c["value"] == d["value"] and c["unit"] == d["unit"]
     assert 1 <= c["cores"] <= (os.cpu_count() or 1) and "60000x2400" in c["sample"] and "slower restatement" in c["sample"]
+    one = c["blas_one_thread"]                 # the reference benchmark suite's own setting (benchmark/benchmarks.jl:5)
+    assert one is None or 0 < one <= 1.5 * d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
