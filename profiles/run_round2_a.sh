@@ -10,6 +10,9 @@ $T 240 python -m pytest tests/test_zz_gpu_nuts.py tests/test_zz_gpu_native.py te
 $T 200 python profiles/bench_nuts.py 2>&1 | tee gpurun_out/r2a_nuts.txt
 $T 100 python profiles/bench_native.py 2>&1 | tee gpurun_out/r2a_native.txt
 $T 240 python bench.py --steps 2000 --warmup 10 2> gpurun_out/r2a_bench.err | tee gpurun_out/r2a_bench.json
+# the CPU arm now times both restatements of the reference's fg! (OpenBLAS gemv route / OpenMP nest) and the one-thread BLAS setting:
+# the box's 16 host cores have only ever been measured with the (then slower) OpenMP nest
+$T 120 python bench.py --impl reference --steps 100 --warmup 3 2> gpurun_out/r2a_bench_reference.err | tee gpurun_out/r2a_bench_reference.json
 # fit_templates at 2400 templates: host-resident vs device-resident inverse Hessian (the host BFGS update is ~17 ms per iteration
 # there).  Its three kernels are plain grid-stride loops (no barriers): parity first (tests/experimental_gpu_pipe.py -k hessian).
 $T 120 python -m pytest tests/experimental_gpu_pipe.py -m gpu -q -k "hessian" 2>&1 | tail -15 | tee gpurun_out/r2a_device_hessian_tests.log
