@@ -173,3 +173,14 @@ def test_result_accessors_and_calculate_coeffs_from_result():     # bfgs_result.
     assert np.array_equal(S.calculate_coeffs(pair, la, mh), want)          # the MLE of a CompositeBFGSResult
     got = S.calculate_coeffs(mle, la, mh).reshape(nj, nk).sum(axis=1)      # mzr_test.jl:32-34: the masses are conserved per age
     assert np.allclose(got, mle.mu[:nj], rtol=1e-13)
+
+
+def test_transformations_and_nparams_doctests():                 # transformations.jl:13-16, :39-42 ; hierarchical_models.jl:12-15
+    import math
+    assert np.allclose(S.logtransform((0.5, -1.0, 1.0), (1, 0, 1)), [math.log(0.5), -1.0, 0.0], rtol=0, atol=0)
+    assert np.allclose(S.exptransform((math.log(0.5), -1.0, 0.0), (1, 0, 1)), [0.5, -1.0, 1.0], rtol=1e-16)
+    # the -1 branch (x' = log(-x), inverse -exp(x'); transformations.jl:24-25, :50-51) and the round trip
+    p, tf = np.array([0.3, -2.5, -0.7, 4.0]), np.array([1, 0, -1, 1])
+    assert S.logtransform(p, tf)[2] == math.log(0.7)
+    assert np.allclose(S.exptransform(S.logtransform(p, tf), tf), p, rtol=1e-15)
+    assert S.nparams(S.LinearAMR(1.0, 1.0), S.GaussianDispersion(0.2)) == 3
