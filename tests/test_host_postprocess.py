@@ -184,3 +184,12 @@ def test_transformations_and_nparams_doctests():                 # transformatio
     assert S.logtransform(p, tf)[2] == math.log(0.7)
     assert np.allclose(S.exptransform(S.logtransform(p, tf), tf), p, rtol=1e-15)
     assert S.nparams(S.LinearAMR(1.0, 1.0), S.GaussianDispersion(0.2)) == 3
+
+
+def test_calculate_coeffs_doctest():                              # generic_fitting.jl:13-26
+    n_logage, n_mh = 10, 20
+    R = np.random.default_rng(0).random(n_logage)
+    coeffs = S.calculate_coeffs(S.PowerLawMZR(1.0, -1.0), S.GaussianDispersion(0.2), R,
+                                np.repeat(np.linspace(7.0, 10.0, n_logage), n_mh), np.tile(np.linspace(-2.0, 0.0, n_mh), n_logage))
+    assert isinstance(coeffs, np.ndarray) and coeffs.dtype == np.float64 and coeffs.shape == (n_logage * n_mh,)
+    assert np.allclose(coeffs.reshape(n_logage, n_mh).sum(axis=1), R, rtol=1e-13)      # mzr_test.jl:32-34
