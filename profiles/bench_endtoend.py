@@ -36,9 +36,18 @@ nsteps = 20
 t0 = time.perf_counter(); chain, lps, acc = S.mcmc_sample(ds2, d2, X0, nsteps, rng=np.random.default_rng(1)); t_gpu = time.perf_counter() - t0
 M2, d2 = ds2.download()
 t0 = time.perf_counter(); O.mcmc_logl(X0[:, :64], M2, d2); t_cpu64 = time.perf_counter() - t0
+# what the reference does NOT do but a CPU could: all walkers of a batch in one OpenBLAS GEMM (M @ X), then the Poisson sum per walker
+def _cpu_gemm_logl(Xw):
+    m = np.maximum(M2 @ Xw, np.finfo(np.float64).eps)
+    dd = d2[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(dd > 0, dd - m - dd * np.log(dd / m), -m).sum(axis=0)
+_cpu_gemm_logl(X0[:, :32])
+t0 = time.perf_counter(); _cpu_gemm_logl(X0[:, :256]); t_cpu_gemm = time.perf_counter() - t0
 out(config=2, what="mcmc_sample 1024 walkers x %d steps, 200x200 bins x 500 templates F64" % nsteps, gpu_s=t_gpu,
     gpu_walker_evals_per_s=1024 * nsteps / t_gpu, acceptance=acc,
-    cpu_oracle_walker_evals_per_s=64 / t_cpu64, cpu_threads=O.num_threads(), cpu_sample="64 walkers, threaded over walkers")
+    cpu_oracle_walker_evals_per_s=64 / t_cpu64, cpu_threads=O.num_threads(), cpu_sample="64 walkers, threaded over walkers (one pass over the stack per walker, as the reference's per-walker MCMCModel call)",
+    cpu_batched_gemm_walker_evals_per_s=256 / t_cpu_gemm, cpu_batched_note="256 walkers in one OpenBLAS GEMM + numpy Poisson sum: NOT what the reference does (mcmc_sample.jl:12-23 is one gemv per walker)")
 del M2
 
 # ---- configs 3/4: fit_sfh PowerLawMZR + GaussianDispersion, 60 ages x 40 [M/H] = 2400 templates, 200x300 bins ------
