@@ -340,3 +340,45 @@ def test_ctypes_prototypes_match_header_parameter_classes():
         assert (res is C.c_char_p) == ("char" in ret) and (res is L._int or "char" in ret or res is C.c_int), (name, ret, res)
         checked += 1
     assert checked == len(L.PROTOTYPES)
+
+
+_NULL_SWEEP = r"""
+import ctypes as C, sys, faulthandler
+faulthandler.enable()
+sys.path.insert(0, sys.argv[1])
+import sfh_b200
+L = sfh_b200._lib
+def zero(t):
+    if t in (C.c_void_p, C.c_char_p):
+        return None
+    if issubclass(t, (C._Pointer, C._CFuncPtr)):
+        return C.cast(None, t)
+    return t(0)
+for name in sorted(L.PROTOTYPES):
+    res, argtypes = L.PROTOTYPES[name]
+    r = getattr(L.lib, name)(*[zero(t) for t in argtypes])
+    print(name, r if res is not C.c_char_p else "str", flush=True)
+print("SWEEP DONE")
+"""
+
+
+def test_every_entry_point_survives_null_arguments():
+    """The boundary's error contract ("every call returns int status ... never throws"): each of the library's
+    entry points, called with NULL pointers and zero sizes, hands back a status -- SFH_ERR_INVALID_ARG, or SFH_OK for the
+    finalizer-safe destroy / close calls -- instead of crashing.  Run in a child process so that a crash is a test failure."""
+    import sys
+    r = subprocess.run([sys.executable, "-c", _NULL_SWEEP, ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SWEEP DONE" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+    got = dict(line.split() for line in r.stdout.splitlines() if line and not line.startswith("SWEEP"))
+    syms = header_symbols()
+    assert sorted(got) == syms
+    ok_on_null = {"sfh_stack_destroy", "sfh_ctx_destroy", "sfh_file_close"}
+    for name, val in got.items():
+        if name == "sfh_last_error":
+            continue
+        if name == "sfh_version":
+            assert val == "1"
+        elif name in ok_on_null:
+            assert val == "0", (name, val)
+        else:
+            assert val == "1", f"{name} returned {val} for NULL arguments (expected SFH_ERR_INVALID_ARG = 1)"
