@@ -229,3 +229,17 @@ def test_result_round_trip(tmp_path):
     back = sfh_b200.load_result(q)
     np.testing.assert_array_equal(back["posterior_matrix"], chain["posterior_matrix"])
     assert back["step_size"][0] == 0.05
+
+
+def test_structured_fuzz_never_crashes(tmp_path):
+    """Hostile header / table fields with the table checksum re-sealed (so the mutation reaches the structural validation), plus
+    truncations: every mutant is either refused with a status or opens as a consistent file whose arrays can be read end to end.
+    Runs in a child process (tests/file_fuzz_child.py): a crash of the parser is a failure here, not the end of the test run."""
+    import subprocess
+    import sys
+    child = os.path.join(os.path.dirname(os.path.abspath(__file__)), "file_fuzz_child.py")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, child, root, str(tmp_path), "4000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUZZ DONE" in r.stdout, (r.stdout[-1000:], r.stderr[-3000:])
+    opened, refused = (int(tok.split("=")[1]) for tok in r.stdout.split()[-2:])
+    assert opened > 100 and refused > 1000          # the mutations reach both outcomes
