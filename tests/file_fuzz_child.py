@@ -67,6 +67,12 @@ for it in range(nmut):
     path = os.path.join(workdir, "m.sfh")
     with open(path, "wb") as fh:
         fh.write(buf)
+    sh = C.c_void_p()                                              # the stack loader parses the same file plus its own attributes
+    st = L.lib.sfh_stack_create_from_file(C.byref(sh), path.encode(), int(rng.integers(0, 2)), None)
+    if st == 0:                                                   # (only on a machine with a device)
+        assert L.lib.sfh_stack_destroy(sh) == 0
+    else:
+        assert not sh.value
     h = C.c_void_p()
     st = L.lib.sfh_file_open(path.encode(), C.byref(h))
     if st != 0:
