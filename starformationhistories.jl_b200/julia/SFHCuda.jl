@@ -10,7 +10,6 @@ module SFHCuda
 import StarFormationHistories as SFH
 using StarFormationHistories: AbstractMZR, AbstractAMR, PowerLawMZR, LinearAMR, LogarithmicAMR,
                               GaussianDispersion, fittable_params, free_params
-using TaskLocalValues: TaskLocalValue
 
 const libsfh = get(ENV, "LIBSFHCUDA", "libsfhcuda.so")
 const SFH_F32, SFH_F64, SFH_I64 = Cint(0), Cint(1), Cint(2)
@@ -35,16 +34,37 @@ mutable struct DeviceStack{S} <: AbstractMatrix{S}
     host::Union{Nothing, Matrix{S}}   # kept (when the stack was uploaded) so that getindex and CPU-only helpers keep working
     dims::Tuple{Int, Int}
     handle::Ptr{Cvoid}
-    ctx::TaskLocalValue{Ptr{Cvoid}}   # one sfh_ctx per task, like HMCModel's TaskLocalValue (hmc_sample.jl:127)
+    # Contexts (sfh_ctx: stream + device scratch + pinned buffers) are POOLED per stack: a caller checks one out for the duration
+    # of a call (`with_ctx`), so the pool grows to the number of CONCURRENT callers and no further -- tsample_sfh spawns one
+    # task per short chain (generic_fitting.jl:617-626), and a context per task (the TaskLocalValue of hmc_sample.jl:127) would
+    # leave thousands of them alive.  The library does not track contexts: the finalizer destroys them, then the stack.
+    lock::ReentrantLock
+    idle::Vector{Ptr{Cvoid}}
+    all::Vector{Ptr{Cvoid}}
+    bound::Dict{Ptr{Cvoid}, Tuple{Vector{Float64}, Vector{Float64}}}   # ctx -> the (logAge, MH) grid sfh_hier_bind gave it
     function DeviceStack{S}(host, dims, handle::Ptr{Cvoid}) where S
-        ctx = TaskLocalValue{Ptr{Cvoid}}() do
-            c = Ref{Ptr{Cvoid}}(C_NULL)
-            check(ccall((:sfh_ctx_create, libsfh), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), handle, C_NULL, c))
-            c[]
+        obj = new{S}(host, dims, handle, ReentrantLock(), Ptr{Cvoid}[], Ptr{Cvoid}[],
+                     Dict{Ptr{Cvoid}, Tuple{Vector{Float64}, Vector{Float64}}}())
+        finalizer(obj) do o   # o is unreachable: nobody holds its lock or one of its contexts any more
+            foreach(c -> ccall((:sfh_ctx_destroy, libsfh), Cint, (Ptr{Cvoid},), c), o.all)
+            ccall((:sfh_stack_destroy, libsfh), Cint, (Ptr{Cvoid},), o.handle)
         end
-        obj = new{S}(host, dims, handle, ctx)
-        finalizer(o -> ccall((:sfh_stack_destroy, libsfh), Cint, (Ptr{Cvoid},), o.handle), obj)
         return obj
+    end
+end
+function new_ctx!(s::DeviceStack)   # caller holds s.lock
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sfh_ctx_create, libsfh), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), s.handle, C_NULL, c))
+    push!(s.all, c[])
+    return c[]
+end
+# f(ctx) with a context nobody else is using; safe from any number of tasks / threads (one ctx <=> one concurrent caller)
+function with_ctx(f, s::DeviceStack)
+    c = lock(() -> isempty(s.idle) ? new_ctx!(s) : pop!(s.idle), s.lock)
+    try
+        return f(c)
+    finally
+        lock(() -> push!(s.idle, c), s.lock)
     end
 end
 function DeviceStack(models::Matrix{S}, data::AbstractVector{D}) where {S <: Union{Float32, Float64}, D}
@@ -65,7 +85,7 @@ function SFH.composite!(composite::AbstractVector{<:Number}, coeffs::AbstractVec
     axes(composite, 1) == axes(models, 1) || throw(ArgumentError("axes(composite,1) != axes(models,1)"))
     axes(coeffs, 1) == axes(models, 2) || throw(ArgumentError("axes(coeffs,1) != axes(models,2)"))
     x = convert(Vector{Float64}, coeffs); out = Vector{Float64}(undef, length(composite))
-    check(ccall((:sfh_composite, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), models.ctx[], x, out))
+    with_ctx(c -> check(ccall((:sfh_composite, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), c, x, out)), models)
     composite .= out
     return
 end
@@ -73,14 +93,14 @@ end
 # ---- loglikelihood(coeffs, models, data)      src/fitting/fitting_base.jl:117-125 -----------------
 function SFH.loglikelihood(coeffs::AbstractVector{<:Number}, models::DeviceStack{S}, data::AbstractVector{<:Number}) where S
     x = convert(Vector{Float64}, coeffs); r = Ref{Float64}()
-    check(ccall((:sfh_loglikelihood_coeffs, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), models.ctx[], x, r))
+    with_ctx(c -> check(ccall((:sfh_loglikelihood_coeffs, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), c, x, r)), models)
     return convert(S, r[])      # reference returns the promoted eltype (fitting_core_test.jl:40)
 end
 
 # ---- ∇loglikelihood!(G, composite, models, data)   src/fitting/fitting_base.jl:265-285 ------------
 function SFH.∇loglikelihood!(G::AbstractVector, composite::AbstractVector{<:Number}, models::DeviceStack, data::AbstractVector{<:Number})
     c = convert(Vector{Float64}, composite); g = Vector{Float64}(undef, length(G))
-    check(ccall((:sfh_grad_loglikelihood, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), models.ctx[], c, g))
+    with_ctx(ctx -> check(ccall((:sfh_grad_loglikelihood, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, c, g)), models)
     composite .= c      # the documented side effect: composite now holds 1 - n/m (:219)
     G .= g
     return G
@@ -92,39 +112,50 @@ function SFH.fg!(F, G, coeffs::AbstractVector{<:Number}, models::DeviceStack{S},
     x = convert(Vector{Float64}, coeffs)
     nl = Ref{Float64}()
     g = G === nothing ? C_NULL : Vector{Float64}(undef, length(x))
-    check(ccall((:sfh_eval_fg, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                models.ctx[], x, F === nothing ? C_NULL : nl, g, C_NULL))
+    with_ctx(models) do c
+        check(ccall((:sfh_eval_fg, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    c, x, F === nothing ? C_NULL : nl, g, C_NULL))
+    end
     G === nothing || (G .= g)
     return F === nothing ? nothing : convert(S, nl[])
 end
 
 # ---- hierarchical fg!   mzr.jl:84-215 ("fg_mzr!") / amr.jl:78-173 ("fg_amr!") ---------------------
+# Metallicity models whose formulae the library's prologue / epilogue kernels hold.  LogarithmicAMR carries its Z -> [M/H]
+# conversion as two callables (amr.jl:250-256): only the default pair (MH_from_Z, dMH_dZ with solZ = 0.01524, Y_p = 0.2485,
+# gamma = 1.78; src/utilities.jl:138-156) is what the device evaluates, so the device methods dispatch on exactly that
+# instantiation (functions are singleton types).  Any other AbstractMZR / AbstractAMR / dispersion model -- a LogarithmicAMR with
+# user-supplied conversions included -- falls through to the reference's own generic fg! (mzr.jl:84 / amr.jl:78), which reaches the
+# device through composite! / loglikelihood / ∇loglikelihood! on the DeviceStack and does the chain rule on the host.
+const DeviceLogAMR = LogarithmicAMR{<:Real, typeof(SFH.MH_from_Z), typeof(SFH.dMH_dZ)}
+const DeviceMH = Union{PowerLawMZR, LinearAMR, DeviceLogAMR}
 mh_kind(::PowerLawMZR) = Cint(0); mh_fixed(m::PowerLawMZR) = Float64[m.logMstar0, 0, 0, 0]
 mh_kind(::LinearAMR) = Cint(1);   mh_fixed(m::LinearAMR) = Float64[m.T_max, 0, 0, 0]
 mh_kind(::LogarithmicAMR) = Cint(2); mh_fixed(m::LogarithmicAMR) = Float64[m.T_max, 0.01524, 0.2485, 1.78]
 
-const _bound = IdDict{Any, Tuple{Vector{Float64}, Vector{Float64}}}()   # ctx -> (logAge, MH) already bound
-function bind!(models::DeviceStack, logAge, MH)
-    c = models.ctx[]
-    la, mh = convert(Vector{Float64}, logAge), convert(Vector{Float64}, MH)
-    get(_bound, c, nothing) == (la, mh) && return c
+# sfh_hier_bind once per (context, grid): the grid a context is bound to is remembered in the stack (under its lock)
+function bind!(s::DeviceStack, c::Ptr{Cvoid}, logAge, MH)
+    la, mh = Vector{Float64}(logAge), Vector{Float64}(MH)   # copies: the cache must not alias arrays the caller may change
+    lock(() -> get(s.bound, c, nothing), s.lock) == (la, mh) && return c
     n = Ref{Int64}()
     check(ccall((:sfh_hier_bind, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}), c, la, mh, n))
-    _bound[c] = (la, mh)
+    lock(() -> (s.bound[c] = (la, mh)), s.lock)
     return c
 end
 
-function SFH.fg!(F, G, MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion,
+function SFH.fg!(F, G, MHmodel0::DeviceMH, dispmodel0::GaussianDispersion,
                  variables::AbstractVector{<:Number}, models::DeviceStack, data, composite,
                  logAge::AbstractVector{<:Number}, metallicities::AbstractVector{<:Number})
-    c = bind!(models, logAge, metallicities)
     v = convert(Vector{Float64}, variables)
     free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)..., 0]
     nl = Ref{Float64}()
     g = G === nothing ? C_NULL : Vector{Float64}(undef, length(v))
-    check(ccall((:sfh_eval_fg_hier, libsfh), Cint,
-                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{UInt8}, Ref{Float64}, Ptr{Float64}),
-                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), v, free, nl, g))
+    with_ctx(models) do c
+        bind!(models, c, logAge, metallicities)
+        check(ccall((:sfh_eval_fg_hier, libsfh), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{UInt8}, Ref{Float64}, Ptr{Float64}),
+                    c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), v, free, nl, g))
+    end
     G === nothing || (G .= g)
     return F === nothing ? nothing : nl[]
 end
@@ -132,8 +163,9 @@ end
 # ---- MCMCModel: W walkers per call   src/fitting/mcmc_sample.jl:12-23 ------------------------------
 function batched_loglikelihood(models::DeviceStack, X::Matrix{Float64})
     out = Vector{Float64}(undef, size(X, 2))
-    check(ccall((:sfh_eval_logl_batched, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}),
-                models.ctx[], X, size(X, 2), out))
+    with_ctx(models) do c
+        check(ccall((:sfh_eval_logl_batched, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}), c, X, size(X, 2), out))
+    end
     return out
 end
 (problem::SFH.MCMCModel{<:DeviceStack})(θ) = batched_loglikelihood(problem.models, reshape(convert(Vector{Float64}, θ), :, 1))[1]
@@ -143,21 +175,25 @@ end
 function batched_fg(models::DeviceStack, X::Matrix{Float64}; want_G::Bool=true)
     nl = Vector{Float64}(undef, size(X, 2))
     G = want_G ? Matrix{Float64}(undef, size(X)) : nothing
-    check(ccall((:sfh_eval_fg_batched, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
-                models.ctx[], X, size(X, 2), nl, want_G ? G : C_NULL))
+    with_ctx(models) do c
+        check(ccall((:sfh_eval_fg_batched, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                    c, X, size(X, 2), nl, want_G ? G : C_NULL))
+    end
     return nl, G
 end
 
 # Hierarchical fg! for C variable vectors at once (every chain task of tsample_sfh, generic_fitting.jl:617-626).
 # V is (Nj + nparams) x C in natural units; returns (-logL[C], G[(Nj + nparams), C]).
-function batched_fg(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion, V::Matrix{Float64},
+function batched_fg(MHmodel0::DeviceMH, dispmodel0::GaussianDispersion, V::Matrix{Float64},
                     models::DeviceStack, logAge, MH)
-    c = bind!(models, logAge, MH)
     nl = Vector{Float64}(undef, size(V, 2)); G = similar(V)
     free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)..., false]
-    check(ccall((:sfh_eval_fg_hier_batched, libsfh), Cint,
-                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}),
-                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), V, size(V, 2), free, nl, G))
+    with_ctx(models) do c
+        bind!(models, c, logAge, MH)
+        check(ccall((:sfh_eval_fg_hier_batched, libsfh), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}),
+                    c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), V, size(V, 2), free, nl, G))
+    end
     return nl, G
 end
 
@@ -169,9 +205,11 @@ function device_emcee(models::DeviceStack, x0::Matrix{Float64}, nsteps::Integer;
     T, W = size(x0); nstore = nsteps ÷ nthin
     X = copy(x0); chain = Array{Float64,3}(undef, T, W, nstore); lps = Matrix{Float64}(undef, W, nstore)
     lfin = Vector{Float64}(undef, W); acc = Ref{Float64}(0.0)
-    check(ccall((:sfh_mcmc_run, libsfh), Cint,
-                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
-                models.ctx[], X, W, nsteps, nthin, a_scale, seed, chain, lps, lfin, acc))
+    with_ctx(models) do c
+        check(ccall((:sfh_mcmc_run, libsfh), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                    c, X, W, nsteps, nthin, a_scale, seed, chain, lps, lfin, acc))
+    end
     return permutedims(chain, (3, 1, 2)), permutedims(lps), acc[]
 end
 
@@ -190,7 +228,7 @@ function DeviceStack(edges::Tuple{<:AbstractRange,<:AbstractRange}, points::Abst
                 h, nx, ny, first(edges[1]), step(edges[1]), first(edges[2]), step(edges[2]), length(points), offs,
                 cat(p -> p.colors), cat(p -> p.mags), cat(p -> p.color_err), cat(p -> p.mag_err), cat(p -> p.weights), cov,
                 dtype_code(S), d, dtype_code(Float64), C_NULL))
-    return DeviceStack{S}(nothing, (nx * ny, length(points)), h[])   # same finalizer / per-task contexts as the uploading constructor
+    return DeviceStack{S}(nothing, (nx * ny, length(points)), h[])   # same finalizer / context pool as the uploading constructor
 end
 
 # ---- on-disk container (include/sfhcuda.h: sfh_stack_save / sfh_stack_create_from_file) -------------------------
@@ -228,23 +266,27 @@ bfgs_opts(g_abstol, iterations; device_hessian=false) = BfgsOpts(sizeof(BfgsOpts
 # Returns (minimiser in the fitting space, inverse Hessian, report): fit_templates builds its LogTransformFTResult from them.
 function fit_templates_bfgs(models::DeviceStack, theta0::Vector{Float64}, transform::Integer; g_abstol=1e-8, iterations=5000)
     theta = copy(theta0); invH = Matrix{Float64}(undef, length(theta), length(theta)); rep = BfgsReport()
-    check(ccall((:sfh_fit_templates_bfgs, libsfh), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ref{BfgsOpts}, Ref{BfgsReport}, Ptr{Float64}),
-                models.ctx[], transform, theta, bfgs_opts(g_abstol, iterations), rep, invH))
+    with_ctx(models) do c
+        check(ccall((:sfh_fit_templates_bfgs, libsfh), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ref{BfgsOpts}, Ref{BfgsReport}, Ptr{Float64}),
+                    c, transform, theta, bfgs_opts(g_abstol, iterations), rep, invH))
+    end
     return theta, invH, rep
 end
 
 # fit_sfh's fg_map! (jacobian_corrections = true) / fg_mle! (false) optimisation, generic_fitting.jl:306-327.
 # x0 = [log.(R); transformed free parameters] exactly as fit_sfh assembles it (:285-294).
-function fit_sfh_bfgs(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion, x0::Vector{Float64},
+function fit_sfh_bfgs(MHmodel0::DeviceMH, dispmodel0::GaussianDispersion, x0::Vector{Float64},
                       models::DeviceStack, logAge, MH, jacobian_corrections::Bool; g_abstol=1e-8, iterations=5000)
-    c = bind!(models, logAge, MH)
     par = Float64[fittable_params(MHmodel0)..., fittable_params(dispmodel0)...]
     tf = Int32[SFH.transforms(MHmodel0)..., SFH.transforms(dispmodel0)...]
     free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)...]
     x = copy(x0); invH = Matrix{Float64}(undef, length(x), length(x)); rep = BfgsReport()
-    check(ccall((:sfh_fit_sfh_bfgs, libsfh), Cint,
-                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Cint, Ptr{Float64}, Ref{BfgsOpts}, Ref{BfgsReport}, Ptr{Float64}),
-                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), par, tf, free, jacobian_corrections, x, bfgs_opts(g_abstol, iterations), rep, invH))
+    with_ctx(models) do c
+        bind!(models, c, logAge, MH)
+        check(ccall((:sfh_fit_sfh_bfgs, libsfh), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Cint, Ptr{Float64}, Ref{BfgsOpts}, Ref{BfgsReport}, Ptr{Float64}),
+                    c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), par, tf, free, jacobian_corrections, x, bfgs_opts(g_abstol, iterations), rep, invH))
+    end
     return x, invH, rep
 end
 
@@ -259,29 +301,33 @@ function hmc_sample_nuts(models::DeviceStack, theta0::Matrix{Float64}, nsteps::I
     T, nch = size(theta0); lens = fill(Int64(nsteps), nch)
     samples = Matrix{Float64}(undef, T, nsteps * nch); lps = Vector{Float64}(undef, nsteps * nch); steps = Vector{Float64}(undef, nch)
     o = NutsOpts(sizeof(NutsOpts), max_depth, nwarmup, 0.8, 0.0, seed, 0, 0)
-    check(ccall((:sfh_hmc_sample_nuts, libsfh), Cint,
-                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{NutsOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
-                models.ctx[], nch, theta0, lens, C_NULL, o, samples, lps, steps, C_NULL, C_NULL))
+    with_ctx(models) do c
+        check(ccall((:sfh_hmc_sample_nuts, libsfh), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{NutsOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+                    c, nch, theta0, lens, C_NULL, o, samples, lps, steps, C_NULL, C_NULL))
+    end
     return permutedims(reshape(exp.(samples), T, nsteps, nch), (2, 1, 3))
 end
 
 # x0s: (Nj + nfree) x nchains starting points in the transformed space (tsample_sfh draws them from MvNormal(MLE, MAP.invH), :586);
 # invH = MAP.invH is the dense M^-1 of the kinetic energy (:479-482), ϵ the initial step size.  Returns the transformed-space
 # samples (columns, chains concatenated) for exptransform_samples! (:640-658).
-function sample_sfh_nuts(MHmodel0::Union{PowerLawMZR, LinearAMR, LogarithmicAMR}, dispmodel0::GaussianDispersion, x0s::Matrix{Float64},
+function sample_sfh_nuts(MHmodel0::DeviceMH, dispmodel0::GaussianDispersion, x0s::Matrix{Float64},
                          lens::Vector{Int64}, invH::Matrix{Float64}, models::DeviceStack, logAge, MH; ϵ::Real=0.05, max_depth::Integer=8,
                          seed::UInt64=rand(UInt64))
-    c = bind!(models, logAge, MH)
     par = Float64[fittable_params(MHmodel0)..., fittable_params(dispmodel0)...]
     tf = Int32[SFH.transforms(MHmodel0)..., SFH.transforms(dispmodel0)...]
     free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)...]
     n, nch = size(x0s); tot = sum(lens)
     samples = Matrix{Float64}(undef, n, tot); lps = Vector{Float64}(undef, tot); steps = Vector{Float64}(undef, nch)
     o = NutsOpts(sizeof(NutsOpts), max_depth, 0, 0.8, ϵ, seed, 2, 0)
-    check(ccall((:sfh_sample_sfh_nuts, libsfh), Cint,
-                (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64},
-                 Ref{NutsOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
-                c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), par, tf, free, nch, x0s, lens, invH, o, samples, lps, steps, C_NULL, C_NULL))
+    with_ctx(models) do c
+        bind!(models, c, logAge, MH)
+        check(ccall((:sfh_sample_sfh_nuts, libsfh), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64},
+                     Ref{NutsOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+                    c, mh_kind(MHmodel0), mh_fixed(MHmodel0), Cint(0), par, tf, free, nch, x0s, lens, invH, o, samples, lps, steps, C_NULL, C_NULL))
+    end
     return samples, lps, steps
 end
 
@@ -290,8 +336,10 @@ struct LbfgsbOpts; struct_size::Int32; m::Int32; factr::Float64; pgtol::Float64;
 mutable struct LbfgsbReport; f::Float64; pg_norm::Float64; iterations::Int64; f_calls::Int64; status::Int32; reserved::Int32; LbfgsbReport() = new(); end
 function fit_templates_lbfgsb_native(models::DeviceStack, x0::Vector{Float64}; m::Integer=10, factr::Real=1e-12, pgtol::Real=1e-5)
     x = copy(x0); rep = LbfgsbReport()
-    check(ccall((:sfh_fit_templates_lbfgsb, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{LbfgsbOpts}, Ref{LbfgsbReport}),
-                models.ctx[], x, LbfgsbOpts(sizeof(LbfgsbOpts), m, factr, pgtol, 0, 0), rep))
+    with_ctx(models) do c
+        check(ccall((:sfh_fit_templates_lbfgsb, libsfh), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{LbfgsbOpts}, Ref{LbfgsbReport}),
+                    c, x, LbfgsbOpts(sizeof(LbfgsbOpts), m, factr, pgtol, 0, 0), rep))
+    end
     return rep.f, x
 end
 
