@@ -123,9 +123,10 @@ int sfh_stack_download(const sfh_stack *s, void *models_out, double *data_out);
 /* stream: an existing cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a
  * private non-blocking stream.                                                                 */
 int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out);
-/* LIFETIME: the library does not track the contexts of a stack.  Destroy every context BEFORE its stack (sfh_ctx_destroy reads
- * the stack to select its device), and keep the number of live contexts bounded -- one per CONCURRENT caller, e.g. a pool --
- * each holds a stream, O(nbins + clusters * ntemplates) doubles of device scratch and pinned staging buffers.  Idempotent on NULL. */
+/* LIFETIME: the library does not track the contexts of a stack.  Destroy every context before its stack where you control the
+ * order; sfh_ctx_destroy itself never touches the stack, so finalizers that run in the other order are harmless -- USING a
+ * context whose stack is gone is not.  Keep the number of live contexts bounded (one per CONCURRENT caller, e.g. a pool): each
+ * holds a stream, O(nbins + clusters * ntemplates) doubles of device scratch and pinned staging buffers.  Idempotent on NULL. */
 int sfh_ctx_destroy(sfh_ctx *c);
 int sfh_ctx_stats(const sfh_ctx *c, sfh_stats *out);
 

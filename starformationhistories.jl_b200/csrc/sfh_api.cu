@@ -169,6 +169,7 @@ struct sfh_stack {
 
 struct sfh_ctx {
     sfh_stack *s = nullptr;
+    int device = 0;   // the stack's device, remembered so that sfh_ctx_destroy never has to read a stack that may already be gone
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // scratch
@@ -708,6 +709,7 @@ static int sfh_ctx_create_impl(sfh_stack *s, void *stream, sfh_ctx **out) {
     sfh_ctx *c = new (std::nothrow) sfh_ctx();
     if (!c) return fail(SFH_ERR_OOM, "host allocation failed");
     c->s = s;
+    c->device = s->device;
     auto bail = [&](int st) { sfh_ctx_destroy(c); return st; };
 #define CTX_TRY(expr)                                                                               \
     do {                                                                                            \
@@ -753,7 +755,7 @@ extern "C" int sfh_ctx_create(sfh_stack *s, void *stream, sfh_ctx **out) {
 
 static int sfh_ctx_destroy_impl(sfh_ctx *c) {
     if (!c) return SFH_OK;
-    if (c->s) cudaSetDevice(c->s->device);
+    cudaSetDevice(c->device);   // not c->s->device: a finalizer may have destroyed the stack first (include/sfhcuda.h: LIFETIME)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
