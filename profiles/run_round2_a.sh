@@ -1,6 +1,8 @@
 #!/bin/bash
 # First GPU call of round 2: everything built after round 1's GPU budget ran out.
-#   gpurun --timeout 900 -- 'bash profiles/run_round2_a.sh'
+#   gpurun --timeout 2700 -- 'bash profiles/run_round2_a.sh'
+# (typical run: 6-8 minutes; 2700 s covers the sum of the per-step limits below, so that gpurun's own limit never fires first --
+#  box time is charged for what is used, not for the limit)
 # Every step carries its own `timeout -k` (a step that hangs must not take the box with it), and the one kernel that has never
 # run on a device -- the two-tiles-in-flight fused kernel, a cluster exchange that could deadlock -- comes LAST, its sweeps
 # only if its parity tests finished.
