@@ -22,6 +22,21 @@ import sys
 import threading
 import time
 
+
+def _host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+# The CPU legs use every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the
+# reference arm into a one-core run (round 1's N>1 "vs_reference" ratios): the thread counts are set here, before numpy
+# (OpenBLAS) and the OpenMP oracle are loaded, and re-asserted at run time through threadpoolctl / omp_set_num_threads.
+if "--impl" in sys.argv and "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_host_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -172,6 +187,14 @@ def run_reference(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import oracle as O
+    ncores = _host_cores()
+    O.set_num_threads(ncores)                       # OpenMP nest
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncores, user_api="blas")   # numpy's OpenBLAS
+    except Exception:
+        pass
     x = truth_coeffs() * 1.02
     M, data = host_stack(NB, NT, x)
     routes = cpu_routes(M, data, x)
@@ -214,6 +237,194 @@ def _protect_stdout():
     return os.fdopen(saved, "w")
 
 
+def kernel_name(info, dtype):
+    if info.variant == 4:
+        vec = 16 // np.dtype(dtype).itemsize
+        return "sfh_fg_fused2_kernel<%s,%d,true>" % ("double" if vec == 2 else "float", info.tile_bins // vec)
+    return "sfh_fg_fused_kernel<%s,%d,%d,true,false>" % ("double" if np.dtype(dtype).itemsize == 8 else "float",
+                                                          info.tile_bins, info.consumer_warps)
+
+
+def tiling(info):
+    return {"variant": info.variant, "tile_bins": info.tile_bins, "cluster": info.cluster, "chunks_per_tile": info.chunks_per_tile,
+            "ring_slots": info.ring_slots, "n_clusters": info.n_clusters, "consumer_warps": info.consumer_warps}
+
+
+class Harness:
+    """One process = one GPU.  Everything that touches torch / the library lives here so that the CPU arm never imports them."""
+
+    def __init__(self, args):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import sfh_b200 as S
+        self.C, self.torch, self.dist, self.S, self.L = C, torch, dist, S, S._lib
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream()     # an explicit non-default stream: the kernels AND the timing events live on it
+        torch.cuda.set_stream(self.stream)
+        self.dp = C.POINTER(C.c_double)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def new_ctx(self, ds):
+        ctx = ds.new_ctx(self.stream.cuda_stream)
+        if self.world > 1:
+            self.S.init_library_comm(ctx)     # NCCL communicator + (unless SFH_NO_P2P=1) the fused one-shot NVLink all-reduce
+        return ctx
+
+    def comm_mode(self, ctx):
+        nr, rk, mode = self.C.c_int(), self.C.c_int(), self.C.c_int()
+        self.L.check(self.L.lib.sfh_ctx_comm_info(ctx.handle, self.C.byref(nr), self.C.byref(rk), self.C.byref(mode)))
+        return {0: "single GPU", 1: "NCCL all-reduce on the kernel's stream",
+                2: "one-shot NVLink peer-memory all-reduce fused into the finalize kernel"}[mode.value]
+
+    def timed_device_loop(self, ctx, d_x, d_out, steps, warmup, sampler=None):
+        """K device-resident evaluations timed with CUDA events on the launch stream.  Ranks are aligned ON THE DEVICE: two
+        untimed all-reduced steps are enqueued after the host barrier and e0 is recorded right behind them in-stream -- an
+        all-reduced step cannot finish before every rank has contributed, so all ranks pass e0 within an NVLink latency of
+        each other and the first timed step does not absorb the host barrier's exit skew."""
+        L, C, torch = self.L, self.C, self.torch
+        def step():
+            L.check(L.lib.sfh_enqueue_fg(ctx.handle, d_x.data_ptr(), d_out.data_ptr(), 1))
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        st0, st1 = L.sfh_stats(), L.sfh_stats()
+        if sampler:
+            sampler.start()
+        step(); step()
+        L.check(L.lib.sfh_ctx_stats(ctx.handle, C.byref(st0)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            step()
+        e1.record(self.stream)
+        L.check(L.lib.sfh_ctx_stats(ctx.handle, C.byref(st1)))
+        self.barrier()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        return ms, int(st1.kernel_launches - st0.kernel_launches)
+
+    def parity_sharded_vs_whole(self, make_whole, x, d_out, nt):
+        """N > 1: (i) every rank holds bit-identical [logL, G]; (ii) rank 0 also builds the WHOLE stack (all shards' rows) on its
+        own GPU and evaluates it alone: the all-reduced sharded answer must match it (logL 1e-12; every gradient component
+        1e-10 relative, plus 1e-12 of the largest component for those that nearly cancel)."""
+        torch, dist = self.torch, self.dist
+        mine = d_out.view(torch.int64).clone()
+        allv = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allv, mine)
+        identical = all(bool(torch.equal(v, allv[0])) for v in allv)
+        res = {"ranks_bit_identical": identical}
+        if self.rank == 0:
+            whole = make_whole()
+            cw = whole.new_ctx(self.stream.cuda_stream)
+            d_x = torch.tensor(x, dtype=torch.float64, device="cuda")
+            d_w = torch.zeros(1 + nt, dtype=torch.float64, device="cuda")
+            self.L.check(self.L.lib.sfh_enqueue_fg(cw.handle, d_x.data_ptr(), d_w.data_ptr(), 1))
+            torch.cuda.synchronize()
+            w, sh = d_w.cpu().numpy(), d_out.cpu().numpy()
+            res["logl_rel"] = float(abs(sh[0] - w[0]) / abs(w[0]))
+            tol = 1e-10 * np.abs(w[1:]) + 1e-12 * np.abs(w[1:]).max()
+            res["grad_max_err_over_tol"] = float(np.max(np.abs(sh[1:] - w[1:]) / tol))
+            res["whole_stack_tiling"] = tiling(whole.info())
+            cw.close(); whole.close()
+            del cw, whole
+            torch.cuda.empty_cache()
+        self.barrier()
+        flag = torch.tensor([1.0 if (identical and res.get("logl_rel", 0.0) <= 1e-12 and res.get("grad_max_err_over_tol", 0.0) <= 1.0) else 0.0],
+                            dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        res["ok"] = bool(flag.item() == 1.0)
+        return res
+
+
+def run_config5(H, args, peak):
+    """BASELINE.json config 5, STRONG scaling: ONE 10^6-bin x 10^4-template Float32 stack (40 GB), bin rows split evenly over the
+    N GPUs (generated per shard on the device from a counter-based stream, so every N sees the same matrix), [logL, G]
+    (10001 doubles) all-reduced every evaluation."""
+    S, L, C, torch = H.S, H.L, H.C, H.torch
+    nb5, nt5, seed5 = 1000 * 1000, 10000, 58392
+    rng = np.random.Generator(np.random.Philox(seed5))
+    x5 = rng.random(nt5)
+    b, e = S.shard_rows(nb5, H.world, H.rank, align=128)
+    ds = S.DeviceStack.synthetic(nb5, nt5, np.float32, seed=seed5, scale=1.0, x_true=x5, device=H.local, rows=(b, e),
+                                 tile_bins=args.tile, cluster=args.cluster, consumer_warps=args.nw, variant=args.variant)
+    info = ds.info()
+    assert info.fused == 1
+    ctx = H.new_ctx(ds)
+    d_x = torch.tensor(x5 * 1.02, dtype=torch.float64, device="cuda")
+    d_out = torch.zeros(1 + nt5, dtype=torch.float64, device="cuda")
+    steps = max(3, min(args.steps, 20))
+    ms, _ = H.timed_device_loop(ctx, d_x, d_out, steps, 3)
+    ms_eval = ms / steps
+    ms_e, ms_k = C.c_double(), C.c_double()
+    xh = np.ascontiguousarray(x5 * 1.02)
+    L.check(L.lib.sfh_time_fg(ctx.handle, xh.ctypes.data_as(H.dp), 5, 1, 0, C.byref(ms_e), C.byref(ms_k)))
+    rows = e - b
+    bytes_shard = rows * nt5 * 4 + rows * 8 + 2 * nt5 * 8 + 8
+    kernel_ms = H.max_over_ranks(ms_k.value)
+    out = {"workload": "config5: 10^6 bins x 10^4 templates Float32 (40 GB), bin rows sharded over the GPUs, Poisson data",
+           "scaling": "strong", "n_gpus": H.world, "steps": steps, "ms_per_eval": ms_eval, "evals_per_s": 1e3 / ms_eval,
+           "aggregate_GBps": (nb5 * nt5 * 4 + nb5 * 8) / (ms_eval * 1e-3) / 1e9,
+           "per_gpu": {"rows": rows, "bytes_alg_per_launch": bytes_shard, "kernel_ms": kernel_ms,
+                       "roofline_frac_kernel": bytes_shard / (kernel_ms * 1e-3) / 1e9 / peak,
+                       "roofline_frac_step": bytes_shard / (ms_eval * 1e-3) / 1e9 / peak, "kernel": kernel_name(info, np.float32)},
+           "tiling": tiling(info), "exchange": H.comm_mode(ctx)}
+    torch.cuda.synchronize()
+    out["neg_logL"] = float(-d_out[0].item())
+    if H.world > 1:
+        out["parity"] = H.parity_sharded_vs_whole(
+            lambda: S.DeviceStack.synthetic(nb5, nt5, np.float32, seed=seed5, scale=1.0, x_true=x5, device=H.local), x5 * 1.02, d_out, nt5)
+        assert out["parity"]["ok"], out["parity"]
+    ctx.close(); ds.close()
+    return out
+
+
+def run_hier(H, ctx, steps, warmup, peak, bytes_alg):
+    """The call fit_sfh / sample_sfh make every iteration: the MZR-hierarchical fg! (mzr.jl:84-215) through the host-synchronous
+    C-ABI call sfh_eval_fg_hier (Nj + 3 variables in, [-logL, G] out), wall-clock per call."""
+    L, C = H.L, H.C
+    uA = np.linspace(10.1, 6.6, NJ); uM = np.linspace(-2.5, 0.0, NK)
+    logAge = np.ascontiguousarray(np.repeat(uA, NK)); MH = np.ascontiguousarray(np.tile(uM, NJ))
+    rng = np.random.Generator(np.random.Philox(SEED))
+    v = np.ascontiguousarray(np.concatenate([rng.random(NJ) * 1e6, [1.0, -2.0, 0.2]]) * 1.02)
+    nj = C.c_int64()
+    L.check(L.lib.sfh_hier_bind(ctx.handle, logAge.ctypes.data_as(H.dp), MH.ctypes.data_as(H.dp), C.byref(nj)))
+    fixed = np.array([6.0, 0, 0, 0]); mask = (C.c_uint8 * 3)(1, 1, 1)
+    G = np.empty(NJ + 3); nl = C.c_double()
+    def call():
+        L.check(L.lib.sfh_eval_fg_hier(ctx.handle, 0, fixed.ctypes.data_as(H.dp), 0, v.ctypes.data_as(H.dp), mask, C.byref(nl),
+                                       G.ctypes.data_as(H.dp)))
+    for _ in range(warmup):
+        call()
+    H.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    wall = H.max_over_ranks(time.perf_counter() - t0)
+    ms = 1e3 * wall / steps
+    assert np.isfinite(nl.value) and np.all(np.isfinite(G))
+    return {"what": "sfh_eval_fg_hier (PowerLawMZR + GaussianDispersion, 60 ages + 3 parameters), host buffers, wall clock per call",
+            "ms_per_eval": ms, "evals_per_s": H.world * 1e3 / ms, "h2d_bytes_per_step": (NJ + 3) * 8, "d2h_bytes_per_step": (NJ + 4) * 8,
+            "roofline_frac_end_to_end": bytes_alg / (ms * 1e-3) / 1e9 / peak}
+
+
 def main():
     real_stdout = _protect_stdout()
     ap = argparse.ArgumentParser()
@@ -222,124 +433,86 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the strong-scaling 40 GB block")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
-    ap.add_argument("--nw", type=int, default=0, help="consumer warps per CTA (8 or 16; 0 = auto)")
+    ap.add_argument("--nw", type=int, default=0, help="consumer warps per CTA of the cluster-tile kernel (8 or 16; 0 = auto)")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 cluster-tile kernel, 4 warp-specialised stream kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args, real_stdout)
 
-    import torch
-    import torch.distributed as dist
-    import ctypes as C
-    import sfh_b200 as S
-    L = S._lib
+    H = Harness(args)
+    C, torch, dist, S, L = H.C, H.torch, H.dist, H.S, H.L
+    world, rank, local = H.world, H.rank, H.local
+    peak, peak_src = measured_peaks()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    # ---- one config-3 stack per rank, generated on device (counter-based: shards of one N x larger diagram)
+    # ---- headline: one config-3 stack per rank, generated on device (counter-based: shards of one N x larger diagram)
     x_true = truth_coeffs()
     nb_total = NB * world
+    mk = dict(tile_bins=args.tile, cluster=args.cluster, consumer_warps=args.nw, variant=args.variant)
     ds = S.DeviceStack.synthetic(nb_total, NT, np.float64, seed=SEED, scale=1e-5, x_true=x_true, device=local,
-                                 rows=(rank * NB, (rank + 1) * NB), tile_bins=args.tile, cluster=args.cluster,
-                                 consumer_warps=args.nw)
+                                 rows=(rank * NB, (rank + 1) * NB), **mk)
     info = ds.info()
     assert info.fused == 1, "fused sm_100a kernel not selected"
-    stream = torch.cuda.Stream()          # an explicit non-default stream: the kernels AND the timing events live on it
-    torch.cuda.set_stream(stream)
-    ctx = ds.new_ctx(stream.cuda_stream)
-    if world > 1:
-        # NCCL communicator for the library + (unless SFH_NO_P2P=1) the fused one-shot NVLink all-reduce
-        S.init_library_comm(ctx)
-
+    ctx = H.new_ctx(ds)
     x = x_true * 1.02
     d_x = torch.tensor(x, dtype=torch.float64, device="cuda")
     d_out = torch.zeros(1 + NT, dtype=torch.float64, device="cuda")
-
-    def step():
-        L.check(L.lib.sfh_enqueue_fg(ctx.handle, d_x.data_ptr(), d_out.data_ptr(), 1))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    st0 = L.sfh_stats()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    L.check(L.lib.sfh_ctx_stats(ctx.handle, C.byref(st0)))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    st1 = L.sfh_stats()
-    L.check(L.lib.sfh_ctx_stats(ctx.handle, C.byref(st1)))
-    launches = int(st1.kernel_launches - st0.kernel_launches)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = H.timed_device_loop(ctx, d_x, d_out, args.steps, args.warmup, sampler)
     value = world * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: the reference-facing call, host buffers in/out, H2D + D2H inside the timed region
     G = np.empty(NT)
     nl = C.c_double()
     xh = np.ascontiguousarray(x)
-    dp = C.POINTER(C.c_double)
+    dp = H.dp
     for _ in range(args.warmup):
         L.check(L.lib.sfh_eval_fg(ctx.handle, xh.ctypes.data_as(dp), C.byref(nl), G.ctypes.data_as(dp), None))
-    barrier()
+    H.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record(stream)
+    e0.record(H.stream)
     for _ in range(args.steps):
         L.check(L.lib.sfh_eval_fg(ctx.handle, xh.ctypes.data_as(dp), C.byref(nl), G.ctypes.data_as(dp), None))
-    e1.record(stream)
-    barrier()
+    e1.record(H.stream)
     wall = time.perf_counter() - t0      # the caller-visible time of K synchronous calls (>= the event time)
-    ms2 = torch.tensor([max(e0.elapsed_time(e1), 1e3 * wall)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ms2.item())
+    H.barrier()
+    e2e_ms = H.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * wall))
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
-    # sanity of what was timed: the device-resident and the host-API paths agree
+    # sanity of what was timed: the device-resident and the host-API paths agree bit for bit
     torch.cuda.synchronize()
     out_host = d_out.cpu().numpy()
-    assert np.isfinite(nl.value) and abs(-out_host[0] - nl.value) <= 1e-12 * abs(nl.value)
+    assert np.isfinite(nl.value) and -out_host[0] == nl.value
     assert np.array_equal(out_host[1:], G)
 
     # ---- roofline of the dominant (fused) kernel: CUDA events around that kernel only, on its launch stream
     ms_eval, ms_kernel = C.c_double(), C.c_double()
     L.check(L.lib.sfh_time_fg(ctx.handle, xh.ctypes.data_as(dp), min(args.steps, 50), 1, 0, C.byref(ms_eval), C.byref(ms_kernel)))
     bytes_alg = NB * NT * 8 + NB * 8 + 2 * NT * 8 + 8
-    peak, peak_src = measured_peaks()
     achieved = bytes_alg / (ms_kernel.value * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "sfh_fg_fused_kernel<double,%d,%d,true>" % (info.tile_bins, info.consumer_warps),
-                "kernel_ms": ms_kernel.value, "bytes_alg_per_launch": bytes_alg, "peak_source": peak_src}
+                "traffic": ncu_traffic(), "traffic_source": "constant: dram__bytes_read+write of this kernel from the ncu --set full capture summarised in profiles/ncu_summary.json (not re-measured in this run)",
+                "kernel": kernel_name(info, np.float64), "kernel_ms": ms_kernel.value, "bytes_alg_per_launch": bytes_alg, "peak_source": peak_src}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+    # ---- the hierarchical evaluation fit_sfh / sample_sfh actually call
+    fg_hier = run_hier(H, ctx, min(args.steps, 500), args.warmup, peak, bytes_alg)
+
+    # ---- parity carried by the bench line itself
+    parity = None
+    if world > 1:
+        parity = H.parity_sharded_vs_whole(
+            lambda: S.DeviceStack.synthetic(nb_total, NT, np.float64, seed=SEED, scale=1e-5, x_true=x_true, device=local), x, d_out, NT)
+        assert parity["ok"], parity
+    sharding = ("bin rows, one 60000-bin shard per GPU; [logL,G] (2401 f64) all-reduced every step: " + H.comm_mode(ctx)) if world > 1 else "single GPU"
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as O
         Mh, dh = ds.download()
         Mh = np.asfortranarray(Mh)
         best, routes = time_cpu(Mh, dh, x)
@@ -350,24 +523,38 @@ def main():
                "sample": f"{n_cpu} full evaluations of the same 60000x2400 F64 stack (downloaded from the GPU), median; port of the "
                          f"reference's two-pass fg! (julia not installed): {CPU_ROUTE_TEXT[best]}; the slower restatement ({other}: "
                          f"{CPU_ROUTE_TEXT[other]}) reached {1.0 / routes[other][0]:.1f} evals/s"}
+        # the CPU leg doubles as the checker of what was timed: ALL 2400 gradient components and logL against the oracle
+        nlo, Go, _ = O.fg(x, Mh, dh)
+        gscale = np.abs(Mh).T @ np.abs(1.0 - dh / np.maximum(Mh @ x, np.finfo(np.float64).eps))
+        parity = {"vs_oracle_logl_rel": float(abs(nl.value - nlo) / abs(nlo)),
+                  "vs_oracle_grad_max_err_over_scale": float(np.max(np.abs(G - Go) / gscale)), "components": NT}
+        assert parity["vs_oracle_logl_rel"] <= 1e-12 and parity["vs_oracle_grad_max_err_over_scale"] <= 1e-10, parity
         del Mh
+    ctx.close(); ds.close()
+    del ctx, ds
+    torch.cuda.empty_cache()
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_stack_bytes": int(info.stack_bytes),
-                       "l2": "inputs (1.15 GB/GPU) larger than L2 (126 MB); no flush needed",
-                       "sharding": ("bin rows, one 60000-bin shard per GPU; [logL,G] (2401 f64) all-reduced every step: "
-                                    + ("NCCL" if os.environ.get("SFH_NO_P2P") == "1" else "one-shot NVLink peer-memory reduce fused into the finalize kernel")) if world > 1 else "single GPU",
-                       "value_unit_note": "N>1: value = N shard-evaluations per all-reduced step / time (weak scaling)",
-                       "tile_bins": info.tile_bins, "cluster": info.cluster, "chunks_per_tile": info.chunks_per_tile,
-                       "ring_slots": info.ring_slots, "n_clusters": info.n_clusters, "consumer_warps": info.consumer_warps},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NT * 8, "d2h_bytes_per_step": (NT + 1) * 8,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
-    if cpu is not None:
-        line["cpu_baseline"] = cpu
-    print(json.dumps(line), file=real_stdout, flush=True)
+    config5 = None if args.no_config5 else run_config5(H, args, peak)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "per_gpu_stack_bytes": int(info.stack_bytes),
+                           "l2": "inputs (1.15 GB/GPU) larger than L2 (126 MB); no flush needed",
+                           "sharding": sharding,
+                           "timing": "CUDA events on the launch stream; ranks aligned on the device by two untimed all-reduced steps before e0; max over ranks",
+                           "value_unit_note": "N>1: value = N shard-evaluations per all-reduced step / time (weak scaling)", **tiling(info)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NT * 8, "d2h_bytes_per_step": (NT + 1) * 8,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "fg_hier": fg_hier}
+        if parity is not None:
+            line["parity"] = parity
+        if config5 is not None:
+            line["config5"] = config5
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

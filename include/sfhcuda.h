@@ -68,12 +68,12 @@ typedef struct sfh_opts {
     int64_t row_end;     /* 0,0 = all rows.  (one process per GPU)            */
     double clamp_eps;    /* max(m, eps) clamp; 0 = eps(storage dtype) like the reference            */
                          /* (fitting_base.jl:90,277)                                                */
-    int32_t tile_bins;   /* 0 = auto; else bins per tile of the fused kernel (16/32/64/128)         */
+    int32_t tile_bins;   /* 0 = auto; else bins per tile of the fused kernel (a power of two)        */
     int32_t cluster;     /* 0 = auto; else thread-block-cluster size (1,2,4,8,16)                   */
     int32_t force_unfused; /* 1 = always use the two-pass kernels (debug / A-B measurements)        */
-    int32_t consumer_warps; /* 0 = auto; 8, 12 or 16 consumer warps per CTA                          */
-    int32_t variant;     /* 0 = auto; 1 = shared-memory-resident tile; 2 = register-resident tile;   */
-                         /* 3 = shared-memory tile with two tiles in flight (experimental, opt-in)   */
+    int32_t consumer_warps; /* 0 = auto; 8 or 16 consumer warps per CTA (cluster-tile kernel only)    */
+    int32_t variant;     /* 0 = auto; 1 = cluster-tile kernel (sfh_fused.cuh); 4 = warp-specialised   */
+                         /* stream kernel (sfh_fused2.cuh)                                           */
     int32_t reserved;
 } sfh_opts;
 
@@ -82,9 +82,10 @@ typedef struct sfh_info {
     int32_t dtype, device;
     int32_t fused;     /* 1 if the single-pass fused kernel is in use                  */
     int32_t tile_bins, cluster, chunks_per_tile, ring_slots, n_clusters, consumer_warps;
-    int32_t sm_count, cc_major, cc_minor, register_tile;
+    int32_t sm_count, cc_major, cc_minor;
+    int32_t variant;      /* fused kernel in use: 0 none (two-pass), 1 cluster-tile kernel, 4 warp-specialised stream kernel */
     int32_t panel_layout; /* 1: device copy stored as bin-major panels of tile_bins bins (host layout unchanged) */
-    int32_t pipelined;    /* 1: gradient evaluations use the two-tiles-in-flight kernel (variant 3)               */
+    int32_t reserved0;
     int64_t stack_bytes; /* device bytes held by the stack (padded)                    */
     double clamp_eps;
 } sfh_info;
@@ -382,6 +383,13 @@ int sfh_comm_init(sfh_ctx *c, int nranks, int rank, const void *id128);
  * sfh_comm_init first (NCCL remains the fallback for the two-pass and batched-walker paths).                    */
 int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out);
 int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *handles);
+/* on = 0: back to the NCCL all-reduce (what a rank does when some OTHER rank's sfh_comm_p2p_init failed: the switch must be
+ * taken by all ranks or none, else the ranks that switched wait for flags that never come); on = 1 re-enables after a
+ * successful sfh_comm_p2p_init.  Must be called by every rank between evaluations, never concurrently with one.          */
+int sfh_comm_p2p_enable(sfh_ctx *c, int on);
+/* How this context reduces: *mode = 0 single GPU, 1 NCCL all-reduce on the context stream, 2 one-shot NVLink exchange
+ * inside the finalize kernel (fused path) with NCCL for the other paths.  Every output is nullable.                */
+int sfh_ctx_comm_info(const sfh_ctx *c, int *nranks, int *rank, int *mode);
 
 /* ---- device-side plumbing (no host round trip; used by bench.py and torch interop) ---------- */
 /* Enqueue one fused evaluation on the ctx stream.  d_coeffs: device, ntemplates doubles.

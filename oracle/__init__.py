@@ -100,6 +100,8 @@ def _declare(L):
     L.sfho_gaussian_psf_covariant.restype = dbl
     L.sfho_mcmc_logl_f64.restype = None
     L.sfho_num_threads.restype = C.c_int
+    L.sfho_set_num_threads.restype = None
+    L.sfho_set_num_threads.argtypes = [C.c_int]
 
 
 def _suf(dtype) -> str:
@@ -241,6 +243,11 @@ def blas_threads() -> int:
 
 def num_threads() -> int:
     return int(lib().sfho_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """omp_set_num_threads for the OpenMP routes (launchers such as torchrun export OMP_NUM_THREADS=1)."""
+    lib().sfho_set_num_threads(int(n))
 
 
 # ------------------------------------------------------------------ hierarchical

@@ -280,6 +280,16 @@ int sfho_num_threads(void)
 #endif
 }
 
+/* bench.py's reference arm: launchers (torchrun) export OMP_NUM_THREADS=1 to their workers */
+void sfho_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Template construction: bin_cmd_smooth (src/StarFormationHistories.jl:574-621) = one addstar! per point
  * (:348-364 pixel-space kernel, :366-408 real-space kernel) of

@@ -11,5 +11,6 @@ dt = np.dtype(sys.argv[8] if len(sys.argv) > 8 else 'float64')
 x = 100 * np.random.default_rng(0).random(nt)
 ds = S.DeviceStack.synthetic(nb, nt, dt.type, seed=1, scale=1.0, x_true=x, tile_bins=bt, cluster=c, consumer_warps=nw, variant=var)
 i = ds.info()
-ms, msk = ds.time_fg(x, reps=reps, flush_l2=False)
-print(f"nb={nb} nt={nt} {dt} GB/s={nb*nt*dt.itemsize/msk/1e6:.0f} nw={i.consumer_warps} rt={i.register_tile} pipe={i.pipelined} bt={i.tile_bins} c={i.cluster} kt={i.chunks_per_tile} ring={i.ring_slots} ncl={i.n_clusters} kernel={msk*1e3:.1f} us")
+want_g = os.environ.get('SFH_WANT_G', '1') != '0'
+ms, msk = ds.time_fg(x, reps=reps, want_G=want_g, flush_l2=False)
+print(f"nb={nb} nt={nt} {dt} GB/s={nb*nt*dt.itemsize/msk/1e6:.0f} nw={i.consumer_warps} variant={i.variant} bt={i.tile_bins} c={i.cluster} kt={i.chunks_per_tile} ring={i.ring_slots} ncl={i.n_clusters} kernel={msk*1e3:.1f} us eval={ms*1e3:.1f} us want_G={int(want_g)}")

@@ -25,7 +25,7 @@ def run(nb, nt, dtype, combos, reps=30, label=""):
             print(f"nw={nw:2d} bt={bt:3d} c={c:2d} var={var}  not fused"); ds.close(); continue
         ds.time_fg(x, reps=5, flush_l2=False)
         ms, msk = ds.time_fg(x, reps=reps, flush_l2=(nb * nt * es < 400e6))
-        print(f"nw={i.consumer_warps:2d} rt={i.register_tile} bt={i.tile_bins:3d} c={i.cluster:2d} kt={i.chunks_per_tile:2d} ring={i.ring_slots:2d} ncl={i.n_clusters:3d}  "
+        print(f"nw={i.consumer_warps:2d} variant={i.variant} bt={i.tile_bins:3d} c={i.cluster:2d} kt={i.chunks_per_tile:2d} ring={i.ring_slots:2d} ncl={i.n_clusters:3d}  "
               f"eval={ms*1e3:8.1f} us kernel={msk*1e3:8.1f} us  {bytes_alg/msk/1e6:7.0f} GB/s  frac={bytes_alg/msk/1e6/PEAK:.3f}", flush=True)
         ds.close()
 

@@ -39,7 +39,7 @@ class sfh_info(C.Structure):
                 ("ld", C.c_int64), ("dtype", C.c_int32), ("device", C.c_int32), ("fused", C.c_int32),
                 ("tile_bins", C.c_int32), ("cluster", C.c_int32), ("chunks_per_tile", C.c_int32),
                 ("ring_slots", C.c_int32), ("n_clusters", C.c_int32), ("consumer_warps", C.c_int32), ("sm_count", C.c_int32),
-                ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("register_tile", C.c_int32), ("panel_layout", C.c_int32), ("pipelined", C.c_int32),
+                ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("variant", C.c_int32), ("panel_layout", C.c_int32), ("reserved0", C.c_int32),
                 ("stack_bytes", C.c_int64), ("clamp_eps", C.c_double)]
 
 
@@ -118,6 +118,8 @@ PROTOTYPES = {
     "sfh_comm_init": (_int, [_vp, _int, _int, _vp]),
     "sfh_comm_p2p_handle": (_int, [_vp, _int, _vp]),
     "sfh_comm_p2p_init": (_int, [_vp, _int, _int, _vp]),
+    "sfh_comm_p2p_enable": (_int, [_vp, _int]),
+    "sfh_ctx_comm_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "sfh_enqueue_fg": (_int, [_vp, _vp, _vp, _int]),
     "sfh_enqueue_logl_batched": (_int, [_vp, _vp, _i64, _vp]),
     "sfh_ctx_synchronize": (_int, [_vp]),

@@ -22,7 +22,7 @@
 
 #include "sfh_batched.cuh"
 #include "sfh_fused.cuh"
-#include "sfh_fused_pipe.cuh"
+#include "sfh_fused2.cuh"
 #include "sfh_small.cuh"
 #include "sfh_ensemble.cuh"
 #include "sfh_templates.cuh"
@@ -154,8 +154,8 @@ struct sfh_stack {
     // kernel configuration
     bool fused = false;
     int bt = 0, cluster = 1, kt = 0, ring = 0, n_clusters = 0, n_tiles = 0, nw = 16;
-    bool rt = false;  // register-resident tile variant
-    bool pipe = false;  // two tiles in flight (sfh_fused_pipe.cuh; opt-in, sfh_opts.variant = 3)
+    bool v2 = false;  // warp-specialised stream kernel (sfh_fused2.cuh); else the cluster-tile kernel (sfh_fused.cuh)
+    int lpr = 1;      // v2: lanes per template row (bt = lpr * 16 / sizeof(S))
     uint32_t smem = 0;
     bool evict_first = false;
     bool panel = false;   // device layout: bin-major panels of `bt` bins (see StackLayout); SFH_PANEL=0 forces column-major
@@ -204,7 +204,8 @@ struct sfh_ctx {
     double **d_peers = nullptr;          // device array of nranks inbox pointers (own + IPC-opened)
     std::vector<void *> ipc_opened;
     int64_t p2p_vlen = 0;
-    unsigned long long p2p_epoch = 0;
+    unsigned long long *d_epoch = nullptr;   // device: evaluations exchanged so far (owned by the finalize kernel's last block)
+    double *d_shard_out = nullptr;           // this shard's own [logL, G] before the exchange
     bool p2p = false;
     // timing / stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -274,57 +275,10 @@ cudaError_t launch_fused_t(const sfh_stack *s, const FusedParams &p, cudaStream_
     return cudaLaunchKernelEx(&cfg, sfh_fg_fused_kernel<S, BT, NW, G, RT>, s->tmap_full, s->tmap_tail, p);
 }
 
-// ---- the pipelined variant (sfh_fused_pipe.cuh): gradient evaluations only, shared-memory tile, NW = 8 or 16 ----
-template <typename S, int BT, int NW>
-cudaError_t pipe_op(const sfh_stack *s, int op, const FusedParams *p, cudaStream_t st, int *maxcl) {
-    auto k = sfh_fg_fused_pipe_kernel<S, BT, NW>;
-    if (op == 0) {   // attributes
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-        if (e == cudaSuccess && s->cluster > 8) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        return e;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(op == 1 ? s->cluster * 1024u : (unsigned)(s->n_clusters * s->cluster));
-    cfg.blockDim = dim3((NW + kProducerWarps) * 32);
-    cfg.dynamicSmemBytes = s->smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = s->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    if (op == 1) { cfg.numAttrs = 1; return cudaOccupancyMaxActiveClusters(maxcl, k, &cfg); }   // occupancy
-    cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, k, s->tmap_full, s->tmap_tail, *p);                        // launch
-}
-cudaError_t pipe_dispatch(const sfh_stack *s, int op, const FusedParams *p, cudaStream_t st, int *maxcl) {
-#define SFH_PIPE_NW(S, BT) (s->nw == 8 ? pipe_op<S, BT, 8>(s, op, p, st, maxcl) : pipe_op<S, BT, 16>(s, op, p, st, maxcl))
-    if (s->dtype == SFH_F64) {
-        switch (s->bt) {
-        case 64: return SFH_PIPE_NW(double, 64);
-        case 32: return SFH_PIPE_NW(double, 32);
-        case 16: return SFH_PIPE_NW(double, 16);
-        default: return SFH_PIPE_NW(double, 8);
-        }
-    }
-    switch (s->bt) {
-    case 128: return SFH_PIPE_NW(float, 128);
-    case 64: return SFH_PIPE_NW(float, 64);
-    case 32: return SFH_PIPE_NW(float, 32);
-    case 16: return SFH_PIPE_NW(float, 16);
-    default: return SFH_PIPE_NW(float, 8);
-    }
-#undef SFH_PIPE_NW
-}
-
-// kernel variants: (NW=16, smem tile) (NW=8, smem tile, 2 CTAs/SM) (NW=8, register tile) (NW=12, register tile)
-#define SFH_DISPATCH_G(S, BT, NW, RT, want_g, CALL) ((want_g) ? CALL(S, BT, NW, true, RT) : CALL(S, BT, NW, false, RT))
-#define SFH_DISPATCH_NW(S, BT, s, want_g, CALL)                                                    \
-    ((s)->rt ? (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, true, want_g, CALL)                     \
-                               : SFH_DISPATCH_G(S, BT, 12, true, want_g, CALL))                   \
-             : (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, false, want_g, CALL)                    \
-                               : SFH_DISPATCH_G(S, BT, 16, false, want_g, CALL)))
+// v1 kernel variants: NW = 16 consumer warps (one CTA per SM) or NW = 8 (two CTAs per SM)
+#define SFH_DISPATCH_G(S, BT, NW, want_g, CALL) ((want_g) ? CALL(S, BT, NW, true, false) : CALL(S, BT, NW, false, false))
+#define SFH_DISPATCH_NW(S, BT, s, want_g, CALL) \
+    (((s)->nw == 8) ? SFH_DISPATCH_G(S, BT, 8, want_g, CALL) : SFH_DISPATCH_G(S, BT, 16, want_g, CALL))
 #define SFH_DISPATCH(s, want_g, CALL)                                      \
     [&]() -> cudaError_t {                                                 \
         if ((s)->dtype == SFH_F64) {                                       \
@@ -345,29 +299,105 @@ cudaError_t pipe_dispatch(const sfh_stack *s, int op, const FusedParams *p, cuda
         }                                                                  \
     }()
 
-// choose consumer warps / tile / cluster / ring for this stack; false if the fused tiling cannot hold T.
-// Candidates are scored by a simple model fitted to the round-1 sweeps (profiles/round1_sweep.md):
+// ---- v2 (sfh_fused2.cuh): S x LPR x WANT_G ----
+template <typename S, int LPR, bool G>
+cudaError_t v2_op(const sfh_stack *s, int op, const Fused2Params *p, cudaStream_t st, int *maxcl) {
+    auto k = sfh_fg_fused2_kernel<S, LPR, G>;
+    if (op == 0) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(op == 1 ? s->cluster * 1024u : (unsigned)(s->n_clusters * s->cluster));
+    cfg.blockDim = dim3(kV2Threads);
+    cfg.dynamicSmemBytes = s->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    if (op == 1) { cfg.numAttrs = 1; return cudaOccupancyMaxActiveClusters(maxcl, k, &cfg); }
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, k, *p);
+}
+template <typename S>
+cudaError_t v2_dispatch_lpr(const sfh_stack *s, int op, bool g, const Fused2Params *p, cudaStream_t st, int *maxcl) {
+#define SFH_V2(L) (g ? v2_op<S, L, true>(s, op, p, st, maxcl) : v2_op<S, L, false>(s, op, p, st, maxcl))
+    switch (s->lpr) {
+    case 32: return SFH_V2(32);
+    case 16: return SFH_V2(16);
+    case 8: return SFH_V2(8);
+    case 4: return SFH_V2(4);
+    case 2: return SFH_V2(2);
+    default: return SFH_V2(1);
+    }
+#undef SFH_V2
+}
+// op: 0 = set attributes, 1 = occupancy (max co-resident clusters), 2 = launch
+cudaError_t v2_dispatch(const sfh_stack *s, int op, bool g, const Fused2Params *p, cudaStream_t st, int *maxcl) {
+    return s->dtype == SFH_F64 ? v2_dispatch_lpr<double>(s, op, g, p, st, maxcl) : v2_dispatch_lpr<float>(s, op, g, p, st, maxcl);
+}
+
+// ---- v2 tiling: lanes per template row (=> bins per tile), cluster size, chunks per tile, ring stages ----
+// One CTA per SM.  What the sweeps under profiles/r2_* say matters, in this order:
+//   * every SM must host a CTA: clusters of 1 and 2 pack all 148 SMs, 4 -> 132, 8 -> 120;
+//   * the ring should hold >= ~2.5 tiles so that the A warps keep streaming while the B warps wait for a residual;
+//   * a tile must be long enough for the (serial) reducer warp to keep up: >= ~32 KB per CTA.
+bool choose_config_v2(sfh_stack *s, const sfh_opts *o) {
+    const int es = (int)elem_size(s->dtype), vec = 16 / es;
+    const int cl_opts[4] = {1, 2, 4, 8};
+    double best = -1.0;
+    int b_lpr = 0, b_c = 0, b_kt = 0, b_ns = 0;
+    for (int lpr = 1; lpr <= 32; lpr <<= 1) {
+        const int bt = vec * lpr, rpc = 256 / lpr;
+        if (o && o->tile_bins && o->tile_bins != bt) continue;
+        for (int c : cl_opts) {
+            if (o && o->cluster && o->cluster != c) continue;
+            const int64_t kt64 = std::max<int64_t>((s->nt + (int64_t)c * rpc - 1) / ((int64_t)c * rpc), 1);
+            if (kt64 > kV2KMax) continue;
+            const int kt = (int)kt64, nst = (kt + kV2G - 1) / kV2G;
+            const Fused2Smem fixed = Fused2Smem::make(0, bt, c);
+            if (fixed.total + 64 >= kMaxDynSmem) continue;
+            int ns = (int)((kMaxDynSmem - fixed.total - 64) / (kV2Stage + 16));
+            ns = std::min(ns, (kV2DS - 1) * nst);   // the slot-reuse argument of sfh_fused2.cuh needs ring <= (DS-1) tiles
+            if (ns < nst + 1 && ns < 2 * nst) { if (ns < nst) continue; }
+            const double sm_frac = c == 1 ? 1.0 : c == 2 ? 1.0 : c == 4 ? 132.0 / 148.0 : 120.0 / 148.0;
+            const double tile_kb = (double)s->nt * bt * es / c / 1024.0;              // bytes a CTA streams per tile
+            const double ring_tiles = (double)ns / nst;
+            const double ring_f = std::min(1.0, 0.6 + 0.4 * (ring_tiles - 1.0) / 1.5);  // 1 tile: 0.6 ... >= 2.5 tiles: 1
+            const double red_f = std::min(1.0, tile_kb / (c > 1 ? 40.0 : 24.0));      // reducer must keep up with the stream
+            const double fill = (double)s->nt / ((double)c * kt * rpc);               // padding lanes idle, stages part-filled
+            const int64_t n_tiles = (s->rows + bt - 1) / bt;
+            const double waves = (double)n_tiles / (double)std::max(s->sm_count / c, 1);
+            const double balance = waves >= 1.0 ? waves / std::ceil(waves) : waves;
+            const double score = sm_frac * ring_f * red_f * balance * (0.9 + 0.1 * fill);
+            if (score > best) { best = score; b_lpr = lpr; b_c = c; b_kt = kt; b_ns = ns; }
+        }
+    }
+    if (!b_lpr) return false;
+    s->v2 = true; s->lpr = b_lpr; s->bt = vec * b_lpr; s->cluster = b_c; s->kt = b_kt; s->ring = b_ns; s->nw = kV2A;
+    s->smem = Fused2Smem::make(s->ring, s->bt, s->cluster).total;
+    s->n_tiles = (int)((s->rows + s->bt - 1) / s->bt);
+    return true;
+}
+
+// ---- v1 tiling (sfh_fused.cuh): consumer warps / tile / cluster / ring; false if the fused tiling cannot hold T.
+// Candidates are scored by a simple model fitted to the round-1 sweeps (profiles/r1_sweep_*.txt):
 //   * every SM should host a CTA: clusters of 8 only pack 15 per B200 (120 SMs), 4 -> 37, 2 -> 74;
 //   * the per-tile exchange costs ~1 us, so tiles should carry >= ~8 chunks, and two co-resident CTAs
 //     (NW = 8) hide it;
 //   * prefer larger bin tiles (longer contiguous TMA rows) when the above are equal.
-bool choose_config(sfh_stack *s, const sfh_opts *o) {
+bool choose_config_v1(sfh_stack *s, const sfh_opts *o) {
     const int cands64[5] = {64, 32, 16, 8, 8}, cands32[5] = {128, 64, 32, 16, 8};
     const int *cands = (s->dtype == SFH_F64) ? cands64 : cands32;
-    struct Variant { int nw; bool rt; int ctas_per_sm; };
-    const Variant variants[4] = {{12, true, 1}, {8, true, 1}, {8, false, 2}, {16, false, 1}};
+    struct Variant { int nw; int ctas_per_sm; };
+    const Variant variants[2] = {{8, 2}, {16, 1}};
     const int cl_opts[5] = {1, 2, 4, 8, 16};
-    const bool forced = o && (o->tile_bins || o->cluster || o->consumer_warps || o->variant);
-    const int pipe = (o && o->variant == 3) ? 1 : 0;
+    const bool forced = o && (o->tile_bins || o->cluster || o->consumer_warps);
     double best_score = -1.0;
     int best_bt = 0, best_c = 0, best_kt = 0, best_nw = 0, best_ring = 0;
-    bool best_rt = false;
     for (const Variant &v : variants) {
         const int nw = v.nw;
         if (o && o->consumer_warps && o->consumer_warps != nw) continue;
-        if (o && o->variant == 1 && v.rt) continue;   // 1 = shared-memory tile only
-        if (o && o->variant == 2 && !v.rt) continue;  // 2 = register tile only
-        if (o && o->variant == 3 && v.rt) continue;   // 3 = shared-memory tile, two tiles in flight (sfh_fused_pipe.cuh)
         for (int ci = 0; ci < 5; ++ci) {
             const int bt = cands[ci];
             if (ci == 4 && s->dtype == SFH_F64) continue;  // (f64 has four tile widths)
@@ -377,17 +407,16 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
             for (int c : cl_opts) {
                 if (o && o->cluster && o->cluster != c) continue;
                 const int64_t kt64 = std::max<int64_t>((s->nt + (int64_t)c * g.rpc - 1) / ((int64_t)c * g.rpc), 1);
-                if (kt64 > kmax_for(nw, v.rt)) continue;
+                if (kt64 > kmax_for(nw, false)) continue;
                 const int kt = (int)kt64;
                 const uint32_t budget = (v.ctas_per_sm == 2) ? (kMaxDynSmem / 2 - 1024) : kMaxDynSmem;
-                const int G = stage_chunks_for(v.rt);
-                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw, G, pipe);
+                const int G = stage_chunks_for(false);
+                const FusedSmem fixed = FusedSmem::make(0, bt, c, kt * g.rpc, nw, G);
                 if (fixed.total + 64 >= budget) continue;
                 int ring = (int)((budget - fixed.total - 64) / (chunk_bytes(nw) + 16));
                 ring = std::min(ring, 64) / G * G;   // whole pipeline stages
                 const int nst = (kt + G - 1) / G;
-                if (ring / G < (v.rt ? 2 : (pipe ? 2 * nst + 1 : nst + 1))) continue;   // pipe: the previous tile stays resident
-                // --- score (model fitted to profiles/r1_sweep_*.txt) ---
+                if (ring / G < nst + 1) continue;
                 // co-schedulable clusters on a 148-SM B200: size 8 -> 15, size 4 -> 33 (1 CTA/SM) or 71 (2 CTAs/SM)
                 const int slots = s->sm_count * v.ctas_per_sm;
                 int n_cl_max = slots / c;
@@ -399,29 +428,33 @@ bool choose_config(sfh_stack *s, const sfh_opts *o) {
                 const double waves = (double)n_tiles / (double)std::max(n_cl_max, 1);
                 const double balance = waves >= 1.0 ? waves / std::ceil(waves) : waves;  // tail effect
                 const double tile_us = (double)kt * chunk_bytes(nw) * v.ctas_per_sm / 44e3;  // ~44 GB/s per SM
-                // measured: the register-tile variants are consumer-latency bound (2-3 warps per scheduler), not HBM bound
-                const double exposed = pipe ? 0.15 : (v.rt ? 2.5 : (v.ctas_per_sm == 2 ? 0.35 : 1.0));   // of the ~1 us exchange
+                const double exposed = v.ctas_per_sm == 2 ? 0.35 : 1.0;   // of the ~1 us exchange
                 const double eff = tile_us / (tile_us + exposed);
-                const size_t rowb = bt * elem_size(s->dtype);  // contiguous bytes per template row of a TMA box
-                // column-major rows shorter than 256 B cost DRAM efficiency (r1_sweep_config3_*.txt); the panel layout
-                // (always used by the fused path unless SFH_PANEL=0) makes every tile contiguous
-                static const bool colmajor = [] { const char *e = getenv("SFH_PANEL"); return e && atoi(e) == 0; }();
-                const double rowlen = !colmajor ? 1.0 : (rowb >= 256 ? 1.0 : (rowb >= 128 ? 0.97 : 0.88));
-                const double score = sm_frac * balance * eff * rowlen;
+                const double score = sm_frac * balance * eff;
                 if (score > best_score || (forced && best_bt == 0)) {
                     best_score = score; best_bt = bt; best_c = c; best_kt = kt; best_nw = nw; best_ring = ring;
-                    best_rt = v.rt;
                 }
             }
         }
     }
     if (!best_bt) return false;
-    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt; s->nw = best_nw; s->ring = best_ring; s->rt = best_rt;
-    s->pipe = pipe != 0;
+    s->v2 = false;
+    s->bt = best_bt; s->cluster = best_c; s->kt = best_kt; s->nw = best_nw; s->ring = best_ring;
     const TileGeom g = geom(s->dtype, s->bt, s->nw);
-    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw, stage_chunks_for(s->rt), pipe).total;
+    s->smem = FusedSmem::make(s->ring, s->bt, s->cluster, s->kt * g.rpc, s->nw, stage_chunks_for(false)).total;
     s->n_tiles = (int)((s->rows + s->bt - 1) / s->bt);
     return true;
+}
+
+// sfh_opts.variant: 0 = auto, 1 = cluster-tile kernel (v1), 4 = warp-specialised stream kernel (v2).  SFH_VARIANT overrides "auto".
+bool choose_config(sfh_stack *s, const sfh_opts *o) {
+    int variant = o ? o->variant : 0;
+    if (variant == 0) { if (const char *e = getenv("SFH_VARIANT")) variant = atoi(e); }
+    static const bool colmajor = [] { const char *e = getenv("SFH_PANEL"); return e && atoi(e) == 0; }();
+    if (variant == 1 || colmajor) return choose_config_v1(s, o);   // v2 streams contiguous panels: it needs the panel layout
+    if (variant == 4) return choose_config_v2(s, o);
+    if (o && o->consumer_warps == 16) return choose_config_v1(s, o);
+    return choose_config_v2(s, o) || choose_config_v1(s, o);
 }
 
 int setup_fused(sfh_stack *s, const sfh_opts *o) {
@@ -430,12 +463,24 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
     if (s->cc_major != 10) return SFH_OK;  // TMA/cluster path is written for sm_100a only
     if (s->rows <= 0 || s->nt <= 0) return SFH_OK;
     if (!s->cfg_ok) return SFH_OK;  // (tiling chosen in stack_common_init: the device layout depends on it)
+    if (s->v2) {   // contiguous panel slices through 1-D bulk copies: no tensor map
+        if (!s->panel) return SFH_OK;
+        int maxcl = 0;
+        CU_TRY(v2_dispatch(s, 0, true, nullptr, nullptr, nullptr));
+        CU_TRY(v2_dispatch(s, 0, false, nullptr, nullptr, nullptr));
+        CU_TRY(v2_dispatch(s, 1, true, nullptr, nullptr, &maxcl));
+        if (maxcl <= 0) return SFH_OK;
+        s->n_clusters = std::min(maxcl, s->n_tiles);
+        s->evict_first = (size_t)s->lay.alloc_elems() * elem_size(s->dtype) > s->l2_bytes;
+        s->fused = true;
+        return SFH_OK;
+    }
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return fail(SFH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     const TileGeom g = geom(s->dtype, s->bt, s->nw);
     CUresult r = CUDA_SUCCESS;
     const CUtensorMapDataType tdt = s->dtype == SFH_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    const int G = stage_chunks_for(s->rt);
+    const int G = stage_chunks_for(false);
     const bool one_op = g.rpc * G <= 256;              // a whole stage fits one TMA box (box dims <= 256)
     const int tail = (s->kt % G) ? (s->kt % G) : G;     // chunks in the tile's last stage
     for (int which = 0; which < 2 && r == CUDA_SUCCESS; ++which) {
@@ -468,12 +513,6 @@ int setup_fused(sfh_stack *s, const sfh_opts *o) {
 #define MAX_CL(S, BT, NW, G, RT) max_clusters<S, BT, NW, G, RT>(s, &maxcl)
     CU_TRY(SFH_DISPATCH(s, true, MAX_CL));
 #undef MAX_CL
-    if (s->pipe) {   // the gradient evaluations use the pipelined kernel: same block and smem, possibly other registers
-        int maxcl_p = 0;
-        CU_TRY(pipe_dispatch(s, 0, nullptr, nullptr, nullptr));
-        CU_TRY(pipe_dispatch(s, 1, nullptr, nullptr, &maxcl_p));
-        maxcl = std::min(maxcl, maxcl_p);
-    }
     if (maxcl <= 0) return SFH_OK;  // cannot co-schedule this cluster shape: stay unfused
     s->n_clusters = std::min(maxcl, s->n_tiles);
     // the stack is streamed exactly once per evaluation: do not let it evict the O(Nb) vectors
@@ -678,8 +717,8 @@ static int sfh_stack_info_impl(const sfh_stack *s, sfh_info *info) {
     info->nbins_total = s->nb_total; info->ntemplates = s->nt; info->row_begin = s->row_begin; info->row_end = s->row_end;
     info->ld = s->lay.ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
     info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
-    info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->register_tile = s->rt ? 1 : 0; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
-    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->pipelined = s->pipe ? 1 : 0; info->clamp_eps = s->eps;
+    info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->variant = s->fused ? (s->v2 ? 4 : 1) : 0; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
+    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->reserved0 = 0; info->clamp_eps = s->eps;
     return SFH_OK;
 }
 extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
@@ -759,7 +798,7 @@ static int sfh_ctx_destroy_impl(sfh_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(c->d_inbox); cudaFree(c->d_peers);
+    cudaFree(c->d_inbox); cudaFree(c->d_peers); cudaFree(c->d_epoch); cudaFree(c->d_shard_out);
     for (auto *g : {&c->g_fg[0], &c->g_fg[1], &c->g_hier})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     cudaFree(c->d_coeffs); cudaFree(c->d_out); cudaFree(c->d_composite); cudaFree(c->d_residual);
@@ -805,20 +844,21 @@ extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce, double *out_host = nullptr,
-                    bool p2p_push = false) {
+                    bool p2p_push = false, bool logl_from_fused = false) {
     const sfh_stack *s = c->s;
     FinalizeParams fp{};
     fp.nb = s->rows; fp.nt = s->nt; fp.gstride = c->gstride; fp.n_clusters = s->n_clusters; fp.want_G = want_G_reduce;
     fp.eps = s->eps; fp.composite = composite; fp.data = s->d_data; fp.gpart = c->d_gpart; fp.out = d_out;
     fp.out_host = out_host; fp.lpart = c->d_lpart; fp.ticket = c->d_ticket;
+    if (logl_from_fused) { fp.lpart_in = c->d_lpart; fp.n_lpart_in = s->n_clusters; }
     if (p2p_push) {
         fp.peers = c->d_peers; fp.nranks = c->nranks; fp.rank = c->rank; fp.vlen = c->p2p_vlen;
-        fp.npush = want_G_reduce ? 1 + s->nt : 1; fp.epoch = c->p2p_epoch;
+        fp.shard_out = c->d_shard_out; fp.epoch_ptr = c->d_epoch;
     }
     // enough blocks that every thread has <= 1 bin and every warp <= 1 template (latency-bound kernel)
     const int64_t cap = 4 * std::max(s->sm_count, 1);
     const int64_t nblk_l = std::min<int64_t>(std::max<int64_t>((s->rows + kFinalizeThreads - 1) / kFinalizeThreads, 1), cap);
-    const int64_t need = std::max<int64_t>(nblk_l, want_G_reduce ? (s->nt + 7) / 8 : 0);
+    const int64_t need = std::max<int64_t>(logl_from_fused ? 1 : nblk_l, want_G_reduce ? (s->nt + 7) / 8 : 0);
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(need, 1), cap);
     fp.nblk_logl = (int32_t)nblk_l;
     CU_TRY(launch_pdl(sfh_finalize_kernel, dim3(grid), dim3(kFinalizeThreads), 0, c->stream, fp));
@@ -836,27 +876,29 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         return SFH_OK;
     }
     if (s->fused) {
-        FusedParams p{};
-        p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ring = s->ring; p.n_tiles = s->n_tiles;
-        p.evict_first = s->evict_first ? 1 : 0; p.l2_prefetch = s->l2_prefetch; p.panel = s->panel ? 1 : 0; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
-        p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
-        p.gstride = c->gstride;
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk0, c->stream));
+        if (s->v2) {
+            Fused2Params p{};
+            p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ns = s->ring; p.n_tiles = s->n_tiles;
+            p.evict_first = s->evict_first ? 1 : 0; p.eps = s->eps; p.M = s->dM; p.coeffs = d_coeffs; p.data = s->d_data;
+            p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
+            p.lpart = c->d_lpart; p.gstride = c->gstride;
+            CU_TRY(v2_dispatch(s, 2, want_G != 0, &p, c->stream, nullptr));
+        } else {
+            FusedParams p{};
+            p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ring = s->ring; p.n_tiles = s->n_tiles;
+            p.evict_first = s->evict_first ? 1 : 0; p.l2_prefetch = s->l2_prefetch; p.panel = s->panel ? 1 : 0; p.eps = s->eps; p.coeffs = d_coeffs; p.data = s->d_data;
+            p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
+            p.gstride = c->gstride;
 #define LAUNCH(S, BT, NW, G, RT) launch_fused_t<S, BT, NW, G, RT>(s, p, c->stream)
-        if (s->pipe && want_G) CU_TRY(pipe_dispatch(s, 2, &p, c->stream, nullptr));
-        else CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
+            CU_TRY(SFH_DISPATCH(s, want_G != 0, LAUNCH));
 #undef LAUNCH
+        }
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
         c->stats.kernel_launches++;
         fused_p2p = c->p2p;
-        if (fused_p2p) ++c->p2p_epoch;
-        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, c->comm ? nullptr : out_host, fused_p2p));
-        if (fused_p2p) {
-            const int64_t n = want_G ? 1 + s->nt : 1;
-            CU_TRY(launch_pdl(sfh_p2p_combine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c->stream,
-                              (const double *)c->d_inbox, c->nranks, c->p2p_vlen, n, c->p2p_epoch, d_out));
-            c->stats.kernel_launches++;
-        }
+        // single GPU, or the one-shot exchange (whose last block holds the all-reduced answer): results go straight to pinned memory
+        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, (c->nranks > 1 && !fused_p2p) ? nullptr : out_host, fused_p2p, s->v2));
     } else {
         out_host = nullptr;  // the two-pass path writes G with gemv 'T': results are copied back explicitly
         // two-pass path: gemv 'N' -> logL -> residual -> gemv 'T'  (the reference's own pass structure)
@@ -882,7 +924,8 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         }
         if (time_kernel) CU_TRY(cudaEventRecord(c->evk1, c->stream));
     }
-    if (c->comm && !fused_p2p) {
+    if (c->nranks > 1 && !fused_p2p) {
+        if (!c->comm) return fail(SFH_ERR_NCCL, "sharded context without a communicator");
         const size_t cnt = want_G ? (size_t)(1 + s->nt) : 1;
         int r = g_nccl.AllReduce(d_out, d_out, cnt, kNcclFloat64, kNcclSum, c->comm, c->stream);
         if (r != 0) return fail(SFH_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -896,7 +939,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
 template <typename F>
 int run_graphed(sfh_ctx *c, sfh_ctx::GraphSlot &slot, uint64_t key, F &&enqueue) {
     static const bool disabled = [] { const char *e = getenv("SFH_NO_GRAPH"); return e && e[0] == '1'; }();
-    if (disabled || c->comm) return enqueue();
+    if (disabled || (c->nranks > 1 && !c->p2p)) return enqueue();   // (an NCCL all-reduce is not captured)
     if (slot.exec && slot.key != key) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; slot.failed = false; }
     if (!slot.exec && !slot.failed) {
         const sfh_stats before = c->stats;
@@ -947,7 +990,7 @@ static int sfh_eval_fg_impl(sfh_ctx *c, const double *coeffs, double *neg_logL, 
     const int want_G = G != nullptr;
     memcpy(c->h_in, coeffs, (size_t)s->nt * 8);
     // single-GPU fused path: the finalize kernel stores [logL, G] straight into the mapped pinned buffer
-    const bool direct = s->fused && !c->comm && s->rows > 0 && s->nt > 0;
+    const bool direct = s->fused && (c->nranks == 1 || c->p2p) && s->rows > 0 && s->nt > 0;
     SFH_TRY(run_graphed(c, c->g_fg[want_G], 1, [&]() -> int {
         CU_TRY(cudaMemcpyAsync(c->d_coeffs, c->h_in, (size_t)s->nt * 8, cudaMemcpyHostToDevice, c->stream));
         SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, direct ? c->h_out : nullptr));
@@ -1194,7 +1237,7 @@ static int sfh_eval_fg_hier_impl(sfh_ctx *c, int mh_kind, const double *mh_fixed
     const int want_G = G != nullptr;
     const size_t nv = (size_t)c->nj + 3;
     memcpy(c->h_in, variables, nv * 8);
-    hp.out_host = c->comm ? nullptr : c->h_out;  // epilogue stores [-logL, G] straight into the mapped pinned buffer
+    hp.out_host = (c->nranks > 1 && !c->p2p) ? nullptr : c->h_out;  // epilogue stores [-logL, G] straight into the mapped pinned buffer
     // graph key: everything baked into the captured kernel parameters
     uint64_t key = 0xcbf29ce484222325ull;
     auto mix = [&](const void *ptr, size_t n) { for (size_t i = 0; i < n; ++i) key = (key ^ ((const unsigned char *)ptr)[i]) * 0x100000001b3ull; };
@@ -1692,6 +1735,11 @@ extern "C" int sfh_comm_p2p_handle(sfh_ctx *c, int nranks, void *handle64_out) {
 static int sfh_comm_p2p_init_impl(sfh_ctx *c, int nranks, int rank, const void *handles) {
     if (!c || !handles || nranks < 1 || rank < 0 || rank >= nranks) return fail(SFH_ERR_INVALID_ARG, "bad argument");
     if (!c->d_inbox) return fail(SFH_ERR_INVALID_ARG, "call sfh_comm_p2p_handle first");
+    // the two-pass, batched-walker and helper paths reduce with NCCL: a context with peer inboxes but no communicator would
+    // return un-reduced shard values from those
+    if (!c->comm || c->nranks != nranks || c->rank != rank)
+        return fail(SFH_ERR_INVALID_ARG, "call sfh_comm_init(nranks, rank) with the same nranks / rank first");
+    if (c->p2p) return fail(SFH_ERR_INVALID_ARG, "one-shot exchange already initialised on this context");
     if (nranks > 32) return fail(SFH_ERR_UNSUPPORTED, "too many ranks for the one-shot reduce");
     CU_TRY(cudaSetDevice(c->s->device));
     std::vector<double *> peers((size_t)nranks, nullptr);
@@ -1710,12 +1758,40 @@ static int sfh_comm_p2p_init_impl(sfh_ctx *c, int nranks, int rank, const void *
     }
     CU_TRY(cudaMalloc((void **)&c->d_peers, (size_t)nranks * sizeof(double *)));
     CU_TRY(cudaMemcpy(c->d_peers, peers.data(), (size_t)nranks * sizeof(double *), cudaMemcpyHostToDevice));
-    c->nranks = nranks; c->rank = rank; c->p2p_epoch = 0;
+    CU_TRY(cudaMalloc((void **)&c->d_epoch, 8));
+    CU_TRY(cudaMemset(c->d_epoch, 0, 8));
+    CU_TRY(cudaMalloc((void **)&c->d_shard_out, (size_t)c->p2p_vlen * 8));
+    CU_TRY(cudaMemset(c->d_shard_out, 0, (size_t)c->p2p_vlen * 8));
+    c->nranks = nranks; c->rank = rank;
     c->p2p = true;
     return SFH_OK;
 }
 extern "C" int sfh_comm_p2p_init(sfh_ctx *c, int nranks, int rank, const void *handles) {
     return guarded([&]() -> int { return sfh_comm_p2p_init_impl(c, nranks, rank, handles); });
+}
+
+extern "C" int sfh_comm_p2p_enable(sfh_ctx *c, int on) {
+    return guarded([&]() -> int {
+        if (!c) return fail(SFH_ERR_INVALID_ARG, "NULL ctx");
+        if (on && !(c->d_peers && c->d_epoch)) return fail(SFH_ERR_INVALID_ARG, "sfh_comm_p2p_init has not succeeded on this context");
+        CU_TRY(cudaSetDevice(c->device));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        c->p2p = on != 0;
+        // captured graphs bake the reduction mode in
+        for (auto *g : {&c->g_fg[0], &c->g_fg[1], &c->g_hier})
+            if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; g->failed = false; }
+        return SFH_OK;
+    });
+}
+
+extern "C" int sfh_ctx_comm_info(const sfh_ctx *c, int *nranks, int *rank, int *mode) {
+    return guarded([&]() -> int {
+        if (!c) return fail(SFH_ERR_INVALID_ARG, "NULL ctx");
+        if (nranks) *nranks = c->nranks;
+        if (rank) *rank = c->rank;
+        if (mode) *mode = c->nranks <= 1 ? 0 : (c->p2p ? 2 : 1);
+        return SFH_OK;
+    });
 }
 
 // ---------------------------------------------------------------------------------------------

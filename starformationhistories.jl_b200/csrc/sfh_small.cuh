@@ -71,13 +71,17 @@ struct FinalizeParams {
     double *out;       // device [1 + nt]
     double *out_host;  // nullable: mapped pinned host copy of the same (saves the D2H memcpy of the sync API)
     double *lpart;     // [gridDim.x] per-block logL partials
+    const double *lpart_in;  // nullable: the fused kernel (v2) already summed the Poisson terms per cluster -> [n_lpart_in]
+    int32_t n_lpart_in;
     unsigned int *ticket;
     // K7 v2: one-shot all-reduce over NVLink peer memory, fused into this kernel's tail (nullptr = off).
     // peers[r] = rank r's inbox, laid out [2 parities][nranks][vlen] doubles then [2][nranks] uint64 epoch flags.
     double *const *peers;
     int32_t nranks, rank;
-    int64_t vlen, npush;
-    unsigned long long epoch;
+    int64_t vlen;
+    double *shard_out;              // device [1 + nt]: this shard's own [logL, G] before the exchange
+    unsigned long long *epoch_ptr;  // device: evaluations exchanged so far on this context (read and bumped by the last
+                                    // block only, so a captured CUDA graph of the evaluation can be replayed)
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
@@ -94,21 +98,29 @@ constexpr int kFinalizeThreads = 256;
 // ever waits on more than ~2 dependent L2 round trips.  Measured alternatives (ncu launch lists under profiles/):
 // 296 blocks with a per-thread serial loop over the cluster partials 13 us; one 8-CTA cluster with a DSMEM
 // reduction 27 us (too few threads: 15 dependent load+log chains each).
+//
+// Multi-GPU (p.peers): the LAST block to finish is the whole exchange -- it pushes this shard's [logL, G] into slot
+// [parity][rank] of every rank's inbox with coalesced 16-byte NVLink stores, issues ONE system-scope fence, publishes
+// the epoch flags, waits for the nranks flags in its own inbox and sums the nranks vectors in rank order (identical
+// order on every rank => bit-identical results everywhere).  Round 1 fenced at system scope in every block, pushed
+// scalar stores from 2400 warps and needed a third kernel for the sum: ~20 us per step at 8 GPUs.
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
     griddep_wait();  // PDL: launched while the fused kernel drains
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t par = (int64_t)(p.epoch & 1ull);
+    double *const gout = p.peers ? p.shard_out : p.out;
     // logL: fixed contiguous slice of bins per block, fixed trees => deterministic
-    const int64_t per = (p.nb + p.nblk_logl - 1) / p.nblk_logl;
-    const int64_t b0 = (int64_t)blockIdx.x * per;
-    const int64_t b1 = ((int)blockIdx.x >= p.nblk_logl) ? b0 : ((b0 + per < p.nb) ? b0 + per : p.nb);
-    double acc = 0.0;
-    for (int64_t i = b0 + threadIdx.x; i < b1; i += kFinalizeThreads)
-        acc += poisson_term(__ldcg(p.composite + i), p.data[i], p.eps);
-    const double tot = block_sum<kFinalizeThreads>(acc, sh);
-    if (threadIdx.x == 0) p.lpart[blockIdx.x] = tot;
+    if (!p.lpart_in) {
+        const int64_t per = (p.nb + p.nblk_logl - 1) / p.nblk_logl;
+        const int64_t b0 = (int64_t)blockIdx.x * per;
+        const int64_t b1 = ((int)blockIdx.x >= p.nblk_logl) ? b0 : ((b0 + per < p.nb) ? b0 + per : p.nb);
+        double acc = 0.0;
+        for (int64_t i = b0 + threadIdx.x; i < b1; i += kFinalizeThreads)
+            acc += poisson_term(__ldcg(p.composite + i), p.data[i], p.eps);
+        const double tot = block_sum<kFinalizeThreads>(acc, sh);
+        if (threadIdx.x == 0) p.lpart[blockIdx.x] = tot;
+    }
 
     // G_j = sum over clusters: one WARP per template, lanes take clusters lane, lane+32, ... (independent loads)
     if (p.want_G) {
@@ -118,59 +130,67 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
             for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
             s = warp_sum(s);
             if (lane == 0) {
-                p.out[1 + j] = s;
-                if (p.out_host) p.out_host[1 + j] = s;
+                gout[1 + j] = s;
+                if (p.out_host && !p.peers) p.out_host[1 + j] = s;
             }
-            // one-shot all-reduce, push half: every warp stores ITS gradient entry into slot [parity][rank] of every
-            // rank's inbox (plain NVLink stores, spread over the whole grid)
-            if (p.peers && lane < p.nranks)
-                p.peers[lane][(par * p.nranks + p.rank) * p.vlen + 1 + j] = s;
         }
     }
     // last block folds the per-block logL partials (parallel, fixed order)
-    if (p.peers) __threadfence_system();  // this block's peer stores are visible before its ticket is taken
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (last) {
-        __threadfence();
-        double s = 0.0;
-        for (int b = threadIdx.x; b < p.nblk_logl; b += kFinalizeThreads) s += __ldcg(p.lpart + b);
-        const double all = block_sum<kFinalizeThreads>(s, sh);
-        if (threadIdx.x == 0) {
-            p.out[0] = all;
-            if (p.out_host) p.out_host[0] = all;
-            *p.ticket = 0u;  // re-arm for the next evaluation on this context
-        }
-        if (p.peers && threadIdx.x < p.nranks) {
-            // every block fenced its gradient pushes before taking its ticket; this (last) block adds logL and then
-            // publishes the epoch with a system-scope release: compute and exchange are ONE kernel, no NCCL call
-            double *dst = p.peers[threadIdx.x] + (par * p.nranks + p.rank) * p.vlen;
-            dst[0] = all;  // block_sum leaves the total in every lane of warp 0 (nranks <= 32)
-            __threadfence_system();
-            unsigned long long *flags = reinterpret_cast<unsigned long long *>(p.peers[threadIdx.x] + 2 * p.nranks * p.vlen);
-            st_release_sys_u64(flags + par * p.nranks + p.rank, p.epoch);
+    if (!last) return;
+    __threadfence();
+    double s = 0.0;
+    const double *lp = p.lpart_in ? p.lpart_in : p.lpart;
+    const int nlp = p.lpart_in ? p.n_lpart_in : p.nblk_logl;
+    for (int b = threadIdx.x; b < nlp; b += kFinalizeThreads) s += __ldcg(lp + b);
+    const double all = block_sum<kFinalizeThreads>(s, sh);
+    if (threadIdx.x == 0) {
+        gout[0] = all;
+        if (p.out_host && !p.peers) p.out_host[0] = all;
+        *p.ticket = 0u;  // re-arm for the next evaluation on this context
+    }
+    if (!p.peers) return;
+
+    // ---------------- one-shot all-reduce, entirely inside this block ----------------
+    __shared__ unsigned long long s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = *p.epoch_ptr + 1ull;
+        *p.epoch_ptr = s_epoch;
+    }
+    __syncthreads();   // also orders thread 0's store of gout[0] before the reads below
+    const unsigned long long epoch = s_epoch;
+    const int64_t par = (int64_t)(epoch & 1ull);
+    const int64_t n = p.want_G ? 1 + p.nt : 1;
+    const int64_t n2 = (n + 1) / 2;               // 16-byte units (vlen is even, inboxes are 16-byte aligned)
+    // push: every peer gets the vector as coalesced double2 stores; reads come from L2 (written by other blocks)
+    for (int64_t i = threadIdx.x; i < n2; i += kFinalizeThreads) {
+        double2 v;
+        v.x = __ldcg(gout + 2 * i);
+        v.y = (2 * i + 1 < n) ? __ldcg(gout + 2 * i + 1) : 0.0;
+        for (int r = 0; r < p.nranks; ++r) {
+            double2 *dst = reinterpret_cast<double2 *>(p.peers[r] + (par * p.nranks + p.rank) * p.vlen) + i;
+            *dst = v;
         }
     }
-}
-
-// second half of the one-shot all-reduce: wait until every rank's epoch flag has arrived in MY inbox, then sum the
-// nranks vectors in rank order (identical order on every rank => bit-identical results everywhere, deterministic)
-__global__ void __launch_bounds__(256) sfh_p2p_combine_kernel(const double *inbox, int nranks, int64_t vlen, int64_t n,
-                                                              unsigned long long epoch, double *out) {
-    griddep_wait();
-    const int64_t par = (int64_t)(epoch & 1ull);
-    const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(inbox + 2 * nranks * vlen) + par * nranks;
-    if (threadIdx.x < nranks) {
-        while (ld_acquire_sys_u64(flags + threadIdx.x) != epoch) { }
+    __threadfence_system();   // every thread: its peer stores are performed system-wide before the flag is published
+    __syncthreads();
+    if (threadIdx.x < p.nranks) {
+        unsigned long long *flags = reinterpret_cast<unsigned long long *>(p.peers[threadIdx.x] + 2 * p.nranks * p.vlen);
+        st_release_sys_u64(flags + par * p.nranks + p.rank, epoch);
+        // ... and wait for every rank's vector to have landed in MY inbox
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.peers[p.rank] + 2 * p.nranks * p.vlen) + par * p.nranks;
+        while (ld_acquire_sys_u64(mine + threadIdx.x) != epoch) { }
     }
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        double s = 0.0;
-        for (int r = 0; r < nranks; ++r) s += __ldcg(inbox + (par * nranks + r) * vlen + i);
-        out[i] = s;
+    const double *inbox = p.peers[p.rank] + par * p.nranks * p.vlen;
+    for (int64_t i = threadIdx.x; i < n; i += kFinalizeThreads) {
+        double t = 0.0;
+        for (int r = 0; r < p.nranks; ++r) t += __ldcv(inbox + r * p.vlen + i);
+        p.out[i] = t;
+        if (p.out_host) p.out_host[i] = t;
     }
 }
 

@@ -75,26 +75,55 @@ def init_library_comm(ctx, group=None, p2p=True):
     uid = broadcast_bytes(bytes(idbuf) if rank == 0 else None, 128, 0, group)
     L.check(L.lib.sfh_comm_init(ctx.handle, world, rank, uid))
     if p2p and world > 1 and os.environ.get("SFH_NO_P2P") != "1":
-        try:
-            init_p2p(ctx, group)
-        except (L.SFHError, ValueError):
-            pass  # no peer access between these devices: the NCCL all-reduce stays in place
+        init_p2p(ctx, group)
     return ctx
 
 
-def init_p2p(ctx, group=None):
+def all_ranks_agree(ok: bool, group=None) -> bool:
+    """MIN over the group of a per-rank success flag: a collective every rank must call."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+    if dist.get_backend(group) == "nccl":
+        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.cpu().item()) == 1)
+
+
+def init_p2p(ctx, group=None, open_handles=None):
     """Exchange the CUDA-IPC handles of the per-rank inboxes and switch the fused path to the one-shot NVLink
-    all-reduce that is fused into the finalize kernel (include/sfhcuda.h: sfh_comm_p2p_*)."""
+    all-reduce inside the finalize kernel (include/sfhcuda.h: sfh_comm_p2p_*).  The switch is all-or-nothing: a rank
+    whose peers' inboxes cannot be opened (no peer access in this topology, IPC disabled in its container) must not
+    leave the others spinning on epoch flags it will never write.  So every rank tries, the group takes the MIN of the
+    success flags, and unless every rank succeeded the ranks that did switch it off again (sfh_comm_p2p_enable(ctx, 0))
+    and the NCCL all-reduce stays in place everywhere (returns False).  No evaluation runs in between.
+    `open_handles(rank, blob) -> None | raises` replaces the library calls in the CPU (gloo) tests."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     h = (C.c_char * 64)()
-    L.check(L.lib.sfh_comm_p2p_handle(ctx.handle, world, h))
+    ok = True
+    try:
+        if open_handles is None:
+            L.check(L.lib.sfh_comm_p2p_handle(ctx.handle, world, h))
+    except (L.SFHError, ValueError):
+        ok = False
     mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).clone()
     if dist.get_backend(group) == "nccl":
         mine = mine.to(torch.device("cuda", torch.cuda.current_device()))
     allh = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allh, mine, group=group)
     blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
-    L.check(L.lib.sfh_comm_p2p_init(ctx.handle, world, rank, blob))
-    return ctx
+    if ok:
+        try:
+            if open_handles is None:
+                L.check(L.lib.sfh_comm_p2p_init(ctx.handle, world, rank, blob))
+            else:
+                open_handles(rank, blob)
+        except (L.SFHError, ValueError):
+            ok = False
+    if all_ranks_agree(ok, group):
+        return True
+    if ok and open_handles is None:
+        L.check(L.lib.sfh_comm_p2p_enable(ctx.handle, 0))
+    return False

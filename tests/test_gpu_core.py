@@ -130,31 +130,30 @@ def test_fg_parity_f64(S, nb, nt):
     assert info.cc_major == 10 and info.fused == 1, "fused sm_100a kernel must be the path that runs"
 
 
-@pytest.mark.parametrize("nw,variant", [(8, 1), (16, 1), (8, 2), (12, 2)])
+@pytest.mark.parametrize("nw", [8, 16])
 @pytest.mark.parametrize("tile,cluster", [(8, 2), (16, 1), (16, 2), (32, 2), (32, 4), (64, 4), (64, 8), (32, 8), (16, 8), (64, 16)])
-def test_fused_configs_agree(S, tile, cluster, nw, variant):
-    """Every kernel variant (shared-memory tile with 8/16 consumer warps, register tile with 8/12) x tile x cluster."""
+def test_fused_configs_agree(S, tile, cluster, nw):
+    """The cluster-tile kernel (sfh_opts.variant = 1) with 8 / 16 consumer warps x tile x cluster."""
     nb, nt = 3001, 517
     M, x, data = make_flat_problem(nb, nt, seed=11)
     nlq, Gq, gs, _ = O.fg_quad(x, M, data)
-    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw, variant=variant)
+    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw, variant=1)
     i = ds.info()
     if not i.fused:
         pytest.skip("this (tile, cluster, warps) combination cannot hold T in its per-lane registers")
-    assert i.tile_bins == tile and i.cluster == cluster and i.consumer_warps == nw and i.register_tile == variant - 1
+    assert i.tile_bins == tile and i.cluster == cluster and i.consumer_warps == nw and i.variant == 1
     nl, G, _ = ds.eval_fg(x)
     assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
     assert_grad_close(G, Gq, gs)
 
 
-@pytest.mark.parametrize("nw,variant,tile,cluster", [(8, 1, 8, 2), (8, 1, 8, 4), (16, 1, 8, 1), (8, 1, 16, 4), (16, 1, 32, 2), (8, 1, 64, 8),
-                                                     (16, 1, 128, 4), (8, 2, 16, 2), (12, 2, 32, 4)])
-def test_fused_configs_f32(S, nw, variant, tile, cluster):
-    """Float32-stored stacks through every tile width (8 ... 128 bins) of the fused kernel."""
+@pytest.mark.parametrize("nw,tile,cluster", [(8, 8, 2), (8, 8, 4), (16, 8, 1), (8, 16, 4), (16, 32, 2), (8, 64, 8), (16, 128, 4)])
+def test_fused_configs_f32(S, nw, tile, cluster):
+    """Float32-stored stacks through every tile width (8 ... 128 bins) of the cluster-tile kernel."""
     nb, nt = 2777, 701
     M, x, data = make_flat_problem(nb, nt, seed=13, dtype=np.float32)
     nlq, Gq, gs = O.fg_quad_f32(x, M, data)
-    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw, variant=variant)
+    ds = S.DeviceStack(M, data, tile_bins=tile, cluster=cluster, consumer_warps=nw, variant=1)
     i = ds.info()
     if not i.fused:
         pytest.skip("combination cannot hold T")
@@ -163,6 +162,39 @@ def test_fused_configs_f32(S, nw, variant, tile, cluster):
     assert nl == pytest.approx(nlq, rel=RTOL_F32)
     assert_grad_close(G, Gq, gs, rtol=RTOL_F32)
     Md, dd = ds.download()                       # the panel re-tiling is invisible to the host
+    assert np.array_equal(Md, M) and np.array_equal(dd, data.astype(np.float64))
+
+
+# the warp-specialised stream kernel (sfh_opts.variant = 4): every lanes-per-row width x cluster size, F64 and F32, with
+# shapes whose last chunk / last stage / last tile are partial and whose slices run past the last template
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("lpr,cluster", [(1, 1), (1, 2), (1, 4), (2, 1), (2, 2), (4, 1), (4, 8), (8, 1), (8, 2), (16, 1), (16, 4), (32, 1), (32, 2)])
+@pytest.mark.parametrize("nb,nt", [(3001, 517), (777, 2400), (4099, 129), (50, 5000)])
+def test_stream_kernel_configs(S, dtype, lpr, cluster, nb, nt):
+    vec = 16 // np.dtype(dtype).itemsize
+    M, x, data = make_flat_problem(nb, nt, seed=17 + lpr, dtype=dtype)
+    ds = S.DeviceStack(M, data, tile_bins=vec * lpr, cluster=cluster, variant=4)
+    i = ds.info()
+    if not i.fused:
+        pytest.skip("this (lanes per row, cluster) combination cannot hold T in its per-lane registers")
+    assert i.variant == 4 and i.tile_bins == vec * lpr and i.cluster == cluster and i.panel_layout == 1
+    nl, G, resid = ds.eval_fg(x * 1.1, want_composite=True)
+    if dtype is np.float64:
+        nlq, Gq, gs, compq = O.fg_quad(x * 1.1, M, data)
+        rt_l, rt_g = RTOL_LOGL, 1e-10
+    else:
+        nlq, Gq, gs = O.fg_quad_f32(x * 1.1, M, data)
+        rt_l, rt_g = RTOL_F32, RTOL_F32
+    assert nl == pytest.approx(nlq, rel=rt_l)
+    assert_grad_close(G, Gq, gs, rtol=rt_g)
+    nl2, G2, comp = ds.eval_fg(x * 1.1, want_G=False, want_composite=True)      # logL-only instantiation: same logL, bit for bit
+    assert G2 is None and nl2 == nl
+    if dtype is np.float64:
+        assert np.allclose(comp, compq, rtol=1e-13, atol=0)
+        assert np.allclose(resid, 1.0 - data / np.maximum(comp, np.finfo(np.float64).eps), rtol=0, atol=0)
+    nl3, G3, _ = ds.eval_fg(x * 1.1)                                            # bitwise run-to-run determinism
+    assert nl3 == nl and np.array_equal(G3, G)
+    Md, dd = ds.download()
     assert np.array_equal(Md, M) and np.array_equal(dd, data.astype(np.float64))
 
 
@@ -360,7 +392,7 @@ def test_full_size_properties(S, nb, nt, dtype):
 
 
 def test_very_wide_stack_falls_back_to_two_pass(S):
-    """More templates than the fused tiling can hold (T > 16 CTAs x 20 chunks x 128 rows): the library must switch to
+    """More templates than the fused tiling can hold (T > 8 CTAs x 20 chunks x 256 rows): the library must switch to
     the two-pass kernels by itself and still match the oracle."""
     nb, nt = 48, 50000
     M, x, data = make_flat_problem(nb, nt, seed=21, scale=0.01)
@@ -370,10 +402,10 @@ def test_very_wide_stack_falls_back_to_two_pass(S):
     nlq, Gq, gs, _ = O.fg_quad(x, M, data)
     assert nl == pytest.approx(nlq, rel=RTOL_LOGL)
     assert_grad_close(G, Gq, gs)
-    # the widest stack the fused path still takes (16-CTA clusters)
+    # a stack near the widest the fused path still takes (8-CTA clusters of the stream kernel, 16 of the cluster-tile kernel)
     M2, x2, d2 = make_flat_problem(40, 30000, seed=22, scale=0.01)
     ds2 = S.DeviceStack(M2, d2)
-    assert ds2.info().fused == 1 and ds2.info().cluster == 16
+    assert ds2.info().fused == 1 and ds2.info().cluster in (8, 16)
     nl2, G2, _ = ds2.eval_fg(x2)
     nlq2, Gq2, gs2, _ = O.fg_quad(x2, M2, d2)
     assert nl2 == pytest.approx(nlq2, rel=RTOL_LOGL)

@@ -135,3 +135,17 @@ def test_native_loop_reports_failures(S):
     th = np.log(np.full(4, 1.0))
     assert L.lib.sfh_fit_templates_bfgs(ds.ctx().handle, L.SFH_FIT_LOG_MLE, th.ctypes.data_as(dp), C.byref(o), C.byref(rep), None) == L.SFH_OK
     assert rep.status == 1 and rep.iterations == 2 and not rep.converged
+
+
+# ---- the BFGS inverse Hessian resident on the device (sfh_bfgs_opts.device_hessian): three kernels in csrc/sfh_small.cuh ----
+@pytest.mark.parametrize("nb,nt", [(10000, 20), (20000, 600)])
+def test_device_hessian_bfgs_matches_host_hessian(S, nb, nt):
+    M, x, data = make_flat_problem(nb, nt)
+    a = S.fit_templates(M, data, x0=np.ones(nt), engine="native")
+    b = S.fit_templates(M, data, x0=np.ones(nt), engine="native", device_hessian=True)
+    for k in ("map", "mle"):
+        assert b[k].result.success == a[k].result.success
+        assert np.linalg.norm(a[k].mu - b[k].mu) <= 1e-6 * np.linalg.norm(a[k].mu)
+        H = b[k].invH
+        assert np.allclose(H, H.T, atol=1e-10 * np.abs(H).max()) and np.all(np.diag(H) > 0)
+        assert np.allclose(np.sqrt(np.diag(H)), np.sqrt(np.diag(a[k].invH)), rtol=0.3)
