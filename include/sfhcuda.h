@@ -392,6 +392,29 @@ int sfh_comm_p2p_enable(sfh_ctx *c, int on);
 int sfh_ctx_comm_info(const sfh_ctx *c, int *nranks, int *rank, int *mode);
 
 /* ---- device-side plumbing (no host round trip; used by bench.py and torch interop) ---------- */
+/* ---- multi-GPU from ONE process (`devices, ndev` of sfh_stack_create) ------------------------------
+ * Every reference caller is a single Julia process (fit_sfh, generic_fitting.jl:242-411; fit_templates, solvers.jl:82-90), so a
+ * stack too large for one GPU must be shardable without a process launcher.  sfh_group_create takes the arguments of
+ * sfh_stack_create plus the device list (devices == NULL: ordinals 0..ndev-1), splits the bin rows over the GPUs
+ * (sfh_shard_rows, 128-bin boundaries), enables peer access between all pairs and wires the one-shot NVLink exchange of the
+ * finalize kernel with plain peer pointers -- no NCCL, no CUDA-IPC, no launcher.  sfh_group_ctx returns the group's PRIMARY
+ * context: sfh_hier_bind, sfh_eval_fg, sfh_eval_fg_hier, sfh_composite-free drivers built on them (sfh_fit_templates_lbfgsb,
+ * sfh_fit_templates_bfgs, sfh_fit_fixed_amr_bfgs, sfh_fit_sfh_bfgs) accept it unchanged and return the all-reduced answer; the
+ * other GPUs are driven by worker threads inside the library.  Entry points that reduce with NCCL (two-pass direct calls,
+ * batched walkers, the samplers built on them) answer SFH_ERR_UNSUPPORTED on a group context.  Every shard must get a fused
+ * tiling (SFH_ERR_UNSUPPORTED otherwise).  The primary context is owned by the group: sfh_group_destroy releases everything. */
+typedef struct sfh_group sfh_group;
+int sfh_shard_rows(int64_t nbins, int nshards, int i, int64_t align, int64_t *row_begin, int64_t *row_end); /* pure arithmetic */
+int sfh_group_create(sfh_group **out, const void *models, int64_t nbins, int64_t ntemplates, int dtype, const void *data,
+                     int data_dtype, const int *devices, int ndev, const sfh_opts *opts);
+int sfh_group_create_synthetic(sfh_group **out, int64_t nbins, int64_t ntemplates, int dtype, uint64_t seed, double scale,
+                               const double *x_true, const int *devices, int ndev, const sfh_opts *opts);
+int sfh_group_destroy(sfh_group *g);            /* idempotent on NULL */
+int sfh_group_ctx(sfh_group *g, sfh_ctx **primary);
+int sfh_group_info(const sfh_group *g, int *ndev, sfh_info *infos /* nullable, ndev entries */);
+/* bench plumbing: mean device time of `reps` back-to-back all-reduced evaluations (CUDA events per GPU, max over the GPUs) */
+int sfh_group_time_fg(sfh_group *g, const double *coeffs, int reps, int want_G, double *ms_per_eval_out);
+
 /* Enqueue one fused evaluation on the ctx stream.  d_coeffs: device, ntemplates doubles.
  * d_out: device, 1+ntemplates doubles = [logL (raw sum, un-guarded), G...].  Asynchronous.
  * want_G = 0 skips the gradient pass.                                                          */

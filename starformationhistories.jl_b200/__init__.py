@@ -11,7 +11,7 @@ Importing this package loads ``libsfhcuda.so`` and fails loudly if it is missing
 """
 from . import _lib
 from ._lib import SFHError, device_count
-from .fitting import (DeviceStack, clear_cache, composite_, device_stack, fg_ as fg_flat_, grad_loglikelihood,
+from .fitting import (DeviceStack, DeviceStackGroup, clear_cache, composite_, device_stack, fg_ as fg_flat_, grad_loglikelihood,
                       grad_loglikelihood_, loglikelihood, stack_models)
 from .hierarchical import (GaussianDispersion, HierarchicalOptimizer, LinearAMR, LogarithmicAMR, PowerLawMZR,
                            calculate_coeffs, exptransform, fg_ as fg_hier_, logtransform, nparams, MH_from_Z, dMH_dZ, Z_from_MH, dZ_dMH,
@@ -37,7 +37,7 @@ def fg_(F, G, *args):
     return fg_flat_(F, G, *args)
 
 
-__all__ = ["DeviceStack", "SFHError", "device_count", "stack_models", "composite_", "loglikelihood",
+__all__ = ["DeviceStack", "DeviceStackGroup", "SFHError", "device_count", "stack_models", "composite_", "loglikelihood",
            "grad_loglikelihood", "grad_loglikelihood_", "fg_", "calculate_coeffs", "PowerLawMZR", "LinearAMR",
            "LogarithmicAMR", "GaussianDispersion", "HierarchicalOptimizer", "HMCModel", "MCMCModel", "nparams",
            "exptransform", "logtransform", "clear_cache", "device_stack", "shard_rows", "allreduce_fg", "guard_neg_logl",

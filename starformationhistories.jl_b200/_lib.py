@@ -118,6 +118,13 @@ PROTOTYPES = {
     "sfh_comm_init": (_int, [_vp, _int, _int, _vp]),
     "sfh_comm_p2p_handle": (_int, [_vp, _int, _vp]),
     "sfh_comm_p2p_init": (_int, [_vp, _int, _int, _vp]),
+    "sfh_shard_rows": (_int, [_i64, _int, _int, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "sfh_group_create": (_int, [C.POINTER(_vp), _vp, _i64, _i64, _int, _vp, _int, C.POINTER(_int), _int, C.POINTER(sfh_opts)]),
+    "sfh_group_create_synthetic": (_int, [C.POINTER(_vp), _i64, _i64, _int, C.c_uint64, C.c_double, _dp, C.POINTER(_int), _int, C.POINTER(sfh_opts)]),
+    "sfh_group_destroy": (_int, [_vp]),
+    "sfh_group_ctx": (_int, [_vp, C.POINTER(_vp)]),
+    "sfh_group_info": (_int, [_vp, C.POINTER(_int), C.POINTER(sfh_info)]),
+    "sfh_group_time_fg": (_int, [_vp, _dp, _int, _int, _dp]),
     "sfh_comm_p2p_enable": (_int, [_vp, _int]),
     "sfh_ctx_comm_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "sfh_enqueue_fg": (_int, [_vp, _vp, _vp, _int]),

@@ -83,19 +83,34 @@ __device__ __forceinline__ void bulk_load_1d_hint(uint32_t smem_dst, const void 
                  : "memory");
 }
 
-template <typename S>
+// FAST (Float32 stacks whose elements are all finite with the sign bit clear -- checked once at creation): the float's bits
+// are dropped into a double WITHOUT re-biasing the exponent: one 32 x 32 -> 64 multiply by 2^29 puts the 23 mantissa bits and
+// the 8 exponent bits where a double keeps them, giving exactly x * 2^-896 (also for float denormals, which land on double
+// denormals, and for 0).  The factor 2^896 is folded into the coefficients (A warps) and the residual (B warps), so every
+// product m*c and m*r is bit-identical to the converted one.  Why: cvt.f64.f32 runs on the XU pipe at 16 lanes/clk/SM, and at
+// two conversions per element ncu shows that pipe 78 % busy at 1.9 GHz -- under a sustained run's power cap (1.6 GHz) the
+// conversions, not HBM, bound the Float32 kernel (profiles/r2_experiments.md).
+constexpr double kV2FastScale = 0x1p896;
+template <typename S, bool FAST>
 __device__ __forceinline__ void unpack2(const vec16 &v, double (&out)[16 / sizeof(S)]);
 template <>
-__device__ __forceinline__ void unpack2<double>(const vec16 &v, double (&out)[2]) {
+__device__ __forceinline__ void unpack2<double, false>(const vec16 &v, double (&out)[2]) {
     out[0] = __hiloint2double(v.y, v.x);
     out[1] = __hiloint2double(v.w, v.z);
 }
 template <>
-__device__ __forceinline__ void unpack2<float>(const vec16 &v, double (&out)[4]) {
+__device__ __forceinline__ void unpack2<float, false>(const vec16 &v, double (&out)[4]) {
     out[0] = (double)__uint_as_float(v.x);
     out[1] = (double)__uint_as_float(v.y);
     out[2] = (double)__uint_as_float(v.z);
     out[3] = (double)__uint_as_float(v.w);
+}
+template <>
+__device__ __forceinline__ void unpack2<float, true>(const vec16 &v, double (&out)[4]) {
+    out[0] = __longlong_as_double((long long)((unsigned long long)v.x * 536870912ull));
+    out[1] = __longlong_as_double((long long)((unsigned long long)v.y * 536870912ull));
+    out[2] = __longlong_as_double((long long)((unsigned long long)v.z * 536870912ull));
+    out[3] = __longlong_as_double((long long)((unsigned long long)v.w * 536870912ull));
 }
 
 // Poisson log-likelihood-ratio term, fitting_base.jl:90-92 (`ifelse` = select; NaN propagates like Julia's scalar max)
@@ -105,8 +120,9 @@ __device__ __forceinline__ double poisson_term2(double m, double n, double eps) 
 }
 
 // LPR = lanes per template row of a chunk: BT = LPR * (16 / sizeof(S)) bins per tile; RPC = 256 / LPR templates per chunk.
-template <typename S, int LPR, bool WANT_G>
+template <typename S, int LPR, bool WANT_G, bool FAST>
 __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fused2Params p) {
+    static_assert(!FAST || sizeof(S) == 4, "FAST is the Float32 conversion-free unpack");
     constexpr int VEC = 16 / sizeof(S), BT = VEC * LPR, RPW = 32 / LPR, RPC = RPW * kV2A;
     constexpr int NBL = (BT + 31) / 32;   // bins per reducer lane
     static_assert(LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "LPR must be a power of two");
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
             // ---------------- pass A: composite partials ----------------
             double creg[kV2KMax];
 #pragma unroll
-            for (int k = 0; k < kV2KMax; ++k) creg[k] = (k < kv) ? __ldg(p.coeffs + j0 + (int64_t)k * RPC) : 0.0;
+            for (int k = 0; k < kV2KMax; ++k) creg[k] = (k < kv) ? __ldg(p.coeffs + j0 + (int64_t)k * RPC) * (FAST ? kV2FastScale : 1.0) : 0.0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int xs = it & (kV2DS - 1);
                 double acc[VEC];
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
                         for (int u = 0; u < kV2G; ++u) {
                             if (s * kV2G + u < kv) {
                                 double m[VEC];
-                                unpack2<S>(v[u], m);
+                                unpack2<S, FAST>(v[u], m);
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) acc[e] = fma(m[e], creg[s * kV2G + u], acc[e]);
                             }
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
                 mbar_wait(&rbar[xs], (uint32_t)(it / kV2DS) & 1u);
                 double r[VEC];
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) r[e] = rbuf[xs * BT + bl * VEC + e];
+                for (int e = 0; e < VEC; ++e) r[e] = rbuf[xs * BT + bl * VEC + e] * (FAST ? kV2FastScale : 1.0);
 #pragma unroll
                 for (int s = 0; s < kV2SMax; ++s) {
                     if (s < nst) {
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
                         for (int u = 0; u < kV2G; ++u) {
                             if (s * kV2G + u < kv) {
                                 double m[VEC];
-                                unpack2<S>(v[u], m);
+                                unpack2<S, FAST>(v[u], m);
                                 double g = gacc[s * kV2G + u];
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) g = fma(m[e], r[e], g);
@@ -306,7 +322,22 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
         }
     } else {
         // ================= reducer: partials -> composite -> residual; Poisson term off the critical path =================
-        double lacc = 0.0;
+        // The reducer is ONE warp per SM and a tile can be as short as 0.8 us, so its per-tile dependency chain is kept minimal:
+        // the observed counts are fetched one tile ahead, and when a tile has fewer bins than the warp has lanes the Poisson terms
+        // (a ~400-cycle FP64 log each) are queued -- (m, n) pairs parked in idle lanes by shuffle -- and evaluated 32 at a time.
+        // (Round 2, first version: one log per tile on 2 of 32 lanes kept up at 1.9 GHz but not under a sustained run's power
+        // cap: config 3 with 2-bin tiles went from 181 us isolated to 202 us per step back to back.)
+        constexpr int QT = (BT < 32) ? 32 / BT : 1;   // tiles per queue flush
+        double lacc = 0.0, qm = 0.0, qn = 0.0;
+        bool qvalid = false;
+        int qcount = 0;
+        double n_next[NBL];
+#pragma unroll
+        for (int i = 0; i < NBL; ++i) {
+            const int b = lane + 32 * i;
+            const int64_t bin = (int64_t)cl * BT + b;
+            n_next[i] = (my_tiles > 0 && b < BT && bin < p.nb) ? __ldg(p.data + bin) : 0.0;
+        }
         for (int it = 0; it < my_tiles; ++it) {
             const int64_t tile = (int64_t)cl + (int64_t)it * ncl;
             const int xs = it & (kV2DS - 1);
@@ -314,9 +345,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
             double n_obs[NBL], m[NBL];
 #pragma unroll
             for (int i = 0; i < NBL; ++i) {
+                n_obs[i] = n_next[i];
                 const int b = lane + 32 * i;
-                const int64_t bin = tile * BT + b;
-                n_obs[i] = (b < BT && bin < p.nb) ? __ldg(p.data + bin) : 0.0;
+                const int64_t bin = (tile + ncl) * BT + b;
+                n_next[i] = (it + 1 < my_tiles && b < BT && bin < p.nb) ? __ldg(p.data + bin) : 0.0;
             }
             mbar_wait(&redbar[xs], par);
 #pragma unroll
@@ -372,15 +404,31 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
                 for (int i = 0; i < NBL; ++i) {
                     const int b = lane + 32 * i;
                     const int64_t bin = tile * BT + b;
-                    if (b < BT && bin < p.nb) {
+                    const bool live = b < BT && bin < p.nb;
+                    if (live) {
                         p.composite[bin] = m[i];
                         if (p.residual) p.residual[bin] = r[i];
-                        lacc += poisson_term2(m[i], n_obs[i], p.eps);
                     }
+                    if (BT >= 32) {
+                        if (live) lacc += poisson_term2(m[i], n_obs[i], p.eps);
+                    } else {
+                        // park this tile's BT pairs in lanes [qcount*BT, (qcount+1)*BT)
+                        const int src = lane - qcount * BT;
+                        const double vm = __shfl_sync(0xffffffffu, m[i], src & 31);
+                        const double vn = __shfl_sync(0xffffffffu, n_obs[i], src & 31);
+                        const bool vl = __shfl_sync(0xffffffffu, live ? 1 : 0, src & 31) != 0;
+                        if (src >= 0 && src < BT) { qm = vm; qn = vn; qvalid = vl; }
+                    }
+                }
+                if (BT < 32 && ++qcount == QT) {
+                    if (qvalid) lacc += poisson_term2(qm, qn, p.eps);
+                    qcount = 0;
+                    qvalid = false;
                 }
             }
         }
         if (q == 0) {
+            if (BT < 32 && qcount > 0 && qvalid) lacc += poisson_term2(qm, qn, p.eps);   // the partly filled queue
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, off);
             if (lane == 0) p.lpart[cl] = lacc;

@@ -58,6 +58,25 @@ __device__ __forceinline__ double poisson_term(double m, double n, double eps) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Chain rule of the hierarchical fg! (mzr.jl:124-210 / amr.jl:118-169) as the TAIL of the finalize kernel: everything in it that
+// does not depend on the gradient (the per-template factors W1..W4 below) is prepared by sfh_hier_prologue2_kernel while the
+// variables are being turned into coefficients, so what remains after the fused kernel is four dot products per age group and
+// two 60-element scans -- done by the finalize kernel's last block instead of a fourth, single-block launch (round 1: 22 us).
+// ------------------------------------------------------------------------------------------
+constexpr int kHierTailAges = 256;   // ages the folded tail stages in shared memory (more: the separate epilogue kernel)
+struct HierTail {
+    int32_t on;          // 0 = plain fg!
+    int32_t kind, nj, want_G;
+    uint8_t free_mask[4];
+    const double *W;     // [4][nt]: d r_jk-weighted factors of  sum_k fullG_jk * (...)  for  R_j (cross-age), R_j (same age), mu_j, sigma
+    const double *gA, *gB;   // [nj] d mu_j / d alpha, d mu_j / d beta
+    const int32_t *gptr, *gmem, *sidx;
+    int64_t nt;
+    double *out;         // device [1 + nj + 3]: -logL (guarded), G
+    double *out_host;    // nullable mapped pinned copy
+};
+
+// ------------------------------------------------------------------------------------------
 // finalize: logL = sum_i term(m_i, n_i)   (loglikelihood, fitting_base.jl:84-96, raw sum: the
 // `== 0 -> -Inf` guard of :95 is applied by the caller AFTER any cross-GPU all-reduce)
 // and G_j = sum over clusters of gpart[cl][j].  out = [logL, G_0..G_{T-1}].
@@ -82,6 +101,7 @@ struct FinalizeParams {
     double *shard_out;              // device [1 + nt]: this shard's own [logL, G] before the exchange
     unsigned long long *epoch_ptr;  // device: evaluations exchanged so far on this context (read and bumped by the last
                                     // block only, so a captured CUDA graph of the evaluation can be replayed)
+    HierTail hier;                  // hierarchical chain rule on the (all-reduced) gradient, by the last block
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
@@ -93,6 +113,66 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     return v;
 }
 constexpr int kFinalizeThreads = 256;
+
+enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
+
+// the last block of the finalize kernel: out_fg = [logL raw, +M'r] complete (all-reduced when sharded)
+__device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_fg, double *sh /*[8]*/) {
+    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges];
+    __shared__ double s_par[3];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kFinalizeThreads / 32;
+    const int nj = h.nj;
+    if (tid == 0) {
+        const double logL = __ldcg(out_fg);
+        const double v = (logL != 0.0) ? -logL : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95, solvers.jl:31
+        h.out[0] = v;
+        if (h.out_host) h.out_host[0] = v;
+    }
+    if (!h.want_G) return;
+    const double *W1 = h.W, *W2 = h.W + h.nt, *W3 = h.W + 2 * h.nt, *W4 = h.W + 3 * h.nt;
+    for (int j = warp; j < nj; j += nw) {
+        const int g0 = h.gptr[j], g1 = h.gptr[j + 1];
+        double a_dr = 0.0, a_same = 0.0, a_p = 0.0, a_s = 0.0;
+        for (int g = g0 + lane; g < g1; g += 32) {
+            const int t = h.gmem[g];
+            const double fullG = -__ldcg(out_fg + 1 + t);       // d logL / d r_jk
+            if (h.kind == MH_POWERLAW_MZR) a_dr += fullG * W1[t];   // mzr.jl:166-167
+            a_same += fullG * W2[t];                                // mzr.jl:188-190 / amr.jl:141
+            a_p += fullG * W3[t];                                   // mzr.jl:194-195
+            a_s += fullG * W4[t];                                   // mzr.jl:206-207
+        }
+        a_dr = warp_sum(a_dr); a_same = warp_sum(a_same); a_p = warp_sum(a_p); a_s = warp_sum(a_s);
+        if (lane == 0) { s_dr[j] = a_dr; s_G[j] = -a_same; s_p[j] = -a_p; s_s[j] = a_s; }
+    }
+    __syncthreads();
+    {   // parameter gradients: fixed-order (strided + xor tree) block sums  (mzr.jl:196-198,201-208)
+        double ga = 0.0, gb = 0.0, gs = 0.0;
+        for (int j = tid; j < nj; j += kFinalizeThreads) {
+            ga += s_p[j] * h.gA[j];
+            gb += s_p[j] * h.gB[j];
+            gs -= s_s[j];
+        }
+        const double ta = block_sum<kFinalizeThreads>(ga, sh);
+        const double tb = block_sum<kFinalizeThreads>(gb, sh);
+        const double ts = block_sum<kFinalizeThreads>(gs, sh);
+        if (tid == 0) { s_par[0] = ta; s_par[1] = tb; s_par[2] = ts; }
+    }
+    __syncthreads();
+    if (tid == 0 && h.kind == MH_POWERLAW_MZR) {
+        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181
+        double run = 0.0;
+        for (int i = nj - 1; i >= 1; --i) {
+            run += s_dr[h.sidx[i]];
+            s_G[h.sidx[i - 1]] -= run;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < nj + 3; j += kFinalizeThreads) {
+        const double v = (j < nj) ? s_G[j] : (h.free_mask[j - nj] ? s_par[j - nj] : 0.0);   // fixed parameters receive 0 (mzr.jl:196,201)
+        h.out[1 + j] = v;
+        if (h.out_host) h.out_host[1 + j] = v;
+    }
+}
 
 // Everything here is latency, not bandwidth (60 k logs, ~1 MB of partials): the shape is chosen so that no thread
 // ever waits on more than ~2 dependent L2 round trips.  Measured alternatives (ncu launch lists under profiles/):
@@ -152,7 +232,13 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
         if (p.out_host && !p.peers) p.out_host[0] = all;
         *p.ticket = 0u;  // re-arm for the next evaluation on this context
     }
-    if (!p.peers) return;
+    if (!p.peers) {
+        if (p.hier.on) {
+            __syncthreads();   // thread 0's gout[0]
+            hier_tail(p.hier, p.out, sh);
+        }
+        return;
+    }
 
     // ---------------- one-shot all-reduce, entirely inside this block ----------------
     __shared__ unsigned long long s_epoch;
@@ -191,6 +277,10 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
         for (int r = 0; r < p.nranks; ++r) t += __ldcv(inbox + r * p.vlen + i);
         p.out[i] = t;
         if (p.out_host) p.out_host[i] = t;
+    }
+    if (p.hier.on) {
+        __syncthreads();   // this block wrote all of p.out
+        hier_tail(p.hier, p.out, sh);
     }
 }
 
@@ -269,8 +359,6 @@ __global__ void __launch_bounds__(256) sfh_gemvt_kernel(const S *__restrict__ M,
 // hierarchical prologue / epilogue (K5).  One block; one warp per age group, members visited in
 // template order => deterministic.  Formulas cite src/fitting/hierarchical/{mzr,amr,dispersion_models}.jl
 // ------------------------------------------------------------------------------------------
-enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
-
 struct HierParams {
     int32_t kind;      // sfh_mh_kind
     int32_t nj;        // number of unique ages
@@ -398,6 +486,86 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const H
             const int t = p.gmem[g];
             p.coeffs[t] = p.Ajk[t] * Rj / a;  // mzr.jl:76
         }
+    }
+}
+
+// calculate_coeffs (mzr.jl:50-79 / amr.jl:50-73) for ONE evaluation, spread over the grid: one warp per age group.  Besides the
+// coefficients it prepares everything of the chain rule (mzr.jl:131-209) that does not depend on the gradient -- the factors
+// W1..W4 that multiply fullG_jk in the four per-age sums -- so that the finalize kernel's tail (hier_tail) is left with dot
+// products.  `vars_in` may be the caller's mapped pinned buffer: 63 doubles over PCIe instead of a memcpy node in front.
+constexpr int kHierPro2Threads = 256;
+__global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(const HierParams p, const double *vars_in, double *W) {
+    __shared__ double sv[kHierTailAges + 3];
+    __shared__ int ssidx[kHierTailAges];
+    griddep_wait();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierPro2Threads / 32;
+    const int nj = p.nj;
+    for (int j = tid; j < nj + 3; j += kHierPro2Threads) {
+        const double v = vars_in[j];
+        sv[j] = v;
+        if (blockIdx.x == 0) const_cast<double *>(p.variables)[j] = v;   // device copy for later kernels
+    }
+    for (int j = tid; j < nj; j += kHierPro2Threads) ssidx[j] = p.sidx[j];
+    __syncthreads();
+    const double alpha = sv[nj], beta = sv[nj + 1], sigma = sv[nj + 2];
+    const double s2 = sigma * sigma, s3 = s2 * sigma;
+    const int j = blockIdx.x * nw + warp;
+    if (j >= nj) return;
+    double arg = p.logAge_u[j];
+    if (p.kind == MH_POWERLAW_MZR) {
+        // cumsum(R[s])[invperm(s)]  mzr.jl:61-66 -- oldest first; this age's entry is the running sum up to its own position
+        double run = 0.0;
+        for (int i = 0; i < nj; ++i) {
+            const int jj = ssidx[i];
+            run += sv[jj];
+            if (jj == j) break;
+        }
+        arg = run;
+    }
+    double mu, gA, gB, gM;
+    d_mh_eval(p.kind, alpha, beta, p.fixed, arg, mu, gA, gB, gM);
+    if (lane == 0) { p.mu[j] = mu; p.gA[j] = gA; p.gB[j] = gB; p.gM[j] = gM; }
+    const int g0 = p.gptr[j], g1 = p.gptr[j + 1];
+    const double Rj = sv[j];
+    double a = 0.0;
+    for (int g = g0 + lane; g < g1; g += 32) {
+        const int t = p.gmem[g];
+        const double z = (p.MH[t] - mu) / sigma;
+        const double A = exp(-(z * z) / 2.0);  // dispersion_models.jl:92
+        p.Ajk[t] = A;
+        a += A;
+    }
+    const double Aj = warp_sum(a);
+    if (lane == 0) p.Asum[j] = Aj;
+    double kAR = 0.0, kmu = 0.0, ksg = 0.0;
+    for (int g = g0 + lane; g < g1; g += 32) {
+        const int t = p.gmem[g];
+        const double A = p.Ajk[t], d = p.MH[t] - mu;
+        const double dAmu = A * d / s2;      // dispersion_models.jl:99
+        const double dAsg = A * d * d / s3;  // dispersion_models.jl:98
+        kAR += dAmu * gM;                    // mzr.jl:162,164
+        kmu += dAmu;
+        ksg += dAsg;
+    }
+    kAR = warp_sum(kAR); kmu = warp_sum(kmu); ksg = warp_sum(ksg);
+    const double RA = Rj / Aj;
+    const int64_t nt = p.nt;
+    for (int g = g0 + lane; g < g1; g += 32) {
+        const int t = p.gmem[g];
+        const double A = p.Ajk[t], d = p.MH[t] - mu;
+        const double dAmu = A * d / s2, dAsg = A * d * d / s3;
+        const double coeff = A * Rj / Aj;    // mzr.jl:76
+        p.coeffs[t] = coeff;
+        if (p.kind == MH_POWERLAW_MZR) {
+            const double dAR = dAmu * gM;
+            W[t] = RA * (dAR - (A * kAR / Aj));                            // mzr.jl:166-167
+            W[nt + t] = coeff / Rj + (dAR - (kAR * A / Aj)) * Rj / Aj;     // mzr.jl:188-190
+        } else {
+            W[t] = 0.0;
+            W[nt + t] = coeff / Rj;                                        // amr.jl:141
+        }
+        W[2 * nt + t] = RA * (dAmu - A / Aj * kmu);                        // mzr.jl:194-195
+        W[3 * nt + t] = RA * (dAsg - A / Aj * ksg);                        // mzr.jl:206-207
     }
 }
 
@@ -620,6 +788,17 @@ template <typename D>
 __global__ void sfh_to_double_kernel(const D *in, double *out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (double)in[i];
+}
+
+// Float32 stacks: does any element have its sign bit set, or is any Inf / NaN?  (decides whether the stream kernel may use its
+// conversion-free unpack, sfh_fused2.cuh)
+__global__ void sfh_check_f32_kernel(const uint32_t *bits, int64_t n, int *flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = bits[i];
+        bad |= (b & 0x80000000u) != 0u || (b & 0x7f800000u) == 0x7f800000u;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;
 }
 
 // writes >L2 bytes: used between timed evaluations (bench hygiene)

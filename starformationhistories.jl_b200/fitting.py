@@ -100,7 +100,7 @@ class DeviceStack:
         L.check(L.lib.sfh_stack_create(C.byref(h), M.ctypes.data_as(C.c_void_p), M.shape[0], M.shape[1], _DT[dt],
                                        d.ctypes.data_as(C.c_void_p), _DT[d.dtype], C.byref(o)))
         self._finish_init(h)
-        self._data_id = id(data)
+        self._data_ref = _data_ref(data)
 
     def _finish_init(self, h):
         self.handle = h
@@ -166,7 +166,7 @@ class DeviceStack:
             d.ctypes.data_as(C.c_void_p) if d is not None else None, _DT[d.dtype] if d is not None else _DT[np.dtype(np.float64)],
             C.byref(o)))
         self._finish_init(h)
-        self._data_id = id(data) if data is not None else None
+        self._data_ref = _data_ref(data)
         return self
 
     @classmethod
@@ -191,7 +191,7 @@ class DeviceStack:
         L.check(L.lib.sfh_stack_create_synthetic(C.byref(h), nbins, ntemplates, _DT[dt], C.c_uint64(seed), float(scale),
                                                  _dp(x), C.byref(o)))
         self._finish_init(h)
-        self._data_id = None
+        self._data_ref = None
         return self
 
     @classmethod
@@ -223,7 +223,7 @@ class DeviceStack:
         h = C.c_void_p()
         L.check(L.lib.sfh_stack_create_from_file(C.byref(h), str(path).encode(), int(bool(verify)), C.byref(o)))
         self._finish_init(h)
-        self._data_id = None
+        self._data_ref = None
         return self
 
     def save(self, path, logAge=None, MH=None, hess_shape=None):
@@ -275,7 +275,7 @@ class DeviceStack:
         if d.shape[0] != self.shape[0]:
             raise ValueError("axes(models,1) != axes(data,1)")
         L.check(L.lib.sfh_stack_set_data(self.handle, d.ctypes.data_as(C.c_void_p), _DT[d.dtype]))
-        self._data_id = id(data)
+        self._data_ref = _data_ref(data)
 
     def download(self):
         i = self.info()
@@ -359,11 +359,135 @@ class DeviceStack:
         return ms.value, msk.value
 
 
+class _GroupCtx:
+    """The primary context of a multi-GPU group: owned by the group (never destroyed from here)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+        self.bound_key = None
+        self.n_ages = 0
+
+    def close(self):
+        pass
+
+
+class DeviceStackGroup(DeviceStack):
+    """A template stack sharded by bin rows over several GPUs of THIS process (include/sfhcuda.h: sfh_group_*): what the
+    reference's single-process callers (fit_sfh, fit_templates, ...) need for stacks that do not fit one GPU.  Drop-in for a
+    :class:`DeviceStack` wherever the fused evaluation is used (``fg_``, the hierarchical ``fg_``, ``fit_templates*`` and
+    ``fit_sfh`` with ``engine="native"``); the batched-walker / sampler paths raise ``SFHError`` (unsupported on a group)."""
+
+    def __init__(self, models, data, devices=None, ndev=None, dtype=None, clamp_eps=0.0, tile_bins=0, cluster=0, variant=0):
+        M = _as_stack_matrix(models)
+        dt = np.dtype(dtype) if dtype is not None else M.dtype
+        if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+            dt = np.dtype(np.float64)
+        M = np.asfortranarray(M, dtype=dt)
+        d = np.asarray(data).reshape(-1, order="F")
+        if d.dtype not in _DT:
+            d = d.astype(np.float64)
+        d = np.ascontiguousarray(d)
+        if d.shape[0] != M.shape[0]:
+            raise ValueError("axes(models,1) != axes(data,1)")
+        devs, n = self._devices(devices, ndev)
+        o = L.sfh_opts()
+        o.struct_size = C.sizeof(L.sfh_opts)
+        o.clamp_eps = clamp_eps
+        o.tile_bins, o.cluster, o.variant = tile_bins, cluster, variant
+        g = C.c_void_p()
+        L.check(L.lib.sfh_group_create(C.byref(g), M.ctypes.data_as(C.c_void_p), M.shape[0], M.shape[1], _DT[dt],
+                                       d.ctypes.data_as(C.c_void_p), _DT[d.dtype], devs, n, C.byref(o)))
+        self._finish_group(g, M.shape, dt, n)
+        self._data_ref = None      # the bound data cannot be re-bound on a group: pass the group itself on every call
+
+    @staticmethod
+    def _devices(devices, ndev):
+        if devices is None:
+            n = int(ndev) if ndev is not None else L.device_count()
+            return None, n
+        arr = (C.c_int * len(devices))(*[int(v) for v in devices])
+        return arr, len(devices)
+
+    def _finish_group(self, g, shape, dt, n):
+        self.group = g
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.dtype = dt
+        self.ndev = n
+        self.rows = self.shape[0]
+        h = C.c_void_p()
+        L.check(L.lib.sfh_group_ctx(g, C.byref(h)))
+        self._primary = _GroupCtx(h)
+        self.handle = None
+        self._fin = weakref.finalize(self, L.lib.sfh_group_destroy, g)
+
+    @classmethod
+    def synthetic(cls, nbins, ntemplates, dtype, seed, scale, x_true, devices=None, ndev=None, tile_bins=0, cluster=0, variant=0):
+        self = cls.__new__(cls)
+        devs, n = cls._devices(devices, ndev)
+        o = L.sfh_opts()
+        o.struct_size = C.sizeof(L.sfh_opts)
+        o.tile_bins, o.cluster, o.variant = tile_bins, cluster, variant
+        x = np.ascontiguousarray(x_true, dtype=np.float64)
+        if x.shape[0] != ntemplates:
+            raise ValueError("len(x_true) != ntemplates")
+        g = C.c_void_p()
+        L.check(L.lib.sfh_group_create_synthetic(C.byref(g), int(nbins), int(ntemplates), _DT[np.dtype(dtype)], C.c_uint64(seed),
+                                                 float(scale), _dp(x), devs, n, C.byref(o)))
+        self._finish_group(g, (nbins, ntemplates), np.dtype(dtype), n)
+        self._data_ref = None
+        return self
+
+    def close(self):
+        self._fin()
+
+    def ctx(self):
+        return self._primary
+
+    def new_ctx(self, stream=None):
+        raise L.SFHError("a multi-GPU group has one (primary) context")
+
+    def infos(self):
+        n = C.c_int()
+        arr = (L.sfh_info * self.ndev)()
+        L.check(L.lib.sfh_group_info(self.group, C.byref(n), arr))
+        return list(arr)
+
+    def info(self):
+        return self.infos()[0]
+
+    def set_data(self, data):
+        raise L.SFHError("re-binding data on a multi-GPU group is not supported: create a new group")
+
+    def download(self):
+        raise L.SFHError("a multi-GPU group does not gather its shards back")
+
+    download_data = download
+
+    def time_fg(self, coeffs, reps=10, want_G=True, flush_l2=False):
+        """(ms per all-reduced evaluation, same) -- device-timed, max over the GPUs."""
+        x = np.ascontiguousarray(coeffs, dtype=np.float64)
+        ms = C.c_double()
+        L.check(L.lib.sfh_group_time_fg(self.group, _dp(x), int(reps), int(want_G), C.byref(ms)))
+        return ms.value, ms.value
+
+
 # ---------------------------------------------------------------------------------------------
 # identity-keyed cache for callers that pass bare arrays on every iteration (SURVEY.md section 8b (2))
 # ---------------------------------------------------------------------------------------------
 _cache: dict = {}
 _cache_lock = threading.Lock()
+
+
+def _data_ref(data):
+    """A reference that pins the IDENTITY of the bound data object (id() alone is recycled by the allocator once the
+    original array is collected, so `DeviceStack(M, d1)` followed by a call with a fresh `d2` at the same address silently kept
+    d1).  Weak when the object allows it, strong otherwise (lists, scalars); None when no data was bound by the caller."""
+    if data is None:
+        return None
+    try:
+        return weakref.ref(data)
+    except TypeError:
+        return lambda: data
 
 
 def _weak_ids(obj):
@@ -386,7 +510,10 @@ def _same(refs, obj):
 
 def device_stack(models, data) -> DeviceStack:
     if isinstance(models, DeviceStack):
-        if data is not None and models._data_id is not None and id(data) != models._data_id:
+        # the stack re-binds `data` when the caller passes a DIFFERENT object than the one bound (identity through a weak
+        # reference: a dead referent never compares equal).  In-place mutation of the bound array is NOT detected -- the reference
+        # re-reads `data` on every call, a device stack cannot; call ds.set_data(data) after mutating it.
+        if data is not None and models._data_ref is not None and models._data_ref() is not data:
             models.set_data(data)
         return models
     key = (id(models), id(data))

@@ -29,6 +29,24 @@ def main():
         assert np.allclose(G, G0, rtol=1e-10, atol=1e-10 * np.abs(G0).max())
     nl_f, _, _ = shard.eval_fg(x * 1.1, want_G=False)
     assert abs(nl_f - nl0) <= 1e-12 * abs(nl0)
+    # the exchange the fused path uses must be the one-shot NVLink one (mode 2) unless it was switched off
+    import ctypes as C
+    mode = C.c_int()
+    S._lib.check(S._lib.lib.sfh_ctx_comm_info(shard.ctx().handle, None, None, C.byref(mode)))
+    assert mode.value == (1 if os.environ.get("SFH_NO_P2P") == "1" else 2), mode.value
+    # many evaluations back to back: epochs / inbox parities / the replayed graph, alternating gradient and logL-only calls at
+    # changing coefficients; every one must match the whole stack and be bit-identical across ranks
+    rng_s = np.random.default_rng(123)
+    for it in range(40):
+        xi = x * (1.0 + 0.2 * rng_s.random(nt))
+        wg = it % 3 != 2
+        a = whole.eval_fg(xi, want_G=wg); b = shard.eval_fg(xi, want_G=wg)
+        assert abs(a[0] - b[0]) <= 1e-12 * abs(a[0]), (it, a[0], b[0])
+        if wg:
+            assert np.allclose(a[1], b[1], rtol=1e-10, atol=1e-10 * np.abs(a[1]).max()), it
+            t = torch.tensor([b[0]] + list(b[1]), dtype=torch.float64, device="cuda")
+            ref = t.clone(); dist.broadcast(ref, 0)
+            assert torch.equal(t, ref), it
     # every rank must hold the SAME reduced answer bit for bit (all-reduce is rank-symmetric)
     t = torch.tensor([nl] + list(G[:8]), dtype=torch.float64, device="cuda")
     ref = t.clone(); dist.broadcast(ref, 0)

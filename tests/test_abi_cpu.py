@@ -372,7 +372,7 @@ def test_every_entry_point_survives_null_arguments():
     got = dict(line.split() for line in r.stdout.splitlines() if line and not line.startswith("SWEEP"))
     syms = header_symbols()
     assert sorted(got) == syms
-    ok_on_null = {"sfh_stack_destroy", "sfh_ctx_destroy", "sfh_file_close"}
+    ok_on_null = {"sfh_stack_destroy", "sfh_ctx_destroy", "sfh_file_close", "sfh_group_destroy"}
     for name, val in got.items():
         if name == "sfh_last_error":
             continue

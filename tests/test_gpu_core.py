@@ -198,6 +198,39 @@ def test_stream_kernel_configs(S, dtype, lpr, cluster, nb, nt):
     assert np.array_equal(Md, M) and np.array_equal(dd, data.astype(np.float64))
 
 
+def test_stream_kernel_f32_unpack_paths(S):
+    """Float32 stacks take the conversion-free unpack only when every element is finite and non-negative (checked at creation);
+    otherwise the converting instantiation.  Both must agree with the oracle -- including float denormals (exact in both),
+    a negative template value and NaN propagation (never clamp NaN away)."""
+    nb, nt = 3000, 777
+    M, x, data = make_flat_problem(nb, nt, seed=31, dtype=np.float32)
+    M[5, 7] = np.float32(1e-42)                    # float denormal
+    M[11, 0] = np.float32(0.0)
+    x = x * 1.07
+    want = O.fg_quad_f32(x, M, data)
+    ds = S.DeviceStack(M, data, variant=4)
+    assert ds.info().variant == 4
+    nl, G, _ = ds.eval_fg(x)
+    assert nl == pytest.approx(want[0], rel=RTOL_F32)
+    assert_grad_close(G, want[1], want[2], rtol=RTOL_F32)
+    # one negative entry switches the whole stack over to the converting instantiation
+    M2 = M.copy(); M2[100, 3] = -M2[100, 3]
+    w2 = O.fg_quad_f32(x, M2, data)
+    ds2 = S.DeviceStack(M2, data, variant=4)
+    nl2, G2, _ = ds2.eval_fg(x)
+    assert nl2 == pytest.approx(w2[0], rel=RTOL_F32)
+    assert_grad_close(G2, w2[1], w2[2], rtol=RTOL_F32)
+    # NaN in a template: logL and every gradient component touching that bin are NaN, nothing is silently clamped
+    M3 = M.copy(); M3[17, 5] = np.nan
+    ds3 = S.DeviceStack(M3, data, variant=4)
+    nl3, G3, _ = ds3.eval_fg(x)
+    assert np.isnan(nl3) and np.all(np.isnan(G3))
+    M4 = M.copy(); M4[17, 5] = np.inf
+    ds4 = S.DeviceStack(M4, data, variant=4)
+    nl4, G4, _ = ds4.eval_fg(x)
+    assert not np.isfinite(nl4)
+
+
 def test_unfused_two_pass_agrees(S):
     M, x, data = make_flat_problem(5000, 301, seed=5)
     nlq, Gq, gs, _ = O.fg_quad(x, M, data)
