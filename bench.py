@@ -285,9 +285,18 @@ class Harness:
 
     def new_ctx(self, ds):
         ctx = ds.new_ctx(self.stream.cuda_stream)
-        if self.world > 1:
+        if self.world > 1 and os.environ.get("SFH_BENCH_NO_EXCHANGE") != "1":
             self.S.init_library_comm(ctx)     # NCCL communicator + (unless SFH_NO_P2P=1) the fused one-shot NVLink all-reduce
         return ctx
+
+    def gather(self, v):
+        """[v on rank 0, v on rank 1, ...] on every rank."""
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world == 1:
+            return [float(v)]
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
     def comm_mode(self, ctx):
         nr, rk, mode = self.C.c_int(), self.C.c_int(), self.C.c_int()
@@ -495,16 +504,19 @@ def main():
     L.check(L.lib.sfh_time_fg(ctx.handle, xh.ctypes.data_as(dp), min(args.steps, 50), 1, 0, C.byref(ms_eval), C.byref(ms_kernel)))
     bytes_alg = NB * NT * 8 + NB * 8 + 2 * NT * 8 + 8
     achieved = bytes_alg / (ms_kernel.value * 1e-3) / 1e9
+    kernel_ms_per_rank = H.gather(ms_kernel.value)     # GPUs of one box differ by a few per cent: an all-reduced step runs at the slowest
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "traffic_source": "constant: dram__bytes_read+write of this kernel from the ncu --set full capture summarised in profiles/ncu_summary.json (not re-measured in this run)",
-                "kernel": kernel_name(info, np.float64), "kernel_ms": ms_kernel.value, "bytes_alg_per_launch": bytes_alg, "peak_source": peak_src}
+                "kernel": kernel_name(info, np.float64), "kernel_ms": ms_kernel.value, "kernel_ms_per_rank": kernel_ms_per_rank,
+                "bytes_alg_per_launch": bytes_alg, "peak_source": peak_src}
 
     # ---- the hierarchical evaluation fit_sfh / sample_sfh actually call
     fg_hier = run_hier(H, ctx, min(args.steps, 500), args.warmup, peak, bytes_alg)
 
     # ---- parity carried by the bench line itself
     parity = None
-    if world > 1:
+    no_exchange = os.environ.get("SFH_BENCH_NO_EXCHANGE") == "1"     # diagnostic: N independent shards, nothing reduced
+    if world > 1 and not no_exchange:
         parity = H.parity_sharded_vs_whole(
             lambda: S.DeviceStack.synthetic(nb_total, NT, np.float64, seed=SEED, scale=1e-5, x_true=x_true, device=local), x, d_out, NT)
         assert parity["ok"], parity
@@ -534,7 +546,7 @@ def main():
     del ctx, ds
     torch.cuda.empty_cache()
 
-    config5 = None if args.no_config5 else run_config5(H, args, peak)
+    config5 = None if (args.no_config5 or no_exchange) else run_config5(H, args, peak)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

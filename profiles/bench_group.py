@@ -10,6 +10,9 @@ which = sys.argv[2] if len(sys.argv) > 2 else "config5"
 if which == "config5":
     nb, nt, dt, seed, scale = 1000 * 1000, 10000, np.float32, 58392, 1.0
     x = np.random.Generator(np.random.Philox(seed)).random(nt)
+elif which == "config5half":      # the shard one of two GPUs holds, on however many GPUs were asked for
+    nb, nt, dt, seed, scale = 500 * 1000, 10000, np.float32, 58392, 1.0
+    x = np.random.Generator(np.random.Philox(seed)).random(nt)
 else:
     nb, nt, dt, seed, scale = 60000 * ndev, 2400, np.float64, 94823, 1e-5
     x = np.random.Generator(np.random.Philox(seed)).random(nt) * 1e4
@@ -25,9 +28,13 @@ t0 = time.perf_counter()
 for _ in range(n):
     nl, G, _ = g.eval_fg(xe)
 wall_ms = (time.perf_counter() - t0) / n * 1e3
+t0 = time.perf_counter()
+for _ in range(n):
+    g.eval_fg(xe, want_G=False)
+wall_f_ms = (time.perf_counter() - t0) / n * 1e3
 i = g.infos()
 bytes_shard = (i[0].row_end - i[0].row_begin) * nt * np.dtype(dt).itemsize
 print(json.dumps({"what": f"{which} from ONE process over {ndev} GPU(s)", "nb": nb, "nt": nt, "ndev": ndev, "build_s": t_build,
-                  "ms_per_eval_device": ms_dev, "ms_per_eval_wall_host_api": wall_ms, "per_gpu_GBps_device": bytes_shard / ms_dev / 1e6,
+                  "ms_per_eval_device": ms_dev, "ms_per_eval_wall_host_api": wall_ms, "ms_per_eval_wall_logl_only": wall_f_ms, "per_gpu_GBps_device": bytes_shard / ms_dev / 1e6,
                   "neg_logL": nl, "tiling": [i[0].variant, i[0].tile_bins, i[0].cluster, i[0].chunks_per_tile, i[0].ring_slots, i[0].n_clusters]}))
 g.close()

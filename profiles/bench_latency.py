@@ -13,9 +13,9 @@ def time_call(fn, n=300, warm=20):
     for _ in range(n): fn()
     return (time.perf_counter() - t0) / n * 1e6
 
-def flat(nb, nt, label):
+def flat(nb, nt, label, dt=np.float64):
     x = 100 * np.random.default_rng(0).random(nt)
-    ds = S.DeviceStack.synthetic(nb, nt, np.float64, 1, 1.0, x)
+    ds = S.DeviceStack.synthetic(nb, nt, dt, 1, 1.0, x)
     ctx = ds.ctx(); G = np.empty(nt); nl = C.c_double(); xx = np.ascontiguousarray(x)
     t_fg = time_call(lambda: L.lib.sfh_eval_fg(ctx.handle, xx.ctypes.data_as(dp), C.byref(nl), G.ctypes.data_as(dp), None))
     t_f = time_call(lambda: L.lib.sfh_eval_fg(ctx.handle, xx.ctypes.data_as(dp), C.byref(nl), None, None))
@@ -41,5 +41,6 @@ flat(10000, 100, "config1 100x100 bins x 100")
 flat(9801, 142, "notebook 99x99 x 142")
 flat(40000, 500, "config2 stack")
 flat(60000, 2400, "config3")
+flat(125000, 10000, "config5 shard (1/8) F32", np.float32)
 hier(10000, 21, 26, "mzr_test 100x100 x 546")
 hier(60000, 60, 40, "config3 hier")

@@ -187,7 +187,8 @@ struct sfh_ctx {
     bool bound = false;
     int32_t nj = 0;
     double *d_logAge_u = nullptr, *d_MH = nullptr, *d_vars = nullptr, *d_hscratch = nullptr, *d_Ajk = nullptr,
-           *d_outh = nullptr, *d_W = nullptr;
+           *d_outh = nullptr, *d_W = nullptr, *d_P = nullptr, *d_MHg = nullptr;
+    int32_t *d_ginv = nullptr;
     int32_t *d_jidx = nullptr, *d_gptr = nullptr, *d_gmem = nullptr, *d_sidx = nullptr;
     // batched walkers
     int64_t wcap = 0, wld = 0;
@@ -209,7 +210,6 @@ struct sfh_ctx {
     std::vector<void *> ipc_opened;
     int64_t p2p_vlen = 0;
     unsigned long long *d_epoch = nullptr;   // device: evaluations exchanged so far (owned by the finalize kernel's last block)
-    double *d_shard_out = nullptr;           // this shard's own [logL, G] before the exchange
     bool p2p = false;
     // timing / stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -822,13 +822,13 @@ static int sfh_ctx_destroy_impl(sfh_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(c->d_inbox); cudaFree(c->d_peers); cudaFree(c->d_epoch); cudaFree(c->d_shard_out);
+    cudaFree(c->d_inbox); cudaFree(c->d_peers); cudaFree(c->d_epoch);
     for (auto *g : {&c->g_fg[0], &c->g_fg[1], &c->g_hier})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     cudaFree(c->d_coeffs); cudaFree(c->d_out); cudaFree(c->d_composite); cudaFree(c->d_residual);
     cudaFree(c->d_gpart); cudaFree(c->d_lpart); cudaFree(c->d_ticket);
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
-    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W);
+    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W); cudaFree(c->d_P); cudaFree(c->d_MHg); cudaFree(c->d_ginv);
     cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
     cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG); cudaFree(c->d_logtab); cudaFree(c->d_hb);
     cudaFree(c->d_flush);
@@ -878,7 +878,7 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
     if (tail) fp.hier = *tail;
     if (p2p_push) {
         fp.peers = c->d_peers; fp.nranks = c->nranks; fp.rank = c->rank; fp.vlen = c->p2p_vlen;
-        fp.shard_out = c->d_shard_out; fp.epoch_ptr = c->d_epoch;
+        fp.epoch_ptr = c->d_epoch;
     }
     // enough blocks that every thread has <= 1 bin and every warp <= 1 template (latency-bound kernel)
     const int64_t cap = 4 * std::max(s->sm_count, 1);
@@ -1204,8 +1204,9 @@ static int hier_bind_local(sfh_ctx *c, const double *logAge, const double *MH, i
     std::stable_sort(sidx.begin(), sidx.end(), [&](int32_t a, int32_t b) { return uniq[(size_t)a] > uniq[(size_t)b]; });
 
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
-    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W);
-    c->d_logAge_u = c->d_MH = c->d_vars = c->d_hscratch = c->d_Ajk = c->d_outh = c->d_W = nullptr;
+    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W); cudaFree(c->d_P); cudaFree(c->d_MHg); cudaFree(c->d_ginv);
+    c->d_logAge_u = c->d_MH = c->d_vars = c->d_hscratch = c->d_Ajk = c->d_outh = c->d_W = c->d_P = c->d_MHg = nullptr;
+    c->d_ginv = nullptr;
     for (auto *g : {&c->g_hier}) if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; g->failed = false; }   // bakes the old tables in
     c->d_jidx = c->d_gptr = c->d_gmem = c->d_sidx = nullptr;
     c->bound = false;
@@ -1217,6 +1218,9 @@ static int hier_bind_local(sfh_ctx *c, const double *logAge, const double *MH, i
     CU_TRY(cudaMalloc((void **)&c->d_Ajk, ntp * 8));
     CU_TRY(cudaMalloc((void **)&c->d_outh, (njp + 4) * 8));
     CU_TRY(cudaMalloc((void **)&c->d_W, 4 * ntp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_P, 4 * ntp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_MHg, ntp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_ginv, ntp * 4));
     CU_TRY(cudaMalloc((void **)&c->d_jidx, ntp * 4));
     CU_TRY(cudaMalloc((void **)&c->d_gptr, (njp + 1) * 4));
     CU_TRY(cudaMalloc((void **)&c->d_gmem, ntp * 4));
@@ -1228,6 +1232,12 @@ static int hier_bind_local(sfh_ctx *c, const double *logAge, const double *MH, i
         CU_TRY(cudaMemcpy(c->d_gptr, gptr.data(), ((size_t)nj + 1) * 4, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(c->d_gmem, gmem.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(c->d_sidx, sidx.data(), (size_t)nj * 4, cudaMemcpyHostToDevice));
+        // age-grouped views for the folded path: where each template sits in the group list, and the metallicities in that order
+        std::vector<int32_t> ginv((size_t)nt);
+        std::vector<double> mhg((size_t)nt);
+        for (int64_t g = 0; g < nt; ++g) { ginv[(size_t)gmem[(size_t)g]] = (int32_t)g; mhg[(size_t)g] = MH[gmem[(size_t)g]]; }
+        CU_TRY(cudaMemcpy(c->d_ginv, ginv.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_MHg, mhg.data(), (size_t)nt * 8, cudaMemcpyHostToDevice));
     }
     if ((size_t)nj + 8 > c->h_in_n || (size_t)nj + 8 > c->h_out_n) return fail(SFH_ERR_SHAPE, "more ages than templates?");
     c->nj = nj;
@@ -1306,11 +1316,11 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
             HierTail tl{};
             tl.on = 1; tl.kind = hp.kind; tl.nj = c->nj; tl.want_G = want_G;
             for (int i = 0; i < 4; ++i) tl.free_mask[i] = hp.free_mask[i];
-            tl.W = c->d_W; tl.gA = hp.gA; tl.gB = hp.gB; tl.gptr = hp.gptr; tl.gmem = hp.gmem; tl.sidx = hp.sidx; tl.nt = c->s->nt;
+            tl.W = c->d_W; tl.ginv = c->d_ginv; tl.P = c->d_P; tl.gA = hp.gA; tl.gB = hp.gB; tl.gptr = hp.gptr; tl.sidx = hp.sidx; tl.nt = c->s->nt;
             tl.out = c->d_outh; tl.out_host = c->h_out;
             const unsigned nblk = (unsigned)((c->nj + kHierPro2Threads / 32 - 1) / (kHierPro2Threads / 32));
             CU_TRY(launch_pdl(sfh_hier_prologue2_kernel, dim3(std::max(nblk, 1u)), dim3(kHierPro2Threads), 0, c->stream, hp,
-                              (const double *)c->h_in, c->d_W));
+                              (const double *)c->h_in, c->d_W, (const double *)c->d_MHg));
             c->stats.kernel_launches++;
             SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, nullptr, &tl));
             return SFH_OK;
@@ -1799,7 +1809,7 @@ namespace {
 int p2p_alloc_inbox(sfh_ctx *c, int nranks) {
     if (c->d_inbox) return SFH_OK;
     c->p2p_vlen = round_up(1 + std::max<int64_t>(c->s->nt, 1), 2);
-    const size_t bytes = (size_t)2 * nranks * c->p2p_vlen * 8 + (size_t)2 * nranks * 8;
+    const size_t bytes = (size_t)2 * nranks * c->p2p_vlen * 16;   // [2 parities][nranks][vlen] 16-byte packets (sfh_small.cuh: st_packet)
     CU_TRY(cudaMalloc((void **)&c->d_inbox, bytes));
     CU_TRY(cudaMemset(c->d_inbox, 0, bytes));
     CU_TRY(cudaDeviceSynchronize());
@@ -1811,8 +1821,6 @@ int p2p_attach(sfh_ctx *c, int nranks, int rank, const std::vector<double *> &pe
     CU_TRY(cudaMemcpy(c->d_peers, peers.data(), (size_t)nranks * sizeof(double *), cudaMemcpyHostToDevice));
     CU_TRY(cudaMalloc((void **)&c->d_epoch, 8));
     CU_TRY(cudaMemset(c->d_epoch, 0, 8));
-    CU_TRY(cudaMalloc((void **)&c->d_shard_out, (size_t)c->p2p_vlen * 8));
-    CU_TRY(cudaMemset(c->d_shard_out, 0, (size_t)c->p2p_vlen * 8));
     c->nranks = nranks; c->rank = rank;
     c->p2p = true;
     return SFH_OK;

@@ -232,7 +232,12 @@ public:
         for (const ArrayEntry &e : entries_) {
             uint64_t n = dtype_size(e.dtype);
             bool ok = e.dtype >= 0 && e.dtype <= 3 && e.ndim >= 1 && e.ndim <= kMaxDims && e.name[kNameLen - 1] == 0;
-            for (int d = 0; ok && d < e.ndim; ++d) { ok = e.dims[d] >= 0; n *= (uint64_t)e.dims[d]; }
+            // same overflow-checked product as the writer's spec_bytes: dims whose product wraps mod 2^64 to match nbytes would pass
+            // every other check here and index far outside the mapping later (the table checksum is not cryptographic)
+            for (int d = 0; ok && d < e.ndim; ++d) {
+                ok = e.dims[d] >= 0 && !(e.dims[d] && n > (UINT64_MAX / 16) / (uint64_t)e.dims[d]);
+                n *= (uint64_t)e.dims[d];
+            }
             if (!ok || n != e.nbytes || e.offset % kAlign || e.offset < hdr_.header_bytes || e.offset > size_ || e.nbytes > size_ - e.offset) {
                 *err = "corrupt array table entry"; close(); return false;
             }

@@ -68,9 +68,11 @@ struct HierTail {
     int32_t on;          // 0 = plain fg!
     int32_t kind, nj, want_G;
     uint8_t free_mask[4];
-    const double *W;     // [4][nt]: d r_jk-weighted factors of  sum_k fullG_jk * (...)  for  R_j (cross-age), R_j (same age), mu_j, sigma
+    const double *W;     // [4][nt], template order: the factors of  sum_k fullG_jk * (...)  for  R_j (cross-age), R_j (same age), mu_j, sigma
+    const int32_t *ginv; // [nt] position of template t in the age-grouped list (gmem[ginv[t]] == t)
+    double *P;           // [4][nt] scratch, GROUP order: P[f][g] = fullG_t * W[f][t], written by the warp that reduces G_t
     const double *gA, *gB;   // [nj] d mu_j / d alpha, d mu_j / d beta
-    const int32_t *gptr, *gmem, *sidx;
+    const int32_t *gptr, *sidx;
     int64_t nt;
     double *out;         // device [1 + nj + 3]: -logL (guarded), G
     double *out_host;    // nullable mapped pinned copy
@@ -94,34 +96,49 @@ struct FinalizeParams {
     int32_t n_lpart_in;
     unsigned int *ticket;
     // K7 v2: one-shot all-reduce over NVLink peer memory, fused into this kernel's tail (nullptr = off).
-    // peers[r] = rank r's inbox, laid out [2 parities][nranks][vlen] doubles then [2][nranks] uint64 epoch flags.
+    // peers[r] = rank r's inbox: [2 parities][nranks][vlen] 16-byte self-validating packets (st_packet).
     double *const *peers;
     int32_t nranks, rank;
     int64_t vlen;
-    double *shard_out;              // device [1 + nt]: this shard's own [logL, G] before the exchange
     unsigned long long *epoch_ptr;  // device: evaluations exchanged so far on this context (read and bumped by the last
                                     // block only, so a captured CUDA graph of the evaluation can be replayed)
     HierTail hier;                  // hierarchical chain rule on the (all-reduced) gradient, by the last block
 };
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// One value of the exchange = one 16-byte packet {lo32, epoch32, hi32, epoch32}: each 8-byte half carries its own flag, so the
+// packet validates itself however the store is split on the way (8-byte aligned stores are single transactions) -- no fence and
+// no separate flag store between data and signal, which is what made the first two versions cost 17-18 us per step at 2 GPUs
+// against NCCL's 12 (profiles/r2_experiments.md).
+__device__ __forceinline__ void st_packet(void *dst, double v, uint32_t ep) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((uint32_t)b), "r"(ep), "r"((uint32_t)(b >> 32)), "r"(ep)
+                 : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ double ld_packet_wait(const void *src, uint32_t ep) {
+    uint32_t lo, f0, hi, f1;
+    do {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+    } while (f0 != ep || f1 != ep);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 constexpr int kFinalizeThreads = 256;
 
 enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
 
-// the last block of the finalize kernel: out_fg = [logL raw, +M'r] complete (all-reduced when sharded)
+// The last block of the finalize kernel.  out_fg[0] = raw logL (all-reduced when sharded); P holds, in age-group order, the
+// products fullG_t * W_f[t] that the gradient-reducing warps formed as soon as each G_t existed, so what is left here is one
+// contiguous sum per (age, factor), three 60-term dot products and two scans -- every load an L2 hit or shared memory.  (The
+// stack stream evicts everything older from L2 in spite of its evict-first hint: in the first version each dependent global
+// load here was a DRAM round trip and the tail cost 11 us; profiles/r2_experiments.md section 4.)
 __device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_fg, double *sh /*[8]*/) {
-    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges];
+    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges], s_gA[kHierTailAges], s_gB[kHierTailAges];
+    __shared__ int s_sidx[kHierTailAges], s_gptr[kHierTailAges + 1];
     __shared__ double s_par[3];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kFinalizeThreads / 32;
+    const int tid = threadIdx.x;
     const int nj = h.nj;
+    // everything that does not depend on the gradient is requested first (one DRAM latency, overlapped with the sums below)
+    for (int j = tid; j < nj; j += kFinalizeThreads) { s_sidx[j] = h.sidx[j]; s_gA[j] = h.gA[j]; s_gB[j] = h.gB[j]; }
+    for (int j = tid; j <= nj; j += kFinalizeThreads) s_gptr[j] = h.gptr[j];
     if (tid == 0) {
         const double logL = __ldcg(out_fg);
         const double v = (logL != 0.0) ? -logL : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95, solvers.jl:31
@@ -129,27 +146,28 @@ __device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_f
         if (h.out_host) h.out_host[0] = v;
     }
     if (!h.want_G) return;
-    const double *W1 = h.W, *W2 = h.W + h.nt, *W3 = h.W + 2 * h.nt, *W4 = h.W + 3 * h.nt;
-    for (int j = warp; j < nj; j += nw) {
-        const int g0 = h.gptr[j], g1 = h.gptr[j + 1];
-        double a_dr = 0.0, a_same = 0.0, a_p = 0.0, a_s = 0.0;
-        for (int g = g0 + lane; g < g1; g += 32) {
-            const int t = h.gmem[g];
-            const double fullG = -__ldcg(out_fg + 1 + t);       // d logL / d r_jk
-            if (h.kind == MH_POWERLAW_MZR) a_dr += fullG * W1[t];   // mzr.jl:166-167
-            a_same += fullG * W2[t];                                // mzr.jl:188-190 / amr.jl:141
-            a_p += fullG * W3[t];                                   // mzr.jl:194-195
-            a_s += fullG * W4[t];                                   // mzr.jl:206-207
+    __syncthreads();
+    // one THREAD per (age, factor): the group's products are contiguous in P, members in the reference's order
+    for (int idx = tid; idx < 4 * nj; idx += kFinalizeThreads) {
+        const int j = idx >> 2, f = idx & 3;
+        const int g0 = s_gptr[j], g1 = s_gptr[j + 1];
+        const double *Pf = h.P + (int64_t)f * h.nt;
+        double a = 0.0;
+        if (f != 0 || h.kind == MH_POWERLAW_MZR) {
+#pragma unroll 8
+            for (int g = g0; g < g1; ++g) a += __ldcg(Pf + g);
         }
-        a_dr = warp_sum(a_dr); a_same = warp_sum(a_same); a_p = warp_sum(a_p); a_s = warp_sum(a_s);
-        if (lane == 0) { s_dr[j] = a_dr; s_G[j] = -a_same; s_p[j] = -a_p; s_s[j] = a_s; }
+        if (f == 0) s_dr[j] = a;         // mzr.jl:166-167
+        else if (f == 1) s_G[j] = -a;    // mzr.jl:188-190 / amr.jl:141
+        else if (f == 2) s_p[j] = -a;    // mzr.jl:194-195
+        else s_s[j] = a;                 // mzr.jl:206-207
     }
     __syncthreads();
     {   // parameter gradients: fixed-order (strided + xor tree) block sums  (mzr.jl:196-198,201-208)
         double ga = 0.0, gb = 0.0, gs = 0.0;
         for (int j = tid; j < nj; j += kFinalizeThreads) {
-            ga += s_p[j] * h.gA[j];
-            gb += s_p[j] * h.gB[j];
+            ga += s_p[j] * s_gA[j];
+            gb += s_p[j] * s_gB[j];
             gs -= s_s[j];
         }
         const double ta = block_sum<kFinalizeThreads>(ga, sh);
@@ -157,14 +175,22 @@ __device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_f
         const double ts = block_sum<kFinalizeThreads>(gs, sh);
         if (tid == 0) { s_par[0] = ta; s_par[1] = tb; s_par[2] = ts; }
     }
-    __syncthreads();
-    if (tid == 0 && h.kind == MH_POWERLAW_MZR) {
-        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181
-        double run = 0.0;
-        for (int i = nj - 1; i >= 1; --i) {
-            run += s_dr[h.sidx[i]];
-            s_G[h.sidx[i - 1]] -= run;
+    if (h.kind == MH_POWERLAW_MZR) {
+        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181.  The serial part runs over a
+        // copy in sorted order (s_p is free again after the barrier inside block_sum): one add per age, loads hoisted
+        __syncthreads();
+        for (int i = tid; i < nj; i += kFinalizeThreads) s_p[i] = s_dr[s_sidx[i]];
+        __syncthreads();
+        if (tid == 0) {
+            double run = 0.0;
+#pragma unroll 8
+            for (int i = nj - 1; i >= 1; --i) {
+                run += s_p[i];
+                s_s[i - 1] = run;        // cum[i], to be subtracted from G[s[i-1]]
+            }
         }
+        __syncthreads();
+        for (int i = tid; i + 1 < nj; i += kFinalizeThreads) s_G[s_sidx[i]] -= s_s[i];
     }
     __syncthreads();
     for (int j = tid; j < nj + 3; j += kFinalizeThreads) {
@@ -174,22 +200,26 @@ __device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_f
     }
 }
 
-// Everything here is latency, not bandwidth (60 k logs, ~1 MB of partials): the shape is chosen so that no thread
-// ever waits on more than ~2 dependent L2 round trips.  Measured alternatives (ncu launch lists under profiles/):
-// 296 blocks with a per-thread serial loop over the cluster partials 13 us; one 8-CTA cluster with a DSMEM
-// reduction 27 us (too few threads: 15 dependent load+log chains each).
+// Everything here is latency, not bandwidth (~1 MB of partials): the shape is chosen so that no thread ever waits on more than
+// ~2 dependent L2 round trips.  Measured alternatives (ncu launch lists under profiles/): 296 blocks with a per-thread serial loop
+// over the cluster partials 13 us; one 8-CTA cluster with a DSMEM reduction 27 us (too few threads).
 //
-// Multi-GPU (p.peers): the LAST block to finish is the whole exchange -- it pushes this shard's [logL, G] into slot
-// [parity][rank] of every rank's inbox with coalesced 16-byte NVLink stores, issues ONE system-scope fence, publishes
-// the epoch flags, waits for the nranks flags in its own inbox and sums the nranks vectors in rank order (identical
-// order on every rank => bit-identical results everywhere).  Round 1 fenced at system scope in every block, pushed
-// scalar stores from 2400 warps and needed a third kernel for the sum: ~20 us per step at 8 GPUs.
+// Multi-GPU (p.peers): the exchange happens PER GRADIENT ENTRY in the warp that produced it -- the warp stores its entry as a
+// self-validating packet into slot [parity][rank] of every rank's inbox, polls the nranks packets of the same entry in its own
+// inbox and sums them in rank order (identical order on every rank => bit-identical results everywhere).  2400 warps exchange
+// in parallel: one NVLink round trip for the whole vector, no fence, no flag, no extra kernel, no block that serialises the sum
+// (three earlier versions did, at 16-18 us per step on 2 GPUs; profiles/r2_experiments.md section 3).  The last block only
+// exchanges logL.  Block b handles the same entries on every rank and pushes before it polls, so the ranks' grids cannot
+// wait on each other in a cycle even if a grid were larger than what is co-resident.
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
     griddep_wait();  // PDL: launched while the fused kernel drains
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *const gout = p.peers ? p.shard_out : p.out;
+    // the epoch of THIS evaluation: the stored one + 1 (bumped by the last block only, after every block has read it)
+    const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
+    const uint32_t ep32 = (uint32_t)epoch;
+    const int64_t par = (int64_t)(epoch & 1ull);
     // logL: fixed contiguous slice of bins per block, fixed trees => deterministic
     if (!p.lpart_in) {
         const int64_t per = (p.nb + p.nblk_logl - 1) / p.nblk_logl;
@@ -205,14 +235,27 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     // G_j = sum over clusters: one WARP per template, lanes take clusters lane, lane+32, ... (independent loads)
     if (p.want_G) {
         const int64_t nwarps = (int64_t)gridDim.x * (kFinalizeThreads / 32);
+        const uint4 *inbox = p.peers ? reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen : nullptr;
         for (int64_t j = (int64_t)blockIdx.x * (kFinalizeThreads / 32) + warp; j < p.nt; j += nwarps) {
+            // hierarchical: this template's chain-rule factors and its slot in the age-grouped product table (independent of G)
+            double wf = 0.0;
+            int gpos = 0;
+            if (p.hier.on && p.hier.want_G && lane < 4) { wf = p.hier.W[(int64_t)lane * p.nt + j]; gpos = p.hier.ginv[j]; }
             double s = 0.0;
             for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
-            s = warp_sum(s);
-            if (lane == 0) {
-                gout[1 + j] = s;
-                if (p.out_host && !p.peers) p.out_host[1 + j] = s;
+            s = warp_sum(s);   // xor tree: every lane holds the total
+            if (p.peers) {
+                if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen + 1 + j, s, ep32);
+                const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen + 1 + j, ep32) : 0.0;
+                double t = 0.0;
+                for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
+                s = t;
             }
+            if (lane == 0) {
+                p.out[1 + j] = s;
+                if (p.out_host) p.out_host[1 + j] = s;
+            }
+            if (p.hier.on && p.hier.want_G && lane < 4) p.hier.P[(int64_t)lane * p.nt + gpos] = (-s) * wf;   // fullG_t = d logL / d r_t = -(M'r)_t
         }
     }
     // last block folds the per-block logL partials (parallel, fixed order)
@@ -226,60 +269,23 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     const double *lp = p.lpart_in ? p.lpart_in : p.lpart;
     const int nlp = p.lpart_in ? p.n_lpart_in : p.nblk_logl;
     for (int b = threadIdx.x; b < nlp; b += kFinalizeThreads) s += __ldcg(lp + b);
-    const double all = block_sum<kFinalizeThreads>(s, sh);
-    if (threadIdx.x == 0) {
-        gout[0] = all;
-        if (p.out_host && !p.peers) p.out_host[0] = all;
-        *p.ticket = 0u;  // re-arm for the next evaluation on this context
-    }
-    if (!p.peers) {
-        if (p.hier.on) {
-            __syncthreads();   // thread 0's gout[0]
-            hier_tail(p.hier, p.out, sh);
-        }
-        return;
-    }
-
-    // ---------------- one-shot all-reduce, entirely inside this block ----------------
-    __shared__ unsigned long long s_epoch;
-    if (threadIdx.x == 0) {
-        s_epoch = *p.epoch_ptr + 1ull;
-        *p.epoch_ptr = s_epoch;
-    }
-    __syncthreads();   // also orders thread 0's store of gout[0] before the reads below
-    const unsigned long long epoch = s_epoch;
-    const int64_t par = (int64_t)(epoch & 1ull);
-    const int64_t n = p.want_G ? 1 + p.nt : 1;
-    const int64_t n2 = (n + 1) / 2;               // 16-byte units (vlen is even, inboxes are 16-byte aligned)
-    // push: every peer gets the vector as coalesced double2 stores; reads come from L2 (written by other blocks)
-    for (int64_t i = threadIdx.x; i < n2; i += kFinalizeThreads) {
-        double2 v;
-        v.x = __ldcg(gout + 2 * i);
-        v.y = (2 * i + 1 < n) ? __ldcg(gout + 2 * i + 1) : 0.0;
-        for (int r = 0; r < p.nranks; ++r) {
-            double2 *dst = reinterpret_cast<double2 *>(p.peers[r] + (par * p.nranks + p.rank) * p.vlen) + i;
-            *dst = v;
-        }
-    }
-    __threadfence_system();   // every thread: its peer stores are performed system-wide before the flag is published
-    __syncthreads();
-    if (threadIdx.x < p.nranks) {
-        unsigned long long *flags = reinterpret_cast<unsigned long long *>(p.peers[threadIdx.x] + 2 * p.nranks * p.vlen);
-        st_release_sys_u64(flags + par * p.nranks + p.rank, epoch);
-        // ... and wait for every rank's vector to have landed in MY inbox
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.peers[p.rank] + 2 * p.nranks * p.vlen) + par * p.nranks;
-        while (ld_acquire_sys_u64(mine + threadIdx.x) != epoch) { }
-    }
-    __syncthreads();
-    const double *inbox = p.peers[p.rank] + par * p.nranks * p.vlen;
-    for (int64_t i = threadIdx.x; i < n; i += kFinalizeThreads) {
+    double all = block_sum<kFinalizeThreads>(s, sh);   // valid in warp 0
+    if (p.peers && warp == 0) {
+        if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen, all, ep32);
+        const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen;
+        const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen, ep32) : 0.0;
         double t = 0.0;
-        for (int r = 0; r < p.nranks; ++r) t += __ldcv(inbox + r * p.vlen + i);
-        p.out[i] = t;
-        if (p.out_host) p.out_host[i] = t;
+        for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
+        all = t;
+    }
+    if (threadIdx.x == 0) {
+        p.out[0] = all;
+        if (p.out_host) p.out_host[0] = all;
+        *p.ticket = 0u;  // re-arm for the next evaluation on this context
+        if (p.peers) *p.epoch_ptr = epoch;
     }
     if (p.hier.on) {
-        __syncthreads();   // this block wrote all of p.out
+        __syncthreads();   // thread 0's out[0]
         hier_tail(p.hier, p.out, sh);
     }
 }
@@ -491,82 +497,108 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const H
 
 // calculate_coeffs (mzr.jl:50-79 / amr.jl:50-73) for ONE evaluation, spread over the grid: one warp per age group.  Besides the
 // coefficients it prepares everything of the chain rule (mzr.jl:131-209) that does not depend on the gradient -- the factors
-// W1..W4 that multiply fullG_jk in the four per-age sums -- so that the finalize kernel's tail (hier_tail) is left with dot
-// products.  `vars_in` may be the caller's mapped pinned buffer: 63 doubles over PCIe instead of a memcpy node in front.
+// W1..W4 that multiply fullG_jk in the four per-age sums -- so that the finalize kernel is left with products and sums.
+// `vars_in` may be the caller's mapped pinned buffer: 63 doubles over PCIe instead of a memcpy node in front.
+// Every global load is a DRAM round trip here (the stack stream has flushed L2), so the dependent chain is kept to
+// gptr -> {MHg, gmem}: MHg is the metallicity grid in age-group order (built at sfh_hier_bind), the members' A_jk stay in
+// registers between the three passes, and the serial cumulative mass runs over a sorted copy in shared memory.
 constexpr int kHierPro2Threads = 256;
-__global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(const HierParams p, const double *vars_in, double *W) {
-    __shared__ double sv[kHierTailAges + 3];
-    __shared__ int ssidx[kHierTailAges];
+constexpr int kHierPro2Regs = 4;   // members per lane kept in registers (groups of up to 128 templates; larger ones recompute)
+__global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(const HierParams p, const double *vars_in, double *W,
+                                                                               const double *MHg) {
+    __shared__ double sv[kHierTailAges + 3], sRs[kHierTailAges];
+    __shared__ int spos[kHierTailAges];
     griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierPro2Threads / 32;
     const int nj = p.nj;
-    for (int j = tid; j < nj + 3; j += kHierPro2Threads) {
-        const double v = vars_in[j];
-        sv[j] = v;
-        if (blockIdx.x == 0) const_cast<double *>(p.variables)[j] = v;   // device copy for later kernels
+    const int j = blockIdx.x * nw + warp;
+    // independent loads first: the group's extent, its members and metallicities, its age
+    int g0 = 0, g1 = 0;
+    double age = 0.0;
+    if (j < nj) { g0 = p.gptr[j]; g1 = p.gptr[j + 1]; age = p.logAge_u[j]; }
+    for (int i = tid; i < nj + 3; i += kHierPro2Threads) {
+        const double v = vars_in[i];
+        sv[i] = v;
+        if (blockIdx.x == 0) const_cast<double *>(p.variables)[i] = v;   // device copy for later kernels
     }
-    for (int j = tid; j < nj; j += kHierPro2Threads) ssidx[j] = p.sidx[j];
+    int srt = -1;
+    if (p.kind == MH_POWERLAW_MZR && tid < nj) srt = p.sidx[tid];          // (nj <= kHierTailAges <= block size)
+    int mt[kHierPro2Regs];
+    double mh[kHierPro2Regs];
+#pragma unroll
+    for (int u = 0; u < kHierPro2Regs; ++u) {
+        const int g = g0 + lane + 32 * u;
+        mt[u] = (g < g1) ? p.gmem[g] : -1;
+        mh[u] = (g < g1) ? MHg[g] : 0.0;
+    }
     __syncthreads();
+    if (srt >= 0) { sRs[tid] = sv[srt]; spos[srt] = tid; }                 // R in oldest-first order; where each age sits in it
+    __syncthreads();
+    if (j >= nj) return;
     const double alpha = sv[nj], beta = sv[nj + 1], sigma = sv[nj + 2];
     const double s2 = sigma * sigma, s3 = s2 * sigma;
-    const int j = blockIdx.x * nw + warp;
-    if (j >= nj) return;
-    double arg = p.logAge_u[j];
+    double arg = age;
     if (p.kind == MH_POWERLAW_MZR) {
         // cumsum(R[s])[invperm(s)]  mzr.jl:61-66 -- oldest first; this age's entry is the running sum up to its own position
+        const int pos = spos[j];
         double run = 0.0;
-        for (int i = 0; i < nj; ++i) {
-            const int jj = ssidx[i];
-            run += sv[jj];
-            if (jj == j) break;
-        }
+#pragma unroll 4
+        for (int i = 0; i <= pos; ++i) run += sRs[i];
         arg = run;
     }
     double mu, gA, gB, gM;
     d_mh_eval(p.kind, alpha, beta, p.fixed, arg, mu, gA, gB, gM);
     if (lane == 0) { p.mu[j] = mu; p.gA[j] = gA; p.gB[j] = gB; p.gM[j] = gM; }
-    const int g0 = p.gptr[j], g1 = p.gptr[j + 1];
     const double Rj = sv[j];
-    double a = 0.0;
-    for (int g = g0 + lane; g < g1; g += 32) {
-        const int t = p.gmem[g];
-        const double z = (p.MH[t] - mu) / sigma;
-        const double A = exp(-(z * z) / 2.0);  // dispersion_models.jl:92
-        p.Ajk[t] = A;
-        a += A;
+    const bool big = g1 - g0 > 32 * kHierPro2Regs;   // members beyond the register window are recomputed from global memory
+    double A[kHierPro2Regs], a = 0.0;
+#pragma unroll
+    for (int u = 0; u < kHierPro2Regs; ++u) {
+        const double z = (mh[u] - mu) / sigma;
+        A[u] = (mt[u] >= 0) ? exp(-(z * z) / 2.0) : 0.0;  // dispersion_models.jl:92
+        a += A[u];
     }
+    if (big)
+        for (int g = g0 + lane + 32 * kHierPro2Regs; g < g1; g += 32) { const double z = (MHg[g] - mu) / sigma; a += exp(-(z * z) / 2.0); }
     const double Aj = warp_sum(a);
     if (lane == 0) p.Asum[j] = Aj;
     double kAR = 0.0, kmu = 0.0, ksg = 0.0;
-    for (int g = g0 + lane; g < g1; g += 32) {
-        const int t = p.gmem[g];
-        const double A = p.Ajk[t], d = p.MH[t] - mu;
-        const double dAmu = A * d / s2;      // dispersion_models.jl:99
-        const double dAsg = A * d * d / s3;  // dispersion_models.jl:98
-        kAR += dAmu * gM;                    // mzr.jl:162,164
+    auto sums = [&](double Av, double d) {
+        const double dAmu = Av * d / s2;      // dispersion_models.jl:99
+        const double dAsg = Av * d * d / s3;  // dispersion_models.jl:98
+        kAR += dAmu * gM;                     // mzr.jl:162,164
         kmu += dAmu;
         ksg += dAsg;
-    }
+    };
+#pragma unroll
+    for (int u = 0; u < kHierPro2Regs; ++u)
+        if (mt[u] >= 0) sums(A[u], mh[u] - mu);
+    if (big)
+        for (int g = g0 + lane + 32 * kHierPro2Regs; g < g1; g += 32) { const double d = MHg[g] - mu, z = d / sigma; sums(exp(-(z * z) / 2.0), d); }
     kAR = warp_sum(kAR); kmu = warp_sum(kmu); ksg = warp_sum(ksg);
     const double RA = Rj / Aj;
     const int64_t nt = p.nt;
-    for (int g = g0 + lane; g < g1; g += 32) {
-        const int t = p.gmem[g];
-        const double A = p.Ajk[t], d = p.MH[t] - mu;
-        const double dAmu = A * d / s2, dAsg = A * d * d / s3;
-        const double coeff = A * Rj / Aj;    // mzr.jl:76
+    auto emit = [&](int t, double Av, double d) {
+        const double dAmu = Av * d / s2, dAsg = Av * d * d / s3;
+        const double coeff = Av * Rj / Aj;    // mzr.jl:76
         p.coeffs[t] = coeff;
+        p.Ajk[t] = Av;
         if (p.kind == MH_POWERLAW_MZR) {
             const double dAR = dAmu * gM;
-            W[t] = RA * (dAR - (A * kAR / Aj));                            // mzr.jl:166-167
-            W[nt + t] = coeff / Rj + (dAR - (kAR * A / Aj)) * Rj / Aj;     // mzr.jl:188-190
+            W[t] = RA * (dAR - (Av * kAR / Aj));                            // mzr.jl:166-167
+            W[nt + t] = coeff / Rj + (dAR - (kAR * Av / Aj)) * Rj / Aj;     // mzr.jl:188-190
         } else {
             W[t] = 0.0;
-            W[nt + t] = coeff / Rj;                                        // amr.jl:141
+            W[nt + t] = coeff / Rj;                                         // amr.jl:141
         }
-        W[2 * nt + t] = RA * (dAmu - A / Aj * kmu);                        // mzr.jl:194-195
-        W[3 * nt + t] = RA * (dAsg - A / Aj * ksg);                        // mzr.jl:206-207
-    }
+        W[2 * nt + t] = RA * (dAmu - Av / Aj * kmu);                        // mzr.jl:194-195
+        W[3 * nt + t] = RA * (dAsg - Av / Aj * ksg);                        // mzr.jl:206-207
+    };
+#pragma unroll
+    for (int u = 0; u < kHierPro2Regs; ++u)
+        if (mt[u] >= 0) emit(mt[u], A[u], mh[u] - mu);
+    if (big)
+        for (int g = g0 + lane + 32 * kHierPro2Regs; g < g1; g += 32) { const double d = MHg[g] - mu, z = d / sigma; emit(p.gmem[g], exp(-(z * z) / 2.0), d); }
 }
 
 // chain rule: mzr.jl:124-210 / amr.jl:118-169.  fullG = d logL/d r = -(fg_out[1+t]).

@@ -616,9 +616,36 @@ def grad_loglikelihood_(G, composite, models, data=None):
     return G
 
 
+def _grad_single(model, composite, data):
+    """``grad-loglikelihood(model, composite, data)`` for ONE template (fitting_base.jl:144-160): the scalar
+    ``sum_i -c_i (1 - n_i / max(m_i, eps(T)))`` with ``T = promote_type(eltype(model), eltype(composite), eltype(data))``.
+    On the device this is ``sfh_grad_loglikelihood`` on a one-column stack."""
+    m, c, d = np.asarray(model), np.asarray(composite), np.asarray(data)
+    if not (m.shape == c.shape == d.shape):
+        raise ValueError("axes(model) == axes(composite) == axes(data) must hold")      # fitting_base.jl:147
+    T = np.result_type(*[a.dtype if a.dtype.kind == "f" else np.float32 for a in (m, c, d)])   # integers promote to the float type
+    if T not in (np.dtype(np.float32), np.dtype(np.float64)):
+        T = np.dtype(np.float64)
+    ds = DeviceStack(np.asfortranarray(m.reshape(-1, 1, order="F"), dtype=T), d.reshape(-1, order="F"), dtype=T)
+    try:
+        buf = np.ascontiguousarray(c.reshape(-1, order="F"), dtype=np.float64).copy()
+        g = np.empty(1)
+        L.check(L.lib.sfh_grad_loglikelihood(ds.ctx().handle, _dp(buf), _dp(g)))
+    finally:
+        ds.close()
+    return T.type(g[0])
+
+
 def grad_loglikelihood(*args):
-    """``grad-loglikelihood(models, composite, data)`` / ``(coeffs, models, data)`` -> new gradient vector."""
+    """``grad-loglikelihood(model, composite, data)`` -> scalar (one template, fitting_base.jl:144-160);
+    ``(models, composite, data)`` / ``(coeffs, models, data)`` -> new gradient vector (:171-182, :193-211)."""
     a, b, data = args
+    if not isinstance(a, (DeviceStack, list, tuple)) and not isinstance(b, (DeviceStack, list, tuple)):
+        sa, sb = np.shape(a), np.shape(b)
+        if sa == sb and len(sa) >= 1:
+            # same axes for the first two arguments: the single-template method (a coefficient vector never has the stack's shape,
+            # and a stack never has the composite's).  Mismatched `data` raises like the reference's @argcheck.
+            return _grad_single(a, b, data)
     if isinstance(b, DeviceStack) or (not isinstance(a, DeviceStack) and np.asarray(a).ndim == 1 and not isinstance(a, (list, tuple))):
         coeffs, models = a, b                                              # (coeffs, models, data)  :193-211
         ds = device_stack(models, data)

@@ -42,12 +42,21 @@ mutable struct DeviceStack{S} <: AbstractMatrix{S}
     idle::Vector{Ptr{Cvoid}}
     all::Vector{Ptr{Cvoid}}
     bound::Dict{Ptr{Cvoid}, Tuple{Vector{Float64}, Vector{Float64}}}   # ctx -> the (logAge, MH) grid sfh_hier_bind gave it
-    function DeviceStack{S}(host, dims, handle::Ptr{Cvoid}) where S
+    # Multi-GPU from this ONE process (sfh_group_*): `group` owns one shard per GPU and a single PRIMARY context whose evaluations
+    # fan out to every GPU and come back all-reduced; callers take turns on it (`grouplock`).  handle == C_NULL then.
+    group::Ptr{Cvoid}
+    primary::Ptr{Cvoid}
+    grouplock::ReentrantLock
+    function DeviceStack{S}(host, dims, handle::Ptr{Cvoid}, group::Ptr{Cvoid}=C_NULL, primary::Ptr{Cvoid}=C_NULL) where S
         obj = new{S}(host, dims, handle, ReentrantLock(), Ptr{Cvoid}[], Ptr{Cvoid}[],
-                     Dict{Ptr{Cvoid}, Tuple{Vector{Float64}, Vector{Float64}}}())
+                     Dict{Ptr{Cvoid}, Tuple{Vector{Float64}, Vector{Float64}}}(), group, primary, ReentrantLock())
         finalizer(obj) do o   # o is unreachable: nobody holds its lock or one of its contexts any more
-            foreach(c -> ccall((:sfh_ctx_destroy, libsfh), Cint, (Ptr{Cvoid},), c), o.all)
-            ccall((:sfh_stack_destroy, libsfh), Cint, (Ptr{Cvoid},), o.handle)
+            if o.group != C_NULL
+                ccall((:sfh_group_destroy, libsfh), Cint, (Ptr{Cvoid},), o.group)   # releases the primary context and every shard
+            else
+                foreach(c -> ccall((:sfh_ctx_destroy, libsfh), Cint, (Ptr{Cvoid},), c), o.all)
+                ccall((:sfh_stack_destroy, libsfh), Cint, (Ptr{Cvoid},), o.handle)
+            end
         end
         return obj
     end
@@ -60,6 +69,7 @@ function new_ctx!(s::DeviceStack)   # caller holds s.lock
 end
 # f(ctx) with a context nobody else is using; safe from any number of tasks / threads (one ctx <=> one concurrent caller)
 function with_ctx(f, s::DeviceStack)
+    s.group != C_NULL && return lock(() -> f(s.primary), s.grouplock)   # one evaluation at a time spans all the group's GPUs
     c = lock(() -> isempty(s.idle) ? new_ctx!(s) : pop!(s.idle), s.lock)
     try
         return f(c)
@@ -75,6 +85,20 @@ function DeviceStack(models::Matrix{S}, data::AbstractVector{D}) where {S <: Uni
         (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
         h, models, size(models, 1), size(models, 2), dtype_code(S), d, dtype_code(eltype(d)), C_NULL))
     return DeviceStack{S}(models, size(models), h[])
+end
+# The same stack sharded by bin rows over several GPUs of THIS process -- what fit_sfh / fit_templates need for a stack that does
+# not fit one GPU (every reference caller is a single process: generic_fitting.jl:242-411, solvers.jl:82-90).  No launcher, no
+# NCCL: the library splits the rows, enables peer access and all-reduces [logL, G] inside its finalize kernel.
+function DeviceStack(models::Matrix{S}, data::AbstractVector{D}, devices::AbstractVector{<:Integer}) where {S <: Union{Float32, Float64}, D}
+    size(models, 1) == length(data) || throw(ArgumentError("axes(models,1) != axes(data,1)"))
+    d = D <: Union{Float32, Float64, Int64} ? collect(data) : Float64.(data)
+    devs = convert(Vector{Cint}, devices)
+    g = Ref{Ptr{Cvoid}}(C_NULL); c = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve models d devs check(ccall((:sfh_group_create, libsfh), Cint,
+        (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Cint, Ptr{Cint}, Cint, Ptr{Cvoid}),
+        g, models, size(models, 1), size(models, 2), dtype_code(S), d, dtype_code(eltype(d)), devs, Cint(length(devs)), C_NULL))
+    check(ccall((:sfh_group_ctx, libsfh), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), g[], c))
+    return DeviceStack{S}(models, size(models), C_NULL, g[], c[])
 end
 Base.size(s::DeviceStack) = s.dims
 Base.getindex(s::DeviceStack, i...) = getindex(s.host, i...)
@@ -144,7 +168,9 @@ function bind!(s::DeviceStack, c::Ptr{Cvoid}, logAge, MH)
 end
 
 function SFH.fg!(F, G, MHmodel0::DeviceMH, dispmodel0::GaussianDispersion,
-                 variables::AbstractVector{<:Number}, models::DeviceStack, data, composite,
+                 variables::AbstractVector{<:Number}, models::DeviceStack,
+                 data::Union{AbstractVector{<:Number},AbstractMatrix{<:Number}},
+                 composite::Union{AbstractVector{<:Number},AbstractMatrix{<:Number}},
                  logAge::AbstractVector{<:Number}, metallicities::AbstractVector{<:Number})
     v = convert(Vector{Float64}, variables)
     free = UInt8[free_params(MHmodel0)..., free_params(dispmodel0)..., 0]

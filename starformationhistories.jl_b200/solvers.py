@@ -26,7 +26,7 @@ import numpy as np
 from scipy import optimize
 
 from . import _lib as L
-from .fitting import DeviceStack, composite_, device_stack, fg_ as _fg_flat
+from .fitting import DeviceStack, DeviceStackGroup, composite_, device_stack, fg_ as _fg_flat
 from .hierarchical import HierarchicalOptimizer, calculate_coeffs, logtransform, exptransform
 from .sampling import HMCModel, MCMCModel
 
@@ -37,9 +37,12 @@ def renormalize_x0(data, models, x0, full_coeffs=None):
     x0 = np.asarray(x0, dtype=np.float64)
     full = x0 if full_coeffs is None else np.asarray(full_coeffs, dtype=np.float64)
     ds = device_stack(models, data)
-    comp = np.empty(ds.rows)
-    composite_(comp, full, ds)
-    csum = comp.sum()
+    if isinstance(ds, DeviceStackGroup):
+        csum = float(full @ ds.column_sums())       # sum_i (M full)_i without gathering the sharded composite
+    else:
+        comp = np.empty(ds.rows)
+        composite_(comp, full, ds)
+        csum = comp.sum()
     if csum == 0:
         return x0.copy()                                                   # :112
     return x0 * (np.asarray(data, dtype=np.float64).sum() / csum)          # :113-114

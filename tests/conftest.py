@@ -71,3 +71,37 @@ def make_hier_problem(nj=21, nk=26, nb=400, seed=94823, la_hi=10.0, la_lo=8.0, s
     R = rng.random(nj) * 1e6
     M = np.asfortranarray(rng.random((nb, nt)) / 1e5)
     return dict(nj=nj, nt=nt, nb=nb, logAge=logAge, MH=MH, R=R, M=M, rng=rng)
+
+
+def hier_grad_scale(kind, fixed, v, M, data, logAge, MH, eps=np.finfo(np.float64).eps):
+    """Backward-error scale of the hierarchical gradient, the analogue of test_gpu_core.assert_grad_close's `gscale`.
+
+    G_p = sum_t fullG_t * J_tp with fullG_t = -(M' r)_t and J = d r / d variables.  Any correct implementation carries a
+    rounding error of eps-level times  sum_t |J_tp| * sum_i |M_it r_i|  per component (re-ordering the bin sums and the
+    member sums; the parameter components are near-total cancellations at the optimum), so that is what 1e-10 is taken
+    relative to -- not |G_p|.  J comes from central differences of the oracle's calculate_coeffs: it only sets a SCALE, so
+    ~1e-6 relative accuracy is plenty."""
+    import oracle as O
+    v = np.asarray(v, dtype=np.float64)
+    nj = v.shape[0] - 3
+
+    def coeffs(u):
+        return O.calculate_coeffs(kind, u[nj], u[nj + 1], fixed, u[nj + 2], u[:nj], logAge, MH)
+
+    c = coeffs(v)
+    m = np.asarray(M, dtype=np.float64) @ c
+    r = 1.0 - np.asarray(data, dtype=np.float64) / np.maximum(m, eps)
+    gs = np.abs(M).T @ np.abs(r)                       # flat backward-error scale per template
+    scale = np.empty(nj + 3)
+    for p in range(nj + 3):
+        h = 1e-6 * max(abs(v[p]), 1e-12)
+        up, dn = v.copy(), v.copy()
+        up[p] += h; dn[p] -= h
+        J = (coeffs(up) - coeffs(dn)) / (2 * h)
+        scale[p] = np.abs(J) @ gs
+    return scale
+
+
+def assert_hier_grad_close(G, Gq, scale, rtol=1e-10, what=""):
+    err = np.abs(np.asarray(G) - np.asarray(Gq)) / (scale + 1e-300)
+    assert np.all(err <= rtol), f"{what}: max |dG| / scale = {float(err.max()):.3e} at component {int(err.argmax())} (bar {rtol:g})"

@@ -120,6 +120,21 @@ def test_corruption_and_truncation_are_detected(tmp_path):
     with pytest.raises(sfh_b200.SFHError) as ei:
         sio.SFHFile(tmp_path / "does-not-exist.sfh")
     assert ei.value.status == L.SFH_ERR_IO
+    # a crafted table entry whose dims product WRAPS mod 2^64 onto the true byte count (table checksum recomputed, so only the
+    # overflow check can catch it): dims (2^61 + 125, 8) x 8 bytes == 1000 x 8 bytes mod 2^64  
+    import struct
+    import file_ref
+    b = bytearray(raw)
+    ent = list(struct.unpack("<48sii4qQQQ2Q", bytes(b[128:256])))
+    assert ent[0].rstrip(b"\0") == b"x" and ent[3] == 1000 and ent[8] == 8000
+    ent[2], ent[3], ent[4] = 2, (1 << 61) + 125, 8
+    assert ((ent[3] * ent[4] * 8) & ((1 << 64) - 1)) == 8000
+    b[128:256] = struct.pack("<48sii4qQQQ2Q", *ent)
+    table = bytes(b[128:128 + 2 * 128])
+    hdr = list(struct.unpack("<8sIIQQii8qQ2Q", bytes(b[:128])))
+    hdr[15] = file_ref.checksum(table)
+    b[:128] = struct.pack("<8sIIQQii8qQ2Q", *hdr)
+    expect_io(b, at_open=True)
 
 
 def test_writer_argument_errors(tmp_path):

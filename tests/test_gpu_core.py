@@ -70,6 +70,21 @@ def test_reference_kats(S, T, rtol):
     # grad-loglikelihood / grad-loglikelihood!  :71-162
     models = [jl([[1, 1, 1], [0, 0, 0], [0, 0, 0]], T), jl([[0, 0, 0], [1, 1, 1], [0, 0, 0]], T), jl([[0, 0, 0], [0, 0, 0], [1, 1, 1]], T)]
     c3 = np.array([1.5, 3, 3], dtype=T)
+    # grad-loglikelihood(model, composite, data): ONE template, scalar result of the promoted type  fitting_core_test.jl:77-97
+    model1 = jl([[0, 0, 0], [0, 0, 0], [1, 1, 1]], T)
+    C1 = jl([[1, 1, 1], [2, 2, 2], [3, 3, 3]], T)
+    d1 = np.asfortranarray(np.array([[1, 1, 1], [2, 2, 2], [2, 2, 2]], dtype=np.int64))
+    r = S.grad_loglikelihood(model1, C1, d1)
+    assert r == pytest.approx(-1, rel=rtol) and isinstance(r, T)                       # :79-80
+    r = S.grad_loglikelihood(model1.reshape(-1, order="F"), C1.reshape(-1, order="F"), d1.reshape(-1, order="F"))
+    assert r == pytest.approx(-1, rel=rtol) and isinstance(r, T)                       # :85-86 (flattened inputs)
+    mz_ = jl([[1, 1, 1], [0, 0, 0], [0, 0, 0]], T)
+    Cz_ = jl([[1.5, 1.5, 1.5], [3, 3, 3], [3, 3, 3]], T)
+    dz_ = np.asfortranarray(np.array([[0, 0, 0], [2, 2, 2], [2, 2, 2]], dtype=np.int64))
+    r = S.grad_loglikelihood(mz_, Cz_, dz_)
+    assert r == pytest.approx(-3, rel=rtol) and isinstance(r, T)                       # :92-97 zero-data bins contribute -c_ij
+    with pytest.raises(ValueError):
+        S.grad_loglikelihood(model1, C1, d1[:2])                                       # fitting_base.jl:147
     g = S.grad_loglikelihood(c3, S.DeviceStack(models, data), data)
     assert g.dtype == T and g.shape == (3,) and np.allclose(g, [-1, -1, -1], rtol=rtol)
     grad = np.empty(3, dtype=T)
@@ -389,7 +404,7 @@ def test_concurrent_callers_share_a_stack(S):
         assert out[k][0] == ref[k][0] and np.array_equal(out[k][1], ref[k][1])
 
 
-# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+# ------------------------------------------------------------------ BASELINE sizes: full oracle comparison + size-independent properties
 @pytest.mark.parametrize("nb,nt,dtype", [(60000, 2400, np.float64), (40000, 500, np.float64), (200000, 1000, np.float32)])
 def test_full_size_properties(S, nb, nt, dtype):
     rng = np.random.default_rng(1)
@@ -409,13 +424,20 @@ def test_full_size_properties(S, nb, nt, dtype):
     # (3) linearity of composite!
     _, _, comp2 = ds.eval_fg(2.5 * x1, want_G=False, want_composite=True)
     assert np.allclose(comp2, 2.5 * comp, rtol=1e-13)
-    # (4) a spot check of a few gradient components and composite rows against the oracle on the downloaded stack
-    js = [0, 1, nt // 2, nt - 1]
-    for j in js:
-        assert G[j] == pytest.approx(float(np.dot(Md[:, j].astype(np.float64), resid)), rel=1e-9, abs=1e-6)
-    rows = [0, 1, nb // 3, nb - 1]
-    for i in rows:
-        assert comp[i] == pytest.approx(float(np.dot(Md[i, :].astype(np.float64), x1)), rel=1e-12)
+    # (4) the FULL result against the oracle on the downloaded stack: logL and every one of the nt gradient components from the
+    # double-precision restatement of the reference's two-pass fg! (O.fg; Float32 stacks: the __float128 arbiter on the
+    # Float32-stored values, since the product accumulates those in FP64), every composite row from a numpy gemv.
+    if dtype is np.float64:
+        nlo, Go, _ = O.fg(x1, Md, data)
+        gscale = np.abs(Md).T @ np.abs(1.0 - data / np.maximum(Md @ x1, np.finfo(np.float64).eps))
+        assert nl == pytest.approx(nlo, rel=RTOL_LOGL)
+        assert_grad_close(G, Go, gscale)
+        assert np.allclose(comp, Md @ x1, rtol=1e-13, atol=0)
+    else:
+        nlq, Gq, gs = O.fg_quad_f32(x1, Md, data.astype(np.float32))
+        assert nl == pytest.approx(nlq, rel=RTOL_F32)
+        assert_grad_close(G, Gq, gs, rtol=RTOL_F32)
+        assert np.allclose(comp, Md.astype(np.float64) @ x1, rtol=1e-12, atol=0)
     # (5) shards of the SAME synthetic matrix reproduce the whole (counter-based generator)
     h = nb // 2 + 7
     a = S.DeviceStack.synthetic(nb, nt, dtype, seed=94823, scale=1.0, x_true=x, rows=(0, h)).eval_fg(x1)

@@ -4,13 +4,18 @@ C-ABI, against the CPU oracle (itself pinned by complex-step differentiation: te
 
 Structure follows test/fitting/mzr_test.jl and amr_test.jl: fg! value + gradient (:78-80), stacked layout
 (:82-84), age-permutation invariance (:87-112), logdensity_and_gradient with / without Jacobian and with
-sigma or MH0 fixed (:115-176).  Tolerances as in test_gpu_core.py.
+sigma or MH0 fixed (:115-176).
+
+Tolerances (BASELINE.json north_star): 1e-12 relative on logL; every gradient component within 1e-10 of its BACKWARD-ERROR
+SCALE  sum_t |d r_t / d p| * sum_i |M_it r_i|  (conftest.hier_grad_scale), the chain-rule image of test_gpu_core's per-template
+scale -- the parameter components (alpha, beta, sigma) are near-total cancellations at the optimum, so |G_p| itself is no
+yardstick.  Measured on B200 (profiles/r2_hier_parity_errors.txt): max |dG| / scale between 1e-16 and 4e-14 over all cases.
 """
 import numpy as np
 import pytest
 
 import oracle as O
-from conftest import make_flat_problem, make_hier_problem
+from conftest import assert_hier_grad_close, hier_grad_scale, make_flat_problem, make_hier_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -65,11 +70,9 @@ def test_fg_hier_parity(S, kind, shuffle, ragged):                # mzr_test.jl:
     G = np.empty(v.shape[0])
     nl = S.fg_(True, G, model, disp, v, ds, data, None, p["logAge"], p["MH"])
     assert nl == pytest.approx(nlq, rel=1e-12)
-    # the chain rule amplifies the per-template cancellation: judge against the oracle's own distance to quad
-    scale = np.abs(Gq) + 1e-10 * np.abs(Gq).max()
-    err_gpu = np.max(np.abs(G - Gq) / scale)
-    err_cpu = np.max(np.abs(Go - Gq) / scale)
-    assert err_gpu < max(1e-10, 20 * err_cpu), (err_gpu, err_cpu)
+    scale = hier_grad_scale(kind, fixed, v, p["M"], data, p["logAge"], p["MH"])
+    assert_hier_grad_close(G, Gq, scale, what="device vs __float128 arbiter")
+    assert_hier_grad_close(Go, Gq, scale, what="double oracle vs __float128 arbiter")      # the restatement obeys the same bar
     # F only (G === nothing)  mzr_test.jl:78
     assert S.fg_(True, None, model, disp, v, ds, data, None, p["logAge"], p["MH"]) == pytest.approx(nlq, rel=1e-12)
     # perturbed start (mzr_test.jl:180-182 uses 1.5x) -- away from the optimum plain relative error holds
@@ -77,7 +80,7 @@ def test_fg_hier_parity(S, kind, shuffle, ragged):                # mzr_test.jl:
     nlq2, Gq2, _ = O.fg_hier(kind, fixed, (1, 1, 1), v2, p["M"], data, p["logAge"], p["MH"], quad=True)
     G2 = np.empty(v.shape[0])
     assert S.fg_(True, G2, model, disp, v2, ds, data, None, p["logAge"], p["MH"]) == pytest.approx(nlq2, rel=1e-12)
-    assert np.max(np.abs(G2 - Gq2) / (np.abs(Gq2) + 1e-12 * np.abs(Gq2).max())) < 1e-9
+    assert_hier_grad_close(G2, Gq2, hier_grad_scale(kind, fixed, v2, p["M"], data, p["logAge"], p["MH"]), what="perturbed start")
 
 
 @pytest.mark.parametrize("kind", [O.POWERLAW_MZR, O.LINEAR_AMR])
@@ -93,7 +96,8 @@ def test_age_permutation_invariance(S, kind):                     # mzr_test.jl:
     G2 = np.empty(nj + 3)
     nl2 = S.fg_(True, G2, model, disp, v2, S.DeviceStack(p["M"][:, cols], data), data, None, p["logAge"][cols], p["MH"][cols])
     assert nl2 == pytest.approx(nl, rel=1e-12)
-    assert np.allclose(G2, np.concatenate([G[:nj][perm], G[nj:]]), rtol=1e-8, atol=1e-12 * np.abs(G).max())
+    scale = hier_grad_scale(kind, fixed, v, p["M"], data, p["logAge"], p["MH"])
+    assert_hier_grad_close(G2, np.concatenate([G[:nj][perm], G[nj:]]), np.concatenate([scale[:nj][perm], scale[nj:]]), what="age permutation")
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -113,7 +117,8 @@ def test_free_masks_and_logdensity(S, kind):                      # mzr_test.jl:
         for i in range(3):
             if not free[i]:
                 assert G[nj + i] == 0.0                           # mzr.jl:175,196,201
-        assert np.allclose(G, Go, rtol=1e-7, atol=1e-9 * np.abs(Go).max())
+        scale = hier_grad_scale(kind, fixed, v, p["M"], data, p["logAge"], p["MH"])
+        assert_hier_grad_close(G, Go, scale, what=f"free={free}")
         pars = np.array([a, b, s]); fm = np.array(free)
         tpar = np.array([np.log(pv) if t == 1 else pv for pv, t in zip(pars, tf)])
         xvec = np.concatenate([np.log(p["R"]), tpar[fm]])
@@ -124,7 +129,10 @@ def test_free_masks_and_logdensity(S, kind):                      # mzr_test.jl:
             lpo, gro = O.hier_logdensity_and_gradient(kind, fixed, [int(f) for f in free], (a, b, s), xvec, p["M"], data,
                                                       p["logAge"], p["MH"], jacobian_corrections=jac)
             assert lp == pytest.approx(lpo, rel=1e-12)
-            assert gr.shape == (nj + fm.sum(),) and np.allclose(gr, gro, rtol=1e-7, atol=1e-9 * np.abs(gro).max())
+            # transformed variables: d/d(log R_j) = R_j d/dR_j, d/d(log p) = p d/dp (generic_fitting.jl:150-165): the scale follows
+            tscale = np.concatenate([scale[:nj] * p["R"], (scale[nj:] * np.array([pv if t == 1 else 1.0 for pv, t in zip(pars, tf)]))[fm]])
+            assert gr.shape == (nj + fm.sum(),)
+            assert_hier_grad_close(gr, gro, tscale, what=f"HierarchicalOptimizer free={free} jacobian={jac}")
         # F-only and G-only protocol (generic_fitting.jl:172-178,195-197)
         assert S.HierarchicalOptimizer(model, disp, ds, data, p["logAge"], p["MH"], True, None, True).logdensity_and_gradient(xvec) == pytest.approx(lp, rel=1e-13)
 
@@ -153,7 +161,7 @@ def test_hier_full_config3_shape(S):
     nl = S.fg_(True, G, model, disp, v, ds, data, None, p["logAge"], p["MH"])
     nlq, Gq, _ = O.fg_hier(O.POWERLAW_MZR, (6.0,), (1, 1, 1), v, p["M"], data, p["logAge"], p["MH"], quad=True)
     assert nl == pytest.approx(nlq, rel=1e-12)
-    assert np.max(np.abs(G - Gq) / (np.abs(Gq) + 1e-12 * np.abs(Gq).max())) < 1e-9
+    assert_hier_grad_close(G, Gq, hier_grad_scale(O.POWERLAW_MZR, (6.0,), v, p["M"], data, p["logAge"], p["MH"]), what="config-3 grid")
 
 
 # ------------------------------------------------------------------ sampler adapters
@@ -164,7 +172,11 @@ def test_hmc_model(S):                                            # hmc_sample.j
     logx = np.log(x) + 0.01
     lp, g = hm.logdensity_and_gradient(logx)
     lpo, go = O.hmc_logdensity_and_gradient(logx, M, data)
-    assert lp == pytest.approx(lpo, rel=1e-12) and np.allclose(g, go, rtol=1e-8, atol=1e-8 * np.abs(go).max())
+    assert lp == pytest.approx(lpo, rel=1e-12)
+    # d/d(log x_j) = x_j d/dx_j (hmc_sample.jl:30-35): 1e-10 of the flat backward-error scale times x_j
+    xe = np.exp(logx)
+    gscale = xe * (np.abs(M).T @ np.abs(1.0 - data / np.maximum(M @ xe, np.finfo(np.float64).eps)))
+    assert np.all(np.abs(g - go) <= 1e-10 * gscale), float(np.max(np.abs(g - go) / gscale))
     assert hm.logdensity(logx) == pytest.approx(lpo, rel=1e-12)
 
 
@@ -263,4 +275,6 @@ def test_fg_batched_matches_single_vector_path(S, nb, nt, C, dtype):
     hm = S.HMCModel(ds, None, data)
     LP, GR = hm.logdensity_and_gradient_batched(np.log(X))
     lp0, g0 = hm.logdensity_and_gradient(np.log(X[:, 0]))
-    assert LP[0] == pytest.approx(lp0, rel=1e-12) and np.allclose(GR[:, 0], g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
+    Mf, df = M.astype(np.float64), data.astype(np.float64)
+    gscale0 = X[:, 0] * (np.abs(Mf).T @ np.abs(1.0 - df / np.maximum(Mf @ X[:, 0], np.finfo(np.float64).eps)))
+    assert LP[0] == pytest.approx(lp0, rel=1e-12) and np.all(np.abs(GR[:, 0] - g0) <= 1e-10 * gscale0)

@@ -128,3 +128,57 @@ def test_two_ranks_load_their_shards_from_one_file(tmp_path):
     for rank, nl, G, (b, e), csum in res:
         assert nl == pytest.approx(float(nl_ref), rel=1e-13) and np.allclose(G, G_ref, rtol=1e-11, atol=1e-9)
         assert csum == S.io.checksum64(np.asfortranarray(M[b:e]))   # the shard each rank read is the shard of the original
+
+
+def _p2p_worker(rank, world, port, fail_rank, q):
+    """init_p2p's agreement protocol on `gloo`: the library calls are replaced by a hook that fails on `fail_rank`."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sfh_b200 as S
+        seen = []
+
+        def open_handles(r, blob):
+            seen.append((r, len(blob)))
+            if r == fail_rank:
+                raise ValueError("peer inbox cannot be opened on this rank")
+
+        ok = S.sharding.init_p2p(None, open_handles=open_handles)
+        q.put((rank, ok, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 0, 1])
+def test_p2p_switch_is_all_or_nothing(fail_rank):
+    """if opening the peer inboxes fails on SOME ranks only, those that succeeded must not switch to the one-shot
+    exchange (they would spin on flags that never come).  Every rank reports, the group takes the MIN: all switch or none."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    want = fail_rank < 0
+    assert [r[1] for r in res] == [want, want]
+    assert all(r[2] == [(r[0], 64 * world)] for r in res)        # every rank saw the whole table of handles
+
+
+def test_shard_rows_c_abi_matches_host_partition():
+    """sfh_shard_rows (what sfh_group_create uses) == sharding.shard_rows; shards tile [0, nbins) on `align` boundaries."""
+    import ctypes as C
+    import sfh_b200 as S
+    b, e = C.c_int64(), C.c_int64()
+    for nb in (0, 1, 127, 128, 129, 1000, 60000, 10**6, 10**6 + 7):
+        for n in (1, 2, 3, 4, 8):
+            for align in (32, 128):
+                prev = 0
+                for i in range(n):
+                    S._lib.check(S._lib.lib.sfh_shard_rows(nb, n, i, align, C.byref(b), C.byref(e)))
+                    assert (b.value, e.value) == S.shard_rows(nb, n, i, align=align)
+                    assert b.value == prev and e.value >= b.value and (e.value % align == 0 or e.value == nb)
+                    prev = e.value
+                assert prev == nb
+    assert S._lib.lib.sfh_shard_rows(10, 2, 2, 32, C.byref(b), C.byref(e)) != 0
