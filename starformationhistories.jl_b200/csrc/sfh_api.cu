@@ -180,6 +180,7 @@ struct sfh_ctx {
     double *d_coeffs = nullptr, *d_out = nullptr, *d_composite = nullptr, *d_residual = nullptr;
     double *d_gpart = nullptr, *d_lpart = nullptr;
     unsigned int *d_ticket = nullptr;
+    long long *d_dbg = nullptr;   // SFH_DEBUG_FINALIZE=1: milestones of the finalize kernel's last block
     int64_t gstride = 0;
     double *h_in = nullptr, *h_out = nullptr;  // pinned
     size_t h_in_n = 0, h_out_n = 0;
@@ -187,8 +188,7 @@ struct sfh_ctx {
     bool bound = false;
     int32_t nj = 0;
     double *d_logAge_u = nullptr, *d_MH = nullptr, *d_vars = nullptr, *d_hscratch = nullptr, *d_Ajk = nullptr,
-           *d_outh = nullptr, *d_W = nullptr, *d_P = nullptr, *d_MHg = nullptr;
-    int32_t *d_ginv = nullptr;
+           *d_outh = nullptr, *d_W = nullptr, *d_hsums = nullptr, *d_MHg = nullptr;
     int32_t *d_jidx = nullptr, *d_gptr = nullptr, *d_gmem = nullptr, *d_sidx = nullptr;
     // batched walkers
     int64_t wcap = 0, wld = 0;
@@ -797,6 +797,9 @@ static int sfh_ctx_create_impl(sfh_stack *s, void *stream, sfh_ctx **out) {
     CTX_TRY(cudaMalloc((void **)&c->d_lpart, 1024 * 8));
     CTX_TRY(cudaMalloc((void **)&c->d_ticket, 64));
     CTX_TRY(cudaMemset(c->d_ticket, 0, 64));
+    if (const char *e = getenv("SFH_DEBUG_FINALIZE")) {
+        if (atoi(e)) { CTX_TRY(cudaMalloc((void **)&c->d_dbg, 16 * 8)); CTX_TRY(cudaMemset(c->d_dbg, 0, 16 * 8)); }
+    }
     CTX_TRY(cudaMemset(c->d_composite, 0, ld * 8));
     CTX_TRY(cudaMemset(c->d_out, 0, (1 + nt) * 8));
     c->h_in_n = (size_t)std::max<int64_t>(nt, ld) + 16;
@@ -826,9 +829,9 @@ static int sfh_ctx_destroy_impl(sfh_ctx *c) {
     for (auto *g : {&c->g_fg[0], &c->g_fg[1], &c->g_hier})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     cudaFree(c->d_coeffs); cudaFree(c->d_out); cudaFree(c->d_composite); cudaFree(c->d_residual);
-    cudaFree(c->d_gpart); cudaFree(c->d_lpart); cudaFree(c->d_ticket);
+    cudaFree(c->d_gpart); cudaFree(c->d_lpart); cudaFree(c->d_ticket); cudaFree(c->d_dbg);
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
-    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W); cudaFree(c->d_P); cudaFree(c->d_MHg); cudaFree(c->d_ginv);
+    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W); cudaFree(c->d_hsums); cudaFree(c->d_MHg);
     cudaFree(c->d_X); cudaFree(c->d_Xt); cudaFree(c->d_part); cudaFree(c->d_logl); cudaFree(c->d_neg);
     cudaFree(c->d_resid); cudaFree(c->d_bgpart); cudaFree(c->d_bG); cudaFree(c->d_logtab); cudaFree(c->d_hb);
     cudaFree(c->d_flush);
@@ -876,6 +879,7 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
     fp.out_host = out_host; fp.lpart = c->d_lpart; fp.ticket = c->d_ticket;
     if (logl_from_fused) { fp.lpart_in = c->d_lpart; fp.n_lpart_in = s->n_clusters; }
     if (tail) fp.hier = *tail;
+    fp.dbg = c->d_dbg; fp.hier.dbg = c->d_dbg;
     if (p2p_push) {
         fp.peers = c->d_peers; fp.nranks = c->nranks; fp.rank = c->rank; fp.vlen = c->p2p_vlen;
         fp.epoch_ptr = c->d_epoch;
@@ -886,7 +890,10 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
     const int64_t need = std::max<int64_t>(logl_from_fused ? 1 : nblk_l, want_G_reduce ? (s->nt + 7) / 8 : 0);
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(need, 1), cap);
     fp.nblk_logl = (int32_t)nblk_l;
-    CU_TRY(launch_pdl(sfh_finalize_kernel, dim3(grid), dim3(kFinalizeThreads), 0, c->stream, fp));
+    if (tail && tail->on)   // hierarchical: one block per age group (needs the Poisson partials of the stream kernel: checked by the caller)
+        CU_TRY(launch_pdl(sfh_finalize_hier_kernel, dim3((unsigned)std::max(tail->nj, 1)), dim3(kFinalizeThreads), 0, c->stream, fp));
+    else
+        CU_TRY(launch_pdl(sfh_finalize_kernel, dim3(grid), dim3(kFinalizeThreads), 0, c->stream, fp));
     c->stats.kernel_launches++;
     return SFH_OK;
 }
@@ -1204,9 +1211,8 @@ static int hier_bind_local(sfh_ctx *c, const double *logAge, const double *MH, i
     std::stable_sort(sidx.begin(), sidx.end(), [&](int32_t a, int32_t b) { return uniq[(size_t)a] > uniq[(size_t)b]; });
 
     cudaFree(c->d_logAge_u); cudaFree(c->d_MH); cudaFree(c->d_vars); cudaFree(c->d_hscratch); cudaFree(c->d_Ajk);
-    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W); cudaFree(c->d_P); cudaFree(c->d_MHg); cudaFree(c->d_ginv);
-    c->d_logAge_u = c->d_MH = c->d_vars = c->d_hscratch = c->d_Ajk = c->d_outh = c->d_W = c->d_P = c->d_MHg = nullptr;
-    c->d_ginv = nullptr;
+    cudaFree(c->d_outh); cudaFree(c->d_jidx); cudaFree(c->d_gptr); cudaFree(c->d_gmem); cudaFree(c->d_sidx); cudaFree(c->d_W); cudaFree(c->d_hsums); cudaFree(c->d_MHg);
+    c->d_logAge_u = c->d_MH = c->d_vars = c->d_hscratch = c->d_Ajk = c->d_outh = c->d_W = c->d_hsums = c->d_MHg = nullptr;
     for (auto *g : {&c->g_hier}) if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; g->failed = false; }   // bakes the old tables in
     c->d_jidx = c->d_gptr = c->d_gmem = c->d_sidx = nullptr;
     c->bound = false;
@@ -1218,9 +1224,8 @@ static int hier_bind_local(sfh_ctx *c, const double *logAge, const double *MH, i
     CU_TRY(cudaMalloc((void **)&c->d_Ajk, ntp * 8));
     CU_TRY(cudaMalloc((void **)&c->d_outh, (njp + 4) * 8));
     CU_TRY(cudaMalloc((void **)&c->d_W, 4 * ntp * 8));
-    CU_TRY(cudaMalloc((void **)&c->d_P, 4 * ntp * 8));
+    CU_TRY(cudaMalloc((void **)&c->d_hsums, 4 * njp * 8));
     CU_TRY(cudaMalloc((void **)&c->d_MHg, ntp * 8));
-    CU_TRY(cudaMalloc((void **)&c->d_ginv, ntp * 4));
     CU_TRY(cudaMalloc((void **)&c->d_jidx, ntp * 4));
     CU_TRY(cudaMalloc((void **)&c->d_gptr, (njp + 1) * 4));
     CU_TRY(cudaMalloc((void **)&c->d_gmem, ntp * 4));
@@ -1232,11 +1237,9 @@ static int hier_bind_local(sfh_ctx *c, const double *logAge, const double *MH, i
         CU_TRY(cudaMemcpy(c->d_gptr, gptr.data(), ((size_t)nj + 1) * 4, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(c->d_gmem, gmem.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(c->d_sidx, sidx.data(), (size_t)nj * 4, cudaMemcpyHostToDevice));
-        // age-grouped views for the folded path: where each template sits in the group list, and the metallicities in that order
-        std::vector<int32_t> ginv((size_t)nt);
+        // the metallicities in age-group order (the folded path's prologue reads them without the gmem indirection)
         std::vector<double> mhg((size_t)nt);
-        for (int64_t g = 0; g < nt; ++g) { ginv[(size_t)gmem[(size_t)g]] = (int32_t)g; mhg[(size_t)g] = MH[gmem[(size_t)g]]; }
-        CU_TRY(cudaMemcpy(c->d_ginv, ginv.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
+        for (int64_t g = 0; g < nt; ++g) mhg[(size_t)g] = MH[gmem[(size_t)g]];
         CU_TRY(cudaMemcpy(c->d_MHg, mhg.data(), (size_t)nt * 8, cudaMemcpyHostToDevice));
     }
     if ((size_t)nj + 8 > c->h_in_n || (size_t)nj + 8 > c->h_out_n) return fail(SFH_ERR_SHAPE, "more ages than templates?");
@@ -1309,14 +1312,14 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
     // folded path: wide prologue reading the variables straight from the pinned buffer -> fused kernel -> finalize kernel whose last
     // block applies the chain rule (3 launches, no copy nodes).  Needs the gradient complete inside the finalize kernel: fused
     // path, and either one GPU or the one-shot exchange.
-    const bool folded = c->s->fused && c->s->rows > 0 && c->s->nt > 0 && c->nj <= kHierTailAges && (c->nranks == 1 || c->p2p);
+    const bool folded = c->s->fused && c->s->v2 && c->s->rows > 0 && c->s->nt > 0 && c->nj >= 1 && c->nj <= kHierTailAges && (c->nranks == 1 || c->p2p);
     mix(&folded, sizeof folded);
     SFH_TRY(run_graphed(c, c->g_hier, key, [&]() -> int {
         if (folded) {
             HierTail tl{};
             tl.on = 1; tl.kind = hp.kind; tl.nj = c->nj; tl.want_G = want_G;
             for (int i = 0; i < 4; ++i) tl.free_mask[i] = hp.free_mask[i];
-            tl.W = c->d_W; tl.ginv = c->d_ginv; tl.P = c->d_P; tl.gA = hp.gA; tl.gB = hp.gB; tl.gptr = hp.gptr; tl.sidx = hp.sidx; tl.nt = c->s->nt;
+            tl.W = c->d_W; tl.sums = c->d_hsums; tl.gA = hp.gA; tl.gB = hp.gB; tl.gptr = hp.gptr; tl.gmem = hp.gmem; tl.sidx = hp.sidx; tl.nt = c->s->nt;
             tl.out = c->d_outh; tl.out_host = c->h_out;
             const unsigned nblk = (unsigned)((c->nj + kHierPro2Threads / 32 - 1) / (kHierPro2Threads / 32));
             CU_TRY(launch_pdl(sfh_hier_prologue2_kernel, dim3(std::max(nblk, 1u)), dim3(kHierPro2Threads), 0, c->stream, hp,
@@ -1337,6 +1340,12 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
         return SFH_OK;
     }));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d_dbg) {
+        static int shown = 0;
+        long long t[16];
+        if (shown < 40 && ++shown > 30 && cudaMemcpy(t, c->d_dbg, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "hierarchical finalize, last block (cycles): ticket->logL %lld, parameter sums %lld, scan %lld\n", t[2] - t[1], t[3] - t[2], t[4] - t[3]);
+    }
     if (neg_logL) *neg_logL = c->h_out[0];
     if (G) memcpy(G, c->h_out + 1, nv * 8);
     return SFH_OK;

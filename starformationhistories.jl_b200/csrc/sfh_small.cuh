@@ -58,24 +58,26 @@ __device__ __forceinline__ double poisson_term(double m, double n, double eps) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Chain rule of the hierarchical fg! (mzr.jl:124-210 / amr.jl:118-169) as the TAIL of the finalize kernel: everything in it that
-// does not depend on the gradient (the per-template factors W1..W4 below) is prepared by sfh_hier_prologue2_kernel while the
-// variables are being turned into coefficients, so what remains after the fused kernel is four dot products per age group and
-// two 60-element scans -- done by the finalize kernel's last block instead of a fourth, single-block launch (round 1: 22 us).
+// Chain rule of the hierarchical fg! (mzr.jl:124-210 / amr.jl:118-169) inside the finalize step: everything in it that does not
+// depend on the gradient (the per-template factors W1..W4) is prepared by sfh_hier_prologue2_kernel while the variables are
+// being turned into coefficients; sfh_finalize_hier_kernel (one block per age group) reduces the gradient of the group's
+// templates, multiplies by the factors and leaves four sums per age; its last block finishes with 60-element sums and scans.
+// Round 1 ran a fourth, single-block epilogue launch for this (22 us).
 // ------------------------------------------------------------------------------------------
-constexpr int kHierTailAges = 256;   // ages the folded tail stages in shared memory (more: the separate epilogue kernel)
+constexpr int kHierTailAges = 256;   // ages the folded path stages in shared memory (more: the separate epilogue kernel)
 struct HierTail {
     int32_t on;          // 0 = plain fg!
     int32_t kind, nj, want_G;
     uint8_t free_mask[4];
-    const double *W;     // [4][nt], template order: the factors of  sum_k fullG_jk * (...)  for  R_j (cross-age), R_j (same age), mu_j, sigma
-    const int32_t *ginv; // [nt] position of template t in the age-grouped list (gmem[ginv[t]] == t)
-    double *P;           // [4][nt] scratch, GROUP order: P[f][g] = fullG_t * W[f][t], written by the warp that reduces G_t
+    const double *W;     // [4][nt], AGE-GROUP order (W[f][g], g as in gmem): the factors of  sum_k fullG_jk * (...)  for
+                         // R_j (cross-age), R_j (same age), mu_j, sigma
+    double *sums;        // [4][nj] scratch: the four per-age sums, one block each
     const double *gA, *gB;   // [nj] d mu_j / d alpha, d mu_j / d beta
-    const int32_t *gptr, *sidx;
+    const int32_t *gptr, *gmem, *sidx;
     int64_t nt;
     double *out;         // device [1 + nj + 3]: -logL (guarded), G
     double *out_host;    // nullable mapped pinned copy
+    long long *dbg;      // nullable: see FinalizeParams::dbg
 };
 
 // ------------------------------------------------------------------------------------------
@@ -103,6 +105,7 @@ struct FinalizeParams {
     unsigned long long *epoch_ptr;  // device: evaluations exchanged so far on this context (read and bumped by the last
                                     // block only, so a captured CUDA graph of the evaluation can be replayed)
     HierTail hier;                  // hierarchical chain rule on the (all-reduced) gradient, by the last block
+    long long *dbg;                 // nullable (SFH_DEBUG_FINALIZE=1): clock64() of the last block's thread 0 at its milestones
 };
 
 // One value of the exchange = one 16-byte packet {lo32, epoch32, hi32, epoch32}: each 8-byte half carries its own flag, so the
@@ -125,81 +128,6 @@ constexpr int kFinalizeThreads = 256;
 
 enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
 
-// The last block of the finalize kernel.  out_fg[0] = raw logL (all-reduced when sharded); P holds, in age-group order, the
-// products fullG_t * W_f[t] that the gradient-reducing warps formed as soon as each G_t existed, so what is left here is one
-// contiguous sum per (age, factor), three 60-term dot products and two scans -- every load an L2 hit or shared memory.  (The
-// stack stream evicts everything older from L2 in spite of its evict-first hint: in the first version each dependent global
-// load here was a DRAM round trip and the tail cost 11 us; profiles/r2_experiments.md section 4.)
-__device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_fg, double *sh /*[8]*/) {
-    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges], s_gA[kHierTailAges], s_gB[kHierTailAges];
-    __shared__ int s_sidx[kHierTailAges], s_gptr[kHierTailAges + 1];
-    __shared__ double s_par[3];
-    const int tid = threadIdx.x;
-    const int nj = h.nj;
-    // everything that does not depend on the gradient is requested first (one DRAM latency, overlapped with the sums below)
-    for (int j = tid; j < nj; j += kFinalizeThreads) { s_sidx[j] = h.sidx[j]; s_gA[j] = h.gA[j]; s_gB[j] = h.gB[j]; }
-    for (int j = tid; j <= nj; j += kFinalizeThreads) s_gptr[j] = h.gptr[j];
-    if (tid == 0) {
-        const double logL = __ldcg(out_fg);
-        const double v = (logL != 0.0) ? -logL : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95, solvers.jl:31
-        h.out[0] = v;
-        if (h.out_host) h.out_host[0] = v;
-    }
-    if (!h.want_G) return;
-    __syncthreads();
-    // one THREAD per (age, factor): the group's products are contiguous in P, members in the reference's order
-    for (int idx = tid; idx < 4 * nj; idx += kFinalizeThreads) {
-        const int j = idx >> 2, f = idx & 3;
-        const int g0 = s_gptr[j], g1 = s_gptr[j + 1];
-        const double *Pf = h.P + (int64_t)f * h.nt;
-        double a = 0.0;
-        if (f != 0 || h.kind == MH_POWERLAW_MZR) {
-#pragma unroll 8
-            for (int g = g0; g < g1; ++g) a += __ldcg(Pf + g);
-        }
-        if (f == 0) s_dr[j] = a;         // mzr.jl:166-167
-        else if (f == 1) s_G[j] = -a;    // mzr.jl:188-190 / amr.jl:141
-        else if (f == 2) s_p[j] = -a;    // mzr.jl:194-195
-        else s_s[j] = a;                 // mzr.jl:206-207
-    }
-    __syncthreads();
-    {   // parameter gradients: fixed-order (strided + xor tree) block sums  (mzr.jl:196-198,201-208)
-        double ga = 0.0, gb = 0.0, gs = 0.0;
-        for (int j = tid; j < nj; j += kFinalizeThreads) {
-            ga += s_p[j] * s_gA[j];
-            gb += s_p[j] * s_gB[j];
-            gs -= s_s[j];
-        }
-        const double ta = block_sum<kFinalizeThreads>(ga, sh);
-        const double tb = block_sum<kFinalizeThreads>(gb, sh);
-        const double ts = block_sum<kFinalizeThreads>(gs, sh);
-        if (tid == 0) { s_par[0] = ta; s_par[1] = tb; s_par[2] = ts; }
-    }
-    if (h.kind == MH_POWERLAW_MZR) {
-        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181.  The serial part runs over a
-        // copy in sorted order (s_p is free again after the barrier inside block_sum): one add per age, loads hoisted
-        __syncthreads();
-        for (int i = tid; i < nj; i += kFinalizeThreads) s_p[i] = s_dr[s_sidx[i]];
-        __syncthreads();
-        if (tid == 0) {
-            double run = 0.0;
-#pragma unroll 8
-            for (int i = nj - 1; i >= 1; --i) {
-                run += s_p[i];
-                s_s[i - 1] = run;        // cum[i], to be subtracted from G[s[i-1]]
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i + 1 < nj; i += kFinalizeThreads) s_G[s_sidx[i]] -= s_s[i];
-    }
-    __syncthreads();
-    for (int j = tid; j < nj + 3; j += kFinalizeThreads) {
-        const double v = (j < nj) ? s_G[j] : (h.free_mask[j - nj] ? s_par[j - nj] : 0.0);   // fixed parameters receive 0 (mzr.jl:196,201)
-        h.out[1 + j] = v;
-        if (h.out_host) h.out_host[1 + j] = v;
-    }
-}
-
 // Everything here is latency, not bandwidth (~1 MB of partials): the shape is chosen so that no thread ever waits on more than
 // ~2 dependent L2 round trips.  Measured alternatives (ncu launch lists under profiles/): 296 blocks with a per-thread serial loop
 // over the cluster partials 13 us; one 8-CTA cluster with a DSMEM reduction 27 us (too few threads).
@@ -211,6 +139,18 @@ __device__ __forceinline__ void hier_tail(const HierTail &h, const double *out_f
 // (three earlier versions did, at 16-18 us per step on 2 GPUs; profiles/r2_experiments.md section 3).  The last block only
 // exchanges logL.  Block b handles the same entries on every rank and pushes before it polls, so the ranks' grids cannot
 // wait on each other in a cycle even if a grid were larger than what is co-resident.
+
+// last block, warp 0: raw logL of this shard -> all-reduced over the ranks (same packet protocol, slot 0 of the vector)
+__device__ __forceinline__ double exchange_logl(const FinalizeParams &p, double all, int lane, int64_t par, uint32_t ep32) {
+    if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen, all, ep32);
+    const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen;
+    const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen, ep32) : 0.0;
+    double t = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
+    return t;
+}
+
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
@@ -237,10 +177,6 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
         const int64_t nwarps = (int64_t)gridDim.x * (kFinalizeThreads / 32);
         const uint4 *inbox = p.peers ? reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen : nullptr;
         for (int64_t j = (int64_t)blockIdx.x * (kFinalizeThreads / 32) + warp; j < p.nt; j += nwarps) {
-            // hierarchical: this template's chain-rule factors and its slot in the age-grouped product table (independent of G)
-            double wf = 0.0;
-            int gpos = 0;
-            if (p.hier.on && p.hier.want_G && lane < 4) { wf = p.hier.W[(int64_t)lane * p.nt + j]; gpos = p.hier.ginv[j]; }
             double s = 0.0;
             for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
             s = warp_sum(s);   // xor tree: every lane holds the total
@@ -248,6 +184,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
                 if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen + 1 + j, s, ep32);
                 const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen + 1 + j, ep32) : 0.0;
                 double t = 0.0;
+#pragma unroll 1
                 for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
                 s = t;
             }
@@ -255,7 +192,6 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
                 p.out[1 + j] = s;
                 if (p.out_host) p.out_host[1 + j] = s;
             }
-            if (p.hier.on && p.hier.want_G && lane < 4) p.hier.P[(int64_t)lane * p.nt + gpos] = (-s) * wf;   // fullG_t = d logL / d r_t = -(M'r)_t
         }
     }
     // last block folds the per-block logL partials (parallel, fixed order)
@@ -270,23 +206,154 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     const int nlp = p.lpart_in ? p.n_lpart_in : p.nblk_logl;
     for (int b = threadIdx.x; b < nlp; b += kFinalizeThreads) s += __ldcg(lp + b);
     double all = block_sum<kFinalizeThreads>(s, sh);   // valid in warp 0
-    if (p.peers && warp == 0) {
-        if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen, all, ep32);
-        const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen;
-        const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen, ep32) : 0.0;
-        double t = 0.0;
-        for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
-        all = t;
-    }
+    if (p.peers && warp == 0) all = exchange_logl(p, all, lane, par, ep32);
     if (threadIdx.x == 0) {
         p.out[0] = all;
         if (p.out_host) p.out_host[0] = all;
         *p.ticket = 0u;  // re-arm for the next evaluation on this context
         if (p.peers) *p.epoch_ptr = epoch;
     }
-    if (p.hier.on) {
-        __syncthreads();   // thread 0's out[0]
-        hier_tail(p.hier, p.out, sh);
+}
+
+// The finalize step of the HIERARCHICAL evaluation: block j = age group j.  Its 8 warps each add a fixed eighth of the cluster
+// partials for the group's templates (lane = member, so the loads of a warp are one contiguous row of gpart per cluster), warp 0
+// combines them in fixed order, exchanges the entries when sharded (lane = member: pushes to and polls from every rank),
+// stores G_t, multiplies fullG_t = -G_t by the four chain-rule factors (W in age-group order: coalesced) and reduces over the
+// members: four numbers per age.  The last block adds logL, the three parameter sums (mzr.jl:196-208) and the cross-age suffix scan
+// (mzr.jl:172-181) over shared-memory copies and writes [-logL, G] (Nj + 3 numbers) to device memory and the pinned buffer.
+// (Versions with the chain rule as a tail of the flat kernel -- per-age warps, then a product table summed by one block -- spent
+// 5 us on 9600 uncoalesced 8-byte loads from one SM; profiles/r2_experiments.md section 4.)
+__global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(const FinalizeParams p) {
+    __shared__ double part[kFinalizeThreads / 32][32];
+    __shared__ double sh[kFinalizeThreads / 32];
+    __shared__ bool last;
+    griddep_wait();
+    const HierTail &h = p.hier;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kFinalizeThreads / 32;
+    const int j = blockIdx.x;
+    const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
+    const uint32_t ep32 = (uint32_t)epoch;
+    const int64_t par = (int64_t)(epoch & 1ull);
+    if (p.want_G) {
+        const int g0 = h.gptr[j], g1 = h.gptr[j + 1];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 1
+        for (int base = g0; base < g1; base += 32) {
+            const int g = base + lane;
+            const bool valid = g < g1;
+            const int t = valid ? h.gmem[g] : 0;
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+            if (warp == 0 && valid) { w0 = h.W[g]; w1 = h.W[h.nt + g]; w2 = h.W[2 * h.nt + g]; w3 = h.W[3 * h.nt + g]; }   // (independent of G)
+            double s = 0.0;
+            if (valid) {
+#pragma unroll 4
+                for (int cl = warp; cl < p.n_clusters; cl += nw) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + t);
+            }
+            part[warp][lane] = s;
+            __syncthreads();
+            if (warp == 0) {
+                double G = 0.0;
+#pragma unroll
+                for (int w = 0; w < nw; ++w) G += part[w][lane];
+                if (p.peers && valid) {
+                    const int64_t slot = (par * p.nranks + p.rank) * p.vlen + 1 + t;
+#pragma unroll 1
+                    for (int r = 0; r < p.nranks; ++r) st_packet(reinterpret_cast<uint4 *>(p.peers[r]) + slot, G, ep32);
+                    const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen + 1 + t;
+                    double tsum = 0.0;
+#pragma unroll 1
+                    for (int r = 0; r < p.nranks; ++r) tsum += ld_packet_wait(inbox + (int64_t)r * p.vlen, ep32);   // rank order
+                    G = tsum;
+                }
+                if (valid) {
+                    p.out[1 + t] = G;
+                    a0 += (-G) * w0; a1 += (-G) * w1; a2 += (-G) * w2; a3 += (-G) * w3;   // fullG_t = d logL / d r_t = -(M'r)_t
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+            if (lane == 0) { h.sums[j] = a0; h.sums[h.nj + j] = a1; h.sums[2 * h.nj + j] = a2; h.sums[3 * h.nj + j] = a3; }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (p.dbg && tid == 0) p.dbg[1] = clock64();
+
+    // ---------------- last block: logL, parameter sums, suffix scan ----------------
+    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges];
+    __shared__ int s_sidx[kHierTailAges];
+    __shared__ double s_par[3];
+    const int nj = h.nj;
+    double ga = 0.0, gb = 0.0;
+    if (p.want_G) {
+#pragma unroll 1
+        for (int i = tid; i < nj; i += kFinalizeThreads) {
+            s_sidx[i] = h.sidx[i];
+            s_dr[i] = __ldcg(h.sums + i);                  // mzr.jl:166-167
+            s_G[i] = -__ldcg(h.sums + nj + i);             // mzr.jl:188-190 / amr.jl:141
+            const double pj = -__ldcg(h.sums + 2 * nj + i);   // mzr.jl:194-195
+            s_p[i] = pj;
+            s_s[i] = __ldcg(h.sums + 3 * nj + i);          // mzr.jl:206-207
+            ga += pj * h.gA[i];
+            gb += pj * h.gB[i];
+        }
+    }
+    double acc = 0.0;
+    for (int b = tid; b < p.n_lpart_in; b += kFinalizeThreads) acc += __ldcg(p.lpart_in + b);
+    double all = block_sum<kFinalizeThreads>(acc, sh);   // valid in warp 0 (and a barrier: the shared copies above are complete)
+    if (p.peers && warp == 0) all = exchange_logl(p, all, lane, par, ep32);
+    if (tid == 0) {
+        p.out[0] = all;
+        const double v = (all != 0.0) ? -all : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95, solvers.jl:31
+        h.out[0] = v;
+        if (h.out_host) h.out_host[0] = v;
+        *p.ticket = 0u;
+        if (p.peers) *p.epoch_ptr = epoch;
+    }
+    if (p.dbg && tid == 0) p.dbg[2] = clock64();
+    if (!p.want_G) return;
+    {   // parameter gradients: fixed-order (strided + xor tree) block sums  (mzr.jl:196-198,201-208)
+        double gs = 0.0;
+#pragma unroll 1
+        for (int i = tid; i < nj; i += kFinalizeThreads) gs -= s_s[i];
+        const double ta = block_sum<kFinalizeThreads>(ga, sh);
+        const double tb = block_sum<kFinalizeThreads>(gb, sh);
+        const double ts = block_sum<kFinalizeThreads>(gs, sh);
+        if (tid == 0) { s_par[0] = ta; s_par[1] = tb; s_par[2] = ts; }
+    }
+    if (p.dbg && tid == 0) p.dbg[3] = clock64();
+    if (h.kind == MH_POWERLAW_MZR) {
+        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181.  The serial part runs over a
+        // copy in sorted order (s_p / s_s are free again after the barriers inside block_sum): one add per age
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < nj; i += kFinalizeThreads) s_p[i] = s_dr[s_sidx[i]];
+        __syncthreads();
+        if (tid == 0) {
+            double run = 0.0;
+#pragma unroll 4
+            for (int i = nj - 1; i >= 1; --i) {
+                run += s_p[i];
+                s_s[i - 1] = run;        // cum[i], to be subtracted from G[s[i-1]]
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i + 1 < nj; i += kFinalizeThreads) s_G[s_sidx[i]] -= s_s[i];
+    }
+    __syncthreads();
+    if (p.dbg && tid == 0) p.dbg[4] = clock64();
+#pragma unroll 1
+    for (int i = tid; i < nj + 3; i += kFinalizeThreads) {
+        const double v = (i < nj) ? s_G[i] : (h.free_mask[i - nj] ? s_par[i - nj] : 0.0);   // fixed parameters receive 0 (mzr.jl:196,201)
+        h.out[1 + i] = v;
+        if (h.out_host) h.out_host[1 + i] = v;
     }
 }
 
@@ -497,25 +564,29 @@ __global__ void __launch_bounds__(kHierThreads) sfh_hier_prologue_kernel(const H
 
 // calculate_coeffs (mzr.jl:50-79 / amr.jl:50-73) for ONE evaluation, spread over the grid: one warp per age group.  Besides the
 // coefficients it prepares everything of the chain rule (mzr.jl:131-209) that does not depend on the gradient -- the factors
-// W1..W4 that multiply fullG_jk in the four per-age sums -- so that the finalize kernel is left with products and sums.
-// `vars_in` may be the caller's mapped pinned buffer: 63 doubles over PCIe instead of a memcpy node in front.
-// Every global load is a DRAM round trip here (the stack stream has flushed L2), so the dependent chain is kept to
-// gptr -> {MHg, gmem}: MHg is the metallicity grid in age-group order (built at sfh_hier_bind), the members' A_jk stay in
-// registers between the three passes, and the serial cumulative mass runs over a sorted copy in shared memory.
+// W1..W4 that multiply fullG_jk in the four per-age sums, stored in AGE-GROUP order -- so that the finalize step is left with
+// products and sums.  `vars_in` may be the caller's mapped pinned buffer: 63 doubles over PCIe instead of a memcpy node in front.
+// Every global load is a DRAM round trip here (the stack stream has flushed L2) and every instruction a cold fetch (the kernel runs
+// once per evaluation), so: the dependent load chain is gptr -> {MHg, gmem} (MHg = the metallicity grid in group order, built at
+// sfh_hier_bind), the members' A_jk stay in shared memory between the passes, the cumulative mass runs over a sorted copy in
+// shared memory, and each of the three member loops exists ONCE in the code (the first version, with the passes unrolled over a
+// register window, was 3400 instructions and took 13 us; this one ~1000).
 constexpr int kHierPro2Threads = 256;
-constexpr int kHierPro2Regs = 4;   // members per lane kept in registers (groups of up to 128 templates; larger ones recompute)
+constexpr int kHierPro2Keep = 128;   // members per group whose A_jk are kept in shared memory (beyond: recomputed)
 __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(const HierParams p, const double *vars_in, double *W,
                                                                                const double *MHg) {
     __shared__ double sv[kHierTailAges + 3], sRs[kHierTailAges];
     __shared__ int spos[kHierTailAges];
+    __shared__ double sA[kHierPro2Threads / 32][kHierPro2Keep];
     griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierPro2Threads / 32;
     const int nj = p.nj;
     const int j = blockIdx.x * nw + warp;
-    // independent loads first: the group's extent, its members and metallicities, its age
+    // independent loads first: the group's extent and age
     int g0 = 0, g1 = 0;
     double age = 0.0;
     if (j < nj) { g0 = p.gptr[j]; g1 = p.gptr[j + 1]; age = p.logAge_u[j]; }
+#pragma unroll 1
     for (int i = tid; i < nj + 3; i += kHierPro2Threads) {
         const double v = vars_in[i];
         sv[i] = v;
@@ -523,14 +594,6 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
     }
     int srt = -1;
     if (p.kind == MH_POWERLAW_MZR && tid < nj) srt = p.sidx[tid];          // (nj <= kHierTailAges <= block size)
-    int mt[kHierPro2Regs];
-    double mh[kHierPro2Regs];
-#pragma unroll
-    for (int u = 0; u < kHierPro2Regs; ++u) {
-        const int g = g0 + lane + 32 * u;
-        mt[u] = (g < g1) ? p.gmem[g] : -1;
-        mh[u] = (g < g1) ? MHg[g] : 0.0;
-    }
     __syncthreads();
     if (srt >= 0) { sRs[tid] = sv[srt]; spos[srt] = tid; }                 // R in oldest-first order; where each age sits in it
     __syncthreads();
@@ -550,55 +613,55 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
     d_mh_eval(p.kind, alpha, beta, p.fixed, arg, mu, gA, gB, gM);
     if (lane == 0) { p.mu[j] = mu; p.gA[j] = gA; p.gB[j] = gB; p.gM[j] = gM; }
     const double Rj = sv[j];
-    const bool big = g1 - g0 > 32 * kHierPro2Regs;   // members beyond the register window are recomputed from global memory
-    double A[kHierPro2Regs], a = 0.0;
-#pragma unroll
-    for (int u = 0; u < kHierPro2Regs; ++u) {
-        const double z = (mh[u] - mu) / sigma;
-        A[u] = (mt[u] >= 0) ? exp(-(z * z) / 2.0) : 0.0;  // dispersion_models.jl:92
-        a += A[u];
+    double *myA = sA[warp];
+    // pass 1: A_jk and their sum
+    double a = 0.0;
+#pragma unroll 1
+    for (int g = g0 + lane; g < g1; g += 32) {
+        const double z = (MHg[g] - mu) / sigma;
+        const double Av = exp(-(z * z) / 2.0);  // dispersion_models.jl:92
+        if (g - g0 < kHierPro2Keep) myA[g - g0] = Av;
+        a += Av;
     }
-    if (big)
-        for (int g = g0 + lane + 32 * kHierPro2Regs; g < g1; g += 32) { const double z = (MHg[g] - mu) / sigma; a += exp(-(z * z) / 2.0); }
     const double Aj = warp_sum(a);
     if (lane == 0) p.Asum[j] = Aj;
+    // pass 2 (per-age sums of the dispersion derivatives) and pass 3 (coefficients and chain-rule factors) share one loop body
     double kAR = 0.0, kmu = 0.0, ksg = 0.0;
-    auto sums = [&](double Av, double d) {
-        const double dAmu = Av * d / s2;      // dispersion_models.jl:99
-        const double dAsg = Av * d * d / s3;  // dispersion_models.jl:98
-        kAR += dAmu * gM;                     // mzr.jl:162,164
-        kmu += dAmu;
-        ksg += dAsg;
-    };
-#pragma unroll
-    for (int u = 0; u < kHierPro2Regs; ++u)
-        if (mt[u] >= 0) sums(A[u], mh[u] - mu);
-    if (big)
-        for (int g = g0 + lane + 32 * kHierPro2Regs; g < g1; g += 32) { const double d = MHg[g] - mu, z = d / sigma; sums(exp(-(z * z) / 2.0), d); }
-    kAR = warp_sum(kAR); kmu = warp_sum(kmu); ksg = warp_sum(ksg);
     const double RA = Rj / Aj;
     const int64_t nt = p.nt;
-    auto emit = [&](int t, double Av, double d) {
-        const double dAmu = Av * d / s2, dAsg = Av * d * d / s3;
-        const double coeff = Av * Rj / Aj;    // mzr.jl:76
-        p.coeffs[t] = coeff;
-        p.Ajk[t] = Av;
-        if (p.kind == MH_POWERLAW_MZR) {
-            const double dAR = dAmu * gM;
-            W[t] = RA * (dAR - (Av * kAR / Aj));                            // mzr.jl:166-167
-            W[nt + t] = coeff / Rj + (dAR - (kAR * Av / Aj)) * Rj / Aj;     // mzr.jl:188-190
-        } else {
-            W[t] = 0.0;
-            W[nt + t] = coeff / Rj;                                         // amr.jl:141
+#pragma unroll 1
+    for (int pass = 2; pass <= 3; ++pass) {
+#pragma unroll 1
+        for (int g = g0 + lane; g < g1; g += 32) {
+            const double d = MHg[g] - mu;
+            double Av;
+            if (g - g0 < kHierPro2Keep) Av = myA[g - g0];
+            else { const double z = d / sigma; Av = exp(-(z * z) / 2.0); }
+            const double dAmu = Av * d / s2;      // dispersion_models.jl:99
+            const double dAsg = Av * d * d / s3;  // dispersion_models.jl:98
+            if (pass == 2) {
+                kAR += dAmu * gM;                 // mzr.jl:162,164
+                kmu += dAmu;
+                ksg += dAsg;
+            } else {
+                const int t = p.gmem[g];
+                const double coeff = Av * Rj / Aj;    // mzr.jl:76
+                p.coeffs[t] = coeff;
+                p.Ajk[t] = Av;
+                if (p.kind == MH_POWERLAW_MZR) {
+                    const double dAR = dAmu * gM;
+                    W[g] = RA * (dAR - (Av * kAR / Aj));                            // mzr.jl:166-167
+                    W[nt + g] = coeff / Rj + (dAR - (kAR * Av / Aj)) * Rj / Aj;     // mzr.jl:188-190
+                } else {
+                    W[g] = 0.0;
+                    W[nt + g] = coeff / Rj;                                         // amr.jl:141
+                }
+                W[2 * nt + g] = RA * (dAmu - Av / Aj * kmu);                        // mzr.jl:194-195
+                W[3 * nt + g] = RA * (dAsg - Av / Aj * ksg);                        // mzr.jl:206-207
+            }
         }
-        W[2 * nt + t] = RA * (dAmu - Av / Aj * kmu);                        // mzr.jl:194-195
-        W[3 * nt + t] = RA * (dAsg - Av / Aj * ksg);                        // mzr.jl:206-207
-    };
-#pragma unroll
-    for (int u = 0; u < kHierPro2Regs; ++u)
-        if (mt[u] >= 0) emit(mt[u], A[u], mh[u] - mu);
-    if (big)
-        for (int g = g0 + lane + 32 * kHierPro2Regs; g < g1; g += 32) { const double d = MHg[g] - mu, z = d / sigma; emit(p.gmem[g], exp(-(z * z) / 2.0), d); }
+        if (pass == 2) { kAR = warp_sum(kAR); kmu = warp_sum(kmu); ksg = warp_sum(ksg); }
+    }
 }
 
 // chain rule: mzr.jl:124-210 / amr.jl:118-169.  fullG = d logL/d r = -(fg_out[1+t]).
