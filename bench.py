@@ -4,15 +4,21 @@
 A "step" is ONE fused evaluation of fg! (composite -> Poisson logL -> gradient; src/fitting/solvers.jl:20-38)
 over the BASELINE.json headline stack: 200x300 bins x 2400 templates (60 ages x 40 [M/H]), Float64,
 Poisson-sampled synthetic Hess diagram.  Each rank holds one such stack (N>1: a bin-row shard of an N x larger
-Hess diagram, [logL, G] all-reduced with NCCL on the kernel's stream every step => weak scaling).
+Hess diagram, [logL, G] all-reduced inside the finalize kernel every step => weak scaling).
 
-  value       evaluations/s with everything resident in HBM, timed with CUDA events on the launching stream
+  value       evaluations/s with everything resident in HBM, timed with CUDA events on the launching stream; ranks aligned
+              on the device (two untimed all-reduced steps, then e0 in-stream), max over ranks
   e2e         same through the reference-facing C-ABI call sfh_eval_fg with HOST buffers (H2D coeffs, D2H [-logL, G])
+  fg_hier     the call fit_sfh / sample_sfh make: sfh_eval_fg_hier (PowerLawMZR + GaussianDispersion), wall clock per call
   roofline    algorithmic bytes of the fused kernel / its event-timed duration, vs MEASURED_PEAKS.json hbm_gbs
+  config5     BASELINE config 5 as STRONG scaling: one 10^6 x 10^4 Float32 stack (40 GB) split over the N GPUs
+  parity      N = 1: logL and all 2400 gradient components vs the oracle; N > 1: ranks bit-identical and the all-reduced
+              answer == the WHOLE stack evaluated on rank 0's GPU alone (config 3 x N and config 5).  The run fails otherwise.
   cpu_baseline  the faster of the oracle's two threaded two-pass ports of the reference algorithm (BLAS gemv route / OpenMP nest)
-                on this box's host cores
+                on this box's host cores (N = 1 only)
 
-  --impl reference : the reference arm = that same CPU port, all host threads, on the same config.
+  --impl reference : the reference arm = that same CPU port, all host threads (set here, not inherited from the launcher),
+                     on the same config.
 """
 import argparse
 import json

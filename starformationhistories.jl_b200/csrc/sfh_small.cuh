@@ -140,15 +140,25 @@ enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
 // exchanges logL.  Block b handles the same entries on every rank and pushes before it polls, so the ranks' grids cannot
 // wait on each other in a cycle even if a grid were larger than what is co-resident.
 
-// last block, warp 0: raw logL of this shard -> all-reduced over the ranks (same packet protocol, slot 0 of the vector)
-__device__ __forceinline__ double exchange_logl(const FinalizeParams &p, double all, int lane, int64_t par, uint32_t ep32) {
+// raw logL of this shard -> all-reduced over the ranks (same packet protocol, slot 0 of the vector).  With the stream kernel the
+// shard's logL exists when the finalize kernel STARTS (per-cluster Poisson partials), so block 0 pushes it at once and the last
+// block only polls: the logL round trip overlaps the gradient's instead of following it.
+__device__ __forceinline__ void push_logl(const FinalizeParams &p, double all, int lane, int64_t par, uint32_t ep32) {
     if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen, all, ep32);
+}
+__device__ __forceinline__ double poll_logl(const FinalizeParams &p, int lane, int64_t par, uint32_t ep32) {
     const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen;
     const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen, ep32) : 0.0;
     double t = 0.0;
 #pragma unroll 1
     for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
     return t;
+}
+// block 0, at kernel start: the fused kernel's per-cluster Poisson partials -> this shard's logL (fixed order); returns it in warp 0
+__device__ __forceinline__ double early_logl(const FinalizeParams &p, double *sh) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < p.n_lpart_in; b += kFinalizeThreads) acc += __ldcg(p.lpart_in + b);
+    return block_sum<kFinalizeThreads>(acc, sh);
 }
 
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
@@ -160,8 +170,17 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
     const uint32_t ep32 = (uint32_t)epoch;
     const int64_t par = (int64_t)(epoch & 1ull);
-    // logL: fixed contiguous slice of bins per block, fixed trees => deterministic
-    if (!p.lpart_in) {
+    if (p.lpart_in) {
+        // stream kernel: the shard's logL is a sum of per-cluster partials that already exist -- block 0 finishes it right away
+        if (blockIdx.x == 0) {
+            const double all = early_logl(p, sh);
+            if (warp == 0) {
+                if (p.peers) push_logl(p, all, lane, par, ep32);
+                else if (lane == 0) { p.out[0] = all; if (p.out_host) p.out_host[0] = all; }
+            }
+        }
+    } else {
+        // logL from the composite: fixed contiguous slice of bins per block, fixed trees => deterministic
         const int64_t per = (p.nb + p.nblk_logl - 1) / p.nblk_logl;
         const int64_t b0 = (int64_t)blockIdx.x * per;
         const int64_t b1 = ((int)blockIdx.x >= p.nblk_logl) ? b0 : ((b0 + per < p.nb) ? b0 + per : p.nb);
@@ -194,19 +213,22 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
             }
         }
     }
-    // last block folds the per-block logL partials (parallel, fixed order)
+    if (p.lpart_in && !p.peers) return;   // single GPU, stream kernel: nothing is left for a last block -- no fence, no ticket
+    // the last block: folds the per-block logL partials (parallel, fixed order) / finishes the logL exchange, bumps the epoch
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!last) return;
     __threadfence();
-    double s = 0.0;
-    const double *lp = p.lpart_in ? p.lpart_in : p.lpart;
-    const int nlp = p.lpart_in ? p.n_lpart_in : p.nblk_logl;
-    for (int b = threadIdx.x; b < nlp; b += kFinalizeThreads) s += __ldcg(lp + b);
-    double all = block_sum<kFinalizeThreads>(s, sh);   // valid in warp 0
-    if (p.peers && warp == 0) all = exchange_logl(p, all, lane, par, ep32);
+    double all = 0.0;
+    if (!p.lpart_in) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < p.nblk_logl; b += kFinalizeThreads) s += __ldcg(p.lpart + b);
+        all = block_sum<kFinalizeThreads>(s, sh);   // valid in warp 0
+        if (p.peers && warp == 0) push_logl(p, all, lane, par, ep32);
+    }
+    if (p.peers && warp == 0) all = poll_logl(p, lane, par, ep32);
     if (threadIdx.x == 0) {
         p.out[0] = all;
         if (p.out_host) p.out_host[0] = all;
@@ -224,7 +246,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
 // (Versions with the chain rule as a tail of the flat kernel -- per-age warps, then a product table summed by one block -- spent
 // 5 us on 9600 uncoalesced 8-byte loads from one SM; profiles/r2_experiments.md section 4.)
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(const FinalizeParams p) {
-    __shared__ double part[kFinalizeThreads / 32][32];
+    __shared__ double part[kFinalizeThreads / 32][32], part2[kFinalizeThreads / 32][32];
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
     griddep_wait();
@@ -234,41 +256,63 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
     const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
     const uint32_t ep32 = (uint32_t)epoch;
     const int64_t par = (int64_t)(epoch & 1ull);
+    if (blockIdx.x == 0) {   // the shard's logL exists already (per-cluster partials of the stream kernel): finish / push it now
+        const double all0 = early_logl(p, sh);
+        if (warp == 0) {
+            if (p.peers) push_logl(p, all0, lane, par, ep32);
+            else if (lane == 0) p.out[0] = all0;
+        }
+    }
     if (p.want_G) {
         const int g0 = h.gptr[j], g1 = h.gptr[j + 1];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        // two members per lane and pass (g, g + 32): a group of up to 64 templates costs ONE round of dependent loads
 #pragma unroll 1
-        for (int base = g0; base < g1; base += 32) {
-            const int g = base + lane;
-            const bool valid = g < g1;
-            const int t = valid ? h.gmem[g] : 0;
-            double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-            if (warp == 0 && valid) { w0 = h.W[g]; w1 = h.W[h.nt + g]; w2 = h.W[2 * h.nt + g]; w3 = h.W[3 * h.nt + g]; }   // (independent of G)
-            double s = 0.0;
-            if (valid) {
-#pragma unroll 4
-                for (int cl = warp; cl < p.n_clusters; cl += nw) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + t);
+        for (int base = g0; base < g1; base += 64) {
+            const int gA_ = base + lane, gB_ = base + 32 + lane;
+            const bool vA = gA_ < g1, vB = gB_ < g1;
+            const int tA = vA ? h.gmem[gA_] : 0, tB = vB ? h.gmem[gB_] : 0;
+            double wA[4] = {0.0, 0.0, 0.0, 0.0}, wB[4] = {0.0, 0.0, 0.0, 0.0};
+            if (warp == 0) {   // (independent of G: requested before the partials)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    if (vA) wA[f] = h.W[(int64_t)f * h.nt + gA_];
+                    if (vB) wB[f] = h.W[(int64_t)f * h.nt + gB_];
+                }
             }
-            part[warp][lane] = s;
+            double sA = 0.0, sB = 0.0;
+#pragma unroll 5
+            for (int cl = warp; cl < p.n_clusters; cl += nw) {
+                const double *row = p.gpart + (int64_t)cl * p.gstride;
+                if (vA) sA += __ldcg(row + tA);
+                if (vB) sB += __ldcg(row + tB);
+            }
+            part[warp][lane] = sA;
+            part2[warp][lane] = sB;
             __syncthreads();
             if (warp == 0) {
-                double G = 0.0;
+                double GA = 0.0, GB = 0.0;
 #pragma unroll
-                for (int w = 0; w < nw; ++w) G += part[w][lane];
-                if (p.peers && valid) {
-                    const int64_t slot = (par * p.nranks + p.rank) * p.vlen + 1 + t;
+                for (int w = 0; w < nw; ++w) { GA += part[w][lane]; GB += part2[w][lane]; }
+                if (p.peers) {
+                    const int64_t slot = (par * p.nranks + p.rank) * p.vlen + 1;
 #pragma unroll 1
-                    for (int r = 0; r < p.nranks; ++r) st_packet(reinterpret_cast<uint4 *>(p.peers[r]) + slot, G, ep32);
-                    const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen + 1 + t;
-                    double tsum = 0.0;
+                    for (int r = 0; r < p.nranks; ++r) {
+                        if (vA) st_packet(reinterpret_cast<uint4 *>(p.peers[r]) + slot + tA, GA, ep32);
+                        if (vB) st_packet(reinterpret_cast<uint4 *>(p.peers[r]) + slot + tB, GB, ep32);
+                    }
+                    const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen + 1;
+                    double tsA = 0.0, tsB = 0.0;
 #pragma unroll 1
-                    for (int r = 0; r < p.nranks; ++r) tsum += ld_packet_wait(inbox + (int64_t)r * p.vlen, ep32);   // rank order
-                    G = tsum;
+                    for (int r = 0; r < p.nranks; ++r) {   // rank order
+                        if (vA) tsA += ld_packet_wait(inbox + (int64_t)r * p.vlen + tA, ep32);
+                        if (vB) tsB += ld_packet_wait(inbox + (int64_t)r * p.vlen + tB, ep32);
+                    }
+                    GA = tsA; GB = tsB;
                 }
-                if (valid) {
-                    p.out[1 + t] = G;
-                    a0 += (-G) * w0; a1 += (-G) * w1; a2 += (-G) * w2; a3 += (-G) * w3;   // fullG_t = d logL / d r_t = -(M'r)_t
-                }
+                // fullG_t = d logL / d r_t = -(M'r)_t
+                if (vA) { p.out[1 + tA] = GA; a0 += (-GA) * wA[0]; a1 += (-GA) * wA[1]; a2 += (-GA) * wA[2]; a3 += (-GA) * wA[3]; }
+                if (vB) { p.out[1 + tB] = GB; a0 += (-GB) * wB[0]; a1 += (-GB) * wB[1]; a2 += (-GB) * wB[2]; a3 += (-GB) * wB[3]; }
             }
             __syncthreads();
         }
@@ -286,28 +330,25 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
     if (p.dbg && tid == 0) p.dbg[1] = clock64();
 
     // ---------------- last block: logL, parameter sums, suffix scan ----------------
-    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges];
+    __shared__ double s_dr[kHierTailAges], s_G[kHierTailAges], s_p[kHierTailAges], s_s[kHierTailAges], s_gA[kHierTailAges], s_gB[kHierTailAges];
     __shared__ int s_sidx[kHierTailAges];
     __shared__ double s_par[3];
-    const int nj = h.nj;
-    double ga = 0.0, gb = 0.0;
+    const int nj = h.nj;   // (<= kHierTailAges <= kFinalizeThreads)
     if (p.want_G) {
 #pragma unroll 1
         for (int i = tid; i < nj; i += kFinalizeThreads) {
             s_sidx[i] = h.sidx[i];
             s_dr[i] = __ldcg(h.sums + i);                  // mzr.jl:166-167
             s_G[i] = -__ldcg(h.sums + nj + i);             // mzr.jl:188-190 / amr.jl:141
-            const double pj = -__ldcg(h.sums + 2 * nj + i);   // mzr.jl:194-195
-            s_p[i] = pj;
+            s_p[i] = -__ldcg(h.sums + 2 * nj + i);         // mzr.jl:194-195
             s_s[i] = __ldcg(h.sums + 3 * nj + i);          // mzr.jl:206-207
-            ga += pj * h.gA[i];
-            gb += pj * h.gB[i];
+            s_gA[i] = h.gA[i];
+            s_gB[i] = h.gB[i];
         }
     }
-    double acc = 0.0;
-    for (int b = tid; b < p.n_lpart_in; b += kFinalizeThreads) acc += __ldcg(p.lpart_in + b);
-    double all = block_sum<kFinalizeThreads>(acc, sh);   // valid in warp 0 (and a barrier: the shared copies above are complete)
-    if (p.peers && warp == 0) all = exchange_logl(p, all, lane, par, ep32);
+    double all = 0.0;
+    if (warp == 0) all = p.peers ? poll_logl(p, lane, par, ep32) : __ldcg(p.out);   // block 0 produced / pushed it at kernel start
+    __syncthreads();   // the shared copies above are complete
     if (tid == 0) {
         p.out[0] = all;
         const double v = (all != 0.0) ? -all : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95, solvers.jl:31
@@ -318,34 +359,34 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
     }
     if (p.dbg && tid == 0) p.dbg[2] = clock64();
     if (!p.want_G) return;
-    {   // parameter gradients: fixed-order (strided + xor tree) block sums  (mzr.jl:196-198,201-208)
-        double gs = 0.0;
+    // parameter gradients (mzr.jl:196-198,201-208): warp 0, lane-strided partial sums + one xor tree each (fixed order)
+    if (warp == 0) {
+        double pa = 0.0, pb = 0.0, ps = 0.0;
 #pragma unroll 1
-        for (int i = tid; i < nj; i += kFinalizeThreads) gs -= s_s[i];
-        const double ta = block_sum<kFinalizeThreads>(ga, sh);
-        const double tb = block_sum<kFinalizeThreads>(gb, sh);
-        const double ts = block_sum<kFinalizeThreads>(gs, sh);
-        if (tid == 0) { s_par[0] = ta; s_par[1] = tb; s_par[2] = ts; }
+        for (int i = lane; i < nj; i += 32) { pa += s_p[i] * s_gA[i]; pb += s_p[i] * s_gB[i]; ps -= s_s[i]; }
+        pa = warp_sum(pa); pb = warp_sum(pb); ps = warp_sum(ps);
+        if (lane == 0) { s_par[0] = pa; s_par[1] = pb; s_par[2] = ps; }
     }
     if (p.dbg && tid == 0) p.dbg[3] = clock64();
     if (h.kind == MH_POWERLAW_MZR) {
-        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181.  The serial part runs over a
-        // copy in sorted order (s_p / s_s are free again after the barriers inside block_sum): one add per age
+        // cum = reverse(cumsum(reverse(ksum[s])))  mzr.jl:172 ;  G[s[i-1]] -= cum[i]  :179-181: an inclusive SUFFIX sum over the
+        // ages in sorted order, done as a log-step scan in shared memory (8 steps for 256 ages; the serial loop was 1.5 us of 60
+        // dependent adds).  Pairs are added in a different order than a running sum: deterministic, and 1e-16 relative.
+        __syncthreads();   // warp 0 is done with s_p / s_s
+        double v = 0.0;
+        if (tid < nj) v = s_dr[s_sidx[tid]];
+        __syncthreads();
+        if (tid < nj) s_p[tid] = v;
         __syncthreads();
 #pragma unroll 1
-        for (int i = tid; i < nj; i += kFinalizeThreads) s_p[i] = s_dr[s_sidx[i]];
-        __syncthreads();
-        if (tid == 0) {
-            double run = 0.0;
-#pragma unroll 4
-            for (int i = nj - 1; i >= 1; --i) {
-                run += s_p[i];
-                s_s[i - 1] = run;        // cum[i], to be subtracted from G[s[i-1]]
-            }
+        for (int d = 1; d < nj; d <<= 1) {
+            const double add = (tid + d < nj) ? s_p[tid + d] : 0.0;
+            __syncthreads();
+            if (tid < nj) s_p[tid] += add;
+            __syncthreads();
         }
-        __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i + 1 < nj; i += kFinalizeThreads) s_G[s_sidx[i]] -= s_s[i];
+        // s_p[i] = sum_{i' >= i} ksum[s[i']]:  G[s[i-1]] -= s_p[i]
+        if (tid >= 1 && tid < nj) s_G[s_sidx[tid - 1]] -= s_p[tid];
     }
     __syncthreads();
     if (p.dbg && tid == 0) p.dbg[4] = clock64();
@@ -586,6 +627,10 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
     int g0 = 0, g1 = 0;
     double age = 0.0;
     if (j < nj) { g0 = p.gptr[j]; g1 = p.gptr[j + 1]; age = p.logAge_u[j]; }
+    // ... and the first 64 members' metallicities and template indices: their DRAM latency overlaps the PCIe read below
+    const int gf = g0 + lane;
+    const double mhp0 = (gf < g1) ? MHg[gf] : 0.0, mhp1 = (gf + 32 < g1) ? MHg[gf + 32] : 0.0;
+    const int tp0 = (gf < g1) ? p.gmem[gf] : 0, tp1 = (gf + 32 < g1) ? p.gmem[gf + 32] : 0;
 #pragma unroll 1
     for (int i = tid; i < nj + 3; i += kHierPro2Threads) {
         const double v = vars_in[i];
@@ -618,7 +663,8 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
     double a = 0.0;
 #pragma unroll 1
     for (int g = g0 + lane; g < g1; g += 32) {
-        const double z = (MHg[g] - mu) / sigma;
+        const double mhv = (g == gf) ? mhp0 : (g == gf + 32 ? mhp1 : MHg[g]);
+        const double z = (mhv - mu) / sigma;
         const double Av = exp(-(z * z) / 2.0);  // dispersion_models.jl:92
         if (g - g0 < kHierPro2Keep) myA[g - g0] = Av;
         a += Av;
@@ -633,7 +679,7 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
     for (int pass = 2; pass <= 3; ++pass) {
 #pragma unroll 1
         for (int g = g0 + lane; g < g1; g += 32) {
-            const double d = MHg[g] - mu;
+            const double d = ((g == gf) ? mhp0 : (g == gf + 32 ? mhp1 : MHg[g])) - mu;
             double Av;
             if (g - g0 < kHierPro2Keep) Av = myA[g - g0];
             else { const double z = d / sigma; Av = exp(-(z * z) / 2.0); }
@@ -644,7 +690,7 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
                 kmu += dAmu;
                 ksg += dAsg;
             } else {
-                const int t = p.gmem[g];
+                const int t = (g == gf) ? tp0 : (g == gf + 32 ? tp1 : p.gmem[g]);
                 const double coeff = Av * Rj / Aj;    // mzr.jl:76
                 p.coeffs[t] = coeff;
                 p.Ajk[t] = Av;

@@ -40,3 +40,16 @@ def test_reference_arm_json_line():
 def test_reference_arm_other_ranks_exit_quietly():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.timeout(900)
+def test_reference_arm_ignores_the_launchers_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; round 1's N > 1 reference arm therefore ran on ONE core and the
+    driver's vs_reference ratios at N = 2, 4, 8 were void.  The arm now sets its own thread counts from the affinity mask."""
+    ncores = len(os.sched_getaffinity(0))
+    if ncores < 2:
+        pytest.skip("one core: nothing to cap")
+    r = _run({"OMP_NUM_THREADS": "1", "OPENBLAS_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert d["cpu_baseline"]["cores"] == ncores, d["cpu_baseline"]
