@@ -184,6 +184,11 @@ struct sfh_ctx {
     int64_t gstride = 0;
     double *h_in = nullptr, *h_out = nullptr;  // pinned
     size_t h_in_n = 0, h_out_n = 0;
+    // completion by self-validating packets (FinalizeParams::pkt_host): h_out_n 16-byte packets, pinned; the epoch of the
+    // evaluation in flight is stored behind the inputs in h_in and relayed to d_hostep by the first kernel of the evaluation
+    void *h_pkt = nullptr;
+    unsigned long long *d_hostep = nullptr;
+    uint32_t pkt_epoch = 0;
     // hierarchical binding
     bool bound = false;
     int32_t nj = 0;
@@ -806,6 +811,10 @@ static int sfh_ctx_create_impl(sfh_stack *s, void *stream, sfh_ctx **out) {
     c->h_out_n = (size_t)std::max<int64_t>(nt + 1, ld) + 16;
     CTX_TRY(cudaMallocHost((void **)&c->h_in, c->h_in_n * 8));
     CTX_TRY(cudaMallocHost((void **)&c->h_out, c->h_out_n * 8));
+    CTX_TRY(cudaMallocHost((void **)&c->h_pkt, c->h_out_n * 16));
+    memset(c->h_pkt, 0, c->h_out_n * 16);
+    CTX_TRY(cudaMalloc((void **)&c->d_hostep, 8));
+    CTX_TRY(cudaMemset(c->d_hostep, 0, 8));
     CTX_TRY(cudaEventCreate(&c->ev0));
     CTX_TRY(cudaEventCreate(&c->ev1));
     CTX_TRY(cudaEventCreate(&c->evk0));
@@ -837,6 +846,8 @@ static int sfh_ctx_destroy_impl(sfh_ctx *c) {
     cudaFree(c->d_flush);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_pkt) cudaFreeHost(c->h_pkt);
+    cudaFree(c->d_hostep);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evk0) cudaEventDestroy(c->evk0);
@@ -870,8 +881,17 @@ extern "C" int sfh_ctx_synchronize(sfh_ctx *c) {
 // evaluation plumbing (device side)
 // ---------------------------------------------------------------------------------------------
 namespace {
+// Experiment switches of the round-2 latency work, read on every call so that one process can A/B them (profiles/bench_modes.py):
+//   SFH_PDL_EARLY   bit mask of the kernels that release their dependent launch at kernel START instead of at exit:
+//                   1 fused kernel (finalize resident early), 2 finalize kernels (the next evaluation's first kernel), 4 hierarchical
+//                   prologue (the fused kernel becomes resident and streams the stack while the coefficients are being formed)
+//   SFH_HOST_PACKETS=0  completion by cudaStreamSynchronize + copy node instead of packets polled in pinned memory
+constexpr int kPdlFused = 1, kPdlFinalize = 2, kPdlPrologue = 4, kPdlDefault = kPdlFinalize | kPdlPrologue;
+int pdl_early_mask() { const char *e = getenv("SFH_PDL_EARLY"); return (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : kPdlDefault; }
+bool host_packets_on() { const char *e = getenv("SFH_HOST_PACKETS"); return !(e && e[0] == '0'); }
+
 int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce, double *out_host = nullptr,
-                    bool p2p_push = false, bool logl_from_fused = false, const HierTail *tail = nullptr) {
+                    bool p2p_push = false, bool logl_from_fused = false, const HierTail *tail = nullptr, void *pkt_host = nullptr) {
     const sfh_stack *s = c->s;
     FinalizeParams fp{};
     fp.nb = s->rows; fp.nt = s->nt; fp.gstride = c->gstride; fp.n_clusters = s->n_clusters; fp.want_G = want_G_reduce;
@@ -880,6 +900,7 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
     if (logl_from_fused) { fp.lpart_in = c->d_lpart; fp.n_lpart_in = s->n_clusters; }
     if (tail) fp.hier = *tail;
     fp.dbg = c->d_dbg; fp.hier.dbg = c->d_dbg;
+    fp.pkt_host = pkt_host; fp.pkt_epoch = c->d_hostep; fp.pdl_early = (pdl_early_mask() & kPdlFinalize) ? 1 : 0;
     if (p2p_push) {
         fp.peers = c->d_peers; fp.nranks = c->nranks; fp.rank = c->rank; fp.vlen = c->p2p_vlen;
         fp.epoch_ptr = c->d_epoch;
@@ -900,7 +921,7 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
 
 // d_out = [logL raw, G...]; leaves M*coeffs in c->d_composite and (want_G) the residual in c->d_residual
 int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_G, bool time_kernel,
-                    double *out_host = nullptr, const HierTail *tail = nullptr) {
+                    double *out_host = nullptr, const HierTail *tail = nullptr, void *pkt_host = nullptr) {
     sfh_stack *s = c->s;
     bool fused_p2p = false;
     if (s->rows == 0 || s->nt == 0) {
@@ -914,7 +935,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
             p.nb = s->rows; p.nt = s->nt; p.kt = s->kt; p.ns = s->ring; p.n_tiles = s->n_tiles;
             p.evict_first = s->evict_first ? 1 : 0; p.eps = s->eps; p.M = s->dM; p.coeffs = d_coeffs; p.data = s->d_data;
             p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
-            p.lpart = c->d_lpart; p.gstride = c->gstride;
+            p.lpart = c->d_lpart; p.gstride = c->gstride; p.pdl_early = (pdl_early_mask() & kPdlFused) ? 1 : 0;
             CU_TRY(v2_dispatch(s, 2, want_G != 0, &p, c->stream, nullptr));
         } else {
             FusedParams p{};
@@ -930,7 +951,9 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
         c->stats.kernel_launches++;
         fused_p2p = c->p2p;
         // single GPU, or the one-shot exchange (whose last block holds the all-reduced answer): results go straight to pinned memory
-        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, (c->nranks > 1 && !fused_p2p) ? nullptr : out_host, fused_p2p, s->v2, tail));
+        const bool results_here = !(c->nranks > 1 && !fused_p2p);   // (an NCCL all-reduce follows otherwise)
+        SFH_TRY(launch_finalize(c, c->d_composite, d_out, want_G, results_here ? out_host : nullptr, fused_p2p, s->v2, tail,
+                                results_here ? pkt_host : nullptr));
     } else {
         out_host = nullptr;  // the two-pass path writes G with gemv 'T': results are copied back explicitly
         // two-pass path: gemv 'N' -> logL -> residual -> gemv 'T'  (the reference's own pass structure)
@@ -998,6 +1021,44 @@ int run_graphed(sfh_ctx *c, sfh_ctx::GraphSlot &slot, uint64_t key, F &&enqueue)
     return SFH_OK;
 }
 
+// Completion of a host-synchronous evaluation WITHOUT cudaStreamSynchronize: the finalize kernel stored every result into the
+// pinned buffer as a 16-byte packet {lo32, epoch, hi32, epoch}; a result is there when both halves carry this evaluation's
+// epoch (each 8-byte half is a single PCIe write and a single host load).  Reads packet 0 into *first and packets 1..n into
+// rest[0..n).  The stream is queried now and then so that a faulted or result-less evaluation fails instead of hanging.
+inline uint32_t next_packet_epoch(sfh_ctx *c, size_t n_in) {
+    if (++c->pkt_epoch == 0) c->pkt_epoch = 1;
+    const unsigned long long e = c->pkt_epoch;
+    memcpy(c->h_in + n_in, &e, 8);
+    return c->pkt_epoch;
+}
+int wait_packets(sfh_ctx *c, uint32_t ep, double *first, double *rest, size_t n) {
+    const uint64_t *pk = static_cast<const uint64_t *>(c->h_pkt);
+    const size_t total = 1 + (rest ? n : 0);
+    uint64_t spins = 0;
+    bool drained = false;
+    for (size_t j = 0; j < total;) {
+        const uint64_t a = __atomic_load_n(pk + 2 * j, __ATOMIC_ACQUIRE), b = __atomic_load_n(pk + 2 * j + 1, __ATOMIC_ACQUIRE);
+        if ((uint32_t)(a >> 32) == ep && (uint32_t)(b >> 32) == ep) {
+            const uint64_t bits = (a & 0xffffffffull) | (b << 32);
+            double v;
+            memcpy(&v, &bits, 8);
+            if (j == 0) { if (first) *first = v; } else rest[j - 1] = v;
+            ++j;
+            continue;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 8191u) == 0) {
+            if (drained) return fail(SFH_ERR_CUDA, "the evaluation finished without delivering result %zu of %zu", j, total);
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) drained = true;   // everything has run: the packets must be there on the next pass
+            else if (q != cudaErrorNotReady) return fail(SFH_ERR_CUDA, "evaluation failed: %s", cudaGetErrorString(q));
+        }
+    }
+    return SFH_OK;
+}
+
 inline double guard_neg_logl(double logL) {  // fitting_base.jl:95 then the sign flip of solvers.jl:31
     return (logL != 0.0) ? -logL : std::numeric_limits<double>::infinity();
 }
@@ -1033,18 +1094,35 @@ static int eval_fg_local(sfh_ctx *c, const double *coeffs, double *neg_logL, dou
     memcpy(c->h_in, coeffs, (size_t)s->nt * 8);
     // single-GPU fused path: the finalize kernel stores [logL, G] straight into the mapped pinned buffer
     const bool direct = s->fused && (c->nranks == 1 || c->p2p) && s->rows > 0 && s->nt > 0;
-    SFH_TRY(run_graphed(c, c->g_fg[want_G], 1, [&]() -> int {
-        CU_TRY(cudaMemcpyAsync(c->d_coeffs, c->h_in, (size_t)s->nt * 8, cudaMemcpyHostToDevice, c->stream));
-        SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, direct ? c->h_out : nullptr));
+    // ... as self-validating packets the host polls (no copy node in front, no stream synchronisation behind): 2 kernels + 1 upload kernel
+    const bool pk = direct && host_packets_on();
+    const uint32_t ep = pk ? next_packet_epoch(c, (size_t)s->nt) : 0u;
+    SFH_TRY(run_graphed(c, c->g_fg[want_G], (pk ? 2 : 1) + 16 * (uint64_t)pdl_early_mask(), [&]() -> int {
+        if (pk) {
+            const unsigned nblk = (unsigned)((s->nt + 2 * kCopyInThreads - 1) / (2 * kCopyInThreads));
+            CU_TRY(launch_pdl(sfh_copy_in_kernel, dim3(nblk), dim3(kCopyInThreads), 0, c->stream, c->d_coeffs, (const double *)c->h_in,
+                              (int64_t)s->nt, c->d_hostep));
+            c->stats.kernel_launches++;
+        } else {
+            CU_TRY(cudaMemcpyAsync(c->d_coeffs, c->h_in, (size_t)s->nt * 8, cudaMemcpyHostToDevice, c->stream));
+        }
+        SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, (direct && !pk) ? c->h_out : nullptr, nullptr, pk ? c->h_pkt : nullptr));
         if (!direct) {
             const size_t n_out = want_G ? (size_t)(1 + s->nt) : 1;
             CU_TRY(cudaMemcpyAsync(c->h_out, c->d_out, n_out * 8, cudaMemcpyDeviceToHost, c->stream));
         }
         return SFH_OK;
     }));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    if (neg_logL) *neg_logL = guard_neg_logl(c->h_out[0]);
-    if (G) memcpy(G, c->h_out + 1, (size_t)s->nt * 8);
+    if (pk) {
+        double raw = 0.0;
+        SFH_TRY(wait_packets(c, ep, &raw, (want_G && G) ? G : nullptr, (size_t)s->nt));
+        if (neg_logL) *neg_logL = guard_neg_logl(raw);
+        if (composite_out) CU_TRY(cudaStreamSynchronize(c->stream));
+    } else {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (neg_logL) *neg_logL = guard_neg_logl(c->h_out[0]);
+        if (G) memcpy(G, c->h_out + 1, (size_t)s->nt * 8);
+    }
     if (composite_out && s->rows > 0) {
         // what the reference leaves in `composite`: the residual after grad-loglikelihood! (fitting_base.jl:219)
         CU_TRY(cudaMemcpy(composite_out, want_G ? c->d_residual : c->d_composite, (size_t)s->rows * 8,
@@ -1304,6 +1382,7 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
     const size_t nv = (size_t)c->nj + 3;
     memcpy(c->h_in, variables, nv * 8);
     hp.out_host = (c->nranks > 1 && !c->p2p) ? nullptr : c->h_out;  // epilogue stores [-logL, G] straight into the mapped pinned buffer
+    hp.pdl_early = (pdl_early_mask() & kPdlPrologue) ? 1 : 0;
     // graph key: everything baked into the captured kernel parameters
     uint64_t key = 0xcbf29ce484222325ull;
     auto mix = [&](const void *ptr, size_t n) { for (size_t i = 0; i < n; ++i) key = (key ^ ((const unsigned char *)ptr)[i]) * 0x100000001b3ull; };
@@ -1313,19 +1392,23 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
     // block applies the chain rule (3 launches, no copy nodes).  Needs the gradient complete inside the finalize kernel: fused
     // path, and either one GPU or the one-shot exchange.
     const bool folded = c->s->fused && c->s->v2 && c->s->rows > 0 && c->s->nt > 0 && c->nj >= 1 && c->nj <= kHierTailAges && (c->nranks == 1 || c->p2p);
-    mix(&folded, sizeof folded);
+    const bool pk = folded && host_packets_on();   // results as packets the host polls (wait_packets)
+    const int pdl_mask = pdl_early_mask();
+    mix(&folded, sizeof folded); mix(&pk, sizeof pk); mix(&pdl_mask, sizeof pdl_mask);
+    const uint32_t ep = pk ? next_packet_epoch(c, nv) : 0u;
+    if (pk) hp.pkt_epoch_out = c->d_hostep;
     SFH_TRY(run_graphed(c, c->g_hier, key, [&]() -> int {
         if (folded) {
             HierTail tl{};
             tl.on = 1; tl.kind = hp.kind; tl.nj = c->nj; tl.want_G = want_G;
             for (int i = 0; i < 4; ++i) tl.free_mask[i] = hp.free_mask[i];
             tl.W = c->d_W; tl.sums = c->d_hsums; tl.gA = hp.gA; tl.gB = hp.gB; tl.gptr = hp.gptr; tl.gmem = hp.gmem; tl.sidx = hp.sidx; tl.nt = c->s->nt;
-            tl.out = c->d_outh; tl.out_host = c->h_out;
+            tl.out = c->d_outh; tl.out_host = pk ? nullptr : c->h_out;
             const unsigned nblk = (unsigned)((c->nj + kHierPro2Threads / 32 - 1) / (kHierPro2Threads / 32));
             CU_TRY(launch_pdl(sfh_hier_prologue2_kernel, dim3(std::max(nblk, 1u)), dim3(kHierPro2Threads), 0, c->stream, hp,
                               (const double *)c->h_in, c->d_W, (const double *)c->d_MHg));
             c->stats.kernel_launches++;
-            SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, nullptr, &tl));
+            SFH_TRY(enqueue_fg_impl(c, c->d_coeffs, c->d_out, want_G, false, nullptr, &tl, pk ? c->h_pkt : nullptr));
             return SFH_OK;
         }
         CU_TRY(cudaMemcpyAsync(c->d_vars, c->h_in, nv * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1339,6 +1422,12 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
         }
         return SFH_OK;
     }));
+    if (pk) {
+        double v0 = 0.0;
+        SFH_TRY(wait_packets(c, ep, &v0, (want_G && G) ? G : nullptr, nv));
+        if (neg_logL) *neg_logL = v0;
+        return SFH_OK;
+    }
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (c->d_dbg) {
         static int shown = 0;

@@ -47,6 +47,7 @@ struct Fused2Params {
     int32_t ns;           // ring stage slots (<= (kV2DS-1) * stages per tile: bounds how far A can run ahead of B)
     int32_t n_tiles;      // ceil(nb / BT)
     int32_t evict_first;  // L2 evict_first policy on the stack stream
+    int32_t pdl_early;    // 1: release the dependent (finalize) launch at kernel start
     double eps;           // clamp (fitting_base.jl:90,277)
     const void *M;        // device stack, bin-major panels [n_tiles][nt][BT]
     const double *coeffs; // [nt]
@@ -163,8 +164,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
     // every CTA's barriers must be initialised before any peer signals them
     cluster_arrive();
     cluster_wait();
-    // PDL: everything above overlaps the previous kernel's tail; its outputs (coeffs) are read only below
-    griddep_wait();
+    // PDL.  Everything above overlaps the previous kernel's tail, and so does the PRODUCER: the stack is immutable, so it starts
+    // filling the ring while the predecessor (coefficient upload kernel / hierarchical prologue / previous finalize) is still
+    // running -- those release this launch at their start.  Every other role waits: the A warps read the predecessor's
+    // coefficients, the reducer and the B warps overwrite buffers the previous finalize reads.
+    // (pdl_early: release the finalize launch at once as well; measured: its waiting blocks occupy SMs the next evaluation's
+    // CTAs want, slower in a sustained loop -- off by default, profiles/r2_experiments.md section 6.)
+    if (p.pdl_early) griddep_launch_dependents();
+    if (warp != kV2A + kV2B) griddep_wait();
 
     const int my_tiles = (p.n_tiles > (int)cl) ? (p.n_tiles - (int)cl + (int)ncl - 1) / (int)ncl : 0;
     const uint32_t ring_base = smem_u32(smem + L.ring_off);

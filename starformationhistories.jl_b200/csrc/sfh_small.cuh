@@ -105,6 +105,13 @@ struct FinalizeParams {
     unsigned long long *epoch_ptr;  // device: evaluations exchanged so far on this context (read and bumped by the last
                                     // block only, so a captured CUDA graph of the evaluation can be replayed)
     HierTail hier;                  // hierarchical chain rule on the (all-reduced) gradient, by the last block
+    // Completion without a stream synchronisation: when pkt_host is set, every result is ALSO stored into the caller's mapped
+    // pinned buffer as a self-validating packet (st_packet) carrying the epoch the host wrote next to its inputs; the host polls
+    // the packets (sfh_api.cu: wait_packets) instead of waiting for the stream to drain.  pkt_epoch = device copy of that epoch
+    // (written by the upload kernel / the hierarchical prologue of the same evaluation).
+    void *pkt_host;
+    const unsigned long long *pkt_epoch;
+    int32_t pdl_early;              // release the dependent launch at kernel start
     long long *dbg;                 // nullable (SFH_DEBUG_FINALIZE=1): clock64() of the last block's thread 0 at its milestones
 };
 
@@ -164,8 +171,11 @@ __device__ __forceinline__ double early_logl(const FinalizeParams &p, double *sh
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
+    if (p.pdl_early) griddep_launch_dependents();   // the next evaluation's first kernel may become resident (it waits in turn)
     griddep_wait();  // PDL: launched while the fused kernel drains
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t hep = p.pkt_host ? (uint32_t)__ldcg(p.pkt_epoch) : 0u;   // the host's epoch of this evaluation
+    uint4 *const pkt = reinterpret_cast<uint4 *>(p.pkt_host);
     // the epoch of THIS evaluation: the stored one + 1 (bumped by the last block only, after every block has read it)
     const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
     const uint32_t ep32 = (uint32_t)epoch;
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
             const double all = early_logl(p, sh);
             if (warp == 0) {
                 if (p.peers) push_logl(p, all, lane, par, ep32);
-                else if (lane == 0) { p.out[0] = all; if (p.out_host) p.out_host[0] = all; }
+                else if (lane == 0) { p.out[0] = all; if (p.out_host) p.out_host[0] = all; if (pkt) st_packet(pkt, all, hep); }
             }
         }
     } else {
@@ -210,6 +220,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
             if (lane == 0) {
                 p.out[1 + j] = s;
                 if (p.out_host) p.out_host[1 + j] = s;
+                if (pkt) st_packet(pkt + 1 + j, s, hep);
             }
         }
     }
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     if (threadIdx.x == 0) {
         p.out[0] = all;
         if (p.out_host) p.out_host[0] = all;
+        if (pkt) st_packet(pkt, all, hep);
         *p.ticket = 0u;  // re-arm for the next evaluation on this context
         if (p.peers) *p.epoch_ptr = epoch;
     }
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
     __shared__ double part[kFinalizeThreads / 32][32], part2[kFinalizeThreads / 32][32];
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
+    if (p.pdl_early) griddep_launch_dependents();
     griddep_wait();
     const HierTail &h = p.hier;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kFinalizeThreads / 32;
@@ -354,6 +367,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
         const double v = (all != 0.0) ? -all : __longlong_as_double(0x7ff0000000000000LL);  // fitting_base.jl:95, solvers.jl:31
         h.out[0] = v;
         if (h.out_host) h.out_host[0] = v;
+        if (p.pkt_host) st_packet(reinterpret_cast<uint4 *>(p.pkt_host), v, (uint32_t)__ldcg(p.pkt_epoch));
         *p.ticket = 0u;
         if (p.peers) *p.epoch_ptr = epoch;
     }
@@ -395,7 +409,27 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
         const double v = (i < nj) ? s_G[i] : (h.free_mask[i - nj] ? s_par[i - nj] : 0.0);   // fixed parameters receive 0 (mzr.jl:196,201)
         h.out[1 + i] = v;
         if (h.out_host) h.out_host[1 + i] = v;
+        if (p.pkt_host) st_packet(reinterpret_cast<uint4 *>(p.pkt_host) + 1 + i, v, (uint32_t)__ldcg(p.pkt_epoch));
     }
+}
+
+// Upload of one evaluation's inputs WITHOUT a copy node: n doubles from the caller's mapped pinned buffer to device memory, plus
+// the 64-bit epoch the host stored behind them (see FinalizeParams::pkt_host).  The dependent launch is released first, so the
+// fused kernel becomes resident and its producers fill their rings while the 19 KB cross PCIe; its A warps wait for this grid.
+// The device copy is written after griddepcontrol.wait only (a previous evaluation on the stream may still be reading it).
+constexpr int kCopyInThreads = 256;
+__global__ void __launch_bounds__(kCopyInThreads) sfh_copy_in_kernel(double *dst, const double *src_host, int64_t n, unsigned long long *epoch_dst) {
+    griddep_launch_dependents();
+    const int64_t i = ((int64_t)blockIdx.x * kCopyInThreads + threadIdx.x) * 2;
+    double v0 = 0.0, v1 = 0.0;
+    unsigned long long ep = 0ull;
+    if (i + 1 < n) { const double2 v = __ldcv(reinterpret_cast<const double2 *>(src_host + i)); v0 = v.x; v1 = v.y; }
+    else if (i < n) v0 = __ldcv(src_host + i);
+    if (i == 0 && epoch_dst) ep = __ldcv(reinterpret_cast<const unsigned long long *>(src_host + n));
+    griddep_wait();
+    if (i < n) dst[i] = v0;
+    if (i + 1 < n) dst[i + 1] = v1;
+    if (i == 0 && epoch_dst) *epoch_dst = ep;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -494,6 +528,8 @@ struct HierParams {
     const double *fg_out;                    // [1+nt]: logL raw, +M'r  (input of the epilogue)
     double *out;                             // [1 + nj + 3]: -logL (guarded), G
     double *out_host;                        // nullable: mapped pinned host copy of `out`
+    unsigned long long *pkt_epoch_out;       // nullable (folded path): device copy of the host's epoch word behind the variables
+    int32_t pdl_early;                       // folded path: release the dependent launch at kernel start
     // batched launches (grid = chains): block k works on chain k, whose arrays sit k strides further on
     int64_t bs_vars, bs_scratch, bs_coeffs, bs_fg, bs_out;   // element strides; all 0 for a single evaluation
 };
@@ -619,6 +655,7 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
     __shared__ double sv[kHierTailAges + 3], sRs[kHierTailAges];
     __shared__ int spos[kHierTailAges];
     __shared__ double sA[kHierPro2Threads / 32][kHierPro2Keep];
+    if (p.pdl_early) griddep_launch_dependents();   // the fused kernel becomes resident and streams ahead; its A warps wait for this grid
     griddep_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHierPro2Threads / 32;
     const int nj = p.nj;
@@ -637,6 +674,8 @@ __global__ void __launch_bounds__(kHierPro2Threads) sfh_hier_prologue2_kernel(co
         sv[i] = v;
         if (blockIdx.x == 0) const_cast<double *>(p.variables)[i] = v;   // device copy for later kernels
     }
+    // the host's epoch of this evaluation rides behind the variables (FinalizeParams::pkt_host)
+    if (p.pkt_epoch_out && blockIdx.x == 0 && tid == 0) *p.pkt_epoch_out = __ldcv(reinterpret_cast<const unsigned long long *>(vars_in + nj + 3));
     int srt = -1;
     if (p.kind == MH_POWERLAW_MZR && tid < nj) srt = p.sidx[tid];          // (nj <= kHierTailAges <= block size)
     __syncthreads();

@@ -268,6 +268,31 @@ def test_bitwise_determinism(S):
     assert a[0] == c[0] and np.array_equal(a[1], c[1])
 
 
+@pytest.mark.parametrize("nb,nt", [(700, 33), (10000, 100), (20000, 1203)])
+def test_packet_completion_never_returns_a_stale_result(S, nb, nt):
+    """The host-synchronous call returns when the finalize kernel's self-validating packets {lo, epoch, hi, epoch} have
+    arrived in pinned memory -- there is no stream synchronisation behind it (csrc/sfh_api.cu wait_packets).  Thousands of
+    back-to-back calls with a DIFFERENT coefficient vector each time, with and without the gradient: every answer must be
+    the one of its own inputs, bit for bit (a stale or torn packet would surface as the previous call's value)."""
+    M, x, data = make_flat_problem(nb, nt, seed=11)
+    ds = S.DeviceStack(M, data)
+    rng = np.random.default_rng(5)
+    xs = [x * (1 + 0.2 * rng.random(nt)) for _ in range(5)]
+    want = [ds.eval_fg(xk) for xk in xs]
+    for k, xk in enumerate(xs):                                   # the references themselves: against the oracle
+        nlq, Gq, gs, _ = O.fg_quad(xk, M, data)
+        assert want[k][0] == pytest.approx(nlq, rel=RTOL_LOGL)
+        assert_grad_close(want[k][1], Gq, gs)
+    for it in range(3000):
+        k = int(rng.integers(5))
+        if it % 7 == 3:
+            nl = ds.eval_fg(xs[k], want_G=False)[0]
+            assert nl == want[k][0], (it, k)
+        else:
+            nl, G = ds.eval_fg(xs[k])[:2]
+            assert nl == want[k][0] and np.array_equal(G, want[k][1]), (it, k)
+
+
 @pytest.mark.parametrize("nb,nt", [(100, 100), (9801, 142), (11250, 2000), (5000, 2400)])
 def test_fg_parity_f32_storage(S, nb, nt):
     """Float32-stored templates, FP64 accumulation, vs exact arithmetic on the same stored values (1e-6)."""
