@@ -436,7 +436,7 @@ def run_hier(H, ctx, steps, warmup, peak, bytes_alg):
     ms = 1e3 * wall / steps
     assert np.isfinite(nl.value) and np.all(np.isfinite(G))
     return {"what": "sfh_eval_fg_hier (PowerLawMZR + GaussianDispersion, 60 ages + 3 parameters), host buffers, wall clock per call",
-            "ms_per_eval": ms, "evals_per_s": H.world * 1e3 / ms, "h2d_bytes_per_step": (NJ + 3) * 8, "d2h_bytes_per_step": (NJ + 4) * 8,
+            "ms_per_eval": ms, "evals_per_s": H.world * 1e3 / ms, "h2d_bytes_per_step": (NJ + 3) * 8 + 8, "d2h_bytes_per_step": (NJ + 4) * 16,
             "roofline_frac_end_to_end": bytes_alg / (ms * 1e-3) / 1e9 / peak}
 
 
@@ -494,6 +494,7 @@ def main():
         L.check(L.lib.sfh_eval_fg(ctx.handle, xh.ctypes.data_as(dp), C.byref(nl), G.ctypes.data_as(dp), None))
     e1.record(H.stream)
     wall = time.perf_counter() - t0      # the caller-visible time of K synchronous calls (>= the event time)
+    e1.synchronize()                     # (a call returns when its result packets have arrived, a little before the stream drains)
     H.barrier()
     e2e_ms = H.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * wall))
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
@@ -563,8 +564,11 @@ def main():
                            "sharding": sharding,
                            "timing": "CUDA events on the launch stream; ranks aligned on the device by two untimed all-reduced steps before e0; max over ranks",
                            "value_unit_note": "N>1: value = N shard-evaluations per all-reduced step / time (weak scaling)", **tiling(info)},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NT * 8, "d2h_bytes_per_step": (NT + 1) * 8,
-                        "ms_per_step": e2e_ms / args.steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NT * 8 + 8, "d2h_bytes_per_step": (NT + 1) * 16,
+                        "ms_per_step": e2e_ms / args.steps,
+                        "transport": "sfh_eval_fg(host coeffs) -> host [-logL, G]: an upload kernel pulls the coefficients (+ an 8-byte epoch) "
+                                     "from the pinned input buffer, the finalize kernel stores every result as a 16-byte self-validating "
+                                     "packet into pinned host memory, the call returns when the host has read all of them"},
                 "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "fg_hier": fg_hier}
         if parity is not None:
             line["parity"] = parity

@@ -811,8 +811,8 @@ static int sfh_ctx_create_impl(sfh_stack *s, void *stream, sfh_ctx **out) {
     c->h_out_n = (size_t)std::max<int64_t>(nt + 1, ld) + 16;
     CTX_TRY(cudaMallocHost((void **)&c->h_in, c->h_in_n * 8));
     CTX_TRY(cudaMallocHost((void **)&c->h_out, c->h_out_n * 8));
-    CTX_TRY(cudaMallocHost((void **)&c->h_pkt, c->h_out_n * 16));
-    memset(c->h_pkt, 0, c->h_out_n * 16);
+    CTX_TRY(cudaMallocHost((void **)&c->h_pkt, (c->h_out_n + kPktG0) * 16));
+    memset(c->h_pkt, 0, (c->h_out_n + kPktG0) * 16);
     CTX_TRY(cudaMalloc((void **)&c->d_hostep, 8));
     CTX_TRY(cudaMemset(c->d_hostep, 0, 8));
     CTX_TRY(cudaEventCreate(&c->ev0));
@@ -1023,21 +1023,22 @@ int run_graphed(sfh_ctx *c, sfh_ctx::GraphSlot &slot, uint64_t key, F &&enqueue)
 
 // Completion of a host-synchronous evaluation WITHOUT cudaStreamSynchronize: the finalize kernel stored every result into the
 // pinned buffer as a 16-byte packet {lo32, epoch, hi32, epoch}; a result is there when both halves carry this evaluation's
-// epoch (each 8-byte half is a single PCIe write and a single host load).  Reads packet 0 into *first and packets 1..n into
-// rest[0..n).  The stream is queried now and then so that a faulted or result-less evaluation fails instead of hanging.
+// epoch (each 8-byte half is a single PCIe write and a single host load).  Reads packet 0 into *first and the n packets from
+// rest_at on into rest[0..n).  The stream is queried now and then so that a faulted or result-less evaluation fails instead of hanging.
 inline uint32_t next_packet_epoch(sfh_ctx *c, size_t n_in) {
     if (++c->pkt_epoch == 0) c->pkt_epoch = 1;
     const unsigned long long e = c->pkt_epoch;
     memcpy(c->h_in + n_in, &e, 8);
     return c->pkt_epoch;
 }
-int wait_packets(sfh_ctx *c, uint32_t ep, double *first, double *rest, size_t n) {
+int wait_packets(sfh_ctx *c, uint32_t ep, double *first, double *rest, size_t n, size_t rest_at = 1) {
     const uint64_t *pk = static_cast<const uint64_t *>(c->h_pkt);
     const size_t total = 1 + (rest ? n : 0);
     uint64_t spins = 0;
     bool drained = false;
     for (size_t j = 0; j < total;) {
-        const uint64_t a = __atomic_load_n(pk + 2 * j, __ATOMIC_ACQUIRE), b = __atomic_load_n(pk + 2 * j + 1, __ATOMIC_ACQUIRE);
+        const size_t at = j == 0 ? 0 : rest_at + j - 1;   // packet 0, then n packets from rest_at on
+        const uint64_t a = __atomic_load_n(pk + 2 * at, __ATOMIC_ACQUIRE), b = __atomic_load_n(pk + 2 * at + 1, __ATOMIC_ACQUIRE);
         if ((uint32_t)(a >> 32) == ep && (uint32_t)(b >> 32) == ep) {
             const uint64_t bits = (a & 0xffffffffull) | (b << 32);
             double v;
@@ -1115,7 +1116,7 @@ static int eval_fg_local(sfh_ctx *c, const double *coeffs, double *neg_logL, dou
     }));
     if (pk) {
         double raw = 0.0;
-        SFH_TRY(wait_packets(c, ep, &raw, (want_G && G) ? G : nullptr, (size_t)s->nt));
+        SFH_TRY(wait_packets(c, ep, &raw, (want_G && G) ? G : nullptr, (size_t)s->nt, (size_t)kPktG0));
         if (neg_logL) *neg_logL = guard_neg_logl(raw);
         if (composite_out) CU_TRY(cudaStreamSynchronize(c->stream));
     } else {

@@ -132,6 +132,9 @@ __device__ __forceinline__ double ld_packet_wait(const void *src, uint32_t ep) {
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 constexpr int kFinalizeThreads = 256;
+constexpr int kFinE = 4;      // entries a warp of the sharded finalize kernel has in flight (pushed before any is polled)
+constexpr int kPktG0 = 8;     // host packets of the flat call: [0] = logL, [kPktG0 + j] = G_j -- a block's 8 packets start on a 128-byte boundary
+constexpr int kMaxExchangeRanks = 32;   // ranks of the one-shot exchange (sfh_comm_p2p_init / sfh_group_create refuse more)
 
 enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
 
@@ -170,6 +173,7 @@ __device__ __forceinline__ double early_logl(const FinalizeParams &p, double *sh
 
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const FinalizeParams p) {
     __shared__ double sh[kFinalizeThreads / 32];
+    __shared__ double shg[2][kFinE][kFinalizeThreads / 32];   // a pass's results, gathered for the host packets
     __shared__ bool last;
     if (p.pdl_early) griddep_launch_dependents();   // the next evaluation's first kernel may become resident (it waits in turn)
     griddep_wait();  // PDL: launched while the fused kernel drains
@@ -201,26 +205,72 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
         if (threadIdx.x == 0) p.lpart[blockIdx.x] = tot;
     }
 
-    // G_j = sum over clusters: one WARP per template, lanes take clusters lane, lane+32, ... (independent loads)
+    // G_j = sum over clusters: one WARP per template, lanes take clusters lane, lane+32, ... (independent loads).  A block owns 8
+    // CONSECUTIVE templates per pass; their results leave for the host together: 8 packets = 128 aligned bytes in ONE store
+    // instruction of warp 0, i.e. whole 64-byte lines.  (2400 separate 16-byte stores, four to a line and arriving at different
+    // times while the host polls that very line, cost +8 us per call on one of the boxes measured and -4 on another:
+    // profiles/r2_experiments.md section 6a.)
     if (p.want_G) {
-        const int64_t nwarps = (int64_t)gridDim.x * (kFinalizeThreads / 32);
-        const uint4 *inbox = p.peers ? reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen : nullptr;
-        for (int64_t j = (int64_t)blockIdx.x * (kFinalizeThreads / 32) + warp; j < p.nt; j += nwarps) {
-            double s = 0.0;
-            for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
-            s = warp_sum(s);   // xor tree: every lane holds the total
-            if (p.peers) {
-                if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen + 1 + j, s, ep32);
-                const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen + 1 + j, ep32) : 0.0;
-                double t = 0.0;
-#pragma unroll 1
-                for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);
-                s = t;
+        constexpr int NW = kFinalizeThreads / 32;
+        const int64_t nwarps = (int64_t)gridDim.x * NW;
+        const int64_t jb0 = (int64_t)blockIdx.x * NW;
+        if (!p.peers) {
+            int buf = 0;
+            for (int64_t jb = jb0; jb < p.nt; jb += nwarps, buf ^= 1) {
+                const int64_t j = jb + warp;
+                if (j < p.nt) {
+                    double s = 0.0;
+                    for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
+                    s = warp_sum(s);   // xor tree: every lane holds the total
+                    if (lane == 0) {
+                        p.out[1 + j] = s;
+                        if (p.out_host) p.out_host[1 + j] = s;
+                        shg[buf][0][warp] = s;
+                    }
+                }
+                if (pkt) {
+                    __syncthreads();   // (one barrier per pass: the two buffers alternate)
+                    if (warp == 0 && lane < NW && jb + lane < p.nt) st_packet(pkt + kPktG0 + jb + lane, shg[buf][0][lane], hep);
+                }
             }
-            if (lane == 0) {
-                p.out[1 + j] = s;
-                if (p.out_host) p.out_host[1 + j] = s;
-                if (pkt) st_packet(pkt + 1 + j, s, hep);
+        } else {
+            // sharded: a warp that owns several entries (T > warps of the grid, e.g. 10^4 templates) pushes ALL of them before it
+            // polls any, so their NVLink round trips overlap instead of following one another (config 5 at 8 GPUs: 3 per warp)
+            const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen;
+            int buf = 0;
+            for (int64_t jb = jb0; jb < p.nt; jb += kFinE * nwarps, buf ^= 1) {
+#pragma unroll
+                for (int e = 0; e < kFinE; ++e) {
+                    const int64_t j = jb + e * nwarps + warp;
+                    if (j < p.nt) {
+                        double s = 0.0;
+                        for (int cl = lane; cl < p.n_clusters; cl += 32) s += __ldcg(p.gpart + (int64_t)cl * p.gstride + j);
+                        s = warp_sum(s);
+                        if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen + 1 + j, s, ep32);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < kFinE; ++e) {
+                    const int64_t j = jb + e * nwarps + warp;
+                    if (j < p.nt) {
+                        const double v = (lane < p.nranks) ? ld_packet_wait(inbox + (int64_t)lane * p.vlen + 1 + j, ep32) : 0.0;
+                        double t = 0.0;
+#pragma unroll 1
+                        for (int r = 0; r < p.nranks; ++r) t += __shfl_sync(0xffffffffu, v, r);   // rank order: bit-identical everywhere
+                        if (lane == 0) {
+                            p.out[1 + j] = t;
+                            if (p.out_host) p.out_host[1 + j] = t;
+                            shg[buf][e][warp] = t;
+                        }
+                    }
+                }
+                if (pkt) {
+                    __syncthreads();
+                    if (warp < kFinE && lane < NW) {   // warp e sends pass e's 8 packets
+                        const int64_t j = jb + (int64_t)warp * nwarps + lane;
+                        if (j < p.nt) st_packet(pkt + kPktG0 + j, shg[buf][warp][lane], hep);
+                    }
+                }
             }
         }
     }
@@ -259,6 +309,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
 // 5 us on 9600 uncoalesced 8-byte loads from one SM; profiles/r2_experiments.md section 4.)
 __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(const FinalizeParams p) {
     __shared__ double part[kFinalizeThreads / 32][32], part2[kFinalizeThreads / 32][32];
+    __shared__ double xch[kMaxExchangeRanks][32], xch2[kMaxExchangeRanks][32];   // the ranks' packets of one pass, [rank][member]
     __shared__ double sh[kFinalizeThreads / 32];
     __shared__ bool last;
     if (p.pdl_early) griddep_launch_dependents();
@@ -303,8 +354,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
             part[warp][lane] = sA;
             part2[warp][lane] = sB;
             __syncthreads();
+            double GA = 0.0, GB = 0.0;
             if (warp == 0) {
-                double GA = 0.0, GB = 0.0;
 #pragma unroll
                 for (int w = 0; w < nw; ++w) { GA += part[w][lane]; GB += part2[w][lane]; }
                 if (p.peers) {
@@ -314,15 +365,25 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
                         if (vA) st_packet(reinterpret_cast<uint4 *>(p.peers[r]) + slot + tA, GA, ep32);
                         if (vB) st_packet(reinterpret_cast<uint4 *>(p.peers[r]) + slot + tB, GB, ep32);
                     }
-                    const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen + 1;
-                    double tsA = 0.0, tsB = 0.0;
-#pragma unroll 1
-                    for (int r = 0; r < p.nranks; ++r) {   // rank order
-                        if (vA) tsA += ld_packet_wait(inbox + (int64_t)r * p.vlen + tA, ep32);
-                        if (vB) tsB += ld_packet_wait(inbox + (int64_t)r * p.vlen + tB, ep32);
-                    }
-                    GA = tsA; GB = tsB;
                 }
+            }
+            if (p.peers) {
+                // every warp polls one rank's packets (lane = member), so the nranks waits run side by side instead of one
+                // after another in warp 0 (8 dependent L2 round trips at 8 GPUs); warp 0 then adds them in rank order
+                const uint4 *inbox = reinterpret_cast<const uint4 *>(p.peers[p.rank]) + par * p.nranks * p.vlen + 1;
+#pragma unroll 1
+                for (int r = warp; r < p.nranks; r += nw) {
+                    xch[r][lane] = vA ? ld_packet_wait(inbox + (int64_t)r * p.vlen + tA, ep32) : 0.0;
+                    xch2[r][lane] = vB ? ld_packet_wait(inbox + (int64_t)r * p.vlen + tB, ep32) : 0.0;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    GA = 0.0; GB = 0.0;
+#pragma unroll 1
+                    for (int r = 0; r < p.nranks; ++r) { GA += xch[r][lane]; GB += xch2[r][lane]; }   // rank order
+                }
+            }
+            if (warp == 0) {
                 // fullG_t = d logL / d r_t = -(M'r)_t
                 if (vA) { p.out[1 + tA] = GA; a0 += (-GA) * wA[0]; a1 += (-GA) * wA[1]; a2 += (-GA) * wA[2]; a3 += (-GA) * wA[3]; }
                 if (vB) { p.out[1 + tB] = GB; a0 += (-GB) * wB[0]; a1 += (-GB) * wB[1]; a2 += (-GB) * wB[2]; a3 += (-GB) * wB[3]; }
