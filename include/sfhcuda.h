@@ -136,7 +136,11 @@ int sfh_ctx_stats(const sfh_ctx *c, sfh_stats *out);
  *   neg_logL != NULL  <=>  F !== nothing ;  G != NULL  <=>  G !== nothing.
  *   *neg_logL = -logL (logL == 0 -> +Inf, fitting_base.jl:95);  G[j] = sum_i M_ij (1 - n_i/m_i).
  *   composite_out (nullable, nbins doubles): what the reference leaves in `composite`:
- *   the residual 1 - n/m when G != NULL (fitting_base.jl:219), else M*coeffs.                  */
+ *   the residual 1 - n/m when G != NULL (fitting_base.jl:219), else M*coeffs.
+ * Host-synchronous: returns when neg_logL / G hold the answer.  On the fused path the call does not synchronise the stream:
+ * the results arrive in a pinned buffer as self-validating packets which the calling thread polls (DESIGN.md section 3,
+ * "Completion by packets"); the caller's arrays may be pageable.  Environment switches for A/B measurements only:
+ * SFH_HOST_PACKETS=0 (synchronise instead), SFH_PDL_EARLY=<bit mask>, SFH_NO_GRAPH=1.                                    */
 int sfh_eval_fg(sfh_ctx *c, const double *coeffs, double *neg_logL, double *G, double *composite_out);
 /* composite!(C, coeffs, models)  fitting_base.jl:55-65 */
 int sfh_composite(sfh_ctx *c, const double *coeffs, double *composite_out);
