@@ -562,7 +562,11 @@ def main():
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_stack_bytes": int(info.stack_bytes),
-                           "l2": "inputs (1.15 GB/GPU) larger than L2 (126 MB); no flush needed",
+                           "l2": "inputs (1.15 GB/GPU) larger than L2 (126 MB): no flush between iterations; the stack is streamed with the L2 "
+                                 f"evict_first policy except the head of every CTA's tile sequence ({int(info.l2_resident_mb)} MB in total = "
+                                 f"{100.0 * info.l2_resident_mb * 1048576 / info.stack_bytes:.1f} % of the stack, loaded evict_last), which "
+                                 "therefore stays L2-resident between evaluations of the same stack (SFH_L2_KEEP_MB=0 switches it off)",
+                           "l2_resident_mb": int(info.l2_resident_mb),
                            "sharding": sharding,
                            "timing": "CUDA events on the launch stream; ranks aligned on the device by two untimed all-reduced steps before e0; max over ranks",
                            "value_unit_note": "N>1: value = N shard-evaluations per all-reduced step / time (weak scaling)", **tiling(info)},

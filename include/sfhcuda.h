@@ -85,7 +85,7 @@ typedef struct sfh_info {
     int32_t sm_count, cc_major, cc_minor;
     int32_t variant;      /* fused kernel in use: 0 none (two-pass), 1 cluster-tile kernel, 4 warp-specialised stream kernel */
     int32_t panel_layout; /* 1: device copy stored as bin-major panels of tile_bins bins (host layout unchanged) */
-    int32_t reserved0;
+    int32_t l2_resident_mb; /* MB of the stack the fused kernel keeps L2-resident between evaluations (0: none / stack fits L2) */
     int64_t stack_bytes; /* device bytes held by the stack (padded)                    */
     double clamp_eps;
 } sfh_info;

@@ -39,7 +39,7 @@ class sfh_info(C.Structure):
                 ("ld", C.c_int64), ("dtype", C.c_int32), ("device", C.c_int32), ("fused", C.c_int32),
                 ("tile_bins", C.c_int32), ("cluster", C.c_int32), ("chunks_per_tile", C.c_int32),
                 ("ring_slots", C.c_int32), ("n_clusters", C.c_int32), ("consumer_warps", C.c_int32), ("sm_count", C.c_int32),
-                ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("variant", C.c_int32), ("panel_layout", C.c_int32), ("reserved0", C.c_int32),
+                ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("variant", C.c_int32), ("panel_layout", C.c_int32), ("l2_resident_mb", C.c_int32),
                 ("stack_bytes", C.c_int64), ("clamp_eps", C.c_double)]
 
 

@@ -739,6 +739,7 @@ extern "C" int sfh_stack_destroy(sfh_stack *s) {
     return guarded([&]() -> int { return sfh_stack_destroy_impl(s); });
 }
 
+namespace { int l2_keep_stages(const sfh_stack *s); }
 static int sfh_stack_info_impl(const sfh_stack *s, sfh_info *info) {
     if (!s || !info) return fail(SFH_ERR_INVALID_ARG, "NULL argument");
     memset(info, 0, sizeof *info);
@@ -746,7 +747,7 @@ static int sfh_stack_info_impl(const sfh_stack *s, sfh_info *info) {
     info->ld = s->lay.ld; info->dtype = s->dtype; info->device = s->device; info->fused = s->fused ? 1 : 0;
     info->tile_bins = s->bt; info->cluster = s->cluster; info->chunks_per_tile = s->kt; info->ring_slots = s->ring;
     info->n_clusters = s->n_clusters; info->consumer_warps = s->nw; info->variant = s->fused ? (s->v2 ? 4 : 1) : 0; info->sm_count = s->sm_count; info->cc_major = s->cc_major; info->cc_minor = s->cc_minor;
-    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->reserved0 = 0; info->clamp_eps = s->eps;
+    info->stack_bytes = (int64_t)((size_t)s->lay.alloc_elems() * elem_size(s->dtype)); info->panel_layout = s->panel ? 1 : 0; info->l2_resident_mb = (s->fused && s->v2) ? (int32_t)(l2_keep_stages(s) * (double)std::max(s->n_clusters, 1) * std::max(s->cluster, 1) * (double)kV2Stage / 1048576.0) : 0; info->clamp_eps = s->eps;
     return SFH_OK;
 }
 extern "C" int sfh_stack_info(const sfh_stack *s, sfh_info *info) {
@@ -890,6 +891,23 @@ constexpr int kPdlFused = 1, kPdlFinalize = 2, kPdlPrologue = 4, kPdlDefault = k
 int pdl_early_mask() { const char *e = getenv("SFH_PDL_EARLY"); return (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : kPdlDefault; }
 bool host_packets_on() { const char *e = getenv("SFH_HOST_PACKETS"); return !(e && e[0] == '0'); }
 
+// How many stages at the head of every CTA's tile sequence stay L2-resident between evaluations (sfh_fused2.cuh: keep_stages).
+// Budget = min(3/4 of L2, 8 % of the stack): measured over stacks of 160 MB ... 5 GB (profiles/r2_experiments.md section 8) a larger
+// share slows stacks that are only a little larger than L2 (the streamed remainder is left too little room) and 112 of 126 MB
+// slows every shape.  SFH_L2_KEEP_MB overrides the budget (0 = stream everything evict_first, as before).
+double l2_keep_bytes(const sfh_stack *s) {
+    if (!s->evict_first) return 0.0;   // the whole stack fits L2: nothing is streamed evict_first
+    const char *e = getenv("SFH_L2_KEEP_MB");
+    if (e) return atof(e) * 1048576.0;
+    const double stack_bytes = (double)s->lay.alloc_elems() * (double)elem_size(s->dtype);
+    return std::min(0.75 * (double)s->l2_bytes, 0.08 * stack_bytes);
+}
+int l2_keep_stages(const sfh_stack *s) {
+    const double per_stage = (double)std::max(s->n_clusters, 1) * std::max(s->cluster, 1) * (double)kV2Stage;   // all CTAs, one stage each
+    const double n = l2_keep_bytes(s) / per_stage;
+    return n >= 1.0 ? (int)std::min(n, 1e6) : 0;
+}
+
 int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want_G_reduce, double *out_host = nullptr,
                     bool p2p_push = false, bool logl_from_fused = false, const HierTail *tail = nullptr, void *pkt_host = nullptr) {
     const sfh_stack *s = c->s;
@@ -936,6 +954,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
             p.evict_first = s->evict_first ? 1 : 0; p.eps = s->eps; p.M = s->dM; p.coeffs = d_coeffs; p.data = s->d_data;
             p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
             p.lpart = c->d_lpart; p.gstride = c->gstride; p.pdl_early = (pdl_early_mask() & kPdlFused) ? 1 : 0;
+            p.keep_stages = l2_keep_stages(s);
             CU_TRY(v2_dispatch(s, 2, want_G != 0, &p, c->stream, nullptr));
         } else {
             FusedParams p{};

@@ -48,6 +48,7 @@ struct Fused2Params {
     int32_t n_tiles;      // ceil(nb / BT)
     int32_t evict_first;  // L2 evict_first policy on the stack stream
     int32_t pdl_early;    // 1: release the dependent (finalize) launch at kernel start
+    int32_t keep_stages;  // the first keep_stages stages of every CTA's tile sequence are loaded with the L2 evict_last policy
     double eps;           // clamp (fitting_base.jl:90,277)
     const void *M;        // device stack, bin-major panels [n_tiles][nt][BT]
     const double *coeffs; // [nt]
@@ -179,7 +180,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
     if (warp == kV2A + kV2B) {
         // ================= producer: one bulk copy per stage =================
         if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
+            // L2 residency between evaluations: a stack larger than L2 is streamed evict_first, EXCEPT the head of every CTA's
+            // tile sequence (keep_stages stages, ~half of L2 in total), which is loaded evict_last and therefore still there
+            // when the next evaluation of the same stack starts: those bytes never touch HBM again, and the ring's first fill
+            // comes at L2 latency.  (The stack is immutable and a fit evaluates it thousands of times.)
+            const uint64_t pol = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+            int stage_no = 0;
             constexpr int64_t row_bytes = (int64_t)BT * sizeof(S);
             const int64_t row0 = (int64_t)q * kt * RPC;                      // first template of this CTA's slice
             int64_t rows_mine = p.nt - row0;
@@ -199,11 +205,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
                         mbar_arrive_expect_tx(&full[slot], bytes);
                         const uint32_t dst = ring_base + (uint32_t)slot * kV2Stage;
                         const char *src = base + (int64_t)s * kV2G * RPC * row_bytes;
-                        if (p.evict_first) bulk_load_1d_hint(dst, src, bytes, smem_u32(&full[slot]), pol);
+                        if (p.evict_first) bulk_load_1d_hint(dst, src, bytes, smem_u32(&full[slot]), stage_no < p.keep_stages ? pol_keep : pol);
                         else bulk_load_1d(dst, src, bytes, smem_u32(&full[slot]));
                     } else {
                         mbar_arrive(&full[slot]);   // a stage wholly past the last template: nothing to fetch
                     }
+                    ++stage_no;
                     if (++slot == NS) { slot = 0; ++round; }
                 }
             }
