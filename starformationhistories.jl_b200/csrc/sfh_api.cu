@@ -377,12 +377,16 @@ bool choose_config_v2(sfh_stack *s, const sfh_opts *o) {
             const double ring_f = std::min(1.0, 0.6 + 0.4 * (ring_tiles - 1.0) / 1.5);  // 1 tile: 0.6 ... >= 2.5 tiles: 1
             // the (serial) reducer warp must keep up with the stream also at a power-capped clock: r2d, config 3 back to back,
             // 38 KB tiles 202 us per step vs 173 us with 77 KB tiles
-            const double red_f = std::min(1.0, tile_kb / (c > 1 ? 80.0 : 64.0));
+            const double red_f = std::min(1.0, tile_kb / (c > 1 ? 72.0 : 64.0));
             const double fill = (double)s->nt / ((double)c * kt * rpc);               // padding lanes idle, stages part-filled
             const int64_t n_tiles = (s->rows + bt - 1) / bt;
             const double waves = (double)n_tiles / (double)std::max(s->sm_count / c, 1);
             const double balance = waves >= 1.0 ? waves / std::ceil(waves) : waves;
-            const double score = sm_frac * ring_f * red_f * balance * (0.9 + 0.1 * fill);
+            // r2ae: with everything else equal a CTA pair on a twice as wide tile beats two single CTAs (config 3: 8-bin tiles on 74
+            // pairs 0.1644 vs 4-bin tiles on 148 CTAs 0.1695 ms per step at full clock, hierarchical call 0.182 vs 0.190 ms at any
+            // clock; flat calls 1.3 % slower under a sustained power cap): half as many partial rows for the finalize kernel
+            const double pair_f = c == 2 ? 1.02 : 1.0;
+            const double score = sm_frac * ring_f * red_f * balance * (0.9 + 0.1 * fill) * pair_f;
             if (score > best) { best = score; b_lpr = lpr; b_c = c; b_kt = kt; b_ns = ns; }
         }
     }
