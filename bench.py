@@ -119,10 +119,10 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(key="fused_kernel_dram_bytes_per_launch"):
     p = os.path.join(ROOT, "profiles", "ncu_summary.json")
     try:
-        return json.load(open(p)).get("fused_kernel_dram_bytes_per_launch")
+        return json.load(open(p)).get(key)
     except Exception:
         return None
 
@@ -515,7 +515,9 @@ def main():
     achieved = bytes_alg / (ms_kernel.value * 1e-3) / 1e9
     kernel_ms_per_rank = H.gather(ms_kernel.value)     # GPUs of one box differ by a few per cent: an all-reduced step runs at the slowest
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "traffic_source": "constant: dram__bytes_read+write of this kernel from the ncu --set full capture summarised in profiles/ncu_summary.json (not re-measured in this run)",
+                "traffic": ncu_traffic(), "traffic_source": "constant: dram__bytes_read+write of this kernel from the ncu --set full capture (cold caches) summarised in profiles/ncu_summary.json (not re-measured in this run)",
+                "traffic_steady_state": ncu_traffic("fused_kernel_dram_read_bytes_per_launch_steady_state"),
+                "traffic_steady_state_source": "constant: dram__bytes_read of launches 21-23 of a back-to-back series, ncu application replay with caches untouched (profiles/r2_final2_warm.csv): the L2-resident head of the stack is not re-read",
                 "kernel": kernel_name(info, np.float64), "kernel_ms": ms_kernel.value, "kernel_ms_per_rank": kernel_ms_per_rank,
                 "bytes_alg_per_launch": bytes_alg, "peak_source": peak_src}
 

@@ -44,8 +44,13 @@ if fused:
     summary["fused_kernel_dram_bytes_per_launch"] = rd + wr
     summary["fused_kernel_ncu_duration_us"] = k["gpu__time_duration.sum"]["value"]
 json.dump(summary, open(os.path.join(out_dir, f"{tag}_fused_ncu.json"), "w"), indent=1)
-json.dump({"fused_kernel_dram_bytes_per_launch": summary.get("fused_kernel_dram_bytes_per_launch"), "from": f"profiles/{tag}_fused_ncu.json"},
-          open(os.path.join(out_dir, "ncu_summary.json"), "w"), indent=1)
+ncu_sum_path = os.path.join(out_dir, "ncu_summary.json")
+try:
+    prev = json.load(open(ncu_sum_path))     # keep hand-added keys (steady-state traffic from an application-replay run)
+except Exception:
+    prev = {}
+prev.update({"fused_kernel_dram_bytes_per_launch": summary.get("fused_kernel_dram_bytes_per_launch"), "from": f"profiles/{tag}_fused_ncu.json"})
+json.dump(prev, open(ncu_sum_path, "w"), indent=1)
 
 # launch list -> per-kernel shares
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
