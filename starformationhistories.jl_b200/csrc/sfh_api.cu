@@ -1121,7 +1121,7 @@ static int eval_fg_local(sfh_ctx *c, const double *coeffs, double *neg_logL, dou
     // ... as self-validating packets the host polls (no copy node in front, no stream synchronisation behind): 2 kernels + 1 upload kernel
     const bool pk = direct && host_packets_on();
     const uint32_t ep = pk ? next_packet_epoch(c, (size_t)s->nt) : 0u;
-    SFH_TRY(run_graphed(c, c->g_fg[want_G], (pk ? 2 : 1) + 16 * (uint64_t)pdl_early_mask(), [&]() -> int {
+    SFH_TRY(run_graphed(c, c->g_fg[want_G], (pk ? 2 : 1) + 16 * (uint64_t)pdl_early_mask() + 256 * (uint64_t)(s->v2 ? l2_keep_stages(s) : 0), [&]() -> int {
         if (pk) {
             const unsigned nblk = (unsigned)((s->nt + 2 * kCopyInThreads - 1) / (2 * kCopyInThreads));
             CU_TRY(launch_pdl(sfh_copy_in_kernel, dim3(nblk), dim3(kCopyInThreads), 0, c->stream, c->d_coeffs, (const double *)c->h_in,
@@ -1418,7 +1418,8 @@ static int eval_fg_hier_local(sfh_ctx *c, int mh_kind, const double *mh_fixed, i
     const bool folded = c->s->fused && c->s->v2 && c->s->rows > 0 && c->s->nt > 0 && c->nj >= 1 && c->nj <= kHierTailAges && (c->nranks == 1 || c->p2p);
     const bool pk = folded && host_packets_on();   // results as packets the host polls (wait_packets)
     const int pdl_mask = pdl_early_mask();
-    mix(&folded, sizeof folded); mix(&pk, sizeof pk); mix(&pdl_mask, sizeof pdl_mask);
+    const int keep_st = c->s->v2 ? l2_keep_stages(c->s) : 0;
+    mix(&folded, sizeof folded); mix(&pk, sizeof pk); mix(&pdl_mask, sizeof pdl_mask); mix(&keep_st, sizeof keep_st);
     const uint32_t ep = pk ? next_packet_epoch(c, nv) : 0u;
     if (pk) hp.pkt_epoch_out = c->d_hostep;
     SFH_TRY(run_graphed(c, c->g_hier, key, [&]() -> int {

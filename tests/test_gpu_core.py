@@ -293,6 +293,30 @@ def test_packet_completion_never_returns_a_stale_result(S, nb, nt):
             assert nl == want[k][0] and np.array_equal(G, want[k][1]), (it, k)
 
 
+def test_l2_resident_head_changes_nothing_but_time(S, monkeypatch):
+    """A stack larger than L2 is streamed evict_first except the head of every CTA's tile sequence (evict_last: it stays in L2
+    between evaluations, sfh_info.l2_resident_mb).  Cache policies must be invisible in the results: the same stack evaluated
+    with the budget at its default, switched off and oversized gives bit-identical answers (the switch is read per call)."""
+    rng = np.random.default_rng(3)
+    nb, nt = 21000, 1000                                         # 168 MB of Float64 > 126 MB of L2
+    x = 100 * rng.random(nt)
+    ds = S.DeviceStack.synthetic(nb, nt, np.float64, seed=77, scale=1.0, x_true=x)
+    info = ds.info()
+    assert info.fused == 1 and info.variant == 4
+    assert 0 < info.l2_resident_mb <= 0.08 * info.stack_bytes / 2**20 + 1
+    x1 = x * (1 + 0.05 * rng.standard_normal(nt))
+    ref = ds.eval_fg(x1)
+    for mb in ("0", "200", "16"):
+        monkeypatch.setenv("SFH_L2_KEEP_MB", mb)
+        for _ in range(3):
+            got = ds.eval_fg(x1)
+            assert got[0] == ref[0] and np.array_equal(got[1], ref[1]), mb
+    monkeypatch.setenv("SFH_L2_KEEP_MB", "0")
+    assert ds.info().l2_resident_mb == 0
+    small = S.DeviceStack.synthetic(2000, 100, np.float64, seed=1, scale=1.0, x_true=x[:100])   # fits L2: nothing is streamed
+    assert small.info().l2_resident_mb == 0
+
+
 @pytest.mark.parametrize("nb,nt", [(100, 100), (9801, 142), (11250, 2000), (5000, 2400)])
 def test_fg_parity_f32_storage(S, nb, nt):
     """Float32-stored templates, FP64 accumulation, vs exact arithmetic on the same stored values (1e-6)."""
