@@ -926,6 +926,7 @@ int launch_finalize(sfh_ctx *c, const double *composite, double *d_out, int want
     if (p2p_push) {
         fp.peers = c->d_peers; fp.nranks = c->nranks; fp.rank = c->rank; fp.vlen = c->p2p_vlen;
         fp.epoch_ptr = c->d_epoch;
+        fp.epoch_from_fused = logl_from_fused ? 1 : 0;   // (the stream kernel bumps it: enqueue_fg_impl passes the same pointer)
     }
     // enough blocks that every thread has <= 1 bin and every warp <= 1 template (latency-bound kernel)
     const int64_t cap = 4 * std::max(s->sm_count, 1);
@@ -959,6 +960,7 @@ int enqueue_fg_impl(sfh_ctx *c, const double *d_coeffs, double *d_out, int want_
             p.composite = c->d_composite; p.residual = want_G ? c->d_residual : nullptr; p.gpart = c->d_gpart;
             p.lpart = c->d_lpart; p.gstride = c->gstride; p.pdl_early = (pdl_early_mask() & kPdlFused) ? 1 : 0;
             p.keep_stages = l2_keep_stages(s);
+            p.epoch_ptr = c->p2p ? c->d_epoch : nullptr;   // the one-shot exchange follows in the finalize kernel
             CU_TRY(v2_dispatch(s, 2, want_G != 0, &p, c->stream, nullptr));
         } else {
             FusedParams p{};

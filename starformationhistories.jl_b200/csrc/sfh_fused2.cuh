@@ -58,6 +58,9 @@ struct Fused2Params {
     double *gpart;        // [n_clusters][gstride] out
     double *lpart;        // [n_clusters] out: per-cluster sum of the Poisson terms (raw logL partial)
     int64_t gstride;
+    unsigned long long *epoch_ptr;   // nullable: the exchange epoch of the finalize kernel that follows (FinalizeParams::epoch_ptr), bumped
+                                     // here -- by ONE thread, after this grid's griddepcontrol.wait, i.e. after the previous finalize
+                                     // kernel has completed -- so that the sharded finalize kernel needs no last block for it
 };
 
 struct Fused2Smem {
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) sfh_fg_fused2_kernel(const Fuse
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, off);
             if (lane == 0) p.lpart[cl] = lacc;
+            if (lane == 0 && cl == 0 && p.epoch_ptr) *p.epoch_ptr = *p.epoch_ptr + 1ull;
         }
     }
     // no CTA may exit while a peer can still address its shared memory

@@ -102,6 +102,8 @@ struct FinalizeParams {
     double *const *peers;
     int32_t nranks, rank;
     int64_t vlen;
+    int32_t epoch_from_fused;       // 1: the stream kernel of this evaluation has already bumped *epoch_ptr (Fused2Params::epoch_ptr):
+                                    // the epoch is read as it is, and the flat kernel needs neither ticket nor last block
     unsigned long long *epoch_ptr;  // device: evaluations exchanged so far on this context (read and bumped by the last
                                     // block only, so a captured CUDA graph of the evaluation can be replayed)
     HierTail hier;                  // hierarchical chain rule on the (all-reduced) gradient, by the last block
@@ -180,8 +182,9 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t hep = p.pkt_host ? (uint32_t)__ldcg(p.pkt_epoch) : 0u;   // the host's epoch of this evaluation
     uint4 *const pkt = reinterpret_cast<uint4 *>(p.pkt_host);
-    // the epoch of THIS evaluation: the stored one + 1 (bumped by the last block only, after every block has read it)
-    const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
+    // the epoch of THIS evaluation: bumped by the stream kernel before this grid started, or the stored one + 1 (then bumped by
+    // the last block only, after every block has read it)
+    const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + (p.epoch_from_fused ? 0ull : 1ull) : 0ull;
     const uint32_t ep32 = (uint32_t)epoch;
     const int64_t par = (int64_t)(epoch & 1ull);
     if (p.lpart_in) {
@@ -275,6 +278,19 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_kernel(const Fi
         }
     }
     if (p.lpart_in && !p.peers) return;   // single GPU, stream kernel: nothing is left for a last block -- no fence, no ticket
+    if (p.lpart_in && p.epoch_from_fused) {
+        // sharded, stream kernel: block 0 pushed the shard's logL at kernel start and collects the sum here, after its own gradient
+        // entries; the epoch was bumped by the fused kernel -- no fence, no ticket, no last block either
+        if (blockIdx.x == 0 && warp == 0) {
+            const double all = poll_logl(p, lane, par, ep32);
+            if (lane == 0) {
+                p.out[0] = all;
+                if (p.out_host) p.out_host[0] = all;
+                if (pkt) st_packet(pkt, all, hep);
+            }
+        }
+        return;
+    }
     // the last block: folds the per-block logL partials (parallel, fixed order) / finishes the logL exchange, bumps the epoch
     __threadfence();
     __syncthreads();
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
     const HierTail &h = p.hier;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kFinalizeThreads / 32;
     const int j = blockIdx.x;
-    const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + 1ull : 0ull;
+    const unsigned long long epoch = p.peers ? __ldcg(p.epoch_ptr) + (p.epoch_from_fused ? 0ull : 1ull) : 0ull;
     const uint32_t ep32 = (uint32_t)epoch;
     const int64_t par = (int64_t)(epoch & 1ull);
     if (blockIdx.x == 0) {   // the shard's logL exists already (per-cluster partials of the stream kernel): finish / push it now
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) sfh_finalize_hier_kernel(con
         if (h.out_host) h.out_host[0] = v;
         if (p.pkt_host) st_packet(reinterpret_cast<uint4 *>(p.pkt_host), v, (uint32_t)__ldcg(p.pkt_epoch));
         *p.ticket = 0u;
-        if (p.peers) *p.epoch_ptr = epoch;
+        if (p.peers && !p.epoch_from_fused) *p.epoch_ptr = epoch;
     }
     if (p.dbg && tid == 0) p.dbg[2] = clock64();
     if (!p.want_G) return;
