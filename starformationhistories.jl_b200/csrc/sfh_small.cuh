@@ -148,13 +148,15 @@ enum { MH_POWERLAW_MZR = 0, MH_LINEAR_AMR = 1, MH_LOG_AMR = 2 };
 // self-validating packet into slot [parity][rank] of every rank's inbox, polls the nranks packets of the same entry in its own
 // inbox and sums them in rank order (identical order on every rank => bit-identical results everywhere).  2400 warps exchange
 // in parallel: one NVLink round trip for the whole vector, no fence, no flag, no extra kernel, no block that serialises the sum
-// (three earlier versions did, at 16-18 us per step on 2 GPUs; profiles/r2_experiments.md section 3).  The last block only
-// exchanges logL.  Block b handles the same entries on every rank and pushes before it polls, so the ranks' grids cannot
-// wait on each other in a cycle even if a grid were larger than what is co-resident.
+// (three earlier versions did, at 16-18 us per step on 2 GPUs; profiles/r2_experiments.md section 3).  logL travels the same way
+// from block 0.  Block b handles the same entries on every rank and pushes before it polls, so the ranks' grids cannot wait on
+// each other in a cycle even if a grid were larger than what is co-resident.  The two parities of the inbox suffice: a rank can
+// be at most one evaluation ahead of a peer, because finishing evaluation k+1 needs the peer's packets of k+1, which the peer
+// sends only after it has finished reading those of k (stream order).
 
 // raw logL of this shard -> all-reduced over the ranks (same packet protocol, slot 0 of the vector).  With the stream kernel the
-// shard's logL exists when the finalize kernel STARTS (per-cluster Poisson partials), so block 0 pushes it at once and the last
-// block only polls: the logL round trip overlaps the gradient's instead of following it.
+// shard's logL exists when the finalize kernel STARTS (per-cluster Poisson partials), so block 0 pushes it at once and collects
+// the sum after its own gradient entries (the hierarchical kernel: in its last block): the logL round trip overlaps the gradient's.
 __device__ __forceinline__ void push_logl(const FinalizeParams &p, double all, int lane, int64_t par, uint32_t ep32) {
     if (lane < p.nranks) st_packet(reinterpret_cast<uint4 *>(p.peers[lane]) + (par * p.nranks + p.rank) * p.vlen, all, ep32);
 }
