@@ -214,9 +214,12 @@ def run_reference(args, real_stdout):
         trial[name] = (time.perf_counter() - t0) / 3
     best = min(trial, key=trial.get)
     fn, cores = routes[best]
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         fn()
+        per_step.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
     v = args.steps / dt
     other = [k for k in routes if k != best][0]
@@ -225,6 +228,7 @@ def run_reference(args, real_stdout):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: one full-size stack on rank 0, host cores only"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "route": best,
+                             "median_step_value": 1.0 / float(np.median(per_step)),   # shared hosts stall now and then: the mean (value) carries that
                              "blas_one_thread": time_cpu_one_thread(M, data, x),
                              "sample": f"{args.steps} full evaluations of the 60000x2400 F64 stack; port of fitting_base.jl:55-65,84-96,"
                                        f"265-285 (julia not installed): {CPU_ROUTE_TEXT[best]}; the slower restatement "
