@@ -26,6 +26,7 @@
 #include "sfh_small.cuh"
 #include "sfh_ensemble.cuh"
 #include "sfh_templates.cuh"
+#include "sfh_packets.h"
 #include "sfh_file.h"
 #include "sfh_drivers.h"
 #include "sfh_nuts.h"
@@ -1057,31 +1058,14 @@ inline uint32_t next_packet_epoch(sfh_ctx *c, size_t n_in) {
     return c->pkt_epoch;
 }
 int wait_packets(sfh_ctx *c, uint32_t ep, double *first, double *rest, size_t n, size_t rest_at = 1) {
-    const uint64_t *pk = static_cast<const uint64_t *>(c->h_pkt);
-    const size_t total = 1 + (rest ? n : 0);
-    uint64_t spins = 0;
-    bool drained = false;
-    for (size_t j = 0; j < total;) {
-        const size_t at = j == 0 ? 0 : rest_at + j - 1;   // packet 0, then n packets from rest_at on
-        const uint64_t a = __atomic_load_n(pk + 2 * at, __ATOMIC_ACQUIRE), b = __atomic_load_n(pk + 2 * at + 1, __ATOMIC_ACQUIRE);
-        if ((uint32_t)(a >> 32) == ep && (uint32_t)(b >> 32) == ep) {
-            const uint64_t bits = (a & 0xffffffffull) | (b << 32);
-            double v;
-            memcpy(&v, &bits, 8);
-            if (j == 0) { if (first) *first = v; } else rest[j - 1] = v;
-            ++j;
-            continue;
-        }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-        if ((++spins & 8191u) == 0) {
-            if (drained) return fail(SFH_ERR_CUDA, "the evaluation finished without delivering result %zu of %zu", j, total);
-            const cudaError_t q = cudaStreamQuery(c->stream);
-            if (q == cudaSuccess) drained = true;   // everything has run: the packets must be there on the next pass
-            else if (q != cudaErrorNotReady) return fail(SFH_ERR_CUDA, "evaluation failed: %s", cudaGetErrorString(q));
-        }
-    }
+    cudaError_t qerr = cudaSuccess;
+    size_t missing = 0;
+    const int r = sfh_packets::wait(static_cast<const uint64_t *>(c->h_pkt), ep, first, rest, n, rest_at, [&]() -> int {
+        qerr = cudaStreamQuery(c->stream);
+        return qerr == cudaSuccess ? sfh_packets::kDrained : qerr == cudaErrorNotReady ? sfh_packets::kRunning : sfh_packets::kFailed;
+    }, &missing);
+    if (r == sfh_packets::kMissing) return fail(SFH_ERR_CUDA, "the evaluation finished without delivering result packet %zu", missing);
+    if (r == sfh_packets::kStreamError) return fail(SFH_ERR_CUDA, "evaluation failed: %s", cudaGetErrorString(qerr));
     return SFH_OK;
 }
 

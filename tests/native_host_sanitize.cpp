@@ -10,7 +10,11 @@
 //   * lbfgsb_minimize with lb = 0 (fit_templates_lbfgsb, solvers.jl:82-90) on a problem whose solution has active bounds;
 //   * run_chains: 24 chain threads of ragged length parked on one batched log-density (dense mass matrix), a run whose batch
 //     function fails half-way (every thread must be torn down), and a run whose chains are empty;
-//   * the container: Writer -> commit -> Reader round trip, multi-threaded checksums, a flipped payload byte and a truncated file.
+//   * the container: Writer -> commit -> Reader round trip, multi-threaded checksums, a flipped payload byte and a truncated file;
+//   * completion by packets (csrc/sfh_packets.h, what sfh_eval_fg polls instead of synchronising the stream): a thread standing in
+//     for the finalize kernel delivers every evaluation's packets in random order, each packet as two separately written 8-byte
+//     halves in either order, over the stale packets of the previous evaluation -- the waiting side must return exactly this
+//     evaluation's values; an evaluation that ends without delivering, a half-delivered packet and a stream error must fail.
 // Exit status 0 = every check passed and no sanitizer report (reports abort the process).
 #include <cmath>
 #include <cstdio>
@@ -18,9 +22,13 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+#include <thread>
+
 #include "sfh_drivers.h"
 #include "sfh_file.h"
 #include "sfh_nuts.h"
+#include "sfh_packets.h"
 
 static int failures = 0;
 #define CHECK(cond)                                                             \
@@ -351,8 +359,102 @@ static void test_file(const char *dir) {
     unlink(path.c_str());
 }
 
+// ---- completion by packets ----------------------------------------------------------------------------------------------
+static double packet_value(uint32_t epoch, size_t j) { return 1e3 * (double)epoch + (double)j + 0.25; }
+
+static void test_packets() {
+    namespace pk = sfh_packets;
+    const size_t n = 301, rest_at = 8, npk = rest_at + n;
+    std::vector<uint64_t> buf(2 * npk, 0);
+    std::atomic<uint32_t> request{0}, delivered{0};
+    std::atomic<bool> stop{false};
+    // the "device": for every requested epoch, all packets in a random order, halves written separately in a random order
+    std::thread dev([&] {
+        uint64_t st = 12345;
+        auto rnd = [&] { st = st * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(st >> 33); };
+        uint32_t done = 0;
+        std::vector<size_t> order(n + 1);
+        while (!stop.load(std::memory_order_acquire)) {
+            const uint32_t want = request.load(std::memory_order_acquire);
+            if (want == done) { std::this_thread::yield(); continue; }
+            for (size_t i = 0; i <= n; ++i) order[i] = i;
+            for (size_t i = n; i > 0; --i) std::swap(order[i], order[rnd() % (i + 1)]);
+            for (size_t i = 0; i <= n; ++i) {
+                const size_t j = order[i], at = j == 0 ? 0 : rest_at + j - 1;
+                uint64_t p[2];
+                pk::encode(p, packet_value(want, j), want);
+                const int first_half = (int)(rnd() & 1u);
+                __atomic_store_n(&buf[2 * at + first_half], p[first_half], __ATOMIC_RELEASE);
+                if ((rnd() & 7u) == 0) std::this_thread::yield();            // the other half arrives later
+                __atomic_store_n(&buf[2 * at + 1 - first_half], p[1 - first_half], __ATOMIC_RELEASE);
+            }
+            done = want;
+            delivered.store(done, std::memory_order_release);
+        }
+    });
+    std::vector<double> G(n);
+    bool all_ok = true;
+    for (uint32_t ep = 1; ep <= 400; ++ep) {
+        request.store(ep, std::memory_order_release);
+        double f = 0.0;
+        size_t missing = 0;
+        const bool f_only = ep % 3 == 0;   // logL-only call: packet 0 alone is waited for, and the NEXT call starts while this
+                                           // epoch's gradient packets are still landing (they must not be taken for the next epoch's)
+        const int r = pk::wait(buf.data(), ep, &f, f_only ? nullptr : G.data(), n, rest_at,
+                               [&]() -> int { return delivered.load(std::memory_order_acquire) == ep ? pk::kDrained : pk::kRunning; }, &missing, 64);
+        all_ok = all_ok && r == pk::kOk && f == packet_value(ep, 0);
+        for (size_t j = 1; j <= n && all_ok && !f_only; ++j) all_ok = G[j - 1] == packet_value(ep, j);
+        if (!all_ok) { std::printf("packets: epoch %u failed (r = %d, missing %zu)\n", ep, r, missing); break; }
+    }
+    CHECK(all_ok);
+    while (delivered.load(std::memory_order_acquire) != request.load()) std::this_thread::yield();
+    stop.store(true, std::memory_order_release);
+    dev.join();
+    // an evaluation that drains without delivering: must fail with the index of the missing packet, not hang
+    {
+        double f = 0.0;
+        size_t missing = 999;
+        int calls = 0;
+        const int r = pk::wait(buf.data(), 100000u, &f, G.data(), n, rest_at, [&]() -> int { ++calls; return pk::kDrained; }, &missing, 16);
+        CHECK(r == pk::kMissing && missing == 0 && calls == 1);
+    }
+    // a packet of which only ONE half ever arrives is never accepted
+    {
+        uint64_t p[2];
+        pk::encode(p, 7.5, 500000u);
+        __atomic_store_n(&buf[0], p[0], __ATOMIC_RELEASE);
+        pk::encode(p, packet_value(500000u, 1), 500000u);
+        __atomic_store_n(&buf[2 * rest_at], p[0], __ATOMIC_RELEASE);
+        __atomic_store_n(&buf[2 * rest_at + 1], p[1], __ATOMIC_RELEASE);
+        double f = 0.0;
+        size_t missing = 999;
+        const int r = pk::wait(buf.data(), 500000u, &f, G.data(), n, rest_at, [&]() -> int { return pk::kDrained; }, &missing, 16);
+        CHECK(r == pk::kMissing && missing == 0);
+        double v = 0.0;
+        CHECK(!pk::try_read(buf.data(), 500000u, &v) && pk::try_read(buf.data() + 2 * rest_at, 500000u, &v) && v == packet_value(500000u, 1));
+    }
+    // a stream error ends the wait at once
+    {
+        double f = 0.0;
+        size_t missing = 0;
+        const int r = pk::wait(buf.data(), 600000u, &f, nullptr, 0, rest_at, [&]() -> int { return pk::kFailed; }, &missing, 4);
+        CHECK(r == pk::kStreamError);
+    }
+    // encode / try_read round trip over awkward values
+    {
+        const double vals[] = {0.0, -0.0, 1.0, -1.5e300, 4.9e-324, 1.0 / 0.0, -1.0 / 0.0};
+        for (double x : vals) {
+            uint64_t p[2];
+            double v = 1.0;
+            pk::encode(p, x, 0xfffffffeu);
+            CHECK(pk::try_read(p, 0xfffffffeu, &v) && std::memcmp(&v, &x, 8) == 0 && !pk::try_read(p, 0xfffffffdu, &v));
+        }
+    }
+}
+
 int main(int argc, char **argv) {
     const char *dir = argc > 1 ? argv[1] : "/tmp";
+    test_packets();
     test_bfgs(300, 24, 1e-8);
     test_bfgs_threaded_hessian();
     test_lbfgsb();

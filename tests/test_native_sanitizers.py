@@ -1,5 +1,6 @@
 """The library's host-only C++ -- native BFGS / L-BFGS-B loops (csrc/sfh_drivers.h), the multi-threaded NUTS around one batched
-evaluation (csrc/sfh_nuts.h) and the on-disk container (csrc/sfh_file.h) -- built by itself and run under AddressSanitizer +
+evaluation (csrc/sfh_nuts.h), the on-disk container (csrc/sfh_file.h) and the host side of the packet completion protocol
+(csrc/sfh_packets.h: a thread stands in for the finalize kernel and delivers torn, reordered packets over stale ones) -- built by itself and run under AddressSanitizer +
 UndefinedBehaviorSanitizer and under ThreadSanitizer (tests/native_host_sanitize.cpp; a CPU Poisson objective stands in for the
 device evaluations).  The reference has no race detection of its own; its chains run on Julia threads
 (hmc_sample.jl:123-141, generic_fitting.jl:617-626), here they are host threads parked on a condition variable, which is what
